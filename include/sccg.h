@@ -1,0 +1,107 @@
+/* =================================================================================================
+ * sccg.h -- C ABI of the B200-native SCCG hot path (libsccg_b200.so).
+ *
+ * The reference (Jan-Celin/SCCG-genome-compression) has no plugin / FFI interface: its hot path is a
+ * set of free functions inside two executables.  Each entry point below replaces one of those
+ * functions; the reference line it stands in for is cited.  Plain C, plain pointers and sizes.
+ *
+ * Conventions
+ *   - every function returns SCCG_OK (0) or a negative SCCG_E_* code; sccg_last_error() gives text
+ *     for the calling thread's most recent failure.  No exceptions cross this boundary.
+ *   - host-pointer entry points: caller-owned input buffers, read-only, not retained after return;
+ *     outputs are allocated by the library and released with sccg_free().
+ *   - *_device entry points take DEVICE pointers (inputs already resident in HBM) and leave the
+ *     result in device memory owned by the context (valid until the next call on that context).
+ *   - one opaque context per GPU; calls on one context must be serialised by the caller, distinct
+ *     contexts may be driven from distinct host threads.
+ *   - there is NO CPU fallback: without a usable CUDA device sccg_create() fails.
+ * ================================================================================================= */
+#ifndef SCCG_H
+#define SCCG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCCG_OK 0
+#define SCCG_E_CUDA (-1)        /* CUDA runtime / launch failure, or no device                            */
+#define SCCG_E_ARG (-2)         /* invalid argument (NULL, negative size, size >= 2^31, unsupported k)    */
+#define SCCG_E_FORMAT (-3)      /* malformed record stream: the reference would throw (stoi) -> exit 1    */
+#define SCCG_E_BOUNDS (-4)      /* abs+len exceeds the reference: decompression.cpp:223-229 -> exit(1)    */
+#define SCCG_E_NOMEM (-5)
+
+typedef struct sccg_ctx sccg_ctx;
+
+/* vector<Position> of match_sequences (compression.cpp:20-24, :36) as struct-of-arrays.
+ * Record i is a match iff lit_off[i+1] == lit_off[i]; then (p[i], l[i]) = (start_reference, length).
+ * Otherwise it is a literal run lits[lit_off[i] .. lit_off[i+1]) and p[i] = -1, l[i] = 0. */
+typedef struct {
+    int64_t  n;
+    int32_t* p;
+    int32_t* l;
+    int64_t* lit_off;   /* n + 1 entries */
+    char*    lits;
+} sccg_records;
+
+/* phases whose device time the last call measured with CUDA events on the context's stream */
+typedef struct {
+    float h2d_ms;         /* host -> device copies (0 for *_device entry points)        */
+    float kernels_ms;     /* every kernel of the call, first launch to last completion  */
+    float d2h_ms;         /* device -> host copy of the result                          */
+    float match_ms;       /* compress: segment-match (local) or index+parse (global)    */
+    float serialize_ms;   /* compress: run lists + record text ; decompress: tokenizer  */
+    float gather_ms;      /* decompress: reference-copy / literal gather + case/N/wrap  */
+    int32_t launches;     /* kernels launched by the call                               */
+    int32_t mode;         /* compress: 0 local, 1 global                                */
+} sccg_profile;
+
+sccg_ctx*   sccg_create(int device);                 /* NULL on failure (see sccg_last_error)      */
+void        sccg_destroy(sccg_ctx* ctx);
+const char* sccg_last_error(void);
+void        sccg_free(void* p);                      /* releases any buffer returned by the library */
+void        sccg_records_free(sccg_records* r);
+int         sccg_get_profile(sccg_ctx* ctx, sccg_profile* out);
+const char* sccg_version(void);
+
+/* compress_genome minus file I/O and the external 7z stage (compression.cpp:320-579).
+ * ref / tgt: raw symbols as read_genomes_from_files leaves them (:181-220): case preserved, no
+ * newlines.  header: the target's first '>' line, may be empty.  out: the final, delta-encoded
+ * compressed_genome.txt image.  mode_out: 0 = local segment matching, 1 = global fallback. */
+int sccg_compress(sccg_ctx* ctx, const char* ref, int64_t ref_len, const char* tgt, int64_t tgt_len,
+                  const char* header, int64_t header_len, char** out, int64_t* out_len, int* mode_out);
+
+/* same, inputs already in device memory; the encoded image stays on the device:
+ * *d_out is owned by the context and valid until its next call. */
+int sccg_compress_device(sccg_ctx* ctx, const void* d_ref, int64_t ref_len, const void* d_tgt, int64_t tgt_len,
+                         const char* header, int64_t header_len, void** d_out, int64_t* out_len, int* mode_out);
+
+/* match_sequences(Sr, St, k, m, global, offset)  (compression.cpp:36-179).
+ * global == 0: one segment pair, nr and nt <= 1000 (the reference's own call sites :401, :428).
+ * global != 0: whole sequences, any length < 2^31 (:561). */
+int sccg_match_sequences(sccg_ctx* ctx, const char* Sr, int64_t nr, const char* St, int64_t nt,
+                         int k, int m, int global, int offset, sccg_records* out);
+
+/* reconstruct_genome(reference, encoded, n_indices, lowercase_indices)  (decompression.cpp:117-279).
+ * ref must already be prepared as decompress_genome does (:105-110).  out: the 50-column wrapped
+ * sequence text ending in '\n' (what main writes after "<header>\n", :322). */
+int sccg_reconstruct(sccg_ctx* ctx, const char* ref, int64_t ref_len, const char* encoded, int64_t enc_len,
+                     const char* n_idx, int64_t n_len, const char* low_idx, int64_t low_len,
+                     char** out, int64_t* out_len);
+
+/* same, reference and the three text lines already in device memory; result stays on the device */
+int sccg_reconstruct_device(sccg_ctx* ctx, const void* d_ref, int64_t ref_len, const void* d_encoded, int64_t enc_len,
+                            const void* d_n_idx, int64_t n_len, const void* d_low_idx, int64_t low_len,
+                            void** d_out, int64_t* out_len);
+
+/* decompress_genome's in-memory part + reconstruct_genome + main's header line
+ * (decompression.cpp:66-110, :117-279, :322): intermediate file image + raw reference symbols in,
+ * reconstructed_genome.fa image out. */
+int sccg_decompress(sccg_ctx* ctx, const char* ref_raw, int64_t ref_len, const char* intermediate, int64_t inter_len,
+                    char** out, int64_t* out_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCCG_H */

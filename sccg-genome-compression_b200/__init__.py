@@ -1,0 +1,172 @@
+"""sccg-genome-compression_b200 -- host-side Python mirror of the reference's hot-path functions
+(match_sequences / compress_genome / reconstruct_genome of Jan-Celin/SCCG-genome-compression) over
+the C ABI of libsccg_b200.so (include/sccg.h).  The library is hand-written CUDA for sm_100a; there
+is no CPU fallback: importing works anywhere, but creating a context without the built library or
+without a CUDA device raises.
+
+The directory name contains a hyphen, so import it through the shim module at the repo root:
+
+    import sccg_b200
+    ctx = sccg_b200.Context(device=0)
+    text, mode = ctx.compress(ref_symbols, tgt_symbols, header)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+DEFAULT_LIB = PKG_DIR / "libsccg_b200.so"
+
+SCCG_OK, SCCG_E_CUDA, SCCG_E_ARG, SCCG_E_FORMAT, SCCG_E_BOUNDS, SCCG_E_NOMEM = 0, -1, -2, -3, -4, -5
+
+
+class SccgError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"sccg error {code}: {message}")
+        self.code = code
+
+
+class _Records(C.Structure):
+    _fields_ = [("n", C.c_int64), ("p", C.POINTER(C.c_int32)), ("l", C.POINTER(C.c_int32)),
+                ("lit_off", C.POINTER(C.c_int64)), ("lits", C.c_void_p)]
+
+
+class Profile(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("kernels_ms", C.c_float), ("d2h_ms", C.c_float), ("match_ms", C.c_float),
+                ("serialize_ms", C.c_float), ("gather_ms", C.c_float), ("launches", C.c_int32), ("mode", C.c_int32)]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+@dataclass
+class Record:
+    """One element of match_sequences' vector<Position> (compression.cpp:20-24)."""
+    p: int
+    l: int
+    lit: bytes
+
+    def __repr__(self):
+        return f"({self.p},{self.l})" if not self.lit else f"lit[{len(self.lit)}]{self.lit[:24]!r}"
+
+
+_libs: dict[str, C.CDLL] = {}
+
+
+def load_library(path: str | os.PathLike | None = None) -> C.CDLL:
+    p = Path(path) if path else DEFAULT_LIB
+    key = str(p)
+    if key in _libs:
+        return _libs[key]
+    if not p.exists():
+        raise OSError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(key)
+    vp, i64, cp = C.c_void_p, C.c_int64, C.c_char_p
+    lib.sccg_create.restype = vp
+    lib.sccg_create.argtypes = [C.c_int]
+    lib.sccg_destroy.argtypes = [vp]
+    lib.sccg_last_error.restype = cp
+    lib.sccg_version.restype = cp
+    lib.sccg_free.argtypes = [vp]
+    lib.sccg_records_free.argtypes = [C.POINTER(_Records)]
+    lib.sccg_get_profile.argtypes = [vp, C.POINTER(Profile)]
+    lib.sccg_compress.argtypes = [vp, cp, i64, cp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_int)]
+    lib.sccg_compress_device.argtypes = [vp, vp, i64, vp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_int)]
+    lib.sccg_match_sequences.argtypes = [vp, cp, i64, cp, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_Records)]
+    lib.sccg_reconstruct.argtypes = [vp, cp, i64, cp, i64, cp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64)]
+    lib.sccg_reconstruct_device.argtypes = [vp, vp, i64, vp, i64, vp, i64, vp, i64, C.POINTER(vp), C.POINTER(i64)]
+    lib.sccg_decompress.argtypes = [vp, cp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64)]
+    _libs[key] = lib
+    return lib
+
+
+class Context:
+    """One sccg_ctx (one GPU).  Method names follow the reference's free functions."""
+
+    def __init__(self, device: int = 0, lib_path: str | os.PathLike | None = None):
+        self.lib = load_library(lib_path)
+        self.handle = self.lib.sccg_create(device)
+        if not self.handle:
+            raise SccgError(SCCG_E_CUDA, self.lib.sccg_last_error().decode())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.sccg_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != SCCG_OK:
+            raise SccgError(rc, self.lib.sccg_last_error().decode())
+
+    def _take(self, ptr: C.c_void_p, n: int) -> bytes:
+        data = C.string_at(ptr, n) if (ptr.value and n) else b""
+        if ptr.value:
+            self.lib.sccg_free(ptr)
+        return data
+
+    def version(self) -> str:
+        return self.lib.sccg_version().decode()
+
+    def profile(self) -> dict:
+        p = Profile()
+        self._check(self.lib.sccg_get_profile(self.handle, C.byref(p)))
+        return p.as_dict()
+
+    # compress_genome minus file I/O and 7z (compression.cpp:320-579)
+    def compress(self, ref: bytes, tgt: bytes, header: bytes = b"") -> tuple[bytes, int]:
+        out = C.c_void_p(); n = C.c_int64(); mode = C.c_int()
+        self._check(self.lib.sccg_compress(self.handle, ref, len(ref), tgt, len(tgt), header, len(header),
+                                           C.byref(out), C.byref(n), C.byref(mode)))
+        return self._take(out, n.value), mode.value
+
+    def compress_device(self, d_ref: int, ref_len: int, d_tgt: int, tgt_len: int, header: bytes = b"") -> tuple[int, int, int]:
+        """device pointers in -> (device pointer of the encoded image, its length, mode)"""
+        out = C.c_void_p(); n = C.c_int64(); mode = C.c_int()
+        self._check(self.lib.sccg_compress_device(self.handle, d_ref, ref_len, d_tgt, tgt_len, header, len(header),
+                                                  C.byref(out), C.byref(n), C.byref(mode)))
+        return out.value or 0, n.value, mode.value
+
+    # match_sequences (compression.cpp:36-179)
+    def match_sequences(self, Sr: bytes, St: bytes, k: int, m: int, is_global: bool, offset: int = 0) -> list[Record]:
+        recs = _Records()
+        self._check(self.lib.sccg_match_sequences(self.handle, Sr, len(Sr), St, len(St), k, m, int(is_global), offset, C.byref(recs)))
+        total = recs.lit_off[recs.n] if recs.n else 0
+        lits = C.string_at(recs.lits, total) if total else b""
+        out = [Record(recs.p[i], recs.l[i], lits[recs.lit_off[i]:recs.lit_off[i + 1]]) for i in range(recs.n)]
+        self.lib.sccg_records_free(C.byref(recs))
+        return out
+
+    # reconstruct_genome (decompression.cpp:117-279)
+    def reconstruct(self, ref: bytes, encoded: bytes, n_idx: bytes, low_idx: bytes) -> bytes:
+        out = C.c_void_p(); n = C.c_int64()
+        self._check(self.lib.sccg_reconstruct(self.handle, ref, len(ref), encoded, len(encoded), n_idx, len(n_idx),
+                                              low_idx, len(low_idx), C.byref(out), C.byref(n)))
+        return self._take(out, n.value)
+
+    def reconstruct_device(self, d_ref: int, ref_len: int, d_enc: int, enc_len: int, d_n: int, n_len: int, d_low: int, low_len: int) -> tuple[int, int]:
+        out = C.c_void_p(); n = C.c_int64()
+        self._check(self.lib.sccg_reconstruct_device(self.handle, d_ref, ref_len, d_enc, enc_len, d_n, n_len, d_low, low_len,
+                                                     C.byref(out), C.byref(n)))
+        return out.value or 0, n.value
+
+    # decompress_genome (in-memory part) + reconstruct_genome + header line (decompression.cpp:66-110, :117-279, :322)
+    def decompress(self, ref_raw: bytes, intermediate: bytes) -> bytes:
+        out = C.c_void_p(); n = C.c_int64()
+        self._check(self.lib.sccg_decompress(self.handle, ref_raw, len(ref_raw), intermediate, len(intermediate), C.byref(out), C.byref(n)))
+        return self._take(out, n.value)

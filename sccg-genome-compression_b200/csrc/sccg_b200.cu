@@ -1,0 +1,250 @@
+// libsccg_b200.so -- C ABI (include/sccg.h) over the sm_100a kernels.  No CPU fallback: without a
+// CUDA device sccg_create() fails and every other entry point needs a context.
+#include "sccg_compress.cuh"
+#include "sccg_global.cuh"
+#include "sccg_decode.cuh"
+
+#include <new>
+
+using namespace sccg;
+
+namespace sccg {
+
+static int check_sizes(i64 a, i64 b) {
+    if (a < 0 || b < 0 || a >= 0x7fffffffLL || b >= 0x7fffffffLL) return set_error(SCCG_E_ARG, "sequence length must be in [0, 2^31-1)");
+    return SCCG_OK;
+}
+
+// copies a host buffer into a grow-only device slot (pageable source: cudaMemcpyAsync stages it)
+static int upload(sccg_ctx* c, int slot, const void* h, i64 n, u8** d) {
+    SCCG_TRY(buf(c, slot, (size_t)n + 64, d));
+    if (n > 0) SCCG_CK(cudaMemcpyAsync(*d, h, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    return SCCG_OK;
+}
+
+static int download(sccg_ctx* c, const u8* d, i64 n, char** out) {
+    char* h = (char*)malloc((size_t)n + 1);
+    if (!h) return set_error(SCCG_E_NOMEM, "malloc of the result failed");
+    if (n > 0) {
+        cudaError_t e = cudaMemcpyAsync(h, d, (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { free(h); return set_error(SCCG_E_CUDA, "result download failed: %s", cudaGetErrorString(e)); }
+    }
+    h[n] = 0;
+    *out = h;
+    return SCCG_OK;
+}
+
+static void prof_reset(sccg_ctx* c) { memset(&c->prof, 0, sizeof c->prof); }
+
+}  // namespace sccg
+
+extern "C" {
+
+const char* sccg_version(void) {
+#ifdef SCCG_EMU
+    return "sccg-b200 0.1 (SIMT emulator build: kernel logic tests only)";
+#else
+    return "sccg-b200 0.1 (sm_100a)";
+#endif
+}
+
+const char* sccg_last_error(void) { return g_last_error.c_str(); }
+
+sccg_ctx* sccg_create(int device) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        set_error(SCCG_E_CUDA, "no CUDA device available (%s): this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { set_error(SCCG_E_ARG, "device index out of range"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error(SCCG_E_CUDA, "cudaSetDevice failed"); return nullptr; }
+    sccg_ctx* c = new (std::nothrow) sccg_ctx();
+    if (!c) { set_error(SCCG_E_NOMEM, "out of host memory"); return nullptr; }
+    memset(c, 0, sizeof *c);
+    c->device = device;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (c->sm_count <= 0) c->sm_count = 148;
+    c->h_pinned_cap = 1 << 20;
+    bool ok = cudaStreamCreate(&c->stream) == cudaSuccess && cudaMallocHost(&c->h_pinned, c->h_pinned_cap) == cudaSuccess;
+    for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+    if (!ok) { set_error(SCCG_E_CUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError())); sccg_destroy(c); return nullptr; }
+    return c;
+}
+
+void sccg_destroy(sccg_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < B_NSLOTS; ++i) if (c->bufs[i].p) cudaFree(c->bufs[i].p);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void sccg_free(void* p) { free(p); }
+
+void sccg_records_free(sccg_records* r) {
+    if (!r) return;
+    free(r->p); free(r->l); free(r->lit_off); free(r->lits);
+    memset(r, 0, sizeof *r);
+}
+
+int sccg_get_profile(sccg_ctx* c, sccg_profile* out) {
+    if (!c || !out) return set_error(SCCG_E_ARG, "null argument");
+    *out = c->prof;
+    return SCCG_OK;
+}
+
+int sccg_compress_device(sccg_ctx* c, const void* d_ref, int64_t ref_len, const void* d_tgt, int64_t tgt_len,
+                         const char* header, int64_t header_len, void** d_out, int64_t* out_len, int* mode_out) {
+    if (!c || !d_out || !out_len || (header_len > 0 && !header)) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_TRY(check_sizes(ref_len, tgt_len));
+    if (((uintptr_t)d_ref | (uintptr_t)d_tgt) & 15) return set_error(SCCG_E_ARG, "device inputs must be 16-byte aligned");
+    SCCG_CK(cudaSetDevice(c->device));
+    prof_reset(c);
+    CompressResult res;
+    SCCG_TRY(compress_device(c, (const u8*)d_ref, ref_len, (const u8*)d_tgt, tgt_len, header, header_len < 0 ? 0 : header_len, &res));
+    *d_out = res.d_out; *out_len = res.out_len;
+    if (mode_out) *mode_out = res.mode;
+    return SCCG_OK;
+}
+
+int sccg_compress(sccg_ctx* c, const char* ref, int64_t ref_len, const char* tgt, int64_t tgt_len,
+                  const char* header, int64_t header_len, char** out, int64_t* out_len, int* mode_out) {
+    if (!c || !out || !out_len || (ref_len > 0 && !ref) || (tgt_len > 0 && !tgt) || (header_len > 0 && !header)) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_TRY(check_sizes(ref_len, tgt_len));
+    SCCG_CK(cudaSetDevice(c->device));
+    prof_reset(c);
+    u8 *d_ref = nullptr, *d_tgt = nullptr;
+    SCCG_CK(cudaEventRecord(c->ev[4], c->stream));
+    SCCG_TRY(upload(c, B_REF, ref, ref_len, &d_ref));
+    SCCG_TRY(upload(c, B_TGT, tgt, tgt_len, &d_tgt));
+    SCCG_CK(cudaEventRecord(c->ev[5], c->stream));
+    CompressResult res;
+    SCCG_TRY(compress_device(c, d_ref, ref_len, d_tgt, tgt_len, header, header_len < 0 ? 0 : header_len, &res));
+    SCCG_CK(cudaEventRecord(c->ev[6], c->stream));
+    SCCG_TRY(download(c, res.d_out, res.out_len, out));
+    SCCG_CK(cudaEventRecord(c->ev[7], c->stream));
+    SCCG_CK(cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->prof.h2d_ms, c->ev[4], c->ev[5]);
+    cudaEventElapsedTime(&c->prof.d2h_ms, c->ev[6], c->ev[7]);
+    *out_len = res.out_len;
+    if (mode_out) *mode_out = res.mode;
+    return SCCG_OK;
+}
+
+int sccg_match_sequences(sccg_ctx* c, const char* Sr, int64_t nr, const char* St, int64_t nt,
+                         int k, int m, int global, int offset, sccg_records* out) {
+    if (!c || !out || (nr > 0 && !Sr) || (nt > 0 && !St)) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_TRY(check_sizes(nr, nt));
+    SCCG_CK(cudaSetDevice(c->device));
+    prof_reset(c);
+    memset(out, 0, sizeof *out);
+    u8 *d_ref = nullptr, *d_tgt = nullptr;
+    SCCG_TRY(upload(c, B_REF, Sr, nr, &d_ref));
+    SCCG_TRY(upload(c, B_TGT, St, nt, &d_tgt));
+    if (global) return match_sequences_global(c, d_ref, nr, d_tgt, nt, St, k, m, offset, out);
+
+    // local: one segment pair through the segment kernel, single pass with the caller's k
+    if (nr > SEG || nt > SEG) return set_error(SCCG_E_ARG, "local match_sequences takes one segment pair (<= 1000 symbols each)");
+    if (k < K2 || k > 32) return set_error(SCCG_E_ARG, "local match_sequences supports 10 <= k <= 32");
+    u32 *seginfo = nullptr, *matches = nullptr;
+    SCCG_TRY(buf(c, B_SEGINFO, 2, &seginfo));
+    SCCG_TRY(buf(c, B_MATCH, LM_SLOT + 1, &matches));
+    int nmatch = 0;
+    u32 h_matches[LM_SLOT];
+    if (nt > 0) {
+        // the kernel upper-cases on load (the reference driver does so before calling, :369-370); callers pass
+        // upper-cased symbols, for which this is the identity
+        const size_t smem = sizeof(LmWarpSmem) * LM_WARPS;
+        SCCG_SET_MAX_SMEM(seg_match_k, smem);
+        LAUNCH(c, seg_match_k, dim3(1), dim3(LM_WARPS * 32), smem, (const u8*)d_ref, (i64)(nr > 0 ? nr : 0), (const u8*)d_tgt, nt, 1, k, 0, seginfo, matches);
+        u32 info = 0;
+        SCCG_CK(cudaMemcpyAsync(&info, seginfo, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+        SCCG_CK(cudaMemcpyAsync(h_matches, matches, sizeof(u32) * LM_SLOT, cudaMemcpyDeviceToHost, c->stream));
+        SCCG_CK(cudaStreamSynchronize(c->stream));
+        nmatch = (int)SEGINFO_NMATCH(info);
+    }
+    // vector<Position>: alternating literal / match records (compression.cpp:97-108, :152-156, :164-167)
+    int64_t cap = 2 * (int64_t)nmatch + 2;
+    out->p = (int32_t*)malloc(sizeof(int32_t) * (size_t)cap);
+    out->l = (int32_t*)malloc(sizeof(int32_t) * (size_t)cap);
+    out->lit_off = (int64_t*)malloc(sizeof(int64_t) * (size_t)(cap + 1));
+    out->lits = (char*)malloc((size_t)nt + 1);
+    if (!out->p || !out->l || !out->lit_off || !out->lits) { sccg_records_free(out); return set_error(SCCG_E_NOMEM, "out of host memory"); }
+    int64_t n = 0, lit = 0;
+    int pos = 0;
+    for (int i = 0; i <= nmatch; ++i) {
+        int tpos = i < nmatch ? (int)(h_matches[i] & 0x3ffu) : (int)nt;
+        if (tpos > pos) {
+            out->p[n] = -1; out->l[n] = 0; out->lit_off[n] = lit;
+            memcpy(out->lits + lit, St + pos, (size_t)(tpos - pos));
+            lit += tpos - pos; ++n;
+        }
+        if (i < nmatch) {
+            out->p[n] = (int)((h_matches[i] >> 10) & 0x3ffu) + offset;
+            out->l[n] = (int)(h_matches[i] >> 20);
+            out->lit_off[n] = lit; ++n;
+            pos = tpos + out->l[n - 1];
+        }
+    }
+    out->lit_off[n] = lit;
+    out->n = n;
+    (void)m;
+    return SCCG_OK;
+}
+
+int sccg_reconstruct_device(sccg_ctx* c, const void* d_ref, int64_t ref_len, const void* d_encoded, int64_t enc_len,
+                            const void* d_n_idx, int64_t n_len, const void* d_low_idx, int64_t low_len,
+                            void** d_out, int64_t* out_len) {
+    if (!c || !d_out || !out_len) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_TRY(check_sizes(ref_len, enc_len));
+    SCCG_TRY(check_sizes(n_len, low_len));
+    if (((uintptr_t)d_ref | (uintptr_t)d_encoded | (uintptr_t)d_n_idx | (uintptr_t)d_low_idx) & 15) return set_error(SCCG_E_ARG, "device inputs must be 16-byte aligned");
+    SCCG_CK(cudaSetDevice(c->device));
+    prof_reset(c);
+    u8* out = nullptr; i64 n = 0;
+    SCCG_TRY(reconstruct_device(c, (const u8*)d_ref, ref_len, (const u8*)d_encoded, enc_len, (const u8*)d_n_idx, n_len,
+                                (const u8*)d_low_idx, low_len, 0, &out, &n));
+    *d_out = out; *out_len = n;
+    return SCCG_OK;
+}
+
+int sccg_reconstruct(sccg_ctx* c, const char* ref, int64_t ref_len, const char* encoded, int64_t enc_len,
+                     const char* n_idx, int64_t n_len, const char* low_idx, int64_t low_len, char** out, int64_t* out_len) {
+    if (!c || !out || !out_len || (ref_len > 0 && !ref) || (enc_len > 0 && !encoded) || (n_len > 0 && !n_idx) || (low_len > 0 && !low_idx))
+        return set_error(SCCG_E_ARG, "null argument");
+    SCCG_TRY(check_sizes(ref_len, enc_len));
+    SCCG_TRY(check_sizes(n_len, low_len));
+    SCCG_CK(cudaSetDevice(c->device));
+    prof_reset(c);
+    u8 *d_ref = nullptr, *d_enc = nullptr, *d_n = nullptr, *d_low = nullptr;
+    SCCG_CK(cudaEventRecord(c->ev[4], c->stream));
+    SCCG_TRY(upload(c, B_REF, ref, ref_len, &d_ref));
+    SCCG_TRY(upload(c, B_ENC, encoded, enc_len, &d_enc));
+    SCCG_TRY(upload(c, B_NIDX, n_idx, n_len, &d_n));
+    SCCG_TRY(upload(c, B_LOW, low_idx, low_len, &d_low));
+    SCCG_CK(cudaEventRecord(c->ev[5], c->stream));
+    u8* d_res = nullptr; i64 n = 0;
+    SCCG_TRY(reconstruct_device(c, d_ref, ref_len, d_enc, enc_len, d_n, n_len, d_low, low_len, 0, &d_res, &n));
+    SCCG_CK(cudaEventRecord(c->ev[6], c->stream));
+    SCCG_TRY(download(c, d_res, n, out));
+    SCCG_CK(cudaEventRecord(c->ev[7], c->stream));
+    SCCG_CK(cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->prof.h2d_ms, c->ev[4], c->ev[5]);
+    cudaEventElapsedTime(&c->prof.d2h_ms, c->ev[6], c->ev[7]);
+    *out_len = n;
+    return SCCG_OK;
+}
+
+int sccg_decompress(sccg_ctx* c, const char* ref_raw, int64_t ref_len, const char* inter, int64_t inter_len, char** out, int64_t* out_len) {
+    if (!c || !out || !out_len || (ref_len > 0 && !ref_raw) || (inter_len > 0 && !inter)) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_TRY(check_sizes(ref_len, inter_len));
+    SCCG_CK(cudaSetDevice(c->device));
+    prof_reset(c);
+    return decompress_host(c, ref_raw, ref_len, inter, inter_len, out, out_len);
+}
+
+}  // extern "C"

@@ -1,0 +1,22 @@
+// Build switch: nvcc (product, sm_100a) vs. the CPU SIMT emulator used only by the unit tests.
+#pragma once
+
+#ifdef SCCG_EMU
+// tests/emu/build_emu.sh: g++ -DSCCG_EMU -- kernel LOGIC tests in the GPU-less build container.
+#include "simt_emu.h"
+#define SCCG_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
+#define SCCG_DYN_SMEM(name) unsigned char* name = emu::dyn_smem()
+#define SCCG_SET_MAX_SMEM(kernel, bytes) ((void)0)
+#else
+#include <cuda_runtime.h>
+#define SCCG_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define SCCG_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define SCCG_SET_MAX_SMEM(kernel, bytes) \
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+#endif
+
+#include <stdint.h>
+
+#define SCCG_FULL_MASK 0xffffffffu

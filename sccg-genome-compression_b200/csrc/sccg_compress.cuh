@@ -1,0 +1,134 @@
+// compress_genome on the device (compression.cpp:320-579 minus file I/O and 7z): orchestration of
+// the run-list, segment-match, driver and writer kernels.  Global fallback lives in sccg_global.cuh.
+#pragma once
+#include "sccg_rle.cuh"
+#include "sccg_local.cuh"
+
+namespace sccg {
+
+// device scalars (u32 each)
+enum Scalar {
+    S_LOW_K = 0, S_LOW_KE, S_LOW_TEXT, S_ABORT, S_BODY_MAIN, S_BODY_BASE, S_N_K, S_N_KE, S_N_TEXT,
+    S_G0, S_G1, S_G2, S_G3, S_G4, S_G5, S_G6, S_G7, S_COUNT = 32
+};
+
+// writes the separator after the lowercase line and publishes where the body starts
+//   local : "<low>\n,\n<body>"   (compression.cpp:368)      global: "<low>\n<nruns>\n<body>" (:522, :555)
+__global__ void put_separators_k(u8* out, u32 hdr_bytes, u32* scalars, int global_mode) {
+    u32 low = scalars[S_LOW_TEXT];
+    u8* o = out + hdr_bytes + low;
+    if (!global_mode) {
+        o[0] = '\n'; o[1] = ','; o[2] = '\n';
+        scalars[S_BODY_BASE] = hdr_bytes + low + 3u;
+    } else {
+        u32 nt = scalars[S_N_TEXT];
+        o[0] = '\n';                       // the N-run text is written at o + 1 by runs_write_k
+        o[1 + nt] = '\n';
+        scalars[S_BODY_BASE] = hdr_bytes + low + 1u + nt + 1u;
+    }
+}
+
+struct CompressResult {
+    u8* d_out;
+    i64 out_len;
+    int mode;
+};
+
+static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt, i64 nt, const char* header, i64 nh,
+                                  u32 low_k, const u32* cnt_s, const u32* cnt_e, CompressResult* res);
+
+static int read_scalars(sccg_ctx* c, const u32* d_scalars, u32* host, int count) {
+    SCCG_CK(cudaMemcpyAsync(c->h_pinned, d_scalars, sizeof(u32) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
+    SCCG_CK(cudaStreamSynchronize(c->stream));
+    memcpy(host, c->h_pinned, sizeof(u32) * (size_t)count);
+    return SCCG_OK;
+}
+
+static int write_header(sccg_ctx* c, u8* d_out, const char* header, i64 nh) {
+    if (nh <= 0) return SCCG_OK;                                              // compression.cpp:337-339
+    if ((size_t)nh + 1 > c->h_pinned_cap) return set_error(SCCG_E_ARG, "header line too long");
+    memcpy(c->h_pinned, header, (size_t)nh);
+    ((char*)c->h_pinned)[nh] = '\n';
+    SCCG_CK(cudaMemcpyAsync(d_out, c->h_pinned, (size_t)nh + 1, cudaMemcpyHostToDevice, c->stream));
+    SCCG_CK(cudaStreamSynchronize(c->stream));                                // staging area is reused
+    return SCCG_OK;
+}
+
+static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt, i64 nt, const char* header, i64 nh, CompressResult* res) {
+    u32* sc = nullptr;
+    SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
+    SCCG_CK(cudaMemsetAsync(sc, 0, sizeof(u32) * S_COUNT, c->stream));
+    SCCG_CK(cudaEventRecord(c->ev[0], c->stream));
+
+    // ---- lowercase runs of the raw target: count (:341-367)
+    u32 *cnt_s = nullptr, *cnt_e = nullptr;
+    SCCG_TRY(rle_count<0>(c, d_tgt, nt, B_RUN_CNT, &cnt_s, &cnt_e, sc + S_LOW_K, sc + S_LOW_KE));
+
+    // ---- local segment matching (:381-474)
+    const i64 n_rseg = (nr + SEG - 1) / SEG, n_tseg = (nt + SEG - 1) / SEG;
+    const int n_iter = (int)(n_rseg < n_tseg ? n_rseg : n_tseg);             // :392
+    u32 *seginfo = nullptr, *matches = nullptr, *seg_bytes = nullptr;
+    int* seg_prev = nullptr;
+    SCCG_TRY(buf(c, B_SEGINFO, (size_t)n_iter + 1, &seginfo));
+    SCCG_TRY(buf(c, B_MATCH, (size_t)n_iter * LM_SLOT + 1, &matches));
+    SCCG_TRY(buf(c, B_SEGBYTES, (size_t)n_iter + 1, &seg_bytes));
+    SCCG_TRY(buf(c, B_SEGPREV, (size_t)n_iter + 1, &seg_prev));
+    SCCG_CK(cudaEventRecord(c->ev[1], c->stream));
+    if (n_iter > 0) {
+        const size_t smem = sizeof(LmWarpSmem) * LM_WARPS;
+        SCCG_SET_MAX_SMEM(seg_match_k, smem);
+        unsigned want = div_up(n_iter, LM_WARPS);
+        unsigned cap = (unsigned)c->sm_count * 3u;
+        unsigned grid = want < cap ? want : cap;
+        LAUNCH(c, seg_match_k, dim3(grid), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, n_iter, K1, K2, seginfo, matches);
+        LAUNCH(c, seg_bytes_k, dim3(div_up(n_iter, 256)), dim3(256), 0, (const u32*)seginfo, (const u32*)matches, n_iter, seg_bytes, seg_prev, sc + S_ABORT);
+    }
+    SCCG_CK(cudaEventRecord(c->ev[2], c->stream));
+    SCCG_TRY(scan_exclusive_u32(c, seg_bytes, seg_bytes, (i64)n_iter, sc + S_BODY_MAIN));
+
+    u32 h[S_COUNT];
+    SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
+    if (h[S_LOW_K] != h[S_LOW_KE]) return set_error(SCCG_E_CUDA, "internal: run start/end counts differ");
+    if (h[S_ABORT]) {                                                         // :462-473 -> global (:484-574)
+        return compress_global_device(c, d_ref, nr, d_tgt, nt, header, nh, h[S_LOW_K], cnt_s, cnt_e, res);
+    }
+
+    // ---- assemble "<header>\n<lowercase runs>\n,\n<body>"
+    const i64 leftover = n_tseg > n_iter ? nt - (i64)n_iter * SEG : 0;        // :476-481
+    const size_t hdr_bytes = nh > 0 ? (size_t)nh + 1 : 0;
+    const size_t cap = hdr_bytes + 24ull * h[S_LOW_K] + 3 + h[S_BODY_MAIN] + (size_t)leftover;
+    if (cap >= 0xffffffffull) return set_error(SCCG_E_ARG, "encoded output would exceed 4 GiB");
+    u8* out = nullptr;
+    SCCG_TRY(buf(c, B_OUT, cap + 16, &out));
+    SCCG_TRY(write_header(c, out, header, nh));
+    int *run_s = nullptr, *run_e = nullptr;
+    SCCG_TRY(rle_emit<0>(c, d_tgt, nt, h[S_LOW_K], cnt_s, cnt_e, sc + S_LOW_K, B_RUN_START, B_RUN_END, B_RUN_BYTES, &run_s, &run_e,
+                         out + hdr_bytes, sc + S_LOW_TEXT));
+    LAUNCH(c, put_separators_k, dim3(1), dim3(1), 0, out, (u32)hdr_bytes, sc, 0);
+    if (n_iter > 0) {
+        unsigned want = div_up(n_iter, 8);
+        unsigned capg = (unsigned)c->sm_count * 8u;
+        LAUNCH(c, seg_write_k, dim3(want < capg ? want : capg), dim3(256), 0, d_tgt, nt, (const u32*)seginfo, (const u32*)matches,
+               (const u32*)seg_bytes, (const int*)seg_prev, n_iter, out, (const u32*)(sc + S_BODY_BASE));
+    }
+    if (leftover > 0) {
+        unsigned g = div_up(leftover, 256 * 16);
+        unsigned capg = (unsigned)c->sm_count * 8u;
+        LAUNCH(c, upper_copy_k, dim3(g < capg ? g : capg), dim3(256), 0, d_tgt + (i64)n_iter * SEG, leftover, out,
+               (const u32*)(sc + S_BODY_BASE), h[S_BODY_MAIN]);
+    }
+    SCCG_CK(cudaEventRecord(c->ev[3], c->stream));
+    u32 h2[8];
+    SCCG_TRY(read_scalars(c, sc, h2, 8));
+    res->d_out = out;
+    res->out_len = (i64)hdr_bytes + h2[S_LOW_TEXT] + 3 + h[S_BODY_MAIN] + leftover;
+    res->mode = 0;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); c->prof.kernels_ms = ms;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->prof.match_ms = ms;
+    c->prof.serialize_ms = c->prof.kernels_ms - c->prof.match_ms;
+    c->prof.mode = 0;
+    return SCCG_OK;
+}
+
+}  // namespace sccg

@@ -1,0 +1,332 @@
+// Local (segment-aligned) match-and-encode: one warp per 1000-symbol segment pair.
+//   reference: match_sequences compression.cpp:36-179 called per segment from the driver :395-474.
+//
+// Per segment the warp
+//   1. stages r_i and t_i (upper-cased on the fly, :369-370) in shared memory with coalesced 8-byte
+//      loads and builds the diagonal-0 mismatch bitmap in the same pass;
+//   2. takes the exact fast path when t_i == r_i (the single candidate p = 0 of length 1000 cannot
+//      be tied), otherwise
+//   3. builds the k-mer index of r_i as a chained hash table in shared memory (:41-47; bucket order
+//      is irrelevant because candidate selection is evaluated as an order-independent reduction that
+//      equals the reference's ascending-p fold incl. its `pn == 0` quirk, :114-130) and
+//   4. runs the greedy parse (:64-161) warp-uniformly: cooperative k-mer hash (REDUX), chain walk,
+//      32-lane extension with ballot (extend_alignment :27-34); k = 14 first, k' = 10 if no match
+//      (:401, :428).
+// Output: one packed u32 per match (tpos | p << 10 | l << 20) in a fixed 100-entry slot per segment
+// and one u32 of per-segment status; literals are implied by the gaps between matches.
+#pragma once
+#include "sccg_scan.cuh"
+
+namespace sccg {
+
+static const int LM_WARPS = 8;
+static const int LM_HT_BITS = 10;
+static const int LM_HT = 1 << LM_HT_BITS;
+static const int LM_SEQ_PAD = 1040;
+static const int LM_SLOT = 100;               // max matches per segment: 1000 / k' (k' = 10)
+static const u32 LM_HASH_B = 0x01000193u;
+
+struct LmWarpSmem {
+    u8 r[LM_SEQ_PAD];
+    u8 t[LM_SEQ_PAD];
+    u32 head[LM_HT];       // 0 = empty, else p + 1
+    u16 next[1024];        // chain: 0 = end, else p + 1
+    u32 mm[32];            // bit (b & 31) of mm[b >> 5] set <=> r[b] != t[b] or b >= min(Lr, Lt)
+    u32 mlist[LM_SLOT + 4];
+};
+
+// seginfo layout
+#define SEGINFO_NMATCH(x) ((x) & 0xffu)
+#define SEGINFO_LIT(x) (((x) >> 8) & 0x7ffu)
+#define SEGINFO_ALLN(x) (((x) >> 20) & 1u)
+#define SEGINFO_BAD(x) (((x) >> 21) & 1u)
+
+__device__ __forceinline__ u32 lm_bucket(u32 h) { return (h * 0x9E3779B1u) >> (32 - LM_HT_BITS); }
+
+__device__ __forceinline__ u32 ld_unaligned32(const u8* base, int off) {
+    const u32* w = reinterpret_cast<const u32*>(base);
+    int q = off >> 2;
+    return __funnelshift_r(w[q], w[q + 1], (u32)(off & 3) * 8u);
+}
+
+// min(maxl, length of the common prefix of r[p..] and t[j..]); all 32 lanes, uniform arguments
+__device__ __forceinline__ int warp_lcp(const u8* r, int p, const u8* t, int j, int maxl) {
+    const int lane = lane_of();
+    for (int base = 0; base < maxl; base += 128) {
+        int o = base + 4 * lane;
+        u32 diff = 0xffffffffu;                               // beyond maxl counts as a mismatch at o
+        if (o < maxl) diff = ld_unaligned32(r, p + o) ^ ld_unaligned32(t, j + o);
+        u32 bal = __ballot_sync(SCCG_FULL_MASK, diff != 0u);
+        if (bal) {
+            int src = __ffs((int)bal) - 1;
+            u32 d = __shfl_sync(SCCG_FULL_MASK, diff, src);
+            int l = base + 4 * src + ((__ffs((int)d) - 1) >> 3);
+            return l < maxl ? l : maxl;
+        }
+    }
+    return maxl;
+}
+
+// first set bit of the 1024-bit diagonal bitmap at or after j, minus j
+__device__ __forceinline__ int diag_lcp(const u32* mm, int j) {
+    const int lane = lane_of();
+    u32 v = mm[lane];
+    int lo = 32 * lane;
+    if (lo + 31 < j) v = 0u;
+    else if (lo < j) v &= 0xffffffffu << (j - lo);
+    u32 bal = __ballot_sync(SCCG_FULL_MASK, v != 0u);
+    int src = __ffs((int)bal) - 1;                            // bits >= min(Lr, Lt) are always set
+    u32 vv = __shfl_sync(SCCG_FULL_MASK, v, src);
+    return 32 * src + (__ffs((int)vv) - 1) - j;
+}
+
+// k-mer index of r[0..Lr) (compression.cpp:41-47) as a chained hash table
+__device__ __forceinline__ void lm_build_index(LmWarpSmem& S, int Lr, int k, u32 bk1) {
+    const int lane = lane_of();
+    for (int x = lane; x < LM_HT; x += 32) S.head[x] = 0u;
+    __syncwarp();
+    int nk = Lr - k + 1;
+    if (nk > 0) {
+        int chunk = (nk + 31) >> 5;
+        int p = lane * chunk;
+        int p1 = p + chunk < nk ? p + chunk : nk;
+        if (p < p1) {
+            u32 h = 0u;
+            for (int i = 0; i < k; ++i) h = h * LM_HASH_B + S.r[p + i];
+            for (;;) {
+                u32 old = atomicExch(&S.head[lm_bucket(h)], (u32)(p + 1));
+                S.next[p] = (u16)old;
+                if (++p >= p1) break;
+                h = (h - (u32)S.r[p - 1] * bk1) * LM_HASH_B + S.r[p - 1 + k];   // roll one symbol
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// the greedy parse of one segment (compression.cpp:64-167); returns the number of matches, stored in S.mlist
+__device__ __forceinline__ int lm_parse(LmWarpSmem& S, int Lr, int Lt, int k, u32 powk) {
+    const int lane = lane_of();
+    int j = 0, e = -1, nmatch = 0;
+    while (j < Lt - k + 1) {                                                     // :64
+        u32 term = lane < k ? (u32)S.t[j + lane] * powk : 0u;
+        u32 h = __reduce_add_sync(SCCG_FULL_MASK, term);
+        u32 c = S.head[lm_bucket(h)];
+        int best_l = 0, cnt = 0;
+        bool zero_in = false;
+        u32 best_key = 0xffffffffu;                                              // (|p - e| << 16 | p), p != 0 only
+        while (c) {                                                              // :114 every candidate
+            int p = (int)c - 1;
+            int maxl = (Lr - p) < (Lt - j) ? (Lr - p) : (Lt - j);
+            int l = (p == j) ? diag_lcp(S.mm, j) : warp_lcp(S.r, p, S.t, j, maxl);   // :115 (0-based: also verifies the k-mer)
+            if (l >= k) {
+                if (l > best_l) { best_l = l; cnt = 0; zero_in = false; best_key = 0xffffffffu; }   // :127-128
+                if (l == best_l) {                                               // :124-126 as a reduction
+                    ++cnt;
+                    if (p == 0) zero_in = true;
+                    else {
+                        int d = p - e; if (d < 0) d = -d;
+                        u32 key = ((u32)d << 16) | (u32)p;
+                        if (key < best_key) best_key = key;
+                    }
+                }
+            }
+            c = S.next[p];
+        }
+        if (best_l == 0) { ++j; continue; }                                      // :77-81 literal
+        // p = 0 survives only when it is the single longest candidate (`pn1 == 0` is "unset", :125)
+        int p_sel = (cnt == 1 && zero_in) ? 0 : (int)(best_key & 0xffffu);
+        if (lane == 0) S.mlist[nmatch] = (u32)j | ((u32)p_sel << 10) | ((u32)best_l << 20);
+        ++nmatch;
+        e = p_sel + best_l - 1;                                                  // :149
+        j += best_l;                                                             // :159
+    }
+    return nmatch;
+}
+
+// k1 > 0 always; k2 == 0 disables the second pass (function-level match_sequences)
+__global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restrict__ ref, i64 nr, const u8* __restrict__ tgt, i64 nt,
+                                                            int n_iter, int k1, int k2, u32* __restrict__ seginfo, u32* __restrict__ matches) {
+    SCCG_DYN_SMEM(smem_raw);
+    LmWarpSmem& S = reinterpret_cast<LmWarpSmem*>(smem_raw)[threadIdx.x >> 5];
+    const int lane = lane_of();
+    const int warps_total = (int)(gridDim.x * (blockDim.x >> 5));
+    const int warp_global = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+
+    // B^(k-1-lane) for the cooperative k-mer hash, B^(k-1) for the rolling update
+    u32 pow1 = 0u, pow2 = 0u, bk1_1 = 1u, bk1_2 = 1u;
+    {
+        u32 x = 1u;
+        for (int i = 0; i < k1; ++i) { if (lane == k1 - 1 - i) pow1 = x; if (i == k1 - 1) bk1_1 = x; x *= LM_HASH_B; }
+        x = 1u;
+        for (int i = 0; i < k2; ++i) { if (lane == k2 - 1 - i) pow2 = x; if (i == k2 - 1) bk1_2 = x; x *= LM_HASH_B; }
+    }
+
+    for (int seg = warp_global; seg < n_iter; seg += warps_total) {
+        const i64 off = (i64)seg * SEG;
+        const int Lr = (int)((nr - off) < SEG ? (nr - off) : SEG);
+        const int Lt = (int)((nt - off) < SEG ? (nt - off) : SEG);
+        const int Lmin = Lr < Lt ? Lr : Lt;
+        __syncwarp();                                        // previous segment fully consumed
+        int all_n = 1;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            int q = lane + 32 * it;
+            int b0 = 8 * q;
+            u64 rw = 0ull, tw = 0ull;
+            if (b0 < Lr) rw = upper8(__ldg(reinterpret_cast<const u64*>(ref + off + b0)));
+            if (b0 < Lt) tw = upper8(__ldg(reinterpret_cast<const u64*>(tgt + off + b0)));
+            reinterpret_cast<u64*>(S.r)[q] = rw;
+            reinterpret_cast<u64*>(S.t)[q] = tw;
+            u32 mmb = movemask8(nonzero_flags8(rw ^ tw));
+            int valid = Lmin - b0;
+            if (valid < 8) mmb |= valid <= 0 ? 0xffu : ((0xffu << valid) & 0xffu);
+            reinterpret_cast<u8*>(S.mm)[q] = (u8)mmb;
+            int vt = Lt - b0;
+            u32 need = vt >= 8 ? 0xffu : (vt <= 0 ? 0u : ((1u << vt) - 1u));
+            if ((movemask8(eq_flags8(tw, 'N')) & need) != need) all_n = 0;
+        }
+        if (lane < 2) reinterpret_cast<u64*>(S.r)[128 + lane] = 0ull, reinterpret_cast<u64*>(S.t)[128 + lane] = 0ull;
+        all_n = __all_sync(SCCG_FULL_MASK, all_n);
+        __syncwarp();
+
+        int nmatch = 0;
+        const int f0 = diag_lcp(S.mm, 0);                    // first diagonal-0 mismatch (== Lmin if none)
+        if (Lr == Lt && Lt >= k1 && f0 >= Lt) {
+            // t_i == r_i: candidate p = 0 extends to Lt; any other p gives l <= Lr - p < Lt -> untied
+            if (lane == 0) S.mlist[0] = 0u | (0u << 10) | ((u32)Lt << 20);
+            nmatch = 1;
+        } else {
+            lm_build_index(S, Lr, k1, bk1_1);
+            nmatch = lm_parse(S, Lr, Lt, k1, pow1);                              // compression.cpp:401
+            if (nmatch == 0 && k2 > 0) {
+                lm_build_index(S, Lr, k2, bk1_2);
+                nmatch = lm_parse(S, Lr, Lt, k2, pow2);                          // compression.cpp:428
+            }
+        }
+        __syncwarp();
+        int covered = 0;
+        for (int m = lane; m < nmatch; m += 32) {
+            u32 pk = S.mlist[m];
+            matches[(i64)seg * LM_SLOT + m] = pk;
+            covered += (int)(pk >> 20);
+        }
+        covered = __reduce_add_sync(SCCG_FULL_MASK, covered);
+        if (lane == 0) {
+            int lit = Lt - covered;                                              // count_mismatches :413
+            u32 bad = (2 * lit > Lt) ? 1u : 0u;                                  // (float)lit / Lt > 0.5f  :417-419
+            seginfo[seg] = (u32)nmatch | ((u32)lit << 8) | ((u32)(all_n ? 1 : 0) << 20) | (bad << 21);
+        }
+    }
+}
+
+// Segment driver bookkeeping (compression.cpp:395-474): T2 abort test, delta chain carry, text size.
+// One thread per segment.
+__global__ void seg_bytes_k(const u32* __restrict__ seginfo, const u32* __restrict__ matches, int n_iter,
+                            u32* __restrict__ seg_bytes, int* __restrict__ seg_prev_p, u32* __restrict__ d_abort) {
+    int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= n_iter) return;
+    u32 info = seginfo[i];
+    int nmatch = (int)SEGINFO_NMATCH(info);
+    if (nmatch == 0) {
+        // both passes failed (:454-473).  counter > T2 <=> this and the 4 preceding segments all incremented it
+        if (!SEGINFO_ALLN(info) && i >= T2_LIMIT) {
+            bool all_inc = true;
+            for (int d = 1; d <= T2_LIMIT; ++d) {
+                u32 x = seginfo[i - d];
+                bool inc = !SEGINFO_ALLN(x) && (SEGINFO_NMATCH(x) == 0 || SEGINFO_BAD(x));
+                all_inc = all_inc && inc;
+            }
+            if (all_inc) atomicOr(d_abort, 1u);
+        }
+        seg_bytes[i] = 0u;                                   // silently dropped segment
+        seg_prev_p[i] = 0;
+        return;
+    }
+    int prev = 0;                                            // p of the previous match in file order (delta_encode :258)
+    for (int s = i - 1; s >= 0; --s) {
+        u32 x = seginfo[s];
+        int nm = (int)SEGINFO_NMATCH(x);
+        if (nm) { prev = s * SEG + (int)((matches[(i64)s * LM_SLOT + nm - 1] >> 10) & 0x3ffu); break; }
+    }
+    seg_prev_p[i] = prev;
+    u32 bytes = SEGINFO_LIT(info);
+    int pp = prev;
+    for (int m = 0; m < nmatch; ++m) {
+        u32 pk = matches[(i64)i * LM_SLOT + m];
+        int p_abs = i * SEG + (int)((pk >> 10) & 0x3ffu);
+        bytes += 3u + (u32)dec_len_i32(p_abs - pp) + (u32)dec_len_u32(pk >> 20);
+        pp = p_abs;
+    }
+    seg_bytes[i] = bytes;
+}
+
+// writes "(dp,l)" at o, returns its length
+__device__ __forceinline__ int write_token(u8* o, int dp, int l) {
+    int w = 0;
+    o[w++] = '(';
+    w += write_dec_i32(o + w, dp);
+    o[w++] = ',';
+    w += write_dec_i32(o + w, l);
+    o[w++] = ')';
+    return w;
+}
+
+// Record writer (compression.cpp:406-415) fused with delta_encode (:222-304): one warp per segment.
+__global__ void __launch_bounds__(256) seg_write_k(const u8* __restrict__ tgt, i64 nt, const u32* __restrict__ seginfo, const u32* __restrict__ matches,
+                                                   const u32* __restrict__ seg_off, const int* __restrict__ seg_prev_p, int n_iter,
+                                                   u8* __restrict__ out, const u32* __restrict__ d_body_base) {
+    const int lane = lane_of();
+    const int warps_total = (int)(gridDim.x * (blockDim.x >> 5));
+    const u32 body_base = *d_body_base;
+    for (int seg = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); seg < n_iter; seg += warps_total) {
+        const int nmatch = (int)SEGINFO_NMATCH(seginfo[seg]);
+        if (nmatch == 0) continue;
+        const i64 toff = (i64)seg * SEG;
+        const int Lt = (int)((nt - toff) < SEG ? (nt - toff) : SEG);
+        u8* base = out + body_base + seg_off[seg];
+        int prevp = seg_prev_p[seg], prev_end = 0;
+        u32 cursor = 0;
+        for (int c0 = 0; c0 < nmatch; c0 += 32) {
+            int m = c0 + lane;
+            bool valid = m < nmatch;
+            u32 pk = valid ? matches[(i64)seg * LM_SLOT + m] : 0u;
+            int tpos = (int)(pk & 0x3ffu), l = (int)(pk >> 20);
+            int p_abs = seg * SEG + (int)((pk >> 10) & 0x3ffu);
+            int te = tpos + l;
+            int pp = __shfl_up_sync(SCCG_FULL_MASK, p_abs, 1);
+            int pe = __shfl_up_sync(SCCG_FULL_MASK, te, 1);
+            if (lane == 0) { pp = prevp; pe = prev_end; }
+            int gap = valid ? tpos - pe : 0;
+            int tok = valid ? 3 + dec_len_i32(p_abs - pp) + dec_len_u32((u32)l) : 0;
+            u32 mine = (u32)(gap + tok);
+            u32 incl = warp_scan_incl(mine);
+            u32 o = cursor + incl - mine;
+            if (valid) {
+                if (gap <= 8) for (int x = 0; x < gap; ++x) base[o + x] = upper1(tgt[toff + pe + x]);
+                write_token(base + o + gap, p_abs - pp, l);
+            }
+            u32 big = __ballot_sync(SCCG_FULL_MASK, valid && gap > 8);   // long literal runs: whole warp copies
+            while (big) {
+                int src = __ffs((int)big) - 1; big &= big - 1;
+                int g = __shfl_sync(SCCG_FULL_MASK, gap, src);
+                int s0 = __shfl_sync(SCCG_FULL_MASK, pe, src);
+                u32 o0 = __shfl_sync(SCCG_FULL_MASK, o, src);
+                for (int x = lane; x < g; x += 32) base[o0 + x] = upper1(tgt[toff + s0 + x]);
+            }
+            int lastl = (nmatch - 1 - c0) < 31 ? (nmatch - 1 - c0) : 31;
+            prevp = __shfl_sync(SCCG_FULL_MASK, p_abs, lastl);
+            prev_end = __shfl_sync(SCCG_FULL_MASK, te, lastl);
+            cursor += __shfl_sync(SCCG_FULL_MASK, incl, 31);
+        }
+        for (int x = prev_end + lane; x < Lt; x += 32) base[cursor + (u32)(x - prev_end)] = upper1(tgt[toff + x]);   // trailing literals :164-167
+    }
+}
+
+// out[i] = toupper(src[i])  (leftover target segments, compression.cpp:476-481; global literals)
+__global__ void upper_copy_k(const u8* __restrict__ src, i64 n, u8* __restrict__ out, const u32* __restrict__ d_base, u32 extra) {
+    u8* dst = out + (d_base ? *d_base : 0u) + extra;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) dst[i] = upper1(src[i]);
+}
+
+}  // namespace sccg

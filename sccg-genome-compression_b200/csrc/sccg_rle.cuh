@@ -1,0 +1,133 @@
+// Lowercase-run and N-run extraction by parallel RLE, and the run-list text writer.
+//   reference: compression.cpp:341-367 (lowercase, raw target), :527-554 (N, upper-cased target).
+// HBM-bound: the target is streamed once per pass as 16-byte vectors (1 B per base per pass).
+#pragma once
+#include "sccg_scan.cuh"
+
+namespace sccg {
+
+static const int RLE_T = 256;
+static const int RLE_TILE = RLE_T * 16;
+
+// MODE 0: islower(raw byte)            (compression.cpp:345)
+// MODE 1: toupper(raw byte) == 'N'     (compression.cpp:523, :531)
+template <int MODE> __device__ __forceinline__ int rle_pred1(u8 c) {
+    return MODE == 0 ? (c >= 'a' && c <= 'z') : (c == 'N' || c == 'n');
+}
+template <int MODE> __device__ __forceinline__ u32 rle_pred8(u64 w) {
+    if (MODE == 0) return movemask8(lower_flags8(w));
+    return movemask8(eq_flags8(w, 'N') | eq_flags8(w, 'n'));
+}
+
+// start/end masks of the 16 positions [i, i+16) owned by this thread
+template <int MODE> __device__ __forceinline__ void rle_masks(const u8* __restrict__ src, i64 n, i64 i, u32* starts, u32* ends) {
+    *starts = 0; *ends = 0;
+    if (i >= n) return;
+    ulonglong2 v = *reinterpret_cast<const ulonglong2*>(src + i);     // buffers carry >= 64 B of slack
+    u32 m = rle_pred8<MODE>(v.x) | (rle_pred8<MODE>(v.y) << 8);
+    i64 left = n - i;
+    if (left < 16) m &= (1u << (int)left) - 1u;
+    u32 prev = (i > 0) ? (u32)rle_pred1<MODE>(src[i - 1]) : 0u;
+    u32 next = (i + 16 < n) ? (u32)rle_pred1<MODE>(src[i + 16]) : 0u;
+    *starts = m & ~((m << 1) | prev) & 0xffffu;
+    *ends = m & ~((m >> 1) | (next << 15)) & 0xffffu;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(RLE_T) rle_count_k(const u8* __restrict__ src, i64 n, u32* __restrict__ cnt_s, u32* __restrict__ cnt_e) {
+    __shared__ u32 sm[40];
+    i64 i = (i64)blockIdx.x * RLE_TILE + (i64)threadIdx.x * 16;
+    u32 s, e;
+    rle_masks<MODE>(src, n, i, &s, &e);
+    u32 packed = (u32)__popc(s) | ((u32)__popc(e) << 16);             // <= 2048 each per tile: no overflow
+    u32 tot;
+    block_scan_excl(packed, sm, &tot);
+    if (threadIdx.x == 0) { cnt_s[blockIdx.x] = tot & 0xffffu; cnt_e[blockIdx.x] = tot >> 16; }
+}
+
+// run k: [run_start[k], run_end[k]) ; the k-th start pairs with the k-th end
+template <int MODE>
+__global__ void __launch_bounds__(RLE_T) rle_write_k(const u8* __restrict__ src, i64 n, const u32* __restrict__ off_s, const u32* __restrict__ off_e,
+                                                     int* __restrict__ run_start, int* __restrict__ run_end) {
+    __shared__ u32 sm[40];
+    i64 i = (i64)blockIdx.x * RLE_TILE + (i64)threadIdx.x * 16;
+    u32 s, e;
+    rle_masks<MODE>(src, n, i, &s, &e);
+    u32 packed = (u32)__popc(s) | ((u32)__popc(e) << 16);
+    u32 tot;
+    u32 excl = block_scan_excl(packed, sm, &tot);
+    u32 ks = off_s[blockIdx.x] + (excl & 0xffffu);
+    u32 ke = off_e[blockIdx.x] + (excl >> 16);
+    while (s) { int b = __ffs((int)s) - 1; s &= s - 1; run_start[ks++] = (int)(i + b); }
+    while (e) { int b = __ffs((int)e) - 1; e &= e - 1; run_end[ke++] = (int)(i + b + 1); }
+}
+
+// text length of run-list item k  (compression.cpp:351-366)
+__device__ __forceinline__ int run_item_bytes(int delta, int len, bool last_at_end) {
+    if (len == 1) return dec_len_i32(delta) + (last_at_end ? 0 : 1);        // "d,"  or  "d" at the very end
+    return 3 + dec_len_i32(delta) + dec_len_i32(len);                       // "(d,len)"
+}
+
+__global__ void runs_bytes_k(const int* __restrict__ run_start, const int* __restrict__ run_end, const u32* __restrict__ d_count, i64 n, u32* __restrict__ bytes) {
+    u32 K = *d_count;
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    int st = run_start[k], en = run_end[k];
+    int delta = st - (k ? run_start[k - 1] : 0);
+    bytes[k] = (u32)run_item_bytes(delta, en - st, k == K - 1 && (i64)en == n);
+}
+
+__global__ void runs_write_k(const int* __restrict__ run_start, const int* __restrict__ run_end, const u32* __restrict__ d_count, i64 n,
+                             const u32* __restrict__ offs, u8* __restrict__ dst) {
+    u32 K = *d_count;
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    int st = run_start[k], en = run_end[k], len = en - st;
+    int delta = st - (k ? run_start[k - 1] : 0);
+    u8* o = dst + offs[k];
+    if (len == 1) {
+        int w = write_dec_i32(o, delta);
+        if (!(k == K - 1 && (i64)en == n)) o[w] = ',';
+    } else {
+        int w = 0;
+        o[w++] = '(';
+        w += write_dec_i32(o + w, delta);
+        o[w++] = ',';
+        w += write_dec_i32(o + w, len);
+        o[w] = ')';
+    }
+}
+
+// Phase 1: count runs.  Leaves the per-tile exclusive offsets in cnt_s / cnt_e and the run count in d_count.
+template <int MODE>
+static int rle_count(sccg_ctx* c, const u8* d_src, i64 n, int slot_cnt, u32** cnt_s, u32** cnt_e, u32* d_count, u32* d_count_e) {
+    unsigned ntiles = div_up(n > 0 ? n : 1, RLE_TILE);
+    u32* cnt = nullptr;
+    SCCG_TRY(buf(c, slot_cnt, (size_t)ntiles * 2, &cnt));
+    *cnt_s = cnt; *cnt_e = cnt + ntiles;
+    LAUNCH(c, rle_count_k<MODE>, dim3(ntiles), dim3(RLE_T), 0, d_src, n, *cnt_s, *cnt_e);
+    SCCG_TRY(scan_exclusive_u32(c, *cnt_s, *cnt_s, (i64)ntiles, d_count));
+    SCCG_TRY(scan_exclusive_u32(c, *cnt_e, *cnt_e, (i64)ntiles, d_count_e));
+    return SCCG_OK;
+}
+
+// Phase 2 (K known on the host): materialise the runs and their text.  d_text_len receives the text length;
+// the text is written at dst (capacity >= 24 * K).
+template <int MODE>
+static int rle_emit(sccg_ctx* c, const u8* d_src, i64 n, u32 K, const u32* cnt_s, const u32* cnt_e, const u32* d_count,
+                    int slot_start, int slot_end, int slot_bytes, int** run_start, int** run_end, u8* dst, u32* d_text_len) {
+    unsigned ntiles = div_up(n > 0 ? n : 1, RLE_TILE);
+    SCCG_TRY(buf(c, slot_start, (size_t)K + 1, run_start));
+    SCCG_TRY(buf(c, slot_end, (size_t)K + 1, run_end));
+    u32* bytes = nullptr;
+    SCCG_TRY(buf(c, slot_bytes, (size_t)K + 1, &bytes));
+    if (K == 0) { LAUNCH(c, scan_zero_total_k, dim3(1), dim3(1), 0, d_text_len); return SCCG_OK; }
+    LAUNCH(c, rle_write_k<MODE>, dim3(ntiles), dim3(RLE_T), 0, d_src, n, cnt_s, cnt_e, *run_start, *run_end);
+    unsigned g = div_up(K, 256);
+    LAUNCH(c, runs_bytes_k, dim3(g), dim3(256), 0, (const int*)*run_start, (const int*)*run_end, d_count, n, bytes);
+    SCCG_TRY(scan_exclusive_u32(c, bytes, bytes, (i64)K, d_text_len));
+    if (dst) LAUNCH(c, runs_write_k, dim3(g), dim3(256), 0, (const int*)*run_start, (const int*)*run_end, d_count, n, (const u32*)bytes, dst);
+    return SCCG_OK;
+}
+
+}  // namespace sccg

@@ -1,0 +1,104 @@
+"""Kernel-logic tests of the compression path on the CPU: the CUDA sources compiled against the SIMT
+emulator (tests/emu) versus the C oracle and the golden outputs of the compiled reference.  These
+do not replace the `-m gpu` parity tests (tests/test_gpu_*.py); they keep the kernels honest in the
+GPU-less build container."""
+import base64
+import os
+import random
+import zlib
+
+import pytest
+
+import oracle_lib as ol
+from cases import cases, rnd
+from emu_lib import emu_context
+
+CASES = cases()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = emu_context()
+    yield c
+    c.close()
+
+
+@pytest.fixture(params=[0, 1, 2], ids=["asc", "desc", "mixed"])
+def sweep_order(request):
+    os.environ["SCCG_EMU_ORDER"] = str(request.param)
+    yield request.param
+    os.environ.pop("SCCG_EMU_ORDER", None)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
+def test_compress_matches_golden(ctx, case, golden):
+    g = golden["cases"][case.name]
+    expect = zlib.decompress(base64.b64decode(g["intermediate_z"]))
+    if case.name == "J_grammar_symbols":
+        pytest.xfail("literal '(' in the target: needs the text-level delta pass (DESIGN.md, known gap)")
+    got, mode = ctx.compress(case.ref, case.tgt, case.header)
+    assert mode == g["mode"]
+    assert got == expect
+
+
+def _mutated_pair(seed, n, alphabet=b"ACGT", snp=0.01, indel=0.0):
+    r = random.Random(repr(seed))
+    ref = bytes(r.choice(alphabet) for _ in range(n))
+    t = bytearray()
+    for c in ref:
+        x = r.random()
+        if x < snp:
+            t.append(r.choice(alphabet))
+        elif x < snp + indel / 2:
+            continue
+        elif x < snp + indel:
+            t.append(c); t.append(r.choice(alphabet))
+        else:
+            t.append(c)
+    return ref, bytes(t)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_match_sequences_local_vs_oracle(ctx, seed, sweep_order):
+    alphabet = [b"ACGT", b"AC", b"ACGTN", b"A", b"ACGTacgtn"][seed % 5]
+    n = random.Random(seed).randint(1, 1000)
+    ref, tgt = _mutated_pair(("loc", seed), n, alphabet, snp=0.03, indel=0.004)
+    ref, tgt = ref.upper()[:1000], tgt.upper()[:1000]
+    for k in (14, 10):
+        exp = [(r.p, r.l, r.lit) for r in ol.orc_match_sequences(ref, tgt, k, 0, False, 5000)]
+        got = [(r.p, r.l, r.lit) for r in ctx.match_sequences(ref, tgt, k, 0, False, 5000)]
+        assert got == exp
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_compress_local_random(ctx, seed):
+    r = random.Random(repr(("cl", seed)))
+    n = r.randint(2000, 30000)
+    ref, tgt = _mutated_pair(("cl", seed), n, b"ACGT", snp=[0.001, 0.01, 0.05][seed % 3])
+    t = bytearray(tgt)
+    for _ in range(10):
+        a = r.randrange(len(t)); b = min(len(t), a + r.choice([1, 2, 30, 700, 2500]))
+        t[a:b] = bytes(t[a:b]).lower()
+        a = r.randrange(len(t)); b = min(len(t), a + r.choice([1, 5, 120, 1500]))
+        t[a:b] = b"N" * (b - a)
+        if seed % 2:
+            ref = ref[:a] + b"N" * (b - a) + ref[b:]
+    rc, exp, mode = ol.orc_compress(ref, bytes(t), b">rnd")
+    assert rc == 0
+    if mode != 0:
+        pytest.skip("went global")
+    got, gmode = ctx.compress(ref, bytes(t), b">rnd")
+    assert gmode == 0 and got == exp
+
+
+def test_many_segments_scan_paths(ctx):
+    # > 2048 segments so that the device-wide scan takes its multi-tile path
+    ref = rnd(3_000_000 // 4, "big") * 4
+    tgt = bytearray(ref)
+    r = random.Random("bigm")
+    for p in r.sample(range(len(tgt)), 3000):
+        tgt[p] = r.choice(b"ACGT")
+    tgt = bytes(tgt[:2_999_500]).replace(b"ACGTAC", b"acgtac", 50)
+    rc, exp, mode = ol.orc_compress(ref, tgt, b">big")
+    got, gmode = ctx.compress(ref, tgt, b">big")
+    assert (gmode, got) == (mode, exp)
