@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- SCCG hot path on B200: compression Mbp/s and decompression Gbp/s on the chr1-sized
+synthetic local pair (BASELINE.json configs[1]), kernel-only and end to end, with the HBM roofline
+of the dominant kernel and the reference's CPU implementation timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size BP] [--verify]
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one chromosome-sized
+pair: compress (lowercase RLE + segment match + driver + record/delta serialisation) and then
+decompress of the produced record stream.  N > 1: one process per GPU (torchrun), every rank works on
+its own pair of the same size (chromosome sharding, no data-path collective) -> weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "compress Mbp/s (decompress Gbp/s in `decompress`), chr1-sized synthetic local pair"
+HEADER = b">chr1 synthetic hg19-vs-hg18 shape"
+
+import sccg_b200  # noqa: E402  (registers the hyphenated package dir as sccg_genome_compression_b200)
+
+
+def peaks() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag.set()
+        self.thread.join(timeout=6)
+
+    def summary(self) -> dict:
+        sm = [int(s[0]) for s in self.samples if s and s[0].isdigit()]
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own CPU implementation (oracle/_ref when it was
+# compiled from /root/reference, else the C oracle port), timed on this box's host cores.
+# ----------------------------------------------------------------------------------------------
+def _ref_compress_worker(args):
+    """one process: reference `compress` + `decompress` executables on one FASTA slice"""
+    import oracle_lib as ol
+    ref_fa, tgt_fa, out_dir, n_bp = args
+    t0 = time.perf_counter()
+    r = subprocess.run([str(ol.REF_DIR / "compress"), ref_fa, tgt_fa, out_dir], env=ol.shim_env(), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    t1 = time.perf_counter()
+    d = subprocess.run([str(ol.REF_DIR / "decompress"), out_dir + "/compressed_genome.txt.7z", ref_fa, out_dir + "/dec"], env=ol.shim_env(),
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    t2 = time.perf_counter()
+    return r.returncode, d.returncode, t1 - t0, t2 - t1, n_bp
+
+
+def _port_compress_worker(args):
+    import oracle_lib as ol
+    ref, tgt = args
+    t0 = time.perf_counter()
+    rc, text, _ = ol.orc_compress(ref, tgt, HEADER)
+    t1 = time.perf_counter()
+    rc2, _ = ol.orc_decompress(ref, text)
+    t2 = time.perf_counter()
+    return rc, rc2, t1 - t0, t2 - t1, len(tgt)
+
+
+def cpu_reference_pass(ref, tgt, cores: int, slice_bp: int, tmp: Path) -> dict:
+    """`cores` processes, each running the reference on its own `slice_bp` slice of the workload (segments are
+    independent in local mode, so slices are the reference's natural unit of parallel work)."""
+    import concurrent.futures as cf
+    import oracle_lib as ol
+    kind = "reference" if ol.have_reference() else "port"
+    jobs = []
+    n = len(tgt)
+    for c in range(cores):
+        a = (c * slice_bp) % max(1, n - slice_bp)
+        a -= a % 1000
+        r, t = bytes(ref[a:a + slice_bp]), bytes(tgt[a:a + slice_bp])
+        if kind == "reference":
+            d = tmp / f"job{c}"
+            d.mkdir(parents=True, exist_ok=True)
+            ol.write_fasta(d / "ref.fa", r, b">ref")
+            ol.write_fasta(d / "tgt.fa", t, HEADER)
+            jobs.append((str(d / "ref.fa"), str(d / "tgt.fa"), str(d / "out"), len(t)))
+        else:
+            jobs.append((r, t))
+    t0 = time.perf_counter()
+    with cf.ProcessPoolExecutor(max_workers=cores) as ex:
+        res = list(ex.map(_ref_compress_worker if kind == "reference" else _port_compress_worker, jobs))
+    wall = time.perf_counter() - t0
+    assert all(r[0] == 0 and r[1] == 0 for r in res), "reference run failed"
+    bp = sum(r[4] for r in res)
+    comp_wall = max(r[2] for r in res)
+    dec_wall = max(r[3] for r in res)
+    return {"kind": kind, "cores": cores, "bp": bp, "compress_s": comp_wall, "decompress_s": dec_wall, "wall_s": wall,
+            "compress_mbp_s": bp / comp_wall / 1e6, "decompress_gbp_s": bp / dec_wall / 1e9}
+
+
+def run_reference_arm(args, rank: int) -> None:
+    if rank != 0:
+        return
+    from sccg_genome_compression_b200 import synth
+    cores = os.cpu_count() or 1
+    slice_bp = 4_000_000
+    n = min(args.size, max(slice_bp * 2, min(args.size, cores * slice_bp + slice_bp)))
+    ref, tgt = synth.local_pair(n, synth.seed_for(2, 0))
+    ref, tgt = ref.tobytes(), tgt.tobytes()
+    times_c, times_d, bp = [], [], 0
+    with tempfile.TemporaryDirectory() as d:
+        for step in range(args.warmup + args.steps):
+            r = cpu_reference_pass(ref, tgt, cores, slice_bp, Path(d))
+            if step >= args.warmup:
+                times_c.append(r["compress_s"]); times_d.append(r["decompress_s"]); bp = r["bp"]
+    ms = 1e3 * sum(times_c) / len(times_c)
+    value = bp / (ms / 1e3) / 1e6
+    dec = bp / (sum(times_d) / len(times_d)) / 1e9
+    sample = (f"{cores} processes x {slice_bp} bp slices of the chr1-sized synthetic local pair per step; whole `compress` program "
+              "(FASTA read + match + write + delta_encode; 7z replaced by a copy shim), wall time of the slowest process")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_name(args.size), "bp_per_step": bp},
+            "decompress": {"value": dec, "unit": "Gbp/s"},
+            "cpu_baseline": {"value": value, "unit": "Mbp/s", "cores": cores, "kind": r["kind"], "sample": sample},
+            "e2e": {"value": value, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(size: int) -> str:
+    from sccg_genome_compression_b200 import synth
+    base = "chr1-sized synthetic pair (249,250,621 bp reference, target with 0.1% SNPs + compensated small indels, 50% lowercase runs, co-located and target-only N runs), local segment-matching path"
+    return base if size == synth.CHR1_LEN else base + f" -- REDUCED to {size} bp (debug run, not the named config)"
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=0, help="bp per pair (default: chr1 = 249,250,621)")
+    ap.add_argument("--verify", action="store_true", help="compare the full-size output with the C oracle (untimed)")
+    ap.add_argument("--cpu-sample", type=int, default=20_000_000, help="bp of the workload timed on 1 host core as cpu_baseline")
+    args = ap.parse_args()
+    from sccg_genome_compression_b200 import synth
+    if args.size <= 0:
+        args.size = synth.CHR1_LEN
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import sccg_b200
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- workload: every rank owns one chromosome-sized pair (rank-dependent seed)
+    ref_np, tgt_np = synth.local_pair(args.size, synth.seed_for(2, rank))
+    nr, nt = int(ref_np.size), int(tgt_np.size)
+    h_ref = torch.from_numpy(ref_np).pin_memory()
+    h_tgt = torch.from_numpy(tgt_np).pin_memory()
+    d_ref = h_ref.cuda()
+    d_tgt = h_tgt.cuda()
+    ctx = sccg_b200.Context(local_rank)
+
+    # ---- compress, device-resident inputs (kernel-only `value`)
+    def compress_step():
+        ptr, length, mode = ctx.compress_device(d_ref.data_ptr(), nr, d_tgt.data_ptr(), nt, HEADER)
+        return ptr, length, mode, ctx.profile()
+
+    for _ in range(args.warmup):
+        ptr, enc_len, mode, prof = compress_step()
+    barrier()
+    ev_ms, match_ms, launches = 0.0, 0.0, 0
+    with ClockSampler(local_rank) as clocks:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ptr, enc_len, mode, prof = compress_step()
+            ev_ms += prof["kernels_ms"]; match_ms += prof["match_ms"]; launches += prof["launches"]
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+    assert mode == 0, "workload left the local path"
+    comp_ms = max_over_ranks(ev_ms / args.steps)
+    comp_wall_ms = max_over_ranks(wall_ms / args.steps)
+    match_ms_avg = max_over_ranks(match_ms / args.steps)
+
+    # the encoded image (device) -> host once, for the decompress half and for --verify
+    enc_bytes = ctx.download(ptr, enc_len)
+
+    # ---- decompress, device-resident inputs
+    dec = None
+    try:
+        import oracle_lib as ol
+        header, low, nline, body = ol.split_intermediate(enc_bytes)
+        d_body = torch.frombuffer(bytearray(body), dtype=torch.uint8).cuda()
+        d_low = torch.frombuffer(bytearray(low) or bytearray(1), dtype=torch.uint8).cuda()
+        d_n = torch.zeros(16, dtype=torch.uint8, device="cuda")
+        d_refu = torch.from_numpy(np.frombuffer(ref_np.tobytes().upper(), dtype=np.uint8).copy()).cuda()   # decompress_genome :110
+        for _ in range(args.warmup):
+            optr, out_len = ctx.reconstruct_device(d_refu.data_ptr(), nr, d_body.data_ptr(), len(body), d_n.data_ptr(), 0, d_low.data_ptr(), len(low))
+        barrier()
+        dms, dl, gather_ms = 0.0, 0, 0.0
+        for _ in range(args.steps):
+            optr, out_len = ctx.reconstruct_device(d_refu.data_ptr(), nr, d_body.data_ptr(), len(body), d_n.data_ptr(), 0, d_low.data_ptr(), len(low))
+            p = ctx.profile(); dms += p["kernels_ms"]; dl += p["launches"]; gather_ms += p["gather_ms"]
+        barrier()
+        dec_ms = max_over_ranks(dms / args.steps)
+        launches += dl
+        dec = {"value": world * nt / (dec_ms / 1e3) / 1e9, "unit": "Gbp/s", "ms_per_step": dec_ms,
+               "roofline": None}
+        hbm, which = peaks()
+        g_ms = max_over_ranks(gather_ms / args.steps)
+        dec_bytes = len(body) + nt + out_len
+        dec["roofline"] = {"bound": "hbm", "kernel": "decode_gather_k", "achieved": dec_bytes / (g_ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
+                           "frac": dec_bytes / (g_ms / 1e3) / 1e9 / hbm, "traffic": None, "peak_source": which}
+    except sccg_b200.SccgError as e:
+        if "not implemented" not in str(e):
+            raise
+        dec = {"unavailable": str(e)}
+
+    # ---- end to end through the host-pointer C ABI (H2D of both genomes + D2H of the record stream inside)
+    for _ in range(max(1, args.warmup // 2)):
+        out, mode2 = ctx.compress(_as_bytes(h_ref), _as_bytes(h_tgt), HEADER)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_prof = None
+    for _ in range(args.steps):
+        out, mode2 = ctx.compress(_as_bytes(h_ref), _as_bytes(h_tgt), HEADER)
+        e2e_prof = ctx.profile()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    assert out == enc_bytes, "end-to-end output differs from the device-resident output"
+
+    verified = None
+    if args.verify and rank == 0:
+        import oracle_lib as ol
+        rc, exp, emode = ol.orc_compress(ref_np.tobytes(), tgt_np.tobytes(), HEADER)
+        verified = bool(rc == 0 and exp == enc_bytes and emode == mode)
+        assert verified, "full-size output differs from the oracle"
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the reference on one host core, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_sample > 0:
+        with tempfile.TemporaryDirectory() as d:
+            sample = min(args.cpu_sample, nt)
+            r = cpu_reference_pass(ref_np[:sample].tobytes(), tgt_np[:sample].tobytes(), 1, sample, Path(d))
+        cpu = {"value": r["compress_mbp_s"], "unit": "Mbp/s", "cores": 1, "kind": r["kind"],
+               "decompress_gbp_s": r["decompress_gbp_s"],
+               "sample": f"first {sample} bp of the same pair; whole reference `compress` program on 1 core (FASTA read + match + write + "
+                         f"delta_encode, 7z = copy shim): {r['compress_s']:.2f} s; `decompress`: {r['decompress_s']:.2f} s"}
+
+    if rank == 0:
+        hbm, which = peaks()
+        algo_bytes = nr + nt                       # segment-match kernel: both genomes read once (SURVEY 8d, 2.0 B/bp)
+        ach = algo_bytes / (match_ms_avg / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * nt / (comp_ms / 1e3) / 1e6, "unit": "Mbp/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": comp_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_name(args.size), "bp_per_gpu": nt, "sharding": "one chromosome-sized pair per GPU, no data-path collective",
+                       "l2": "inputs (2 x 249 MB) larger than the 126 MB L2, no flush needed", "timing": "CUDA events on the library stream, max over ranks",
+                       "encoded_bytes": enc_len, "mode": "local"},
+            "wall_ms_per_step": comp_wall_ms,
+            "decompress": dec,
+            "roofline": {"bound": "hbm", "kernel": "seg_match_k", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": match_ms_avg, "peak_source": which},
+            "cpu_baseline": cpu,
+            "e2e": {"value": world * nt / (e2e_ms / 1e3) / 1e6, "unit": "Mbp/s", "h2d_bytes_per_step": nr + nt, "d2h_bytes_per_step": enc_len,
+                    "ms_per_step": e2e_ms, "h2d_ms": e2e_prof["h2d_ms"], "d2h_ms": e2e_prof["d2h_ms"], "kernels_ms": e2e_prof["kernels_ms"]},
+            "gpu_launches": launches,
+            "clocks": clocks.summary(),
+        }
+        if verified is not None:
+            line["verified_against_oracle"] = verified
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _as_bytes(t):
+    """zero-copy view of a pinned CPU uint8 tensor as a ctypes char buffer"""
+    import ctypes
+    return (ctypes.c_char * t.numel()).from_address(t.data_ptr())
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,8 @@ void        sccg_free(void* p);                      /* releases any buffer retu
 void        sccg_records_free(sccg_records* r);
 int         sccg_get_profile(sccg_ctx* ctx, sccg_profile* out);
 const char* sccg_version(void);
+/* copies n bytes of a device buffer returned by a *_device entry point to host memory (stream-ordered, blocking) */
+int         sccg_download(sccg_ctx* ctx, const void* d_src, int64_t n, void* h_dst);
 
 /* compress_genome minus file I/O and the external 7z stage (compression.cpp:320-579).
  * ref / tgt: raw symbols as read_genomes_from_files leaves them (:181-220): case preserved, no

@@ -74,6 +74,7 @@ def load_library(path: str | os.PathLike | None = None) -> C.CDLL:
     lib.sccg_free.argtypes = [vp]
     lib.sccg_records_free.argtypes = [C.POINTER(_Records)]
     lib.sccg_get_profile.argtypes = [vp, C.POINTER(Profile)]
+    lib.sccg_download.argtypes = [vp, vp, i64, vp]
     lib.sccg_compress.argtypes = [vp, cp, i64, cp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_int)]
     lib.sccg_compress_device.argtypes = [vp, vp, i64, vp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_int)]
     lib.sccg_match_sequences.argtypes = [vp, cp, i64, cp, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_Records)]
@@ -127,6 +128,12 @@ class Context:
         p = Profile()
         self._check(self.lib.sccg_get_profile(self.handle, C.byref(p)))
         return p.as_dict()
+
+    def download(self, d_ptr: int, n: int) -> bytes:
+        """device buffer (as returned by *_device calls) -> host bytes"""
+        buf = C.create_string_buffer(max(n, 1))
+        self._check(self.lib.sccg_download(self.handle, d_ptr, n, buf))
+        return buf.raw[:n]
 
     # compress_genome minus file I/O and 7z (compression.cpp:320-579)
     def compress(self, ref: bytes, tgt: bytes, header: bytes = b"") -> tuple[bytes, int]:

@@ -15,26 +15,6 @@ static int check_sizes(i64 a, i64 b) {
     return SCCG_OK;
 }
 
-// copies a host buffer into a grow-only device slot (pageable source: cudaMemcpyAsync stages it)
-static int upload(sccg_ctx* c, int slot, const void* h, i64 n, u8** d) {
-    SCCG_TRY(buf(c, slot, (size_t)n + 64, d));
-    if (n > 0) SCCG_CK(cudaMemcpyAsync(*d, h, (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    return SCCG_OK;
-}
-
-static int download(sccg_ctx* c, const u8* d, i64 n, char** out) {
-    char* h = (char*)malloc((size_t)n + 1);
-    if (!h) return set_error(SCCG_E_NOMEM, "malloc of the result failed");
-    if (n > 0) {
-        cudaError_t e = cudaMemcpyAsync(h, d, (size_t)n, cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) { free(h); return set_error(SCCG_E_CUDA, "result download failed: %s", cudaGetErrorString(e)); }
-    }
-    h[n] = 0;
-    *out = h;
-    return SCCG_OK;
-}
-
 static void prof_reset(sccg_ctx* c) { memset(&c->prof, 0, sizeof c->prof); }
 
 }  // namespace sccg
@@ -89,6 +69,16 @@ void sccg_records_free(sccg_records* r) {
     if (!r) return;
     free(r->p); free(r->l); free(r->lit_off); free(r->lits);
     memset(r, 0, sizeof *r);
+}
+
+int sccg_download(sccg_ctx* c, const void* d_src, int64_t n, void* h_dst) {
+    if (!c || n < 0 || (n > 0 && (!d_src || !h_dst))) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_CK(cudaSetDevice(c->device));
+    if (n > 0) {
+        SCCG_CK(cudaMemcpyAsync(h_dst, d_src, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        SCCG_CK(cudaStreamSynchronize(c->stream));
+    }
+    return SCCG_OK;
 }
 
 int sccg_get_profile(sccg_ctx* c, sccg_profile* out) {

@@ -81,9 +81,11 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
         unsigned cap = (unsigned)c->sm_count * 3u;
         unsigned grid = want < cap ? want : cap;
         LAUNCH(c, seg_match_k, dim3(grid), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, n_iter, K1, K2, seginfo, matches);
+        SCCG_CK(cudaEventRecord(c->ev[2], c->stream));
         LAUNCH(c, seg_bytes_k, dim3(div_up(n_iter, 256)), dim3(256), 0, (const u32*)seginfo, (const u32*)matches, n_iter, seg_bytes, seg_prev, sc + S_ABORT);
+    } else {
+        SCCG_CK(cudaEventRecord(c->ev[2], c->stream));
     }
-    SCCG_CK(cudaEventRecord(c->ev[2], c->stream));
     SCCG_TRY(scan_exclusive_u32(c, seg_bytes, seg_bytes, (i64)n_iter, sc + S_BODY_MAIN));
 
     u32 h[S_COUNT];

@@ -85,4 +85,26 @@ template <typename T> static int buf(sccg_ctx* c, int slot, size_t count, T** ou
 
 static inline unsigned div_up(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
+// copies a host buffer into a grow-only device slot (pageable source: cudaMemcpyAsync stages it)
+static int upload(sccg_ctx* c, int slot, const void* h, i64 n, u8** d) {
+    SCCG_TRY(buf(c, slot, (size_t)n + 64, d));
+    if (n > 0) SCCG_CK(cudaMemcpyAsync(*d, h, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    return SCCG_OK;
+}
+
+static int download(sccg_ctx* c, const u8* d, i64 n, char** out) {
+    char* h = (char*)malloc((size_t)n + 1);
+    if (!h) return set_error(SCCG_E_NOMEM, "malloc of the result failed");
+    if (n > 0) {
+        cudaError_t e = cudaMemcpyAsync(h, d, (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { free(h); return set_error(SCCG_E_CUDA, "result download failed: %s", cudaGetErrorString(e)); }
+    }
+    h[n] = 0;
+    *out = h;
+    return SCCG_OK;
+}
+
+
+
 }  // namespace sccg

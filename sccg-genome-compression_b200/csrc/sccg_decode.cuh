@@ -1,11 +1,449 @@
+// Record-decode (decompression): reconstruct_genome, decompression.cpp:117-279, on the device.
+//
+//   run-list parsers (:126-207)  -> parse_runs: number tokenizer + prefix sum of the deltas; runs stay
+//                                   (start,len) pairs instead of one int per lowercase / N base
+//   token decode (:210-236)      -> classify every byte of the body (literal / token start / inside
+//                                   a token), three prefix sums (output offset, segment index, token
+//                                   index), prefix sum of the token deltas -> absolute positions
+//   N merge, tolower, 50-col wrap (:241-274) -> ONE output-centric gather kernel: every thread
+//                                   produces 16 bytes of the final text straight from the reference /
+//                                   the literal bytes (no intermediate "stripped" sequence in HBM)
+//
+// Input grammar: exactly what the compressor emits (N1 in SURVEY.md) plus the optional ',' after a
+// tuple that the reference parser tolerates.  Anything else returns SCCG_E_FORMAT where the reference
+// would throw from stoi (exit 1) or run into undefined behaviour (unsorted / overlapping run lists).
 #pragma once
 #include "sccg_compress.cuh"
+#include "sccg_strip.cuh"
+
 namespace sccg {
+
+static const int TOK_MAX = 25;        // "(-2147483648,2147483647)" is 24 characters
+
+enum DecScalar { D_ERR = 0, D_NSEG, D_NTOK, D_LS, D_LOW_ITEMS, D_N_ITEMS, D_NSUM, D_LSUM, D_STRIP, D_COUNT = 16 };
+enum DecErr { DE_FORMAT = 1, DE_BOUNDS = 2 };
+
+__device__ __forceinline__ bool is_digit(u8 c) { return c >= '0' && c <= '9'; }
+
+// std::stoi on s[i..] restricted to what the writers emit: optional '-', 1..10 digits, fits in int.
+// returns the number of characters consumed, 0 on failure
+__device__ __forceinline__ int parse_int(const u8* __restrict__ s, i64 i, i64 n, int* out) {
+    int w = 0;
+    bool neg = false;
+    if (i < n && s[i] == '-') { neg = true; ++w; }
+    i64 v = 0;
+    int nd = 0;
+    while (i + w < n && is_digit(s[i + w]) && nd < 11) { v = v * 10 + (s[i + w] - '0'); ++w; ++nd; }
+    if (nd == 0 || nd > 10) return 0;
+    if (neg) v = -v;
+    if (v > 2147483647LL || v < -2147483648LL) return 0;
+    *out = (int)v;
+    return w;
+}
+
+// is byte i inside a "(...)" token that started before i?  (the last parenthesis in the TOK_MAX bytes before i is '(')
+__device__ __forceinline__ bool inside_token(const u8* __restrict__ s, i64 i) {
+    for (int d = 1; d <= TOK_MAX; ++d) {
+        if (i - d < 0) return false;
+        u8 c = s[i - d];
+        if (c == '(') return true;
+        if (c == ')') return false;
+    }
+    return false;
+}
+
+// byte i is copied to the output as a literal symbol (decompression.cpp:233)
+__device__ __forceinline__ bool is_literal(const u8* __restrict__ s, i64 i) { return s[i] != '(' && !inside_token(s, i); }
+
+// parses "(a,b)" at s[i]; returns its length in characters or 0
+__device__ __forceinline__ int parse_tuple(const u8* __restrict__ s, i64 i, i64 n, int* a, int* b) {
+    int w = 1;
+    int k = parse_int(s, i + w, n, a);
+    if (!k) return 0;
+    w += k;
+    if (i + w >= n || s[i + w] != ',') return 0;
+    ++w;
+    k = parse_int(s, i + w, n, b);
+    if (!k) return 0;
+    w += k;
+    if (i + w >= n || s[i + w] != ')') return 0;
+    return w + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// body: per-byte classification (decompression.cpp:213-236)
+//   contrib[i] = symbols this byte contributes to the decoded sequence (1 literal, len token start, 0 inside)
+//   isseg[i]   = 1 where a copy segment starts (token start, or first byte of a literal run)
+//   istok[i]   = 1 at token starts
+// ------------------------------------------------------------------------------------------------
+__global__ void dec_classify_k(const u8* __restrict__ enc, i64 ne, u32* __restrict__ contrib, u32* __restrict__ isseg, u32* __restrict__ istok, u32* __restrict__ sc) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ne) return;
+    u8 c = enc[i];
+    bool inside = inside_token(enc, i);
+    u32 con = 0, seg = 0, tok = 0;
+    if (inside) {
+        // bytes of a token after its '(' : nothing to emit
+    } else if (c == '(') {
+        int d, l;
+        int w = parse_tuple(enc, i, ne, &d, &l);
+        if (!w || l < 0) { atomicOr(&sc[D_ERR], (u32)DE_FORMAT); }
+        else { con = (u32)l; seg = 1; tok = 1; }
+    } else {
+        con = 1;                                                  // literal symbol (:233)
+        seg = (i > 0 && is_literal(enc, i - 1)) ? 0u : 1u;        // first byte of a literal run
+    }
+    contrib[i] = con; isseg[i] = seg; istok[i] = tok;
+}
+
+// compacts segments and tokens
+//   seg_dst[k] : offset of segment k in the decoded (N-free) sequence
+//   seg_src[k] : literal run -> index into enc | LIT_FLAG ; token -> token index (absolute position filled later)
+//   tok_delta[t], tok_len[t]
+#define SEG_LIT_FLAG 0x4000000000000000LL
+__global__ void dec_compact_k(const u8* __restrict__ enc, i64 ne, const u32* __restrict__ off, const u32* __restrict__ segidx, const u32* __restrict__ tokidx,
+                              u32* __restrict__ seg_dst, i64* __restrict__ seg_src, int* __restrict__ tok_delta, int* __restrict__ tok_len) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ne) return;
+    u8 c = enc[i];
+    bool inside = inside_token(enc, i);
+    if (inside) return;
+    if (c == '(') {
+        int d = 0, l = 0;
+        if (!parse_tuple(enc, i, ne, &d, &l)) return;
+        u32 k = segidx[i], t = tokidx[i];
+        seg_dst[k] = off[i];
+        seg_src[k] = (i64)t;
+        tok_delta[t] = d; tok_len[t] = l;
+    } else {
+        bool prev_lit = i > 0 && is_literal(enc, i - 1);
+        if (!prev_lit) { u32 k = segidx[i]; seg_dst[k] = off[i]; seg_src[k] = (i64)i | SEG_LIT_FLAG; }
+    }
+}
+
+// abs[t] = prefix sum of the deltas (decompression.cpp:220-222), bounds check (:223-229)
+__global__ void dec_token_abs_k(const int* __restrict__ tok_delta, const int* __restrict__ tok_len, const u32* __restrict__ delta_excl, u32 ntok, i64 nr,
+                                int* __restrict__ tok_abs, u32* __restrict__ sc) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntok) return;
+    int a = (int)(delta_excl[t] + (u32)tok_delta[t]);             // prev_abs_start + delta, int arithmetic
+    tok_abs[t] = a;
+    i64 end = (i64)(int)((u32)a + (u32)tok_len[t]);               // `absolute_start + length` is evaluated in int
+    if (end > nr) atomicOr(&sc[D_ERR], (u32)DE_BOUNDS);
+    else if (a < 0) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);         // substr(pos > size) throws out_of_range
+}
+
+// ------------------------------------------------------------------------------------------------
+// run lists (decompression.cpp:126-207): "(d,len)" | "d," | "d"
+// ------------------------------------------------------------------------------------------------
+__global__ void runs_classify_k(const u8* __restrict__ s, i64 n, u32* __restrict__ isitem, u32* __restrict__ sc) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u8 c = s[i];
+    bool inside = inside_token(s, i);
+    u32 item = 0;
+    if (inside) {
+        if (!(is_digit(c) || c == '-' || c == ',' || c == ')')) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);
+    } else if (c == '(') {
+        int d, l;
+        if (!parse_tuple(s, i, n, &d, &l) || l < 0) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);
+        item = 1;
+    } else if (is_digit(c) || c == '-') {
+        bool start = (i == 0) || !(is_digit(s[i - 1]) || s[i - 1] == '-');
+        if (start) {
+            int d;
+            int w = parse_int(s, i, n, &d);
+            if (!w || (i + w < n && s[i + w] != ',')) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);
+            item = 1;
+        }
+    } else if (c == ',') {
+        // separator after a single, or the optional one after a tuple (:143-144)
+        if (i == 0 || !(is_digit(s[i - 1]) || s[i - 1] == ')')) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);
+    } else {
+        atomicOr(&sc[D_ERR], (u32)DE_FORMAT);
+    }
+    isitem[i] = item;
+}
+
+__global__ void runs_compact_k(const u8* __restrict__ s, i64 n, const u32* __restrict__ itemidx, int* __restrict__ delta, int* __restrict__ len) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u8 c = s[i];
+    if (inside_token(s, i)) return;
+    if (c == '(') {
+        int d = 0, l = 0;
+        if (!parse_tuple(s, i, n, &d, &l)) return;
+        delta[itemidx[i]] = d; len[itemidx[i]] = l;
+    } else if (is_digit(c) || c == '-') {
+        bool start = (i == 0) || !(is_digit(s[i - 1]) || s[i - 1] == '-');
+        if (!start) return;
+        int d = 0;
+        if (!parse_int(s, i, n, &d)) return;
+        delta[itemidx[i]] = d; len[itemidx[i]] = 1;
+    }
+}
+
+// start[k] = prefix sum of deltas; validates ascending, non-overlapping runs
+__global__ void runs_finish_k(const int* __restrict__ delta, const int* __restrict__ len, const u32* __restrict__ delta_excl, u32 K,
+                              int* __restrict__ start, u32* __restrict__ sc) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    int st = (int)(delta_excl[k] + (u32)delta[k]);
+    start[k] = st;
+    if (st < 0 || len[k] < 0) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);
+    if (k > 0) {
+        int pst = (int)delta_excl[k];                             // previous start
+        if ((i64)st < (i64)pst + (i64)len[k - 1]) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);
+    }
+}
+
+struct RunTable { int* start; int* len; u32* cum; u32 K; };        // cum[k] = sum of len[0..k)
+
+static int parse_runs(sccg_ctx* c, const u8* d_text, i64 n, int slot_base, u32* sc, int sc_items, u32* sc_sum, RunTable* out) {
+    // slot_base: 4 consecutive buffer slots
+    out->start = nullptr; out->len = nullptr; out->cum = nullptr; out->K = 0;
+    if (n <= 0) {
+        SCCG_TRY(buf(c, slot_base + 1, 4, &out->start));
+        SCCG_TRY(buf(c, slot_base + 2, 4, &out->len));
+        SCCG_TRY(buf(c, slot_base + 3, 4, &out->cum));
+        return SCCG_OK;
+    }
+    u32* isitem = nullptr;
+    SCCG_TRY(buf(c, slot_base, (size_t)n + 1, &isitem));
+    unsigned g = div_up(n, 256);
+    LAUNCH(c, runs_classify_k, dim3(g), dim3(256), 0, d_text, n, isitem, sc);
+    SCCG_TRY(scan_exclusive_u32(c, isitem, isitem, n, sc + sc_items));
+    u32 h[D_COUNT];
+    SCCG_TRY(read_scalars(c, sc, h, D_COUNT));
+    if (h[D_ERR]) return set_error(SCCG_E_FORMAT, "malformed run list (the reference would throw from stoi or misbehave)");
+    u32 K = h[sc_items];
+    int *delta = nullptr;
+    u32* excl = nullptr;
+    SCCG_TRY(buf(c, slot_base + 1, (size_t)K + 1, &out->start));
+    SCCG_TRY(buf(c, slot_base + 2, (size_t)K + 1, &out->len));
+    SCCG_TRY(buf(c, slot_base + 3, (size_t)K + 1, &out->cum));
+    SCCG_TRY(buf(c, B_TILE0, (size_t)K + 1, &delta));
+    SCCG_TRY(buf(c, B_TILE1, (size_t)K + 1, &excl));
+    out->K = K;
+    if (K == 0) return SCCG_OK;
+    LAUNCH(c, runs_compact_k, dim3(g), dim3(256), 0, d_text, n, (const u32*)isitem, delta, out->len);
+    SCCG_TRY(scan_exclusive_u32(c, (const u32*)delta, excl, (i64)K, nullptr));
+    LAUNCH(c, runs_finish_k, dim3(div_up(K, 256)), dim3(256), 0, (const int*)delta, (const int*)out->len, (const u32*)excl, K, out->start, sc);
+    SCCG_TRY(scan_exclusive_u32(c, (const u32*)out->len, out->cum, (i64)K, sc_sum));
+    return SCCG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the gather: N merge (:244-252), tolower (:255-262), 50-column wrap (:266-274)
+// ------------------------------------------------------------------------------------------------
+// last k with arr[k] <= x, or -1
+__device__ __forceinline__ int upper_idx_i32(const int* __restrict__ arr, int n, i64 x) {
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if ((i64)arr[mid] <= x) lo = mid + 1; else hi = mid; }
+    return lo - 1;
+}
+__device__ __forceinline__ int upper_idx_u32(const u32* __restrict__ arr, int n, i64 x) {
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if ((i64)arr[mid] <= x) lo = mid + 1; else hi = mid; }
+    return lo - 1;
+}
+
+struct GatherArgs {
+    const u8* ref; const u8* enc;
+    const u32* seg_dst; const i64* seg_src; const int* tok_abs; int nseg;
+    const int* n_start; const int* n_len; const u32* n_cum; int n_k;
+    const int* l_start; const int* l_len; int l_k;
+    i64 Lm;          // symbols in the N-merged sequence
+    i64 total;       // bytes of wrapped text
+    u8* out;
+};
+
+static const int GATHER_BYTES = 16;
+
+__global__ void __launch_bounds__(256) dec_gather_k(GatherArgs a) {
+    i64 q0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * GATHER_BYTES;
+    if (q0 >= a.total) return;
+    u8 buf16[GATHER_BYTES];
+    // cursors, (re)positioned lazily by binary search and then advanced monotonically
+    int nk = -2, lk = -2, sk = -2;
+    for (int x = 0; x < GATHER_BYTES; ++x) {
+        i64 q = q0 + x;
+        u8 o = '\n';
+        if (q < a.total) {
+            i64 line = q / (WRAP + 1);
+            int col = (int)(q - line * (WRAP + 1));
+            i64 b = line * WRAP + col;
+            if (col < WRAP && b < a.Lm) {
+                // N runs (original coordinates)
+                if (nk == -2) nk = upper_idx_i32(a.n_start, a.n_k, b);
+                else while (nk + 1 < a.n_k && (i64)a.n_start[nk + 1] <= b) ++nk;
+                bool is_n = false;
+                i64 s = b;
+                if (nk >= 0) {
+                    i64 st = a.n_start[nk], ln = a.n_len[nk];
+                    if (b < st + ln) is_n = true;
+                    else s = b - ((i64)a.n_cum[nk] + ln);
+                }
+                if (is_n) o = 'N';
+                else {
+                    if (sk == -2) sk = upper_idx_u32(a.seg_dst, a.nseg, s);
+                    else while (sk + 1 < a.nseg && (i64)a.seg_dst[sk + 1] <= s) ++sk;
+                    i64 src = a.seg_src[sk];
+                    i64 within = s - (i64)a.seg_dst[sk];
+                    if (src & SEG_LIT_FLAG) o = a.enc[(src & ~SEG_LIT_FLAG) + within];
+                    else o = a.ref[(i64)a.tok_abs[src] + within];
+                }
+                // lowercase runs
+                if (lk == -2) lk = upper_idx_i32(a.l_start, a.l_k, b);
+                else while (lk + 1 < a.l_k && (i64)a.l_start[lk + 1] <= b) ++lk;
+                if (lk >= 0 && b < (i64)a.l_start[lk] + (i64)a.l_len[lk]) o = lower1(o);
+            }
+        }
+        buf16[x] = o;
+    }
+    if (q0 + GATHER_BYTES <= a.total) {
+        uint4 v;
+        v.x = (u32)buf16[0] | ((u32)buf16[1] << 8) | ((u32)buf16[2] << 16) | ((u32)buf16[3] << 24);
+        v.y = (u32)buf16[4] | ((u32)buf16[5] << 8) | ((u32)buf16[6] << 16) | ((u32)buf16[7] << 24);
+        v.z = (u32)buf16[8] | ((u32)buf16[9] << 8) | ((u32)buf16[10] << 16) | ((u32)buf16[11] << 24);
+        v.w = (u32)buf16[12] | ((u32)buf16[13] << 8) | ((u32)buf16[14] << 16) | ((u32)buf16[15] << 24);
+        *reinterpret_cast<uint4*>(a.out + q0) = v;
+    } else {
+        for (int x = 0; q0 + x < a.total; ++x) a.out[q0 + x] = buf16[x];
+    }
+}
+
+// reconstruct_genome.  header_reserve bytes are left free in front of the text (multiple of 16) so that the caller
+// can place "<header>\n" right before it.  *d_out points at the text itself.
 static int reconstruct_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_enc, i64 ne, const u8* d_n, i64 nn, const u8* d_low, i64 nl,
                               i64 header_reserve, u8** d_out, i64* out_len) {
-    return set_error(SCCG_E_ARG, "decode not implemented yet");
+    u32* sc = nullptr;
+    SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
+    SCCG_CK(cudaMemsetAsync(sc, 0, sizeof(u32) * S_COUNT, c->stream));
+    SCCG_CK(cudaEventRecord(c->ev[0], c->stream));
+
+    RunTable lows, ns;
+    SCCG_TRY(parse_runs(c, d_low, nl, B_NUM0, sc, D_LOW_ITEMS, sc + D_LSUM, &lows));     // slots B_NUM0..B_NUM3
+    SCCG_TRY(parse_runs(c, d_n, nn, B_NUM4, sc, D_N_ITEMS, sc + D_NSUM, &ns));          // slots B_NUM4, B_NUM5, B_LRUN_S, B_LRUN_E
+
+    // ---- body tokenizer
+    u32 *contrib = nullptr, *isseg = nullptr, *istok = nullptr;
+    i64 ne1 = ne > 0 ? ne : 1;
+    SCCG_TRY(buf(c, B_TOK_FLAG, (size_t)ne1 * 3 + 3, &contrib));
+    isseg = contrib + ne1; istok = isseg + ne1;
+    if (ne > 0) {
+        LAUNCH(c, dec_classify_k, dim3(div_up(ne, 256)), dim3(256), 0, d_enc, ne, contrib, isseg, istok, sc);
+    }
+    SCCG_TRY(scan_exclusive_u32(c, contrib, contrib, ne, sc + D_LS));
+    SCCG_TRY(scan_exclusive_u32(c, isseg, isseg, ne, sc + D_NSEG));
+    SCCG_TRY(scan_exclusive_u32(c, istok, istok, ne, sc + D_NTOK));
+    u32 h[D_COUNT];
+    SCCG_TRY(read_scalars(c, sc, h, D_COUNT));
+    if (h[D_ERR] & DE_FORMAT) return set_error(SCCG_E_FORMAT, "malformed record stream (the reference would throw from stoi)");
+    const u32 nseg = h[D_NSEG], ntok = h[D_NTOK];
+    const i64 Ls = h[D_LS];
+    const i64 nsum = ns.K ? (i64)h[D_NSUM] : 0;
+
+    u32* seg_dst = nullptr; i64* seg_src = nullptr; int *tok_delta = nullptr, *tok_len = nullptr, *tok_abs = nullptr; u32* delta_excl = nullptr;
+    SCCG_TRY(buf(c, B_TOK_POS, (size_t)nseg + 1, &seg_dst));
+    SCCG_TRY(buf(c, B_ITEM_SRC, (size_t)nseg + 1, &seg_src));
+    SCCG_TRY(buf(c, B_ITEM_OFF, (size_t)ntok * 3 + 3, &tok_delta));
+    tok_len = tok_delta + ntok + 1; tok_abs = tok_len + ntok + 1;
+    SCCG_TRY(buf(c, B_TILE2, (size_t)ntok + 1, &delta_excl));
+    if (ne > 0) {
+        LAUNCH(c, dec_compact_k, dim3(div_up(ne, 256)), dim3(256), 0, d_enc, ne, (const u32*)contrib, (const u32*)isseg, (const u32*)istok,
+               seg_dst, seg_src, tok_delta, tok_len);
+    }
+    if (ntok > 0) {
+        SCCG_TRY(scan_exclusive_u32(c, (const u32*)tok_delta, delta_excl, (i64)ntok, nullptr));
+        LAUNCH(c, dec_token_abs_k, dim3(div_up(ntok, 256)), dim3(256), 0, (const int*)tok_delta, (const int*)tok_len, (const u32*)delta_excl, ntok, nr, tok_abs, sc);
+    }
+    SCCG_CK(cudaEventRecord(c->ev[1], c->stream));
+
+    // ---- sizes: N-merged length, wrapped text length
+    const i64 Lm = Ls + nsum;
+    const i64 nchunks = (Lm + WRAP - 1) / WRAP;
+    const i64 total = Lm > 0 ? Lm + nchunks : 1;
+    if (total >= 0xffffffffLL) return set_error(SCCG_E_ARG, "decoded output would exceed 4 GiB");
+    u8* out = nullptr;
+    SCCG_TRY(buf(c, B_OUT, (size_t)(header_reserve + total + 32), &out));
+    GatherArgs a;
+    a.ref = d_ref; a.enc = d_enc; a.seg_dst = seg_dst; a.seg_src = seg_src; a.tok_abs = tok_abs; a.nseg = (int)nseg;
+    a.n_start = ns.start; a.n_len = ns.len; a.n_cum = ns.cum; a.n_k = (int)ns.K;
+    a.l_start = lows.start; a.l_len = lows.len; a.l_k = (int)lows.K;
+    a.Lm = Lm; a.total = total; a.out = out + header_reserve;
+    LAUNCH(c, dec_gather_k, dim3(div_up(total, 256 * GATHER_BYTES)), dim3(256), 0, a);
+    SCCG_CK(cudaEventRecord(c->ev[2], c->stream));
+    SCCG_TRY(read_scalars(c, sc, h, D_COUNT));
+    if (h[D_ERR] & DE_BOUNDS) return set_error(SCCG_E_BOUNDS, "ERROR: absolute_start + length exceeds reference genome size");
+    if (h[D_ERR]) return set_error(SCCG_E_FORMAT, "malformed record stream or run list");
+    // the last N run must end inside the merged sequence, the reference would read out of range otherwise (:250)
+    *d_out = out + header_reserve;
+    *out_len = total;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[2]); c->prof.kernels_ms = ms;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->prof.serialize_ms = ms;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->prof.gather_ms = ms;
+    return SCCG_OK;
 }
+
+
+// decompress_genome's in-memory part (decompression.cpp:66-110) + reconstruct_genome + main's "<header>\n" (:322)
 static int decompress_host(sccg_ctx* c, const char* ref_raw, i64 ref_len, const char* inter, i64 inter_len, char** out, int64_t* out_len) {
-    return set_error(SCCG_E_ARG, "decode not implemented yet");
+    // ---- the 3 / 4 getline calls (:66-101)
+    const char* lines[4] = {inter, inter, inter, inter};
+    i64 lens[4] = {0, 0, 0, 0};
+    i64 cur = 0;
+    auto next_line = [&](const char** b, i64* n) -> bool {
+        if (cur >= inter_len) return false;
+        const char* q = (const char*)memchr(inter + cur, '\n', (size_t)(inter_len - cur));
+        *b = inter + cur;
+        if (q) { *n = (q - inter) - cur; cur = (q - inter) + 1; } else { *n = inter_len - cur; cur = inter_len; }
+        return true;
+    };
+    if (!next_line(&lines[0], &lens[0])) return set_error(SCCG_E_FORMAT, "Greska pri citanju datoteke (empty intermediate file)");
+    i64 nh = 0; const char* header = inter;
+    const char *low, *nline, *body; i64 nl, nn, nb;
+    if (lens[0] > 0 && lines[0][0] == '>') {
+        header = lines[0]; nh = lens[0];
+        if (!next_line(&low, &nl)) return set_error(SCCG_E_FORMAT, "Greska pri citanju indeksa malih slova");
+    } else { low = lines[0]; nl = lens[0]; }
+    if (!next_line(&nline, &nn)) return set_error(SCCG_E_FORMAT, "Greska pri citanju indeksa nepoznatih nukleotida");
+    if (!next_line(&body, &nb)) return set_error(SCCG_E_FORMAT, "Greska pri citanju kodiranog genoma");
+    const bool local_mode = (nn == 1 && nline[0] == ',');                      // :105
+    // ---- uploads
+    u8 *d_raw = nullptr, *d_ref = nullptr, *d_enc = nullptr, *d_n = nullptr, *d_low = nullptr;
+    SCCG_CK(cudaEventRecord(c->ev[4], c->stream));
+    SCCG_TRY(upload(c, B_TGT, ref_raw, ref_len, &d_raw));
+    SCCG_TRY(upload(c, B_ENC, body, nb, &d_enc));
+    SCCG_TRY(upload(c, B_NIDX, nline, local_mode ? 0 : nn, &d_n));
+    SCCG_TRY(upload(c, B_LOW, low, nl, &d_low));
+    SCCG_CK(cudaEventRecord(c->ev[5], c->stream));
+    // ---- reference preparation (:105-110)
+    SCCG_TRY(buf(c, B_REF, (size_t)ref_len + 64, &d_ref));
+    i64 nr = ref_len;
+    u32* sc = nullptr;
+    SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
+    if (local_mode) {
+        if (ref_len > 0) LAUNCH(c, upper_k, dim3(div_up(ref_len, 256 * 16)), dim3(256), 0, (const u8*)d_raw, ref_len, d_ref);
+    } else {
+        SCCG_TRY(strip_n<0>(c, d_raw, ref_len, d_ref, B_TILE3, sc + D_STRIP, &nr));
+    }
+    const i64 reserve = ((nh + 1) + 15) & ~(i64)15;
+    u8* d_text = nullptr; i64 n = 0;
+    SCCG_TRY(reconstruct_device(c, d_ref, nr, d_enc, nb, d_n, local_mode ? 0 : nn, d_low, nl, reserve, &d_text, &n));
+    // "<header>\n" right in front of the text (:322; an absent header still yields the "\n")
+    memcpy(c->h_pinned, header, (size_t)nh);
+    ((char*)c->h_pinned)[nh] = '\n';
+    SCCG_CK(cudaMemcpyAsync(d_text - (nh + 1), c->h_pinned, (size_t)nh + 1, cudaMemcpyHostToDevice, c->stream));
+    SCCG_CK(cudaEventRecord(c->ev[6], c->stream));
+    SCCG_TRY(download(c, d_text - (nh + 1), n + nh + 1, out));
+    SCCG_CK(cudaEventRecord(c->ev[7], c->stream));
+    SCCG_CK(cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->prof.h2d_ms, c->ev[4], c->ev[5]);
+    cudaEventElapsedTime(&c->prof.d2h_ms, c->ev[6], c->ev[7]);
+    *out_len = n + nh + 1;
+    return SCCG_OK;
 }
-}
+
+}  // namespace sccg

@@ -21,7 +21,7 @@ class Case:
 
 
 def rnd(n: int, seed, alphabet: bytes = b"ACGT") -> bytes:
-    r = random.Random(seed)
+    r = random.Random(seed if isinstance(seed, (int, str, bytes)) else repr(seed))
     return bytes(r.choice(alphabet) for _ in range(n))
 
 

@@ -1,0 +1,103 @@
+"""Kernel-logic tests of the record-decode path on the CPU (SIMT emulator build) versus the golden
+outputs of the compiled reference and the C oracle."""
+import base64
+import random
+import zlib
+
+import pytest
+
+import oracle_lib as ol
+import sccg_b200
+from cases import cases, fasta_cases, rnd
+from emu_lib import emu_context
+
+CASES = cases()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = emu_context()
+    yield c
+    c.close()
+
+
+def unpack(s):
+    return zlib.decompress(base64.b64decode(s))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
+def test_decompress_matches_golden(ctx, case, golden):
+    g = golden["cases"][case.name]
+    inter = unpack(g["intermediate_z"])
+    if g["rc_decompress"] != 0:
+        with pytest.raises(sccg_b200.SccgError) as e:
+            ctx.decompress(case.ref, inter)
+        assert e.value.code in (sccg_b200.SCCG_E_FORMAT, sccg_b200.SCCG_E_BOUNDS)
+        return
+    got = ctx.decompress(case.ref, inter)
+    assert got == unpack(g["reconstructed_z"])
+
+
+def test_fasta_level_goldens(ctx, golden):
+    for fc in fasta_cases():
+        g = golden["fasta_cases"][fc.name]
+        ref = ol.orc_parse_reference_fasta(fc.ref_file)
+        got = ctx.decompress(ref, unpack(g["intermediate_z"]))
+        assert got == unpack(g["reconstructed_z"]), fc.name
+
+
+def make_record_stream(seed):
+    """hand-built record streams: random tokens / literals / N runs / lowercase runs"""
+    r = random.Random(seed)
+    ref = rnd(r.randint(50, 5000), ("rr", seed))
+    body = bytearray(); prev = 0; length = 0
+    for _ in range(r.randint(0, 300)):
+        if r.random() < 0.5:
+            lit = rnd(r.randint(1, 40), ("lit", seed, len(body)), b"ACGTNRYK")
+            body += lit; length += len(lit)
+        else:
+            p = r.randrange(len(ref)); l = r.randint(0, min(700, len(ref) - p))
+            body += b"(%d,%d)" % (p - prev, l); prev = p; length += l
+
+    def runs(total, maxlen):
+        out, pos, prev_s, items = bytearray(), 0, 0, []
+        while pos < total and r.random() < 0.9 and len(items) < 40:
+            s = pos + r.randint(0, max(1, total // 10)); l = r.choice([1, 1, 2, r.randint(1, maxlen)])
+            if s + l > total:
+                break
+            items.append((s, l)); pos = s + l + 1
+        for idx, (s, l) in enumerate(items):
+            last = idx == len(items) - 1
+            if l == 1:
+                out += b"%d" % (s - prev_s) + (b"" if last and r.random() < 0.5 else b",")
+            else:
+                out += b"(%d,%d)" % (s - prev_s, l) + (b"," if r.random() < 0.2 else b"")
+            prev_s = s
+        return bytes(out), sum(l for _, l in items)
+    nlist, nsum = runs(length, 50) if seed % 2 else (b"", 0)
+    low, _ = runs(length + nsum, 300)
+    return ref, bytes(body), nlist, low
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_reconstruct_random_vs_oracle(ctx, seed):
+    ref, body, nlist, low = make_record_stream(seed)
+    rc, exp = ol.orc_reconstruct(ref, body, nlist, low)
+    if rc != 0:
+        with pytest.raises(sccg_b200.SccgError):
+            ctx.reconstruct(ref, body, nlist, low)
+    else:
+        assert ctx.reconstruct(ref, body, nlist, low) == exp
+
+
+def test_reconstruct_errors(ctx):
+    ref = rnd(500, "e")
+    with pytest.raises(sccg_b200.SccgError) as e:
+        ctx.reconstruct(ref, b"(400,200)", b"", b"")                   # decompression.cpp:223-229
+    assert e.value.code == sccg_b200.SCCG_E_BOUNDS
+    for enc in (b"(a,5)", b"(5,)", b"(99999999999,5)", b"AC(7,(503,497)"):   # stoi throws in the reference
+        with pytest.raises(sccg_b200.SccgError) as e:
+            ctx.reconstruct(ref, enc, b"", b"")
+        assert e.value.code == sccg_b200.SCCG_E_FORMAT
+    assert ctx.reconstruct(ref, b"", b"", b"") == b"\n"
+    assert ctx.reconstruct(ref, b"ACGT", b"", b"1,") == b"AcGT\n"

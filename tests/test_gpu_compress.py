@@ -1,0 +1,87 @@
+"""GPU parity tests of the compression path (B200, `-m gpu`): libsccg_b200.so through its C ABI versus
+the committed outputs of the compiled reference (tests/golden) and the C oracle on seeded inputs."""
+import base64
+import random
+import zlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from cases import cases
+from test_emu_compress import _mutated_pair
+
+pytestmark = pytest.mark.gpu
+CASES = cases()
+DUMP = Path(__file__).resolve().parent.parent / "gpurun_out"
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import sccg_b200
+    c = sccg_b200.Context(0)
+    yield c
+    c.close()
+
+
+def _report(name, got, exp):
+    """first difference, written where gpurun brings it back"""
+    DUMP.mkdir(exist_ok=True)
+    n = min(len(got), len(exp))
+    d = next((i for i in range(n) if got[i] != exp[i]), n)
+    msg = f"{name}: len got {len(got)} exp {len(exp)} first diff at {d}\n got: {got[max(0, d - 60):d + 120]!r}\n exp: {exp[max(0, d - 60):d + 120]!r}\n"
+    with open(DUMP / "parity_failures.txt", "a") as f:
+        f.write(msg)
+    return msg
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
+def test_compress_matches_golden(ctx, case, golden):
+    g = golden["cases"][case.name]
+    expect = zlib.decompress(base64.b64decode(g["intermediate_z"]))
+    if case.name == "J_grammar_symbols":
+        pytest.xfail("literal '(' in the target: needs the text-level delta pass (DESIGN.md, known gap)")
+    got, mode = ctx.compress(case.ref, case.tgt, case.header)
+    assert mode == g["mode"]
+    assert got == expect, _report(case.name, got, expect)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_match_sequences_local_vs_oracle(ctx, seed):
+    alphabet = [b"ACGT", b"AC", b"ACGTN", b"A", b"ACGTRYKM"][seed % 5]
+    n = random.Random(seed).randint(1, 1000)
+    ref, tgt = _mutated_pair(("loc", seed), n, alphabet, snp=0.03, indel=0.004)
+    ref, tgt = ref[:1000], tgt[:1000]
+    for k in (14, 10):
+        exp = [(r.p, r.l, r.lit) for r in ol.orc_match_sequences(ref, tgt, k, 0, False, 5000)]
+        got = [(r.p, r.l, r.lit) for r in ctx.match_sequences(ref, tgt, k, 0, False, 5000)]
+        assert got == exp
+
+
+@pytest.mark.parametrize("n,snp", [(5_000_000, 0.001), (3_000_000, 0.02), (1_000_000, 0.10)])
+def test_compress_local_synthetic_vs_oracle(ctx, n, snp):
+    from sccg_genome_compression_b200 import synth
+    ref, tgt = synth.local_pair(n, synth.seed_for(2, 7), snp=snp)
+    ref, tgt = ref.tobytes(), tgt.tobytes()
+    rc, exp, mode = ol.orc_compress(ref, tgt, b">chrS synthetic")
+    assert rc == 0
+    got, gmode = ctx.compress(ref, tgt, b">chrS synthetic")
+    assert gmode == mode
+    assert got == exp, _report(f"local_synth_{n}", got, exp)
+    # same call through the device-resident entry point
+    import torch
+    dr = torch.frombuffer(bytearray(ref), dtype=torch.uint8).cuda()
+    dt = torch.frombuffer(bytearray(tgt), dtype=torch.uint8).cuda()
+    ptr, length, dmode = ctx.compress_device(dr.data_ptr(), len(ref), dt.data_ptr(), len(tgt), b">chrS synthetic")
+    assert dmode == mode and ctx.download(ptr, length) == exp
+
+
+def test_compress_large_local_50mbp(ctx):
+    from sccg_genome_compression_b200 import synth
+    ref, tgt = synth.local_pair(50_000_000, synth.seed_for(2, 3))
+    ref, tgt = ref.tobytes(), tgt.tobytes()
+    rc, exp, mode = ol.orc_compress(ref, tgt, b">chr50")
+    got, gmode = ctx.compress(ref, tgt, b">chr50")
+    assert (gmode, len(got)) == (mode, len(exp))
+    assert got == exp, _report("local_50mbp", got, exp)
