@@ -140,7 +140,9 @@ int sccg_match_sequences(sccg_ctx* c, const char* Sr, int64_t nr, const char* St
     // local: one segment pair through the segment kernel, single pass with the caller's k
     if (nr > SEG || nt > SEG) return set_error(SCCG_E_ARG, "local match_sequences takes one segment pair (<= 1000 symbols each)");
     if (k < K2 || k > 32) return set_error(SCCG_E_ARG, "local match_sequences supports 10 <= k <= 32");
-    u32 *seginfo = nullptr, *matches = nullptr;
+    u32 *seginfo = nullptr, *matches = nullptr, *sc = nullptr;
+    SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
+    SCCG_CK(cudaMemsetAsync(sc, 0, sizeof(u32) * S_COUNT, c->stream));
     SCCG_TRY(buf(c, B_SEGINFO, 2, &seginfo));
     SCCG_TRY(buf(c, B_MATCH, LM_SLOT + 1, &matches));
     int nmatch = 0;
@@ -150,7 +152,7 @@ int sccg_match_sequences(sccg_ctx* c, const char* Sr, int64_t nr, const char* St
         // upper-cased symbols, for which this is the identity
         const size_t smem = sizeof(LmWarpSmem) * LM_WARPS;
         SCCG_SET_MAX_SMEM(seg_match_k, smem);
-        LAUNCH(c, seg_match_k, dim3(1), dim3(LM_WARPS * 32), smem, (const u8*)d_ref, (i64)(nr > 0 ? nr : 0), (const u8*)d_tgt, nt, 1, k, 0, seginfo, matches);
+        LAUNCH(c, seg_match_k, dim3(1), dim3(LM_WARPS * 32), smem, (const u8*)d_ref, (i64)(nr > 0 ? nr : 0), (const u8*)d_tgt, nt, 1, k, 0, seginfo, matches, sc + S_WORK);
         u32 info = 0;
         SCCG_CK(cudaMemcpyAsync(&info, seginfo, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
         SCCG_CK(cudaMemcpyAsync(h_matches, matches, sizeof(u32) * LM_SLOT, cudaMemcpyDeviceToHost, c->stream));

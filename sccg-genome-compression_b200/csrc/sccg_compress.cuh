@@ -9,7 +9,7 @@ namespace sccg {
 // device scalars (u32 each)
 enum Scalar {
     S_LOW_K = 0, S_LOW_KE, S_LOW_TEXT, S_ABORT, S_BODY_MAIN, S_BODY_BASE, S_N_K, S_N_KE, S_N_TEXT,
-    S_G0, S_G1, S_G2, S_G3, S_G4, S_G5, S_G6, S_G7, S_COUNT = 32
+    S_WORK, S_G1, S_G2, S_G3, S_G4, S_G5, S_G6, S_G7, S_COUNT = 32
 };
 
 // writes the separator after the lowercase line and publishes where the body starts
@@ -80,7 +80,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
         unsigned want = div_up(n_iter, LM_WARPS);
         unsigned cap = (unsigned)c->sm_count * 3u;
         unsigned grid = want < cap ? want : cap;
-        LAUNCH(c, seg_match_k, dim3(grid), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, n_iter, K1, K2, seginfo, matches);
+        LAUNCH(c, seg_match_k, dim3(grid), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, n_iter, K1, K2, seginfo, matches, sc + S_WORK);
         SCCG_CK(cudaEventRecord(c->ev[2], c->stream));
         LAUNCH(c, seg_bytes_k, dim3(div_up(n_iter, 256)), dim3(256), 0, (const u32*)seginfo, (const u32*)matches, n_iter, seg_bytes, seg_prev, sc + S_ABORT);
     } else {

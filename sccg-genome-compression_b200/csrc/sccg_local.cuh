@@ -118,7 +118,9 @@ __device__ __forceinline__ int lm_parse(LmWarpSmem& S, int Lr, int Lt, int k, u3
         while (c) {                                                              // :114 every candidate
             int p = (int)c - 1;
             int maxl = (Lr - p) < (Lt - j) ? (Lr - p) : (Lt - j);
-            int l = (p == j) ? diag_lcp(S.mm, j) : warp_lcp(S.r, p, S.t, j, maxl);   // :115 (0-based: also verifies the k-mer)
+            int l = 0;                                                           // :115 (0-based: also verifies the k-mer)
+            if (p == j) l = diag_lcp(S.mm, j);
+            else if (ld_unaligned32(S.r, p) == ld_unaligned32(S.t, j)) l = warp_lcp(S.r, p, S.t, j, maxl);   // hash-chain false positives die here
             if (l >= k) {
                 if (l > best_l) { best_l = l; cnt = 0; zero_in = false; best_key = 0xffffffffu; }   // :127-128
                 if (l == best_l) {                                               // :124-126 as a reduction
@@ -144,9 +146,25 @@ __device__ __forceinline__ int lm_parse(LmWarpSmem& S, int Lr, int Lt, int k, u3
     return nmatch;
 }
 
-// k1 > 0 always; k2 == 0 disables the second pass (function-level match_sequences)
+// raw (not yet upper-cased) 8-byte words of segment `seg`: lane holds words lane, lane+32, lane+64, lane+96
+__device__ __forceinline__ void lm_fetch(const u8* __restrict__ ref, i64 nr, const u8* __restrict__ tgt, i64 nt, int seg, int n_iter, int lane,
+                                         u64 (&rw)[4], u64 (&tw)[4]) {
+    const i64 off = (i64)seg * SEG;
+    const int Lr = seg < n_iter ? (int)((nr - off) < SEG ? (nr - off) : SEG) : 0;
+    const int Lt = seg < n_iter ? (int)((nt - off) < SEG ? (nt - off) : SEG) : 0;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        int b0 = 8 * (lane + 32 * it);
+        rw[it] = b0 < Lr ? __ldg(reinterpret_cast<const u64*>(ref + off + b0)) : 0ull;
+        tw[it] = b0 < Lt ? __ldg(reinterpret_cast<const u64*>(tgt + off + b0)) : 0ull;
+    }
+}
+
+// k1 > 0 always; k2 == 0 disables the second pass (function-level match_sequences).
+// work_counter: device u32, zero before the launch; hands out segments gridDim*warps .. n_iter-1.
 __global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restrict__ ref, i64 nr, const u8* __restrict__ tgt, i64 nt,
-                                                            int n_iter, int k1, int k2, u32* __restrict__ seginfo, u32* __restrict__ matches) {
+                                                            int n_iter, int k1, int k2, u32* __restrict__ seginfo, u32* __restrict__ matches,
+                                                            u32* __restrict__ work_counter) {
     SCCG_DYN_SMEM(smem_raw);
     LmWarpSmem& S = reinterpret_cast<LmWarpSmem*>(smem_raw)[threadIdx.x >> 5];
     const int lane = lane_of();
@@ -162,7 +180,12 @@ __global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restric
         for (int i = 0; i < k2; ++i) { if (lane == k2 - 1 - i) pow2 = x; if (i == k2 - 1) bk1_2 = x; x *= LM_HASH_B; }
     }
 
-    for (int seg = warp_global; seg < n_iter; seg += warps_total) {
+    // segments are claimed dynamically (their cost varies by an order of magnitude) and the next segment's
+    // symbols are fetched into registers while the current one is parsed
+    u64 nrw[4], ntw[4];
+    int seg = warp_global < n_iter ? warp_global : n_iter;
+    lm_fetch(ref, nr, tgt, nt, seg, n_iter, lane, nrw, ntw);
+    while (seg < n_iter) {
         const i64 off = (i64)seg * SEG;
         const int Lr = (int)((nr - off) < SEG ? (nr - off) : SEG);
         const int Lt = (int)((nt - off) < SEG ? (nt - off) : SEG);
@@ -173,9 +196,7 @@ __global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restric
         for (int it = 0; it < 4; ++it) {
             int q = lane + 32 * it;
             int b0 = 8 * q;
-            u64 rw = 0ull, tw = 0ull;
-            if (b0 < Lr) rw = upper8(__ldg(reinterpret_cast<const u64*>(ref + off + b0)));
-            if (b0 < Lt) tw = upper8(__ldg(reinterpret_cast<const u64*>(tgt + off + b0)));
+            u64 rw = upper8(nrw[it]), tw = upper8(ntw[it]);
             reinterpret_cast<u64*>(S.r)[q] = rw;
             reinterpret_cast<u64*>(S.t)[q] = tw;
             u32 mmb = movemask8(nonzero_flags8(rw ^ tw));
@@ -186,6 +207,10 @@ __global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restric
             u32 need = vt >= 8 ? 0xffu : (vt <= 0 ? 0u : ((1u << vt) - 1u));
             if ((movemask8(eq_flags8(tw, 'N')) & need) != need) all_n = 0;
         }
+        int next_seg = 0;
+        if (lane == 0) next_seg = (int)atomicAdd(work_counter, 1u) + warps_total;
+        next_seg = __shfl_sync(SCCG_FULL_MASK, next_seg, 0);
+        lm_fetch(ref, nr, tgt, nt, next_seg, n_iter, lane, nrw, ntw);
         if (lane < 2) reinterpret_cast<u64*>(S.r)[128 + lane] = 0ull, reinterpret_cast<u64*>(S.t)[128 + lane] = 0ull;
         all_n = __all_sync(SCCG_FULL_MASK, all_n);
         __syncwarp();
@@ -217,6 +242,7 @@ __global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restric
             u32 bad = (2 * lit > Lt) ? 1u : 0u;                                  // (float)lit / Lt > 0.5f  :417-419
             seginfo[seg] = (u32)nmatch | ((u32)lit << 8) | ((u32)(all_n ? 1 : 0) << 20) | (bad << 21);
         }
+        seg = next_seg;
     }
 }
 

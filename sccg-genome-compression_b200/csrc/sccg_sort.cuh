@@ -1,0 +1,94 @@
+// Stable LSD radix sort of (u32 key, u32 value) pairs, 8 bits per pass: the reference k-mer index
+// build of global mode (compression.cpp:41-47 over the whole N-stripped reference).
+//   key   = 32-bit hash of the k-mer at position p,  value = p
+// Stable + ascending input order  =>  inside every key the positions stay ascending, which is the
+// reference's per-bucket order (vector<int>::push_back in ascending i).
+// Per pass: histogram (read 4 B/elem), scan of 256 x nblocks counters, scatter (read 8 B, write 8 B).
+#pragma once
+#include "sccg_scan.cuh"
+
+namespace sccg {
+
+static const int RS_WARPS = 8;
+static const int RS_T = RS_WARPS * 32;
+static const int RS_CHUNKS = 16;                    // 32-element chunks per warp
+static const int RS_TILE = RS_T * RS_CHUNKS;        // 4096 elements per block
+
+__global__ void __launch_bounds__(RS_T) rs_hist_k(const u32* __restrict__ keys, i64 n, int shift, u32* __restrict__ hist, unsigned nblocks) {
+    __shared__ u32 h[256];
+    h[threadIdx.x] = 0u;
+    __syncthreads();
+    i64 base = (i64)blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int r = 0; r < RS_CHUNKS; ++r) {
+        i64 i = base + (i64)r * RS_T + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];     // digit-major for the scan
+}
+
+__global__ void __launch_bounds__(RS_T) rs_scatter_k(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in, i64 n, int shift,
+                                                    const u32* __restrict__ offs, unsigned nblocks, u32* __restrict__ keys_out, u32* __restrict__ vals_out) {
+    __shared__ u32 cnt[RS_WARPS][256];              // per-warp digit counts, then running output positions
+    const int lane = lane_of(), w = (int)(threadIdx.x >> 5);
+    for (int x = (int)threadIdx.x; x < RS_WARPS * 256; x += RS_T) (&cnt[0][0])[x] = 0u;
+    __syncthreads();
+    // each warp owns a contiguous sub-tile and walks it in order: chunk c = elements [c*32, c*32+32)
+    const i64 wbase = (i64)blockIdx.x * RS_TILE + (i64)w * (RS_CHUNKS * 32);
+    u32 k[RS_CHUNKS], v[RS_CHUNKS];
+#pragma unroll
+    for (int c = 0; c < RS_CHUNKS; ++c) {
+        i64 i = wbase + c * 32 + lane;
+        bool valid = i < n;
+        k[c] = valid ? keys_in[i] : 0xffffffffu;
+        v[c] = valid ? vals_in[i] : 0u;
+        u32 d = (k[c] >> shift) & 255u;
+        u32 peers = __match_any_sync(SCCG_FULL_MASK, valid ? d : 256u);
+        if (valid && lane == __ffs((int)peers) - 1) cnt[w][d] += (u32)__popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // digit d = threadIdx.x: exclusive prefix over the warps + global offset of (digit, block)
+        u32 run = offs[(size_t)threadIdx.x * nblocks + blockIdx.x];
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ++ww) { u32 t = cnt[ww][threadIdx.x]; cnt[ww][threadIdx.x] = run; run += t; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < RS_CHUNKS; ++c) {
+        i64 i = wbase + c * 32 + lane;
+        bool valid = i < n;
+        u32 d = (k[c] >> shift) & 255u;
+        u32 peers = __match_any_sync(SCCG_FULL_MASK, valid ? d : 256u);
+        u32 below = peers & ((1u << lane) - 1u);
+        if (valid) {
+            u32 pos = cnt[w][d] + (u32)__popc(below);
+            keys_out[pos] = k[c];
+            vals_out[pos] = v[c];
+        }
+        __syncwarp();
+        if (valid && lane == __ffs((int)peers) - 1) cnt[w][d] += (u32)__popc(peers);
+        __syncwarp();
+    }
+}
+
+// sorts (keys, vals) of length n by key; the result ends up in (keys, vals); (keys2, vals2) is scratch of the same size
+static int radix_sort_pairs(sccg_ctx* c, u32* keys, u32* vals, u32* keys2, u32* vals2, i64 n, int slot_hist) {
+    if (n <= 1) return SCCG_OK;
+    unsigned nblocks = div_up(n, RS_TILE);
+    u32* hist = nullptr;
+    SCCG_TRY(buf(c, slot_hist, (size_t)nblocks * 256 + 1, &hist));
+    u32 *ki = keys, *vi = vals, *ko = keys2, *vo = vals2;
+    for (int pass = 0; pass < 4; ++pass) {
+        int shift = pass * 8;
+        LAUNCH(c, rs_hist_k, dim3(nblocks), dim3(RS_T), 0, (const u32*)ki, n, shift, hist, nblocks);
+        SCCG_TRY(scan_exclusive_u32(c, hist, hist, (i64)nblocks * 256, nullptr));
+        LAUNCH(c, rs_scatter_k, dim3(nblocks), dim3(RS_T), 0, (const u32*)ki, (const u32*)vi, n, shift, (const u32*)hist, nblocks, ko, vo);
+        u32* t = ki; ki = ko; ko = t;
+        t = vi; vi = vo; vo = t;
+    }
+    return SCCG_OK;          // 4 passes: the data is back in (keys, vals)
+}
+
+}  // namespace sccg
