@@ -1,11 +1,489 @@
+// Global mode (compression.cpp:484-574): N-run extraction, N-stripping, reference k-mer index and
+// the stateful banded greedy parse  match_sequences(ref, tgt, k = 14, m = 100, global = true)  (:561).
+//
+//   index   : hash32 of every reference k-mer + stable radix sort  ->  (key, position) sorted by key,
+//             positions ascending inside a key (the reference's bucket order, :41-47)
+//   parse   : one persistent CTA walks the state (index, prev_match_end) exactly like :64-161.
+//             * until the first match (prev_match_end == -1, every candidate is "in range") and in the
+//               `pn2 == 0` fall-through (:134) candidates come from the sorted index (binary search);
+//             * otherwise only candidates with |p - prev_match_end| <= m can be used (:83-96, :116), i.e.
+//               the k-mers of a 2m+1 window of the reference: the CTA stages that window in shared
+//               memory, hashes it into a small filter and scans the target forward 1 position per
+//               thread until a position hits the window ("no k-mer" and "no candidate in range" are
+//               the same literal step, :77-81 vs :92-96).
+//             * candidate selection is the order-independent form of the ascending-p fold (:114-130).
+//   writer  : tokens "(dp,l)" with the delta chain of delta_encode (:258-292) + literal gaps.
 #pragma once
 #include "sccg_compress.cuh"
+#include "sccg_strip.cuh"
+#include "sccg_sort.cuh"
+
 namespace sccg {
+
+static const int GP_T = 512;                 // threads of the parse CTA
+static const int GP_MAX_M = 120;             // window = 2m+1 <= 241 positions
+static const int GP_WIN_BYTES = 288;
+static const int GP_FILTER = 512;
+static const int GP_SHORT = 64;              // per-thread extension before the block-wide one takes over
+
+__device__ __forceinline__ u64 ld_unaligned64(const u8* p) {
+    uintptr_t a = (uintptr_t)p;
+    const u64* q = reinterpret_cast<const u64*>(a & ~(uintptr_t)7);
+    u32 sh = (u32)(a & 7) * 8u;
+    u64 lo = q[0];
+    if (sh == 0) return lo;
+    return (lo >> sh) | (q[1] << (64u - sh));
+}
+
+// 32-bit hash of the k-mer s[0..k), 8 <= k <= 16; the words may come from global or shared memory
+__device__ __forceinline__ u32 kmer_hash_words(u64 w0, u64 w1, int k) {
+    if (k < 16) w1 &= (k == 8) ? 0ull : (~0ull >> (8 * (16 - k)));
+    u64 x = (w0 * 0x9E3779B97F4A7C15ULL) ^ ((w1 + 0x632BE59BD9B4E019ULL) * 0xD6E8FEB86659FD93ULL);
+    x ^= x >> 29;
+    x *= 0x94D049BB133111EBULL;
+    return (u32)(x >> 32);
+}
+__device__ __forceinline__ bool kmer_equal_words(u64 a0, u64 a1, u64 b0, u64 b1, int k) {
+    u64 m1 = (k == 8) ? 0ull : (k < 16 ? (~0ull >> (8 * (16 - k))) : ~0ull);
+    return a0 == b0 && ((a1 ^ b1) & m1) == 0ull;
+}
+
+__global__ void __launch_bounds__(256) kmer_keys_k(const u8* __restrict__ R, i64 nk, int k, u32* __restrict__ keys, u32* __restrict__ vals) {
+    i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nk) return;
+    keys[p] = kmer_hash_words(ld_unaligned64(R + p), ld_unaligned64(R + p + 8), k);
+    vals[p] = (u32)p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the persistent parse CTA
+// ------------------------------------------------------------------------------------------------
+struct GpShared {
+    u8 win[GP_WIN_BYTES];
+    u32 f_hash[GP_FILTER];
+    u8 f_off[GP_FILTER];
+    int i_scratch[8];
+    unsigned long long key_scratch;
+    int long_list[GP_T];
+    int long_n;
+    // accumulators of the candidate fold
+    int best_l, cnt, zero_in;
+    unsigned long long best_key;
+};
+
+struct GpArgs {
+    const u8* R; i64 nr;          // N-stripped, upper-cased reference
+    const u8* T; i64 nt;          // N-stripped, upper-cased target
+    const u32* keys; const u32* vals; i64 nk;
+    int k, m;
+    int* m_tpos; int* m_p; int* m_l;   // out: matches
+    u32* d_count;                      // out: number of matches
+};
+
+// length of the common prefix of R[p..] and T[j..], capped at cap (cap <= remaining lengths)
+__device__ __forceinline__ int serial_lcp(const u8* __restrict__ R, i64 p, const u8* __restrict__ T, i64 j, int cap) {
+    int l = 0;
+    while (l < cap) {
+        u64 d = ld_unaligned64(R + p + l) ^ ld_unaligned64(T + j + l);
+        if (d) { l += (__ffsll((long long)d) - 1) >> 3; break; }
+        l += 8;
+    }
+    return l < cap ? l : cap;
+}
+
+// block-wide: min(maxl, lcp(R[p..], T[j..])) ; all threads, uniform arguments
+__device__ __forceinline__ i64 block_lcp(GpShared& S, const u8* __restrict__ R, i64 p, const u8* __restrict__ T, i64 j, i64 maxl) {
+    for (i64 base = 0; base < maxl; base += (i64)GP_T * 8) {
+        i64 o = base + (i64)threadIdx.x * 8;
+        int mis = -1;                                            // offset of the first mismatch inside my 8 bytes
+        if (o >= maxl) mis = 0;
+        else {
+            u64 d = ld_unaligned64(R + p + o) ^ ld_unaligned64(T + j + o);
+            if (d) mis = (__ffsll((long long)d) - 1) >> 3;
+        }
+        if (threadIdx.x == 0) S.i_scratch[0] = 0x7fffffff;
+        if (__syncthreads_or(mis >= 0)) {
+            if (mis >= 0) atomicMin(&S.i_scratch[0], (int)threadIdx.x * 8 + mis);
+            __syncthreads();
+            i64 l = base + S.i_scratch[0];
+            __syncthreads();
+            return l < maxl ? l : maxl;
+        }
+    }
+    return maxl;
+}
+
+__device__ __forceinline__ void fold_reset(GpShared& S) {
+    if (threadIdx.x == 0) { S.best_l = 0; S.cnt = 0; S.zero_in = 0; S.best_key = ~0ull; }
+    __syncthreads();
+}
+
+// merges one chunk of candidates (one per thread, p < 0 = none) into the fold accumulators: the order-independent
+// form of compression.cpp:114-130 (max length; ties: nearest to prev_match_end, then smaller p; p == 0 is "unset")
+__device__ __forceinline__ void fold_chunk(GpShared& S, const GpArgs& a, i64 p, i64 j, int e) {
+    int my_l = 0;
+    bool is_long = false;
+    if (p >= 0) {
+        i64 maxl = (a.nr - p) < (a.nt - j) ? (a.nr - p) : (a.nt - j);
+        int cap = maxl < GP_SHORT ? (int)maxl : GP_SHORT;
+        int l = serial_lcp(a.R, p, a.T, j, cap);                 // extend_alignment :27-34 (from offset 0: verifies the k-mer too)
+        if (l >= a.k) { my_l = l; is_long = (l == GP_SHORT && maxl > GP_SHORT); }
+    }
+    if (threadIdx.x == 0) S.long_n = 0;
+    int n_long = __syncthreads_count(is_long);
+    if (n_long) {
+        if (is_long) S.long_list[atomicAdd(&S.long_n, 1)] = (int)threadIdx.x;
+        __syncthreads();
+        for (int i = 0; i < n_long; ++i) {
+            int owner = S.long_list[i];
+            if ((int)threadIdx.x == owner) { S.i_scratch[2] = (int)(p & 0xffffffff); S.i_scratch[3] = (int)(p >> 32); }
+            __syncthreads();
+            i64 pp = ((i64)S.i_scratch[3] << 32) | (u32)S.i_scratch[2];
+            i64 maxl = (a.nr - pp) < (a.nt - j) ? (a.nr - pp) : (a.nt - j);
+            i64 l = GP_SHORT + block_lcp(S, a.R, pp + GP_SHORT, a.T, j + GP_SHORT, maxl - GP_SHORT);
+            if ((int)threadIdx.x == owner) my_l = (int)l;
+        }
+    }
+    // chunk maximum
+    if (threadIdx.x == 0) S.i_scratch[1] = 0;
+    __syncthreads();
+    if (my_l > 0) atomicMax(&S.i_scratch[1], my_l);
+    __syncthreads();
+    int cm = S.i_scratch[1];
+    if (cm == 0) return;
+    if (threadIdx.x == 0 && cm > S.best_l) { S.best_l = cm; S.cnt = 0; S.zero_in = 0; S.best_key = ~0ull; }
+    __syncthreads();
+    if (cm == S.best_l) {
+        bool is = my_l == cm;
+        if (is) {
+            atomicAdd(&S.cnt, 1);
+            if (p == 0) S.zero_in = 1;
+            else {
+                i64 d = p - (i64)e; if (d < 0) d = -d;
+                atomicMin(&S.best_key, ((unsigned long long)d << 32) | (unsigned long long)(u32)p);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// every candidate of the k-mer T[j..j+k) from the sorted index folded with prev_match_end = e (pn1 / ln1 of :124-129)
+__device__ __forceinline__ void fold_index_candidates(GpShared& S, const GpArgs& a, i64 j, int e) {
+    fold_reset(S);
+    u32 h = kmer_hash_words(ld_unaligned64(a.T + j), ld_unaligned64(a.T + j + 8), a.k);
+    i64 lo = 0, hi = a.nk;                                       // lower_bound(keys, h): uniform, every thread computes it
+    while (lo < hi) { i64 mid = (lo + hi) >> 1; if (a.keys[mid] < h) lo = mid + 1; else hi = mid; }
+    for (i64 base = lo;; base += GP_T) {
+        i64 idx = base + threadIdx.x;
+        bool valid = idx < a.nk && a.keys[idx] == h;
+        fold_chunk(S, a, valid ? (i64)a.vals[idx] : -1, j, e);
+        if (!__syncthreads_and(valid)) break;                    // the key range ended inside this chunk
+    }
+}
+
+__device__ __forceinline__ int fold_result_p(const GpShared& S) {
+    return (S.cnt == 1 && S.zero_in) ? 0 : (int)(S.best_key & 0xffffffffULL);
+}
+
+__global__ void __launch_bounds__(GP_T) global_parse_k(GpArgs a) {
+    __shared__ GpShared S;
+    const int tid = (int)threadIdx.x;
+    const int k = a.k;
+    i64 j = 0;
+    int e = -1;                                                   // prev_match_end :51
+    u32 nmatch = 0;
+    const i64 last_j = a.nt - k;                                  // loop: index < L - k + 1  (:64)
+
+    while (j <= last_j) {
+        int sel_p = 0, sel_l = 0;
+        if (e == -1) {
+            // ---- no match yet: first position whose k-mer occurs anywhere in the reference (:77, all candidates in range :87)
+            i64 found = -1;
+            for (; j <= last_j; j += GP_T) {
+                i64 pos = j + tid;
+                bool hit = false;
+                if (pos <= last_j) {
+                    u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
+                    u32 h = kmer_hash_words(w0, w1, k);
+                    i64 lo = 0, hi = a.nk;
+                    while (lo < hi) { i64 mid = (lo + hi) >> 1; if (a.keys[mid] < h) lo = mid + 1; else hi = mid; }
+                    for (; lo < a.nk && a.keys[lo] == h && !hit; ++lo) {
+                        const u8* rp = a.R + a.vals[lo];
+                        hit = kmer_equal_words(ld_unaligned64(rp), ld_unaligned64(rp + 8), w0, w1, k);
+                    }
+                }
+                if (tid == 0) S.i_scratch[4] = 0x7fffffff;
+                if (__syncthreads_or(hit)) {
+                    if (hit) atomicMin(&S.i_scratch[4], tid);
+                    __syncthreads();
+                    found = j + S.i_scratch[4];
+                    __syncthreads();
+                    break;
+                }
+            }
+            if (found < 0) break;
+            j = found;
+            fold_index_candidates(S, a, j, e);
+            sel_p = fold_result_p(S); sel_l = S.best_l;
+            __syncthreads();
+        } else {
+            // ---- banded state: candidates must satisfy |p - e| <= m (:87, :116)
+            i64 wlo = (i64)e - a.m; if (wlo < 0) wlo = 0;
+            i64 whi = (i64)e + a.m; if (whi > a.nr - k) whi = a.nr - k;
+            if (whi < wlo) break;                                 // no reference k-mer can ever be in range again
+            const int wlen = (int)(whi - wlo + 1);
+            const int wbytes = wlen + k - 1;
+            for (int x = tid; x < GP_FILTER; x += GP_T) S.f_hash[x] = 0u;
+            for (int x = tid; x < GP_WIN_BYTES; x += GP_T) S.win[x] = x < wbytes ? a.R[wlo + x] : (u8)0;
+            __syncthreads();
+            if (tid < wlen) {
+                u32 h = kmer_hash_words(ld_unaligned64(S.win + tid), ld_unaligned64(S.win + tid + 8), k) | 1u;
+                u32 slot = (h >> 1) & (GP_FILTER - 1);
+                while (atomicCAS(&S.f_hash[slot], 0u, h) != 0u) slot = (slot + 1) & (GP_FILTER - 1);
+                S.f_off[slot] = (u8)tid;
+            }
+            __syncthreads();
+            // scan the target for the first position whose k-mer is in the window; everything before it is literal (:77-96)
+            i64 found = -1;
+            for (; j <= last_j; j += GP_T) {
+                i64 pos = j + tid;
+                bool hit = false;
+                if (pos <= last_j) {
+                    u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
+                    u32 h = kmer_hash_words(w0, w1, k) | 1u;
+                    u32 slot = (h >> 1) & (GP_FILTER - 1);
+                    for (u32 fh; (fh = S.f_hash[slot]) != 0u && !hit; slot = (slot + 1) & (GP_FILTER - 1)) {
+                        if (fh == h) {
+                            const u8* wp = S.win + S.f_off[slot];
+                            hit = kmer_equal_words(ld_unaligned64(wp), ld_unaligned64(wp + 8), w0, w1, k);
+                        }
+                    }
+                }
+                if (tid == 0) S.i_scratch[4] = 0x7fffffff;
+                if (__syncthreads_or(hit)) {
+                    if (hit) atomicMin(&S.i_scratch[4], tid);
+                    __syncthreads();
+                    found = j + S.i_scratch[4];
+                    __syncthreads();
+                    break;
+                }
+            }
+            if (found < 0) break;
+            j = found;
+            // in-range candidates: the window positions whose k-mer equals T[j..j+k)  (pn2 / ln2, :116-123)
+            i64 cand = -1;
+            if (tid < wlen) {
+                u64 w0 = ld_unaligned64(a.T + j), w1 = ld_unaligned64(a.T + j + 8);
+                if (kmer_equal_words(ld_unaligned64(S.win + tid), ld_unaligned64(S.win + tid + 8), w0, w1, k)) cand = wlo + tid;
+            }
+            fold_reset(S);
+            fold_chunk(S, a, cand, j, e);
+            sel_p = fold_result_p(S); sel_l = S.best_l;
+            __syncthreads();
+            if (sel_p == 0) {                                     // `pn2 != 0` fails (:134): unrestricted best over ALL candidates
+                fold_index_candidates(S, a, j, e);
+                sel_p = fold_result_p(S); sel_l = S.best_l;
+                __syncthreads();
+            }
+        }
+        if (tid == 0) { a.m_tpos[nmatch] = (int)j; a.m_p[nmatch] = sel_p; a.m_l[nmatch] = sel_l; }   // :152-156
+        ++nmatch;
+        e = sel_p + sel_l - 1;                                    // :149
+        j += sel_l;                                               // :159
+    }
+    if (tid == 0) *a.d_count = nmatch;
+}
+
+// ------------------------------------------------------------------------------------------------
+// record writer for one long parse (compression.cpp:564-573 + delta_encode :258-292)
+// ------------------------------------------------------------------------------------------------
+// bytes[i] = literal gap before match i + its token
+__global__ void g_match_bytes_k(const int* __restrict__ tpos, const int* __restrict__ mp, const int* __restrict__ ml, u32 M, u32* __restrict__ bytes) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    int prev_end = i ? tpos[i - 1] + ml[i - 1] : 0;
+    int prev_p = i ? mp[i - 1] : 0;
+    bytes[i] = (u32)(tpos[i] - prev_end) + 3u + (u32)dec_len_i32(mp[i] - prev_p) + (u32)dec_len_u32((u32)ml[i]);
+}
+__global__ void g_write_tokens_k(const int* __restrict__ tpos, const int* __restrict__ mp, const int* __restrict__ ml, u32 M, const u32* __restrict__ offs,
+                                 u8* __restrict__ out, const u32* __restrict__ d_body_base) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    int prev_end = i ? tpos[i - 1] + ml[i - 1] : 0;
+    int prev_p = i ? mp[i - 1] : 0;
+    write_token(out + *d_body_base + offs[i] + (u32)(tpos[i] - prev_end), mp[i] - prev_p, ml[i]);
+}
+// literal symbols: every target position not covered by a match; 16 positions per thread
+__global__ void __launch_bounds__(256) g_write_literals_k(const u8* __restrict__ T, i64 nt, const int* __restrict__ tpos, const int* __restrict__ ml, u32 M,
+                                                         const u32* __restrict__ offs, const u32* __restrict__ d_tok_total, u8* __restrict__ out,
+                                                         const u32* __restrict__ d_body_base) {
+    i64 x0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (x0 >= nt) return;
+    u8* body = out + *d_body_base;
+    // i = number of matches starting at or before x
+    int lo = 0, hi = (int)M;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if ((i64)tpos[mid] <= x0) lo = mid + 1; else hi = mid; }
+    int i = lo;
+    for (int d = 0; d < 16 && x0 + d < nt; ++d) {
+        i64 x = x0 + d;
+        while (i < (int)M && (i64)tpos[i] <= x) ++i;
+        i64 gap_start = i ? (i64)tpos[i - 1] + ml[i - 1] : 0;
+        if (x < gap_start) continue;                              // inside match i-1
+        u32 o = (i < (int)M ? offs[i] : *d_tok_total) + (u32)(x - gap_start);
+        body[o] = T[x];
+    }
+}
+
+// match_sequences(ref, tgt, k, m, true) on device-resident, already prepared sequences.  Leaves the matches in
+// (m_tpos, m_p, m_l) and their number in *h_count.
+struct GlobalMatches { int* tpos; int* p; int* l; u32 count; };
+
+static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i64 nt, int k, int m, u32* sc, GlobalMatches* out) {
+    if (k < 8 || k > 16) return set_error(SCCG_E_ARG, "global match_sequences supports 8 <= k <= 16");
+    if (m < 0 || m > GP_MAX_M) return set_error(SCCG_E_ARG, "global match_sequences supports 0 <= m <= 120");
+    const i64 nk = nr - k + 1 > 0 ? nr - k + 1 : 0;
+    u32 *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr;
+    SCCG_TRY(buf(c, B_GKEYS, (size_t)nk + 1, &keys));
+    SCCG_TRY(buf(c, B_GVALS, (size_t)nk + 1, &vals));
+    SCCG_TRY(buf(c, B_GKEYS2, (size_t)nk + 1, &keys2));
+    SCCG_TRY(buf(c, B_GVALS2, (size_t)nk + 1, &vals2));
+    if (nk > 0) {
+        LAUNCH(c, kmer_keys_k, dim3(div_up(nk, 256)), dim3(256), 0, R, nk, k, keys, vals);
+        SCCG_TRY(radix_sort_pairs(c, keys, vals, keys2, vals2, nk, B_GHIST));
+    }
+    const size_t cap = (size_t)(nt / k) + 2;
+    int* mbuf = nullptr;
+    SCCG_TRY(buf(c, B_GREC, cap * 3, &mbuf));
+    GpArgs a;
+    a.R = R; a.nr = nr; a.T = T; a.nt = nt; a.keys = keys; a.vals = vals; a.nk = nk; a.k = k; a.m = m;
+    a.m_tpos = mbuf; a.m_p = mbuf + cap; a.m_l = mbuf + 2 * cap; a.d_count = sc + S_G1;
+    LAUNCH(c, global_parse_k, dim3(1), dim3(GP_T), 0, a);
+    u32 h[S_COUNT];
+    SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
+    out->tpos = a.m_tpos; out->p = a.m_p; out->l = a.m_l; out->count = h[S_G1];
+    return SCCG_OK;
+}
+
 static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt, i64 nt, const char* header, i64 nh,
                                   u32 low_k, const u32* cnt_s, const u32* cnt_e, CompressResult* res) {
-    return set_error(SCCG_E_ARG, "global mode not implemented yet");
+    u32* sc = nullptr;
+    SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
+    // ---- N runs of the upper-cased target, original coordinates (:527-554): count
+    u32 *ncnt_s = nullptr, *ncnt_e = nullptr;
+    SCCG_TRY(rle_count<1>(c, d_tgt, nt, B_NRUN_CNT, &ncnt_s, &ncnt_e, sc + S_N_K, sc + S_N_KE));
+    // ---- toupper + erase every 'N' from both sequences (:523-524, :556-557)
+    u8 *R2 = nullptr, *T2 = nullptr;
+    SCCG_TRY(buf(c, B_GREF, (size_t)nr + 64, &R2));
+    SCCG_TRY(buf(c, B_GTGT, (size_t)nt + 64, &T2));
+    i64 nr2 = 0, nt2 = 0;
+    SCCG_TRY(strip_n<1>(c, d_ref, nr, R2, B_TILE3, sc + S_G2, &nr2));
+    SCCG_TRY(strip_n<1>(c, d_tgt, nt, T2, B_TILE3, sc + S_G3, &nt2));
+    SCCG_CK(cudaMemsetAsync(R2 + nr2, 0, 64, c->stream));          // unaligned word loads run up to 15 B past the end
+    SCCG_CK(cudaMemsetAsync(T2 + nt2, 0, 64, c->stream));
+    u32 h[S_COUNT];
+    SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
+    if (h[S_N_K] != h[S_N_KE]) return set_error(SCCG_E_CUDA, "internal: N-run start/end counts differ");
+    const u32 n_k = h[S_N_K];
+
+    // ---- the global parse (:561)
+    SCCG_CK(cudaEventRecord(c->ev[1], c->stream));
+    GlobalMatches gm;
+    SCCG_TRY(global_match_device(c, R2, nr2, T2, nt2, K1, GLOBAL_M, sc, &gm));
+    SCCG_CK(cudaEventRecord(c->ev[2], c->stream));
+    const u32 M = gm.count;
+
+    // ---- sizes
+    u32* mbytes = nullptr;
+    SCCG_TRY(buf(c, B_GTMP0, (size_t)M + 1, &mbytes));
+    if (M) LAUNCH(c, g_match_bytes_k, dim3(div_up(M, 256)), dim3(256), 0, (const int*)gm.tpos, (const int*)gm.p, (const int*)gm.l, M, mbytes);
+    SCCG_TRY(scan_exclusive_u32(c, mbytes, mbytes, (i64)M, sc + S_G4));
+    u32 last[3] = {0, 0, 0};                                      // end of the last match in the target
+    if (M) {
+        SCCG_CK(cudaMemcpyAsync(&last[0], gm.tpos + (M - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        SCCG_CK(cudaMemcpyAsync(&last[1], gm.l + (M - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    }
+    SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
+    const i64 trailing = nt2 - ((i64)last[0] + (i64)last[1]);
+    const u64 body_bytes = (u64)h[S_G4] + (u64)trailing;
+
+    // ---- assemble "<header>\n<lowercase runs>\n<N runs>\n<body>"
+    const size_t hdr_bytes = nh > 0 ? (size_t)nh + 1 : 0;
+    const size_t cap = hdr_bytes + 24ull * low_k + 1 + 24ull * n_k + 1 + body_bytes;
+    if (cap >= 0xffffffffull) return set_error(SCCG_E_ARG, "encoded output would exceed 4 GiB");
+    u8* out = nullptr;
+    SCCG_TRY(buf(c, B_OUT, cap + 16, &out));
+    SCCG_TRY(write_header(c, out, header, nh));
+    int *run_s = nullptr, *run_e = nullptr, *nrun_s = nullptr, *nrun_e = nullptr;
+    SCCG_TRY(rle_emit<0>(c, d_tgt, nt, low_k, cnt_s, cnt_e, sc + S_LOW_K, B_RUN_START, B_RUN_END, B_RUN_BYTES, &run_s, &run_e,
+                         out + hdr_bytes, sc + S_LOW_TEXT));
+    // the N-run text goes right after "<low>\n": its position depends on the (device-side) length of the lowercase text
+    u8* ntext = nullptr;
+    SCCG_TRY(buf(c, B_NRUN_TEXT, 24ull * n_k + 16, &ntext));
+    SCCG_TRY(rle_emit<1>(c, d_tgt, nt, n_k, ncnt_s, ncnt_e, sc + S_N_K, B_NRUN_START, B_NRUN_END, B_NRUN_BYTES, &nrun_s, &nrun_e,
+                         ntext, sc + S_N_TEXT));
+    LAUNCH(c, put_separators_k, dim3(1), dim3(1), 0, out, (u32)hdr_bytes, sc, 1);
+    SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
+    const u32 low_text = h[S_LOW_TEXT], n_text = h[S_N_TEXT];
+    if (n_text) SCCG_CK(cudaMemcpyAsync(out + hdr_bytes + low_text + 1, ntext, n_text, cudaMemcpyDeviceToDevice, c->stream));
+    if (M) LAUNCH(c, g_write_tokens_k, dim3(div_up(M, 256)), dim3(256), 0, (const int*)gm.tpos, (const int*)gm.p, (const int*)gm.l, M,
+                  (const u32*)mbytes, out, (const u32*)(sc + S_BODY_BASE));
+    if (nt2 > 0) LAUNCH(c, g_write_literals_k, dim3(div_up(nt2, 256 * 16)), dim3(256), 0, (const u8*)T2, nt2, (const int*)gm.tpos, (const int*)gm.l, M,
+                        (const u32*)mbytes, (const u32*)(sc + S_G4), out, (const u32*)(sc + S_BODY_BASE));
+    SCCG_CK(cudaEventRecord(c->ev[3], c->stream));
+    SCCG_CK(cudaStreamSynchronize(c->stream));
+    res->d_out = out;
+    res->out_len = (i64)hdr_bytes + low_text + 1 + n_text + 1 + (i64)body_bytes;
+    res->mode = 1;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); c->prof.kernels_ms = ms;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->prof.match_ms = ms;
+    c->prof.serialize_ms = c->prof.kernels_ms - c->prof.match_ms;
+    c->prof.mode = 1;
+    return SCCG_OK;
 }
+
+// function-level match_sequences(Sr, St, k, m, global = true, offset): sequences are used as given (:561 passes
+// upper-cased, N-free strings); records go back to the host as struct-of-arrays
 static int match_sequences_global(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt, i64 nt, const char* h_tgt, int k, int m, int offset, sccg_records* out) {
-    return set_error(SCCG_E_ARG, "global mode not implemented yet");
+    u32* sc = nullptr;
+    SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
+    SCCG_CK(cudaMemsetAsync(sc, 0, sizeof(u32) * S_COUNT, c->stream));
+    SCCG_CK(cudaMemsetAsync((void*)(d_ref + nr), 0, 64, c->stream));
+    SCCG_CK(cudaMemsetAsync((void*)(d_tgt + nt), 0, 64, c->stream));
+    GlobalMatches gm;
+    SCCG_TRY(global_match_device(c, d_ref, nr, d_tgt, nt, k, m, sc, &gm));
+    const u32 M = gm.count;
+    int* hm = (int*)malloc(sizeof(int) * 3 * (size_t)(M + 1));
+    if (!hm) return set_error(SCCG_E_NOMEM, "out of host memory");
+    if (M) {
+        cudaMemcpyAsync(hm, gm.tpos, sizeof(int) * M, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(hm + M, gm.p, sizeof(int) * M, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(hm + 2 * (size_t)M, gm.l, sizeof(int) * M, cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { free(hm); return set_error(SCCG_E_CUDA, "download of the matches failed"); }
+    int64_t cap = 2 * (int64_t)M + 2;
+    out->p = (int32_t*)malloc(sizeof(int32_t) * (size_t)cap);
+    out->l = (int32_t*)malloc(sizeof(int32_t) * (size_t)cap);
+    out->lit_off = (int64_t*)malloc(sizeof(int64_t) * (size_t)(cap + 1));
+    out->lits = (char*)malloc((size_t)nt + 1);
+    if (!out->p || !out->l || !out->lit_off || !out->lits) { free(hm); sccg_records_free(out); return set_error(SCCG_E_NOMEM, "out of host memory"); }
+    int64_t n = 0, lit = 0, pos = 0;
+    for (u32 i = 0; i <= M; ++i) {
+        int64_t tpos = i < M ? hm[i] : nt;
+        if (tpos > pos) {
+            out->p[n] = -1; out->l[n] = 0; out->lit_off[n] = lit;
+            memcpy(out->lits + lit, h_tgt + pos, (size_t)(tpos - pos));
+            lit += tpos - pos; ++n;
+        }
+        if (i < M) {
+            out->p[n] = hm[M + i] + offset; out->l[n] = hm[2 * (size_t)M + i]; out->lit_off[n] = lit; ++n;
+            pos = tpos + hm[2 * (size_t)M + i];
+        }
+    }
+    out->lit_off[n] = lit;
+    out->n = n;
+    free(hm);
+    return SCCG_OK;
 }
-}
+
+}  // namespace sccg

@@ -105,6 +105,18 @@ void block_barrier() {
     while (b->bar_gen == gen) yield();
 }
 
+int block_barrier_count(int pred) {
+    BlockCtx* b = g_blk;
+    unsigned gen = b->bar_gen;
+    int slot = (int)(gen & 1u);
+    if (b->bar_count == 0) b->bar_red[slot] = 0;          // first arriver of this generation
+    if (pred) b->bar_red[slot]++;
+    b->progress++;
+    if (++b->bar_count == b->alive) { b->bar_count = 0; b->bar_gen++; return b->bar_red[slot]; }
+    while (b->bar_gen == gen) yield();
+    return b->bar_red[slot];
+}
+
 // ---- per-worker resources ----
 struct Worker {
     BlockCtx ctx;

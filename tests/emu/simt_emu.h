@@ -74,6 +74,7 @@ struct BlockCtx {
     void* sched_sp = nullptr;
     int bar_count = 0;
     unsigned bar_gen = 0;
+    int bar_red[2] = {0, 0};      // __syncthreads_count / _or / _and accumulators, indexed by barrier generation parity
     Slot slots[32][4];
     unsigned long long progress = 0;
     unsigned char* dyn_smem = nullptr;
@@ -86,6 +87,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
 Slot* collective_arrive(uint32_t mask, uint64_t val);   // blocks until every lane of mask arrived
 void collective_release(Slot* s);
 void block_barrier();
+int block_barrier_count(int pred);
 [[noreturn]] void fail(const char* msg);
 
 inline int lane_id() { return g_blk->cur->linear & 31; }
@@ -106,6 +108,9 @@ template <typename T> inline T from_bits(uint64_t b) { T v; memcpy(&v, &b, sizeo
 // synchronisation + warp collectives
 // ------------------------------------------------------------------------------------------------
 inline void __syncthreads() { emu::block_barrier(); }
+inline int __syncthreads_count(int pred) { return emu::block_barrier_count(pred); }
+inline int __syncthreads_or(int pred) { return emu::block_barrier_count(pred) != 0; }
+inline int __syncthreads_and(int pred) { return emu::block_barrier_count(!pred) == 0; }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::Slot* s = emu::collective_arrive(mask, 0); emu::collective_release(s); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
@@ -150,6 +155,14 @@ inline unsigned __ballot_sync(unsigned mask, int pred) {
     emu::Slot* s = emu::collective_arrive(mask, pred ? 1 : 0);
     unsigned r = 0;
     for (int i = 0; i < 32; ++i) if (((mask >> i) & 1u) && s->vals[i]) r |= 1u << i;
+    emu::collective_release(s);
+    return r;
+}
+template <typename T> inline unsigned __match_any_sync(unsigned mask, T v) {
+    emu::Slot* s = emu::collective_arrive(mask, emu::to_bits(v));
+    uint64_t mine = emu::to_bits(v);
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) if (((mask >> i) & 1u) && s->vals[i] == mine) r |= 1u << i;
     emu::collective_release(s);
     return r;
 }

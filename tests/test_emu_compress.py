@@ -102,3 +102,53 @@ def test_many_segments_scan_paths(ctx):
     rc, exp, mode = ol.orc_compress(ref, tgt, b">big")
     got, gmode = ctx.compress(ref, tgt, b">big")
     assert (gmode, got) == (mode, exp)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_match_sequences_global_vs_oracle(ctx, seed, sweep_order):
+    """banded global parse incl. lost state, chance re-syncs, repeats (2-letter alphabet) and the pn2 == 0 quirk region"""
+    alphabet = [b"ACGT", b"ACGT", b"AC", b"ACGT"][seed % 4]
+    n = 12000 if alphabet == b"ACGT" else 2500
+    ref, tgt = _mutated_pair(("glob", seed), n, alphabet, snp=0.01, indel=0.002)
+    r = random.Random(seed)
+    if seed % 2:
+        cut = sorted(r.sample(range(len(tgt)), 4))
+        parts = [tgt[:cut[0]], tgt[cut[0]:cut[1]], tgt[cut[1]:cut[2]], tgt[cut[2]:cut[3]], tgt[cut[3]:]]
+        r.shuffle(parts)
+        tgt = b"".join(parts)
+    if seed % 3 == 0:
+        tgt = rnd(r.randint(1, 700), ("pre", seed)) + tgt        # unrelated prefix: long first-match search
+    exp = [(x.p, x.l, x.lit) for x in ol.orc_match_sequences(ref, tgt, 14, 100, True, 0)]
+    got = [(x.p, x.l, x.lit) for x in ctx.match_sequences(ref, tgt, 14, 100, True, 0)]
+    assert got == exp
+
+
+@pytest.mark.parametrize("k,m", [(8, 0), (10, 5), (16, 120), (12, 37)])
+def test_match_sequences_global_other_parameters(ctx, k, m):
+    ref, tgt = _mutated_pair(("gp", k, m), 6000, b"ACG", snp=0.02, indel=0.003)
+    exp = [(x.p, x.l, x.lit) for x in ol.orc_match_sequences(ref, tgt, k, m, True, 11)]
+    got = [(x.p, x.l, x.lit) for x in ctx.match_sequences(ref, tgt, k, m, True, 11)]
+    assert got == exp
+
+
+def test_global_degenerate_inputs(ctx):
+    ref = rnd(3000, "gd")
+    for tgt in (b"", ref[:5], ref[:14], rnd(500, "unrelated"), ref, b"A" * 400):
+        for rr in (ref, b"", ref[:10], b"A" * 300):
+            exp = [(x.p, x.l, x.lit) for x in ol.orc_match_sequences(rr, tgt, 14, 100, True, 0)]
+            got = [(x.p, x.l, x.lit) for x in ctx.match_sequences(rr, tgt, 14, 100, True, 0)]
+            assert got == exp, (len(rr), len(tgt))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_compress_global_random(ctx, seed):
+    from sccg_genome_compression_b200 import synth
+    if seed < 2:
+        ref, tgt = synth.global_gap_pair(150_000 + 7 * seed, 140_000, synth.seed_for(1, seed))
+    else:
+        ref, tgt = synth.divergent_pair(120_000, synth.seed_for(3, seed))
+    ref, tgt = ref.tobytes(), tgt.tobytes()
+    rc, exp, mode = ol.orc_compress(ref, tgt, b">g")
+    got, gmode = ctx.compress(ref, tgt, b">g")
+    assert mode == 1 and (gmode, got) == (mode, exp)
+    assert ctx.decompress(ref, got) == ol.orc_decompress(ref, exp)[1]
