@@ -68,6 +68,17 @@ __device__ __forceinline__ int write_dec_i32(u8* dst, int v) {
     return off + n;
 }
 
+// 8 bytes at an arbitrary address (global or shared): two aligned loads + funnel shift.  Reads up to 15 bytes past p:
+// every buffer this library allocates carries >= 64 bytes of slack.
+__device__ __forceinline__ u64 ld_unaligned64(const u8* p) {
+    uintptr_t a = (uintptr_t)p;
+    const u64* q = reinterpret_cast<const u64*>(a & ~(uintptr_t)7);
+    u32 sh = (u32)(a & 7) * 8u;
+    u64 lo = q[0];
+    if (sh == 0) return lo;
+    return (lo >> sh) | (q[1] << (64u - sh));
+}
+
 __device__ __forceinline__ int lane_of() { return (int)(threadIdx.x & 31); }
 
 // inclusive warp scan (all 32 lanes must call)

@@ -78,7 +78,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
         const size_t smem = sizeof(LmWarpSmem) * LM_WARPS;
         SCCG_SET_MAX_SMEM(seg_match_k, smem);
         unsigned want = div_up(n_iter, LM_WARPS);
-        unsigned cap = (unsigned)c->sm_count * 3u;
+        unsigned cap = (unsigned)c->sm_count * 8u;                          // 8 CTAs of 4 warps fit the 227 KB of shared memory
         unsigned grid = want < cap ? want : cap;
         LAUNCH(c, seg_match_k, dim3(grid), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, n_iter, K1, K2, seginfo, matches, sc + S_WORK);
         SCCG_CK(cudaEventRecord(c->ev[2], c->stream));

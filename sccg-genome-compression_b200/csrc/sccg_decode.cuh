@@ -253,63 +253,149 @@ struct GatherArgs {
     const u32* seg_dst; const i64* seg_src; const int* tok_abs; int nseg;
     const int* n_start; const int* n_len; const u32* n_cum; int n_k;
     const int* l_start; const int* l_len; int l_k;
+    i64 Ls;          // symbols decoded from the record stream (N-free)
     i64 Lm;          // symbols in the N-merged sequence
     i64 total;       // bytes of wrapped text
     u8* out;
 };
 
-static const int GATHER_BYTES = 16;
+static const int GATHER_T = 256;
+static const int GATHER_TILE = GATHER_T * 16;
 
-__global__ void __launch_bounds__(256) dec_gather_k(GatherArgs a) {
-    i64 q0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * GATHER_BYTES;
-    if (q0 >= a.total) return;
-    u8 buf16[GATHER_BYTES];
-    // cursors, (re)positioned lazily by binary search and then advanced monotonically
-    int nk = -2, lk = -2, sk = -2;
-    for (int x = 0; x < GATHER_BYTES; ++x) {
-        i64 q = q0 + x;
-        u8 o = '\n';
-        if (q < a.total) {
-            i64 line = q / (WRAP + 1);
-            int col = (int)(q - line * (WRAP + 1));
-            i64 b = line * WRAP + col;
-            if (col < WRAP && b < a.Lm) {
-                // N runs (original coordinates)
-                if (nk == -2) nk = upper_idx_i32(a.n_start, a.n_k, b);
-                else while (nk + 1 < a.n_k && (i64)a.n_start[nk + 1] <= b) ++nk;
-                bool is_n = false;
-                i64 s = b;
-                if (nk >= 0) {
-                    i64 st = a.n_start[nk], ln = a.n_len[nk];
-                    if (b < st + ln) is_n = true;
-                    else s = b - ((i64)a.n_cum[nk] + ln);
-                }
-                if (is_n) o = 'N';
-                else {
-                    if (sk == -2) sk = upper_idx_u32(a.seg_dst, a.nseg, s);
-                    else while (sk + 1 < a.nseg && (i64)a.seg_dst[sk + 1] <= s) ++sk;
-                    i64 src = a.seg_src[sk];
-                    i64 within = s - (i64)a.seg_dst[sk];
-                    if (src & SEG_LIT_FLAG) o = a.enc[(src & ~SEG_LIT_FLAG) + within];
-                    else o = a.ref[(i64)a.tok_abs[src] + within];
-                }
-                // lowercase runs
-                if (lk == -2) lk = upper_idx_i32(a.l_start, a.l_k, b);
-                else while (lk + 1 < a.l_k && (i64)a.l_start[lk + 1] <= b) ++lk;
-                if (lk >= 0 && b < (i64)a.l_start[lk] + (i64)a.l_len[lk]) o = lower1(o);
-            }
+// last k in [lo, hi] with arr[k] <= x, or lo - 1   (lo may be -1: then the search starts at 0)
+__device__ __forceinline__ int bounded_upper_i32(const int* __restrict__ arr, int lo, int hi, i64 x) {
+    int a = lo < 0 ? 0 : lo, b = hi + 1;
+    while (a < b) { int mid = (a + b) >> 1; if ((i64)arr[mid] <= x) a = mid + 1; else b = mid; }
+    return a - 1;
+}
+__device__ __forceinline__ int bounded_upper_u32(const u32* __restrict__ arr, int lo, int hi, i64 x) {
+    int a = lo < 0 ? 0 : lo, b = hi + 1;
+    while (a < b) { int mid = (a + b) >> 1; if ((i64)arr[mid] <= x) a = mid + 1; else b = mid; }
+    return a - 1;
+}
+
+// symbol index (N-merged coordinates) shown at / just before output byte q
+__device__ __forceinline__ i64 gather_sym_of(i64 q, i64 Lm) {
+    i64 line = q / (WRAP + 1);
+    int col = (int)(q - line * (WRAP + 1));
+    i64 b = line * WRAP + (col < WRAP ? col : WRAP - 1);
+    return b < Lm ? b : Lm - 1;
+}
+// N-free coordinate of merged symbol b (or of the first N-free symbol after it when b is an N)
+__device__ __forceinline__ i64 gather_strip(const GatherArgs& a, i64 b) {
+    int nk = upper_idx_i32(a.n_start, a.n_k, b);
+    if (nk < 0) return b;
+    i64 st = a.n_start[nk], ln = a.n_len[nk];
+    if (b < st + ln) return st - (i64)a.n_cum[nk];
+    return b - ((i64)a.n_cum[nk] + ln);
+}
+
+// Every thread produces one aligned 16-byte piece of the final text.  Fast path (the piece lies inside one copy
+// segment, touches no N run and is entirely inside or outside a lowercase run): two unaligned 8-byte loads, SWAR
+// tolower, newline spliced in with shifts, one 16-byte store.  Anything else: byte by byte.
+__global__ void __launch_bounds__(GATHER_T) dec_gather_k(GatherArgs a) {
+    __shared__ int win[6];            // search windows of this CTA: seg lo/hi, N-run lo/hi, lowercase-run lo/hi
+    const i64 Q0 = (i64)blockIdx.x * GATHER_TILE;
+    const i64 Q1 = (Q0 + GATHER_TILE < a.total ? Q0 + GATHER_TILE : a.total) - 1;     // last byte of the tile
+    if (a.Lm > 0) {
+        if (threadIdx.x == 0) {
+            win[2] = upper_idx_i32(a.n_start, a.n_k, gather_sym_of(Q0, a.Lm));
+            win[3] = upper_idx_i32(a.n_start, a.n_k, gather_sym_of(Q1, a.Lm));
+        } else if (threadIdx.x == 32) {
+            win[4] = upper_idx_i32(a.l_start, a.l_k, gather_sym_of(Q0, a.Lm));
+            win[5] = upper_idx_i32(a.l_start, a.l_k, gather_sym_of(Q1, a.Lm));
+        } else if (threadIdx.x == 64) {
+            win[0] = a.nseg ? upper_idx_u32(a.seg_dst, a.nseg, gather_strip(a, gather_sym_of(Q0, a.Lm))) : -1;
+        } else if (threadIdx.x == 96) {
+            i64 s1 = gather_strip(a, gather_sym_of(Q1, a.Lm));
+            if (s1 > a.Ls - 1) s1 = a.Ls - 1;
+            win[1] = a.nseg ? upper_idx_u32(a.seg_dst, a.nseg, s1) : -1;
         }
-        buf16[x] = o;
     }
-    if (q0 + GATHER_BYTES <= a.total) {
-        uint4 v;
-        v.x = (u32)buf16[0] | ((u32)buf16[1] << 8) | ((u32)buf16[2] << 16) | ((u32)buf16[3] << 24);
-        v.y = (u32)buf16[4] | ((u32)buf16[5] << 8) | ((u32)buf16[6] << 16) | ((u32)buf16[7] << 24);
-        v.z = (u32)buf16[8] | ((u32)buf16[9] << 8) | ((u32)buf16[10] << 16) | ((u32)buf16[11] << 24);
-        v.w = (u32)buf16[12] | ((u32)buf16[13] << 8) | ((u32)buf16[14] << 16) | ((u32)buf16[15] << 24);
-        *reinterpret_cast<uint4*>(a.out + q0) = v;
-    } else {
-        for (int x = 0; q0 + x < a.total; ++x) a.out[q0 + x] = buf16[x];
+    __syncthreads();
+    const i64 q0 = Q0 + (i64)threadIdx.x * 16;
+    if (q0 >= a.total) return;
+    const u32 line0 = (u32)((u64)q0 / (u32)(WRAP + 1));
+    const int col0 = (int)((u64)q0 - (u64)line0 * (WRAP + 1));
+    const int c = WRAP - col0;                                   // offset of the '\n' inside this piece if < 16
+    const i64 b = (i64)line0 * WRAP + col0;                      // first symbol of the piece
+    const int ns = c < 16 ? 15 : 16;
+    bool fast = (q0 + 16 <= a.total - 1) && a.Lm > 0;
+    i64 noff = 0;
+    int lower_all = 0, sk = -1;
+    if (fast) {
+        int nk = bounded_upper_i32(a.n_start, win[2], win[3], b + ns - 1);
+        if (nk >= 0) {
+            i64 en = (i64)a.n_start[nk] + a.n_len[nk];
+            if (en > b) fast = false; else noff = (i64)a.n_cum[nk] + a.n_len[nk];
+        }
+    }
+    if (fast) {
+        i64 s = b - noff;
+        sk = bounded_upper_u32(a.seg_dst, win[0], win[1], s);
+        i64 seg_end = sk + 1 < a.nseg ? (i64)a.seg_dst[sk + 1] : a.Ls;
+        if (sk < 0 || s + ns > seg_end) fast = false;
+    }
+    if (fast) {
+        int lk = bounded_upper_i32(a.l_start, win[4], win[5], b + ns - 1);
+        if (lk >= 0) {
+            i64 ls = a.l_start[lk], le = ls + a.l_len[lk];
+            if (le > b) { if (ls <= b && le >= b + ns) lower_all = 1; else fast = false; }
+        }
+    }
+    if (fast) {
+        i64 src = a.seg_src[sk];
+        i64 within = (b - noff) - (i64)a.seg_dst[sk];
+        const u8* sp = (src & SEG_LIT_FLAG) ? a.enc + (src & ~SEG_LIT_FLAG) + within : a.ref + (i64)a.tok_abs[src] + within;
+        u64 w0 = ld_unaligned64(sp), w1 = ld_unaligned64(sp + 8);
+        if (lower_all) { w0 = lower8(w0); w1 = lower8(w1); }
+        if (c < 8) {
+            u64 lowmask = c ? (~0ull >> (64 - 8 * c)) : 0ull;
+            u64 carry = w0 >> 56;
+            w0 = (w0 & lowmask) | ((u64)'\n' << (8 * c)) | ((w0 & ~lowmask) << 8);
+            w1 = (w1 << 8) | carry;
+        } else if (c < 16) {
+            int cc = c - 8;
+            u64 lowmask = cc ? (~0ull >> (64 - 8 * cc)) : 0ull;
+            w1 = (w1 & lowmask) | ((u64)'\n' << (8 * cc)) | ((w1 & ~lowmask) << 8);
+        }
+        ulonglong2 v; v.x = w0; v.y = w1;
+        *reinterpret_cast<ulonglong2*>(a.out + q0) = v;
+        return;
+    }
+    // ---- slow path: N merge (:244-252), tolower (:255-262), wrap (:266-274) byte by byte
+    int nk = -2, lk = -2;
+    sk = -2;
+    for (int x = 0; x < 16; ++x) {
+        i64 q = q0 + x;
+        if (q >= a.total) break;
+        u8 o = '\n';
+        i64 line = q / (WRAP + 1);
+        int col = (int)(q - line * (WRAP + 1));
+        i64 bb = line * WRAP + col;
+        if (col < WRAP && bb < a.Lm) {
+            if (nk == -2) nk = bounded_upper_i32(a.n_start, win[2], win[3], bb);
+            else while (nk + 1 < a.n_k && (i64)a.n_start[nk + 1] <= bb) ++nk;
+            bool is_n = false;
+            i64 s = bb;
+            if (nk >= 0) {
+                i64 st = a.n_start[nk], ln = a.n_len[nk];
+                if (bb < st + ln) is_n = true;
+                else s = bb - ((i64)a.n_cum[nk] + ln);
+            }
+            if (is_n) o = 'N';
+            else {
+                if (sk == -2) sk = bounded_upper_u32(a.seg_dst, win[0], win[1], s);
+                else while (sk + 1 < a.nseg && (i64)a.seg_dst[sk + 1] <= s) ++sk;
+                i64 src = a.seg_src[sk];
+                i64 within = s - (i64)a.seg_dst[sk];
+                o = (src & SEG_LIT_FLAG) ? a.enc[(src & ~SEG_LIT_FLAG) + within] : a.ref[(i64)a.tok_abs[src] + within];
+            }
+            if (lk == -2) lk = bounded_upper_i32(a.l_start, win[4], win[5], bb);
+            else while (lk + 1 < a.l_k && (i64)a.l_start[lk + 1] <= bb) ++lk;
+            if (lk >= 0 && bb < (i64)a.l_start[lk] + (i64)a.l_len[lk]) o = lower1(o);
+        }
+        a.out[q] = o;
     }
 }
 
@@ -371,8 +457,8 @@ static int reconstruct_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_
     a.ref = d_ref; a.enc = d_enc; a.seg_dst = seg_dst; a.seg_src = seg_src; a.tok_abs = tok_abs; a.nseg = (int)nseg;
     a.n_start = ns.start; a.n_len = ns.len; a.n_cum = ns.cum; a.n_k = (int)ns.K;
     a.l_start = lows.start; a.l_len = lows.len; a.l_k = (int)lows.K;
-    a.Lm = Lm; a.total = total; a.out = out + header_reserve;
-    LAUNCH(c, dec_gather_k, dim3(div_up(total, 256 * GATHER_BYTES)), dim3(256), 0, a);
+    a.Ls = Ls; a.Lm = Lm; a.total = total; a.out = out + header_reserve;
+    LAUNCH(c, dec_gather_k, dim3(div_up(total, GATHER_TILE)), dim3(GATHER_T), 0, a);
     SCCG_CK(cudaEventRecord(c->ev[2], c->stream));
     SCCG_TRY(read_scalars(c, sc, h, D_COUNT));
     if (h[D_ERR] & DE_BOUNDS) return set_error(SCCG_E_BOUNDS, "ERROR: absolute_start + length exceeds reference genome size");

@@ -26,15 +26,6 @@ static const int GP_WIN_BYTES = 288;
 static const int GP_FILTER = 512;
 static const int GP_SHORT = 64;              // per-thread extension before the block-wide one takes over
 
-__device__ __forceinline__ u64 ld_unaligned64(const u8* p) {
-    uintptr_t a = (uintptr_t)p;
-    const u64* q = reinterpret_cast<const u64*>(a & ~(uintptr_t)7);
-    u32 sh = (u32)(a & 7) * 8u;
-    u64 lo = q[0];
-    if (sh == 0) return lo;
-    return (lo >> sh) | (q[1] << (64u - sh));
-}
-
 // 32-bit hash of the k-mer s[0..k), 8 <= k <= 16; the words may come from global or shared memory
 __device__ __forceinline__ u32 kmer_hash_words(u64 w0, u64 w1, int k) {
     if (k < 16) w1 &= (k == 8) ? 0ull : (~0ull >> (8 * (16 - k)));

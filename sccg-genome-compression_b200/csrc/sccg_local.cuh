@@ -19,8 +19,8 @@
 
 namespace sccg {
 
-static const int LM_WARPS = 8;
-static const int LM_HT_BITS = 10;
+static const int LM_WARPS = 4;                // 4 warps x 6.7 KB: 8 CTAs = 32 warps per SM
+static const int LM_HT_BITS = 9;              // 512 chain heads for <= 987 k-mers (false positives die on a 4-byte tag)
 static const int LM_HT = 1 << LM_HT_BITS;
 static const int LM_SEQ_PAD = 1040;
 static const int LM_SLOT = 100;               // max matches per segment: 1000 / k' (k' = 10)
@@ -104,6 +104,35 @@ __device__ __forceinline__ void lm_build_index(LmWarpSmem& S, int Lr, int k, u32
     __syncwarp();
 }
 
+// one lane, one candidate: min(maxl, lcp(r[p..], t[j..])) with 8-byte compares (used when a bucket is crowded, H7)
+__device__ __forceinline__ int lane_lcp(const u8* r, int p, const u8* t, int j, int maxl) {
+    int l = 0;
+    while (l < maxl) {
+        u32 a0 = ld_unaligned32(r, p + l), b0 = ld_unaligned32(t, j + l);
+        if (a0 != b0) { l += (__ffs((int)(a0 ^ b0)) - 1) >> 3; break; }
+        u32 a1 = ld_unaligned32(r, p + l + 4), b1 = ld_unaligned32(t, j + l + 4);
+        if (a1 != b1) { l += 4 + ((__ffs((int)(a1 ^ b1)) - 1) >> 3); break; }
+        l += 8;
+    }
+    return l < maxl ? l : maxl;
+}
+
+// running state of the candidate fold (compression.cpp:114-130 as an order-independent reduction):
+// longest length; among the longest: how many, is p == 0 among them, and min (|p - e| << 16 | p) over p != 0
+struct LmFold { int best_l; int cnt; bool zero_in; u32 best_key; };
+__device__ __forceinline__ void lm_fold_one(LmFold& f, int p, int l, int e) {
+    if (l > f.best_l) { f.best_l = l; f.cnt = 0; f.zero_in = false; f.best_key = 0xffffffffu; }     // :127-128
+    if (l == f.best_l) {                                                                             // :124-126
+        ++f.cnt;
+        if (p == 0) f.zero_in = true;
+        else {
+            int d = p - e; if (d < 0) d = -d;
+            u32 key = ((u32)d << 16) | (u32)p;
+            if (key < f.best_key) f.best_key = key;
+        }
+    }
+}
+
 // the greedy parse of one segment (compression.cpp:64-167); returns the number of matches, stored in S.mlist
 __device__ __forceinline__ int lm_parse(LmWarpSmem& S, int Lr, int Lt, int k, u32 powk) {
     const int lane = lane_of();
@@ -112,36 +141,54 @@ __device__ __forceinline__ int lm_parse(LmWarpSmem& S, int Lr, int Lt, int k, u3
         u32 term = lane < k ? (u32)S.t[j + lane] * powk : 0u;
         u32 h = __reduce_add_sync(SCCG_FULL_MASK, term);
         u32 c = S.head[lm_bucket(h)];
-        int best_l = 0, cnt = 0;
-        bool zero_in = false;
-        u32 best_key = 0xffffffffu;                                              // (|p - e| << 16 | p), p != 0 only
-        while (c) {                                                              // :114 every candidate
-            int p = (int)c - 1;
-            int maxl = (Lr - p) < (Lt - j) ? (Lr - p) : (Lt - j);
-            int l = 0;                                                           // :115 (0-based: also verifies the k-mer)
-            if (p == j) l = diag_lcp(S.mm, j);
-            else if (ld_unaligned32(S.r, p) == ld_unaligned32(S.t, j)) l = warp_lcp(S.r, p, S.t, j, maxl);   // hash-chain false positives die here
-            if (l >= k) {
-                if (l > best_l) { best_l = l; cnt = 0; zero_in = false; best_key = 0xffffffffu; }   // :127-128
-                if (l == best_l) {                                               // :124-126 as a reduction
-                    ++cnt;
-                    if (p == 0) zero_in = true;
-                    else {
-                        int d = p - e; if (d < 0) d = -d;
-                        u32 key = ((u32)d << 16) | (u32)p;
-                        if (key < best_key) best_key = key;
+        const u32 tag = ld_unaligned32(S.t, j);
+        LmFold f; f.best_l = 0; f.cnt = 0; f.zero_in = false; f.best_key = 0xffffffffu;
+        while (c) {                                                              // :114 every candidate of the bucket
+            // gather up to 32 chain entries whose first 4 symbols match (hash-chain false positives die here)
+            int myp = -1, nb = 0;
+            while (c && nb < 32) {
+                int p = (int)c - 1;
+                c = S.next[p];
+                if (ld_unaligned32(S.r, p) == tag) { if (lane == nb) myp = p; ++nb; }
+            }
+            if (nb <= 2) {
+                // the common case: extend cooperatively, 128 symbols per step (extend_alignment :27-34)
+                for (int i = 0; i < nb; ++i) {
+                    int p = __shfl_sync(SCCG_FULL_MASK, myp, i);
+                    int maxl = (Lr - p) < (Lt - j) ? (Lr - p) : (Lt - j);
+                    int l = (p == j) ? diag_lcp(S.mm, j) : warp_lcp(S.r, p, S.t, j, maxl);
+                    if (l >= k) lm_fold_one(f, p, l, e);
+                }
+            } else {
+                // crowded bucket (low-complexity sequence): one candidate per lane
+                int l = 0;
+                if (myp >= 0) {
+                    int maxl = (Lr - myp) < (Lt - j) ? (Lr - myp) : (Lt - j);
+                    l = lane_lcp(S.r, myp, S.t, j, maxl);
+                    if (l < k) l = 0;
+                }
+                int bmax = (int)__reduce_max_sync(SCCG_FULL_MASK, (u32)l);
+                if (bmax > 0) {
+                    if (bmax > f.best_l) { f.best_l = bmax; f.cnt = 0; f.zero_in = false; f.best_key = 0xffffffffu; }
+                    if (bmax == f.best_l) {
+                        bool is = l == bmax;
+                        f.cnt += __popc(__ballot_sync(SCCG_FULL_MASK, is));
+                        if (__any_sync(SCCG_FULL_MASK, is && myp == 0)) f.zero_in = true;
+                        u32 key = 0xffffffffu;
+                        if (is && myp != 0) { int d = myp - e; if (d < 0) d = -d; key = ((u32)d << 16) | (u32)myp; }
+                        key = __reduce_min_sync(SCCG_FULL_MASK, key);
+                        if (key < f.best_key) f.best_key = key;
                     }
                 }
             }
-            c = S.next[p];
         }
-        if (best_l == 0) { ++j; continue; }                                      // :77-81 literal
+        if (f.best_l == 0) { ++j; continue; }                                    // :77-81 literal
         // p = 0 survives only when it is the single longest candidate (`pn1 == 0` is "unset", :125)
-        int p_sel = (cnt == 1 && zero_in) ? 0 : (int)(best_key & 0xffffu);
-        if (lane == 0) S.mlist[nmatch] = (u32)j | ((u32)p_sel << 10) | ((u32)best_l << 20);
+        int p_sel = (f.cnt == 1 && f.zero_in) ? 0 : (int)(f.best_key & 0xffffu);
+        if (lane == 0) S.mlist[nmatch] = (u32)j | ((u32)p_sel << 10) | ((u32)f.best_l << 20);
         ++nmatch;
-        e = p_sel + best_l - 1;                                                  // :149
-        j += best_l;                                                             // :159
+        e = p_sel + f.best_l - 1;                                                // :149
+        j += f.best_l;                                                           // :159
     }
     return nmatch;
 }

@@ -70,6 +70,8 @@ def compensated_indels(rng: np.random.Generator, seq: np.ndarray, count: int, ma
         return seq
     sites = np.sort(rng.integers(1000, n - 2000, size=count))
     sites = sites[np.concatenate(([True], np.diff(sites) > 1000))]
+    # assembly gaps carry no indels: keep sites whose neighbourhood is free of N
+    sites = sites[(seq[sites] != ord("N")) & (seq[sites + 300] != ord("N")) & (seq[np.maximum(sites - 300, 0)] != ord("N"))]
     parts, cur = [], 0
     for s in sites.tolist():
         d = int(rng.integers(1, max_d + 1))

@@ -101,3 +101,22 @@ def test_reconstruct_errors(ctx):
         assert e.value.code == sccg_b200.SCCG_E_FORMAT
     assert ctx.reconstruct(ref, b"", b"", b"") == b"\n"
     assert ctx.reconstruct(ref, b"ACGT", b"", b"1,") == b"AcGT\n"
+
+
+@pytest.mark.parametrize("shape", ["local", "gap", "divergent"])
+def test_decompress_many_tiles_vs_oracle(ctx, shape):
+    """multi-tile gather (search windows per CTA) on record streams produced by the oracle compressor"""
+    from sccg_genome_compression_b200 import synth
+    if shape == "local":
+        ref, tgt = synth.local_pair(300_000, synth.seed_for(2, 21))
+    elif shape == "gap":
+        ref, tgt = synth.global_gap_pair(200_000, 180_000, synth.seed_for(1, 21))
+    else:
+        ref, tgt = synth.divergent_pair(150_000, synth.seed_for(3, 21))
+    ref, tgt = ref.tobytes(), tgt.tobytes()
+    tgt = tgt[:5000] + b"N" * 7 + tgt[5007:90_000] + b"N" * 4300 + tgt[94_300:]      # N runs crossing tile borders
+    rc, inter, mode = ol.orc_compress(ref, tgt, b">tiles")
+    assert rc == 0
+    rc, exp = ol.orc_decompress(ref, inter)
+    assert rc == 0
+    assert ctx.decompress(ref, inter) == exp
