@@ -1,0 +1,58 @@
+// compress <reference_file> <target_file> <output_folder>
+// Drop-in for the reference's compression.cpp main (:584-610) with the hot path (match-and-encode) on a B200 through
+// libsccg_b200.so.  Same argv, same output files (<out>/compressed_genome.txt, then the external `7z a -mx=9`), same
+// exit codes.  There is no CPU matcher: without a usable GPU the program fails.
+#include <chrono>
+#include <cstdlib>
+#include <filesystem>
+#include <iostream>
+
+#include "fasta_io.hpp"
+#include "sccg.h"
+
+int main(int argc, char* argv[]) {
+    if (argc != 4) {                                                        // compression.cpp:587-590
+        std::cerr << "Usage: " << argv[0] << " <reference_file> <target_file> <output_folder>\n";
+        return 1;
+    }
+    try {
+        const std::string ref_path = argv[1], tgt_path = argv[2], out_dir = argv[3];
+        if (!std::filesystem::exists(out_dir)) std::filesystem::create_directory(out_dir);
+        auto t0 = std::chrono::high_resolution_clock::now();
+
+        std::string file, ref, tgt, header;
+        if (!sccg_host::read_file(ref_path, file)) { std::cerr << "Error opening reference file: " << ref_path << "\n"; return 1; }
+        sccg_host::parse_fasta(file, false, ref, nullptr);
+        if (!sccg_host::read_file(tgt_path, file)) { std::cerr << "Error opening target file: " << tgt_path << "\n"; return 1; }
+        sccg_host::parse_fasta(file, true, tgt, &header);
+        file.clear(); file.shrink_to_fit();
+
+        const char* dev = getenv("SCCG_DEVICE");
+        sccg_ctx* ctx = sccg_create(dev ? atoi(dev) : 0);
+        if (!ctx) { std::cerr << "Error: " << sccg_last_error() << "\n"; return 1; }
+        char* out = nullptr; int64_t out_len = 0; int mode = 0;
+        int rc = sccg_compress(ctx, ref.data(), (int64_t)ref.size(), tgt.data(), (int64_t)tgt.size(), header.data(), (int64_t)header.size(),
+                               &out, &out_len, &mode);
+        if (rc != SCCG_OK) { std::cerr << "Error: " << sccg_last_error() << "\n"; sccg_destroy(ctx); return 1; }
+        sccg_profile prof; sccg_get_profile(ctx, &prof);
+
+        std::filesystem::create_directories(out_dir);                        // :334
+        const std::string txt = out_dir + "/compressed_genome.txt";
+        FILE* f = fopen(txt.c_str(), "wb");
+        if (!f || fwrite(out, 1, (size_t)out_len, f) != (size_t)out_len) { std::cerr << "Greska pri otvaranju datoteke: " << txt << "\n"; return 1; }
+        fclose(f);
+        sccg_free(out);
+        sccg_destroy(ctx);
+        std::cout << "mode: " << (mode ? "global" : "local") << ", GPU kernels " << prof.kernels_ms << " ms, H2D " << prof.h2d_ms << " ms, D2H "
+                  << prof.d2h_ms << " ms\n";
+
+        const std::string cmd = "7z a -mx=9 \"" + txt + ".7z\" \"" + txt + "\"";   // :308, the external stage stays as it is
+        if (system(cmd.c_str()) != 0) { std::cerr << "Greska prilikom komprimiranja datoteke 7-zipom !\n"; exit(1); }
+        std::chrono::duration<double> dt = std::chrono::high_resolution_clock::now() - t0;
+        std::cout << "Time taken to compress: " << dt.count() << " s\n";       // :602
+    } catch (const std::exception& ex) {
+        std::cerr << "Error: " << ex.what() << "\n";
+        return 1;
+    }
+    return 0;
+}
