@@ -363,17 +363,20 @@ __global__ void __launch_bounds__(GATHER_T) dec_gather_k(GatherArgs a) {
         *reinterpret_cast<ulonglong2*>(a.out + q0) = v;
         return;
     }
-    // ---- slow path: N merge (:244-252), tolower (:255-262), wrap (:266-274) byte by byte
+    // ---- slow path (piece straddles a segment / run boundary or the end of the text): N merge (:244-252),
+    //      tolower (:255-262), wrap (:266-274) symbol by symbol with monotone cursors, no divisions
     int nk = -2, lk = -2;
     sk = -2;
+    int col = col0;
+    i64 bb = b;
+    u32 piece[4] = {0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au};
+    const int nbytes = (a.total - q0) < 16 ? (int)(a.total - q0) : 16;
+#pragma unroll
     for (int x = 0; x < 16; ++x) {
-        i64 q = q0 + x;
-        if (q >= a.total) break;
         u8 o = '\n';
-        i64 line = q / (WRAP + 1);
-        int col = (int)(q - line * (WRAP + 1));
-        i64 bb = line * WRAP + col;
-        if (col < WRAP && bb < a.Lm) {
+        if (x >= nbytes) {}
+        else if (col == WRAP) col = 0;                              // line break after 50 symbols
+        else if (bb < a.Lm) {                                       // (bb == Lm: the final '\n')
             if (nk == -2) nk = bounded_upper_i32(a.n_start, win[2], win[3], bb);
             else while (nk + 1 < a.n_k && (i64)a.n_start[nk + 1] <= bb) ++nk;
             bool is_n = false;
@@ -394,8 +397,14 @@ __global__ void __launch_bounds__(GATHER_T) dec_gather_k(GatherArgs a) {
             if (lk == -2) lk = bounded_upper_i32(a.l_start, win[4], win[5], bb);
             else while (lk + 1 < a.l_k && (i64)a.l_start[lk + 1] <= bb) ++lk;
             if (lk >= 0 && bb < (i64)a.l_start[lk] + (i64)a.l_len[lk]) o = lower1(o);
+            ++bb; ++col;
         }
-        a.out[q] = o;
+        piece[x >> 2] = (piece[x >> 2] & ~(0xffu << (8 * (x & 3)))) | ((u32)o << (8 * (x & 3)));
+    }
+    if (nbytes == 16) {
+        *reinterpret_cast<uint4*>(a.out + q0) = make_uint4(piece[0], piece[1], piece[2], piece[3]);
+    } else {
+        for (int x = 0; x < nbytes; ++x) a.out[q0 + x] = (u8)(piece[x >> 2] >> (8 * (x & 3)));
     }
 }
 

@@ -29,9 +29,8 @@ static const u32 LM_HASH_B = 0x01000193u;
 struct LmWarpSmem {
     u8 r[LM_SEQ_PAD];
     u8 t[LM_SEQ_PAD];
-    u32 head[LM_HT];       // 0 = empty, else p + 1
-    u16 next[1024];        // chain: 0 = end, else p + 1
-    u32 mm[32];            // bit (b & 31) of mm[b >> 5] set <=> r[b] != t[b] or b >= min(Lr, Lt)
+    u32 head[LM_HT];       // 0 = empty, else chain entry: (p + 1) | 6 tag bits of the k-mer hash << 10
+    u16 next[1024];        // chain: 0 = end, else entry of the next position
     u32 mlist[LM_SLOT + 4];
 };
 
@@ -41,7 +40,9 @@ struct LmWarpSmem {
 #define SEGINFO_ALLN(x) (((x) >> 20) & 1u)
 #define SEGINFO_BAD(x) (((x) >> 21) & 1u)
 
-__device__ __forceinline__ u32 lm_bucket(u32 h) { return (h * 0x9E3779B1u) >> (32 - LM_HT_BITS); }
+__device__ __forceinline__ u32 lm_mix(u32 h) { return h * 0x9E3779B1u; }
+__device__ __forceinline__ u32 lm_bucket(u32 hm) { return hm >> (32 - LM_HT_BITS); }
+__device__ __forceinline__ u32 lm_tag(u32 hm) { return (hm >> (32 - LM_HT_BITS - 6)) & 0x3fu; }
 
 __device__ __forceinline__ u32 ld_unaligned32(const u8* base, int off) {
     const u32* w = reinterpret_cast<const u32*>(base);
@@ -67,17 +68,29 @@ __device__ __forceinline__ int warp_lcp(const u8* r, int p, const u8* t, int j, 
     return maxl;
 }
 
-// first set bit of the 1024-bit diagonal bitmap at or after j, minus j
-__device__ __forceinline__ int diag_lcp(const u32* mm, int j) {
-    const int lane = lane_of();
-    u32 v = mm[lane];
-    int lo = 32 * lane;
-    if (lo + 31 < j) v = 0u;
-    else if (lo < j) v &= 0xffffffffu << (j - lo);
-    u32 bal = __ballot_sync(SCCG_FULL_MASK, v != 0u);
-    int src = __ffs((int)bal) - 1;                            // bits >= min(Lr, Lt) are always set
-    u32 vv = __shfl_sync(SCCG_FULL_MASK, v, src);
-    return 32 * src + (__ffs((int)vv) - 1) - j;
+// Diagonal 0 (p == j, by far the most common candidate): wm[it] bit `lane` is set iff the 8-byte word 32*it+lane of r
+// and t differ inside [0, Lmin).  Returns min(Lmin - j, lcp(r[j..], t[j..])); uniform, no shuffles.
+__device__ __forceinline__ int diag_lcp(const LmWarpSmem& S, const u32 (&wm)[4], int j, int Lmin) {
+    const u64* r64 = reinterpret_cast<const u64*>(S.r);
+    const u64* t64 = reinterpret_cast<const u64*>(S.t);
+    const int w = j >> 3;
+    const int lim = Lmin - j;
+    u64 x = (r64[w] ^ t64[w]) >> (8 * (j & 7));                   // symbols j.. of the first word
+    if (x) { int l = (__ffsll((long long)x) - 1) >> 3; return l < lim ? l : lim; }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        u32 m = wm[it];
+        int lo = 32 * it;
+        if (lo + 31 <= w) m = 0u;
+        else if (lo <= w) m &= 0xfffffffeu << (w - lo);           // words > w only
+        if (m) {
+            int q = lo + __ffs((int)m) - 1;
+            u64 y = r64[q] ^ t64[q];
+            int l = 8 * q + ((__ffsll((long long)y) - 1) >> 3) - j;
+            return l < lim ? l : lim;
+        }
+    }
+    return lim;
 }
 
 // k-mer index of r[0..Lr) (compression.cpp:41-47) as a chained hash table
@@ -94,7 +107,8 @@ __device__ __forceinline__ void lm_build_index(LmWarpSmem& S, int Lr, int k, u32
             u32 h = 0u;
             for (int i = 0; i < k; ++i) h = h * LM_HASH_B + S.r[p + i];
             for (;;) {
-                u32 old = atomicExch(&S.head[lm_bucket(h)], (u32)(p + 1));
+                u32 hm = lm_mix(h);
+                u32 old = atomicExch(&S.head[lm_bucket(hm)], (u32)(p + 1) | (lm_tag(hm) << 10));
                 S.next[p] = (u16)old;
                 if (++p >= p1) break;
                 h = (h - (u32)S.r[p - 1] * bk1) * LM_HASH_B + S.r[p - 1 + k];   // roll one symbol
@@ -134,29 +148,32 @@ __device__ __forceinline__ void lm_fold_one(LmFold& f, int p, int l, int e) {
 }
 
 // the greedy parse of one segment (compression.cpp:64-167); returns the number of matches, stored in S.mlist
-__device__ __forceinline__ int lm_parse(LmWarpSmem& S, int Lr, int Lt, int k, u32 powk) {
+__device__ __forceinline__ int lm_parse(LmWarpSmem& S, const u32 (&wm)[4], int Lr, int Lt, int k, u32 powk) {
+    const int Lmin = Lr < Lt ? Lr : Lt;
     const int lane = lane_of();
     int j = 0, e = -1, nmatch = 0;
     while (j < Lt - k + 1) {                                                     // :64
         u32 term = lane < k ? (u32)S.t[j + lane] * powk : 0u;
-        u32 h = __reduce_add_sync(SCCG_FULL_MASK, term);
-        u32 c = S.head[lm_bucket(h)];
+        u32 hm = lm_mix(__reduce_add_sync(SCCG_FULL_MASK, term));
+        u32 c = S.head[lm_bucket(hm)];
+        const u32 qtag = lm_tag(hm);
         const u32 tag = ld_unaligned32(S.t, j);
         LmFold f; f.best_l = 0; f.cnt = 0; f.zero_in = false; f.best_key = 0xffffffffu;
         while (c) {                                                              // :114 every candidate of the bucket
             // gather up to 32 chain entries whose first 4 symbols match (hash-chain false positives die here)
             int myp = -1, nb = 0;
             while (c && nb < 32) {
-                int p = (int)c - 1;
+                int p = (int)(c & 0x3ffu) - 1;
+                u32 ctag = c >> 10;
                 c = S.next[p];
-                if (ld_unaligned32(S.r, p) == tag) { if (lane == nb) myp = p; ++nb; }
+                if (ctag == qtag && ld_unaligned32(S.r, p) == tag) { if (lane == nb) myp = p; ++nb; }
             }
             if (nb <= 2) {
                 // the common case: extend cooperatively, 128 symbols per step (extend_alignment :27-34)
                 for (int i = 0; i < nb; ++i) {
                     int p = __shfl_sync(SCCG_FULL_MASK, myp, i);
                     int maxl = (Lr - p) < (Lt - j) ? (Lr - p) : (Lt - j);
-                    int l = (p == j) ? diag_lcp(S.mm, j) : warp_lcp(S.r, p, S.t, j, maxl);
+                    int l = (p == j) ? diag_lcp(S, wm, j, Lmin) : warp_lcp(S.r, p, S.t, j, maxl);
                     if (l >= k) lm_fold_one(f, p, l, e);
                 }
             } else {
@@ -239,20 +256,22 @@ __global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restric
         const int Lmin = Lr < Lt ? Lr : Lt;
         __syncwarp();                                        // previous segment fully consumed
         int all_n = 1;
+        u32 wm[4];                                           // diagonal-0 mismatch flags per 8-byte word (uniform)
+        const int wv = Lmin >> 3, rem = Lmin & 7;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             int q = lane + 32 * it;
-            int b0 = 8 * q;
-            u64 rw = upper8(nrw[it]), tw = upper8(ntw[it]);
+            u64 rw = nrw[it], tw = ntw[it];
+            if ((rw | tw) & 0x2020202020202020ULL) { rw = upper8(rw); tw = upper8(tw); }   // only bytes with bit 5 can be a-z
             reinterpret_cast<u64*>(S.r)[q] = rw;
             reinterpret_cast<u64*>(S.t)[q] = tw;
-            u32 mmb = movemask8(nonzero_flags8(rw ^ tw));
-            int valid = Lmin - b0;
-            if (valid < 8) mmb |= valid <= 0 ? 0xffu : ((0xffu << valid) & 0xffu);
-            reinterpret_cast<u8*>(S.mm)[q] = (u8)mmb;
-            int vt = Lt - b0;
-            u32 need = vt >= 8 ? 0xffu : (vt <= 0 ? 0u : ((1u << vt) - 1u));
-            if ((movemask8(eq_flags8(tw, 'N')) & need) != need) all_n = 0;
+            u64 diff = rw ^ tw;
+            bool d = q < wv ? diff != 0ull : (q == wv && rem ? (diff & (~0ull >> (64 - 8 * rem))) != 0ull : false);
+            wm[it] = __ballot_sync(SCCG_FULL_MASK, d);
+            int vt = Lt - 8 * q;                             // target symbols in this word
+            u64 nx = tw ^ 0x4E4E4E4E4E4E4E4EULL;             // 'N' * 8
+            if (vt >= 8) { if (nx) all_n = 0; }
+            else if (vt > 0) { if (nx & (~0ull >> (64 - 8 * vt))) all_n = 0; }
         }
         int next_seg = 0;
         if (lane == 0) next_seg = (int)atomicAdd(work_counter, 1u) + warps_total;
@@ -263,17 +282,16 @@ __global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restric
         __syncwarp();
 
         int nmatch = 0;
-        const int f0 = diag_lcp(S.mm, 0);                    // first diagonal-0 mismatch (== Lmin if none)
-        if (Lr == Lt && Lt >= k1 && f0 >= Lt) {
+        if (Lr == Lt && Lt >= k1 && (wm[0] | wm[1] | wm[2] | wm[3]) == 0u) {
             // t_i == r_i: candidate p = 0 extends to Lt; any other p gives l <= Lr - p < Lt -> untied
             if (lane == 0) S.mlist[0] = 0u | (0u << 10) | ((u32)Lt << 20);
             nmatch = 1;
         } else {
             lm_build_index(S, Lr, k1, bk1_1);
-            nmatch = lm_parse(S, Lr, Lt, k1, pow1);                              // compression.cpp:401
+            nmatch = lm_parse(S, wm, Lr, Lt, k1, pow1);                              // compression.cpp:401
             if (nmatch == 0 && k2 > 0) {
                 lm_build_index(S, Lr, k2, bk1_2);
-                nmatch = lm_parse(S, Lr, Lt, k2, pow2);                          // compression.cpp:428
+                nmatch = lm_parse(S, wm, Lr, Lt, k2, pow2);                          // compression.cpp:428
             }
         }
         __syncwarp();
