@@ -290,37 +290,91 @@ __device__ __forceinline__ i64 gather_strip(const GatherArgs& a, i64 b) {
     return b - ((i64)a.n_cum[nk] + ln);
 }
 
-// Every thread produces one aligned 16-byte piece of the final text.  Fast path (the piece lies inside one copy
-// segment, touches no N run and is entirely inside or outside a lowercase run): two unaligned 8-byte loads, SWAR
-// tolower, newline spliced in with shifts, one 16-byte store.  Anything else: byte by byte.
+// warp-cooperative 32-ary search: last k with arr[k] <= x, or -1.  All 32 lanes, uniform arguments.
+__device__ __forceinline__ int warp_upper_i32(const int* __restrict__ arr, int n, i64 x) {
+    const int lane = lane_of();
+    int lo = 0, hi = n;                                           // the count of elements <= x lies in [lo, hi]
+    while (hi > lo) {
+        int step = (hi - lo + 31) >> 5;
+        int pi = lo + lane * step;
+        bool le = pi < hi && (i64)arr[pi] <= x;
+        int c = __popc(__ballot_sync(SCCG_FULL_MASK, le));
+        if (c == 0) { hi = lo; break; }
+        int nlo = lo + (c - 1) * step + 1;
+        int nhi = lo + c * step; if (nhi > hi) nhi = hi;
+        lo = nlo; hi = nhi;
+    }
+    return lo - 1;
+}
+__device__ __forceinline__ int warp_upper_u32(const u32* __restrict__ arr, int n, i64 x) {
+    const int lane = lane_of();
+    int lo = 0, hi = n;
+    while (hi > lo) {
+        int step = (hi - lo + 31) >> 5;
+        int pi = lo + lane * step;
+        bool le = pi < hi && (i64)arr[pi] <= x;
+        int c = __popc(__ballot_sync(SCCG_FULL_MASK, le));
+        if (c == 0) { hi = lo; break; }
+        int nlo = lo + (c - 1) * step + 1;
+        int nhi = lo + c * step; if (nhi > hi) nhi = hi;
+        lo = nlo; hi = nhi;
+    }
+    return lo - 1;
+}
+
+// one symbol of the final text (slow path): N merge (:244-252), copy (:230-233), tolower (:255-262), wrap (:266-274)
+__device__ __forceinline__ u8 gather_byte(const GatherArgs& a, const int* win, u32 q) {
+    if ((i64)q == a.total - 1) return '\n';                       // the final newline (:274)
+    u32 line = q / (u32)(WRAP + 1);
+    int col = (int)(q - line * (u32)(WRAP + 1));
+    if (col == WRAP) return '\n';
+    i64 bb = (i64)line * WRAP + col;
+    int nk = bounded_upper_i32(a.n_start, win[2], win[3], bb);
+    i64 s = bb;
+    if (nk >= 0) {
+        i64 st = a.n_start[nk], ln = a.n_len[nk];
+        if (bb < st + ln) return 'N';
+        s = bb - ((i64)a.n_cum[nk] + ln);
+    }
+    int sk = bounded_upper_u32(a.seg_dst, win[0], win[1], s);
+    i64 src = a.seg_src[sk];
+    i64 within = s - (i64)a.seg_dst[sk];
+    u8 o = (src & SEG_LIT_FLAG) ? a.enc[(src & ~SEG_LIT_FLAG) + within] : a.ref[(i64)a.tok_abs[src] + within];
+    int lk = bounded_upper_i32(a.l_start, win[4], win[5], bb);
+    if (lk >= 0 && bb < (i64)a.l_start[lk] + (i64)a.l_len[lk]) o = lower1(o);
+    return o;
+}
+
+// Every thread owns one aligned 16-byte piece of the final text.  Fast path (the piece lies inside one copy segment,
+// touches no N run and is entirely inside or outside a lowercase run): two unaligned 8-byte loads, SWAR tolower,
+// newline spliced in with shifts, one 16-byte store.  Pieces that straddle a boundary are handed to the warp: 16 lanes
+// per piece, one symbol per lane, so boundary pieces cost one pass instead of a 16-step serial loop in a single lane.
 __global__ void __launch_bounds__(GATHER_T) dec_gather_k(GatherArgs a) {
     __shared__ int win[6];            // search windows of this CTA: seg lo/hi, N-run lo/hi, lowercase-run lo/hi
+    const int lane = lane_of(), warp = (int)(threadIdx.x >> 5);
     const i64 Q0 = (i64)blockIdx.x * GATHER_TILE;
     const i64 Q1 = (Q0 + GATHER_TILE < a.total ? Q0 + GATHER_TILE : a.total) - 1;     // last byte of the tile
-    if (a.Lm > 0) {
-        if (threadIdx.x == 0) {
-            win[2] = upper_idx_i32(a.n_start, a.n_k, gather_sym_of(Q0, a.Lm));
-            win[3] = upper_idx_i32(a.n_start, a.n_k, gather_sym_of(Q1, a.Lm));
-        } else if (threadIdx.x == 32) {
-            win[4] = upper_idx_i32(a.l_start, a.l_k, gather_sym_of(Q0, a.Lm));
-            win[5] = upper_idx_i32(a.l_start, a.l_k, gather_sym_of(Q1, a.Lm));
-        } else if (threadIdx.x == 64) {
-            win[0] = a.nseg ? upper_idx_u32(a.seg_dst, a.nseg, gather_strip(a, gather_sym_of(Q0, a.Lm))) : -1;
-        } else if (threadIdx.x == 96) {
-            i64 s1 = gather_strip(a, gather_sym_of(Q1, a.Lm));
-            if (s1 > a.Ls - 1) s1 = a.Ls - 1;
-            win[1] = a.nseg ? upper_idx_u32(a.seg_dst, a.nseg, s1) : -1;
-        }
+    if (a.Lm > 0 && warp < 6) {
+        // six 32-ary searches, one per warp
+        const i64 bq = gather_sym_of((warp & 1) ? Q1 : Q0, a.Lm);
+        int r;
+        if (warp < 2) {
+            i64 sx = gather_strip(a, bq);
+            if (sx > a.Ls - 1) sx = a.Ls - 1;
+            r = a.nseg ? warp_upper_u32(a.seg_dst, a.nseg, sx) : -1;
+        } else if (warp < 4) r = warp_upper_i32(a.n_start, a.n_k, bq);
+        else r = warp_upper_i32(a.l_start, a.l_k, bq);
+        if (lane == 0) win[warp] = r;
     }
     __syncthreads();
     const i64 q0 = Q0 + (i64)threadIdx.x * 16;
-    if (q0 >= a.total) return;
+    const bool live = q0 < a.total;
     const u32 line0 = (u32)((u64)q0 / (u32)(WRAP + 1));
     const int col0 = (int)((u64)q0 - (u64)line0 * (WRAP + 1));
     const int c = WRAP - col0;                                   // offset of the '\n' inside this piece if < 16
     const i64 b = (i64)line0 * WRAP + col0;                      // first symbol of the piece
     const int ns = c < 16 ? 15 : 16;
-    bool fast = (q0 + 16 <= a.total - 1) && a.Lm > 0;
+    bool fast = live && (q0 + 16 <= a.total - 1) && a.Lm > 0;
     i64 noff = 0;
     int lower_all = 0, sk = -1;
     if (fast) {
@@ -361,50 +415,20 @@ __global__ void __launch_bounds__(GATHER_T) dec_gather_k(GatherArgs a) {
         }
         ulonglong2 v; v.x = w0; v.y = w1;
         *reinterpret_cast<ulonglong2*>(a.out + q0) = v;
-        return;
     }
-    // ---- slow path (piece straddles a segment / run boundary or the end of the text): N merge (:244-252),
-    //      tolower (:255-262), wrap (:266-274) symbol by symbol with monotone cursors, no divisions
-    int nk = -2, lk = -2;
-    sk = -2;
-    int col = col0;
-    i64 bb = b;
-    u32 piece[4] = {0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au};
-    const int nbytes = (a.total - q0) < 16 ? (int)(a.total - q0) : 16;
-#pragma unroll
-    for (int x = 0; x < 16; ++x) {
-        u8 o = '\n';
-        if (x >= nbytes) {}
-        else if (col == WRAP) col = 0;                              // line break after 50 symbols
-        else if (bb < a.Lm) {                                       // (bb == Lm: the final '\n')
-            if (nk == -2) nk = bounded_upper_i32(a.n_start, win[2], win[3], bb);
-            else while (nk + 1 < a.n_k && (i64)a.n_start[nk + 1] <= bb) ++nk;
-            bool is_n = false;
-            i64 s = bb;
-            if (nk >= 0) {
-                i64 st = a.n_start[nk], ln = a.n_len[nk];
-                if (bb < st + ln) is_n = true;
-                else s = bb - ((i64)a.n_cum[nk] + ln);
-            }
-            if (is_n) o = 'N';
-            else {
-                if (sk == -2) sk = bounded_upper_u32(a.seg_dst, win[0], win[1], s);
-                else while (sk + 1 < a.nseg && (i64)a.seg_dst[sk + 1] <= s) ++sk;
-                i64 src = a.seg_src[sk];
-                i64 within = s - (i64)a.seg_dst[sk];
-                o = (src & SEG_LIT_FLAG) ? a.enc[(src & ~SEG_LIT_FLAG) + within] : a.ref[(i64)a.tok_abs[src] + within];
-            }
-            if (lk == -2) lk = bounded_upper_i32(a.l_start, win[4], win[5], bb);
-            else while (lk + 1 < a.l_k && (i64)a.l_start[lk + 1] <= bb) ++lk;
-            if (lk >= 0 && bb < (i64)a.l_start[lk] + (i64)a.l_len[lk]) o = lower1(o);
-            ++bb; ++col;
+    // ---- boundary pieces: two per round, 16 lanes each, one symbol per lane
+    u32 slow = __ballot_sync(SCCG_FULL_MASK, live && !fast);
+    const u32 my_q0 = (u32)q0;                                   // total < 2^32
+    while (slow) {
+        int s1 = __ffs((int)slow) - 1; slow &= slow - 1;
+        int s2 = -1;
+        if (slow) { s2 = __ffs((int)slow) - 1; slow &= slow - 1; }
+        int src = lane < 16 ? s1 : s2;
+        u32 pq0 = __shfl_sync(SCCG_FULL_MASK, my_q0, src < 0 ? 0 : src);
+        if (src >= 0) {
+            u32 q = pq0 + (u32)(lane & 15);
+            if ((i64)q < a.total) a.out[q] = gather_byte(a, win, q);
         }
-        piece[x >> 2] = (piece[x >> 2] & ~(0xffu << (8 * (x & 3)))) | ((u32)o << (8 * (x & 3)));
-    }
-    if (nbytes == 16) {
-        *reinterpret_cast<uint4*>(a.out + q0) = make_uint4(piece[0], piece[1], piece[2], piece[3]);
-    } else {
-        for (int x = 0; x < nbytes; ++x) a.out[q0 + x] = (u8)(piece[x >> 2] >> (8 * (x & 3)));
     }
 }
 
