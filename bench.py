@@ -44,38 +44,45 @@ def peaks() -> tuple[float, str]:
 
 
 class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    """streams `nvidia-smi -lms 100` (clocks, throttle reasons) while the timed regions run"""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.samples, self.stop_flag, self.thread = index, [], threading.Event(), None
+        self.index, self.samples, self.proc, self.thread = index, [], None, None
 
     def _run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append(parts)
 
     def __enter__(self):
-        self.thread = threading.Thread(target=self._run, daemon=True)
-        self.thread.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+            time.sleep(0.35)                      # let the first sample land before the timed region starts
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop_flag.set()
-        self.thread.join(timeout=6)
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.thread.join(timeout=5)
 
     def summary(self) -> dict:
-        sm = [int(s[0]) for s in self.samples if s and s[0].isdigit()]
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        sm = [int(s[0]) for s in self.samples if s[0].isdigit()]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if s[2 + i].lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(self.samples)}
 
@@ -178,7 +185,7 @@ def workload_name(size: int) -> str:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=0, help="bp per pair (default: chr1 = 249,250,621)")
@@ -219,84 +226,85 @@ def main() -> None:
     # ---- workload: every rank owns one chromosome-sized pair (rank-dependent seed)
     ref_np, tgt_np = synth.local_pair(args.size, synth.seed_for(2, rank))
     nr, nt = int(ref_np.size), int(tgt_np.size)
-    h_ref = torch.from_numpy(ref_np).pin_memory()
-    h_tgt = torch.from_numpy(tgt_np).pin_memory()
+    pad = torch.zeros(64, dtype=torch.uint8)                    # *_device entry points may read a few bytes past the end
+    h_ref = torch.cat([torch.from_numpy(ref_np), pad]).pin_memory()
+    h_tgt = torch.cat([torch.from_numpy(tgt_np), pad]).pin_memory()
     d_ref = h_ref.cuda()
     d_tgt = h_tgt.cuda()
     ctx = sccg_b200.Context(local_rank)
+    import oracle_lib as ol                                      # split_intermediate only (pure python line split)
 
-    # ---- compress, device-resident inputs (kernel-only `value`)
     def compress_step():
         ptr, length, mode = ctx.compress_device(d_ref.data_ptr(), nr, d_tgt.data_ptr(), nt, HEADER)
         return ptr, length, mode, ctx.profile()
 
+    # untimed: one pass to get the record stream that the decompress half consumes
+    ptr, enc_len, mode, prof = compress_step()
+    assert mode == 0, "workload left the local path"
+    enc_bytes = ctx.download(ptr, enc_len)
+    header, low, nline, body = ol.split_intermediate(enc_bytes)
+    d_body = torch.cat([torch.frombuffer(bytearray(body), dtype=torch.uint8), pad]).cuda()
+    d_low = torch.cat([torch.frombuffer(bytearray(low), dtype=torch.uint8), pad]).cuda()
+    d_n = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    d_refu = torch.cat([torch.from_numpy(np.frombuffer(ref_np.tobytes().upper(), dtype=np.uint8).copy()), pad]).cuda()   # decompress_genome :110
+
+    def decompress_step():
+        optr, out_len = ctx.reconstruct_device(d_refu.data_ptr(), nr, d_body.data_ptr(), len(body), d_n.data_ptr(), 0, d_low.data_ptr(), len(low))
+        return optr, out_len, ctx.profile()
+
+    out_cap = nt + nt // 50 + len(HEADER) + 64
+    h_enc = torch.empty(max(enc_len + 4096, 1 << 20), dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(out_cap, dtype=torch.uint8).pin_memory()
+    h_inter = torch.frombuffer(bytearray(enc_bytes), dtype=torch.uint8).pin_memory()
+
     for _ in range(args.warmup):
-        ptr, enc_len, mode, prof = compress_step()
-    barrier()
-    ev_ms, match_ms, launches = 0.0, 0.0, 0
+        compress_step(); decompress_step()
+        ctx.compress_into(_as_bytes(h_ref, nr), _as_bytes(h_tgt, nt), HEADER, h_enc.data_ptr(), h_enc.numel())
+        ctx.decompress_into(_as_bytes(h_ref, nr), _as_bytes(h_inter, enc_len), h_out.data_ptr(), h_out.numel())
+
+    ev_ms = match_ms = dms = gather_ms = 0.0
+    launches = 0
     with ClockSampler(local_rank) as clocks:
+        # ---- (1) compress, inputs resident in HBM
+        barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            ptr, enc_len, mode, prof = compress_step()
+            ptr, enc_len2, mode, prof = compress_step()
             ev_ms += prof["kernels_ms"]; match_ms += prof["match_ms"]; launches += prof["launches"]
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
-    assert mode == 0, "workload left the local path"
+        # ---- (2) decompress, inputs resident in HBM
+        for _ in range(args.steps):
+            optr, out_len, p = decompress_step()
+            dms += p["kernels_ms"]; gather_ms += p["gather_ms"]; launches += p["launches"]
+        barrier()
+        # ---- (3) end to end through the host-pointer C ABI: pinned host buffers, H2D + kernels + D2H inside
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e_len, e_mode = ctx.compress_into(_as_bytes(h_ref, nr), _as_bytes(h_tgt, nt), HEADER, h_enc.data_ptr(), h_enc.numel())
+            e2e_prof = ctx.profile(); launches += e2e_prof["launches"]
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            d_len = ctx.decompress_into(_as_bytes(h_ref, nr), _as_bytes(h_inter, enc_len), h_out.data_ptr(), h_out.numel())
+            e2e_dprof = ctx.profile(); launches += e2e_dprof["launches"]
+        barrier()
+        e2e_dec_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    assert enc_len2 == enc_len and bytes(h_enc[:e_len].numpy()) == enc_bytes, "end-to-end output differs from the device-resident output"
+    expect_fa = HEADER + b"\n" + b"\n".join(tgt_np[i:i + 50].tobytes() for i in range(0, min(nt, 5000), 50))
+    assert bytes(h_out[:len(expect_fa)].numpy()) == expect_fa and d_len == len(HEADER) + 1 + out_len, "round trip does not reproduce the target"
     comp_ms = max_over_ranks(ev_ms / args.steps)
     comp_wall_ms = max_over_ranks(wall_ms / args.steps)
     match_ms_avg = max_over_ranks(match_ms / args.steps)
-
-    # the encoded image (device) -> host once, for the decompress half and for --verify
-    enc_bytes = ctx.download(ptr, enc_len)
-
-    # ---- decompress, device-resident inputs
-    dec = None
-    try:
-        import oracle_lib as ol
-        header, low, nline, body = ol.split_intermediate(enc_bytes)
-        d_body = torch.frombuffer(bytearray(body), dtype=torch.uint8).cuda()
-        d_low = torch.frombuffer(bytearray(low) or bytearray(1), dtype=torch.uint8).cuda()
-        d_n = torch.zeros(16, dtype=torch.uint8, device="cuda")
-        d_refu = torch.from_numpy(np.frombuffer(ref_np.tobytes().upper(), dtype=np.uint8).copy()).cuda()   # decompress_genome :110
-        for _ in range(args.warmup):
-            optr, out_len = ctx.reconstruct_device(d_refu.data_ptr(), nr, d_body.data_ptr(), len(body), d_n.data_ptr(), 0, d_low.data_ptr(), len(low))
-        barrier()
-        dms, dl, gather_ms = 0.0, 0, 0.0
-        for _ in range(args.steps):
-            optr, out_len = ctx.reconstruct_device(d_refu.data_ptr(), nr, d_body.data_ptr(), len(body), d_n.data_ptr(), 0, d_low.data_ptr(), len(low))
-            p = ctx.profile(); dms += p["kernels_ms"]; dl += p["launches"]; gather_ms += p["gather_ms"]
-        barrier()
-        dec_ms = max_over_ranks(dms / args.steps)
-        launches += dl
-        dec = {"value": world * nt / (dec_ms / 1e3) / 1e9, "unit": "Gbp/s", "ms_per_step": dec_ms,
-               "roofline": None}
-        hbm, which = peaks()
-        g_ms = max_over_ranks(gather_ms / args.steps)
-        dec_bytes = len(body) + nt + out_len
-        dec["roofline"] = {"bound": "hbm", "kernel": "decode_gather_k", "achieved": dec_bytes / (g_ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
-                           "frac": dec_bytes / (g_ms / 1e3) / 1e9 / hbm, "traffic": None, "peak_source": which}
-    except sccg_b200.SccgError as e:
-        if "not implemented" not in str(e):
-            raise
-        dec = {"unavailable": str(e)}
-
-    # ---- end to end through the host-pointer C ABI (H2D of both genomes + D2H of the record stream inside)
-    for _ in range(max(1, args.warmup // 2)):
-        out, mode2 = ctx.compress(_as_bytes(h_ref), _as_bytes(h_tgt), HEADER)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_prof = None
-    for _ in range(args.steps):
-        out, mode2 = ctx.compress(_as_bytes(h_ref), _as_bytes(h_tgt), HEADER)
-        e2e_prof = ctx.profile()
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
-    assert out == enc_bytes, "end-to-end output differs from the device-resident output"
+    dec_ms = max_over_ranks(dms / args.steps)
+    g_ms = max_over_ranks(gather_ms / args.steps)
+    e2e_ms = max_over_ranks(e2e_ms)
+    e2e_dec_ms = max_over_ranks(e2e_dec_ms)
 
     verified = None
     if args.verify and rank == 0:
-        import oracle_lib as ol
-        rc, exp, emode = ol.orc_compress(ref_np.tobytes(), tgt_np.tobytes(), HEADER)
+        rc, exp, emode = ol.orc_compress(ref_np.tobytes(), tgt_np.tobytes(), HEADER)      # the oracle as the checker (untimed)
         verified = bool(rc == 0 and exp == enc_bytes and emode == mode)
         assert verified, "full-size output differs from the oracle"
 
@@ -315,6 +323,8 @@ def main() -> None:
         hbm, which = peaks()
         algo_bytes = nr + nt                       # segment-match kernel: both genomes read once (SURVEY 8d, 2.0 B/bp)
         ach = algo_bytes / (match_ms_avg / 1e3) / 1e9
+        dec_bytes = len(body) + nt + out_len       # gather kernel: record stream + copied reference symbols + wrapped text (2.02 B/bp)
+        dach = dec_bytes / (g_ms / 1e3) / 1e9
         line = {
             "metric": METRIC, "value": world * nt / (comp_ms / 1e3) / 1e6, "unit": "Mbp/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": comp_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -323,12 +333,18 @@ def main() -> None:
                        "l2": "inputs (2 x 249 MB) larger than the 126 MB L2, no flush needed", "timing": "CUDA events on the library stream, max over ranks",
                        "encoded_bytes": enc_len, "mode": "local"},
             "wall_ms_per_step": comp_wall_ms,
-            "decompress": dec,
+            "decompress": {"value": world * nt / (dec_ms / 1e3) / 1e9, "unit": "Gbp/s", "ms_per_step": dec_ms,
+                           "roofline": {"bound": "hbm", "kernel": "dec_gather_k", "achieved": dach, "peak": hbm, "unit": "GB/s", "frac": dach / hbm,
+                                        "traffic": None, "algorithmic_bytes_per_launch": dec_bytes, "kernel_ms": g_ms, "peak_source": which},
+                           "e2e": {"value": world * nt / (e2e_dec_ms / 1e3) / 1e9, "unit": "Gbp/s", "ms_per_step": e2e_dec_ms,
+                                   "h2d_bytes_per_step": nr + enc_len, "d2h_bytes_per_step": d_len, "h2d_ms": e2e_dprof["h2d_ms"],
+                                   "d2h_ms": e2e_dprof["d2h_ms"], "kernels_ms": e2e_dprof["kernels_ms"]}},
             "roofline": {"bound": "hbm", "kernel": "seg_match_k", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
                          "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": match_ms_avg, "peak_source": which},
             "cpu_baseline": cpu,
             "e2e": {"value": world * nt / (e2e_ms / 1e3) / 1e6, "unit": "Mbp/s", "h2d_bytes_per_step": nr + nt, "d2h_bytes_per_step": enc_len,
-                    "ms_per_step": e2e_ms, "h2d_ms": e2e_prof["h2d_ms"], "d2h_ms": e2e_prof["d2h_ms"], "kernels_ms": e2e_prof["kernels_ms"]},
+                    "ms_per_step": e2e_ms, "h2d_ms": e2e_prof["h2d_ms"], "d2h_ms": e2e_prof["d2h_ms"], "kernels_ms": e2e_prof["kernels_ms"],
+                    "api": "sccg_compress_into: pinned host buffers in, pinned host buffer out"},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
         }
@@ -340,10 +356,10 @@ def main() -> None:
         dist.destroy_process_group()
 
 
-def _as_bytes(t):
-    """zero-copy view of a pinned CPU uint8 tensor as a ctypes char buffer"""
+def _as_bytes(t, n=None):
+    """zero-copy view of the first n bytes of a pinned CPU uint8 tensor as a ctypes char buffer"""
     import ctypes
-    return (ctypes.c_char * t.numel()).from_address(t.data_ptr())
+    return (ctypes.c_char * (t.numel() if n is None else n)).from_address(t.data_ptr())
 
 
 if __name__ == "__main__":

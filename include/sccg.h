@@ -103,6 +103,17 @@ int sccg_reconstruct_device(sccg_ctx* ctx, const void* d_ref, int64_t ref_len, c
 int sccg_decompress(sccg_ctx* ctx, const char* ref_raw, int64_t ref_len, const char* intermediate, int64_t inter_len,
                     char** out, int64_t* out_len);
 
+/* *_into variants: identical, but the result is written into a buffer of the caller instead of a fresh allocation
+ * (page-locked host memory gives full PCIe speed).  If out_cap is too small they return SCCG_E_ARG and *out_len holds
+ * the required size. */
+int sccg_compress_into(sccg_ctx* ctx, const char* ref, int64_t ref_len, const char* tgt, int64_t tgt_len,
+                       const char* header, int64_t header_len, char* out, int64_t out_cap, int64_t* out_len, int* mode_out);
+int sccg_reconstruct_into(sccg_ctx* ctx, const char* ref, int64_t ref_len, const char* encoded, int64_t enc_len,
+                          const char* n_idx, int64_t n_len, const char* low_idx, int64_t low_len,
+                          char* out, int64_t out_cap, int64_t* out_len);
+int sccg_decompress_into(sccg_ctx* ctx, const char* ref_raw, int64_t ref_len, const char* intermediate, int64_t inter_len,
+                         char* out, int64_t out_cap, int64_t* out_len);
+
 #ifdef __cplusplus
 }
 #endif

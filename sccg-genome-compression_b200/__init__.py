@@ -81,6 +81,9 @@ def load_library(path: str | os.PathLike | None = None) -> C.CDLL:
     lib.sccg_reconstruct.argtypes = [vp, cp, i64, cp, i64, cp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64)]
     lib.sccg_reconstruct_device.argtypes = [vp, vp, i64, vp, i64, vp, i64, vp, i64, C.POINTER(vp), C.POINTER(i64)]
     lib.sccg_decompress.argtypes = [vp, cp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64)]
+    lib.sccg_compress_into.argtypes = [vp, cp, i64, cp, i64, cp, i64, vp, i64, C.POINTER(i64), C.POINTER(C.c_int)]
+    lib.sccg_reconstruct_into.argtypes = [vp, cp, i64, cp, i64, cp, i64, cp, i64, vp, i64, C.POINTER(i64)]
+    lib.sccg_decompress_into.argtypes = [vp, cp, i64, cp, i64, vp, i64, C.POINTER(i64)]
     _libs[key] = lib
     return lib
 
@@ -141,6 +144,18 @@ class Context:
         self._check(self.lib.sccg_compress(self.handle, ref, len(ref), tgt, len(tgt), header, len(header),
                                            C.byref(out), C.byref(n), C.byref(mode)))
         return self._take(out, n.value), mode.value
+
+    def compress_into(self, ref, tgt, header: bytes, out_ptr: int, out_cap: int) -> tuple[int, int]:
+        """result written to the caller's (ideally page-locked) buffer -> (length, mode)"""
+        n = C.c_int64(); mode = C.c_int()
+        self._check(self.lib.sccg_compress_into(self.handle, ref, len(ref), tgt, len(tgt), header, len(header), out_ptr, out_cap,
+                                                C.byref(n), C.byref(mode)))
+        return n.value, mode.value
+
+    def decompress_into(self, ref_raw, intermediate, out_ptr: int, out_cap: int) -> int:
+        n = C.c_int64()
+        self._check(self.lib.sccg_decompress_into(self.handle, ref_raw, len(ref_raw), intermediate, len(intermediate), out_ptr, out_cap, C.byref(n)))
+        return n.value
 
     def compress_device(self, d_ref: int, ref_len: int, d_tgt: int, tgt_len: int, header: bytes = b"") -> tuple[int, int, int]:
         """device pointers in -> (device pointer of the encoded image, its length, mode)"""

@@ -101,9 +101,9 @@ int sccg_compress_device(sccg_ctx* c, const void* d_ref, int64_t ref_len, const 
     return SCCG_OK;
 }
 
-int sccg_compress(sccg_ctx* c, const char* ref, int64_t ref_len, const char* tgt, int64_t tgt_len,
-                  const char* header, int64_t header_len, char** out, int64_t* out_len, int* mode_out) {
-    if (!c || !out || !out_len || (ref_len > 0 && !ref) || (tgt_len > 0 && !tgt) || (header_len > 0 && !header)) return set_error(SCCG_E_ARG, "null argument");
+static int compress_host(sccg_ctx* c, const char* ref, int64_t ref_len, const char* tgt, int64_t tgt_len, const char* header, int64_t header_len,
+                         char* dst, int64_t dst_cap, char** out, int64_t* out_len, int* mode_out) {
+    if (!c || !out_len || (ref_len > 0 && !ref) || (tgt_len > 0 && !tgt) || (header_len > 0 && !header)) return set_error(SCCG_E_ARG, "null argument");
     SCCG_TRY(check_sizes(ref_len, tgt_len));
     SCCG_CK(cudaSetDevice(c->device));
     prof_reset(c);
@@ -115,14 +115,25 @@ int sccg_compress(sccg_ctx* c, const char* ref, int64_t ref_len, const char* tgt
     CompressResult res;
     SCCG_TRY(compress_device(c, d_ref, ref_len, d_tgt, tgt_len, header, header_len < 0 ? 0 : header_len, &res));
     SCCG_CK(cudaEventRecord(c->ev[6], c->stream));
-    SCCG_TRY(download(c, res.d_out, res.out_len, out));
+    SCCG_TRY(deliver(c, res.d_out, res.out_len, dst, dst_cap, out, out_len));
     SCCG_CK(cudaEventRecord(c->ev[7], c->stream));
     SCCG_CK(cudaStreamSynchronize(c->stream));
     cudaEventElapsedTime(&c->prof.h2d_ms, c->ev[4], c->ev[5]);
     cudaEventElapsedTime(&c->prof.d2h_ms, c->ev[6], c->ev[7]);
-    *out_len = res.out_len;
     if (mode_out) *mode_out = res.mode;
     return SCCG_OK;
+}
+
+int sccg_compress(sccg_ctx* c, const char* ref, int64_t ref_len, const char* tgt, int64_t tgt_len,
+                  const char* header, int64_t header_len, char** out, int64_t* out_len, int* mode_out) {
+    if (!out) return set_error(SCCG_E_ARG, "null argument");
+    return compress_host(c, ref, ref_len, tgt, tgt_len, header, header_len, nullptr, 0, out, out_len, mode_out);
+}
+
+int sccg_compress_into(sccg_ctx* c, const char* ref, int64_t ref_len, const char* tgt, int64_t tgt_len,
+                       const char* header, int64_t header_len, char* out, int64_t out_cap, int64_t* out_len, int* mode_out) {
+    if (!out) return set_error(SCCG_E_ARG, "null argument");
+    return compress_host(c, ref, ref_len, tgt, tgt_len, header, header_len, out, out_cap, nullptr, out_len, mode_out);
 }
 
 int sccg_match_sequences(sccg_ctx* c, const char* Sr, int64_t nr, const char* St, int64_t nt,
@@ -204,9 +215,9 @@ int sccg_reconstruct_device(sccg_ctx* c, const void* d_ref, int64_t ref_len, con
     return SCCG_OK;
 }
 
-int sccg_reconstruct(sccg_ctx* c, const char* ref, int64_t ref_len, const char* encoded, int64_t enc_len,
-                     const char* n_idx, int64_t n_len, const char* low_idx, int64_t low_len, char** out, int64_t* out_len) {
-    if (!c || !out || !out_len || (ref_len > 0 && !ref) || (enc_len > 0 && !encoded) || (n_len > 0 && !n_idx) || (low_len > 0 && !low_idx))
+static int reconstruct_host(sccg_ctx* c, const char* ref, int64_t ref_len, const char* encoded, int64_t enc_len, const char* n_idx, int64_t n_len,
+                            const char* low_idx, int64_t low_len, char* dst, int64_t dst_cap, char** out, int64_t* out_len) {
+    if (!c || !out_len || (ref_len > 0 && !ref) || (enc_len > 0 && !encoded) || (n_len > 0 && !n_idx) || (low_len > 0 && !low_idx))
         return set_error(SCCG_E_ARG, "null argument");
     SCCG_TRY(check_sizes(ref_len, enc_len));
     SCCG_TRY(check_sizes(n_len, low_len));
@@ -222,13 +233,24 @@ int sccg_reconstruct(sccg_ctx* c, const char* ref, int64_t ref_len, const char* 
     u8* d_res = nullptr; i64 n = 0;
     SCCG_TRY(reconstruct_device(c, d_ref, ref_len, d_enc, enc_len, d_n, n_len, d_low, low_len, 0, &d_res, &n));
     SCCG_CK(cudaEventRecord(c->ev[6], c->stream));
-    SCCG_TRY(download(c, d_res, n, out));
+    SCCG_TRY(deliver(c, d_res, n, dst, dst_cap, out, out_len));
     SCCG_CK(cudaEventRecord(c->ev[7], c->stream));
     SCCG_CK(cudaStreamSynchronize(c->stream));
     cudaEventElapsedTime(&c->prof.h2d_ms, c->ev[4], c->ev[5]);
     cudaEventElapsedTime(&c->prof.d2h_ms, c->ev[6], c->ev[7]);
-    *out_len = n;
     return SCCG_OK;
+}
+
+int sccg_reconstruct(sccg_ctx* c, const char* ref, int64_t ref_len, const char* encoded, int64_t enc_len,
+                     const char* n_idx, int64_t n_len, const char* low_idx, int64_t low_len, char** out, int64_t* out_len) {
+    if (!out) return set_error(SCCG_E_ARG, "null argument");
+    return reconstruct_host(c, ref, ref_len, encoded, enc_len, n_idx, n_len, low_idx, low_len, nullptr, 0, out, out_len);
+}
+
+int sccg_reconstruct_into(sccg_ctx* c, const char* ref, int64_t ref_len, const char* encoded, int64_t enc_len,
+                          const char* n_idx, int64_t n_len, const char* low_idx, int64_t low_len, char* out, int64_t out_cap, int64_t* out_len) {
+    if (!out) return set_error(SCCG_E_ARG, "null argument");
+    return reconstruct_host(c, ref, ref_len, encoded, enc_len, n_idx, n_len, low_idx, low_len, out, out_cap, nullptr, out_len);
 }
 
 int sccg_decompress(sccg_ctx* c, const char* ref_raw, int64_t ref_len, const char* inter, int64_t inter_len, char** out, int64_t* out_len) {
@@ -236,7 +258,15 @@ int sccg_decompress(sccg_ctx* c, const char* ref_raw, int64_t ref_len, const cha
     SCCG_TRY(check_sizes(ref_len, inter_len));
     SCCG_CK(cudaSetDevice(c->device));
     prof_reset(c);
-    return decompress_host(c, ref_raw, ref_len, inter, inter_len, out, out_len);
+    return decompress_host(c, ref_raw, ref_len, inter, inter_len, nullptr, 0, out, out_len);
+}
+
+int sccg_decompress_into(sccg_ctx* c, const char* ref_raw, int64_t ref_len, const char* inter, int64_t inter_len, char* out, int64_t out_cap, int64_t* out_len) {
+    if (!c || !out || !out_len || (ref_len > 0 && !ref_raw) || (inter_len > 0 && !inter)) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_TRY(check_sizes(ref_len, inter_len));
+    SCCG_CK(cudaSetDevice(c->device));
+    prof_reset(c);
+    return decompress_host(c, ref_raw, ref_len, inter, inter_len, out, out_cap, nullptr, out_len);
 }
 
 }  // extern "C"

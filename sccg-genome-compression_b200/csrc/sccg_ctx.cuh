@@ -105,6 +105,18 @@ static int download(sccg_ctx* c, const u8* d, i64 n, char** out) {
     return SCCG_OK;
 }
 
+// result delivery: either into a buffer of the caller (dst != NULL; pin it for full PCIe speed) or into a fresh malloc
+static int deliver(sccg_ctx* c, const u8* d, i64 n, char* dst, i64 dst_cap, char** out_alloc, int64_t* out_len) {
+    *out_len = n;
+    if (!dst) return download(c, d, n, out_alloc);
+    if (dst_cap < n) return set_error(SCCG_E_ARG, "output buffer too small (required size returned in *out_len)");
+    if (n > 0) {
+        SCCG_CK(cudaMemcpyAsync(dst, d, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        SCCG_CK(cudaStreamSynchronize(c->stream));
+    }
+    return SCCG_OK;
+}
+
 
 
 }  // namespace sccg

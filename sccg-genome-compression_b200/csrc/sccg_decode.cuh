@@ -508,7 +508,7 @@ static int reconstruct_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_
 
 
 // decompress_genome's in-memory part (decompression.cpp:66-110) + reconstruct_genome + main's "<header>\n" (:322)
-static int decompress_host(sccg_ctx* c, const char* ref_raw, i64 ref_len, const char* inter, i64 inter_len, char** out, int64_t* out_len) {
+static int decompress_host(sccg_ctx* c, const char* ref_raw, i64 ref_len, const char* inter, i64 inter_len, char* dst, i64 dst_cap, char** out, int64_t* out_len) {
     // ---- the 3 / 4 getline calls (:66-101)
     const char* lines[4] = {inter, inter, inter, inter};
     i64 lens[4] = {0, 0, 0, 0};
@@ -556,12 +556,11 @@ static int decompress_host(sccg_ctx* c, const char* ref_raw, i64 ref_len, const 
     ((char*)c->h_pinned)[nh] = '\n';
     SCCG_CK(cudaMemcpyAsync(d_text - (nh + 1), c->h_pinned, (size_t)nh + 1, cudaMemcpyHostToDevice, c->stream));
     SCCG_CK(cudaEventRecord(c->ev[6], c->stream));
-    SCCG_TRY(download(c, d_text - (nh + 1), n + nh + 1, out));
+    SCCG_TRY(deliver(c, d_text - (nh + 1), n + nh + 1, dst, dst_cap, out, out_len));
     SCCG_CK(cudaEventRecord(c->ev[7], c->stream));
     SCCG_CK(cudaStreamSynchronize(c->stream));
     cudaEventElapsedTime(&c->prof.h2d_ms, c->ev[4], c->ev[5]);
     cudaEventElapsedTime(&c->prof.d2h_ms, c->ev[6], c->ev[7]);
-    *out_len = n + nh + 1;
     return SCCG_OK;
 }
 

@@ -24,7 +24,10 @@ static const int LM_HT_BITS = 9;              // 512 chain heads for <= 987 k-me
 static const int LM_HT = 1 << LM_HT_BITS;
 static const int LM_SEQ_PAD = 1040;
 static const int LM_SLOT = 100;               // max matches per segment: 1000 / k' (k' = 10)
-static const u32 LM_HASH_B = 0x01000193u;
+// k-mer hash: h = sum over the k-mer of c_i * 2^(s * (k-1-i)) mod 2^32 with s = ceil(32 / k): symbols older than the
+// last ceil(32/s) <= k have left the 32-bit register, so sliding by one symbol is a single multiply-add with the
+// incoming symbol (no outgoing term).  Collisions are harmless: every chain entry is verified symbol by symbol.
+__host__ __device__ __forceinline__ int lm_hash_shift(int k) { return (32 + k - 1) / k; }
 
 struct LmWarpSmem {
     u8 r[LM_SEQ_PAD];
@@ -42,7 +45,7 @@ struct LmWarpSmem {
 
 __device__ __forceinline__ u32 lm_mix(u32 h) { return h * 0x9E3779B1u; }
 __device__ __forceinline__ u32 lm_bucket(u32 hm) { return hm >> (32 - LM_HT_BITS); }
-__device__ __forceinline__ u32 lm_tag(u32 hm) { return (hm >> (32 - LM_HT_BITS - 6)) & 0x3fu; }
+__device__ __forceinline__ u32 lm_tag(u32 hm) { return (hm >> (32 - LM_HT_BITS - 16)) & 0xfc00u; }   // 6 tag bits at bit 10
 
 __device__ __forceinline__ u32 ld_unaligned32(const u8* base, int off) {
     const u32* w = reinterpret_cast<const u32*>(base);
@@ -94,24 +97,25 @@ __device__ __forceinline__ int diag_lcp(const LmWarpSmem& S, const u32 (&wm)[4],
 }
 
 // k-mer index of r[0..Lr) (compression.cpp:41-47) as a chained hash table
-__device__ __forceinline__ void lm_build_index(LmWarpSmem& S, int Lr, int k, u32 bk1) {
+__device__ __forceinline__ void lm_build_index(LmWarpSmem& S, int Lr, int k) {
     const int lane = lane_of();
     for (int x = lane; x < LM_HT; x += 32) S.head[x] = 0u;
     __syncwarp();
     int nk = Lr - k + 1;
     if (nk > 0) {
+        const u32 mul = 1u << lm_hash_shift(k);
         int chunk = (nk + 31) >> 5;
         int p = lane * chunk;
         int p1 = p + chunk < nk ? p + chunk : nk;
         if (p < p1) {
             u32 h = 0u;
-            for (int i = 0; i < k; ++i) h = h * LM_HASH_B + S.r[p + i];
-            for (;;) {
+            for (int i = 0; i < k - 1; ++i) h = h * mul + S.r[p + i];
+            const u8* in = S.r + (k - 1);
+            for (; p < p1; ++p) {
+                h = h * mul + in[p];                                             // slide: symbol p + k - 1 enters
                 u32 hm = lm_mix(h);
-                u32 old = atomicExch(&S.head[lm_bucket(hm)], (u32)(p + 1) | (lm_tag(hm) << 10));
+                u32 old = atomicExch(&S.head[lm_bucket(hm)], (u32)(p + 1) | lm_tag(hm));
                 S.next[p] = (u16)old;
-                if (++p >= p1) break;
-                h = (h - (u32)S.r[p - 1] * bk1) * LM_HASH_B + S.r[p - 1 + k];   // roll one symbol
             }
         }
     }
@@ -156,7 +160,7 @@ __device__ __forceinline__ int lm_parse(LmWarpSmem& S, const u32 (&wm)[4], int L
         u32 term = lane < k ? (u32)S.t[j + lane] * powk : 0u;
         u32 hm = lm_mix(__reduce_add_sync(SCCG_FULL_MASK, term));
         u32 c = S.head[lm_bucket(hm)];
-        const u32 qtag = lm_tag(hm);
+        const u32 qtag = lm_tag(hm);                                             // already positioned at bit 10
         const u32 tag = ld_unaligned32(S.t, j);
         LmFold f; f.best_l = 0; f.cnt = 0; f.zero_in = false; f.best_key = 0xffffffffu;
         while (c) {                                                              // :114 every candidate of the bucket
@@ -164,7 +168,7 @@ __device__ __forceinline__ int lm_parse(LmWarpSmem& S, const u32 (&wm)[4], int L
             int myp = -1, nb = 0;
             while (c && nb < 32) {
                 int p = (int)(c & 0x3ffu) - 1;
-                u32 ctag = c >> 10;
+                u32 ctag = c & 0xfc00u;
                 c = S.next[p];
                 if (ctag == qtag && ld_unaligned32(S.r, p) == tag) { if (lane == nb) myp = p; ++nb; }
             }
@@ -235,13 +239,13 @@ __global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restric
     const int warps_total = (int)(gridDim.x * (blockDim.x >> 5));
     const int warp_global = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
 
-    // B^(k-1-lane) for the cooperative k-mer hash, B^(k-1) for the rolling update
-    u32 pow1 = 0u, pow2 = 0u, bk1_1 = 1u, bk1_2 = 1u;
+    // 2^(s*(k-1-lane)) for the cooperative k-mer hash of a target position (0 once the symbol has left the register)
+    u32 pow1 = 0u, pow2 = 0u;
     {
-        u32 x = 1u;
-        for (int i = 0; i < k1; ++i) { if (lane == k1 - 1 - i) pow1 = x; if (i == k1 - 1) bk1_1 = x; x *= LM_HASH_B; }
-        x = 1u;
-        for (int i = 0; i < k2; ++i) { if (lane == k2 - 1 - i) pow2 = x; if (i == k2 - 1) bk1_2 = x; x *= LM_HASH_B; }
+        int sh = lm_hash_shift(k1) * (k1 - 1 - lane);
+        if (lane < k1 && sh < 32) pow1 = 1u << sh;
+        sh = k2 > 0 ? lm_hash_shift(k2) * (k2 - 1 - lane) : 32;
+        if (lane < k2 && sh < 32) pow2 = 1u << sh;
     }
 
     // segments are claimed dynamically (their cost varies by an order of magnitude) and the next segment's
@@ -287,10 +291,10 @@ __global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restric
             if (lane == 0) S.mlist[0] = 0u | (0u << 10) | ((u32)Lt << 20);
             nmatch = 1;
         } else {
-            lm_build_index(S, Lr, k1, bk1_1);
+            lm_build_index(S, Lr, k1);
             nmatch = lm_parse(S, wm, Lr, Lt, k1, pow1);                              // compression.cpp:401
             if (nmatch == 0 && k2 > 0) {
-                lm_build_index(S, Lr, k2, bk1_2);
+                lm_build_index(S, Lr, k2);
                 nmatch = lm_parse(S, wm, Lr, Lt, k2, pow2);                          // compression.cpp:428
             }
         }
