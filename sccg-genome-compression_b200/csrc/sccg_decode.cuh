@@ -331,15 +331,19 @@ __device__ __forceinline__ u8 gather_byte(const GatherArgs& a, const int* win, u
     i64 bb = (i64)line * WRAP + col;
     int nk = bounded_upper_i32(a.n_start, win[2], win[3], bb);
     i64 s = bb;
+    bool is_n = false;
     if (nk >= 0) {
         i64 st = a.n_start[nk], ln = a.n_len[nk];
-        if (bb < st + ln) return 'N';
-        s = bb - ((i64)a.n_cum[nk] + ln);
+        if (bb < st + ln) is_n = true;
+        else s = bb - ((i64)a.n_cum[nk] + ln);
     }
-    int sk = bounded_upper_u32(a.seg_dst, win[0], win[1], s);
-    i64 src = a.seg_src[sk];
-    i64 within = s - (i64)a.seg_dst[sk];
-    u8 o = (src & SEG_LIT_FLAG) ? a.enc[(src & ~SEG_LIT_FLAG) + within] : a.ref[(i64)a.tok_abs[src] + within];
+    u8 o = 'N';
+    if (!is_n) {
+        int sk = bounded_upper_u32(a.seg_dst, win[0], win[1], s);
+        i64 src = a.seg_src[sk];
+        i64 within = s - (i64)a.seg_dst[sk];
+        o = (src & SEG_LIT_FLAG) ? a.enc[(src & ~SEG_LIT_FLAG) + within] : a.ref[(i64)a.tok_abs[src] + within];
+    }
     int lk = bounded_upper_i32(a.l_start, win[4], win[5], bb);
     if (lk >= 0 && bb < (i64)a.l_start[lk] + (i64)a.l_len[lk]) o = lower1(o);
     return o;

@@ -79,7 +79,7 @@ def make_record_stream(seed):
     return ref, bytes(body), nlist, low
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(40))
 def test_reconstruct_random_vs_oracle(ctx, seed):
     ref, body, nlist, low = make_record_stream(seed)
     rc, exp = ol.orc_reconstruct(ref, body, nlist, low)
@@ -101,6 +101,7 @@ def test_reconstruct_errors(ctx):
         assert e.value.code == sccg_b200.SCCG_E_FORMAT
     assert ctx.reconstruct(ref, b"", b"", b"") == b"\n"
     assert ctx.reconstruct(ref, b"ACGT", b"", b"1,") == b"AcGT\n"
+    assert ctx.reconstruct(ref, b"ACGT", b"(1,2)", b"(0,3)") == b"annCGT\n"      # a lowercase run covers re-inserted N
 
 
 @pytest.mark.parametrize("shape", ["local", "gap", "divergent"])
