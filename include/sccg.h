@@ -55,6 +55,8 @@ typedef struct {
     float gather_ms;      /* decompress: reference-copy / literal gather + case/N/wrap  */
     int32_t launches;     /* kernels launched by the call                               */
     int32_t mode;         /* compress: 0 local, 1 global                                */
+    int32_t front_steps;  /* global parse: exact steps the sequential front executed itself */
+    int32_t spec_rounds;  /* global parse: speculation rounds (1 + number of "lost" re-speculations) */
 } sccg_profile;
 
 sccg_ctx*   sccg_create(int device);                 /* NULL on failure (see sccg_last_error)      */

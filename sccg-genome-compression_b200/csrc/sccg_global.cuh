@@ -176,113 +176,311 @@ __device__ __forceinline__ int fold_result_p(const GpShared& S) {
     return (S.cnt == 1 && S.zero_in) ? 0 : (int)(S.best_key & 0xffffffffULL);
 }
 
-__global__ void __launch_bounds__(GP_T) global_parse_k(GpArgs a) {
-    __shared__ GpShared S;
+// One step of the parse loop (:64-161) from state (j, e): scans [j, scan_end) for the first position that yields a match
+// (everything before it is literal, :77-96).  Found: j = that position, (sel_p, sel_l) = the chosen candidate, returns
+// true.  Not found: j = scan_end (state e unchanged), returns false.  All threads, uniform arguments.
+__device__ __forceinline__ bool gp_step(GpShared& S, const GpArgs& a, i64& j, int e, i64 scan_end, int& sel_p, int& sel_l) {
     const int tid = (int)threadIdx.x;
     const int k = a.k;
-    i64 j = 0;
-    int e = -1;                                                   // prev_match_end :51
-    u32 nmatch = 0;
-    const i64 last_j = a.nt - k;                                  // loop: index < L - k + 1  (:64)
-
-    while (j <= last_j) {
-        int sel_p = 0, sel_l = 0;
-        if (e == -1) {
-            // ---- no match yet: first position whose k-mer occurs anywhere in the reference (:77, all candidates in range :87)
-            i64 found = -1;
-            for (; j <= last_j; j += GP_T) {
-                i64 pos = j + tid;
-                bool hit = false;
-                if (pos <= last_j) {
-                    u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
-                    u32 h = kmer_hash_words(w0, w1, k);
-                    i64 lo = 0, hi = a.nk;
-                    while (lo < hi) { i64 mid = (lo + hi) >> 1; if (a.keys[mid] < h) lo = mid + 1; else hi = mid; }
-                    for (; lo < a.nk && a.keys[lo] == h && !hit; ++lo) {
-                        const u8* rp = a.R + a.vals[lo];
-                        hit = kmer_equal_words(ld_unaligned64(rp), ld_unaligned64(rp + 8), w0, w1, k);
-                    }
-                }
-                if (tid == 0) S.i_scratch[4] = 0x7fffffff;
-                if (__syncthreads_or(hit)) {
-                    if (hit) atomicMin(&S.i_scratch[4], tid);
-                    __syncthreads();
-                    found = j + S.i_scratch[4];
-                    __syncthreads();
-                    break;
+    i64 found = -1;
+    if (e == -1) {
+        // ---- no match yet: first position whose k-mer occurs anywhere in the reference (:77, all candidates in range :87)
+        for (; j < scan_end; j += GP_T) {
+            i64 pos = j + tid;
+            bool hit = false;
+            if (pos < scan_end) {
+                u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
+                u32 h = kmer_hash_words(w0, w1, k);
+                i64 lo = 0, hi = a.nk;
+                while (lo < hi) { i64 mid = (lo + hi) >> 1; if (a.keys[mid] < h) lo = mid + 1; else hi = mid; }
+                for (; lo < a.nk && a.keys[lo] == h && !hit; ++lo) {
+                    const u8* rp = a.R + a.vals[lo];
+                    hit = kmer_equal_words(ld_unaligned64(rp), ld_unaligned64(rp + 8), w0, w1, k);
                 }
             }
-            if (found < 0) break;
-            j = found;
-            fold_index_candidates(S, a, j, e);
-            sel_p = fold_result_p(S); sel_l = S.best_l;
-            __syncthreads();
-        } else {
-            // ---- banded state: candidates must satisfy |p - e| <= m (:87, :116)
-            i64 wlo = (i64)e - a.m; if (wlo < 0) wlo = 0;
-            i64 whi = (i64)e + a.m; if (whi > a.nr - k) whi = a.nr - k;
-            if (whi < wlo) break;                                 // no reference k-mer can ever be in range again
-            const int wlen = (int)(whi - wlo + 1);
-            const int wbytes = wlen + k - 1;
-            for (int x = tid; x < GP_FILTER; x += GP_T) S.f_hash[x] = 0u;
-            for (int x = tid; x < GP_WIN_BYTES; x += GP_T) S.win[x] = x < wbytes ? a.R[wlo + x] : (u8)0;
-            __syncthreads();
-            if (tid < wlen) {
-                u32 h = kmer_hash_words(ld_unaligned64(S.win + tid), ld_unaligned64(S.win + tid + 8), k) | 1u;
-                u32 slot = (h >> 1) & (GP_FILTER - 1);
-                while (atomicCAS(&S.f_hash[slot], 0u, h) != 0u) slot = (slot + 1) & (GP_FILTER - 1);
-                S.f_off[slot] = (u8)tid;
-            }
-            __syncthreads();
-            // scan the target for the first position whose k-mer is in the window; everything before it is literal (:77-96)
-            i64 found = -1;
-            for (; j <= last_j; j += GP_T) {
-                i64 pos = j + tid;
-                bool hit = false;
-                if (pos <= last_j) {
-                    u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
-                    u32 h = kmer_hash_words(w0, w1, k) | 1u;
-                    u32 slot = (h >> 1) & (GP_FILTER - 1);
-                    for (u32 fh; (fh = S.f_hash[slot]) != 0u && !hit; slot = (slot + 1) & (GP_FILTER - 1)) {
-                        if (fh == h) {
-                            const u8* wp = S.win + S.f_off[slot];
-                            hit = kmer_equal_words(ld_unaligned64(wp), ld_unaligned64(wp + 8), w0, w1, k);
-                        }
-                    }
-                }
-                if (tid == 0) S.i_scratch[4] = 0x7fffffff;
-                if (__syncthreads_or(hit)) {
-                    if (hit) atomicMin(&S.i_scratch[4], tid);
-                    __syncthreads();
-                    found = j + S.i_scratch[4];
-                    __syncthreads();
-                    break;
-                }
-            }
-            if (found < 0) break;
-            j = found;
-            // in-range candidates: the window positions whose k-mer equals T[j..j+k)  (pn2 / ln2, :116-123)
-            i64 cand = -1;
-            if (tid < wlen) {
-                u64 w0 = ld_unaligned64(a.T + j), w1 = ld_unaligned64(a.T + j + 8);
-                if (kmer_equal_words(ld_unaligned64(S.win + tid), ld_unaligned64(S.win + tid + 8), w0, w1, k)) cand = wlo + tid;
-            }
-            fold_reset(S);
-            fold_chunk(S, a, cand, j, e);
-            sel_p = fold_result_p(S); sel_l = S.best_l;
-            __syncthreads();
-            if (sel_p == 0) {                                     // `pn2 != 0` fails (:134): unrestricted best over ALL candidates
-                fold_index_candidates(S, a, j, e);
-                sel_p = fold_result_p(S); sel_l = S.best_l;
+            if (tid == 0) S.i_scratch[4] = 0x7fffffff;
+            if (__syncthreads_or(hit)) {
+                if (hit) atomicMin(&S.i_scratch[4], tid);
                 __syncthreads();
+                found = j + S.i_scratch[4];
+                __syncthreads();
+                break;
             }
         }
-        if (tid == 0) { a.m_tpos[nmatch] = (int)j; a.m_p[nmatch] = sel_p; a.m_l[nmatch] = sel_l; }   // :152-156
-        ++nmatch;
-        e = sel_p + sel_l - 1;                                    // :149
-        j += sel_l;                                               // :159
+        if (found < 0) { j = scan_end; return false; }
+        j = found;
+        fold_index_candidates(S, a, j, e);
+        sel_p = fold_result_p(S); sel_l = S.best_l;
+        __syncthreads();
+        return true;
     }
-    if (tid == 0) *a.d_count = nmatch;
+    // ---- banded state: candidates must satisfy |p - e| <= m (:87, :116)
+    i64 wlo = (i64)e - a.m; if (wlo < 0) wlo = 0;
+    i64 whi = (i64)e + a.m; if (whi > a.nr - k) whi = a.nr - k;
+    if (whi < wlo) { j = scan_end; return false; }            // no reference k-mer can be in range: literals only
+    const int wlen = (int)(whi - wlo + 1);
+    const int wbytes = wlen + k - 1;
+    for (int x = tid; x < GP_FILTER; x += GP_T) S.f_hash[x] = 0u;
+    for (int x = tid; x < GP_WIN_BYTES; x += GP_T) S.win[x] = x < wbytes ? a.R[wlo + x] : (u8)0;
+    __syncthreads();
+    if (tid < wlen) {
+        u32 h = kmer_hash_words(ld_unaligned64(S.win + tid), ld_unaligned64(S.win + tid + 8), k) | 1u;
+        u32 slot = (h >> 1) & (GP_FILTER - 1);
+        while (atomicCAS(&S.f_hash[slot], 0u, h) != 0u) slot = (slot + 1) & (GP_FILTER - 1);
+        S.f_off[slot] = (u8)tid;
+    }
+    __syncthreads();
+    for (; j < scan_end; j += GP_T) {
+        i64 pos = j + tid;
+        bool hit = false;
+        if (pos < scan_end) {
+            u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
+            u32 h = kmer_hash_words(w0, w1, k) | 1u;
+            u32 slot = (h >> 1) & (GP_FILTER - 1);
+            for (u32 fh; (fh = S.f_hash[slot]) != 0u && !hit; slot = (slot + 1) & (GP_FILTER - 1)) {
+                if (fh == h) {
+                    const u8* wp = S.win + S.f_off[slot];
+                    hit = kmer_equal_words(ld_unaligned64(wp), ld_unaligned64(wp + 8), w0, w1, k);
+                }
+            }
+        }
+        if (tid == 0) S.i_scratch[4] = 0x7fffffff;
+        if (__syncthreads_or(hit)) {
+            if (hit) atomicMin(&S.i_scratch[4], tid);
+            __syncthreads();
+            found = j + S.i_scratch[4];
+            __syncthreads();
+            break;
+        }
+    }
+    if (found < 0) { j = scan_end; return false; }
+    j = found;
+    // in-range candidates: the window positions whose k-mer equals T[j..j+k)  (pn2 / ln2, :116-123)
+    i64 cand = -1;
+    if (tid < wlen) {
+        u64 w0 = ld_unaligned64(a.T + j), w1 = ld_unaligned64(a.T + j + 8);
+        if (kmer_equal_words(ld_unaligned64(S.win + tid), ld_unaligned64(S.win + tid + 8), w0, w1, k)) cand = wlo + tid;
+    }
+    fold_reset(S);
+    fold_chunk(S, a, cand, j, e);
+    sel_p = fold_result_p(S); sel_l = S.best_l;
+    __syncthreads();
+    if (sel_p == 0) {                                         // `pn2 != 0` fails (:134): unrestricted best over ALL candidates
+        fold_index_candidates(S, a, j, e);
+        sel_p = fold_result_p(S); sel_l = S.best_l;
+        __syncthreads();
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Chunk-speculative execution of the sequential parse.
+//
+// The parse is a deterministic function of its state (index j, prev_match_end e).  The target is cut into chunks of
+// GP_CHUNK positions; gp_spec_k parses every chunk in parallel (one CTA each) from a GUESSED entry state until the
+// index leaves the chunk, recording its matches and exit state.  gp_front_k then walks the true state from (0, -1):
+// whenever the true state equals a chunk's entry guess or the state after one of its recorded matches, the rest of
+// that chunk's speculative output is provably what the sequential parse would produce and is accepted wholesale;
+// otherwise the front executes exact steps itself until the states meet again.  Two guesses per chunk:
+//   slot 0 (DIAG): the parse is inside a match on the diagonal d found by looking one k-mer near the chunk start up in
+//                  the index; the entry state is then (first mismatch on that diagonal after the boundary, its e);
+//   slot 1 (LOST): the parse reaches the boundary with a given e and no usable candidate ("lost" after a rearrangement);
+//                  re-issued by the host every time the front gets lost with a new e.
+// ------------------------------------------------------------------------------------------------
+static const int GP_CHUNK_DEFAULT = 32768;      // positions per speculative chunk (SCCG_GP_CHUNK overrides it: tests use tiny chunks)
+static const int GP_DIAG_PROBES = 64;
+
+struct GpChunkInfo { i64 entry_j; i64 exit_j; int entry_e; int exit_e; u32 count; int valid; };
+
+struct GpSpecArgs {
+    GpArgs a;
+    GpChunkInfo* info;          // [2][nchunks]
+    int* c_tpos; int* c_p; int* c_l;   // [2][nchunks][cap_c]
+    u32 nchunks, cap_c;
+    int chunk;                  // positions per chunk
+    int slot;                   // 0 DIAG, 1 LOST
+    u32 first_chunk;            // chunks >= first_chunk are (re)computed
+    int lost_e;                 // slot 1: the e every chunk is entered with
+};
+
+__global__ void __launch_bounds__(GP_T) gp_spec_k(GpSpecArgs s) {
+    __shared__ GpShared S;
+    const GpArgs& a = s.a;
+    const int tid = (int)threadIdx.x;
+    const u32 c = s.first_chunk + blockIdx.x;
+    if (c >= s.nchunks) return;
+    const i64 B = (i64)c * s.chunk, last_j = a.nt - a.k;
+    const i64 j_stop = B + s.chunk;
+    GpChunkInfo* info = s.info + (size_t)s.slot * s.nchunks + c;
+    const size_t base = ((size_t)s.slot * s.nchunks + c) * s.cap_c;
+    i64 j = B;
+    int e = s.lost_e;
+    bool valid = true;
+    if (s.slot == 0) {
+        // diagonal guess: the first probe position whose k-mer has exactly one exact occurrence in the reference
+        int d_found = 0x7fffffff;
+        i64 my_d = 0;
+        if (tid < GP_DIAG_PROBES && B + tid <= last_j) {
+            i64 pos = B + tid;
+            u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
+            u32 h = kmer_hash_words(w0, w1, a.k);
+            i64 lo = 0, hi = a.nk;
+            while (lo < hi) { i64 mid = (lo + hi) >> 1; if (a.keys[mid] < h) lo = mid + 1; else hi = mid; }
+            int hits = 0;
+            for (; lo < a.nk && a.keys[lo] == h && hits < 2; ++lo) {
+                const u8* rp = a.R + a.vals[lo];
+                if (kmer_equal_words(ld_unaligned64(rp), ld_unaligned64(rp + 8), w0, w1, a.k)) { ++hits; my_d = (i64)a.vals[lo] - pos; }
+            }
+            if (hits == 1) d_found = tid;
+        }
+        if (tid == 0) S.i_scratch[5] = 0x7fffffff;
+        __syncthreads();
+        if (d_found != 0x7fffffff) atomicMin(&S.i_scratch[5], d_found);
+        __syncthreads();
+        int winner = S.i_scratch[5];
+        if (tid == winner) { S.i_scratch[6] = (int)(my_d & 0xffffffff); S.i_scratch[7] = (int)(my_d >> 32); }
+        __syncthreads();
+        if (winner == 0x7fffffff) valid = false;
+        else {
+            i64 d = ((i64)S.i_scratch[7] << 32) | (u32)S.i_scratch[6];
+            i64 p0 = B + d;
+            if (p0 < 0 || p0 >= a.nr) valid = false;
+            else {
+                i64 maxl = (a.nr - p0) < (a.nt - B) ? (a.nr - p0) : (a.nt - B);
+                i64 l = block_lcp(S, a.R, p0, a.T, B, maxl);       // the match covering the boundary ends at its first mismatch
+                j = B + l;
+                i64 ee = j + d - 1;
+                if (ee < 0 || ee > 0x7fffffff) valid = false; else e = (int)ee;
+            }
+        }
+        __syncthreads();
+    }
+    u32 n = 0;
+    const i64 entry_j = j;
+    const int entry_e = e;
+    if (valid) {
+        while (j < j_stop && j <= last_j) {
+            int sel_p = 0, sel_l = 0;
+            i64 scan_end = j_stop < last_j + 1 ? j_stop : last_j + 1;
+            if (!gp_step(S, a, j, e, scan_end, sel_p, sel_l)) break;
+            if (tid == 0) { s.c_tpos[base + n] = (int)j; s.c_p[base + n] = sel_p; s.c_l[base + n] = sel_l; }
+            ++n;
+            e = sel_p + sel_l - 1;
+            j += sel_l;
+        }
+    }
+    if (tid == 0) { info->entry_j = entry_j; info->entry_e = entry_e; info->exit_j = j; info->exit_e = e; info->count = n; info->valid = valid ? 1 : 0; }
+}
+
+// pieces of the final match list, in order: a run of the front's own matches or a suffix of a chunk's speculative list
+struct GpPiece { u32 src; u32 first; u32 count; };          // src: 0xffffffff = front buffer, else slot * nchunks + chunk
+struct GpFrontState { i64 j; int e; int status; u32 npieces; u32 nfront; u32 lost_from_chunk; int lost_e; u32 steps; u32 spliced; };
+enum { GP_RUNNING = 0, GP_DONE = 1, GP_LOST = 2 };
+
+struct GpFrontArgs {
+    GpSpecArgs s;
+    GpFrontState* st;
+    GpPiece* pieces; u32 cap_pieces;
+    int* f_tpos; int* f_p; int* f_l;       // the front's own matches
+};
+
+__global__ void __launch_bounds__(GP_T) gp_front_k(GpFrontArgs f) {
+    __shared__ GpShared S;
+    const GpArgs& a = f.s.a;
+    const int tid = (int)threadIdx.x;
+    const i64 last_j = a.nt - a.k;
+    i64 j = f.st->j;
+    int e = f.st->e;
+    u32 npieces = f.st->npieces, nfront = f.st->nfront, steps = f.st->steps, spliced = f.st->spliced;
+    int lost_streak = 0;
+    int status = GP_RUNNING;
+    __syncthreads();
+    while (true) {
+        if (j > last_j) { status = GP_DONE; break; }
+        const u32 c = (u32)(j / f.s.chunk);
+        // ---- splice: does a speculative run of chunk c pass through the true state (j, e)?
+        bool took = false;
+        for (int slot = 0; slot < 2 && !took; ++slot) {
+            const GpChunkInfo ci = f.s.info[(size_t)slot * f.s.nchunks + c];
+            if (!ci.valid) continue;
+            const size_t base = ((size_t)slot * f.s.nchunks + c) * f.s.cap_c;
+            int first = -1;
+            if (ci.entry_j == j && ci.entry_e == e) first = 0;
+            else if (ci.count) {
+                // the state after match i is (tpos + l, p + l - 1); tpos + l is increasing: binary search
+                int lo = 0, hi = (int)ci.count;
+                while (lo < hi) { int mid = (lo + hi) >> 1; if ((i64)f.s.c_tpos[base + mid] + f.s.c_l[base + mid] < j) lo = mid + 1; else hi = mid; }
+                if (lo < (int)ci.count && (i64)f.s.c_tpos[base + lo] + f.s.c_l[base + lo] == j && f.s.c_p[base + lo] + f.s.c_l[base + lo] - 1 == e)
+                    first = lo + 1;
+            }
+            if (first >= 0) {
+                if ((u32)first < ci.count) {
+                    if (tid == 0) { GpPiece pc; pc.src = (u32)slot * f.s.nchunks + c; pc.first = (u32)first; pc.count = ci.count - (u32)first; f.pieces[npieces] = pc; }
+                    ++npieces;
+                }
+                j = ci.exit_j; e = ci.exit_e;
+                took = true; ++spliced;
+                lost_streak = 0;
+            }
+        }
+        if (took) { if (npieces + 2 >= f.cap_pieces) { status = GP_LOST; break; } continue; }
+        // ---- exact step of the sequential parse, at most to the end of this chunk
+        int sel_p = 0, sel_l = 0;
+        i64 scan_end = (i64)(c + 1) * f.s.chunk;
+        if (scan_end > last_j + 1) scan_end = last_j + 1;
+        const i64 j_before = j;
+        ++steps;
+        if (gp_step(S, a, j, e, scan_end, sel_p, sel_l)) {
+            if (tid == 0) {
+                f.f_tpos[nfront] = (int)j; f.f_p[nfront] = sel_p; f.f_l[nfront] = sel_l;
+                if (npieces && f.pieces[npieces - 1].src == 0xffffffffu && f.pieces[npieces - 1].first + f.pieces[npieces - 1].count == nfront)
+                    f.pieces[npieces - 1].count++;
+            }
+            __syncthreads();
+            bool extend = npieces && f.pieces[npieces - 1].src == 0xffffffffu && f.pieces[npieces - 1].first + f.pieces[npieces - 1].count == nfront + 1;
+            if (!extend) {
+                if (tid == 0) { GpPiece pc; pc.src = 0xffffffffu; pc.first = nfront; pc.count = 1; f.pieces[npieces] = pc; }
+                ++npieces;
+            }
+            __syncthreads();
+            ++nfront;
+            e = sel_p + sel_l - 1;
+            j += sel_l;
+            lost_streak = 0;
+        } else if (e != -1 && j - j_before >= f.s.chunk / 2) {
+            // a long stretch without any usable candidate: the parse is "lost" with this e; let the host re-speculate
+            // the following chunks under that assumption (slot 1) unless they already are
+            if (++lost_streak >= 2) {
+                const u32 nc = (u32)(j / f.s.chunk);
+                bool have = nc < f.s.nchunks && f.s.info[(size_t)f.s.nchunks + nc].valid && f.s.info[(size_t)f.s.nchunks + nc].entry_e == e &&
+                            f.s.info[(size_t)f.s.nchunks + nc].entry_j == j;
+                if (!have && nc < f.s.nchunks) { status = GP_LOST; break; }
+            }
+        }
+        if (npieces + 2 >= f.cap_pieces) { status = GP_LOST; break; }
+    }
+    if (tid == 0) {
+        f.st->j = j; f.st->e = e; f.st->status = status; f.st->npieces = npieces; f.st->nfront = nfront; f.st->steps = steps; f.st->spliced = spliced;
+        f.st->lost_from_chunk = (u32)(j / f.s.chunk); f.st->lost_e = e;
+    }
+}
+
+// final match list = concatenation of the pieces
+__global__ void gp_piece_counts_k(const GpPiece* __restrict__ pieces, u32 n, u32* __restrict__ counts) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) counts[i] = pieces[i].count;
+}
+__global__ void __launch_bounds__(128) gp_concat_k(GpFrontArgs f, const u32* __restrict__ offs, u32 npieces, int* __restrict__ o_tpos, int* __restrict__ o_p, int* __restrict__ o_l) {
+    for (u32 i = blockIdx.x; i < npieces; i += gridDim.x) {
+        const GpPiece pc = f.pieces[i];
+        const int *st, *sp, *sl;
+        if (pc.src == 0xffffffffu) { st = f.f_tpos; sp = f.f_p; sl = f.f_l; }
+        else { size_t base = (size_t)pc.src * f.s.cap_c; st = f.s.c_tpos + base; sp = f.s.c_p + base; sl = f.s.c_l + base; }
+        const u32 o = offs[i];
+        for (u32 x = threadIdx.x; x < pc.count; x += blockDim.x) {
+            o_tpos[o + x] = st[pc.first + x]; o_p[o + x] = sp[pc.first + x]; o_l[o + x] = sl[pc.first + x];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -332,6 +530,7 @@ struct GlobalMatches { int* tpos; int* p; int* l; u32 count; };
 static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i64 nt, int k, int m, u32* sc, GlobalMatches* out) {
     if (k < 8 || k > 16) return set_error(SCCG_E_ARG, "global match_sequences supports 8 <= k <= 16");
     if (m < 0 || m > GP_MAX_M) return set_error(SCCG_E_ARG, "global match_sequences supports 0 <= m <= 120");
+    // ---- reference k-mer index (:41-47): hash32 keys + stable radix sort
     const i64 nk = nr - k + 1 > 0 ? nr - k + 1 : 0;
     u32 *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr;
     SCCG_TRY(buf(c, B_GKEYS, (size_t)nk + 1, &keys));
@@ -342,16 +541,58 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
         LAUNCH(c, kmer_keys_k, dim3(div_up(nk, 256)), dim3(256), 0, R, nk, k, keys, vals);
         SCCG_TRY(radix_sort_pairs(c, keys, vals, keys2, vals2, nk, B_GHIST));
     }
-    const size_t cap = (size_t)(nt / k) + 2;
-    int* mbuf = nullptr;
-    SCCG_TRY(buf(c, B_GREC, cap * 3, &mbuf));
-    GpArgs a;
-    a.R = R; a.nr = nr; a.T = T; a.nt = nt; a.keys = keys; a.vals = vals; a.nk = nk; a.k = k; a.m = m;
-    a.m_tpos = mbuf; a.m_p = mbuf + cap; a.m_l = mbuf + 2 * cap; a.d_count = sc + S_G1;
-    LAUNCH(c, global_parse_k, dim3(1), dim3(GP_T), 0, a);
+    // ---- chunk-speculative parse (:64-161)
+    int chunk = GP_CHUNK_DEFAULT;
+    if (const char* env = getenv("SCCG_GP_CHUNK")) { int v = atoi(env); if (v >= 64 && v <= (1 << 24)) chunk = v; }
+    const u32 nchunks = nt > 0 ? div_up(nt, chunk) : 1;
+    const u32 cap_c = (u32)(chunk / k) + 2;
+    const size_t cap_all = (size_t)(nt / k) + 2;
+    GpChunkInfo* info = nullptr; int* cbuf = nullptr; int* fbuf = nullptr; int* obuf = nullptr; GpPiece* pieces = nullptr; GpFrontState* st = nullptr; u32* pcounts = nullptr;
+    const u32 cap_pieces = (u32)(cap_all < 0x7ffffff0u ? cap_all : 0x7ffffff0u) + 2 * nchunks + 8;
+    SCCG_TRY(buf(c, B_GTMP1, (size_t)2 * nchunks + 1, &info));
+    SCCG_TRY(buf(c, B_GLIT, (size_t)2 * nchunks * cap_c * 3 + 1, &cbuf));
+    SCCG_TRY(buf(c, B_GTMP2, cap_all * 3 + 1, &fbuf));
+    SCCG_TRY(buf(c, B_GREC, cap_all * 3 + 1, &obuf));
+    SCCG_TRY(buf(c, B_GTMP3, (size_t)cap_pieces + 1, &pieces));
+    SCCG_TRY(buf(c, B_GOFFS, 4, &st));
+    SCCG_CK(cudaMemsetAsync(info, 0, sizeof(GpChunkInfo) * 2 * nchunks, c->stream));
+    GpFrontState h_st; memset(&h_st, 0, sizeof h_st);
+    h_st.j = 0; h_st.e = -1; h_st.status = GP_RUNNING;
+    SCCG_CK(cudaMemcpyAsync(st, &h_st, sizeof h_st, cudaMemcpyHostToDevice, c->stream));
+    GpFrontArgs f;
+    f.s.a.R = R; f.s.a.nr = nr; f.s.a.T = T; f.s.a.nt = nt; f.s.a.keys = keys; f.s.a.vals = vals; f.s.a.nk = nk; f.s.a.k = k; f.s.a.m = m;
+    f.s.a.m_tpos = nullptr; f.s.a.m_p = nullptr; f.s.a.m_l = nullptr; f.s.a.d_count = nullptr;
+    f.s.info = info; f.s.c_tpos = cbuf; f.s.c_p = cbuf + (size_t)2 * nchunks * cap_c; f.s.c_l = cbuf + (size_t)4 * nchunks * cap_c;
+    f.s.nchunks = nchunks; f.s.cap_c = cap_c; f.s.chunk = chunk; f.s.slot = 0; f.s.first_chunk = 1; f.s.lost_e = 0;
+    f.st = st; f.pieces = pieces; f.cap_pieces = cap_pieces; f.f_tpos = fbuf; f.f_p = fbuf + cap_all; f.f_l = fbuf + 2 * cap_all;
+    if (nchunks > 1) LAUNCH(c, gp_spec_k, dim3(nchunks - 1), dim3(GP_T), 0, f.s);        // slot 0: diagonal guesses, chunks 1..
+    for (int round = 0;; ++round) {
+        c->prof.spec_rounds = round + 1;
+        LAUNCH(c, gp_front_k, dim3(1), dim3(GP_T), 0, f);
+        SCCG_CK(cudaMemcpyAsync(c->h_pinned, st, sizeof h_st, cudaMemcpyDeviceToHost, c->stream));
+        SCCG_CK(cudaStreamSynchronize(c->stream));
+        memcpy(&h_st, c->h_pinned, sizeof h_st);
+        if (h_st.status == GP_DONE) break;
+        if (h_st.npieces + 2 >= cap_pieces) return set_error(SCCG_E_NOMEM, "internal: piece list overflow in the global parse");
+        if (h_st.status != GP_LOST || round > 1000000) return set_error(SCCG_E_CUDA, "internal: global parse did not terminate");
+        // lost with e = lost_e: speculate the remaining chunks under that assumption (slot 1)
+        GpSpecArgs ls = f.s;
+        ls.slot = 1; ls.first_chunk = h_st.lost_from_chunk; ls.lost_e = h_st.lost_e;
+        if (ls.first_chunk < nchunks) LAUNCH(c, gp_spec_k, dim3(nchunks - ls.first_chunk), dim3(GP_T), 0, ls);
+    }
+    // ---- concatenate the accepted pieces
+    const u32 np = h_st.npieces;
+    SCCG_TRY(buf(c, B_GTMP0, (size_t)np + 1, &pcounts));
+    if (np) LAUNCH(c, gp_piece_counts_k, dim3(div_up(np, 256)), dim3(256), 0, (const GpPiece*)pieces, np, pcounts);
+    SCCG_TRY(scan_exclusive_u32(c, pcounts, pcounts, (i64)np, sc + S_G1));
+    if (np) {
+        unsigned g = np < (unsigned)c->sm_count * 16u ? np : (unsigned)c->sm_count * 16u;
+        LAUNCH(c, gp_concat_k, dim3(g), dim3(128), 0, f, (const u32*)pcounts, np, obuf, obuf + cap_all, obuf + 2 * cap_all);
+    }
     u32 h[S_COUNT];
     SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
-    out->tpos = a.m_tpos; out->p = a.m_p; out->l = a.m_l; out->count = h[S_G1];
+    out->tpos = obuf; out->p = obuf + cap_all; out->l = obuf + 2 * cap_all; out->count = h[S_G1];
+    c->prof.front_steps = (int32_t)h_st.steps;
     return SCCG_OK;
 }
 

@@ -152,3 +152,29 @@ def test_compress_global_random(ctx, seed):
     got, gmode = ctx.compress(ref, tgt, b">g")
     assert mode == 1 and (gmode, got) == (mode, exp)
     assert ctx.decompress(ref, got) == ol.orc_decompress(ref, exp)[1]
+
+
+@pytest.mark.parametrize("chunk", [64, 300, 1024])
+@pytest.mark.parametrize("seed", range(8))
+def test_global_speculative_parse_small_chunks(ctx, seed, chunk):
+    """tiny speculation chunks: splices, failed guesses, lost re-speculation rounds and long matches skipping chunks"""
+    os.environ["SCCG_GP_CHUNK"] = str(chunk)
+    try:
+        alphabet = [b"ACGT", b"ACGT", b"AC", b"ACGT"][seed % 4]
+        n = 9000 if alphabet == b"ACGT" else 2500
+        ref, tgt = _mutated_pair(("spec", seed), n, alphabet, snp=[0.002, 0.02][seed % 2], indel=0.002)
+        r = random.Random(seed)
+        if seed % 2:
+            cut = sorted(r.sample(range(len(tgt)), 4))
+            parts = [tgt[:cut[0]], tgt[cut[0]:cut[1]], tgt[cut[1]:cut[2]], tgt[cut[2]:cut[3]], tgt[cut[3]:]]
+            r.shuffle(parts)
+            tgt = b"".join(parts)
+        if seed % 3 == 0:
+            tgt = tgt[:len(tgt) // 2] + rnd(3000, ("junk", seed)) + tgt[len(tgt) // 2:]     # long unmatched stretch: lost state
+        exp = [(x.p, x.l, x.lit) for x in ol.orc_match_sequences(ref, tgt, 14, 100, True, 0)]
+        got = [(x.p, x.l, x.lit) for x in ctx.match_sequences(ref, tgt, 14, 100, True, 0)]
+        assert got == exp
+        prof = ctx.profile()
+        assert prof["spec_rounds"] >= 1
+    finally:
+        os.environ.pop("SCCG_GP_CHUNK", None)
