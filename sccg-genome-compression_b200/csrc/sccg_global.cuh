@@ -288,7 +288,7 @@ __device__ __forceinline__ bool gp_step(GpShared& S, const GpArgs& a, i64& j, in
 //                  re-issued by the host every time the front gets lost with a new e.
 // ------------------------------------------------------------------------------------------------
 static const int GP_CHUNK_DEFAULT = 32768;      // positions per speculative chunk (SCCG_GP_CHUNK overrides it: tests use tiny chunks)
-static const int GP_DIAG_PROBES = 64;
+static const int GP_DIAG_PROBES = 64;           // must stay 64 (vote encoding)
 
 struct GpChunkInfo { i64 entry_j; i64 exit_j; int entry_e; int exit_e; u32 count; int valid; };
 
@@ -316,10 +316,13 @@ __global__ void __launch_bounds__(GP_T) gp_spec_k(GpSpecArgs s) {
     i64 j = B;
     int e = s.lost_e;
     bool valid = true;
-    if (s.slot == 0) {
-        // diagonal guess: the first probe position whose k-mer has exactly one exact occurrence in the reference
-        int d_found = 0x7fffffff;
+    if (s.slot == 0 && c == 0) {
+        e = -1;                                                   // the true initial state (0, -1): not a guess
+    } else if (s.slot == 0) {
+        // diagonal guess: every probe position whose k-mer occurs exactly once in the reference votes for its
+        // diagonal; the most frequent diagonal wins (a k-mer hit by a mutation may be unique somewhere else)
         i64 my_d = 0;
+        bool have = false;
         if (tid < GP_DIAG_PROBES && B + tid <= last_j) {
             i64 pos = B + tid;
             u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
@@ -331,22 +334,25 @@ __global__ void __launch_bounds__(GP_T) gp_spec_k(GpSpecArgs s) {
                 const u8* rp = a.R + a.vals[lo];
                 if (kmer_equal_words(ld_unaligned64(rp), ld_unaligned64(rp + 8), w0, w1, a.k)) { ++hits; my_d = (i64)a.vals[lo] - pos; }
             }
-            if (hits == 1) d_found = tid;
+            have = hits == 1;
         }
-        if (tid == 0) S.i_scratch[5] = 0x7fffffff;
+        i64* votes = reinterpret_cast<i64*>(S.long_list);         // GP_DIAG_PROBES diagonals (scratch reuse)
+        if (tid < GP_DIAG_PROBES) votes[tid] = have ? my_d : (i64)0x7fffffffffffffffLL;
+        if (tid == 0) S.i_scratch[5] = -1;
         __syncthreads();
-        if (d_found != 0x7fffffff) atomicMin(&S.i_scratch[5], d_found);
+        int score = -1;
+        if (have) { score = 0; for (int x = 0; x < GP_DIAG_PROBES; ++x) score += votes[x] == my_d; }
+        if (score > 0) atomicMax(&S.i_scratch[5], score * 64 + (63 - tid));   // most votes, then the earliest probe
         __syncthreads();
-        int winner = S.i_scratch[5];
-        if (tid == winner) { S.i_scratch[6] = (int)(my_d & 0xffffffff); S.i_scratch[7] = (int)(my_d >> 32); }
-        __syncthreads();
-        if (winner == 0x7fffffff) valid = false;
+        int best = S.i_scratch[5];
+        if (best < 0) valid = false;
         else {
-            i64 d = ((i64)S.i_scratch[7] << 32) | (u32)S.i_scratch[6];
+            i64 d = votes[63 - (best & 63)];
             i64 p0 = B + d;
             if (p0 < 0 || p0 >= a.nr) valid = false;
             else {
                 i64 maxl = (a.nr - p0) < (a.nt - B) ? (a.nr - p0) : (a.nt - B);
+                __syncthreads();
                 i64 l = block_lcp(S, a.R, p0, a.T, B, maxl);       // the match covering the boundary ends at its first mismatch
                 j = B + l;
                 i64 ee = j + d - 1;
@@ -398,15 +404,42 @@ __global__ void __launch_bounds__(GP_T) gp_front_k(GpFrontArgs f) {
     while (true) {
         if (j > last_j) { status = GP_DONE; break; }
         const u32 c = (u32)(j / f.s.chunk);
-        // ---- splice: does a speculative run of chunk c pass through the true state (j, e)?
+        // ---- bulk splice: thread t checks chunk c + t; a run of chunks whose entry state equals the exit state of its
+        //      predecessor (the first one: the true state) is accepted in one go
         bool took = false;
+        for (int slot = 0; slot < 2 && !took; ++slot) {
+            const GpChunkInfo* inf = f.s.info + (size_t)slot * f.s.nchunks;
+            const u32 cc = c + (u32)tid;
+            bool ok = false;
+            if (cc < f.s.nchunks && inf[cc].valid) {
+                if (tid == 0) ok = inf[cc].entry_j == j && inf[cc].entry_e == e;
+                else ok = inf[cc - 1].valid && inf[cc].entry_j == inf[cc - 1].exit_j && inf[cc].entry_e == inf[cc - 1].exit_e &&
+                          (u32)(inf[cc - 1].exit_j / f.s.chunk) == cc;
+            }
+            if (tid == 0) S.i_scratch[5] = GP_T;
+            __syncthreads();
+            if (!ok) atomicMin(&S.i_scratch[5], tid);
+            __syncthreads();
+            const int run = S.i_scratch[5];                        // chunks c .. c + run - 1 splice
+            __syncthreads();
+            if (run > 0) {
+                if (npieces + (u32)run + 2 >= f.cap_pieces) break;
+                if (tid < run) { GpPiece pc; pc.src = (u32)slot * f.s.nchunks + cc; pc.first = 0; pc.count = inf[cc].count; f.pieces[npieces + tid] = pc; }
+                npieces += (u32)run;
+                j = inf[c + run - 1].exit_j; e = inf[c + run - 1].exit_e;
+                took = true; spliced += (u32)run;
+                lost_streak = 0;
+                __syncthreads();
+            }
+        }
+        if (took) continue;
+        // ---- splice into the middle of a speculative run: does chunk c pass through the true state (j, e) after one of its matches?
         for (int slot = 0; slot < 2 && !took; ++slot) {
             const GpChunkInfo ci = f.s.info[(size_t)slot * f.s.nchunks + c];
             if (!ci.valid) continue;
             const size_t base = ((size_t)slot * f.s.nchunks + c) * f.s.cap_c;
             int first = -1;
-            if (ci.entry_j == j && ci.entry_e == e) first = 0;
-            else if (ci.count) {
+            if (ci.count) {
                 // the state after match i is (tpos + l, p + l - 1); tpos + l is increasing: binary search
                 int lo = 0, hi = (int)ci.count;
                 while (lo < hi) { int mid = (lo + hi) >> 1; if ((i64)f.s.c_tpos[base + mid] + f.s.c_l[base + mid] < j) lo = mid + 1; else hi = mid; }
@@ -424,6 +457,9 @@ __global__ void __launch_bounds__(GP_T) gp_front_k(GpFrontArgs f) {
             }
         }
         if (took) { if (npieces + 2 >= f.cap_pieces) { status = GP_LOST; break; } continue; }
+#ifdef SCCG_EMU_TRACE
+        if (tid == 0) { const GpChunkInfo ci = f.s.info[c]; printf("front: no splice at j=%lld e=%d chunk %u: valid=%d entry=(%lld,%d) exit=(%lld,%d) count=%u\n", (long long)j, e, c, ci.valid, (long long)ci.entry_j, ci.entry_e, (long long)ci.exit_j, ci.exit_e, ci.count); }
+#endif
         // ---- exact step of the sequential parse, at most to the end of this chunk
         int sel_p = 0, sel_l = 0;
         i64 scan_end = (i64)(c + 1) * f.s.chunk;
@@ -563,9 +599,9 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
     f.s.a.R = R; f.s.a.nr = nr; f.s.a.T = T; f.s.a.nt = nt; f.s.a.keys = keys; f.s.a.vals = vals; f.s.a.nk = nk; f.s.a.k = k; f.s.a.m = m;
     f.s.a.m_tpos = nullptr; f.s.a.m_p = nullptr; f.s.a.m_l = nullptr; f.s.a.d_count = nullptr;
     f.s.info = info; f.s.c_tpos = cbuf; f.s.c_p = cbuf + (size_t)2 * nchunks * cap_c; f.s.c_l = cbuf + (size_t)4 * nchunks * cap_c;
-    f.s.nchunks = nchunks; f.s.cap_c = cap_c; f.s.chunk = chunk; f.s.slot = 0; f.s.first_chunk = 1; f.s.lost_e = 0;
+    f.s.nchunks = nchunks; f.s.cap_c = cap_c; f.s.chunk = chunk; f.s.slot = 0; f.s.first_chunk = 0; f.s.lost_e = 0;
     f.st = st; f.pieces = pieces; f.cap_pieces = cap_pieces; f.f_tpos = fbuf; f.f_p = fbuf + cap_all; f.f_l = fbuf + 2 * cap_all;
-    if (nchunks > 1) LAUNCH(c, gp_spec_k, dim3(nchunks - 1), dim3(GP_T), 0, f.s);        // slot 0: diagonal guesses, chunks 1..
+    LAUNCH(c, gp_spec_k, dim3(nchunks), dim3(GP_T), 0, f.s);                             // slot 0: chunk 0 exact, diagonal guesses for the others
     for (int round = 0;; ++round) {
         c->prof.spec_rounds = round + 1;
         LAUNCH(c, gp_front_k, dim3(1), dim3(GP_T), 0, f);

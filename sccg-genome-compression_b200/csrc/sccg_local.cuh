@@ -230,9 +230,12 @@ __device__ __forceinline__ void lm_fetch(const u8* __restrict__ ref, i64 nr, con
 
 // k1 > 0 always; k2 == 0 disables the second pass (function-level match_sequences).
 // work_counter: device u32, zero before the launch; hands out segments gridDim*warps .. n_iter-1.
+// abort_flag (optional): seginfo must be preset to 0xffffffff ("not done"); as soon as some warp sees the T2 abort
+// condition of the driver (:454-473: a failed, non-all-N segment ending a run of 5 counter increments) among finished
+// segments it raises the flag and every warp stops claiming work -- the local attempt is discarded anyway (:466-472).
 __global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restrict__ ref, i64 nr, const u8* __restrict__ tgt, i64 nt,
-                                                            int n_iter, int k1, int k2, u32* __restrict__ seginfo, u32* __restrict__ matches,
-                                                            u32* __restrict__ work_counter) {
+                                                            int n_iter, int k1, int k2, u32* seginfo, u32* __restrict__ matches,
+                                                            u32* __restrict__ work_counter, u32* abort_flag) {
     SCCG_DYN_SMEM(smem_raw);
     LmWarpSmem& S = reinterpret_cast<LmWarpSmem*>(smem_raw)[threadIdx.x >> 5];
     const int lane = lane_of();
@@ -278,7 +281,10 @@ __global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restric
             else if (vt > 0) { if (nx & (~0ull >> (64 - 8 * vt))) all_n = 0; }
         }
         int next_seg = 0;
-        if (lane == 0) next_seg = (int)atomicAdd(work_counter, 1u) + warps_total;
+        if (lane == 0) {
+            next_seg = (int)atomicAdd(work_counter, 1u) + warps_total;
+            if (abort_flag && *reinterpret_cast<volatile u32*>(abort_flag)) next_seg = n_iter;
+        }
         next_seg = __shfl_sync(SCCG_FULL_MASK, next_seg, 0);
         lm_fetch(ref, nr, tgt, nt, next_seg, n_iter, lane, nrw, ntw);
         if (lane < 2) reinterpret_cast<u64*>(S.r)[128 + lane] = 0ull, reinterpret_cast<u64*>(S.t)[128 + lane] = 0ull;
@@ -309,7 +315,27 @@ __global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restric
         if (lane == 0) {
             int lit = Lt - covered;                                              // count_mismatches :413
             u32 bad = (2 * lit > Lt) ? 1u : 0u;                                  // (float)lit / Lt > 0.5f  :417-419
-            seginfo[seg] = (u32)nmatch | ((u32)lit << 8) | ((u32)(all_n ? 1 : 0) << 20) | (bad << 21);
+            u32 info = (u32)nmatch | ((u32)lit << 8) | ((u32)(all_n ? 1 : 0) << 20) | (bad << 21);
+            if (abort_flag) {
+                *reinterpret_cast<volatile u32*>(seginfo + seg) = info;
+                if (!all_n && (nmatch == 0 || bad)) {
+                    // this segment increments the counter: test the five windows of 5 consecutive segments that contain it
+                    __threadfence();
+                    for (int end = seg; end <= seg + T2_LIMIT && end < n_iter; ++end) {
+                        if (end < T2_LIMIT) continue;
+                        bool all_inc = true;
+                        for (int d = 0; d <= T2_LIMIT && all_inc; ++d) {
+                            u32 x = *reinterpret_cast<volatile u32*>(seginfo + end - d);
+                            bool inc = x != 0xffffffffu && !SEGINFO_ALLN(x) && (SEGINFO_NMATCH(x) == 0 || SEGINFO_BAD(x));
+                            if (d == 0 && inc && SEGINFO_NMATCH(x) != 0) inc = false;     // the window must END with a failed segment
+                            all_inc = inc;
+                        }
+                        if (all_inc) { atomicOr(abort_flag, 1u); break; }
+                    }
+                }
+            } else {
+                seginfo[seg] = info;
+            }
         }
         seg = next_seg;
     }
@@ -321,6 +347,7 @@ __global__ void seg_bytes_k(const u32* __restrict__ seginfo, const u32* __restri
                             u32* __restrict__ seg_bytes, int* __restrict__ seg_prev_p, u32* __restrict__ d_abort) {
     int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (i >= n_iter) return;
+    if (*d_abort) return;                                    // raised early by seg_match_k: seginfo is incomplete and will be discarded
     u32 info = seginfo[i];
     int nmatch = (int)SEGINFO_NMATCH(info);
     if (nmatch == 0) {
