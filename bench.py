@@ -224,7 +224,7 @@ def main() -> None:
         return float(t.item())
 
     # ---- workload: every rank owns one chromosome-sized pair (rank-dependent seed)
-    ref_np, tgt_np = synth.local_pair(args.size, synth.seed_for(2, rank))
+    ref_np, tgt_np = synth.local_pair(args.size, synth.seed_for(2, rank + int(os.environ.get("SCCG_BENCH_CHROM", "0"))))
     nr, nt = int(ref_np.size), int(tgt_np.size)
     pad = torch.zeros(64, dtype=torch.uint8)                    # *_device entry points may read a few bytes past the end
     h_ref = torch.cat([torch.from_numpy(ref_np), pad]).pin_memory()

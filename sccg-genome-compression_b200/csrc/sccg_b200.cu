@@ -269,4 +269,11 @@ int sccg_decompress_into(sccg_ctx* c, const char* ref_raw, int64_t ref_len, cons
     return decompress_host(c, ref_raw, ref_len, inter, inter_len, out, out_cap, nullptr, out_len);
 }
 
+#ifdef SCCG_SEG_TIMING
+int sccg_debug_seg_timing(void* d_cycles) {
+    unsigned long long* p = (unsigned long long*)d_cycles;
+    return cudaMemcpyToSymbol(sccg::g_seg_cycles, &p, sizeof p) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 }  // extern "C"

@@ -9,7 +9,7 @@ namespace sccg {
 // device scalars (u32 each)
 enum Scalar {
     S_LOW_K = 0, S_LOW_KE, S_LOW_TEXT, S_ABORT, S_BODY_MAIN, S_BODY_BASE, S_N_K, S_N_KE, S_N_TEXT,
-    S_WORK, S_G1, S_G2, S_G3, S_G4, S_G5, S_G6, S_G7, S_COUNT = 32
+    S_G0, S_G1, S_G2, S_G3, S_G4, S_G5, S_G6, S_G7, S_WORK = 64, S_COUNT = 128   // S_WORK: own 128-byte line (hot atomic)
 };
 
 // writes the separator after the lowercase line and publishes where the body starts

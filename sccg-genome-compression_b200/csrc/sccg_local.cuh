@@ -214,6 +214,11 @@ __device__ __forceinline__ int lm_parse(LmWarpSmem& S, const u32 (&wm)[4], int L
     return nmatch;
 }
 
+#ifdef SCCG_SEG_TIMING
+// development aid (tools/seg_timing.py, separate build): clock64() ticks spent per segment
+__device__ unsigned long long* g_seg_cycles = nullptr;
+#endif
+
 // raw (not yet upper-cased) 8-byte words of segment `seg`: lane holds words lane, lane+32, lane+64, lane+96
 __device__ __forceinline__ void lm_fetch(const u8* __restrict__ ref, i64 nr, const u8* __restrict__ tgt, i64 nt, int seg, int n_iter, int lane,
                                          u64 (&rw)[4], u64 (&tw)[4]) {
@@ -233,7 +238,13 @@ __device__ __forceinline__ void lm_fetch(const u8* __restrict__ ref, i64 nr, con
 // abort_flag (optional): seginfo must be preset to 0xffffffff ("not done"); as soon as some warp sees the T2 abort
 // condition of the driver (:454-473: a failed, non-all-N segment ending a run of 5 counter increments) among finished
 // segments it raises the flag and every warp stops claiming work -- the local attempt is discarded anyway (:466-472).
-__global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restrict__ ref, i64 nr, const u8* __restrict__ tgt, i64 nt,
+#ifndef SCCG_LM_CLAIM
+#define SCCG_LM_CLAIM 2             // segments claimed per atomic
+#endif
+#ifndef SCCG_LM_MIN_CTAS
+#define SCCG_LM_MIN_CTAS 8          // 8 CTAs x 128 threads x 64 registers = the whole register file of an SM
+#endif
+__global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(const u8* __restrict__ ref, i64 nr, const u8* __restrict__ tgt, i64 nt,
                                                             int n_iter, int k1, int k2, u32* seginfo, u32* __restrict__ matches,
                                                             u32* __restrict__ work_counter, u32* abort_flag) {
     SCCG_DYN_SMEM(smem_raw);
@@ -254,7 +265,9 @@ __global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restric
     // segments are claimed dynamically (their cost varies by an order of magnitude) and the next segment's
     // symbols are fetched into registers while the current one is parsed
     u64 nrw[4], ntw[4];
-    int seg = warp_global < n_iter ? warp_global : n_iter;
+    const int claim_base = warps_total * SCCG_LM_CLAIM;       // the first warps_total * CLAIM segments are pre-assigned
+    int claimed_used = 0;
+    int seg = warp_global * SCCG_LM_CLAIM < n_iter ? warp_global * SCCG_LM_CLAIM : n_iter;
     lm_fetch(ref, nr, tgt, nt, seg, n_iter, lane, nrw, ntw);
     while (seg < n_iter) {
         const i64 off = (i64)seg * SEG;
@@ -262,6 +275,9 @@ __global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restric
         const int Lt = (int)((nt - off) < SEG ? (nt - off) : SEG);
         const int Lmin = Lr < Lt ? Lr : Lt;
         __syncwarp();                                        // previous segment fully consumed
+#ifdef SCCG_SEG_TIMING
+        const long long t_begin = clock64();
+#endif
         int all_n = 1;
         u32 wm[4];                                           // diagonal-0 mismatch flags per 8-byte word (uniform)
         const int wv = Lmin >> 3, rem = Lmin & 7;
@@ -280,12 +296,19 @@ __global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restric
             if (vt >= 8) { if (nx) all_n = 0; }
             else if (vt > 0) { if (nx & (~0ull >> (64 - 8 * vt))) all_n = 0; }
         }
-        int next_seg = 0;
-        if (lane == 0) {
-            next_seg = (int)atomicAdd(work_counter, 1u) + warps_total;
-            if (abort_flag && *reinterpret_cast<volatile u32*>(abort_flag)) next_seg = n_iter;
+        // claim the next segment: SCCG_LM_CLAIM consecutive segments per atomic (one hot L2 address for the whole grid)
+        int next_seg = seg + 1;
+        if (++claimed_used >= SCCG_LM_CLAIM) {
+            if (lane == 0) {
+                next_seg = (int)atomicAdd(work_counter, 1u) * SCCG_LM_CLAIM + claim_base;
+#ifndef SCCG_NO_EARLY_ABORT
+                // the abort flag lives in its own cache line: reads must not queue behind the claim atomics
+                if (abort_flag && __ldcg(abort_flag)) next_seg = n_iter;
+#endif
+            }
+            claimed_used = 0;
+            next_seg = __shfl_sync(SCCG_FULL_MASK, next_seg, 0);
         }
-        next_seg = __shfl_sync(SCCG_FULL_MASK, next_seg, 0);
         lm_fetch(ref, nr, tgt, nt, next_seg, n_iter, lane, nrw, ntw);
         if (lane < 2) reinterpret_cast<u64*>(S.r)[128 + lane] = 0ull, reinterpret_cast<u64*>(S.t)[128 + lane] = 0ull;
         all_n = __all_sync(SCCG_FULL_MASK, all_n);
@@ -316,6 +339,7 @@ __global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restric
             int lit = Lt - covered;                                              // count_mismatches :413
             u32 bad = (2 * lit > Lt) ? 1u : 0u;                                  // (float)lit / Lt > 0.5f  :417-419
             u32 info = (u32)nmatch | ((u32)lit << 8) | ((u32)(all_n ? 1 : 0) << 20) | (bad << 21);
+#ifndef SCCG_NO_EARLY_ABORT
             if (abort_flag) {
                 *reinterpret_cast<volatile u32*>(seginfo + seg) = info;
                 if (!all_n && (nmatch == 0 || bad)) {
@@ -333,10 +357,15 @@ __global__ void __launch_bounds__(LM_WARPS * 32) seg_match_k(const u8* __restric
                         if (all_inc) { atomicOr(abort_flag, 1u); break; }
                     }
                 }
-            } else {
+            } else
+#endif
+            {
                 seginfo[seg] = info;
             }
         }
+#ifdef SCCG_SEG_TIMING
+        if (lane == 0 && g_seg_cycles) g_seg_cycles[seg] = (unsigned long long)(clock64() - t_begin);
+#endif
         seg = next_seg;
     }
 }

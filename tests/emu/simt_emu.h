@@ -231,6 +231,7 @@ inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 template <typename T> inline T __ldg(const T* p) { return *p; }
 template <typename T> inline T __ldcs(const T* p) { return *p; }
+template <typename T> inline T __ldcg(const T* p) { return *p; }
 template <typename T> inline void __stcs(T* p, T v) { *p = v; }
 using std::min;
 using std::max;
