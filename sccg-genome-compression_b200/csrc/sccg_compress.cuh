@@ -109,7 +109,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
                          out + hdr_bytes, sc + S_LOW_TEXT));
     LAUNCH(c, put_separators_k, dim3(1), dim3(1), 0, out, (u32)hdr_bytes, sc, 0);
     if (n_iter > 0) {
-        unsigned want = div_up(n_iter, 8);
+        unsigned want = div_up(n_iter, 8 * 32);                              // 8 warps per CTA, 32 segments per warp
         unsigned capg = (unsigned)c->sm_count * 8u;
         LAUNCH(c, seg_write_k, dim3(want < capg ? want : capg), dim3(256), 0, d_tgt, nt, (const u32*)seginfo, (const u32*)matches,
                (const u32*)seg_bytes, (const int*)seg_prev, n_iter, out, (const u32*)(sc + S_BODY_BASE));

@@ -423,54 +423,85 @@ __device__ __forceinline__ int write_token(u8* o, int dp, int l) {
     return w;
 }
 
-// Record writer (compression.cpp:406-415) fused with delta_encode (:222-304): one warp per segment.
+// one segment written by the whole warp (many matches or long literal runs)
+__device__ __forceinline__ void seg_write_coop(const u8* __restrict__ tgt, i64 nt, const u32* __restrict__ matches, int seg, int nmatch,
+                                               u8* __restrict__ base, int prevp) {
+    const int lane = lane_of();
+    const i64 toff = (i64)seg * SEG;
+    const int Lt = (int)((nt - toff) < SEG ? (nt - toff) : SEG);
+    int prev_end = 0;
+    u32 cursor = 0;
+    for (int c0 = 0; c0 < nmatch; c0 += 32) {
+        int m = c0 + lane;
+        bool valid = m < nmatch;
+        u32 pk = valid ? matches[(i64)seg * LM_SLOT + m] : 0u;
+        int tpos = (int)(pk & 0x3ffu), l = (int)(pk >> 20);
+        int p_abs = seg * SEG + (int)((pk >> 10) & 0x3ffu);
+        int te = tpos + l;
+        int pp = __shfl_up_sync(SCCG_FULL_MASK, p_abs, 1);
+        int pe = __shfl_up_sync(SCCG_FULL_MASK, te, 1);
+        if (lane == 0) { pp = prevp; pe = prev_end; }
+        int gap = valid ? tpos - pe : 0;
+        int tok = valid ? 3 + dec_len_i32(p_abs - pp) + dec_len_u32((u32)l) : 0;
+        u32 mine = (u32)(gap + tok);
+        u32 incl = warp_scan_incl(mine);
+        u32 o = cursor + incl - mine;
+        if (valid) {
+            if (gap <= 8) for (int x = 0; x < gap; ++x) base[o + x] = upper1(tgt[toff + pe + x]);
+            write_token(base + o + gap, p_abs - pp, l);
+        }
+        u32 big = __ballot_sync(SCCG_FULL_MASK, valid && gap > 8);   // long literal runs: whole warp copies
+        while (big) {
+            int src = __ffs((int)big) - 1; big &= big - 1;
+            int g = __shfl_sync(SCCG_FULL_MASK, gap, src);
+            int s0 = __shfl_sync(SCCG_FULL_MASK, pe, src);
+            u32 o0 = __shfl_sync(SCCG_FULL_MASK, o, src);
+            for (int x = lane; x < g; x += 32) base[o0 + x] = upper1(tgt[toff + s0 + x]);
+        }
+        int lastl = (nmatch - 1 - c0) < 31 ? (nmatch - 1 - c0) : 31;
+        prevp = __shfl_sync(SCCG_FULL_MASK, p_abs, lastl);
+        prev_end = __shfl_sync(SCCG_FULL_MASK, te, lastl);
+        cursor += __shfl_sync(SCCG_FULL_MASK, incl, 31);
+    }
+    for (int x = prev_end + lane; x < Lt; x += 32) base[cursor + (u32)(x - prev_end)] = upper1(tgt[toff + x]);   // trailing literals :164-167
+}
+
+// Record writer (compression.cpp:406-415) fused with delta_encode (:222-304).  A warp takes 32 consecutive segments:
+// the usual segment (a few tokens, a few literals) is written by its own lane, segments with many matches or long
+// literal runs are handed to the whole warp one after the other.
 __global__ void __launch_bounds__(256) seg_write_k(const u8* __restrict__ tgt, i64 nt, const u32* __restrict__ seginfo, const u32* __restrict__ matches,
                                                    const u32* __restrict__ seg_off, const int* __restrict__ seg_prev_p, int n_iter,
                                                    u8* __restrict__ out, const u32* __restrict__ d_body_base) {
     const int lane = lane_of();
     const int warps_total = (int)(gridDim.x * (blockDim.x >> 5));
-    const u32 body_base = *d_body_base;
-    for (int seg = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); seg < n_iter; seg += warps_total) {
-        const int nmatch = (int)SEGINFO_NMATCH(seginfo[seg]);
-        if (nmatch == 0) continue;
-        const i64 toff = (i64)seg * SEG;
-        const int Lt = (int)((nt - toff) < SEG ? (nt - toff) : SEG);
-        u8* base = out + body_base + seg_off[seg];
-        int prevp = seg_prev_p[seg], prev_end = 0;
-        u32 cursor = 0;
-        for (int c0 = 0; c0 < nmatch; c0 += 32) {
-            int m = c0 + lane;
-            bool valid = m < nmatch;
-            u32 pk = valid ? matches[(i64)seg * LM_SLOT + m] : 0u;
-            int tpos = (int)(pk & 0x3ffu), l = (int)(pk >> 20);
-            int p_abs = seg * SEG + (int)((pk >> 10) & 0x3ffu);
-            int te = tpos + l;
-            int pp = __shfl_up_sync(SCCG_FULL_MASK, p_abs, 1);
-            int pe = __shfl_up_sync(SCCG_FULL_MASK, te, 1);
-            if (lane == 0) { pp = prevp; pe = prev_end; }
-            int gap = valid ? tpos - pe : 0;
-            int tok = valid ? 3 + dec_len_i32(p_abs - pp) + dec_len_u32((u32)l) : 0;
-            u32 mine = (u32)(gap + tok);
-            u32 incl = warp_scan_incl(mine);
-            u32 o = cursor + incl - mine;
-            if (valid) {
-                if (gap <= 8) for (int x = 0; x < gap; ++x) base[o + x] = upper1(tgt[toff + pe + x]);
-                write_token(base + o + gap, p_abs - pp, l);
+    u8* body = out + *d_body_base;
+    for (int seg0 = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; seg0 < n_iter; seg0 += warps_total * 32) {
+        const int seg = seg0 + lane;
+        u32 info = seg < n_iter ? seginfo[seg] : 0u;
+        const int nmatch = (int)SEGINFO_NMATCH(info);
+        const bool light = nmatch > 0 && nmatch <= 6 && SEGINFO_LIT(info) <= 24;
+        if (light) {
+            const i64 toff = (i64)seg * SEG;
+            const int Lt = (int)((nt - toff) < SEG ? (nt - toff) : SEG);
+            u8* o = body + seg_off[seg];
+            int pp = seg_prev_p[seg], pe = 0;
+            for (int m = 0; m < nmatch; ++m) {
+                u32 pk = matches[(i64)seg * LM_SLOT + m];
+                int tpos = (int)(pk & 0x3ffu), l = (int)(pk >> 20);
+                int p_abs = seg * SEG + (int)((pk >> 10) & 0x3ffu);
+                for (int x = pe; x < tpos; ++x) *o++ = upper1(tgt[toff + x]);
+                o += write_token(o, p_abs - pp, l);
+                pp = p_abs; pe = tpos + l;
             }
-            u32 big = __ballot_sync(SCCG_FULL_MASK, valid && gap > 8);   // long literal runs: whole warp copies
-            while (big) {
-                int src = __ffs((int)big) - 1; big &= big - 1;
-                int g = __shfl_sync(SCCG_FULL_MASK, gap, src);
-                int s0 = __shfl_sync(SCCG_FULL_MASK, pe, src);
-                u32 o0 = __shfl_sync(SCCG_FULL_MASK, o, src);
-                for (int x = lane; x < g; x += 32) base[o0 + x] = upper1(tgt[toff + s0 + x]);
-            }
-            int lastl = (nmatch - 1 - c0) < 31 ? (nmatch - 1 - c0) : 31;
-            prevp = __shfl_sync(SCCG_FULL_MASK, p_abs, lastl);
-            prev_end = __shfl_sync(SCCG_FULL_MASK, te, lastl);
-            cursor += __shfl_sync(SCCG_FULL_MASK, incl, 31);
+            for (int x = pe; x < Lt; ++x) *o++ = upper1(tgt[toff + x]);
         }
-        for (int x = prev_end + lane; x < Lt; x += 32) base[cursor + (u32)(x - prev_end)] = upper1(tgt[toff + x]);   // trailing literals :164-167
+        u32 heavy = __ballot_sync(SCCG_FULL_MASK, nmatch > 0 && !light);
+        while (heavy) {
+            int src = __ffs((int)heavy) - 1; heavy &= heavy - 1;
+            int hseg = seg0 + src;
+            int hn = __shfl_sync(SCCG_FULL_MASK, nmatch, src);
+            seg_write_coop(tgt, nt, matches, hseg, hn, body + seg_off[hseg], seg_prev_p[hseg]);
+        }
     }
 }
 

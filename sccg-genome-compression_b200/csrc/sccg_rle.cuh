@@ -7,7 +7,8 @@
 namespace sccg {
 
 static const int RLE_T = 256;
-static const int RLE_TILE = RLE_T * 16;
+static const int RLE_PER_THREAD = 64;                  // bytes per thread: one block scan per 16 KB tile
+static const int RLE_TILE = RLE_T * RLE_PER_THREAD;
 
 // MODE 0: islower(raw byte)            (compression.cpp:345)
 // MODE 1: toupper(raw byte) == 'N'     (compression.cpp:523, :531)
@@ -19,27 +20,33 @@ template <int MODE> __device__ __forceinline__ u32 rle_pred8(u64 w) {
     return movemask8(eq_flags8(w, 'N') | eq_flags8(w, 'n'));
 }
 
-// start/end masks of the 16 positions [i, i+16) owned by this thread
-template <int MODE> __device__ __forceinline__ void rle_masks(const u8* __restrict__ src, i64 n, i64 i, u32* starts, u32* ends) {
+// start / end masks of the 64 positions [i, i+64) owned by this thread (bit b <=> position i + b)
+template <int MODE> __device__ __forceinline__ void rle_masks(const u8* __restrict__ src, i64 n, i64 i, u64* starts, u64* ends) {
     *starts = 0; *ends = 0;
     if (i >= n) return;
-    ulonglong2 v = *reinterpret_cast<const ulonglong2*>(src + i);     // buffers carry >= 64 B of slack
-    u32 m = rle_pred8<MODE>(v.x) | (rle_pred8<MODE>(v.y) << 8);
+    u64 m = 0;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        if (i + 16 * v < n) {
+            ulonglong2 w = *reinterpret_cast<const ulonglong2*>(src + i + 16 * v);   // buffers carry >= 64 B of slack
+            m |= (u64)(rle_pred8<MODE>(w.x) | (rle_pred8<MODE>(w.y) << 8)) << (16 * v);
+        }
+    }
     i64 left = n - i;
-    if (left < 16) m &= (1u << (int)left) - 1u;
-    u32 prev = (i > 0) ? (u32)rle_pred1<MODE>(src[i - 1]) : 0u;
-    u32 next = (i + 16 < n) ? (u32)rle_pred1<MODE>(src[i + 16]) : 0u;
-    *starts = m & ~((m << 1) | prev) & 0xffffu;
-    *ends = m & ~((m >> 1) | (next << 15)) & 0xffffu;
+    if (left < 64) m &= (1ull << (int)left) - 1ull;
+    u64 prev = (i > 0) ? (u64)rle_pred1<MODE>(src[i - 1]) : 0ull;
+    u64 next = (i + 64 < n) ? (u64)rle_pred1<MODE>(src[i + 64]) : 0ull;
+    *starts = m & ~((m << 1) | prev);
+    *ends = m & ~((m >> 1) | (next << 63));
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(RLE_T) rle_count_k(const u8* __restrict__ src, i64 n, u32* __restrict__ cnt_s, u32* __restrict__ cnt_e) {
     __shared__ u32 sm[40];
-    i64 i = (i64)blockIdx.x * RLE_TILE + (i64)threadIdx.x * 16;
-    u32 s, e;
+    i64 i = (i64)blockIdx.x * RLE_TILE + (i64)threadIdx.x * RLE_PER_THREAD;
+    u64 s, e;
     rle_masks<MODE>(src, n, i, &s, &e);
-    u32 packed = (u32)__popc(s) | ((u32)__popc(e) << 16);             // <= 2048 each per tile: no overflow
+    u32 packed = (u32)__popcll(s) | ((u32)__popcll(e) << 16);         // <= 8192 each per tile: no overflow
     u32 tot;
     block_scan_excl(packed, sm, &tot);
     if (threadIdx.x == 0) { cnt_s[blockIdx.x] = tot & 0xffffu; cnt_e[blockIdx.x] = tot >> 16; }
@@ -50,16 +57,16 @@ template <int MODE>
 __global__ void __launch_bounds__(RLE_T) rle_write_k(const u8* __restrict__ src, i64 n, const u32* __restrict__ off_s, const u32* __restrict__ off_e,
                                                      int* __restrict__ run_start, int* __restrict__ run_end) {
     __shared__ u32 sm[40];
-    i64 i = (i64)blockIdx.x * RLE_TILE + (i64)threadIdx.x * 16;
-    u32 s, e;
+    i64 i = (i64)blockIdx.x * RLE_TILE + (i64)threadIdx.x * RLE_PER_THREAD;
+    u64 s, e;
     rle_masks<MODE>(src, n, i, &s, &e);
-    u32 packed = (u32)__popc(s) | ((u32)__popc(e) << 16);
+    u32 packed = (u32)__popcll(s) | ((u32)__popcll(e) << 16);
     u32 tot;
     u32 excl = block_scan_excl(packed, sm, &tot);
     u32 ks = off_s[blockIdx.x] + (excl & 0xffffu);
     u32 ke = off_e[blockIdx.x] + (excl >> 16);
-    while (s) { int b = __ffs((int)s) - 1; s &= s - 1; run_start[ks++] = (int)(i + b); }
-    while (e) { int b = __ffs((int)e) - 1; e &= e - 1; run_end[ke++] = (int)(i + b + 1); }
+    while (s) { int b = __ffsll((long long)s) - 1; s &= s - 1; run_start[ks++] = (int)(i + b); }
+    while (e) { int b = __ffsll((long long)e) - 1; e &= e - 1; run_end[ke++] = (int)(i + b + 1); }
 }
 
 // text length of run-list item k  (compression.cpp:351-366)
