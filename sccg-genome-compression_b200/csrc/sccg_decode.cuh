@@ -485,6 +485,15 @@ static int reconstruct_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_
 
     // ---- sizes: N-merged length, wrapped text length
     const i64 Lm = Ls + nsum;
+    if (ns.K) {
+        // the last N run must end inside the merged sequence: otherwise the reference's merge loop (:244-252) runs
+        // past the end of the decoded string (undefined behaviour there, SCCG_E_FORMAT here)
+        int last[2] = {0, 0};
+        SCCG_CK(cudaMemcpyAsync(&last[0], ns.start + (ns.K - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        SCCG_CK(cudaMemcpyAsync(&last[1], ns.len + (ns.K - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        SCCG_CK(cudaStreamSynchronize(c->stream));
+        if ((i64)last[0] + (i64)last[1] > Lm) return set_error(SCCG_E_FORMAT, "N run list reaches past the end of the decoded sequence");
+    }
     const i64 nchunks = (Lm + WRAP - 1) / WRAP;
     const i64 total = Lm > 0 ? Lm + nchunks : 1;
     if (total >= 0xffffffffLL) return set_error(SCCG_E_ARG, "decoded output would exceed 4 GiB");

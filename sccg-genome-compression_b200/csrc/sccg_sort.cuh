@@ -28,14 +28,22 @@ __global__ void __launch_bounds__(RS_T) rs_hist_k(const u32* __restrict__ keys, 
     hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];     // digit-major for the scan
 }
 
+// Stable scatter of one 4096-element tile.  The tile is first ordered by digit in shared memory (per-warp ranks from
+// __match_any_sync, warps and digits combined by small scans), then written out: consecutive shared-memory entries of
+// one digit go to consecutive global addresses, so the stores are coalesced instead of 32 scattered sectors per warp.
 __global__ void __launch_bounds__(RS_T) rs_scatter_k(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in, i64 n, int shift,
                                                     const u32* __restrict__ offs, unsigned nblocks, u32* __restrict__ keys_out, u32* __restrict__ vals_out) {
-    __shared__ u32 cnt[RS_WARPS][256];              // per-warp digit counts, then running output positions
+    __shared__ u32 cnt[RS_WARPS][256];              // per-warp digit counts, then running tile-local positions
+    __shared__ u32 lstart[256];                     // tile-local start of every digit
+    __shared__ u32 gbase[256];                      // global start of (digit, this tile)
+    __shared__ u32 sk[RS_TILE], sv[RS_TILE];
+    __shared__ u32 wsum[RS_WARPS];
     const int lane = lane_of(), w = (int)(threadIdx.x >> 5);
     for (int x = (int)threadIdx.x; x < RS_WARPS * 256; x += RS_T) (&cnt[0][0])[x] = 0u;
     __syncthreads();
     // each warp owns a contiguous sub-tile and walks it in order: chunk c = elements [c*32, c*32+32)
-    const i64 wbase = (i64)blockIdx.x * RS_TILE + (i64)w * (RS_CHUNKS * 32);
+    const i64 tbase = (i64)blockIdx.x * RS_TILE;
+    const i64 wbase = tbase + (i64)w * (RS_CHUNKS * 32);
     u32 k[RS_CHUNKS], v[RS_CHUNKS];
 #pragma unroll
     for (int c = 0; c < RS_CHUNKS; ++c) {
@@ -49,10 +57,21 @@ __global__ void __launch_bounds__(RS_T) rs_scatter_k(const u32* __restrict__ key
         __syncwarp();
     }
     __syncthreads();
-    {   // digit d = threadIdx.x: exclusive prefix over the warps + global offset of (digit, block)
-        u32 run = offs[(size_t)threadIdx.x * nblocks + blockIdx.x];
+    {   // digit d = threadIdx.x: tile total, exclusive prefix over the warps, exclusive scan over the digits
+        const u32 d = threadIdx.x;
+        u32 tot = 0;
 #pragma unroll
-        for (int ww = 0; ww < RS_WARPS; ++ww) { u32 t = cnt[ww][threadIdx.x]; cnt[ww][threadIdx.x] = run; run += t; }
+        for (int ww = 0; ww < RS_WARPS; ++ww) { u32 t = cnt[ww][d]; cnt[ww][d] = tot; tot += t; }
+        u32 incl = warp_scan_incl(tot);
+        if (lane == 31) wsum[w] = incl;
+        __syncthreads();
+        u32 before = 0;
+        for (int ww = 0; ww < w; ++ww) before += wsum[ww];
+        u32 ls = before + incl - tot;
+        lstart[d] = ls;
+        gbase[d] = offs[(size_t)d * nblocks + blockIdx.x];
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ++ww) cnt[ww][d] += ls;
     }
     __syncthreads();
 #pragma unroll
@@ -64,12 +83,21 @@ __global__ void __launch_bounds__(RS_T) rs_scatter_k(const u32* __restrict__ key
         u32 below = peers & ((1u << lane) - 1u);
         if (valid) {
             u32 pos = cnt[w][d] + (u32)__popc(below);
-            keys_out[pos] = k[c];
-            vals_out[pos] = v[c];
+            sk[pos] = k[c];
+            sv[pos] = v[c];
         }
         __syncwarp();
         if (valid && lane == __ffs((int)peers) - 1) cnt[w][d] += (u32)__popc(peers);
         __syncwarp();
+    }
+    __syncthreads();
+    const int tile_n = (int)((n - tbase) < RS_TILE ? (n - tbase) : RS_TILE);
+    for (int i = (int)threadIdx.x; i < tile_n; i += RS_T) {
+        u32 key = sk[i];
+        u32 d = (key >> shift) & 255u;
+        u32 pos = gbase[d] + ((u32)i - lstart[d]);
+        keys_out[pos] = key;
+        vals_out[pos] = sv[i];
     }
 }
 

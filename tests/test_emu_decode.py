@@ -99,6 +99,11 @@ def test_reconstruct_errors(ctx):
         with pytest.raises(sccg_b200.SccgError) as e:
             ctx.reconstruct(ref, enc, b"", b"")
         assert e.value.code == sccg_b200.SCCG_E_FORMAT
+    for nlist in (b"1000,", b"(6,5)"):                                       # N run past the end: UB in the reference
+        with pytest.raises(sccg_b200.SccgError) as e:
+            ctx.reconstruct(ref, b"ACGT", nlist, b"")
+        assert e.value.code == sccg_b200.SCCG_E_FORMAT
+    assert ctx.reconstruct(ref, b"ACGT", b"4,", b"") == b"ACGTN\n"              # trailing N is fine
     assert ctx.reconstruct(ref, b"", b"", b"") == b"\n"
     assert ctx.reconstruct(ref, b"ACGT", b"", b"1,") == b"AcGT\n"
     assert ctx.reconstruct(ref, b"ACGT", b"(1,2)", b"(0,3)") == b"annCGT\n"      # a lowercase run covers re-inserted N
