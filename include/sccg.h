@@ -31,6 +31,10 @@ extern "C" {
 #define SCCG_E_FORMAT (-3)      /* malformed record stream: the reference would throw (stoi) -> exit 1    */
 #define SCCG_E_BOUNDS (-4)      /* abs+len exceeds the reference: decompression.cpp:223-229 -> exit(1)    */
 #define SCCG_E_NOMEM (-5)
+#define SCCG_E_STOI (-6)        /* compress only: the target carries a literal '(' that makes the reference's text-level
+                                 * delta_encode throw from stoi (compression.cpp:279) -> "Error: stoi", exit 1, and
+                                 * compressed_genome.txt stays un-rewritten.  The output buffer IS filled with that
+                                 * pre-delta image (release it as usual) so a caller can leave the same file behind. */
 
 typedef struct sccg_ctx sccg_ctx;
 
@@ -71,7 +75,7 @@ int         sccg_download(sccg_ctx* ctx, const void* d_src, int64_t n, void* h_d
 
 /* compress_genome minus file I/O and the external 7z stage (compression.cpp:320-579).
  * ref / tgt: raw symbols as read_genomes_from_files leaves them (:181-220): case preserved, no
- * newlines.  header: the target's first '>' line, may be empty.  out: the final, delta-encoded
+ * newlines.  header: the target's first '>' line (must start with '>'), may be empty.  out: the final, delta-encoded
  * compressed_genome.txt image.  mode_out: 0 = local segment matching, 1 = global fallback. */
 int sccg_compress(sccg_ctx* ctx, const char* ref, int64_t ref_len, const char* tgt, int64_t tgt_len,
                   const char* header, int64_t header_len, char** out, int64_t* out_len, int* mode_out);

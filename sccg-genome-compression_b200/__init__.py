@@ -20,13 +20,14 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 DEFAULT_LIB = PKG_DIR / "libsccg_b200.so"
 
-SCCG_OK, SCCG_E_CUDA, SCCG_E_ARG, SCCG_E_FORMAT, SCCG_E_BOUNDS, SCCG_E_NOMEM = 0, -1, -2, -3, -4, -5
+SCCG_OK, SCCG_E_CUDA, SCCG_E_ARG, SCCG_E_FORMAT, SCCG_E_BOUNDS, SCCG_E_NOMEM, SCCG_E_STOI = 0, -1, -2, -3, -4, -5, -6
 
 
 class SccgError(RuntimeError):
-    def __init__(self, code: int, message: str):
+    def __init__(self, code: int, message: str, partial: bytes | None = None):
         super().__init__(f"sccg error {code}: {message}")
         self.code = code
+        self.partial = partial      # SCCG_E_STOI: the un-rewritten image the reference leaves on disk before it exits 1
 
 
 class _Records(C.Structure):
@@ -142,8 +143,10 @@ class Context:
     # compress_genome minus file I/O and 7z (compression.cpp:320-579)
     def compress(self, ref: bytes, tgt: bytes, header: bytes = b"") -> tuple[bytes, int]:
         out = C.c_void_p(); n = C.c_int64(); mode = C.c_int()
-        self._check(self.lib.sccg_compress(self.handle, ref, len(ref), tgt, len(tgt), header, len(header),
-                                           C.byref(out), C.byref(n), C.byref(mode)))
+        rc = self.lib.sccg_compress(self.handle, ref, len(ref), tgt, len(tgt), header, len(header), C.byref(out), C.byref(n), C.byref(mode))
+        if rc == SCCG_E_STOI:
+            raise SccgError(rc, self.lib.sccg_last_error().decode(), self._take(out, n.value))
+        self._check(rc)
         return self._take(out, n.value), mode.value
 
     def compress_into(self, ref, tgt, header: bytes, out_ptr: int, out_cap: int) -> tuple[int, int]:

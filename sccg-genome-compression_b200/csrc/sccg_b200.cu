@@ -17,6 +17,17 @@ static int check_sizes(i64 a, i64 b) {
 
 static void prof_reset(sccg_ctx* c) { memset(&c->prof, 0, sizeof c->prof); }
 
+// read_genomes_from_files only ever yields a header that starts with '>' (compression.cpp:208-213); delta_encode keys its
+// line skipping on that byte (:237), so anything else would shift the text it rewrites
+static int check_header(const char* header, int64_t header_len) {
+    if (header_len > 0 && header[0] != '>') return set_error(SCCG_E_ARG, "header must be empty or start with '>'");
+    if (header_len > 0 && memchr(header, '\n', (size_t)header_len)) return set_error(SCCG_E_ARG, "header must be a single line");
+    return SCCG_OK;
+}
+static int stoi_failure() {
+    return set_error(SCCG_E_STOI, "stoi (a literal '(' in the target breaks the reference's delta_encode; the output holds the un-rewritten image)");
+}
+
 }  // namespace sccg
 
 extern "C" {
@@ -91,6 +102,7 @@ int sccg_compress_device(sccg_ctx* c, const void* d_ref, int64_t ref_len, const 
                          const char* header, int64_t header_len, void** d_out, int64_t* out_len, int* mode_out) {
     if (!c || !d_out || !out_len || (header_len > 0 && !header)) return set_error(SCCG_E_ARG, "null argument");
     SCCG_TRY(check_sizes(ref_len, tgt_len));
+    SCCG_TRY(check_header(header, header_len));
     if (((uintptr_t)d_ref | (uintptr_t)d_tgt) & 15) return set_error(SCCG_E_ARG, "device inputs must be 16-byte aligned");
     SCCG_CK(cudaSetDevice(c->device));
     prof_reset(c);
@@ -98,13 +110,14 @@ int sccg_compress_device(sccg_ctx* c, const void* d_ref, int64_t ref_len, const 
     SCCG_TRY(compress_device(c, (const u8*)d_ref, ref_len, (const u8*)d_tgt, tgt_len, header, header_len < 0 ? 0 : header_len, &res));
     *d_out = res.d_out; *out_len = res.out_len;
     if (mode_out) *mode_out = res.mode;
-    return SCCG_OK;
+    return res.stoi_failed ? stoi_failure() : SCCG_OK;
 }
 
 static int compress_host(sccg_ctx* c, const char* ref, int64_t ref_len, const char* tgt, int64_t tgt_len, const char* header, int64_t header_len,
                          char* dst, int64_t dst_cap, char** out, int64_t* out_len, int* mode_out) {
     if (!c || !out_len || (ref_len > 0 && !ref) || (tgt_len > 0 && !tgt) || (header_len > 0 && !header)) return set_error(SCCG_E_ARG, "null argument");
     SCCG_TRY(check_sizes(ref_len, tgt_len));
+    SCCG_TRY(check_header(header, header_len));
     SCCG_CK(cudaSetDevice(c->device));
     prof_reset(c);
     u8 *d_ref = nullptr, *d_tgt = nullptr;
@@ -121,7 +134,7 @@ static int compress_host(sccg_ctx* c, const char* ref, int64_t ref_len, const ch
     cudaEventElapsedTime(&c->prof.h2d_ms, c->ev[4], c->ev[5]);
     cudaEventElapsedTime(&c->prof.d2h_ms, c->ev[6], c->ev[7]);
     if (mode_out) *mode_out = res.mode;
-    return SCCG_OK;
+    return res.stoi_failed ? stoi_failure() : SCCG_OK;
 }
 
 int sccg_compress(sccg_ctx* c, const char* ref, int64_t ref_len, const char* tgt, int64_t tgt_len,

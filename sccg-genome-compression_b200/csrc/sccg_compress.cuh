@@ -3,13 +3,14 @@
 #pragma once
 #include "sccg_rle.cuh"
 #include "sccg_local.cuh"
+#include "sccg_delta.cuh"
 
 namespace sccg {
 
 // device scalars (u32 each)
 enum Scalar {
     S_LOW_K = 0, S_LOW_KE, S_LOW_TEXT, S_ABORT, S_BODY_MAIN, S_BODY_BASE, S_N_K, S_N_KE, S_N_TEXT,
-    S_G0, S_G1, S_G2, S_G3, S_G4, S_G5, S_G6, S_G7, S_WORK = 64, S_COUNT = 128   // S_WORK: own 128-byte line (hot atomic)
+    S_G0, S_G1, S_G2, S_G3, S_G4, S_G5, S_G6, S_G7, S_PAREN, S_DT = 24 /* 4 slots */, S_WORK = 64, S_COUNT = 128   // S_WORK: own 128-byte line (hot atomic)
 };
 
 // writes the separator after the lowercase line and publishes where the body starts
@@ -32,10 +33,20 @@ struct CompressResult {
     u8* d_out;
     i64 out_len;
     int mode;
+    int stoi_failed;        // delta_encode's stoi would have thrown (:279): d_out is the un-rewritten, pre-delta image
 };
 
+// the reference's delta_encode replayed at text level on a pre-delta image (sccg_delta.cuh); updates res
+static int finish_text_delta(sccg_ctx* c, u32* sc, u32 body_base, CompressResult* res) {
+    u8* fin = nullptr; i64 fin_len = 0; bool failed = false;
+    SCCG_TRY(delta_text_pass(c, res->d_out, res->out_len, body_base, sc + S_DT, &fin, &fin_len, &failed));
+    if (failed) res->stoi_failed = 1;
+    else { res->d_out = fin; res->out_len = fin_len; }
+    return SCCG_OK;
+}
+
 static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt, i64 nt, const char* header, i64 nh,
-                                  u32 low_k, const u32* cnt_s, const u32* cnt_e, CompressResult* res);
+                                  u32 low_k, const u32* cnt_s, const u32* cnt_e, int text_delta, CompressResult* res);
 
 static int read_scalars(sccg_ctx* c, const u32* d_scalars, u32* host, int count) {
     SCCG_CK(cudaMemcpyAsync(c->h_pinned, d_scalars, sizeof(u32) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
@@ -62,7 +73,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
 
     // ---- lowercase runs of the raw target: count (:341-367)
     u32 *cnt_s = nullptr, *cnt_e = nullptr;
-    SCCG_TRY(rle_count<0>(c, d_tgt, nt, B_RUN_CNT, &cnt_s, &cnt_e, sc + S_LOW_K, sc + S_LOW_KE));
+    SCCG_TRY(rle_count<0>(c, d_tgt, nt, B_RUN_CNT, &cnt_s, &cnt_e, sc + S_LOW_K, sc + S_LOW_KE, sc + S_PAREN));
 
     // ---- local segment matching (:381-474)
     const i64 n_rseg = (nr + SEG - 1) / SEG, n_tseg = (nt + SEG - 1) / SEG;
@@ -83,7 +94,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
         SCCG_CK(cudaMemsetAsync(seginfo, 0xff, sizeof(u32) * (size_t)n_iter, c->stream));    // "not done" markers for the early T2 abort
         LAUNCH(c, seg_match_k, dim3(grid), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, n_iter, K1, K2, seginfo, matches, sc + S_WORK, sc + S_ABORT);
         SCCG_CK(cudaEventRecord(c->ev[2], c->stream));
-        LAUNCH(c, seg_bytes_k, dim3(div_up(n_iter, 256)), dim3(256), 0, (const u32*)seginfo, (const u32*)matches, n_iter, seg_bytes, seg_prev, sc + S_ABORT);
+        LAUNCH(c, seg_bytes_k, dim3(div_up(n_iter, 256)), dim3(256), 0, (const u32*)seginfo, (const u32*)matches, n_iter, seg_bytes, seg_prev, sc + S_ABORT, 0);
     } else {
         SCCG_CK(cudaEventRecord(c->ev[2], c->stream));
     }
@@ -93,7 +104,14 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
     SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
     if (h[S_LOW_K] != h[S_LOW_KE]) return set_error(SCCG_E_CUDA, "internal: run start/end counts differ");
     if (h[S_ABORT]) {                                                         // :462-473 -> global (:484-574)
-        return compress_global_device(c, d_ref, nr, d_tgt, nt, header, nh, h[S_LOW_K], cnt_s, cnt_e, res);
+        return compress_global_device(c, d_ref, nr, d_tgt, nt, header, nh, h[S_LOW_K], cnt_s, cnt_e, h[S_PAREN] != 0, res);
+    }
+    // a '(' somewhere in the target: tokens are written with absolute p and delta_encode is replayed at text level
+    const int text_delta = h[S_PAREN] != 0;
+    if (text_delta && n_iter > 0) {
+        LAUNCH(c, seg_bytes_k, dim3(div_up(n_iter, 256)), dim3(256), 0, (const u32*)seginfo, (const u32*)matches, n_iter, seg_bytes, seg_prev, sc + S_ABORT, 1);
+        SCCG_TRY(scan_exclusive_u32(c, seg_bytes, seg_bytes, (i64)n_iter, sc + S_BODY_MAIN));
+        SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
     }
 
     // ---- assemble "<header>\n<lowercase runs>\n,\n<body>"
@@ -112,7 +130,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
         unsigned want = div_up(n_iter, 8 * 32);                              // 8 warps per CTA, 32 segments per warp
         unsigned capg = (unsigned)c->sm_count * 8u;
         LAUNCH(c, seg_write_k, dim3(want < capg ? want : capg), dim3(256), 0, d_tgt, nt, (const u32*)seginfo, (const u32*)matches,
-               (const u32*)seg_bytes, (const int*)seg_prev, n_iter, out, (const u32*)(sc + S_BODY_BASE));
+               (const u32*)seg_bytes, (const int*)seg_prev, n_iter, out, (const u32*)(sc + S_BODY_BASE), text_delta);
     }
     if (leftover > 0) {
         unsigned g = div_up(leftover, 256 * 16);
@@ -126,6 +144,12 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
     res->d_out = out;
     res->out_len = (i64)hdr_bytes + h2[S_LOW_TEXT] + 3 + h[S_BODY_MAIN] + leftover;
     res->mode = 0;
+    res->stoi_failed = 0;
+    if (text_delta) {
+        SCCG_TRY(finish_text_delta(c, sc, (u32)(hdr_bytes + h2[S_LOW_TEXT] + 3), res));
+        SCCG_CK(cudaEventRecord(c->ev[3], c->stream));
+        SCCG_CK(cudaStreamSynchronize(c->stream));
+    }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); c->prof.kernels_ms = ms;
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->prof.match_ms = ms;

@@ -523,19 +523,19 @@ __global__ void __launch_bounds__(128) gp_concat_k(GpFrontArgs f, const u32* __r
 // record writer for one long parse (compression.cpp:564-573 + delta_encode :258-292)
 // ------------------------------------------------------------------------------------------------
 // bytes[i] = literal gap before match i + its token
-__global__ void g_match_bytes_k(const int* __restrict__ tpos, const int* __restrict__ mp, const int* __restrict__ ml, u32 M, u32* __restrict__ bytes) {
+__global__ void g_match_bytes_k(const int* __restrict__ tpos, const int* __restrict__ mp, const int* __restrict__ ml, u32 M, u32* __restrict__ bytes, int absolute) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
     int prev_end = i ? tpos[i - 1] + ml[i - 1] : 0;
-    int prev_p = i ? mp[i - 1] : 0;
+    int prev_p = (i && !absolute) ? mp[i - 1] : 0;
     bytes[i] = (u32)(tpos[i] - prev_end) + 3u + (u32)dec_len_i32(mp[i] - prev_p) + (u32)dec_len_u32((u32)ml[i]);
 }
 __global__ void g_write_tokens_k(const int* __restrict__ tpos, const int* __restrict__ mp, const int* __restrict__ ml, u32 M, const u32* __restrict__ offs,
-                                 u8* __restrict__ out, const u32* __restrict__ d_body_base) {
+                                 u8* __restrict__ out, const u32* __restrict__ d_body_base, int absolute) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
     int prev_end = i ? tpos[i - 1] + ml[i - 1] : 0;
-    int prev_p = i ? mp[i - 1] : 0;
+    int prev_p = (i && !absolute) ? mp[i - 1] : 0;
     write_token(out + *d_body_base + offs[i] + (u32)(tpos[i] - prev_end), mp[i] - prev_p, ml[i]);
 }
 // literal symbols: every target position not covered by a match; 16 positions per thread
@@ -633,7 +633,7 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
 }
 
 static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt, i64 nt, const char* header, i64 nh,
-                                  u32 low_k, const u32* cnt_s, const u32* cnt_e, CompressResult* res) {
+                                  u32 low_k, const u32* cnt_s, const u32* cnt_e, int text_delta, CompressResult* res) {
     u32* sc = nullptr;
     SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
     // ---- N runs of the upper-cased target, original coordinates (:527-554): count
@@ -663,7 +663,7 @@ static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8
     // ---- sizes
     u32* mbytes = nullptr;
     SCCG_TRY(buf(c, B_GTMP0, (size_t)M + 1, &mbytes));
-    if (M) LAUNCH(c, g_match_bytes_k, dim3(div_up(M, 256)), dim3(256), 0, (const int*)gm.tpos, (const int*)gm.p, (const int*)gm.l, M, mbytes);
+    if (M) LAUNCH(c, g_match_bytes_k, dim3(div_up(M, 256)), dim3(256), 0, (const int*)gm.tpos, (const int*)gm.p, (const int*)gm.l, M, mbytes, text_delta);
     SCCG_TRY(scan_exclusive_u32(c, mbytes, mbytes, (i64)M, sc + S_G4));
     u32 last[3] = {0, 0, 0};                                      // end of the last match in the target
     if (M) {
@@ -694,7 +694,7 @@ static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8
     const u32 low_text = h[S_LOW_TEXT], n_text = h[S_N_TEXT];
     if (n_text) SCCG_CK(cudaMemcpyAsync(out + hdr_bytes + low_text + 1, ntext, n_text, cudaMemcpyDeviceToDevice, c->stream));
     if (M) LAUNCH(c, g_write_tokens_k, dim3(div_up(M, 256)), dim3(256), 0, (const int*)gm.tpos, (const int*)gm.p, (const int*)gm.l, M,
-                  (const u32*)mbytes, out, (const u32*)(sc + S_BODY_BASE));
+                  (const u32*)mbytes, out, (const u32*)(sc + S_BODY_BASE), text_delta);
     if (nt2 > 0) LAUNCH(c, g_write_literals_k, dim3(div_up(nt2, 256 * 16)), dim3(256), 0, (const u8*)T2, nt2, (const int*)gm.tpos, (const int*)gm.l, M,
                         (const u32*)mbytes, (const u32*)(sc + S_G4), out, (const u32*)(sc + S_BODY_BASE));
     SCCG_CK(cudaEventRecord(c->ev[3], c->stream));
@@ -702,6 +702,12 @@ static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8
     res->d_out = out;
     res->out_len = (i64)hdr_bytes + low_text + 1 + n_text + 1 + (i64)body_bytes;
     res->mode = 1;
+    res->stoi_failed = 0;
+    if (text_delta) {
+        SCCG_TRY(finish_text_delta(c, sc, (u32)(hdr_bytes + low_text + 1 + n_text + 1), res));
+        SCCG_CK(cudaEventRecord(c->ev[3], c->stream));
+        SCCG_CK(cudaStreamSynchronize(c->stream));
+    }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); c->prof.kernels_ms = ms;
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->prof.match_ms = ms;

@@ -372,8 +372,10 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
 
 // Segment driver bookkeeping (compression.cpp:395-474): T2 abort test, delta chain carry, text size.
 // One thread per segment.
+// absolute != 0: tokens carry the absolute p as the reference writes them BEFORE delta_encode (:406-415); used when the
+// text-level delta pass (sccg_delta.cuh) has to reproduce delta_encode on a body that contains literal '('.
 __global__ void seg_bytes_k(const u32* __restrict__ seginfo, const u32* __restrict__ matches, int n_iter,
-                            u32* __restrict__ seg_bytes, int* __restrict__ seg_prev_p, u32* __restrict__ d_abort) {
+                            u32* __restrict__ seg_bytes, int* __restrict__ seg_prev_p, u32* __restrict__ d_abort, int absolute) {
     int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (i >= n_iter) return;
     if (*d_abort) return;                                    // raised early by seg_match_k: seginfo is incomplete and will be discarded
@@ -406,7 +408,7 @@ __global__ void seg_bytes_k(const u32* __restrict__ seginfo, const u32* __restri
     for (int m = 0; m < nmatch; ++m) {
         u32 pk = matches[(i64)i * LM_SLOT + m];
         int p_abs = i * SEG + (int)((pk >> 10) & 0x3ffu);
-        bytes += 3u + (u32)dec_len_i32(p_abs - pp) + (u32)dec_len_u32(pk >> 20);
+        bytes += 3u + (u32)dec_len_i32(absolute ? p_abs : p_abs - pp) + (u32)dec_len_u32(pk >> 20);
         pp = p_abs;
     }
     seg_bytes[i] = bytes;
@@ -425,7 +427,7 @@ __device__ __forceinline__ int write_token(u8* o, int dp, int l) {
 
 // one segment written by the whole warp (many matches or long literal runs)
 __device__ __forceinline__ void seg_write_coop(const u8* __restrict__ tgt, i64 nt, const u32* __restrict__ matches, int seg, int nmatch,
-                                               u8* __restrict__ base, int prevp) {
+                                               u8* __restrict__ base, int prevp, int absolute) {
     const int lane = lane_of();
     const i64 toff = (i64)seg * SEG;
     const int Lt = (int)((nt - toff) < SEG ? (nt - toff) : SEG);
@@ -441,6 +443,7 @@ __device__ __forceinline__ void seg_write_coop(const u8* __restrict__ tgt, i64 n
         int pp = __shfl_up_sync(SCCG_FULL_MASK, p_abs, 1);
         int pe = __shfl_up_sync(SCCG_FULL_MASK, te, 1);
         if (lane == 0) { pp = prevp; pe = prev_end; }
+        if (absolute) pp = 0;
         int gap = valid ? tpos - pe : 0;
         int tok = valid ? 3 + dec_len_i32(p_abs - pp) + dec_len_u32((u32)l) : 0;
         u32 mine = (u32)(gap + tok);
@@ -471,7 +474,7 @@ __device__ __forceinline__ void seg_write_coop(const u8* __restrict__ tgt, i64 n
 // literal runs are handed to the whole warp one after the other.
 __global__ void __launch_bounds__(256) seg_write_k(const u8* __restrict__ tgt, i64 nt, const u32* __restrict__ seginfo, const u32* __restrict__ matches,
                                                    const u32* __restrict__ seg_off, const int* __restrict__ seg_prev_p, int n_iter,
-                                                   u8* __restrict__ out, const u32* __restrict__ d_body_base) {
+                                                   u8* __restrict__ out, const u32* __restrict__ d_body_base, int absolute) {
     const int lane = lane_of();
     const int warps_total = (int)(gridDim.x * (blockDim.x >> 5));
     u8* body = out + *d_body_base;
@@ -490,7 +493,7 @@ __global__ void __launch_bounds__(256) seg_write_k(const u8* __restrict__ tgt, i
                 int tpos = (int)(pk & 0x3ffu), l = (int)(pk >> 20);
                 int p_abs = seg * SEG + (int)((pk >> 10) & 0x3ffu);
                 for (int x = pe; x < tpos; ++x) *o++ = upper1(tgt[toff + x]);
-                o += write_token(o, p_abs - pp, l);
+                o += write_token(o, absolute ? p_abs : p_abs - pp, l);
                 pp = p_abs; pe = tpos + l;
             }
             for (int x = pe; x < Lt; ++x) *o++ = upper1(tgt[toff + x]);
@@ -500,7 +503,7 @@ __global__ void __launch_bounds__(256) seg_write_k(const u8* __restrict__ tgt, i
             int src = __ffs((int)heavy) - 1; heavy &= heavy - 1;
             int hseg = seg0 + src;
             int hn = __shfl_sync(SCCG_FULL_MASK, nmatch, src);
-            seg_write_coop(tgt, nt, matches, hseg, hn, body + seg_off[hseg], seg_prev_p[hseg]);
+            seg_write_coop(tgt, nt, matches, hseg, hn, body + seg_off[hseg], seg_prev_p[hseg], absolute);
         }
     }
 }

@@ -21,19 +21,24 @@ template <int MODE> __device__ __forceinline__ u32 rle_pred8(u64 w) {
 }
 
 // start / end masks of the 64 positions [i, i+64) owned by this thread (bit b <=> position i + b)
-template <int MODE> __device__ __forceinline__ void rle_masks(const u8* __restrict__ src, i64 n, i64 i, u64* starts, u64* ends) {
+// *paren (optional): non-zero iff one of the owned positions holds '(' (a literal '(' changes what the reference's text-level
+// delta_encode does, compression.cpp:262-292; the compressor then takes its text-level delta pass)
+template <int MODE> __device__ __forceinline__ void rle_masks(const u8* __restrict__ src, i64 n, i64 i, u64* starts, u64* ends, u64* paren = nullptr) {
     *starts = 0; *ends = 0;
+    if (paren) *paren = 0;
     if (i >= n) return;
-    u64 m = 0;
+    u64 m = 0, pm = 0;
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
         if (i + 16 * v < n) {
             ulonglong2 w = *reinterpret_cast<const ulonglong2*>(src + i + 16 * v);   // buffers carry >= 64 B of slack
             m |= (u64)(rle_pred8<MODE>(w.x) | (rle_pred8<MODE>(w.y) << 8)) << (16 * v);
+            if (paren) pm |= (u64)(movemask8(eq_flags8(w.x, '(')) | (movemask8(eq_flags8(w.y, '(')) << 8)) << (16 * v);
         }
     }
     i64 left = n - i;
-    if (left < 64) m &= (1ull << (int)left) - 1ull;
+    if (left < 64) { m &= (1ull << (int)left) - 1ull; pm &= (1ull << (int)left) - 1ull; }
+    if (paren) *paren = pm;
     u64 prev = (i > 0) ? (u64)rle_pred1<MODE>(src[i - 1]) : 0ull;
     u64 next = (i + 64 < n) ? (u64)rle_pred1<MODE>(src[i + 64]) : 0ull;
     *starts = m & ~((m << 1) | prev);
@@ -41,11 +46,17 @@ template <int MODE> __device__ __forceinline__ void rle_masks(const u8* __restri
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(RLE_T) rle_count_k(const u8* __restrict__ src, i64 n, u32* __restrict__ cnt_s, u32* __restrict__ cnt_e) {
+__global__ void __launch_bounds__(RLE_T) rle_count_k(const u8* __restrict__ src, i64 n, u32* __restrict__ cnt_s, u32* __restrict__ cnt_e, u32* paren_flag) {
     __shared__ u32 sm[40];
     i64 i = (i64)blockIdx.x * RLE_TILE + (i64)threadIdx.x * RLE_PER_THREAD;
     u64 s, e;
-    rle_masks<MODE>(src, n, i, &s, &e);
+    if (MODE == 0 && paren_flag) {
+        u64 pm;
+        rle_masks<MODE>(src, n, i, &s, &e, &pm);
+        if (pm) atomicOr(paren_flag, 1u);
+    } else {
+        rle_masks<MODE>(src, n, i, &s, &e);
+    }
     u32 packed = (u32)__popcll(s) | ((u32)__popcll(e) << 16);         // <= 8192 each per tile: no overflow
     u32 tot;
     block_scan_excl(packed, sm, &tot);
@@ -107,12 +118,12 @@ __global__ void runs_write_k(const int* __restrict__ run_start, const int* __res
 
 // Phase 1: count runs.  Leaves the per-tile exclusive offsets in cnt_s / cnt_e and the run count in d_count.
 template <int MODE>
-static int rle_count(sccg_ctx* c, const u8* d_src, i64 n, int slot_cnt, u32** cnt_s, u32** cnt_e, u32* d_count, u32* d_count_e) {
+static int rle_count(sccg_ctx* c, const u8* d_src, i64 n, int slot_cnt, u32** cnt_s, u32** cnt_e, u32* d_count, u32* d_count_e, u32* d_paren_flag = nullptr) {
     unsigned ntiles = div_up(n > 0 ? n : 1, RLE_TILE);
     u32* cnt = nullptr;
     SCCG_TRY(buf(c, slot_cnt, (size_t)ntiles * 2, &cnt));
     *cnt_s = cnt; *cnt_e = cnt + ntiles;
-    LAUNCH(c, rle_count_k<MODE>, dim3(ntiles), dim3(RLE_T), 0, d_src, n, *cnt_s, *cnt_e);
+    LAUNCH(c, rle_count_k<MODE>, dim3(ntiles), dim3(RLE_T), 0, d_src, n, *cnt_s, *cnt_e, d_paren_flag);
     SCCG_TRY(scan_exclusive_u32(c, *cnt_s, *cnt_s, (i64)ntiles, d_count));
     SCCG_TRY(scan_exclusive_u32(c, *cnt_e, *cnt_e, (i64)ntiles, d_count_e));
     return SCCG_OK;

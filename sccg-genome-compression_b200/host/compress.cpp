@@ -33,7 +33,7 @@ int main(int argc, char* argv[]) {
         char* out = nullptr; int64_t out_len = 0; int mode = 0;
         int rc = sccg_compress(ctx, ref.data(), (int64_t)ref.size(), tgt.data(), (int64_t)tgt.size(), header.data(), (int64_t)header.size(),
                                &out, &out_len, &mode);
-        if (rc != SCCG_OK) { std::cerr << "Error: " << sccg_last_error() << "\n"; sccg_destroy(ctx); return 1; }
+        if (rc != SCCG_OK && rc != SCCG_E_STOI) { std::cerr << "Error: " << sccg_last_error() << "\n"; sccg_destroy(ctx); return 1; }
         sccg_profile prof; sccg_get_profile(ctx, &prof);
 
         std::filesystem::create_directories(out_dir);                        // :334
@@ -43,6 +43,7 @@ int main(int argc, char* argv[]) {
         fclose(f);
         sccg_free(out);
         sccg_destroy(ctx);
+        if (rc == SCCG_E_STOI) { std::cerr << "Error: stoi\n"; return 1; }     // delta_encode threw (:279 -> :604-607): file left un-rewritten, no 7z
         std::cout << "mode: " << (mode ? "global" : "local") << ", GPU kernels " << prof.kernels_ms << " ms, H2D " << prof.h2d_ms << " ms, D2H "
                   << prof.d2h_ms << " ms\n";
 

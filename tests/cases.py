@@ -126,6 +126,16 @@ def cases() -> list[Case]:
 
     # J: grammar symbols in the target corrupt the body (compress side is still pinned)
     out.append(Case("J_grammar_symbols", R3[:2000], put(R3[:2000], 500, b"(7,"), expect_mode=0, lossless=False))
+    # J2..J6: what the reference's TEXT-level delta_encode (compression.cpp:262-292) does with literal parentheses
+    #   J2 a lone '(' pairs with the next token's ')' -> stoi("(501") throws: exit 1, file left un-rewritten (rc_compress = 1)
+    #   J3 "()" has no comma -> skipped (:274-277)      J4 '(' with no ')' after it ends the loop (:269-270)
+    #   J5 a literal look-alike "(12x,5)" is rewritten and poisons the chain      J6 the same in global mode
+    out.append(Case("J2_lone_paren_stoi_throws", R3[:2000], put(R3[:2000], 500, b"("), expect_mode=0, lossless=False))
+    out.append(Case("J3_empty_parens", R3[:2500], put(R3[:2500], 1500, b"()"), expect_mode=0, lossless=False))
+    out.append(Case("J4_unclosed_paren_in_tail", R3[:2000], R3[:2000] + b"ACGT(ACGTACGT", expect_mode=0, lossless=False))
+    out.append(Case("J5_token_lookalike", R3[:3000], put(R3[:3000], 1200, b"(12x,5)"), expect_mode=0, lossless=False))
+    rJ = rnd(20000, "J6")
+    out.append(Case("J6_global_literal_paren", rJ, put(rJ[:2500] + rnd(3000, "J6ins") + rJ[2500:], 3000, b"(7,"), expect_mode=1, lossless=False))
 
     # K: co-located N runs compress to plain tokens
     k = rnd(1000, "K1") + b"N" * 1000 + rnd(300, "K2") + b"N" * 400 + rnd(300, "K3")

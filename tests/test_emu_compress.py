@@ -34,8 +34,13 @@ def sweep_order(request):
 def test_compress_matches_golden(ctx, case, golden):
     g = golden["cases"][case.name]
     expect = zlib.decompress(base64.b64decode(g["intermediate_z"]))
-    if case.name == "J_grammar_symbols":
-        pytest.xfail("literal '(' in the target: needs the text-level delta pass (DESIGN.md, known gap)")
+    if g["rc_compress"] != 0:
+        # the reference died in delta_encode's stoi (literal '(' in the target): same failure, same file left behind
+        import sccg_b200
+        with pytest.raises(sccg_b200.SccgError) as ei:
+            ctx.compress(case.ref, case.tgt, case.header)
+        assert ei.value.code == sccg_b200.SCCG_E_STOI and ei.value.partial == expect
+        return
     got, mode = ctx.compress(case.ref, case.tgt, case.header)
     assert mode == g["mode"]
     assert got == expect
@@ -89,6 +94,63 @@ def test_compress_local_random(ctx, seed):
         pytest.skip("went global")
     got, gmode = ctx.compress(ref, bytes(t), b">rnd")
     assert gmode == 0 and got == exp
+
+
+GRAMMAR_PIECES = [b"(", b")", b",", b"(5,", b"(12,3)", b"()", b"(-7,2)", b"(+3,1)", b"(99999999999,1)", b"(2147483647,9)", b"((", b"))", b"(,)",
+                  b"(3", b"7)", b"(x,1)", b"0123456789", b"(1,2,3)", b"(-,", b"(2147483648,1)", b"(-2147483648,1)"]
+
+
+SAFE_PIECES = [b")", b",", b"(5,", b"(12,3)", b"()", b"(-7,2)", b"(+3,1)", b"0123456789", b"(1,2,3)", b"(2147483647,9)", b"(-2147483648,1)", b"))", b"7)"]
+
+
+def grammar_pair(seed, n=9000, pieces=6, make_global=False):
+    """a near-identical pair whose target carries literal grammar symbols of the record stream (experiment J)"""
+    r = random.Random(repr(("gram", seed)))
+    ref = rnd(n, ("gramref", seed))
+    t = bytearray(mutate_some(ref, r, n // 700))
+    if make_global:
+        t[n // 4:n // 4] = rnd(5200, ("gramins", seed))            # a 5 kb insertion: T2 abort -> global parse
+    for _ in range(pieces):
+        piece = r.choice(GRAMMAR_PIECES if seed % 2 else SAFE_PIECES)     # even seeds: stoi never throws
+        at = r.randrange(0, len(t) - len(piece))
+        t[at:at + len(piece)] = piece
+    if seed % 3 == 0:
+        t += r.choice(SAFE_PIECES) + b"ACGT"                      # leftover literals past the last reference segment
+    return ref, bytes(t)
+
+
+def mutate_some(seq, r, count):
+    b = bytearray(seq)
+    for p in r.sample(range(len(b)), count):
+        b[p] = r.choice(b"ACGT")
+    return bytes(b)
+
+
+def check_compress_like_oracle(ctx, ref, tgt, header=b">gram (alt) 1,2"):
+    import sccg_b200
+    rc, exp, mode = ol.orc_compress(ref, tgt, header)
+    if rc != 0:                                                     # the reference throws from stoi: file left un-rewritten, exit 1
+        with pytest.raises(sccg_b200.SccgError) as ei:
+            ctx.compress(ref, tgt, header)
+        assert ei.value.code == sccg_b200.SCCG_E_STOI and ei.value.partial == exp
+        return "stoi"
+    got, gmode = ctx.compress(ref, tgt, header)
+    assert (gmode, got) == (mode, exp)
+    return "ok"
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_text_level_delta_fuzz(ctx, seed):
+    """literal '(' ')' ',' and digits in the target: the text-level delta pass must reproduce delta_encode (:262-292) byte for byte"""
+    ref, tgt = grammar_pair(seed, make_global=(seed % 4 >= 2))
+    check_compress_like_oracle(ctx, ref, tgt)
+
+
+def test_text_level_delta_long_literal_runs(ctx):
+    # '(' far away from the next ')' (wide searches / copies of the warp), target much longer than the reference
+    ref = rnd(3000, "tl")
+    tgt = ref[:1500] + b"(" + ref[1501:] + rnd(70000, "tl2") + b")" + rnd(5000, "tl3") + b"(12,3)" + rnd(300, "tl4")
+    assert check_compress_like_oracle(ctx, ref, tgt) in ("ok", "stoi")
 
 
 def test_many_segments_scan_paths(ctx):

@@ -10,7 +10,7 @@ import pytest
 
 import oracle_lib as ol
 from cases import cases
-from test_emu_compress import _mutated_pair
+from test_emu_compress import _mutated_pair, check_compress_like_oracle, grammar_pair
 
 pytestmark = pytest.mark.gpu
 CASES = cases()
@@ -40,11 +40,32 @@ def _report(name, got, exp):
 def test_compress_matches_golden(ctx, case, golden):
     g = golden["cases"][case.name]
     expect = zlib.decompress(base64.b64decode(g["intermediate_z"]))
-    if case.name == "J_grammar_symbols":
-        pytest.xfail("literal '(' in the target: needs the text-level delta pass (DESIGN.md, known gap)")
+    if g["rc_compress"] != 0:
+        # the reference died in delta_encode's stoi (literal '(' in the target): same failure, same file left behind
+        import sccg_b200
+        with pytest.raises(sccg_b200.SccgError) as ei:
+            ctx.compress(case.ref, case.tgt, case.header)
+        assert ei.value.code == sccg_b200.SCCG_E_STOI and ei.value.partial == expect
+        return
     got, mode = ctx.compress(case.ref, case.tgt, case.header)
     assert mode == g["mode"]
     assert got == expect, _report(case.name, got, expect)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_text_level_delta_fuzz(ctx, seed):
+    ref, tgt = grammar_pair(seed, make_global=(seed % 4 >= 2))
+    check_compress_like_oracle(ctx, ref, tgt)
+
+
+def test_text_level_delta_large(ctx):
+    """a 5 Mbp pair with a handful of literal parentheses: every token goes through the text-level pass"""
+    from sccg_genome_compression_b200 import synth
+    ref, tgt = synth.local_pair(5_000_000, synth.seed_for(2, 11))
+    t = bytearray(tgt.tobytes())
+    for at, piece in ((1_234_567, b"(7,"), (2_500_001, b"()"), (4_000_123, b"(12,3)")):
+        t[at:at + len(piece)] = piece
+    assert check_compress_like_oracle(ctx, ref.tobytes(), bytes(t)) == "ok"
 
 
 @pytest.mark.parametrize("seed", range(24))

@@ -112,3 +112,20 @@ def test_reconstruct_malformed_inputs_agree():
         rc_r, _, _ = ol.ref_reconstruct(ref, enc, b"", b"")
         rc_o, _ = ol.orc_reconstruct(ref, enc, b"", b"")
         assert rc_r == 1 and rc_o == 1
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_grammar_symbols_in_target_cli_level(seed):
+    """literal '(' ')' ',' digits in the target (SURVEY N2 / experiment J): the oracle's text-level delta_encode against
+    the reference program itself, incl. the stoi failure (exit 1, compressed_genome.txt left un-rewritten)"""
+    from test_emu_compress import grammar_pair
+    ref, tgt = grammar_pair(seed, make_global=(seed % 4 >= 2))
+    header = b">gram (alt) 1,2"
+    rc, exp, _ = ol.orc_compress(ref, tgt, header)
+    with tempfile.TemporaryDirectory() as d:
+        d = Path(d)
+        ol.write_fasta(d / "r.fa", ref, b">ref")
+        ol.write_fasta(d / "t.fa", tgt, header)
+        rc_ref, inter = ol.ref_compress_cli(d / "r.fa", d / "t.fa", d / "out")
+    assert (rc != 0) == (rc_ref != 0)
+    assert inter == exp
