@@ -58,6 +58,7 @@ sccg_ctx* sccg_create(int device) {
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (c->sm_count <= 0) c->sm_count = 148;
     c->h_pinned_cap = 1 << 20;
+    { const char* e = getenv("SCCG_NO_DIAG"); c->use_diag = (e && atoi(e) != 0) ? 0 : 1; }    // tests: force the generic segment parse
     bool ok = cudaStreamCreate(&c->stream) == cudaSuccess && cudaMallocHost(&c->h_pinned, c->h_pinned_cap) == cudaSuccess;
     for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
     if (!ok) { set_error(SCCG_E_CUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError())); sccg_destroy(c); return nullptr; }
@@ -176,7 +177,7 @@ int sccg_match_sequences(sccg_ctx* c, const char* Sr, int64_t nr, const char* St
         // upper-cased symbols, for which this is the identity
         const size_t smem = sizeof(LmWarpSmem) * LM_WARPS;
         SCCG_SET_MAX_SMEM(seg_match_k, smem);
-        LAUNCH(c, seg_match_k, dim3(1), dim3(LM_WARPS * 32), smem, (const u8*)d_ref, (i64)(nr > 0 ? nr : 0), (const u8*)d_tgt, nt, 1, k, 0, seginfo, matches, sc + S_WORK, (u32*)nullptr);
+        LAUNCH(c, seg_match_k, dim3(1), dim3(LM_WARPS * 32), smem, (const u8*)d_ref, (i64)(nr > 0 ? nr : 0), (const u8*)d_tgt, nt, 1, k, 0, seginfo, matches, sc + S_WORK, (u32*)nullptr, c->use_diag);
         u32 info = 0;
         SCCG_CK(cudaMemcpyAsync(&info, seginfo, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
         SCCG_CK(cudaMemcpyAsync(h_matches, matches, sizeof(u32) * LM_SLOT, cudaMemcpyDeviceToHost, c->stream));

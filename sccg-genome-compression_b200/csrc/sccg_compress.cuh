@@ -92,7 +92,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
         unsigned cap = (unsigned)c->sm_count * 8u;                          // 8 CTAs of 4 warps fit the 227 KB of shared memory
         unsigned grid = want < cap ? want : cap;
         SCCG_CK(cudaMemsetAsync(seginfo, 0xff, sizeof(u32) * (size_t)n_iter, c->stream));    // "not done" markers for the early T2 abort
-        LAUNCH(c, seg_match_k, dim3(grid), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, n_iter, K1, K2, seginfo, matches, sc + S_WORK, sc + S_ABORT);
+        LAUNCH(c, seg_match_k, dim3(grid), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, n_iter, K1, K2, seginfo, matches, sc + S_WORK, sc + S_ABORT, c->use_diag);
         SCCG_CK(cudaEventRecord(c->ev[2], c->stream));
         LAUNCH(c, seg_bytes_k, dim3(div_up(n_iter, 256)), dim3(256), 0, (const u32*)seginfo, (const u32*)matches, n_iter, seg_bytes, seg_prev, sc + S_ABORT, 0);
     } else {

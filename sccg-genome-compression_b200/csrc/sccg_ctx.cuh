@@ -48,6 +48,10 @@ struct sccg_ctx {
     size_t h_pinned_cap;
     cudaEvent_t ev[8];
     sccg_profile prof;
+    unsigned scan_epoch;           // single-pass scan: epoch of the last launch, tiles handed out so far
+    unsigned scan_counter_base;
+    int scan_counter_ready;
+    int use_diag;                  // seg_match_k: try the diagonal-hypothesis parse first (SCCG_NO_DIAG=1 disables it)
 };
 
 namespace sccg {

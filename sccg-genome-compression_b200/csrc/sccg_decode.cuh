@@ -71,53 +71,102 @@ __device__ __forceinline__ int parse_tuple(const u8* __restrict__ s, i64 i, i64 
 }
 
 // ------------------------------------------------------------------------------------------------
-// body: per-byte classification (decompression.cpp:213-236)
-//   contrib[i] = symbols this byte contributes to the decoded sequence (1 literal, len token start, 0 inside)
-//   isseg[i]   = 1 where a copy segment starts (token start, or first byte of a literal run)
-//   istok[i]   = 1 at token starts
+// body tokenizer (decompression.cpp:213-236): every thread owns 16 consecutive bytes of the record stream.  The state
+// machine  outside --'('--> inside --')'--> outside  is evaluated on bit masks (byte-SWAR compares of the own 16 bytes
+// and of the 32 bytes before them for the entry state), so a warp never serialises over per-byte branches:
+//   token starts   "(d,l)"  -> one copy segment of l symbols taken from the reference
+//   literal runs            -> one copy segment per maximal run of literal bytes
+// Pass 1 (dec_count_k) leaves per-thread totals (decoded symbols, segments, tokens); after three scans, pass 2
+// (dec_emit_k) rebuilds the masks and writes the compacted tables directly:
+//   seg_dst[k] : offset of segment k in the decoded (N-free) sequence
+//   seg_src[k] : literal run -> index into enc | SEG_LIT_FLAG ; token -> token index (absolute position filled later)
+//   tok_delta[t], tok_len[t]
+// No per-byte side arrays exist: the stream is read twice (2 B per encoded byte) + 24 B per 16-byte chunk.
 // ------------------------------------------------------------------------------------------------
-__global__ void dec_classify_k(const u8* __restrict__ enc, i64 ne, u32* __restrict__ contrib, u32* __restrict__ isseg, u32* __restrict__ istok, u32* __restrict__ sc) {
-    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ne) return;
-    u8 c = enc[i];
-    bool inside = inside_token(enc, i);
-    u32 con = 0, seg = 0, tok = 0;
-    if (inside) {
-        // bytes of a token after its '(' : nothing to emit
-    } else if (c == '(') {
-        int d, l;
-        int w = parse_tuple(enc, i, ne, &d, &l);
-        if (!w || l < 0) { atomicOr(&sc[D_ERR], (u32)DE_FORMAT); }
-        else { con = (u32)l; seg = 1; tok = 1; }
-    } else {
-        con = 1;                                                  // literal symbol (:233)
-        seg = (i > 0 && is_literal(enc, i - 1)) ? 0u : 1u;        // first byte of a literal run
+#define SEG_LIT_FLAG 0x4000000000000000LL
+static const int DEC_T = 256;
+static const int DEC_PER_THREAD = 16;
+
+struct DecChunk { u32 tok, lit, segl; };       // bit b <=> byte i0 + b: token start / literal symbol / first byte of a literal run
+
+__device__ __forceinline__ u32 paren_mask16(ulonglong2 v, u8 ch) { return movemask8(eq_flags8(v.x, ch)) | (movemask8(eq_flags8(v.y, ch)) << 8); }
+
+// enc is 16-byte aligned with >= 16 readable bytes past ne; i0 is a multiple of 16 and < ne
+__device__ __forceinline__ DecChunk dec_chunk(const u8* __restrict__ enc, i64 ne, i64 i0) {
+    const ulonglong2 own = *reinterpret_cast<const ulonglong2*>(enc + i0);
+    const i64 left = ne - i0;
+    const u32 V = left >= 16 ? 0xffffu : ((1u << (int)left) - 1u);
+    const u32 O = paren_mask16(own, '(') & V, C = paren_mask16(own, ')') & V;
+    // entry state from the 32 bytes before the chunk (bit j <=> byte i0 - 32 + j)
+    u32 Op = 0, Cp = 0;
+    if (i0 >= 16) {
+        const ulonglong2 p1 = *reinterpret_cast<const ulonglong2*>(enc + i0 - 16);
+        Op = paren_mask16(p1, '(') << 16; Cp = paren_mask16(p1, ')') << 16;
+        if (i0 >= 32) {
+            const ulonglong2 p0 = *reinterpret_cast<const ulonglong2*>(enc + i0 - 32);
+            Op |= paren_mask16(p0, '('); Cp |= paren_mask16(p0, ')');
+        }
     }
-    contrib[i] = con; isseg[i] = seg; istok[i] = tok;
+    // inside_token(i0): the last parenthesis among bytes i0-25 .. i0-1 is '('      (bits 7..31)
+    bool in = (Op & 0xffffff80u) > (Cp & 0xffffff80u);
+    // is_literal(i0 - 1): not '(' and not inside a token that started in bytes i0-26 .. i0-2   (bits 6..30)
+    const bool prev_lit = i0 > 0 && !(Op >> 31) && !((Op & 0x7fffffc0u) > (Cp & 0x7fffffc0u));
+    u32 inside = 0;
+    int last = 0;
+    for (u32 pp = O | C; pp; pp &= pp - 1) {
+        const int b = __ffs((int)pp) - 1;
+        const bool is_open = (O >> b) & 1u;
+        if (in) { inside |= (2u << b) - (1u << last); if (!is_open) in = false; }     // the token runs through its ')'
+        else if (is_open) in = true;                                                   // a stray ')' is a literal (:233)
+        last = b + 1;
+    }
+    if (in) inside |= 0x10000u - (1u << last);
+    DecChunk c;
+    c.tok = O & ~inside;
+    c.lit = V & ~inside & ~c.tok;
+    c.segl = c.lit & ~((c.lit << 1) | (prev_lit ? 1u : 0u));
+    return c;
 }
 
-// compacts segments and tokens
-//   seg_dst[k] : offset of segment k in the decoded (N-free) sequence
-//   seg_src[k] : literal run -> index into enc | LIT_FLAG ; token -> token index (absolute position filled later)
-//   tok_delta[t], tok_len[t]
-#define SEG_LIT_FLAG 0x4000000000000000LL
-__global__ void dec_compact_k(const u8* __restrict__ enc, i64 ne, const u32* __restrict__ off, const u32* __restrict__ segidx, const u32* __restrict__ tokidx,
-                              u32* __restrict__ seg_dst, i64* __restrict__ seg_src, int* __restrict__ tok_delta, int* __restrict__ tok_len) {
-    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ne) return;
-    u8 c = enc[i];
-    bool inside = inside_token(enc, i);
-    if (inside) return;
-    if (c == '(') {
+__global__ void __launch_bounds__(DEC_T) dec_count_k(const u8* __restrict__ enc, i64 ne, u32* __restrict__ th_sym, u32* __restrict__ th_seg, u32* __restrict__ th_tok,
+                                                    u32* __restrict__ sc) {
+    const i64 t = (i64)blockIdx.x * DEC_T + threadIdx.x;
+    const i64 i0 = t * DEC_PER_THREAD;
+    if (i0 >= ne) return;
+    const DecChunk c = dec_chunk(enc, ne, i0);
+    u32 sym = (u32)__popc(c.lit);
+    for (u32 m = c.tok; m; m &= m - 1) {
         int d = 0, l = 0;
-        if (!parse_tuple(enc, i, ne, &d, &l)) return;
-        u32 k = segidx[i], t = tokidx[i];
-        seg_dst[k] = off[i];
-        seg_src[k] = (i64)t;
-        tok_delta[t] = d; tok_len[t] = l;
-    } else {
-        bool prev_lit = i > 0 && is_literal(enc, i - 1);
-        if (!prev_lit) { u32 k = segidx[i]; seg_dst[k] = off[i]; seg_src[k] = (i64)i | SEG_LIT_FLAG; }
+        if (!parse_tuple(enc, i0 + __ffs((int)m) - 1, ne, &d, &l) || l < 0) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);
+        else sym += (u32)l;
+    }
+    th_sym[t] = sym; th_seg[t] = (u32)__popc(c.tok | c.segl); th_tok[t] = (u32)__popc(c.tok);
+}
+
+// th_* hold exclusive prefixes by now
+__global__ void __launch_bounds__(DEC_T) dec_emit_k(const u8* __restrict__ enc, i64 ne, const u32* __restrict__ th_sym, const u32* __restrict__ th_seg,
+                                                   const u32* __restrict__ th_tok, u32* __restrict__ seg_dst, i64* __restrict__ seg_src,
+                                                   int* __restrict__ tok_delta, int* __restrict__ tok_len) {
+    const i64 t = (i64)blockIdx.x * DEC_T + threadIdx.x;
+    const i64 i0 = t * DEC_PER_THREAD;
+    if (i0 >= ne) return;
+    const DecChunk c = dec_chunk(enc, ne, i0);
+    u32 nseg = th_seg[t], ntok = th_tok[t];
+    const u32 sym0 = th_sym[t];
+    u32 tok_syms = 0;                                                  // symbols of the tokens seen so far in this chunk
+    for (u32 m = c.tok | c.segl; m; m &= m - 1) {
+        const int b = __ffs((int)m) - 1;
+        const u32 at = sym0 + (u32)__popc(c.lit & ((1u << b) - 1u)) + tok_syms;
+        seg_dst[nseg] = at;
+        if ((c.tok >> b) & 1u) {
+            int d = 0, l = 0;
+            parse_tuple(enc, i0 + b, ne, &d, &l);                      // validated by dec_count_k
+            seg_src[nseg] = (i64)ntok; tok_delta[ntok] = d; tok_len[ntok] = l;
+            tok_syms += (u32)l; ++ntok;
+        } else {
+            seg_src[nseg] = (i64)(i0 + b) | SEG_LIT_FLAG;
+        }
+        ++nseg;
     }
 }
 
@@ -449,17 +498,17 @@ static int reconstruct_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_
     SCCG_TRY(parse_runs(c, d_low, nl, B_NUM0, sc, D_LOW_ITEMS, sc + D_LSUM, &lows));     // slots B_NUM0..B_NUM3
     SCCG_TRY(parse_runs(c, d_n, nn, B_NUM4, sc, D_N_ITEMS, sc + D_NSUM, &ns));          // slots B_NUM4, B_NUM5, B_LRUN_S, B_LRUN_E
 
-    // ---- body tokenizer
-    u32 *contrib = nullptr, *isseg = nullptr, *istok = nullptr;
-    i64 ne1 = ne > 0 ? ne : 1;
-    SCCG_TRY(buf(c, B_TOK_FLAG, (size_t)ne1 * 3 + 3, &contrib));
-    isseg = contrib + ne1; istok = isseg + ne1;
-    if (ne > 0) {
-        LAUNCH(c, dec_classify_k, dim3(div_up(ne, 256)), dim3(256), 0, d_enc, ne, contrib, isseg, istok, sc);
-    }
-    SCCG_TRY(scan_exclusive_u32(c, contrib, contrib, ne, sc + D_LS));
-    SCCG_TRY(scan_exclusive_u32(c, isseg, isseg, ne, sc + D_NSEG));
-    SCCG_TRY(scan_exclusive_u32(c, istok, istok, ne, sc + D_NTOK));
+    // ---- body tokenizer: count per 16-byte chunk, scan, emit the compacted tables
+    const i64 nth = (ne + DEC_PER_THREAD - 1) / DEC_PER_THREAD;
+    const unsigned dblocks = div_up(nth > 0 ? nth : 1, DEC_T);
+    u32 *th_sym = nullptr, *th_seg = nullptr, *th_tok = nullptr;
+    const size_t th_stride = ((size_t)nth + 4) & ~(size_t)3;                    // keeps the three arrays 16-byte aligned
+    SCCG_TRY(buf(c, B_TOK_FLAG, th_stride * 3 + 4, &th_sym));
+    th_seg = th_sym + th_stride; th_tok = th_seg + th_stride;
+    if (ne > 0) LAUNCH(c, dec_count_k, dim3(dblocks), dim3(DEC_T), 0, d_enc, ne, th_sym, th_seg, th_tok, sc);
+    SCCG_TRY(scan_exclusive_u32(c, th_sym, th_sym, nth, sc + D_LS));
+    SCCG_TRY(scan_exclusive_u32(c, th_seg, th_seg, nth, sc + D_NSEG));
+    SCCG_TRY(scan_exclusive_u32(c, th_tok, th_tok, nth, sc + D_NTOK));
     u32 h[D_COUNT];
     SCCG_TRY(read_scalars(c, sc, h, D_COUNT));
     if (h[D_ERR] & DE_FORMAT) return set_error(SCCG_E_FORMAT, "malformed record stream (the reference would throw from stoi)");
@@ -474,8 +523,7 @@ static int reconstruct_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_
     tok_len = tok_delta + ntok + 1; tok_abs = tok_len + ntok + 1;
     SCCG_TRY(buf(c, B_TILE2, (size_t)ntok + 1, &delta_excl));
     if (ne > 0) {
-        LAUNCH(c, dec_compact_k, dim3(div_up(ne, 256)), dim3(256), 0, d_enc, ne, (const u32*)contrib, (const u32*)isseg, (const u32*)istok,
-               seg_dst, seg_src, tok_delta, tok_len);
+        LAUNCH(c, dec_emit_k, dim3(dblocks), dim3(DEC_T), 0, d_enc, ne, (const u32*)th_sym, (const u32*)th_seg, (const u32*)th_tok, seg_dst, seg_src, tok_delta, tok_len);
     }
     if (ntok > 0) {
         SCCG_TRY(scan_exclusive_u32(c, (const u32*)tok_delta, delta_excl, (i64)ntok, nullptr));

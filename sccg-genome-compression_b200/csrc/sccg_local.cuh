@@ -214,6 +214,108 @@ __device__ __forceinline__ int lm_parse(LmWarpSmem& S, const u32 (&wm)[4], int L
     return nmatch;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Diagonal-hypothesis parse (the common near-identical segment: a few substitutions, Lr == Lt).
+//
+// If every k-mer the greedy parse looks up has no occurrence in r other than the one on diagonal 0 (p == j), the parse is
+// fully determined by the positions where r and t differ: a window t[j..j+k) without a mismatch matches at p = j and
+// extends to the next mismatch (single candidate: no tie, `pn == 0` cannot be displaced, :114-130); a window that
+// contains a mismatch has no candidate and yields a literal (:77-81).  So the warp
+//   1. lists the mismatching symbols from the diagonal bitmap (<= DV_MAX_MIS, else the generic path runs),
+//   2. simulates that parse, collecting the <= 32 windows it looks up (one per lane),
+//   3. PROVES the hypothesis: the looked-up k-mers go into a small hash table and all k-mers of r are streamed past it
+//      (rolling hash, no insertion, no chains); any hit other than a clean window's own diagonal position -- a repeat in
+//      r, an off-diagonal occurrence of a mutated k-mer, or a mere 32-bit hash collision -- rejects the hypothesis.
+// Rejection falls back to the exact generic path (index + parse), so the result is always the reference's; acceptance
+// costs about half of the generic path because nothing is inserted and no candidate list is walked.
+// ------------------------------------------------------------------------------------------------
+static const int DV_MAX_MISWORDS = 12;
+static const int DV_MAX_MIS = 24;
+static const int DV_QPOS = 512;               // S.next[DV_QPOS + slot]: own position + 1 of a clean window, 0 for a mutated one
+
+// returns the number of matches (stored in S.mlist), or 0 when the hypothesis was rejected / not applicable.
+// head_clean (in/out): S.head is all zero.
+__device__ __forceinline__ int lm_diag_parse(LmWarpSmem& S, const u32 (&wm)[4], int L, int k, bool& head_clean) {
+    const int lane = lane_of();
+    if (__popc(wm[0]) + __popc(wm[1]) + __popc(wm[2]) + __popc(wm[3]) > DV_MAX_MISWORDS) return 0;
+    // ---- 1. mismatching symbols, ascending (uniform; lane 0 stores)
+    const u64* r64 = reinterpret_cast<const u64*>(S.r);
+    const u64* t64 = reinterpret_cast<const u64*>(S.t);
+    u16* M = S.next;
+    int c = 0;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        for (u32 m = wm[it]; m; m &= m - 1) {
+            const int q = 32 * it + __ffs((int)m) - 1;
+            u32 bm = movemask8(nonzero_flags8(r64[q] ^ t64[q]));
+            if (8 * q + 8 > L) bm &= (1u << (L - 8 * q)) - 1u;
+            for (; bm; bm &= bm - 1) {
+                if (c < DV_MAX_MIS && lane == 0) M[c] = (u16)(8 * q + __ffs((int)bm) - 1);
+                ++c;
+            }
+        }
+    }
+    if (c > DV_MAX_MIS) return 0;
+    if (lane == 0) M[c] = (u16)L;                                  // sentinel
+    __syncwarp();
+    // ---- 2. the parse under the hypothesis; lane v keeps the v-th looked-up window
+    int j = 0, i = 0, nq = 0, nmatch = 0, myj = 0;
+    bool myclean = false;
+    while (j <= L - k) {
+        const int next = (int)M[i];                                 // first mismatch at or after j
+        const bool clean = next - j >= k;
+        if (nq >= 32) return 0;
+        if (lane == nq) { myj = j; myclean = clean; }
+        ++nq;
+        if (clean) {
+            if (lane == 0) S.mlist[nmatch] = (u32)j | ((u32)j << 10) | ((u32)(next - j) << 20);
+            ++nmatch;
+            j = next;
+        } else {
+            ++j;
+            if (next < j) ++i;
+        }
+    }
+    if (nmatch == 0) return 0;
+    // ---- 3. proof: no other occurrence of any looked-up k-mer in r
+    if (!head_clean) {
+        for (int x = lane; x < LM_HT; x += 32) S.head[x] = 0u;
+        head_clean = true;
+        __syncwarp();
+    }
+    const u32 mul = 1u << lm_hash_shift(k);
+    u32 H = 0u;
+    if (lane < nq) for (int x = 0; x < k; ++x) H = H * mul + S.t[myj + x];
+    const u32 slot = lm_bucket(lm_mix(H));
+    const u16 tagpos = myclean ? (u16)(myj + 1) : (u16)0;
+    const u32 valid = nq >= 32 ? 0xffffffffu : ((1u << nq) - 1u);
+    const u32 peers = __match_any_sync(SCCG_FULL_MASK, lane < nq ? H : 0xffffffffu - (u32)lane);
+    if (lane < nq) { S.head[slot] = H; M[DV_QPOS + slot] = tagpos; }
+    __syncwarp();
+    bool bad = lane < nq && (H == 0u || (peers & valid) != (1u << lane) || S.head[slot] != H || M[DV_QPOS + slot] != tagpos);
+    if (!__any_sync(SCCG_FULL_MASK, bad)) {
+        const int nk = L - k + 1;
+        const int chunk = (nk + 31) >> 5;
+        int p = lane * chunk;
+        const int p1 = p + chunk < nk ? p + chunk : nk;
+        if (p < p1) {
+            u32 h = 0u;
+            for (int x = 0; x < k - 1; ++x) h = h * mul + S.r[p + x];
+            const u8* in = S.r + (k - 1);
+#pragma unroll 4
+            for (; p < p1; ++p) {
+                h = h * mul + in[p];
+                const u32 sl = lm_bucket(lm_mix(h));
+                if (S.head[sl] == h && M[DV_QPOS + sl] != (u16)(p + 1)) bad = true;
+            }
+        }
+    }
+    __syncwarp();
+    if (lane < nq) S.head[slot] = 0u;                               // leave the table clean for the next segment
+    __syncwarp();
+    return __any_sync(SCCG_FULL_MASK, bad) ? 0 : nmatch;
+}
+
 #ifdef SCCG_SEG_TIMING
 // development aid (tools/seg_timing.py, separate build): clock64() ticks spent per segment
 __device__ unsigned long long* g_seg_cycles = nullptr;
@@ -246,7 +348,7 @@ __device__ __forceinline__ void lm_fetch(const u8* __restrict__ ref, i64 nr, con
 #endif
 __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(const u8* __restrict__ ref, i64 nr, const u8* __restrict__ tgt, i64 nt,
                                                             int n_iter, int k1, int k2, u32* seginfo, u32* __restrict__ matches,
-                                                            u32* __restrict__ work_counter, u32* abort_flag) {
+                                                            u32* __restrict__ work_counter, u32* abort_flag, int use_diag) {
     SCCG_DYN_SMEM(smem_raw);
     LmWarpSmem& S = reinterpret_cast<LmWarpSmem*>(smem_raw)[threadIdx.x >> 5];
     const int lane = lane_of();
@@ -267,6 +369,7 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
     u64 nrw[4], ntw[4];
     const int claim_base = warps_total * SCCG_LM_CLAIM;       // the first warps_total * CLAIM segments are pre-assigned
     int claimed_used = 0;
+    bool head_clean = false;                                  // S.head all zero (kept by the diagonal-hypothesis path)
     int seg = warp_global * SCCG_LM_CLAIM < n_iter ? warp_global * SCCG_LM_CLAIM : n_iter;
     lm_fetch(ref, nr, tgt, nt, seg, n_iter, lane, nrw, ntw);
     while (seg < n_iter) {
@@ -319,7 +422,10 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
             // t_i == r_i: candidate p = 0 extends to Lt; any other p gives l <= Lr - p < Lt -> untied
             if (lane == 0) S.mlist[0] = 0u | (0u << 10) | ((u32)Lt << 20);
             nmatch = 1;
+        } else if (use_diag && Lr == Lt && Lt >= k1 && (nmatch = lm_diag_parse(S, wm, Lt, k1, head_clean)) > 0) {
+            // near-identical segment: parse determined by the mismatch positions, hypothesis proven against all of r
         } else {
+            head_clean = false;
             lm_build_index(S, Lr, k1);
             nmatch = lm_parse(S, wm, Lr, Lt, k1, pow1);                              // compression.cpp:401
             if (nmatch == 0 && k2 > 0) {

@@ -21,23 +21,28 @@ template <int MODE> __device__ __forceinline__ u32 rle_pred8(u64 w) {
 }
 
 // start / end masks of the 64 positions [i, i+64) owned by this thread (bit b <=> position i + b)
-// *paren (optional): non-zero iff one of the owned positions holds '(' (a literal '(' changes what the reference's text-level
-// delta_encode does, compression.cpp:262-292; the compressor then takes its text-level delta pass)
+// *paren (optional): non-zero iff one of the owned positions MAY hold '(' (a literal '(' changes what the reference's
+// text-level delta_encode does, compression.cpp:262-292; the compressor then takes its text-level delta pass, which is exact
+// whether or not a '(' is really there).  Cheap test: '(' = 0x28 has bit 6 clear, every letter has it set, so two ANDs per
+// 16 bytes rule out the whole chunk; only chunks with a non-letter byte (digits, IUPAC is fine, '>' headers) are looked at.
 template <int MODE> __device__ __forceinline__ void rle_masks(const u8* __restrict__ src, i64 n, i64 i, u64* starts, u64* ends, u64* paren = nullptr) {
     *starts = 0; *ends = 0;
     if (paren) *paren = 0;
     if (i >= n) return;
-    u64 m = 0, pm = 0;
+    u64 m = 0, pm = 0, all6 = ~0ull;
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
         if (i + 16 * v < n) {
             ulonglong2 w = *reinterpret_cast<const ulonglong2*>(src + i + 16 * v);   // buffers carry >= 64 B of slack
             m |= (u64)(rle_pred8<MODE>(w.x) | (rle_pred8<MODE>(w.y) << 8)) << (16 * v);
-            if (paren) pm |= (u64)(movemask8(eq_flags8(w.x, '(')) | (movemask8(eq_flags8(w.y, '(')) << 8)) << (16 * v);
+            if (paren) all6 &= w.x & w.y;
         }
     }
     i64 left = n - i;
-    if (left < 64) { m &= (1ull << (int)left) - 1ull; pm &= (1ull << (int)left) - 1ull; }
+    if (left < 64) m &= (1ull << (int)left) - 1ull;
+    if (paren && (all6 & 0x4040404040404040ULL) != 0x4040404040404040ULL) {
+        for (int b = 0; b < 64 && b < left; ++b) pm |= (u64)(src[i + b] == '(') << b;       // rare: exact look at this chunk
+    }
     if (paren) *paren = pm;
     u64 prev = (i > 0) ? (u64)rle_pred1<MODE>(src[i - 1]) : 0ull;
     u64 next = (i + 64 < n) ? (u64)rle_pred1<MODE>(src[i + 64]) : 0ull;

@@ -153,6 +153,50 @@ def test_text_level_delta_long_literal_runs(ctx):
     assert check_compress_like_oracle(ctx, ref, tgt) in ("ok", "stoi")
 
 
+def diag_fuzz_pair(r):
+    """near-identical segments (the diagonal-hypothesis path of seg_match_k) with planted traps: repeats inside the
+    reference segment, mutated windows that occur elsewhere, SNPs next to segment borders, clustered SNPs"""
+    alphabet = r.choice([b"ACGT", b"ACGT", b"AC", b"ACG", b"ACGTN"])
+    n = r.choice([1000, 2000, 3000, 2500, 1014, 1999, 14, 15, 40])
+    ref = bytearray(r.choice(alphabet) for _ in range(n))
+    for _ in range(r.randint(0, 3)):                                   # self-repeats of 14..60 symbols inside one segment
+        if n < 200:
+            break
+        seg = r.randrange(0, (n + 999) // 1000) * 1000
+        hi = min(n, seg + 1000)
+        ln = r.randint(14, 60)
+        if hi - seg < 2 * ln + 2:
+            continue
+        a = r.randrange(seg, hi - ln); b = r.randrange(seg, hi - ln)
+        ref[b:b + ln] = ref[a:a + ln]
+    tgt = bytearray(ref)
+    for _ in range(r.choice([0, 1, 1, 2, 3, 5, 12, 30])):              # substitutions, some clustered, some at borders
+        p = r.choice([r.randrange(n), r.randrange(n), min(n - 1, r.choice([0, 1, 13, 14, 985, 986, 987, 999, 1000, 1001, 1013]))])
+        tgt[p] = r.choice(alphabet)
+        if r.random() < 0.3 and p + 3 < n:
+            tgt[p + r.randint(1, 3)] = r.choice(alphabet)
+    if r.random() < 0.3 and n >= 200:                                  # a mutated window that occurs elsewhere in the reference segment
+        seg = r.randrange(0, (n + 999) // 1000) * 1000
+        hi = min(n, seg + 1000)
+        if hi - seg > 120:
+            a = r.randrange(seg, hi - 50); b = r.randrange(seg, hi - 50)
+            tgt[b:b + 20] = ref[a:a + 20]
+    if r.random() < 0.2:
+        tgt = tgt[:r.randrange(max(1, n - 30), n + 1)]                  # shorter last target segment (Lr != Lt)
+    return bytes(ref), bytes(tgt)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_diag_hypothesis_fuzz(ctx, seed):
+    r = random.Random(repr(("dv", seed)))
+    for it in range(60):
+        ref, tgt = diag_fuzz_pair(r)
+        rc, exp, mode = ol.orc_compress(ref, tgt, b">dv")
+        assert rc == 0
+        got, gmode = ctx.compress(ref, tgt, b">dv")
+        assert (gmode, got) == (mode, exp), (seed, it, ref, tgt)
+
+
 def test_many_segments_scan_paths(ctx):
     # > 2048 segments so that the device-wide scan takes its multi-tile path
     ref = rnd(3_000_000 // 4, "big") * 4

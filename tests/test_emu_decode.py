@@ -109,7 +109,7 @@ def test_reconstruct_errors(ctx):
     assert ctx.reconstruct(ref, b"ACGT", b"(1,2)", b"(0,3)") == b"annCGT\n"      # a lowercase run covers re-inserted N
 
 
-@pytest.mark.parametrize("shape", ["local", "gap", "divergent"])
+@pytest.mark.parametrize("shape", ["local", "gap", "divergent", "divergent_big"])
 def test_decompress_many_tiles_vs_oracle(ctx, shape):
     """multi-tile gather (search windows per CTA) on record streams produced by the oracle compressor"""
     from sccg_genome_compression_b200 import synth
@@ -117,6 +117,8 @@ def test_decompress_many_tiles_vs_oracle(ctx, shape):
         ref, tgt = synth.local_pair(300_000, synth.seed_for(2, 21))
     elif shape == "gap":
         ref, tgt = synth.global_gap_pair(200_000, 180_000, synth.seed_for(1, 21))
+    elif shape == "divergent_big":          # > 100 scan tiles: several look-back rounds of the single-pass scan
+        ref, tgt = synth.divergent_pair(600_000, synth.seed_for(3, 22))
     else:
         ref, tgt = synth.divergent_pair(150_000, synth.seed_for(3, 21))
     ref, tgt = ref.tobytes(), tgt.tobytes()

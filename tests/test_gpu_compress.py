@@ -10,7 +10,7 @@ import pytest
 
 import oracle_lib as ol
 from cases import cases
-from test_emu_compress import _mutated_pair, check_compress_like_oracle, grammar_pair
+from test_emu_compress import _mutated_pair, check_compress_like_oracle, diag_fuzz_pair, grammar_pair
 
 pytestmark = pytest.mark.gpu
 CASES = cases()
@@ -50,6 +50,18 @@ def test_compress_matches_golden(ctx, case, golden):
     got, mode = ctx.compress(case.ref, case.tgt, case.header)
     assert mode == g["mode"]
     assert got == expect, _report(case.name, got, expect)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_diag_hypothesis_fuzz(ctx, seed):
+    """the diagonal-hypothesis path of seg_match_k against planted repeats / off-diagonal occurrences (must fall back)"""
+    r = random.Random(repr(("dvgpu", seed)))
+    for it in range(60):
+        ref, tgt = diag_fuzz_pair(r)
+        rc, exp, mode = ol.orc_compress(ref, tgt, b">dv")
+        assert rc == 0
+        got, gmode = ctx.compress(ref, tgt, b">dv")
+        assert (gmode, got) == (mode, exp), _report(f"dv_{seed}_{it}", got, exp)
 
 
 @pytest.mark.parametrize("seed", range(24))
