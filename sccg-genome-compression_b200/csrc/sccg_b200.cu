@@ -283,6 +283,13 @@ int sccg_decompress_into(sccg_ctx* c, const char* ref_raw, int64_t ref_len, cons
     return decompress_host(c, ref_raw, ref_len, inter, inter_len, out, out_cap, nullptr, out_len);
 }
 
+#ifdef SCCG_SEG_STATS
+int sccg_debug_seg_stats(unsigned long long* out8, int reset) {
+    if (cudaMemcpyFromSymbol(out8, sccg::g_seg_stats, sizeof(unsigned long long) * 8) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[8] = {0}; if (cudaMemcpyToSymbol(sccg::g_seg_stats, z, sizeof z) != cudaSuccess) return -1; }
+    return 0;
+}
+#endif
 #ifdef SCCG_SEG_TIMING
 int sccg_debug_seg_timing(void* d_cycles) {
     unsigned long long* p = (unsigned long long*)d_cycles;

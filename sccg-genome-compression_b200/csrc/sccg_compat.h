@@ -25,4 +25,10 @@
 
 #include <stdint.h>
 
+#ifdef SCCG_EMU
+#define SCCG_NOINLINE __attribute__((noinline))
+#else
+#define SCCG_NOINLINE __noinline__
+#endif
+
 #define SCCG_FULL_MASK 0xffffffffu

@@ -231,7 +231,29 @@ __device__ __forceinline__ int lm_parse(LmWarpSmem& S, const u32 (&wm)[4], int L
 // ------------------------------------------------------------------------------------------------
 static const int DV_MAX_MISWORDS = 12;
 static const int DV_MAX_MIS = 24;
-static const int DV_QPOS = 512;               // S.next[DV_QPOS + slot]: own position + 1 of a clean window, 0 for a mutated one
+
+static const int DV_QPOS = 512;               // S.next[DV_QPOS + slot]: (window position + 1) | clean << 15
+// slot of the looked-up-window table: bits 9..17 of the rolling hash mix the last five symbols; slot quality only decides
+// how often two windows collide (-> generic path), never correctness
+__device__ __forceinline__ u32 dv_slot(u32 h) { return (h >> 9) & (u32)(LM_HT - 1); }
+__device__ __forceinline__ u32 mad_u32(u32 a, u32 b, u32 c) {
+#if defined(__CUDA_ARCH__)
+    u32 d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));   // one IMAD (the compiler would emit shift + add for b = 2^s)
+    return d;
+#else
+    return a * b + c;
+#endif
+}
+// r[p..p+k) == t[j..j+k)  (k <= 32, both in shared memory with >= 8 bytes of slack)
+__device__ __forceinline__ bool kmer_equal_smem(const u8* r, int p, const u8* t, int j, int k) {
+    for (int o = 0; o < k; o += 4) {
+        u32 d = ld_unaligned32(r, p + o) ^ ld_unaligned32(t, j + o);
+        if (k - o < 4) d &= (1u << (8 * (k - o))) - 1u;
+        if (d) return false;
+    }
+    return true;
+}
 
 // returns the number of matches (stored in S.mlist), or 0 when the hypothesis was rejected / not applicable.
 // head_clean (in/out): S.head is all zero.
@@ -243,12 +265,14 @@ __device__ __forceinline__ int lm_diag_parse(LmWarpSmem& S, const u32 (&wm)[4], 
     const u64* t64 = reinterpret_cast<const u64*>(S.t);
     u16* M = S.next;
     int c = 0;
-#pragma unroll
+#pragma unroll 1
     for (int it = 0; it < 4; ++it) {
+#pragma unroll 1
         for (u32 m = wm[it]; m; m &= m - 1) {
             const int q = 32 * it + __ffs((int)m) - 1;
             u32 bm = movemask8(nonzero_flags8(r64[q] ^ t64[q]));
             if (8 * q + 8 > L) bm &= (1u << (L - 8 * q)) - 1u;
+#pragma unroll 1
             for (; bm; bm &= bm - 1) {
                 if (c < DV_MAX_MIS && lane == 0) M[c] = (u16)(8 * q + __ffs((int)bm) - 1);
                 ++c;
@@ -285,28 +309,61 @@ __device__ __forceinline__ int lm_diag_parse(LmWarpSmem& S, const u32 (&wm)[4], 
     }
     const u32 mul = 1u << lm_hash_shift(k);
     u32 H = 0u;
-    if (lane < nq) for (int x = 0; x < k; ++x) H = H * mul + S.t[myj + x];
-    const u32 slot = lm_bucket(lm_mix(H));
-    const u16 tagpos = myclean ? (u16)(myj + 1) : (u16)0;
+    if (lane < nq) {
+#pragma unroll 2
+        for (int x = 0; x < k; ++x) H = mad_u32(H, mul, S.t[myj + x]);
+    }
+    const u32 slot = dv_slot(H);
+    const u16 tag = (u16)((myj + 1) | (myclean ? 0x8000 : 0));     // which window sits in the slot
     const u32 valid = nq >= 32 ? 0xffffffffu : ((1u << nq) - 1u);
     const u32 peers = __match_any_sync(SCCG_FULL_MASK, lane < nq ? H : 0xffffffffu - (u32)lane);
-    if (lane < nq) { S.head[slot] = H; M[DV_QPOS + slot] = tagpos; }
+    if (lane < nq) { S.head[slot] = H; M[DV_QPOS + slot] = tag; }
     __syncwarp();
-    bool bad = lane < nq && (H == 0u || (peers & valid) != (1u << lane) || S.head[slot] != H || M[DV_QPOS + slot] != tagpos);
+    // two windows with one hash, two hashes in one slot, or the "empty" value: not provable here
+    bool bad = lane < nq && (H == 0u || (peers & valid) != (1u << lane) || S.head[slot] != H || M[DV_QPOS + slot] != tag);
     if (!__any_sync(SCCG_FULL_MASK, bad)) {
+        // every lane streams `chunk` + 1 consecutive k-mers of r (the extra one overlaps the next lane: an odd byte stride
+        // keeps the lanes on different banks), four per step: four independent table probes, ONE branch
         const int nk = L - k + 1;
         const int chunk = (nk + 31) >> 5;
+        const int steps = (chunk + 4) >> 2;
         int p = lane * chunk;
-        const int p1 = p + chunk < nk ? p + chunk : nk;
-        if (p < p1) {
-            u32 h = 0u;
-            for (int x = 0; x < k - 1; ++x) h = h * mul + S.r[p + x];
-            const u8* in = S.r + (k - 1);
-#pragma unroll 4
-            for (; p < p1; ++p) {
-                h = h * mul + in[p];
-                const u32 sl = lm_bucket(lm_mix(h));
-                if (S.head[sl] == h && M[DV_QPOS + sl] != (u16)(p + 1)) bad = true;
+        u32 h = 0u;
+        if (p < nk) {
+#pragma unroll 1
+            for (int x = 0; x < k - 1; x += 4) {                    // hash of r[p .. p+k-1)
+                const u32 w = ld_unaligned32(S.r, p + x);
+                h = mad_u32(h, mul, w & 0xffu);
+                if (x + 1 < k - 1) h = mad_u32(h, mul, (w >> 8) & 0xffu);
+                if (x + 2 < k - 1) h = mad_u32(h, mul, (w >> 16) & 0xffu);
+                if (x + 3 < k - 1) h = mad_u32(h, mul, w >> 24);
+            }
+#pragma unroll 1
+            for (int st = 0; st < steps; ++st, p += 4) {
+                const u32 w = ld_unaligned32(S.r, p + k - 1);       // the symbols entering at p .. p+3 (zero padding past the end)
+                const u32 h0 = mad_u32(h, mul, w & 0xffu);
+                const u32 h1 = mad_u32(h0, mul, (w >> 8) & 0xffu);
+                const u32 h2 = mad_u32(h1, mul, (w >> 16) & 0xffu);
+                const u32 h3 = mad_u32(h2, mul, w >> 24);
+                const u32 e0 = S.head[dv_slot(h0)], e1 = S.head[dv_slot(h1)], e2 = S.head[dv_slot(h2)], e3 = S.head[dv_slot(h3)];
+                h = h3;
+                if ((e0 == h0) | (e1 == h1) | (e2 == h2) | (e3 == h3)) {
+                    // rare: position p + x of r has the hash of a looked-up window (the hash ignores the first
+                    // k - ceil(32/s) symbols, so a mutated window whose substitution sits there lands here once).  The
+                    // own diagonal position of a clean window is expected; anything else counts only if the k-mers are
+                    // really equal.
+                    u32 m = (e0 == h0 ? 1u : 0u) | (e1 == h1 ? 2u : 0u) | (e2 == h2 ? 4u : 0u) | (e3 == h3 ? 8u : 0u);
+#pragma unroll 1
+                    for (; m; m &= m - 1) {
+                        const int x = __ffs((int)m) - 1;
+                        const u32 hx = x == 0 ? h0 : x == 1 ? h1 : x == 2 ? h2 : h3;
+                        const int px = p + x;
+                        const u32 tg = M[DV_QPOS + dv_slot(hx)];
+                        const int qj = (int)(tg & 0x3ffu) - 1;
+                        if (px >= nk || ((tg & 0x8000u) && qj == px)) continue;
+                        if (kmer_equal_smem(S.r, px, S.t, qj, k)) bad = true;
+                    }
+                }
             }
         }
     }
@@ -319,6 +376,13 @@ __device__ __forceinline__ int lm_diag_parse(LmWarpSmem& S, const u32 (&wm)[4], 
 #ifdef SCCG_SEG_TIMING
 // development aid (tools/seg_timing.py, separate build): clock64() ticks spent per segment
 __device__ unsigned long long* g_seg_cycles = nullptr;
+#endif
+#ifdef SCCG_SEG_STATS
+// development aid (tools/seg_stats.py, separate build): how many segments took which path
+__device__ unsigned long long g_seg_stats[8];      // 0 identical, 1 diagonal accepted, 2 generic (diagonal not tried / rejected), 3 second pass
+#define SEG_STAT(i) do { if (lane == 0) atomicAdd(&g_seg_stats[i], 1ull); } while (0)
+#else
+#define SEG_STAT(i) do { } while (0)
 #endif
 
 // raw (not yet upper-cased) 8-byte words of segment `seg`: lane holds words lane, lane+32, lane+64, lane+96
@@ -381,7 +445,6 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
 #ifdef SCCG_SEG_TIMING
         const long long t_begin = clock64();
 #endif
-        int all_n = 1;
         u32 wm[4];                                           // diagonal-0 mismatch flags per 8-byte word (uniform)
         const int wv = Lmin >> 3, rem = Lmin & 7;
 #pragma unroll
@@ -394,10 +457,6 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
             u64 diff = rw ^ tw;
             bool d = q < wv ? diff != 0ull : (q == wv && rem ? (diff & (~0ull >> (64 - 8 * rem))) != 0ull : false);
             wm[it] = __ballot_sync(SCCG_FULL_MASK, d);
-            int vt = Lt - 8 * q;                             // target symbols in this word
-            u64 nx = tw ^ 0x4E4E4E4E4E4E4E4EULL;             // 'N' * 8
-            if (vt >= 8) { if (nx) all_n = 0; }
-            else if (vt > 0) { if (nx & (~0ull >> (64 - 8 * vt))) all_n = 0; }
         }
         // claim the next segment: SCCG_LM_CLAIM consecutive segments per atomic (one hot L2 address for the whole grid)
         int next_seg = seg + 1;
@@ -414,7 +473,6 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
         }
         lm_fetch(ref, nr, tgt, nt, next_seg, n_iter, lane, nrw, ntw);
         if (lane < 2) reinterpret_cast<u64*>(S.r)[128 + lane] = 0ull, reinterpret_cast<u64*>(S.t)[128 + lane] = 0ull;
-        all_n = __all_sync(SCCG_FULL_MASK, all_n);
         __syncwarp();
 
         int nmatch = 0;
@@ -422,15 +480,22 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
             // t_i == r_i: candidate p = 0 extends to Lt; any other p gives l <= Lr - p < Lt -> untied
             if (lane == 0) S.mlist[0] = 0u | (0u << 10) | ((u32)Lt << 20);
             nmatch = 1;
+            SEG_STAT(0);
         } else if (use_diag && Lr == Lt && Lt >= k1 && (nmatch = lm_diag_parse(S, wm, Lt, k1, head_clean)) > 0) {
             // near-identical segment: parse determined by the mismatch positions, hypothesis proven against all of r
+            SEG_STAT(1);
         } else {
+            SEG_STAT(2);
             head_clean = false;
-            lm_build_index(S, Lr, k1);
-            nmatch = lm_parse(S, wm, Lr, Lt, k1, pow1);                              // compression.cpp:401
-            if (nmatch == 0 && k2 > 0) {
-                lm_build_index(S, Lr, k2);
-                nmatch = lm_parse(S, wm, Lr, Lt, k2, pow2);                          // compression.cpp:428
+            // pass 1 with k (compression.cpp:401), pass 2 with k' only if pass 1 found no match (:428); one copy of the code
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const int k = pass ? k2 : k1;
+                if (k <= 0) break;
+                if (pass) SEG_STAT(3);
+                lm_build_index(S, Lr, k);
+                nmatch = lm_parse(S, wm, Lr, Lt, k, pass ? pow2 : pow1);
+                if (nmatch) break;
             }
         }
         __syncwarp();
@@ -441,6 +506,17 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
             covered += (int)(pk >> 20);
         }
         covered = __reduce_add_sync(SCCG_FULL_MASK, covered);
+        // "segment consists only of N" (:419, :455) matters only where the driver would count the segment: compute it there
+        int all_n = 0;
+        if (nmatch == 0 || 2 * (Lt - covered) > Lt) {
+            int mine = 1;
+            for (int b0 = 8 * lane; b0 < Lt; b0 += 256) {
+                const u64 nx = reinterpret_cast<const u64*>(S.t)[b0 >> 3] ^ 0x4E4E4E4E4E4E4E4EULL;     // 'N' * 8
+                const int vt = Lt - b0;
+                if (vt >= 8 ? nx != 0ull : (nx & (~0ull >> (64 - 8 * vt))) != 0ull) mine = 0;
+            }
+            all_n = __all_sync(SCCG_FULL_MASK, mine);
+        }
         if (lane == 0) {
             int lit = Lt - covered;                                              // count_mismatches :413
             u32 bad = (2 * lit > Lt) ? 1u : 0u;                                  // (float)lit / Lt > 0.5f  :417-419
