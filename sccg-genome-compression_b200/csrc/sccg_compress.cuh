@@ -46,7 +46,7 @@ static int finish_text_delta(sccg_ctx* c, u32* sc, u32 body_base, CompressResult
 }
 
 static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt, i64 nt, const char* header, i64 nh,
-                                  u32 low_k, const u32* cnt_s, const u32* cnt_e, int text_delta, CompressResult* res);
+                                  u32 low_k, const u8* d_low_text, int text_delta, CompressResult* res);
 
 static int read_scalars(sccg_ctx* c, const u32* d_scalars, u32* host, int count) {
     SCCG_CK(cudaMemcpyAsync(c->h_pinned, d_scalars, sizeof(u32) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
@@ -55,13 +55,19 @@ static int read_scalars(sccg_ctx* c, const u32* d_scalars, u32* host, int count)
     return SCCG_OK;
 }
 
+// dst[0 .. *d_len) = src[0 .. *d_len): places a text whose length only the device knows yet
+__global__ void copy_text_k(u8* __restrict__ dst, const u8* __restrict__ src, const u32* __restrict__ d_len) {
+    const u32 n = *d_len;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 static int write_header(sccg_ctx* c, u8* d_out, const char* header, i64 nh) {
     if (nh <= 0) return SCCG_OK;                                              // compression.cpp:337-339
-    if ((size_t)nh + 1 > c->h_pinned_cap) return set_error(SCCG_E_ARG, "header line too long");
-    memcpy(c->h_pinned, header, (size_t)nh);
-    ((char*)c->h_pinned)[nh] = '\n';
-    SCCG_CK(cudaMemcpyAsync(d_out, c->h_pinned, (size_t)nh + 1, cudaMemcpyHostToDevice, c->stream));
-    SCCG_CK(cudaStreamSynchronize(c->stream));                                // staging area is reused
+    if ((size_t)nh + 1 + 16384 > c->h_pinned_cap) return set_error(SCCG_E_ARG, "header line too long");
+    char* stage = (char*)c->h_pinned + 16384;                                 // own part of the staging area: no sync needed here, every call ends with one
+    memcpy(stage, header, (size_t)nh);
+    stage[nh] = '\n';
+    SCCG_CK(cudaMemcpyAsync(d_out, stage, (size_t)nh + 1, cudaMemcpyHostToDevice, c->stream));
     return SCCG_OK;
 }
 
@@ -71,9 +77,16 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
     SCCG_CK(cudaMemsetAsync(sc, 0, sizeof(u32) * S_COUNT, c->stream));
     SCCG_CK(cudaEventRecord(c->ev[0], c->stream));
 
-    // ---- lowercase runs of the raw target: count (:341-367)
+    // ---- lowercase runs of the raw target (:341-367): the whole run-list pipeline is HBM-bound and independent of the
+    //      matcher, which is ALU-bound -> it runs on the side stream underneath seg_match_k
     u32 *cnt_s = nullptr, *cnt_e = nullptr;
-    SCCG_TRY(rle_count<0>(c, d_tgt, nt, B_RUN_CNT, &cnt_s, &cnt_e, sc + S_LOW_K, sc + S_LOW_KE, sc + S_PAREN));
+    u64* low_mask = nullptr;
+    SCCG_CK(cudaEventRecord(c->ev_side[0], c->stream));
+    SCCG_CK(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+    {
+        SideLane side(c);
+        SCCG_TRY(rle_count<0>(c, d_tgt, nt, B_RUN_CNT, B_RUN_MASK, &cnt_s, &cnt_e, &low_mask, sc + S_LOW_K, sc + S_LOW_KE, sc + S_PAREN));
+    }
 
     // ---- local segment matching (:381-474)
     const i64 n_rseg = (nr + SEG - 1) / SEG, n_tseg = (nt + SEG - 1) / SEG;
@@ -100,14 +113,27 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
     }
     SCCG_TRY(scan_exclusive_u32(c, seg_bytes, seg_bytes, (i64)n_iter, sc + S_BODY_MAIN));
 
+    // side lane, while the matcher runs: run count -> runs -> "<lowercase runs>" text in a staging buffer
     u32 h[S_COUNT];
+    u8* low_text = nullptr;
+    {
+        SideLane side(c);
+        SCCG_TRY(read_scalars(c, sc, h, S_COUNT));                            // synchronises the side stream only
+        if (h[S_LOW_K] != h[S_LOW_KE]) return set_error(SCCG_E_CUDA, "internal: run start/end counts differ");
+        const u32 low_k = h[S_LOW_K];
+        int *run_s = nullptr, *run_e = nullptr;
+        SCCG_TRY(buf(c, B_RUN_TEXT, 24ull * low_k + 16, &low_text));
+        SCCG_TRY(rle_emit<0>(c, low_mask, nt, low_k, cnt_s, cnt_e, sc + S_LOW_K, B_RUN_START, B_RUN_END, B_RUN_BYTES, &run_s, &run_e, low_text, sc + S_LOW_TEXT));
+        SCCG_CK(cudaEventRecord(c->ev_side[1], c->stream));
+    }
+    const u32 low_k = h[S_LOW_K];
+    const int text_delta = h[S_PAREN] != 0;                                   // set by rle_count_k on the side lane (finished: the host waited for it)
     SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
-    if (h[S_LOW_K] != h[S_LOW_KE]) return set_error(SCCG_E_CUDA, "internal: run start/end counts differ");
     if (h[S_ABORT]) {                                                         // :462-473 -> global (:484-574)
-        return compress_global_device(c, d_ref, nr, d_tgt, nt, header, nh, h[S_LOW_K], cnt_s, cnt_e, h[S_PAREN] != 0, res);
+        SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));
+        return compress_global_device(c, d_ref, nr, d_tgt, nt, header, nh, low_k, low_text, text_delta, res);
     }
     // a '(' somewhere in the target: tokens are written with absolute p and delta_encode is replayed at text level
-    const int text_delta = h[S_PAREN] != 0;
     if (text_delta && n_iter > 0) {
         LAUNCH(c, seg_bytes_k, dim3(div_up(n_iter, 256)), dim3(256), 0, (const u32*)seginfo, (const u32*)matches, n_iter, seg_bytes, seg_prev, sc + S_ABORT, 1);
         SCCG_TRY(scan_exclusive_u32(c, seg_bytes, seg_bytes, (i64)n_iter, sc + S_BODY_MAIN));
@@ -117,14 +143,13 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
     // ---- assemble "<header>\n<lowercase runs>\n,\n<body>"
     const i64 leftover = n_tseg > n_iter ? nt - (i64)n_iter * SEG : 0;        // :476-481
     const size_t hdr_bytes = nh > 0 ? (size_t)nh + 1 : 0;
-    const size_t cap = hdr_bytes + 24ull * h[S_LOW_K] + 3 + h[S_BODY_MAIN] + (size_t)leftover;
+    const size_t cap = hdr_bytes + 24ull * low_k + 3 + h[S_BODY_MAIN] + (size_t)leftover;
     if (cap >= 0xffffffffull) return set_error(SCCG_E_ARG, "encoded output would exceed 4 GiB");
     u8* out = nullptr;
     SCCG_TRY(buf(c, B_OUT, cap + 16, &out));
     SCCG_TRY(write_header(c, out, header, nh));
-    int *run_s = nullptr, *run_e = nullptr;
-    SCCG_TRY(rle_emit<0>(c, d_tgt, nt, h[S_LOW_K], cnt_s, cnt_e, sc + S_LOW_K, B_RUN_START, B_RUN_END, B_RUN_BYTES, &run_s, &run_e,
-                         out + hdr_bytes, sc + S_LOW_TEXT));
+    SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));                // the run-list text is ready
+    if (low_k) LAUNCH(c, copy_text_k, dim3(low_k < 4096 ? 8 : 128), dim3(256), 0, out + hdr_bytes, (const u8*)low_text, (const u32*)(sc + S_LOW_TEXT));
     LAUNCH(c, put_separators_k, dim3(1), dim3(1), 0, out, (u32)hdr_bytes, sc, 0);
     if (n_iter > 0) {
         unsigned want = div_up(n_iter, 8 * 32);                              // 8 warps per CTA, 32 segments per warp

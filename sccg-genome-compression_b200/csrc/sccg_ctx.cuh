@@ -27,8 +27,8 @@ static int set_error(int code, const char* fmt, const char* a = "", const char* 
 
 // grow-only device buffer slots (one cudaMalloc per slot after warm-up)
 enum Slot {
-    B_REF = 0, B_TGT, B_OUT, B_OUT2, B_SEGINFO, B_MATCH, B_SEGBYTES, B_SEGPREV, B_SCAN0, B_SCAN1, B_SCAN2, B_SCALARS,
-    B_RUN_CNT, B_RUN_START, B_RUN_END, B_RUN_BYTES, B_RUN_TEXT, B_NRUN_CNT, B_NRUN_START, B_NRUN_END, B_NRUN_BYTES, B_NRUN_TEXT,
+    B_REF = 0, B_TGT, B_OUT, B_OUT2, B_SEGINFO, B_MATCH, B_SEGBYTES, B_SEGPREV, B_SCAN0, B_SCAN1, B_SCAN2, B_SCAN3, B_SCALARS,
+    B_RUN_CNT, B_RUN_MASK, B_NRUN_MASK, B_RUN_START, B_RUN_END, B_RUN_BYTES, B_RUN_TEXT, B_NRUN_CNT, B_NRUN_START, B_NRUN_END, B_NRUN_BYTES, B_NRUN_TEXT,
     B_ENC, B_NIDX, B_LOW, B_TOK_FLAG, B_TOK_POS, B_ITEM_OFF, B_ITEM_SRC, B_NUM0, B_NUM1, B_NUM2, B_NUM3, B_NUM4, B_NUM5,
     B_LRUN_S, B_LRUN_E, B_NRUNS_S, B_NRUNS_E, B_NRUNS_CUM, B_TILE0, B_TILE1, B_TILE2, B_TILE3,
     B_GREF, B_GTGT, B_GKEYS, B_GVALS, B_GKEYS2, B_GVALS2, B_GHIST, B_GOFFS, B_GREC, B_GLIT, B_GTMP0, B_GTMP1, B_GTMP2, B_GTMP3,
@@ -48,10 +48,15 @@ struct sccg_ctx {
     size_t h_pinned_cap;
     cudaEvent_t ev[8];
     sccg_profile prof;
-    unsigned scan_epoch;           // single-pass scan: epoch of the last launch, tiles handed out so far
-    unsigned scan_counter_base;
-    int scan_counter_ready;
+    unsigned scan_epoch[2];        // single-pass scan, per lane (0 = main stream, 1 = side stream): epoch of the last launch,
+    unsigned scan_counter_base[2]; //   tiles handed out so far
+    int scan_counter_ready[2];
+    cudaStream_t main_stream, side_stream;   // `stream` is the lane the helpers currently enqueue on (main_stream except inside SideLane)
+    cudaEvent_t ev_side[4];
     int use_diag;                  // seg_match_k: try the diagonal-hypothesis parse first (SCCG_NO_DIAG=1 disables it)
+    cudaStream_t s_h2d, s_d2h;     // copy streams of the pipelined host entry points (created on first use)
+    cudaEvent_t ev_pipe[2], ev_h2d[64], ev_g[64];
+    int pipe_ready;
 };
 
 namespace sccg {
@@ -107,6 +112,40 @@ static int download(sccg_ctx* c, const u8* d, i64 n, char** out) {
     h[n] = 0;
     *out = h;
     return SCCG_OK;
+}
+
+// Independent work (the lowercase-run pipeline of compress) is enqueued on a second stream so that it runs underneath the
+// ALU-bound segment matcher: inside a SideLane scope every helper that uses c->stream targets the side stream.
+struct SideLane {
+    sccg_ctx* c;
+    explicit SideLane(sccg_ctx* ctx) : c(ctx) { c->stream = c->side_stream; }
+    ~SideLane() { c->stream = c->main_stream; }
+};
+static inline int lane_of_stream(const sccg_ctx* c) { return c->stream == c->side_stream ? 1 : 0; }
+
+// copy streams and events of the pipelined host entry points
+static int pipe_streams(sccg_ctx* c) {
+    if (c->pipe_ready) return SCCG_OK;
+    SCCG_CK(cudaStreamCreate(&c->s_h2d));
+    SCCG_CK(cudaStreamCreate(&c->s_d2h));
+    for (int i = 0; i < 2; ++i) SCCG_CK(cudaEventCreate(&c->ev_pipe[i]));
+    for (int i = 0; i < 64; ++i) { SCCG_CK(cudaEventCreate(&c->ev_h2d[i])); SCCG_CK(cudaEventCreate(&c->ev_g[i])); }
+    c->pipe_ready = 1;
+    return SCCG_OK;
+}
+// reference chunk of the pipelined upload: <= 32 chunks, multiples of 1 MiB (SCCG_PIPE_CHUNK overrides it, tests use tiny chunks)
+static i64 pipe_chunk_bytes(i64 n) {
+    i64 ch = 16ll << 20;
+    if (const char* e = getenv("SCCG_PIPE_CHUNK")) { long long v = atoll(e); if (v >= 4096) ch = (v + 4095) & ~4095ll; }
+    while ((n + ch - 1) / ch > 32) ch *= 2;
+    return ch;
+}
+// output chunk of the pipelined download in gather tiles (4 KiB each): <= 32 chunks
+static unsigned pipe_tiles_per_chunk(unsigned ntiles) {
+    unsigned t = 4096;                                             // 16 MiB
+    if (const char* e = getenv("SCCG_PIPE_CHUNK")) { long long v = atoll(e); if (v >= 4096) t = (unsigned)((v + 4095) / 4096); }
+    while ((ntiles + t - 1) / t > 32) t *= 2;
+    return t;
 }
 
 // result delivery: either into a buffer of the caller (dst != NULL; pin it for full PCIe speed) or into a fresh malloc

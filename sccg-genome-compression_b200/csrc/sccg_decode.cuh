@@ -306,6 +306,7 @@ struct GatherArgs {
     i64 Lm;          // symbols in the N-merged sequence
     i64 total;       // bytes of wrapped text
     u8* out;
+    u32 tile0;       // first tile of this launch (the text may be produced in several launches, see decompress_host)
 };
 
 static const int GATHER_T = 256;
@@ -405,7 +406,7 @@ __device__ __forceinline__ u8 gather_byte(const GatherArgs& a, const int* win, u
 __global__ void __launch_bounds__(GATHER_T) dec_gather_k(GatherArgs a) {
     __shared__ int win[6];            // search windows of this CTA: seg lo/hi, N-run lo/hi, lowercase-run lo/hi
     const int lane = lane_of(), warp = (int)(threadIdx.x >> 5);
-    const i64 Q0 = (i64)blockIdx.x * GATHER_TILE;
+    const i64 Q0 = ((i64)blockIdx.x + a.tile0) * GATHER_TILE;
     const i64 Q1 = (Q0 + GATHER_TILE < a.total ? Q0 + GATHER_TILE : a.total) - 1;     // last byte of the tile
     if (a.Lm > 0 && warp < 6) {
         // six 32-ary searches, one per warp
@@ -487,8 +488,11 @@ __global__ void __launch_bounds__(GATHER_T) dec_gather_k(GatherArgs a) {
 
 // reconstruct_genome.  header_reserve bytes are left free in front of the text (multiple of 16) so that the caller
 // can place "<header>\n" right before it.  *d_out points at the text itself.
-static int reconstruct_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_enc, i64 ne, const u8* d_n, i64 nn, const u8* d_low, i64 nl,
-                              i64 header_reserve, u8** d_out, i64* out_len) {
+struct ReconPlan { GatherArgs a; u32* sc; int* tok_len; u32 ntok; unsigned ntiles; };
+
+// everything of reconstruct_genome that does not read the reference symbols: run lists, tokenizer, sizes, output buffer
+static int reconstruct_prepare(sccg_ctx* c, i64 nr, const u8* d_enc, i64 ne, const u8* d_n, i64 nn, const u8* d_low, i64 nl,
+                               i64 header_reserve, ReconPlan* plan) {
     u32* sc = nullptr;
     SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
     SCCG_CK(cudaMemsetAsync(sc, 0, sizeof(u32) * S_COUNT, c->stream));
@@ -547,25 +551,75 @@ static int reconstruct_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_
     if (total >= 0xffffffffLL) return set_error(SCCG_E_ARG, "decoded output would exceed 4 GiB");
     u8* out = nullptr;
     SCCG_TRY(buf(c, B_OUT, (size_t)(header_reserve + total + 32), &out));
-    GatherArgs a;
-    a.ref = d_ref; a.enc = d_enc; a.seg_dst = seg_dst; a.seg_src = seg_src; a.tok_abs = tok_abs; a.nseg = (int)nseg;
+    GatherArgs& a = plan->a;
+    a.ref = nullptr; a.enc = d_enc; a.seg_dst = seg_dst; a.seg_src = seg_src; a.tok_abs = tok_abs; a.nseg = (int)nseg;
     a.n_start = ns.start; a.n_len = ns.len; a.n_cum = ns.cum; a.n_k = (int)ns.K;
     a.l_start = lows.start; a.l_len = lows.len; a.l_k = (int)lows.K;
-    a.Ls = Ls; a.Lm = Lm; a.total = total; a.out = out + header_reserve;
-    LAUNCH(c, dec_gather_k, dim3(div_up(total, GATHER_TILE)), dim3(GATHER_T), 0, a);
+    a.Ls = Ls; a.Lm = Lm; a.total = total; a.out = out + header_reserve; a.tile0 = 0;
+    plan->sc = sc; plan->tok_len = tok_len; plan->ntok = ntok; plan->ntiles = div_up(total, GATHER_TILE);
+    return SCCG_OK;
+}
+
+// tiles [tile0, tile0 + ntiles) of the final text
+static int reconstruct_gather(sccg_ctx* c, const ReconPlan* plan, const u8* d_ref, unsigned tile0, unsigned ntiles) {
+    GatherArgs a = plan->a;
+    a.ref = d_ref; a.tile0 = tile0;
+    if (ntiles) LAUNCH(c, dec_gather_k, dim3(ntiles), dim3(GATHER_T), 0, a);
+    return SCCG_OK;
+}
+
+static int reconstruct_finish(sccg_ctx* c, const ReconPlan* plan) {
     SCCG_CK(cudaEventRecord(c->ev[2], c->stream));
-    SCCG_TRY(read_scalars(c, sc, h, D_COUNT));
+    u32 h[D_COUNT];
+    SCCG_TRY(read_scalars(c, plan->sc, h, D_COUNT));
     if (h[D_ERR] & DE_BOUNDS) return set_error(SCCG_E_BOUNDS, "ERROR: absolute_start + length exceeds reference genome size");
     if (h[D_ERR]) return set_error(SCCG_E_FORMAT, "malformed record stream or run list");
-    // the last N run must end inside the merged sequence, the reference would read out of range otherwise (:250)
-    *d_out = out + header_reserve;
-    *out_len = total;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[2]); c->prof.kernels_ms = ms;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->prof.serialize_ms = ms;
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->prof.gather_ms = ms;
     return SCCG_OK;
 }
+
+// reconstruct_genome in one go (reference already resident and prepared)
+static int reconstruct_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_enc, i64 ne, const u8* d_n, i64 nn, const u8* d_low, i64 nl,
+                              i64 header_reserve, u8** d_out, i64* out_len) {
+    ReconPlan plan;
+    SCCG_TRY(reconstruct_prepare(c, nr, d_enc, ne, d_n, nn, d_low, nl, header_reserve, &plan));
+    SCCG_TRY(reconstruct_gather(c, &plan, d_ref, 0, plan.ntiles));
+    SCCG_TRY(reconstruct_finish(c, &plan));
+    *d_out = plan.a.out;
+    *out_len = plan.a.total;
+    return SCCG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pipelined decompression: the reference streams in over PCIe in chunks while the text streams out
+// ------------------------------------------------------------------------------------------------
+// output byte (wrapped text) at which symbol s of the decoded, N-free sequence appears
+__device__ __forceinline__ i64 out_byte_of_sym(const GatherArgs& a, i64 s) {
+    i64 b = s;
+    if (a.n_k) {
+        int lo = 0, hi = a.n_k;                                   // last N run that lies before symbol s
+        while (lo < hi) { int mid = (lo + hi) >> 1; if ((i64)a.n_start[mid] - (i64)a.n_cum[mid] <= s) lo = mid + 1; else hi = mid; }
+        if (lo > 0) b = s + (i64)a.n_cum[lo - 1] + (i64)a.n_len[lo - 1];
+    }
+    return b + b / WRAP;
+}
+// need_hi[j] = one past the last reference symbol that the tokens feeding output chunk j copy from
+__global__ void dec_need_k(GatherArgs a, const int* __restrict__ tok_len, i64 chunk_bytes, u32* __restrict__ need_hi) {
+    int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (k >= a.nseg) return;
+    const i64 src = a.seg_src[k];
+    if (src & SEG_LIT_FLAG) return;
+    const i64 s0 = a.seg_dst[k], s1 = k + 1 < a.nseg ? (i64)a.seg_dst[k + 1] : a.Ls;
+    if (s1 <= s0) return;
+    const u32 hi = (u32)((i64)a.tok_abs[src] + (i64)tok_len[src]);
+    const i64 c0 = out_byte_of_sym(a, s0) / chunk_bytes, c1 = out_byte_of_sym(a, s1 - 1) / chunk_bytes;
+    for (i64 cj = c0; cj <= c1; ++cj) atomicMax(&need_hi[cj], hi);
+}
+
+static const int PIPE_MAX_CHUNKS = 64;
 
 
 // decompress_genome's in-memory part (decompression.cpp:66-110) + reconstruct_genome + main's "<header>\n" (:322)
@@ -591,35 +645,108 @@ static int decompress_host(sccg_ctx* c, const char* ref_raw, i64 ref_len, const 
     if (!next_line(&nline, &nn)) return set_error(SCCG_E_FORMAT, "Greska pri citanju indeksa nepoznatih nukleotida");
     if (!next_line(&body, &nb)) return set_error(SCCG_E_FORMAT, "Greska pri citanju kodiranog genoma");
     const bool local_mode = (nn == 1 && nline[0] == ',');                      // :105
-    // ---- uploads
+    // ---- uploads: the three text lines first (small), then the reference in chunks on its own copy stream
+    SCCG_TRY(pipe_streams(c));
     u8 *d_raw = nullptr, *d_ref = nullptr, *d_enc = nullptr, *d_n = nullptr, *d_low = nullptr;
     SCCG_CK(cudaEventRecord(c->ev[4], c->stream));
-    SCCG_TRY(upload(c, B_TGT, ref_raw, ref_len, &d_raw));
     SCCG_TRY(upload(c, B_ENC, body, nb, &d_enc));
     SCCG_TRY(upload(c, B_NIDX, nline, local_mode ? 0 : nn, &d_n));
     SCCG_TRY(upload(c, B_LOW, low, nl, &d_low));
-    SCCG_CK(cudaEventRecord(c->ev[5], c->stream));
-    // ---- reference preparation (:105-110)
-    SCCG_TRY(buf(c, B_REF, (size_t)ref_len + 64, &d_ref));
-    i64 nr = ref_len;
+    SCCG_TRY(buf(c, B_TGT, (size_t)ref_len + 128, &d_raw));
+    SCCG_TRY(buf(c, B_REF, (size_t)ref_len + 128, &d_ref));
+    const i64 rchunk = pipe_chunk_bytes(ref_len);
+    const int n_rch = ref_len > 0 ? (int)((ref_len + rchunk - 1) / rchunk) : 0;
+    if (getenv("SCCG_PIPE_POISON")) SCCG_CK(cudaMemsetAsync(d_ref, 0xEE, (size_t)ref_len, c->stream));   // tests: a chunk used before it was prepared shows up
+    SCCG_CK(cudaEventRecord(c->ev_pipe[0], c->stream));                      // buffers may have been (re)allocated: order the copy stream after it
+    SCCG_CK(cudaStreamWaitEvent(c->s_h2d, c->ev_pipe[0], 0));
+    for (int i = 0; i < n_rch; ++i) {
+        const i64 off = (i64)i * rchunk, len = (ref_len - off) < rchunk ? (ref_len - off) : rchunk;
+        SCCG_CK(cudaMemcpyAsync(d_raw + off, ref_raw + off, (size_t)len, cudaMemcpyHostToDevice, c->s_h2d));
+        SCCG_CK(cudaEventRecord(c->ev_h2d[i], c->s_h2d));
+    }
+    SCCG_CK(cudaEventRecord(c->ev[5], c->s_h2d));
     u32* sc = nullptr;
     SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
-    if (local_mode) {
-        if (ref_len > 0) LAUNCH(c, upper_k, dim3(div_up(ref_len, 256 * 16)), dim3(256), 0, (const u8*)d_raw, ref_len, d_ref);
-    } else {
+    // ---- reference preparation (:105-110): global mode erases every N (needs the whole reference), local mode only upper-cases
+    i64 nr = ref_len;
+    int prepared = 0;                                                        // reference chunks already upper-cased (local mode)
+    if (!local_mode) {
+        SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev[5], 0));
         SCCG_TRY(strip_n<0>(c, d_raw, ref_len, d_ref, B_TILE3, sc + D_STRIP, &nr));
+        prepared = n_rch;
     }
     const i64 reserve = ((nh + 1) + 15) & ~(i64)15;
-    u8* d_text = nullptr; i64 n = 0;
-    SCCG_TRY(reconstruct_device(c, d_ref, nr, d_enc, nb, d_n, local_mode ? 0 : nn, d_low, nl, reserve, &d_text, &n));
+    ReconPlan plan;
+    SCCG_TRY(reconstruct_prepare(c, nr, d_enc, nb, d_n, local_mode ? 0 : nn, d_low, nl, reserve, &plan));
+    u8* d_text = plan.a.out;
+    const i64 n = plan.a.total;
     // "<header>\n" right in front of the text (:322; an absent header still yields the "\n")
-    memcpy(c->h_pinned, header, (size_t)nh);
-    ((char*)c->h_pinned)[nh] = '\n';
-    SCCG_CK(cudaMemcpyAsync(d_text - (nh + 1), c->h_pinned, (size_t)nh + 1, cudaMemcpyHostToDevice, c->stream));
-    SCCG_CK(cudaEventRecord(c->ev[6], c->stream));
-    SCCG_TRY(deliver(c, d_text - (nh + 1), n + nh + 1, dst, dst_cap, out, out_len));
-    SCCG_CK(cudaEventRecord(c->ev[7], c->stream));
-    SCCG_CK(cudaStreamSynchronize(c->stream));
+    char* hdr_stage = (char*)c->h_pinned + 4096;                              // scalars live in the first bytes of the staging area
+    memcpy(hdr_stage, header, (size_t)nh);
+    hdr_stage[nh] = '\n';
+    SCCG_CK(cudaMemcpyAsync(d_text - (nh + 1), hdr_stage, (size_t)nh + 1, cudaMemcpyHostToDevice, c->stream));
+    // ---- result buffer
+    const i64 full = n + nh + 1;
+    *out_len = full;
+    char* h_dst = dst;
+    if (!dst) {
+        h_dst = (char*)malloc((size_t)full + 1);
+        if (!h_dst) return set_error(SCCG_E_NOMEM, "malloc of the result failed");
+        h_dst[full] = 0;
+    } else if (dst_cap < full) {
+        return set_error(SCCG_E_ARG, "output buffer too small (required size returned in *out_len)");
+    }
+    // ---- which part of the reference does every output chunk need?
+    const unsigned tiles_per_chunk = pipe_tiles_per_chunk(plan.ntiles);
+    const int n_och = (int)((plan.ntiles + tiles_per_chunk - 1) / tiles_per_chunk);
+    u32 need[PIPE_MAX_CHUNKS];
+    for (int j = 0; j < n_och; ++j) need[j] = 0xffffffffu;
+    if (local_mode && plan.a.nseg > 0 && n_och > 1) {
+        u32* d_need = sc + D_COUNT;                                          // PIPE_MAX_CHUNKS scalars after the decode scalars
+        SCCG_CK(cudaMemsetAsync(d_need, 0, sizeof(u32) * PIPE_MAX_CHUNKS, c->stream));
+        LAUNCH(c, dec_need_k, dim3(div_up(plan.a.nseg, 256)), dim3(256), 0, plan.a, (const int*)plan.tok_len, (i64)tiles_per_chunk * GATHER_TILE, d_need);
+        SCCG_CK(cudaMemcpyAsync((char*)c->h_pinned + 8192, d_need, sizeof(u32) * PIPE_MAX_CHUNKS, cudaMemcpyDeviceToHost, c->stream));
+        SCCG_CK(cudaStreamSynchronize(c->stream));
+        memcpy(need, (char*)c->h_pinned + 8192, sizeof(u32) * (size_t)n_och);
+    }
+    // ---- gather chunk by chunk; every finished chunk goes home on the D2H stream while the next ones are produced
+    int rc = SCCG_OK;
+    cudaError_t ce = cudaSuccess;
+    for (int j = 0; j < n_och && rc == SCCG_OK && ce == cudaSuccess; ++j) {
+        i64 want = need[j] == 0xffffffffu ? ref_len : (i64)need[j] + 32;     // reference symbols [0, want) must be resident
+        if (want > ref_len) want = ref_len;
+        while (prepared < n_rch && (i64)prepared * rchunk < want && rc == SCCG_OK) {
+            const i64 off = (i64)prepared * rchunk, len = (ref_len - off) < rchunk ? (ref_len - off) : rchunk;
+            ce = cudaStreamWaitEvent(c->stream, c->ev_h2d[prepared], 0);
+            if (ce != cudaSuccess) break;
+            c->prof.launches++;
+            SCCG_LAUNCH(upper_k, dim3(div_up(len, 256 * 16)), dim3(256), 0, c->stream, (const u8*)(d_raw + off), len, d_ref + off);
+            ++prepared;
+        }
+        if (ce != cudaSuccess) break;
+        const unsigned t0 = (unsigned)j * tiles_per_chunk;
+        const unsigned tn = plan.ntiles - t0 < tiles_per_chunk ? plan.ntiles - t0 : tiles_per_chunk;
+        rc = reconstruct_gather(c, &plan, d_ref, t0, tn);
+        if (rc != SCCG_OK) break;
+        if (j == 0) cudaEventRecord(c->ev[6], c->stream);
+        ce = cudaEventRecord(c->ev_g[j], c->stream);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(c->s_d2h, c->ev_g[j], 0);
+        // bytes of the device image [-(nh+1), n): chunk 0 also carries the header line
+        const i64 b0 = j == 0 ? -(nh + 1) : (i64)t0 * GATHER_TILE;
+        i64 b1 = ((i64)t0 + tn) * GATHER_TILE; if (b1 > n) b1 = n;
+        if (ce == cudaSuccess && b1 > b0) ce = cudaMemcpyAsync(h_dst + (nh + 1) + b0, d_text + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, c->s_d2h);
+    }
+    if (n_och == 0 && ce == cudaSuccess) {                                    // cannot happen (the text holds at least "\n"); kept for safety
+        ce = cudaMemcpyAsync(h_dst, d_text - (nh + 1), (size_t)full, cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (ce == cudaSuccess) ce = cudaEventRecord(c->ev[7], c->s_d2h);
+    if (rc == SCCG_OK && ce == cudaSuccess) rc = reconstruct_finish(c, &plan);       // synchronises the compute stream, reads the error flags
+    cudaError_t ce2 = cudaStreamSynchronize(c->s_d2h);
+    cudaError_t ce3 = cudaStreamSynchronize(c->s_h2d);
+    if (rc == SCCG_OK && (ce != cudaSuccess || ce2 != cudaSuccess || ce3 != cudaSuccess))
+        rc = set_error(SCCG_E_CUDA, "pipelined decompression failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : (ce2 != cudaSuccess ? ce2 : ce3)));
+    if (rc != SCCG_OK) { if (!dst) free(h_dst); return rc; }
+    if (!dst) *out = h_dst;
     cudaEventElapsedTime(&c->prof.h2d_ms, c->ev[4], c->ev[5]);
     cudaEventElapsedTime(&c->prof.d2h_ms, c->ev[6], c->ev[7]);
     return SCCG_OK;

@@ -633,12 +633,13 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
 }
 
 static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt, i64 nt, const char* header, i64 nh,
-                                  u32 low_k, const u32* cnt_s, const u32* cnt_e, int text_delta, CompressResult* res) {
+                                  u32 low_k, const u8* d_low_text, int text_delta, CompressResult* res) {
     u32* sc = nullptr;
     SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
     // ---- N runs of the upper-cased target, original coordinates (:527-554): count
     u32 *ncnt_s = nullptr, *ncnt_e = nullptr;
-    SCCG_TRY(rle_count<1>(c, d_tgt, nt, B_NRUN_CNT, &ncnt_s, &ncnt_e, sc + S_N_K, sc + S_N_KE));
+    u64* n_mask = nullptr;
+    SCCG_TRY(rle_count<1>(c, d_tgt, nt, B_NRUN_CNT, B_NRUN_MASK, &ncnt_s, &ncnt_e, &n_mask, sc + S_N_K, sc + S_N_KE));
     // ---- toupper + erase every 'N' from both sequences (:523-524, :556-557)
     u8 *R2 = nullptr, *T2 = nullptr;
     SCCG_TRY(buf(c, B_GREF, (size_t)nr + 64, &R2));
@@ -681,13 +682,13 @@ static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8
     u8* out = nullptr;
     SCCG_TRY(buf(c, B_OUT, cap + 16, &out));
     SCCG_TRY(write_header(c, out, header, nh));
-    int *run_s = nullptr, *run_e = nullptr, *nrun_s = nullptr, *nrun_e = nullptr;
-    SCCG_TRY(rle_emit<0>(c, d_tgt, nt, low_k, cnt_s, cnt_e, sc + S_LOW_K, B_RUN_START, B_RUN_END, B_RUN_BYTES, &run_s, &run_e,
-                         out + hdr_bytes, sc + S_LOW_TEXT));
+    int *nrun_s = nullptr, *nrun_e = nullptr;
+    // the lowercase-run text was produced on the side lane of compress_device (sc[S_LOW_TEXT] holds its length)
+    if (low_k) LAUNCH(c, copy_text_k, dim3(low_k < 4096 ? 8 : 128), dim3(256), 0, out + hdr_bytes, d_low_text, (const u32*)(sc + S_LOW_TEXT));
     // the N-run text goes right after "<low>\n": its position depends on the (device-side) length of the lowercase text
     u8* ntext = nullptr;
     SCCG_TRY(buf(c, B_NRUN_TEXT, 24ull * n_k + 16, &ntext));
-    SCCG_TRY(rle_emit<1>(c, d_tgt, nt, n_k, ncnt_s, ncnt_e, sc + S_N_K, B_NRUN_START, B_NRUN_END, B_NRUN_BYTES, &nrun_s, &nrun_e,
+    SCCG_TRY(rle_emit<1>(c, n_mask, nt, n_k, ncnt_s, ncnt_e, sc + S_N_K, B_NRUN_START, B_NRUN_END, B_NRUN_BYTES, &nrun_s, &nrun_e,
                          ntext, sc + S_N_TEXT));
     LAUNCH(c, put_separators_k, dim3(1), dim3(1), 0, out, (u32)hdr_bytes, sc, 1);
     SCCG_TRY(read_scalars(c, sc, h, S_COUNT));

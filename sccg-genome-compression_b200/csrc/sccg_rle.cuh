@@ -25,8 +25,8 @@ template <int MODE> __device__ __forceinline__ u32 rle_pred8(u64 w) {
 // text-level delta_encode does, compression.cpp:262-292; the compressor then takes its text-level delta pass, which is exact
 // whether or not a '(' is really there).  Cheap test: '(' = 0x28 has bit 6 clear, every letter has it set, so two ANDs per
 // 16 bytes rule out the whole chunk; only chunks with a non-letter byte (digits, IUPAC is fine, '>' headers) are looked at.
-template <int MODE> __device__ __forceinline__ void rle_masks(const u8* __restrict__ src, i64 n, i64 i, u64* starts, u64* ends, u64* paren = nullptr) {
-    *starts = 0; *ends = 0;
+template <int MODE> __device__ __forceinline__ void rle_masks(const u8* __restrict__ src, i64 n, i64 i, u64* starts, u64* ends, u64* pred, u64* paren = nullptr) {
+    *starts = 0; *ends = 0; *pred = 0;
     if (paren) *paren = 0;
     if (i >= n) return;
     u64 m = 0, pm = 0, all6 = ~0ull;
@@ -44,6 +44,7 @@ template <int MODE> __device__ __forceinline__ void rle_masks(const u8* __restri
         for (int b = 0; b < 64 && b < left; ++b) pm |= (u64)(src[i + b] == '(') << b;       // rare: exact look at this chunk
     }
     if (paren) *paren = pm;
+    *pred = m;
     u64 prev = (i > 0) ? (u64)rle_pred1<MODE>(src[i - 1]) : 0ull;
     u64 next = (i + 64 < n) ? (u64)rle_pred1<MODE>(src[i + 64]) : 0ull;
     *starts = m & ~((m << 1) | prev);
@@ -51,31 +52,40 @@ template <int MODE> __device__ __forceinline__ void rle_masks(const u8* __restri
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(RLE_T) rle_count_k(const u8* __restrict__ src, i64 n, u32* __restrict__ cnt_s, u32* __restrict__ cnt_e, u32* paren_flag) {
+__global__ void __launch_bounds__(RLE_T) rle_count_k(const u8* __restrict__ src, i64 n, u32* __restrict__ cnt_s, u32* __restrict__ cnt_e, u64* __restrict__ pred_mask,
+                                                     u32* paren_flag) {
     __shared__ u32 sm[40];
     i64 i = (i64)blockIdx.x * RLE_TILE + (i64)threadIdx.x * RLE_PER_THREAD;
-    u64 s, e;
+    u64 s, e, m;
     if (MODE == 0 && paren_flag) {
         u64 pm;
-        rle_masks<MODE>(src, n, i, &s, &e, &pm);
+        rle_masks<MODE>(src, n, i, &s, &e, &m, &pm);
         if (pm) atomicOr(paren_flag, 1u);
     } else {
-        rle_masks<MODE>(src, n, i, &s, &e);
+        rle_masks<MODE>(src, n, i, &s, &e, &m);
     }
+    if (i < n) pred_mask[i >> 6] = m;                               // 1 bit per symbol: the write pass never reads the symbols again
     u32 packed = (u32)__popcll(s) | ((u32)__popcll(e) << 16);         // <= 8192 each per tile: no overflow
     u32 tot;
     block_scan_excl(packed, sm, &tot);
     if (threadIdx.x == 0) { cnt_s[blockIdx.x] = tot & 0xffffu; cnt_e[blockIdx.x] = tot >> 16; }
 }
 
-// run k: [run_start[k], run_end[k]) ; the k-th start pairs with the k-th end
-template <int MODE>
-__global__ void __launch_bounds__(RLE_T) rle_write_k(const u8* __restrict__ src, i64 n, const u32* __restrict__ off_s, const u32* __restrict__ off_e,
+// run k: [run_start[k], run_end[k]) ; the k-th start pairs with the k-th end.  Works on the predicate bit masks left by
+// rle_count_k (n / 8 bytes instead of n).
+__global__ void __launch_bounds__(RLE_T) rle_write_k(const u64* __restrict__ pred_mask, i64 n, const u32* __restrict__ off_s, const u32* __restrict__ off_e,
                                                      int* __restrict__ run_start, int* __restrict__ run_end) {
     __shared__ u32 sm[40];
-    i64 i = (i64)blockIdx.x * RLE_TILE + (i64)threadIdx.x * RLE_PER_THREAD;
-    u64 s, e;
-    rle_masks<MODE>(src, n, i, &s, &e);
+    const i64 t = (i64)blockIdx.x * RLE_T + threadIdx.x;
+    const i64 i = t * RLE_PER_THREAD;
+    u64 s = 0, e = 0;
+    if (i < n) {
+        const u64 m = pred_mask[t];
+        const u64 prev = t > 0 ? pred_mask[t - 1] >> 63 : 0ull;
+        const u64 next = i + 64 < n ? pred_mask[t + 1] & 1ull : 0ull;
+        s = m & ~((m << 1) | prev);
+        e = m & ~((m >> 1) | (next << 63));
+    }
     u32 packed = (u32)__popcll(s) | ((u32)__popcll(e) << 16);
     u32 tot;
     u32 excl = block_scan_excl(packed, sm, &tot);
@@ -123,12 +133,14 @@ __global__ void runs_write_k(const int* __restrict__ run_start, const int* __res
 
 // Phase 1: count runs.  Leaves the per-tile exclusive offsets in cnt_s / cnt_e and the run count in d_count.
 template <int MODE>
-static int rle_count(sccg_ctx* c, const u8* d_src, i64 n, int slot_cnt, u32** cnt_s, u32** cnt_e, u32* d_count, u32* d_count_e, u32* d_paren_flag = nullptr) {
+static int rle_count(sccg_ctx* c, const u8* d_src, i64 n, int slot_cnt, int slot_mask, u32** cnt_s, u32** cnt_e, u64** pred_mask, u32* d_count, u32* d_count_e,
+                     u32* d_paren_flag = nullptr) {
     unsigned ntiles = div_up(n > 0 ? n : 1, RLE_TILE);
     u32* cnt = nullptr;
     SCCG_TRY(buf(c, slot_cnt, (size_t)ntiles * 2, &cnt));
+    SCCG_TRY(buf(c, slot_mask, (size_t)ntiles * RLE_T + 2, pred_mask));
     *cnt_s = cnt; *cnt_e = cnt + ntiles;
-    LAUNCH(c, rle_count_k<MODE>, dim3(ntiles), dim3(RLE_T), 0, d_src, n, *cnt_s, *cnt_e, d_paren_flag);
+    LAUNCH(c, rle_count_k<MODE>, dim3(ntiles), dim3(RLE_T), 0, d_src, n, *cnt_s, *cnt_e, *pred_mask, d_paren_flag);
     SCCG_TRY(scan_exclusive_u32(c, *cnt_s, *cnt_s, (i64)ntiles, d_count));
     SCCG_TRY(scan_exclusive_u32(c, *cnt_e, *cnt_e, (i64)ntiles, d_count_e));
     return SCCG_OK;
@@ -137,7 +149,7 @@ static int rle_count(sccg_ctx* c, const u8* d_src, i64 n, int slot_cnt, u32** cn
 // Phase 2 (K known on the host): materialise the runs and their text.  d_text_len receives the text length;
 // the text is written at dst (capacity >= 24 * K).
 template <int MODE>
-static int rle_emit(sccg_ctx* c, const u8* d_src, i64 n, u32 K, const u32* cnt_s, const u32* cnt_e, const u32* d_count,
+static int rle_emit(sccg_ctx* c, const u64* pred_mask, i64 n, u32 K, const u32* cnt_s, const u32* cnt_e, const u32* d_count,
                     int slot_start, int slot_end, int slot_bytes, int** run_start, int** run_end, u8* dst, u32* d_text_len) {
     unsigned ntiles = div_up(n > 0 ? n : 1, RLE_TILE);
     SCCG_TRY(buf(c, slot_start, (size_t)K + 1, run_start));
@@ -145,7 +157,7 @@ static int rle_emit(sccg_ctx* c, const u8* d_src, i64 n, u32 K, const u32* cnt_s
     u32* bytes = nullptr;
     SCCG_TRY(buf(c, slot_bytes, (size_t)K + 1, &bytes));
     if (K == 0) { LAUNCH(c, scan_zero_total_k, dim3(1), dim3(1), 0, d_text_len); return SCCG_OK; }
-    LAUNCH(c, rle_write_k<MODE>, dim3(ntiles), dim3(RLE_T), 0, d_src, n, cnt_s, cnt_e, *run_start, *run_end);
+    LAUNCH(c, rle_write_k, dim3(ntiles), dim3(RLE_T), 0, pred_mask, n, cnt_s, cnt_e, *run_start, *run_end);
     unsigned g = div_up(K, 256);
     LAUNCH(c, runs_bytes_k, dim3(g), dim3(256), 0, (const int*)*run_start, (const int*)*run_end, d_count, n, bytes);
     SCCG_TRY(scan_exclusive_u32(c, bytes, bytes, (i64)K, d_text_len));

@@ -93,26 +93,29 @@ static int scan_exclusive_u32(sccg_ctx* c, const u32* in, u32* out, i64 n, u32* 
         return SCCG_OK;
     }
     const unsigned ntiles = div_up(n, SCAN_TILE);
-    // descriptor array + counter: zeroed when (re)allocated, then only ever advanced (epoch / counter base)
-    const size_t before = c->bufs[B_SCAN0].cap;
+    // descriptor array + counter (one set per lane: scans on the main and on the side stream may run concurrently):
+    // zeroed when (re)allocated, then only ever advanced (epoch / counter base)
+    const int ln = lane_of_stream(c);
+    const int slot_desc = ln ? B_SCAN2 : B_SCAN0, slot_cnt = ln ? B_SCAN3 : B_SCAN1;
+    const size_t before = c->bufs[slot_desc].cap;
     u64* desc = nullptr;
-    SCCG_TRY(buf(c, B_SCAN0, (size_t)ntiles + 2, &desc));
-    if (c->bufs[B_SCAN0].cap != before) {
-        SCCG_CK(cudaMemsetAsync(desc, 0, c->bufs[B_SCAN0].cap, c->stream));
-        c->scan_epoch = 0;
+    SCCG_TRY(buf(c, slot_desc, (size_t)ntiles + 2, &desc));
+    if (c->bufs[slot_desc].cap != before) {
+        SCCG_CK(cudaMemsetAsync(desc, 0, c->bufs[slot_desc].cap, c->stream));
+        c->scan_epoch[ln] = 0;
     }
     u32* counter = nullptr;
-    SCCG_TRY(buf(c, B_SCAN1, 64, &counter));
-    if (!c->scan_counter_ready) {
+    SCCG_TRY(buf(c, slot_cnt, 64, &counter));
+    if (!c->scan_counter_ready[ln]) {
         SCCG_CK(cudaMemsetAsync(counter, 0, 256, c->stream));
-        c->scan_counter_ready = 1; c->scan_counter_base = 0;
+        c->scan_counter_ready[ln] = 1; c->scan_counter_base[ln] = 0;
     }
-    if (++c->scan_epoch >= 0x7fffffffu) {                        // epoch space exhausted: start over with clean descriptors
-        SCCG_CK(cudaMemsetAsync(desc, 0, c->bufs[B_SCAN0].cap, c->stream));
-        c->scan_epoch = 1;
+    if (++c->scan_epoch[ln] >= 0x7fffffffu) {                    // epoch space exhausted: start over with clean descriptors
+        SCCG_CK(cudaMemsetAsync(desc, 0, c->bufs[slot_desc].cap, c->stream));
+        c->scan_epoch[ln] = 1;
     }
-    LAUNCH(c, scan_onepass_k, dim3(ntiles), dim3(SCAN_T), 0, in, out, n, desc, counter, c->scan_counter_base, c->scan_epoch, d_total);
-    c->scan_counter_base += ntiles;                              // modulo 2^32, like the device counter
+    LAUNCH(c, scan_onepass_k, dim3(ntiles), dim3(SCAN_T), 0, in, out, n, desc, counter, c->scan_counter_base[ln], c->scan_epoch[ln], d_total);
+    c->scan_counter_base[ln] += ntiles;                          // modulo 2^32, like the device counter
     return SCCG_OK;
 }
 

@@ -224,6 +224,7 @@ cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { if (n) mem
 cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = new emu_stream_t(); return 0; }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return 0; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
 cudaError_t cudaDeviceSynchronize() { return 0; }
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emu_event_t(); return 0; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }

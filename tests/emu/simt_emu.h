@@ -257,6 +257,7 @@ cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st = nullptr)
 cudaError_t cudaStreamCreate(cudaStream_t* s);
 cudaError_t cudaStreamDestroy(cudaStream_t s);
 cudaError_t cudaStreamSynchronize(cudaStream_t s);
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned flags);
 cudaError_t cudaDeviceSynchronize();
 cudaError_t cudaEventCreate(cudaEvent_t* e);
 cudaError_t cudaEventDestroy(cudaEvent_t e);

@@ -128,3 +128,30 @@ def test_decompress_many_tiles_vs_oracle(ctx, shape):
     rc, exp = ol.orc_decompress(ref, inter)
     assert rc == 0
     assert ctx.decompress(ref, inter) == exp
+
+
+@pytest.mark.parametrize("chunk", [4096, 20000, 1 << 20])
+def test_decompress_pipelined_small_chunks(ctx, chunk, monkeypatch):
+    """the pipelined host path (reference uploaded / upper-cased chunk by chunk, text gathered and sent home chunk by
+    chunk): every output chunk may only touch reference chunks that were prepared for it (poisoned otherwise)"""
+    from sccg_genome_compression_b200 import synth
+    monkeypatch.setenv("SCCG_PIPE_CHUNK", str(chunk))
+    monkeypatch.setenv("SCCG_PIPE_POISON", "1")
+    for shape in ("local", "gap"):
+        if shape == "local":
+            ref, tgt = synth.local_pair(260_000, synth.seed_for(2, 31))
+            ref, tgt = ref.tobytes(), tgt.tobytes()
+            tgt = tgt[:100_000] + tgt[100_000:100_900][::-1] + tgt[100_900:]          # a segment that falls back to literals
+        else:
+            ref, tgt = synth.global_gap_pair(150_000, 140_000, synth.seed_for(1, 31))
+            ref, tgt = ref.tobytes(), tgt.tobytes()
+        rc, inter, mode = ol.orc_compress(ref, tgt, b">pipelined")
+        assert rc == 0
+        rc, exp = ol.orc_decompress(ref, inter)
+        assert rc == 0
+        assert ctx.decompress(ref, inter) == exp
+    # tokens that point far ahead / far back in the reference (hand-built stream, local-mode N line)
+    ref = rnd(120_000, "pipe")
+    inter = b">x\n\n,\n(110000,5000)(-110000,30000)ACGT(60000,100)(-50000,20000)"
+    rc, exp = ol.orc_decompress(ref, inter)
+    assert rc == 0 and ctx.decompress(ref, inter) == exp

@@ -83,3 +83,26 @@ def test_roundtrip_local_synthetic(ctx, n):
     if n <= 5_000_000:
         rc, orc = ol.orc_decompress(ref, inter)
         assert rc == 0 and orc == back
+
+
+@pytest.mark.parametrize("chunk", [4096, 65536, 1 << 20])
+def test_decompress_pipelined_small_chunks(ctx, chunk, monkeypatch):
+    """pipelined host path on the GPU: many small reference / output chunks, un-prepared reference chunks are poisoned"""
+    from sccg_genome_compression_b200 import synth
+    monkeypatch.setenv("SCCG_PIPE_CHUNK", str(chunk))
+    monkeypatch.setenv("SCCG_PIPE_POISON", "1")
+    for shape in ("local", "gap"):
+        if shape == "local":
+            ref, tgt = synth.local_pair(3_000_000, synth.seed_for(2, 31))
+        else:
+            ref, tgt = synth.global_gap_pair(1_500_000, 1_400_000, synth.seed_for(1, 31))
+        ref, tgt = ref.tobytes(), tgt.tobytes()
+        rc, inter, mode = ol.orc_compress(ref, tgt, b">pipelined")
+        assert rc == 0
+        rc, exp = ol.orc_decompress(ref, inter)
+        assert rc == 0
+        assert ctx.decompress(ref, inter) == exp
+    ref = rnd(120_000, "pipe")
+    inter = b">x\n\n,\n(110000,5000)(-110000,30000)ACGT(60000,100)(-50000,20000)"
+    rc, exp = ol.orc_decompress(ref, inter)
+    assert rc == 0 and ctx.decompress(ref, inter) == exp
