@@ -118,7 +118,7 @@ int sccg_compress_device(sccg_ctx* c, const void* d_ref, int64_t ref_len, const 
     SCCG_CK(cudaSetDevice(c->device));
     prof_reset(c);
     CompressResult res;
-    SCCG_TRY(compress_device(c, (const u8*)d_ref, ref_len, (const u8*)d_tgt, tgt_len, header, header_len < 0 ? 0 : header_len, &res));
+    SCCG_TRY(compress_device(c, (const u8*)d_ref, ref_len, (const u8*)d_tgt, tgt_len, header, header_len < 0 ? 0 : header_len, &res, nullptr));
     *d_out = res.d_out; *out_len = res.out_len;
     if (mode_out) *mode_out = res.mode;
     return res.stoi_failed ? stoi_failure() : SCCG_OK;
@@ -131,13 +131,30 @@ static int compress_host(sccg_ctx* c, const char* ref, int64_t ref_len, const ch
     SCCG_TRY(check_header(header, header_len));
     SCCG_CK(cudaSetDevice(c->device));
     prof_reset(c);
+    // the target goes up first (the run-list pipeline only needs it), then the reference in chunks: the matcher starts on
+    // every chunk as it lands, so the kernels hide under the PCIe transfer
     u8 *d_ref = nullptr, *d_tgt = nullptr;
+    SCCG_TRY(pipe_streams(c));
+    SCCG_TRY(buf(c, B_REF, (size_t)ref_len + 128, &d_ref));
+    SCCG_TRY(buf(c, B_TGT, (size_t)tgt_len + 128, &d_tgt));
     SCCG_CK(cudaEventRecord(c->ev[4], c->stream));
-    SCCG_TRY(upload(c, B_REF, ref, ref_len, &d_ref));
-    SCCG_TRY(upload(c, B_TGT, tgt, tgt_len, &d_tgt));
-    SCCG_CK(cudaEventRecord(c->ev[5], c->stream));
+    SCCG_CK(cudaStreamWaitEvent(c->s_h2d, c->ev[4], 0));
+    ChunkArrival arr;
+    arr.chunk = pipe_chunk_bytes(ref_len);
+    arr.n = ref_len > 0 ? (int)((ref_len + arr.chunk - 1) / arr.chunk) : 0;
+    arr.ev_ref = c->ev_h2d; arr.ev_tgt = c->ev_pipe[1];
+    if (tgt_len > 0) SCCG_CK(cudaMemcpyAsync(d_tgt, tgt, (size_t)tgt_len, cudaMemcpyHostToDevice, c->s_h2d));
+    SCCG_CK(cudaEventRecord(arr.ev_tgt, c->s_h2d));
+    for (int i = 0; i < arr.n; ++i) {
+        const i64 off = (i64)i * arr.chunk, len = (ref_len - off) < arr.chunk ? (ref_len - off) : arr.chunk;
+        SCCG_CK(cudaMemcpyAsync(d_ref + off, ref + off, (size_t)len, cudaMemcpyHostToDevice, c->s_h2d));
+        SCCG_CK(cudaEventRecord(arr.ev_ref[i], c->s_h2d));
+    }
+    SCCG_CK(cudaEventRecord(c->ev[5], c->s_h2d));
     CompressResult res;
-    SCCG_TRY(compress_device(c, d_ref, ref_len, d_tgt, tgt_len, header, header_len < 0 ? 0 : header_len, &res));
+    int rc_c = compress_device(c, d_ref, ref_len, d_tgt, tgt_len, header, header_len < 0 ? 0 : header_len, &res, &arr);
+    SCCG_CK(cudaStreamSynchronize(c->s_h2d));                                 // the caller's buffers are no longer in use
+    if (rc_c != SCCG_OK) return rc_c;
     SCCG_CK(cudaEventRecord(c->ev[6], c->stream));
     SCCG_TRY(deliver(c, res.d_out, res.out_len, dst, dst_cap, out, out_len));
     SCCG_CK(cudaEventRecord(c->ev[7], c->stream));
@@ -187,7 +204,7 @@ int sccg_match_sequences(sccg_ctx* c, const char* Sr, int64_t nr, const char* St
         // upper-cased symbols, for which this is the identity
         const size_t smem = sizeof(LmWarpSmem) * LM_WARPS;
         SCCG_SET_MAX_SMEM(seg_match_k, smem);
-        LAUNCH(c, seg_match_k, dim3(1), dim3(LM_WARPS * 32), smem, (const u8*)d_ref, (i64)(nr > 0 ? nr : 0), (const u8*)d_tgt, nt, 1, k, 0, seginfo, matches, sc + S_WORK, (u32*)nullptr, c->use_diag);
+        LAUNCH(c, seg_match_k, dim3(1), dim3(LM_WARPS * 32), smem, (const u8*)d_ref, (i64)(nr > 0 ? nr : 0), (const u8*)d_tgt, nt, 0, 1, 1, k, 0, seginfo, matches, sc + S_WORK, (u32*)nullptr, c->use_diag);
         u32 info = 0;
         SCCG_CK(cudaMemcpyAsync(&info, seginfo, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
         SCCG_CK(cudaMemcpyAsync(h_matches, matches, sizeof(u32) * LM_SLOT, cudaMemcpyDeviceToHost, c->stream));

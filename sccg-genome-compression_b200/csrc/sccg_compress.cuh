@@ -71,7 +71,16 @@ static int write_header(sccg_ctx* c, u8* d_out, const char* header, i64 nh) {
     return SCCG_OK;
 }
 
-static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt, i64 nt, const char* header, i64 nh, CompressResult* res) {
+// host entry points: the inputs are still arriving on the copy stream when compress_device starts
+struct ChunkArrival {
+    i64 chunk;               // bytes per reference chunk
+    int n;                   // number of reference chunks
+    cudaEvent_t* ev_ref;     // ev_ref[i]: reference bytes [0, (i + 1) * chunk) are resident
+    cudaEvent_t ev_tgt;      // the whole target is resident
+};
+
+static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt, i64 nt, const char* header, i64 nh, CompressResult* res,
+                           const ChunkArrival* arr) {
     u32* sc = nullptr;
     SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
     SCCG_CK(cudaMemsetAsync(sc, 0, sizeof(u32) * S_COUNT, c->stream));
@@ -83,6 +92,10 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
     u64* low_mask = nullptr;
     SCCG_CK(cudaEventRecord(c->ev_side[0], c->stream));
     SCCG_CK(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+    if (arr) {                                                                // both lanes need the whole target
+        SCCG_CK(cudaStreamWaitEvent(c->side_stream, arr->ev_tgt, 0));
+        SCCG_CK(cudaStreamWaitEvent(c->stream, arr->ev_tgt, 0));
+    }
     {
         SideLane side(c);
         SCCG_TRY(rle_count<0>(c, d_tgt, nt, B_RUN_CNT, B_RUN_MASK, &cnt_s, &cnt_e, &low_mask, sc + S_LOW_K, sc + S_LOW_KE, sc + S_PAREN));
@@ -104,8 +117,24 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
         unsigned want = div_up(n_iter, LM_WARPS);
         unsigned cap = (unsigned)c->sm_count * 8u;                          // 8 CTAs of 4 warps fit the 227 KB of shared memory
         unsigned grid = want < cap ? want : cap;
+        (void)grid;
         SCCG_CK(cudaMemsetAsync(seginfo, 0xff, sizeof(u32) * (size_t)n_iter, c->stream));    // "not done" markers for the early T2 abort
-        LAUNCH(c, seg_match_k, dim3(grid), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, n_iter, K1, K2, seginfo, matches, sc + S_WORK, sc + S_ABORT, c->use_diag);
+        // one launch per arrived reference chunk (device-resident inputs: a single launch)
+        const int n_launch = arr ? arr->n : 1;
+        int seg_lo = 0;
+        for (int i = 0; i < n_launch && seg_lo < n_iter; ++i) {
+            int seg_hi = n_iter;
+            if (arr && i + 1 < n_launch) {
+                const i64 resident = (i64)(i + 1) * arr->chunk;
+                seg_hi = (int)(resident / SEG < (i64)n_iter ? resident / SEG : (i64)n_iter);
+            }
+            if (arr) SCCG_CK(cudaStreamWaitEvent(c->stream, arr->ev_ref[i + 1 < n_launch ? i : arr->n - 1], 0));
+            if (seg_hi <= seg_lo) continue;
+            const unsigned w = div_up(seg_hi - seg_lo, LM_WARPS);
+            LAUNCH(c, seg_match_k, dim3(w < cap ? w : cap), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, seg_lo, seg_hi, n_iter, K1, K2, seginfo, matches,
+                   sc + S_WORK + (i & 31), sc + S_ABORT, c->use_diag);
+            seg_lo = seg_hi;
+        }
         SCCG_CK(cudaEventRecord(c->ev[2], c->stream));
         LAUNCH(c, seg_bytes_k, dim3(div_up(n_iter, 256)), dim3(256), 0, (const u32*)seginfo, (const u32*)matches, n_iter, seg_bytes, seg_prev, sc + S_ABORT, 0);
     } else {
@@ -131,6 +160,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
     SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
     if (h[S_ABORT]) {                                                         // :462-473 -> global (:484-574)
         SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));
+        if (arr && arr->n > 0) SCCG_CK(cudaStreamWaitEvent(c->stream, arr->ev_ref[arr->n - 1], 0));     // the global parse reads all of the reference
         return compress_global_device(c, d_ref, nr, d_tgt, nt, header, nh, low_k, low_text, text_delta, res);
     }
     // a '(' somewhere in the target: tokens are written with absolute p and delta_encode is replayed at text level

@@ -400,7 +400,9 @@ __device__ __forceinline__ void lm_fetch(const u8* __restrict__ ref, i64 nr, con
 }
 
 // k1 > 0 always; k2 == 0 disables the second pass (function-level match_sequences).
-// work_counter: device u32, zero before the launch; hands out segments gridDim*warps .. n_iter-1.
+// One launch handles the segments [seg_begin, n_iter) (the host entry points launch one range per uploaded chunk of the
+// reference); n_total is the number of segment pairs of the whole job (T2 windows look across launch borders).
+// work_counter: device u32, zero before the launch; hands out the segments after the pre-assigned ones.
 // abort_flag (optional): seginfo must be preset to 0xffffffff ("not done"); as soon as some warp sees the T2 abort
 // condition of the driver (:454-473: a failed, non-all-N segment ending a run of 5 counter increments) among finished
 // segments it raises the flag and every warp stops claiming work -- the local attempt is discarded anyway (:466-472).
@@ -411,7 +413,7 @@ __device__ __forceinline__ void lm_fetch(const u8* __restrict__ ref, i64 nr, con
 #define SCCG_LM_MIN_CTAS 8          // 8 CTAs x 128 threads x 64 registers = the whole register file of an SM
 #endif
 __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(const u8* __restrict__ ref, i64 nr, const u8* __restrict__ tgt, i64 nt,
-                                                            int n_iter, int k1, int k2, u32* seginfo, u32* __restrict__ matches,
+                                                            int seg_begin, int n_iter, int n_total, int k1, int k2, u32* seginfo, u32* __restrict__ matches,
                                                             u32* __restrict__ work_counter, u32* abort_flag, int use_diag) {
     SCCG_DYN_SMEM(smem_raw);
     LmWarpSmem& S = reinterpret_cast<LmWarpSmem*>(smem_raw)[threadIdx.x >> 5];
@@ -431,10 +433,10 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
     // segments are claimed dynamically (their cost varies by an order of magnitude) and the next segment's
     // symbols are fetched into registers while the current one is parsed
     u64 nrw[4], ntw[4];
-    const int claim_base = warps_total * SCCG_LM_CLAIM;       // the first warps_total * CLAIM segments are pre-assigned
+    const int claim_base = seg_begin + warps_total * SCCG_LM_CLAIM;   // the first warps_total * CLAIM segments are pre-assigned
     int claimed_used = 0;
     bool head_clean = false;                                  // S.head all zero (kept by the diagonal-hypothesis path)
-    int seg = warp_global * SCCG_LM_CLAIM < n_iter ? warp_global * SCCG_LM_CLAIM : n_iter;
+    int seg = seg_begin + warp_global * SCCG_LM_CLAIM < n_iter ? seg_begin + warp_global * SCCG_LM_CLAIM : n_iter;
     lm_fetch(ref, nr, tgt, nt, seg, n_iter, lane, nrw, ntw);
     while (seg < n_iter) {
         const i64 off = (i64)seg * SEG;
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
                 if (!all_n && (nmatch == 0 || bad)) {
                     // this segment increments the counter: test the five windows of 5 consecutive segments that contain it
                     __threadfence();
-                    for (int end = seg; end <= seg + T2_LIMIT && end < n_iter; ++end) {
+                    for (int end = seg; end <= seg + T2_LIMIT && end < n_total; ++end) {
                         if (end < T2_LIMIT) continue;
                         bool all_inc = true;
                         for (int d = 0; d <= T2_LIMIT && all_inc; ++d) {

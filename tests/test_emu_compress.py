@@ -197,6 +197,24 @@ def test_diag_hypothesis_fuzz(ctx, seed):
         assert (gmode, got) == (mode, exp), (seed, it, ref, tgt)
 
 
+@pytest.mark.parametrize("chunk", [4096, 50000])
+def test_compress_chunked_upload(ctx, chunk, monkeypatch):
+    """host entry point: the reference arrives in chunks and the segment matcher is launched once per chunk"""
+    from sccg_genome_compression_b200 import synth
+    monkeypatch.setenv("SCCG_PIPE_CHUNK", str(chunk))
+    for n, cut in ((123_456, 0), (90_000, 17_000), (64_000, -9_000)):
+        ref, tgt = synth.local_pair(n, synth.seed_for(2, 41))
+        ref, tgt = ref.tobytes(), tgt.tobytes()
+        if cut > 0:
+            tgt = tgt[:-cut]                        # reference longer than the target
+        elif cut < 0:
+            ref = ref[:cut]                         # target longer than the reference: leftover literals
+        rc, exp, mode = ol.orc_compress(ref, tgt, b">chunks")
+        assert rc == 0
+        got, gmode = ctx.compress(ref, tgt, b">chunks")
+        assert (gmode, got) == (mode, exp)
+
+
 def test_many_segments_scan_paths(ctx):
     # > 2048 segments so that the device-wide scan takes its multi-tile path
     ref = rnd(3_000_000 // 4, "big") * 4
