@@ -114,10 +114,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
     if (n_iter > 0) {
         const size_t smem = sizeof(LmWarpSmem) * LM_WARPS;
         SCCG_SET_MAX_SMEM(seg_match_k, smem);
-        unsigned want = div_up(n_iter, LM_WARPS);
-        unsigned cap = (unsigned)c->sm_count * 8u;                          // 8 CTAs of 4 warps fit the 227 KB of shared memory
-        unsigned grid = want < cap ? want : cap;
-        (void)grid;
+        const unsigned cap = (unsigned)c->sm_count * 8u;                    // 8 CTAs of 4 warps fit the 227 KB of shared memory
         SCCG_CK(cudaMemsetAsync(seginfo, 0xff, sizeof(u32) * (size_t)n_iter, c->stream));    // "not done" markers for the early T2 abort
         // one launch per arrived reference chunk (device-resident inputs: a single launch)
         const int n_launch = arr ? arr->n : 1;

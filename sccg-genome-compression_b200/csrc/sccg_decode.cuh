@@ -300,6 +300,8 @@ __device__ __forceinline__ int upper_idx_u32(const u32* __restrict__ arr, int n,
 struct GatherArgs {
     const u8* ref; const u8* enc;
     const u32* seg_dst; const i64* seg_src; const int* tok_abs; int nseg;
+    const i64* seg_ptr;      // resolved source of segment k: literal run -> offset into enc | SEG_LIT_FLAG, token -> offset into ref
+    const int4* tile_win;    // per 4 KiB tile of text: {first segment, first lowercase run, N symbols before the tile, staged path ok}
     const int* n_start; const int* n_len; const u32* n_cum; int n_k;
     const int* l_start; const int* l_len; int l_k;
     i64 Ls;          // symbols decoded from the record stream (N-free)
@@ -390,9 +392,9 @@ __device__ __forceinline__ u8 gather_byte(const GatherArgs& a, const int* win, u
     u8 o = 'N';
     if (!is_n) {
         int sk = bounded_upper_u32(a.seg_dst, win[0], win[1], s);
-        i64 src = a.seg_src[sk];
+        i64 src = a.seg_ptr[sk];
         i64 within = s - (i64)a.seg_dst[sk];
-        o = (src & SEG_LIT_FLAG) ? a.enc[(src & ~SEG_LIT_FLAG) + within] : a.ref[(i64)a.tok_abs[src] + within];
+        o = (src & SEG_LIT_FLAG) ? a.enc[(src & ~SEG_LIT_FLAG) + within] : a.ref[src + within];
     }
     int lk = bounded_upper_i32(a.l_start, win[4], win[5], bb);
     if (lk >= 0 && bb < (i64)a.l_start[lk] + (i64)a.l_len[lk]) o = lower1(o);
@@ -403,25 +405,26 @@ __device__ __forceinline__ u8 gather_byte(const GatherArgs& a, const int* win, u
 // touches no N run and is entirely inside or outside a lowercase run): two unaligned 8-byte loads, SWAR tolower,
 // newline spliced in with shifts, one 16-byte store.  Pieces that straddle a boundary are handed to the warp: 16 lanes
 // per piece, one symbol per lane, so boundary pieces cost one pass instead of a 16-step serial loop in a single lane.
-__global__ void __launch_bounds__(GATHER_T) dec_gather_k(GatherArgs a) {
-    __shared__ int win[6];            // search windows of this CTA: seg lo/hi, N-run lo/hi, lowercase-run lo/hi
+// (generic tile path: used for the rare tiles that contain re-inserted N runs; win = 6 ints of shared memory)
+__device__ __forceinline__ void gather_tile_generic(const GatherArgs& a, int* win, i64 Q0, int byte_off) {
     const int lane = lane_of(), warp = (int)(threadIdx.x >> 5);
-    const i64 Q0 = ((i64)blockIdx.x + a.tile0) * GATHER_TILE;
     const i64 Q1 = (Q0 + GATHER_TILE < a.total ? Q0 + GATHER_TILE : a.total) - 1;     // last byte of the tile
-    if (a.Lm > 0 && warp < 6) {
-        // six 32-ary searches, one per warp
-        const i64 bq = gather_sym_of((warp & 1) ? Q1 : Q0, a.Lm);
-        int r;
-        if (warp < 2) {
-            i64 sx = gather_strip(a, bq);
-            if (sx > a.Ls - 1) sx = a.Ls - 1;
-            r = a.nseg ? warp_upper_u32(a.seg_dst, a.nseg, sx) : -1;
-        } else if (warp < 4) r = warp_upper_i32(a.n_start, a.n_k, bq);
-        else r = warp_upper_i32(a.l_start, a.l_k, bq);
-        if (lane == 0) win[warp] = r;
+    if (a.Lm > 0) {
+        // six 32-ary searches shared among the warps of the CTA
+        for (int wi = warp; wi < 6; wi += (int)(blockDim.x >> 5)) {
+            const i64 bq = gather_sym_of((wi & 1) ? Q1 : Q0, a.Lm);
+            int r;
+            if (wi < 2) {
+                i64 sx = gather_strip(a, bq);
+                if (sx > a.Ls - 1) sx = a.Ls - 1;
+                r = a.nseg ? warp_upper_u32(a.seg_dst, a.nseg, sx) : -1;
+            } else if (wi < 4) r = warp_upper_i32(a.n_start, a.n_k, bq);
+            else r = warp_upper_i32(a.l_start, a.l_k, bq);
+            if (lane == 0) win[wi] = r;
+        }
     }
     __syncthreads();
-    const i64 q0 = Q0 + (i64)threadIdx.x * 16;
+    const i64 q0 = Q0 + byte_off + (i64)threadIdx.x * 16;
     const bool live = q0 < a.total;
     const u32 line0 = (u32)((u64)q0 / (u32)(WRAP + 1));
     const int col0 = (int)((u64)q0 - (u64)line0 * (WRAP + 1));
@@ -452,9 +455,9 @@ __global__ void __launch_bounds__(GATHER_T) dec_gather_k(GatherArgs a) {
         }
     }
     if (fast) {
-        i64 src = a.seg_src[sk];
+        i64 src = a.seg_ptr[sk];
         i64 within = (b - noff) - (i64)a.seg_dst[sk];
-        const u8* sp = (src & SEG_LIT_FLAG) ? a.enc + (src & ~SEG_LIT_FLAG) + within : a.ref + (i64)a.tok_abs[src] + within;
+        const u8* sp = (src & SEG_LIT_FLAG) ? a.enc + (src & ~SEG_LIT_FLAG) + within : a.ref + src + within;
         u64 w0 = ld_unaligned64(sp), w1 = ld_unaligned64(sp + 8);
         if (lower_all) { w0 = lower8(w0); w1 = lower8(w1); }
         if (c < 8) {
@@ -482,6 +485,168 @@ __global__ void __launch_bounds__(GATHER_T) dec_gather_k(GatherArgs a) {
         if (src >= 0) {
             u32 q = pq0 + (u32)(lane & 15);
             if ((i64)q < a.total) a.out[q] = gather_byte(a, win, q);
+        }
+    }
+}
+
+
+// ---- staged tile path ------------------------------------------------------------------------------------------------
+// dst (shared, any alignment) <- src (global, any alignment), n bytes; whole warp, uniform arguments.  8 bytes per lane and
+// step; the source may be read up to 15 bytes past its end (buffers carry that slack).
+__device__ __forceinline__ void warp_copy_g2s(u8* dst, const u8* __restrict__ src, u32 n) {
+    const u32 lane = (u32)lane_of();
+    u32 head = (u32)((8u - ((u32)(uintptr_t)dst & 7u)) & 7u);
+    if (head > n) head = n;
+    if (lane < head) dst[lane] = src[lane];
+    const u32 nw = (n - head) >> 3;
+    u64* d64 = reinterpret_cast<u64*>(dst + head);
+    const u8* s = src + head;
+    for (u32 i = lane; i < nw; i += 32) d64[i] = ld_unaligned64(s + 8 * (size_t)i);
+    const u32 done = head + (nw << 3);
+    if (done + lane < n) dst[done + lane] = src[done + lane];
+}
+// tolower on n bytes of shared memory (decompression.cpp:255-262); whole warp, uniform arguments
+__device__ __forceinline__ void warp_lower_smem(u8* p, u32 n) {
+    const u32 lane = (u32)lane_of();
+    u32 head = (u32)((8u - ((u32)(uintptr_t)p & 7u)) & 7u);
+    if (head > n) head = n;
+    if (lane < head) p[lane] = lower1(p[lane]);
+    const u32 nw = (n - head) >> 3;
+    u64* p64 = reinterpret_cast<u64*>(p + head);
+    for (u32 i = lane; i < nw; i += 32) p64[i] = lower8(p64[i]);
+    const u32 done = head + (nw << 3);
+    if (done + lane < n) p[done + lane] = lower1(p[done + lane]);
+}
+
+static const int GATHER_PAD = 64;
+
+// seg_ptr[k]: where segment k copies from (one dependent load less in the gather)
+__global__ void dec_resolve_k(const i64* __restrict__ seg_src, const int* __restrict__ tok_abs, int nseg, i64* __restrict__ seg_ptr) {
+    int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (k >= nseg) return;
+    const i64 src = seg_src[k];
+    seg_ptr[k] = (src & SEG_LIT_FLAG) ? src : (i64)tok_abs[src];
+}
+
+// merged-coordinate symbol range [b0, b1) shown in the text bytes [Q0, Qe)
+__device__ __forceinline__ void tile_symbols(i64 Q0, i64 Qe, i64 Lm, u32* b0, u32* b1) {
+    const u32 l0 = (u32)Q0 / (u32)(WRAP + 1), c0 = (u32)Q0 - l0 * (u32)(WRAP + 1);
+    const u32 l1 = (u32)Qe / (u32)(WRAP + 1), c1 = (u32)Qe - l1 * (u32)(WRAP + 1);
+    *b0 = l0 * WRAP + (c0 < (u32)WRAP ? c0 : (u32)WRAP);
+    u32 e = l1 * WRAP + (c1 < (u32)WRAP ? c1 : (u32)WRAP);
+    if ((i64)e > Lm) e = (u32)Lm;
+    *b1 = e;
+}
+
+// per tile: where its copy segments and lowercase runs start (the searches leave the gather's critical path)
+__global__ void dec_tile_win_k(GatherArgs a, unsigned ntiles, int4* __restrict__ tile_win) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const i64 Q0 = (i64)t * GATHER_TILE;
+    const i64 Qe = Q0 + GATHER_TILE < a.total ? Q0 + GATHER_TILE : a.total;
+    int4 w = make_int4(0, 0, 0, 0);
+    u32 b0 = 0, b1 = 0;
+    bool staged = a.Lm > 0;
+    if (staged) { tile_symbols(Q0, Qe, a.Lm, &b0, &b1); if (b1 <= b0) staged = false; }   // nothing but the final newline
+    u32 noff = 0;
+    if (staged && a.n_k) {
+        const int nk = upper_idx_i32(a.n_start, a.n_k, (i64)b1 - 1);
+        if (nk >= 0) {
+            if ((i64)a.n_start[nk] + a.n_len[nk] > (i64)b0) staged = false;               // an N run inside the tile
+            else noff = a.n_cum[nk] + (u32)a.n_len[nk];
+        }
+    }
+    if (staged) {
+        w.x = upper_idx_u32(a.seg_dst, a.nseg, (i64)(b0 - noff));                         // segment that holds the first symbol
+        int lk = upper_idx_i32(a.l_start, a.l_k, (i64)b0);                                // first lowercase run that reaches into the tile
+        if (lk < 0 || (i64)a.l_start[lk] + a.l_len[lk] <= (i64)b0) ++lk;
+        w.y = lk; w.z = (int)noff; w.w = 1;
+    }
+    tile_win[t] = w;
+}
+
+// One CTA (4 warps) produces one 4 KiB tile of the final text.  Tiles without re-inserted N (all but a handful):
+//   1. the copy segments that overlap the tile are copied by whole warps, segment by segment, from the reference / the
+//      literal bytes into a shared-memory image of the tile's symbols (coalesced 8-byte loads, no per-byte search);
+//   2. the lowercase runs that overlap the tile are applied to that image, run by run (decompression.cpp:255-262);
+//   3. every thread formats 2 x 16 bytes of text from the image: newline every 50 symbols (:266-274), 16-byte stores.
+// Tiles that contain N runs take the generic per-piece path above (gather_tile_generic).
+static const int GATHER_CTA = 128;
+__global__ void __launch_bounds__(GATHER_CTA) dec_gather_k(GatherArgs a) {
+    __shared__ int win[6];
+    __align__(16) __shared__ u8 A[GATHER_TILE + GATHER_PAD];
+    const int warp = (int)(threadIdx.x >> 5);
+    const unsigned tile = blockIdx.x + a.tile0;
+    const i64 Q0 = (i64)tile * GATHER_TILE;
+    const i64 Qe = Q0 + GATHER_TILE < a.total ? Q0 + GATHER_TILE : a.total;           // exclusive
+    const int4 tw = a.tile_win[tile];
+    if (!tw.w) {
+        // generic path: written for 256 threads x 16 bytes -> two rounds of 128 threads over the two halves of the tile
+        gather_tile_generic(a, win, Q0, 0);
+        __syncthreads();
+        gather_tile_generic(a, win, Q0, GATHER_CTA * 16);
+        return;
+    }
+    u32 b0, b1;
+    tile_symbols(Q0, Qe, a.Lm, &b0, &b1);
+    const u32 noff = (u32)tw.z;
+    const u32 s0 = b0 - noff, s1 = b1 - noff;                                         // N-free coordinates of the tile's symbols
+    // ---- 1. copy segments -> image
+    for (int k = tw.x + warp; k < a.nseg; k += GATHER_CTA / 32) {
+        const u32 d0 = a.seg_dst[k];
+        if (d0 >= s1) break;
+        const u32 d1 = k + 1 < a.nseg ? a.seg_dst[k + 1] : (u32)a.Ls;
+        const u32 lo = d0 > s0 ? d0 : s0, hi = d1 < s1 ? d1 : s1;
+        if (hi <= lo) continue;
+        const i64 src = a.seg_ptr[k];
+        const u8* sp = (src & SEG_LIT_FLAG) ? a.enc + (src & ~SEG_LIT_FLAG) : a.ref + src;
+        warp_copy_g2s(A + (lo - s0), sp + (lo - d0), hi - lo);
+    }
+    __syncthreads();
+    // ---- 2. lowercase runs (merged coordinates; image offset = b - b0)
+    for (int k = tw.y + warp; k < a.l_k; k += GATHER_CTA / 32) {
+        const i64 ls = a.l_start[k];
+        if (ls >= (i64)b1) break;
+        const i64 le = ls + a.l_len[k];
+        const u32 lo = ls > (i64)b0 ? (u32)ls : b0, hi = le < (i64)b1 ? (u32)le : b1;
+        if (hi > lo) warp_lower_smem(A + (lo - b0), hi - lo);
+    }
+    __syncthreads();
+    // ---- 3. format: 2 x 16 bytes of text per thread
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const i64 q0 = Q0 + ((i64)threadIdx.x + half * GATHER_CTA) * 16;
+        if (q0 >= a.total) return;
+        const u32 line0 = (u32)q0 / (u32)(WRAP + 1);
+        const int col0 = (int)((u32)q0 - line0 * (u32)(WRAP + 1));
+        const int c = WRAP - col0;                                   // offset of the '\n' inside this piece if < 16
+        const u32 ao = line0 * WRAP + (u32)col0 - b0;                // image offset of the first symbol of the piece
+        if (q0 + 16 <= a.total - 1) {
+            const u32* A32 = reinterpret_cast<const u32*>(A);
+            const u32 i = ao >> 2, sh = (ao & 3u) * 8u;
+            const u32 x0 = A32[i], x1 = A32[i + 1], x2 = A32[i + 2], x3 = A32[i + 3], x4 = A32[i + 4];
+            u64 w0 = (u64)__funnelshift_r(x0, x1, sh) | ((u64)__funnelshift_r(x1, x2, sh) << 32);
+            u64 w1 = (u64)__funnelshift_r(x2, x3, sh) | ((u64)__funnelshift_r(x3, x4, sh) << 32);
+            if (c < 8) {
+                u64 lowmask = c ? (~0ull >> (64 - 8 * c)) : 0ull;
+                u64 carry = w0 >> 56;
+                w0 = (w0 & lowmask) | ((u64)'\n' << (8 * c)) | ((w0 & ~lowmask) << 8);
+                w1 = (w1 << 8) | carry;
+            } else if (c < 16) {
+                int cc = c - 8;
+                u64 lowmask = cc ? (~0ull >> (64 - 8 * cc)) : 0ull;
+                w1 = (w1 & lowmask) | ((u64)'\n' << (8 * cc)) | ((w1 & ~lowmask) << 8);
+            }
+            ulonglong2 v; v.x = w0; v.y = w1;
+            *reinterpret_cast<ulonglong2*>(a.out + q0) = v;
+        } else {
+            // the piece(s) at the very end of the text: the final newline (:274) does not sit on a line border
+            u32 sym = ao;
+            for (int d = 0; d < 16 && q0 + d < a.total; ++d) {
+                const bool nl = (q0 + d == a.total - 1) || (col0 + d) % (WRAP + 1) == WRAP;
+                a.out[q0 + d] = nl ? (u8)'\n' : A[sym];
+                if (!nl) ++sym;
+            }
         }
     }
 }
@@ -557,6 +722,14 @@ static int reconstruct_prepare(sccg_ctx* c, i64 nr, const u8* d_enc, i64 ne, con
     a.l_start = lows.start; a.l_len = lows.len; a.l_k = (int)lows.K;
     a.Ls = Ls; a.Lm = Lm; a.total = total; a.out = out + header_reserve; a.tile0 = 0;
     plan->sc = sc; plan->tok_len = tok_len; plan->ntok = ntok; plan->ntiles = div_up(total, GATHER_TILE);
+    // resolved segment sources and per-tile entry points: the gather itself starts from two table loads
+    i64* seg_ptr = nullptr; int4* tile_win = nullptr;
+    SCCG_TRY(buf(c, B_SEG_PTR, (size_t)nseg + 1, &seg_ptr));
+    SCCG_TRY(buf(c, B_TILE_WIN, (size_t)plan->ntiles + 1, &tile_win));
+    if (nseg) LAUNCH(c, dec_resolve_k, dim3(div_up(nseg, 256)), dim3(256), 0, (const i64*)seg_src, (const int*)tok_abs, (int)nseg, seg_ptr);
+    a.seg_ptr = seg_ptr; a.tile_win = tile_win;
+    LAUNCH(c, dec_tile_win_k, dim3(div_up(plan->ntiles, 128)), dim3(128), 0, a, plan->ntiles, tile_win);
+    SCCG_CK(cudaEventRecord(c->ev[1], c->stream));                              // everything up to here is "tokenizer" time
     return SCCG_OK;
 }
 
@@ -564,7 +737,7 @@ static int reconstruct_prepare(sccg_ctx* c, i64 nr, const u8* d_enc, i64 ne, con
 static int reconstruct_gather(sccg_ctx* c, const ReconPlan* plan, const u8* d_ref, unsigned tile0, unsigned ntiles) {
     GatherArgs a = plan->a;
     a.ref = d_ref; a.tile0 = tile0;
-    if (ntiles) LAUNCH(c, dec_gather_k, dim3(ntiles), dim3(GATHER_T), 0, a);
+    if (ntiles) LAUNCH(c, dec_gather_k, dim3(ntiles), dim3(GATHER_CTA), 0, a);
     return SCCG_OK;
 }
 
