@@ -565,13 +565,17 @@ __global__ void dec_tile_win_k(GatherArgs a, unsigned ntiles, int4* __restrict__
     tile_win[t] = w;
 }
 
-// One CTA (4 warps) produces one 4 KiB tile of the final text.  Tiles without re-inserted N (all but a handful):
+// One small CTA produces one 4 KiB tile of the final text.  Tiles without re-inserted N (all but a handful):
 //   1. the copy segments that overlap the tile are copied by whole warps, segment by segment, from the reference / the
 //      literal bytes into a shared-memory image of the tile's symbols (coalesced 8-byte loads, no per-byte search);
 //   2. the lowercase runs that overlap the tile are applied to that image, run by run (decompression.cpp:255-262);
-//   3. every thread formats 2 x 16 bytes of text from the image: newline every 50 symbols (:266-274), 16-byte stores.
+//   3. every thread formats a few 16-byte pieces of text from the image: newline every 50 symbols (:266-274), 16-byte stores.
 // Tiles that contain N runs take the generic per-piece path above (gather_tile_generic).
-static const int GATHER_CTA = 128;
+#ifndef SCCG_GATHER_CTA
+#define SCCG_GATHER_CTA 64
+#endif
+static const int GATHER_CTA = SCCG_GATHER_CTA;             // threads per 4 KiB tile: fewer threads per tile = more tiles in flight per SM
+static const int GATHER_ROUNDS = GATHER_TILE / 16 / GATHER_CTA;
 __global__ void __launch_bounds__(GATHER_CTA) dec_gather_k(GatherArgs a) {
     __shared__ int win[6];
     __align__(16) __shared__ u8 A[GATHER_TILE + GATHER_PAD];
@@ -581,40 +585,63 @@ __global__ void __launch_bounds__(GATHER_CTA) dec_gather_k(GatherArgs a) {
     const i64 Qe = Q0 + GATHER_TILE < a.total ? Q0 + GATHER_TILE : a.total;           // exclusive
     const int4 tw = a.tile_win[tile];
     if (!tw.w) {
-        // generic path: written for 256 threads x 16 bytes -> two rounds of 128 threads over the two halves of the tile
-        gather_tile_generic(a, win, Q0, 0);
-        __syncthreads();
-        gather_tile_generic(a, win, Q0, GATHER_CTA * 16);
+        // generic path: one 16-byte piece per thread and round
+        for (int r = 0; r < GATHER_ROUNDS; ++r) {
+            gather_tile_generic(a, win, Q0, r * GATHER_CTA * 16);
+            __syncthreads();
+        }
         return;
     }
     u32 b0, b1;
     tile_symbols(Q0, Qe, a.Lm, &b0, &b1);
     const u32 noff = (u32)tw.z;
     const u32 s0 = b0 - noff, s1 = b1 - noff;                                         // N-free coordinates of the tile's symbols
-    // ---- 1. copy segments -> image
-    for (int k = tw.x + warp; k < a.nseg; k += GATHER_CTA / 32) {
-        const u32 d0 = a.seg_dst[k];
-        if (d0 >= s1) break;
-        const u32 d1 = k + 1 < a.nseg ? a.seg_dst[k + 1] : (u32)a.Ls;
-        const u32 lo = d0 > s0 ? d0 : s0, hi = d1 < s1 ? d1 : s1;
-        if (hi <= lo) continue;
-        const i64 src = a.seg_ptr[k];
-        const u8* sp = (src & SEG_LIT_FLAG) ? a.enc + (src & ~SEG_LIT_FLAG) : a.ref + src;
-        warp_copy_g2s(A + (lo - s0), sp + (lo - d0), hi - lo);
+    // ---- 1. copy segments -> image.  Warp w owns the segments first + w, first + w + NW, ...; their descriptors are fetched
+    //      32 at a time, one per lane (one memory round trip), and handed out by shuffles
+    const int lane = lane_of();
+    const int NW = GATHER_CTA / 32;
+    for (int kb = tw.x + warp; kb < a.nseg; kb += 32 * NW) {
+        const int kk = kb + lane * NW;
+        u32 md0 = 0xffffffffu, md1 = 0u;
+        i64 mp = 0;
+        if (kk < a.nseg) { md0 = a.seg_dst[kk]; md1 = kk + 1 < a.nseg ? a.seg_dst[kk + 1] : (u32)a.Ls; mp = a.seg_ptr[kk]; }
+        bool done = false;
+        for (int j = 0; j < 32; ++j) {
+            const u32 d0 = __shfl_sync(SCCG_FULL_MASK, md0, j);
+            if (d0 >= s1) { done = true; break; }                 // also the "no such segment" marker
+            const u32 d1 = __shfl_sync(SCCG_FULL_MASK, md1, j);
+            const i64 src = __shfl_sync(SCCG_FULL_MASK, mp, j);
+            const u32 lo = d0 > s0 ? d0 : s0, hi = d1 < s1 ? d1 : s1;
+            if (hi <= lo) continue;
+            const u8* sp = (src & SEG_LIT_FLAG) ? a.enc + (src & ~SEG_LIT_FLAG) : a.ref + src;
+            warp_copy_g2s(A + (lo - s0), sp + (lo - d0), hi - lo);
+        }
+        if (done) break;
     }
+    // lowercase runs of this warp, fetched the same way while the copies are in flight
+    int lkk = tw.y + warp + lane * NW;
+    i64 ml0 = 0x7fffffffffffffffLL, ml1 = 0;
+    if (lkk < a.l_k) { ml0 = a.l_start[lkk]; ml1 = ml0 + a.l_len[lkk]; }
     __syncthreads();
     // ---- 2. lowercase runs (merged coordinates; image offset = b - b0)
-    for (int k = tw.y + warp; k < a.l_k; k += GATHER_CTA / 32) {
-        const i64 ls = a.l_start[k];
-        if (ls >= (i64)b1) break;
-        const i64 le = ls + a.l_len[k];
-        const u32 lo = ls > (i64)b0 ? (u32)ls : b0, hi = le < (i64)b1 ? (u32)le : b1;
-        if (hi > lo) warp_lower_smem(A + (lo - b0), hi - lo);
+    for (int lb = tw.y + warp; lb < a.l_k; lb += 32 * NW) {
+        bool done = false;
+        for (int j = 0; j < 32; ++j) {
+            const i64 ls = __shfl_sync(SCCG_FULL_MASK, ml0, j);
+            if (ls >= (i64)b1) { done = true; break; }
+            const i64 le = __shfl_sync(SCCG_FULL_MASK, ml1, j);
+            const u32 lo = ls > (i64)b0 ? (u32)ls : b0, hi = le < (i64)b1 ? (u32)le : b1;
+            if (hi > lo) warp_lower_smem(A + (lo - b0), hi - lo);
+        }
+        if (done) break;
+        lkk += 32 * NW;                                            // (rare) more than 32 runs per warp in one tile
+        ml0 = 0x7fffffffffffffffLL; ml1 = 0;
+        if (lkk < a.l_k) { ml0 = a.l_start[lkk]; ml1 = ml0 + a.l_len[lkk]; }
     }
     __syncthreads();
-    // ---- 3. format: 2 x 16 bytes of text per thread
+    // ---- 3. format: GATHER_ROUNDS x 16 bytes of text per thread
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int half = 0; half < GATHER_ROUNDS; ++half) {
         const i64 q0 = Q0 + ((i64)threadIdx.x + half * GATHER_CTA) * 16;
         if (q0 >= a.total) return;
         const u32 line0 = (u32)q0 / (u32)(WRAP + 1);
@@ -664,8 +691,8 @@ static int reconstruct_prepare(sccg_ctx* c, i64 nr, const u8* d_enc, i64 ne, con
     SCCG_CK(cudaEventRecord(c->ev[0], c->stream));
 
     RunTable lows, ns;
-    SCCG_TRY(parse_runs(c, d_low, nl, B_NUM0, sc, D_LOW_ITEMS, sc + D_LSUM, &lows));     // slots B_NUM0..B_NUM3
-    SCCG_TRY(parse_runs(c, d_n, nn, B_NUM4, sc, D_N_ITEMS, sc + D_NSUM, &ns));          // slots B_NUM4, B_NUM5, B_LRUN_S, B_LRUN_E
+    SCCG_CK(cudaEventRecord(c->ev_side[2], c->stream));
+    SCCG_CK(cudaStreamWaitEvent(c->side_stream, c->ev_side[2], 0));
 
     // ---- body tokenizer: count per 16-byte chunk, scan, emit the compacted tables
     const i64 nth = (ne + DEC_PER_THREAD - 1) / DEC_PER_THREAD;
@@ -678,6 +705,14 @@ static int reconstruct_prepare(sccg_ctx* c, i64 nr, const u8* d_enc, i64 ne, con
     SCCG_TRY(scan_exclusive_u32(c, th_sym, th_sym, nth, sc + D_LS));
     SCCG_TRY(scan_exclusive_u32(c, th_seg, th_seg, nth, sc + D_NSEG));
     SCCG_TRY(scan_exclusive_u32(c, th_tok, th_tok, nth, sc + D_NTOK));
+    // ---- the two run lists are parsed on the side lane while the tokenizer kernels run
+    {
+        SideLane side(c);
+        SCCG_TRY(parse_runs(c, d_low, nl, B_NUM0, sc, D_LOW_ITEMS, sc + D_LSUM, &lows));     // slots B_NUM0..B_NUM3
+        SCCG_TRY(parse_runs(c, d_n, nn, B_NUM4, sc, D_N_ITEMS, sc + D_NSUM, &ns));          // slots B_NUM4, B_NUM5, B_LRUN_S, B_LRUN_E
+        SCCG_CK(cudaEventRecord(c->ev_side[3], c->stream));
+    }
+    SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[3], 0));
     u32 h[D_COUNT];
     SCCG_TRY(read_scalars(c, sc, h, D_COUNT));
     if (h[D_ERR] & DE_FORMAT) return set_error(SCCG_E_FORMAT, "malformed record stream (the reference would throw from stoi)");
@@ -781,14 +816,24 @@ __device__ __forceinline__ i64 out_byte_of_sym(const GatherArgs& a, i64 s) {
 }
 // need_hi[j] = one past the last reference symbol that the tokens feeding output chunk j copy from
 __global__ void dec_need_k(GatherArgs a, const int* __restrict__ tok_len, i64 chunk_bytes, u32* __restrict__ need_hi) {
-    int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (k >= a.nseg) return;
-    const i64 src = a.seg_src[k];
-    if (src & SEG_LIT_FLAG) return;
-    const i64 s0 = a.seg_dst[k], s1 = k + 1 < a.nseg ? (i64)a.seg_dst[k + 1] : a.Ls;
-    if (s1 <= s0) return;
-    const u32 hi = (u32)((i64)a.tok_abs[src] + (i64)tok_len[src]);
-    const i64 c0 = out_byte_of_sym(a, s0) / chunk_bytes, c1 = out_byte_of_sym(a, s1 - 1) / chunk_bytes;
+    const int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    u32 hi = 0;
+    i64 c0 = -1, c1 = -2;
+    if (k < a.nseg) {
+        const i64 src = a.seg_src[k];
+        const i64 s0 = a.seg_dst[k], s1 = k + 1 < a.nseg ? (i64)a.seg_dst[k + 1] : a.Ls;
+        if (!(src & SEG_LIT_FLAG) && s1 > s0) {
+            hi = (u32)((i64)a.tok_abs[src] + (i64)tok_len[src]);
+            c0 = out_byte_of_sym(a, s0) / chunk_bytes; c1 = out_byte_of_sym(a, s1 - 1) / chunk_bytes;
+        }
+    }
+    // neighbouring segments feed the same output chunk: one atomic per warp instead of one per segment
+    const i64 cw = (i64)__reduce_max_sync(SCCG_FULL_MASK, (int)c0);           // chunk of the token segments of this warp (-1: none)
+    if (__all_sync(SCCG_FULL_MASK, (c0 == cw && c1 == cw) || c1 < c0)) {
+        const u32 m = __reduce_max_sync(SCCG_FULL_MASK, hi);
+        if (lane_of() == 0 && cw >= 0 && m) atomicMax(&need_hi[cw], m);
+        return;
+    }
     for (i64 cj = c0; cj <= c1; ++cj) atomicMax(&need_hi[cj], hi);
 }
 
