@@ -33,6 +33,16 @@ HEADER = b">chr1 synthetic hg19-vs-hg18 shape"
 import sccg_b200  # noqa: E402  (registers the hyphenated package dir as sccg_genome_compression_b200)
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes (read + write) per launch of `kernel` from the committed `ncu --set full` capture of this workload
+    (profiles/traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); None if no capture is committed"""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        return json.loads(p.read_text())["kernels"][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def peaks() -> tuple[float, str]:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -331,15 +341,16 @@ def main() -> None:
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_name(args.size), "bp_per_gpu": nt, "sharding": "one chromosome-sized pair per GPU, no data-path collective",
                        "l2": "inputs (2 x 249 MB) larger than the 126 MB L2, no flush needed", "timing": "CUDA events on the library stream, max over ranks",
+                       "concurrency": "the lowercase-run kernels run on a side stream underneath seg_match_k (its kernel_ms includes that sharing)",
                        "encoded_bytes": enc_len, "mode": "local"},
             "wall_ms_per_step": comp_wall_ms,
             "decompress": {"value": world * nt / (dec_ms / 1e3) / 1e9, "unit": "Gbp/s", "ms_per_step": dec_ms,
                            "roofline": {"bound": "hbm", "kernel": "dec_gather_k", "achieved": dach, "peak": hbm, "unit": "GB/s", "frac": dach / hbm,
-                                        "traffic": None, "algorithmic_bytes_per_launch": dec_bytes, "kernel_ms": g_ms, "peak_source": which},
+                                        "traffic": ncu_traffic("dec_gather_k") if args.size == synth.CHR1_LEN else None, "algorithmic_bytes_per_launch": dec_bytes, "kernel_ms": g_ms, "peak_source": which},
                            "e2e": {"value": world * nt / (e2e_dec_ms / 1e3) / 1e9, "unit": "Gbp/s", "ms_per_step": e2e_dec_ms,
                                    "h2d_bytes_per_step": nr + enc_len, "d2h_bytes_per_step": d_len, "h2d_ms": e2e_dprof["h2d_ms"],
                                    "d2h_ms": e2e_dprof["d2h_ms"], "kernels_ms": e2e_dprof["kernels_ms"]}},
-            "roofline": {"bound": "hbm", "kernel": "seg_match_k", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "seg_match_k", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": ncu_traffic("seg_match_k") if args.size == synth.CHR1_LEN else None,
                          "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": match_ms_avg, "peak_source": which},
             "cpu_baseline": cpu,
             "e2e": {"value": world * nt / (e2e_ms / 1e3) / 1e6, "unit": "Mbp/s", "h2d_bytes_per_step": nr + nt, "d2h_bytes_per_step": enc_len,

@@ -120,6 +120,15 @@ int sccg_reconstruct_into(sccg_ctx* ctx, const char* ref, int64_t ref_len, const
 int sccg_decompress_into(sccg_ctx* ctx, const char* ref_raw, int64_t ref_len, const char* intermediate, int64_t inter_len,
                          char* out, int64_t out_cap, int64_t* out_len);
 
+/* FASTA file images in: read_genomes_from_files (compression.cpp:181-220) and the reference reader of decompress_genome
+ * (decompression.cpp:47-58) run on the device -- header lines skipped ('>' at a line start; in the target only the first one,
+ * which becomes the header line of the output), isspace() bytes removed -- followed by sccg_compress / sccg_decompress.
+ * ref_file / tgt_file: the raw bytes of the FASTA files.  The host never touches the symbols. */
+int sccg_compress_fasta(sccg_ctx* ctx, const char* ref_file, int64_t ref_file_len, const char* tgt_file, int64_t tgt_file_len,
+                        char** out, int64_t* out_len, int* mode_out);
+int sccg_decompress_fasta(sccg_ctx* ctx, const char* ref_file, int64_t ref_file_len, const char* intermediate, int64_t inter_len,
+                          char** out, int64_t* out_len);
+
 #ifdef __cplusplus
 }
 #endif

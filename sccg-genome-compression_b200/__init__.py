@@ -86,6 +86,8 @@ def load_library(path: str | os.PathLike | None = None) -> C.CDLL:
     lib.sccg_compress_into.argtypes = [vp, cp, i64, cp, i64, cp, i64, vp, i64, C.POINTER(i64), C.POINTER(C.c_int)]
     lib.sccg_reconstruct_into.argtypes = [vp, cp, i64, cp, i64, cp, i64, cp, i64, vp, i64, C.POINTER(i64)]
     lib.sccg_decompress_into.argtypes = [vp, cp, i64, cp, i64, vp, i64, C.POINTER(i64)]
+    lib.sccg_compress_fasta.argtypes = [vp, cp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_int)]
+    lib.sccg_decompress_fasta.argtypes = [vp, cp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64)]
     _libs[key] = lib
     return lib
 
@@ -190,6 +192,20 @@ class Context:
         self._check(self.lib.sccg_reconstruct_device(self.handle, d_ref, ref_len, d_enc, enc_len, d_n, n_len, d_low, low_len,
                                                      C.byref(out), C.byref(n)))
         return out.value or 0, n.value
+
+    # read_genomes_from_files on the device + compress_genome (compression.cpp:181-220, :320-579): raw FASTA file images in
+    def compress_fasta(self, ref_file: bytes, tgt_file: bytes) -> tuple[bytes, int]:
+        out = C.c_void_p(); n = C.c_int64(); mode = C.c_int()
+        rc = self.lib.sccg_compress_fasta(self.handle, ref_file, len(ref_file), tgt_file, len(tgt_file), C.byref(out), C.byref(n), C.byref(mode))
+        if rc == SCCG_E_STOI:
+            raise SccgError(rc, self.lib.sccg_last_error().decode(), self._take(out, n.value))
+        self._check(rc)
+        return self._take(out, n.value), mode.value
+
+    def decompress_fasta(self, ref_file: bytes, intermediate: bytes) -> bytes:
+        out = C.c_void_p(); n = C.c_int64()
+        self._check(self.lib.sccg_decompress_fasta(self.handle, ref_file, len(ref_file), intermediate, len(intermediate), C.byref(out), C.byref(n)))
+        return self._take(out, n.value)
 
     # decompress_genome (in-memory part) + reconstruct_genome + header line (decompression.cpp:66-110, :117-279, :322)
     def decompress(self, ref_raw: bytes, intermediate: bytes) -> bytes:

@@ -3,6 +3,7 @@
 #include "sccg_compress.cuh"
 #include "sccg_global.cuh"
 #include "sccg_decode.cuh"
+#include "sccg_fasta.cuh"
 
 #include <new>
 
@@ -308,6 +309,58 @@ int sccg_decompress_into(sccg_ctx* c, const char* ref_raw, int64_t ref_len, cons
     SCCG_CK(cudaSetDevice(c->device));
     prof_reset(c);
     return decompress_host(c, ref_raw, ref_len, inter, inter_len, out, out_cap, nullptr, out_len);
+}
+
+// ---- FASTA images in, FASTA handling on the device -------------------------------------------------------
+static int upload_file(sccg_ctx* c, int slot, const char* h, int64_t n, u8** d) {
+    SCCG_TRY(buf(c, slot, (size_t)(n > 0 ? n : 1) + 128, d));
+    if (n > 0) SCCG_CK(cudaMemcpyAsync(*d, h, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    SCCG_CK(cudaMemsetAsync(*d + (n > 0 ? n : 0), 0, 64, c->stream));
+    return SCCG_OK;
+}
+
+int sccg_compress_fasta(sccg_ctx* c, const char* ref_file, int64_t ref_file_len, const char* tgt_file, int64_t tgt_file_len,
+                        char** out, int64_t* out_len, int* mode_out) {
+    if (!c || !out || !out_len || (ref_file_len > 0 && !ref_file) || (tgt_file_len > 0 && !tgt_file)) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_TRY(check_sizes(ref_file_len, tgt_file_len));
+    SCCG_CK(cudaSetDevice(c->device));
+    prof_reset(c);
+    u8 *d_rf = nullptr, *d_tf = nullptr;
+    u32* sc = nullptr;
+    SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
+    SCCG_CK(cudaEventRecord(c->ev[4], c->stream));
+    SCCG_TRY(upload_file(c, B_FILE_R, ref_file, ref_file_len, &d_rf));
+    SCCG_TRY(upload_file(c, B_FILE_T, tgt_file, tgt_file_len, &d_tf));
+    SCCG_CK(cudaEventRecord(c->ev[5], c->stream));
+    FastaSeq R, T;
+    SCCG_TRY(fasta_ingest(c, d_rf, ref_file_len, false, B_REF, B_FA_TMP, B_FA_RNG, sc + S_G7, &R));      // compression.cpp:193-200
+    SCCG_TRY(fasta_ingest(c, d_tf, tgt_file_len, true, B_TGT, B_FA_TMP, B_FA_RNG, sc + S_G7, &T));       // :207-219
+    const char* header = T.hdr_start >= 0 ? tgt_file + T.hdr_start : "";
+    const int64_t nh = T.hdr_start >= 0 ? T.hdr_end - T.hdr_start : 0;
+    CompressResult res;
+    SCCG_TRY(compress_device(c, R.d_seq, R.len, T.d_seq, T.len, header, nh, &res, nullptr));
+    SCCG_CK(cudaEventRecord(c->ev[6], c->stream));
+    SCCG_TRY(deliver(c, res.d_out, res.out_len, nullptr, 0, out, out_len));
+    SCCG_CK(cudaEventRecord(c->ev[7], c->stream));
+    SCCG_CK(cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->prof.h2d_ms, c->ev[4], c->ev[5]);
+    cudaEventElapsedTime(&c->prof.d2h_ms, c->ev[6], c->ev[7]);
+    if (mode_out) *mode_out = res.mode;
+    return res.stoi_failed ? stoi_failure() : SCCG_OK;
+}
+
+int sccg_decompress_fasta(sccg_ctx* c, const char* ref_file, int64_t ref_file_len, const char* inter, int64_t inter_len, char** out, int64_t* out_len) {
+    if (!c || !out || !out_len || (ref_file_len > 0 && !ref_file) || (inter_len > 0 && !inter)) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_TRY(check_sizes(ref_file_len, inter_len));
+    SCCG_CK(cudaSetDevice(c->device));
+    prof_reset(c);
+    u8* d_rf = nullptr;
+    u32* sc = nullptr;
+    SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
+    SCCG_TRY(upload_file(c, B_FILE_R, ref_file, ref_file_len, &d_rf));
+    FastaSeq R;
+    SCCG_TRY(fasta_ingest(c, d_rf, ref_file_len, false, B_TGT, B_FA_TMP, B_FA_RNG, sc + S_G7, &R));      // decompression.cpp:47-58
+    return decompress_host(c, nullptr, R.len, inter, inter_len, nullptr, 0, out, out_len, R.d_seq);
 }
 
 #ifdef SCCG_SEG_STATS

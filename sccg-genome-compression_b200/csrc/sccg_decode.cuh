@@ -841,7 +841,9 @@ static const int PIPE_MAX_CHUNKS = 64;
 
 
 // decompress_genome's in-memory part (decompression.cpp:66-110) + reconstruct_genome + main's "<header>\n" (:322)
-static int decompress_host(sccg_ctx* c, const char* ref_raw, i64 ref_len, const char* inter, i64 inter_len, char* dst, i64 dst_cap, char** out, int64_t* out_len) {
+// d_raw_in != NULL: the raw reference symbols are already in device memory (FASTA ingest on the device); ref_raw is unused then
+static int decompress_host(sccg_ctx* c, const char* ref_raw, i64 ref_len, const char* inter, i64 inter_len, char* dst, i64 dst_cap, char** out, int64_t* out_len,
+                           const u8* d_raw_in = nullptr) {
     // ---- the 3 / 4 getline calls (:66-101)
     const char* lines[4] = {inter, inter, inter, inter};
     i64 lens[4] = {0, 0, 0, 0};
@@ -870,7 +872,8 @@ static int decompress_host(sccg_ctx* c, const char* ref_raw, i64 ref_len, const 
     SCCG_TRY(upload(c, B_ENC, body, nb, &d_enc));
     SCCG_TRY(upload(c, B_NIDX, nline, local_mode ? 0 : nn, &d_n));
     SCCG_TRY(upload(c, B_LOW, low, nl, &d_low));
-    SCCG_TRY(buf(c, B_TGT, (size_t)ref_len + 128, &d_raw));
+    if (d_raw_in) d_raw = const_cast<u8*>(d_raw_in);
+    else SCCG_TRY(buf(c, B_TGT, (size_t)ref_len + 128, &d_raw));
     SCCG_TRY(buf(c, B_REF, (size_t)ref_len + 128, &d_ref));
     const i64 rchunk = pipe_chunk_bytes(ref_len);
     const int n_rch = ref_len > 0 ? (int)((ref_len + rchunk - 1) / rchunk) : 0;
@@ -879,7 +882,7 @@ static int decompress_host(sccg_ctx* c, const char* ref_raw, i64 ref_len, const 
     SCCG_CK(cudaStreamWaitEvent(c->s_h2d, c->ev_pipe[0], 0));
     for (int i = 0; i < n_rch; ++i) {
         const i64 off = (i64)i * rchunk, len = (ref_len - off) < rchunk ? (ref_len - off) : rchunk;
-        SCCG_CK(cudaMemcpyAsync(d_raw + off, ref_raw + off, (size_t)len, cudaMemcpyHostToDevice, c->s_h2d));
+        if (!d_raw_in) SCCG_CK(cudaMemcpyAsync(d_raw + off, ref_raw + off, (size_t)len, cudaMemcpyHostToDevice, c->s_h2d));
         SCCG_CK(cudaEventRecord(c->ev_h2d[i], c->s_h2d));
     }
     SCCG_CK(cudaEventRecord(c->ev[5], c->s_h2d));

@@ -20,19 +20,16 @@ int main(int argc, char* argv[]) {
         if (!std::filesystem::exists(out_dir)) std::filesystem::create_directory(out_dir);
         auto t0 = std::chrono::high_resolution_clock::now();
 
-        std::string file, ref, tgt, header;
-        if (!sccg_host::read_file(ref_path, file)) { std::cerr << "Error opening reference file: " << ref_path << "\n"; return 1; }
-        sccg_host::parse_fasta(file, false, ref, nullptr);
-        if (!sccg_host::read_file(tgt_path, file)) { std::cerr << "Error opening target file: " << tgt_path << "\n"; return 1; }
-        sccg_host::parse_fasta(file, true, tgt, &header);
-        file.clear(); file.shrink_to_fit();
+        // the raw FASTA images go to the GPU as they are: read_genomes_from_files (:181-220) runs there
+        std::string ref_file, tgt_file;
+        if (!sccg_host::read_file(ref_path, ref_file)) { std::cerr << "Error opening reference file: " << ref_path << "\n"; return 1; }
+        if (!sccg_host::read_file(tgt_path, tgt_file)) { std::cerr << "Error opening target file: " << tgt_path << "\n"; return 1; }
 
         const char* dev = getenv("SCCG_DEVICE");
         sccg_ctx* ctx = sccg_create(dev ? atoi(dev) : 0);
         if (!ctx) { std::cerr << "Error: " << sccg_last_error() << "\n"; return 1; }
         char* out = nullptr; int64_t out_len = 0; int mode = 0;
-        int rc = sccg_compress(ctx, ref.data(), (int64_t)ref.size(), tgt.data(), (int64_t)tgt.size(), header.data(), (int64_t)header.size(),
-                               &out, &out_len, &mode);
+        int rc = sccg_compress_fasta(ctx, ref_file.data(), (int64_t)ref_file.size(), tgt_file.data(), (int64_t)tgt_file.size(), &out, &out_len, &mode);
         if (rc != SCCG_OK && rc != SCCG_E_STOI) { std::cerr << "Error: " << sccg_last_error() << "\n"; sccg_destroy(ctx); return 1; }
         sccg_profile prof; sccg_get_profile(ctx, &prof);
 

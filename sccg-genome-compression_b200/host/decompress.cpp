@@ -24,16 +24,16 @@ int main(int argc, char* argv[]) {
         if (system(cmd.c_str()) != 0) { std::cerr << "Greska pri dekompresiji: " << arc << "\n"; exit(1); }
         const std::string inter_path = out_dir + "/" + fs::path(arc).stem().string();   // :43-44
 
-        std::string file, ref, inter;
+        // the raw FASTA image goes to the GPU as it is: header lines and whitespace are removed there (decompression.cpp:47-58)
+        std::string file, inter;
         if (!sccg_host::read_file(ref_path, file)) { std::cerr << "Greska pri otvaranju reference: " << ref_path << "\n"; exit(1); }
-        sccg_host::parse_fasta(file, false, ref, nullptr);
         if (!sccg_host::read_file(inter_path, inter)) { std::cerr << "Greska pri otvaranju datoteke: " << inter_path << "\n"; exit(1); }
 
         const char* dev = getenv("SCCG_DEVICE");
         sccg_ctx* ctx = sccg_create(dev ? atoi(dev) : 0);
         if (!ctx) { std::cerr << "Error: " << sccg_last_error() << "\n"; return 1; }
         char* out = nullptr; int64_t out_len = 0;
-        int rc = sccg_decompress(ctx, ref.data(), (int64_t)ref.size(), inter.data(), (int64_t)inter.size(), &out, &out_len);
+        int rc = sccg_decompress_fasta(ctx, file.data(), (int64_t)file.size(), inter.data(), (int64_t)inter.size(), &out, &out_len);
         if (rc != SCCG_OK) {
             // SCCG_E_BOUNDS: the reference prints the same ERROR and exit(1)s (:223-229); SCCG_E_FORMAT: it dies in stoi (:309-312)
             std::cerr << (rc == SCCG_E_BOUNDS ? "" : "Error during reconstruction: ") << sccg_last_error() << "\n";
