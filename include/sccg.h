@@ -129,6 +129,37 @@ int sccg_compress_fasta(sccg_ctx* ctx, const char* ref_file, int64_t ref_file_le
 int sccg_decompress_fasta(sccg_ctx* ctx, const char* ref_file, int64_t ref_file_len, const char* intermediate, int64_t inter_len,
                           char** out, int64_t* out_len);
 
+/* One chromosome over several GPUs (the local segment-matching path, compression.cpp:381-481, sharded by segment range).
+ * Shard r owns the segment pairs [seg_base, seg_base + n) and is given exactly the matching slices: ref[seg_base*1000 ..),
+ * tgt[seg_base*1000 ..); the last shard's target slice runs to the end of the target.  sccg_shard_match does the matching and
+ * reports the values that cross shard borders; the caller combines the reports of all shards into one sccg_shard_carry per
+ * shard (sccg-genome-compression_b200/sharding.py: plan_carries) and sccg_shard_write then produces the shard's part of the
+ * lowercase-run line and of the body.  Concatenating the parts in shard order (after "<header>\n", with "\n,\n" between the
+ * two lines) gives exactly the file sccg_compress writes.  If any shard reports abort_inside / has_paren, or a border window
+ * aborts, the pair must go through sccg_compress on one GPU (global mode / text-level delta). */
+typedef struct {
+    int64_t n_segments;
+    int32_t abort_inside;       /* T2 abort condition met inside the shard (compression.cpp:462) */
+    int32_t has_paren;          /* the target slice contains '(' */
+    int32_t head_status[4];     /* first 4 segments: bit 0 = increments the T2 counter, bit 1 = can end an abort window */
+    int32_t tail_status[4];     /* last 4 segments, in order */
+    int32_t has_match;          /* at least one match token */
+    int32_t last_p;             /* absolute reference position of the last match token */
+    int64_t n_runs;             /* lowercase runs inside the target slice */
+    int64_t first_run_start, first_run_len, last_run_start, last_run_len;   /* absolute target coordinates */
+} sccg_shard_info;
+typedef struct {
+    int32_t prev_p;             /* p of the last match token of the shards before this one (0: none) */
+    int32_t skip_first_run;     /* the first lowercase run continues a run of the previous shard */
+    int64_t extra_last_len;     /* symbols the following shards add to the last lowercase run */
+    int64_t prev_run_start;     /* start of the last run that begins before this shard (0: none) */
+    int32_t last_run_reaches_end; /* the (lengthened) last run ends at the end of the target */
+    int32_t reserved;
+} sccg_shard_carry;
+int sccg_shard_match(sccg_ctx* ctx, const char* ref_slice, int64_t ref_len, const char* tgt_slice, int64_t tgt_len,
+                     int64_t seg_base, int is_last, sccg_shard_info* info);
+int sccg_shard_write(sccg_ctx* ctx, const sccg_shard_carry* carry, char** low_part, int64_t* low_len, char** body_part, int64_t* body_len);
+
 #ifdef __cplusplus
 }
 #endif

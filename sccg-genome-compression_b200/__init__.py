@@ -44,6 +44,24 @@ class Profile(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class ShardInfo(C.Structure):
+    """sccg_shard_info (include/sccg.h): what one shard reports across its borders"""
+    _fields_ = [("n_segments", C.c_int64), ("abort_inside", C.c_int32), ("has_paren", C.c_int32), ("head_status", C.c_int32 * 4),
+                ("tail_status", C.c_int32 * 4), ("has_match", C.c_int32), ("last_p", C.c_int32), ("n_runs", C.c_int64),
+                ("first_run_start", C.c_int64), ("first_run_len", C.c_int64), ("last_run_start", C.c_int64), ("last_run_len", C.c_int64)]
+
+    def as_dict(self) -> dict:
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["head_status"] = list(self.head_status); d["tail_status"] = list(self.tail_status)
+        return d
+
+
+class ShardCarry(C.Structure):
+    """sccg_shard_carry (include/sccg.h)"""
+    _fields_ = [("prev_p", C.c_int32), ("skip_first_run", C.c_int32), ("extra_last_len", C.c_int64), ("prev_run_start", C.c_int64),
+                ("last_run_reaches_end", C.c_int32), ("reserved", C.c_int32)]
+
+
 @dataclass
 class Record:
     """One element of match_sequences' vector<Position> (compression.cpp:20-24)."""
@@ -86,6 +104,8 @@ def load_library(path: str | os.PathLike | None = None) -> C.CDLL:
     lib.sccg_compress_into.argtypes = [vp, cp, i64, cp, i64, cp, i64, vp, i64, C.POINTER(i64), C.POINTER(C.c_int)]
     lib.sccg_reconstruct_into.argtypes = [vp, cp, i64, cp, i64, cp, i64, cp, i64, vp, i64, C.POINTER(i64)]
     lib.sccg_decompress_into.argtypes = [vp, cp, i64, cp, i64, vp, i64, C.POINTER(i64)]
+    lib.sccg_shard_match.argtypes = [vp, cp, i64, cp, i64, i64, C.c_int, C.POINTER(ShardInfo)]
+    lib.sccg_shard_write.argtypes = [vp, C.POINTER(ShardCarry), C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64)]
     lib.sccg_compress_fasta.argtypes = [vp, cp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_int)]
     lib.sccg_decompress_fasta.argtypes = [vp, cp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64)]
     _libs[key] = lib
@@ -192,6 +212,19 @@ class Context:
         self._check(self.lib.sccg_reconstruct_device(self.handle, d_ref, ref_len, d_enc, enc_len, d_n, n_len, d_low, low_len,
                                                      C.byref(out), C.byref(n)))
         return out.value or 0, n.value
+
+    # one chromosome over several GPUs: segment-range shards (include/sccg.h, sharding.py)
+    def shard_match(self, ref_slice: bytes, tgt_slice: bytes, seg_base: int, is_last: bool) -> dict:
+        info = ShardInfo()
+        self._check(self.lib.sccg_shard_match(self.handle, ref_slice, len(ref_slice), tgt_slice, len(tgt_slice), seg_base, int(is_last), C.byref(info)))
+        return info.as_dict()
+
+    def shard_write(self, carry: dict) -> tuple[bytes, bytes]:
+        """-> (this shard's part of the lowercase-run line, its part of the body)"""
+        cy = ShardCarry(**carry)
+        low = C.c_void_p(); nl = C.c_int64(); body = C.c_void_p(); nb = C.c_int64()
+        self._check(self.lib.sccg_shard_write(self.handle, C.byref(cy), C.byref(low), C.byref(nl), C.byref(body), C.byref(nb)))
+        return self._take(low, nl.value), self._take(body, nb.value)
 
     # read_genomes_from_files on the device + compress_genome (compression.cpp:181-220, :320-579): raw FASTA file images in
     def compress_fasta(self, ref_file: bytes, tgt_file: bytes) -> tuple[bytes, int]:

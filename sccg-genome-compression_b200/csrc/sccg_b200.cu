@@ -4,6 +4,7 @@
 #include "sccg_global.cuh"
 #include "sccg_decode.cuh"
 #include "sccg_fasta.cuh"
+#include "sccg_shard.cuh"
 
 #include <new>
 
@@ -361,6 +362,31 @@ int sccg_decompress_fasta(sccg_ctx* c, const char* ref_file, int64_t ref_file_le
     FastaSeq R;
     SCCG_TRY(fasta_ingest(c, d_rf, ref_file_len, false, B_TGT, B_FA_TMP, B_FA_RNG, sc + S_G7, &R));      // decompression.cpp:47-58
     return decompress_host(c, nullptr, R.len, inter, inter_len, nullptr, 0, out, out_len, R.d_seq);
+}
+
+int sccg_shard_match(sccg_ctx* c, const char* ref_slice, int64_t ref_len, const char* tgt_slice, int64_t tgt_len, int64_t seg_base, int is_last,
+                     sccg_shard_info* info) {
+    if (!c || !info || (ref_len > 0 && !ref_slice) || (tgt_len > 0 && !tgt_slice) || seg_base < 0) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_TRY(check_sizes(ref_len, tgt_len));
+    if ((seg_base + (tgt_len + SEG - 1) / SEG) * SEG >= 0x7fffffffLL) return set_error(SCCG_E_ARG, "sequence length must be in [0, 2^31-1)");
+    SCCG_CK(cudaSetDevice(c->device));
+    prof_reset(c);
+    u8 *d_ref = nullptr, *d_tgt = nullptr;
+    SCCG_TRY(upload(c, B_REF, ref_slice, ref_len, &d_ref));
+    SCCG_TRY(upload(c, B_TGT, tgt_slice, tgt_len, &d_tgt));
+    return shard_match(c, d_ref, ref_len, d_tgt, tgt_len, seg_base, is_last, info);
+}
+
+int sccg_shard_write(sccg_ctx* c, const sccg_shard_carry* carry, char** low_part, int64_t* low_len, char** body_part, int64_t* body_len) {
+    if (!c || !carry || !low_part || !low_len || !body_part || !body_len) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_CK(cudaSetDevice(c->device));
+    u8 *d_low = nullptr, *d_body = nullptr; i64 nl = 0, nb = 0;
+    SCCG_TRY(shard_write(c, carry, &d_low, &nl, &d_body, &nb));
+    SCCG_TRY(download(c, d_low, nl, low_part));
+    int rc = download(c, d_body, nb, body_part);
+    if (rc != SCCG_OK) { free(*low_part); *low_part = nullptr; return rc; }
+    *low_len = nl; *body_len = nb;
+    return SCCG_OK;
 }
 
 #ifdef SCCG_SEG_STATS

@@ -133,7 +133,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
             seg_lo = seg_hi;
         }
         SCCG_CK(cudaEventRecord(c->ev[2], c->stream));
-        LAUNCH(c, seg_bytes_k, dim3(div_up(n_iter, 256)), dim3(256), 0, (const u32*)seginfo, (const u32*)matches, n_iter, seg_bytes, seg_prev, sc + S_ABORT, 0);
+        LAUNCH(c, seg_bytes_k, dim3(div_up(n_iter, 256)), dim3(256), 0, (const u32*)seginfo, (const u32*)matches, n_iter, seg_bytes, seg_prev, sc + S_ABORT, 0, 0, 0);
     } else {
         SCCG_CK(cudaEventRecord(c->ev[2], c->stream));
     }
@@ -162,7 +162,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
     }
     // a '(' somewhere in the target: tokens are written with absolute p and delta_encode is replayed at text level
     if (text_delta && n_iter > 0) {
-        LAUNCH(c, seg_bytes_k, dim3(div_up(n_iter, 256)), dim3(256), 0, (const u32*)seginfo, (const u32*)matches, n_iter, seg_bytes, seg_prev, sc + S_ABORT, 1);
+        LAUNCH(c, seg_bytes_k, dim3(div_up(n_iter, 256)), dim3(256), 0, (const u32*)seginfo, (const u32*)matches, n_iter, seg_bytes, seg_prev, sc + S_ABORT, 1, 0, 0);
         SCCG_TRY(scan_exclusive_u32(c, seg_bytes, seg_bytes, (i64)n_iter, sc + S_BODY_MAIN));
         SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
     }
@@ -182,7 +182,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
         unsigned want = div_up(n_iter, 8 * 32);                              // 8 warps per CTA, 32 segments per warp
         unsigned capg = (unsigned)c->sm_count * 8u;
         LAUNCH(c, seg_write_k, dim3(want < capg ? want : capg), dim3(256), 0, d_tgt, nt, (const u32*)seginfo, (const u32*)matches,
-               (const u32*)seg_bytes, (const int*)seg_prev, n_iter, out, (const u32*)(sc + S_BODY_BASE), text_delta);
+               (const u32*)seg_bytes, (const int*)seg_prev, n_iter, out, (const u32*)(sc + S_BODY_BASE), text_delta, 0);
     }
     if (leftover > 0) {
         unsigned g = div_up(leftover, 256 * 16);

@@ -39,6 +39,11 @@ struct DevBuf { void* p; size_t cap; };
 
 }  // namespace sccg
 
+namespace sccg {
+// what sccg_shard_match leaves behind for sccg_shard_write (the device buffers stay in their slots)
+struct ShardState { int valid; const unsigned char* d_tgt; long long nt; int n_iter; long long seg_base; int is_last; unsigned low_k; long long leftover; };
+}
+
 struct sccg_ctx {
     int device;
     int sm_count;
@@ -57,6 +62,7 @@ struct sccg_ctx {
     cudaStream_t s_h2d, s_d2h;     // copy streams of the pipelined host entry points (created on first use)
     cudaEvent_t ev_pipe[2], ev_h2d[64], ev_g[64];
     int pipe_ready;
+    sccg::ShardState shard;
 };
 
 namespace sccg {

@@ -453,7 +453,8 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
         for (int it = 0; it < 4; ++it) {
             int q = lane + 32 * it;
             u64 rw = nrw[it], tw = ntw[it];
-            if ((rw | tw) & 0x2020202020202020ULL) { rw = upper8(rw); tw = upper8(tw); }   // only bytes with bit 5 can be a-z
+            if (rw & 0x2020202020202020ULL) rw = upper8(rw);                 // only bytes with bit 5 can be a-z
+            if (tw & 0x2020202020202020ULL) tw = upper8(tw);
             reinterpret_cast<u64*>(S.r)[q] = rw;
             reinterpret_cast<u64*>(S.t)[q] = tw;
             u64 diff = rw ^ tw;
@@ -559,7 +560,8 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
 // absolute != 0: tokens carry the absolute p as the reference writes them BEFORE delta_encode (:406-415); used when the
 // text-level delta pass (sccg_delta.cuh) has to reproduce delta_encode on a body that contains literal '('.
 __global__ void seg_bytes_k(const u32* __restrict__ seginfo, const u32* __restrict__ matches, int n_iter,
-                            u32* __restrict__ seg_bytes, int* __restrict__ seg_prev_p, u32* __restrict__ d_abort, int absolute) {
+                            u32* __restrict__ seg_bytes, int* __restrict__ seg_prev_p, u32* __restrict__ d_abort, int absolute,
+                            int seg_base, int carry_prev) {
     int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (i >= n_iter) return;
     if (*d_abort) return;                                    // raised early by seg_match_k: seginfo is incomplete and will be discarded
@@ -580,18 +582,20 @@ __global__ void seg_bytes_k(const u32* __restrict__ seginfo, const u32* __restri
         seg_prev_p[i] = 0;
         return;
     }
-    int prev = 0;                                            // p of the previous match in file order (delta_encode :258)
+    // p of the previous match in file order (delta_encode :258).  seg_base / carry_prev: this launch covers the segments
+    // seg_base .. of a chromosome that is sharded over several GPUs; carry_prev is the last match of the shards before it
+    int prev = carry_prev;
     for (int s = i - 1; s >= 0; --s) {
         u32 x = seginfo[s];
         int nm = (int)SEGINFO_NMATCH(x);
-        if (nm) { prev = s * SEG + (int)((matches[(i64)s * LM_SLOT + nm - 1] >> 10) & 0x3ffu); break; }
+        if (nm) { prev = (s + seg_base) * SEG + (int)((matches[(i64)s * LM_SLOT + nm - 1] >> 10) & 0x3ffu); break; }
     }
     seg_prev_p[i] = prev;
     u32 bytes = SEGINFO_LIT(info);
     int pp = prev;
     for (int m = 0; m < nmatch; ++m) {
         u32 pk = matches[(i64)i * LM_SLOT + m];
-        int p_abs = i * SEG + (int)((pk >> 10) & 0x3ffu);
+        int p_abs = (i + seg_base) * SEG + (int)((pk >> 10) & 0x3ffu);
         bytes += 3u + (u32)dec_len_i32(absolute ? p_abs : p_abs - pp) + (u32)dec_len_u32(pk >> 20);
         pp = p_abs;
     }
@@ -611,7 +615,7 @@ __device__ __forceinline__ int write_token(u8* o, int dp, int l) {
 
 // one segment written by the whole warp (many matches or long literal runs)
 __device__ __forceinline__ void seg_write_coop(const u8* __restrict__ tgt, i64 nt, const u32* __restrict__ matches, int seg, int nmatch,
-                                               u8* __restrict__ base, int prevp, int absolute) {
+                                               u8* __restrict__ base, int prevp, int absolute, int seg_base) {
     const int lane = lane_of();
     const i64 toff = (i64)seg * SEG;
     const int Lt = (int)((nt - toff) < SEG ? (nt - toff) : SEG);
@@ -622,7 +626,7 @@ __device__ __forceinline__ void seg_write_coop(const u8* __restrict__ tgt, i64 n
         bool valid = m < nmatch;
         u32 pk = valid ? matches[(i64)seg * LM_SLOT + m] : 0u;
         int tpos = (int)(pk & 0x3ffu), l = (int)(pk >> 20);
-        int p_abs = seg * SEG + (int)((pk >> 10) & 0x3ffu);
+        int p_abs = (seg + seg_base) * SEG + (int)((pk >> 10) & 0x3ffu);
         int te = tpos + l;
         int pp = __shfl_up_sync(SCCG_FULL_MASK, p_abs, 1);
         int pe = __shfl_up_sync(SCCG_FULL_MASK, te, 1);
@@ -658,7 +662,7 @@ __device__ __forceinline__ void seg_write_coop(const u8* __restrict__ tgt, i64 n
 // literal runs are handed to the whole warp one after the other.
 __global__ void __launch_bounds__(256) seg_write_k(const u8* __restrict__ tgt, i64 nt, const u32* __restrict__ seginfo, const u32* __restrict__ matches,
                                                    const u32* __restrict__ seg_off, const int* __restrict__ seg_prev_p, int n_iter,
-                                                   u8* __restrict__ out, const u32* __restrict__ d_body_base, int absolute) {
+                                                   u8* __restrict__ out, const u32* __restrict__ d_body_base, int absolute, int seg_base) {
     const int lane = lane_of();
     const int warps_total = (int)(gridDim.x * (blockDim.x >> 5));
     u8* body = out + *d_body_base;
@@ -675,7 +679,7 @@ __global__ void __launch_bounds__(256) seg_write_k(const u8* __restrict__ tgt, i
             for (int m = 0; m < nmatch; ++m) {
                 u32 pk = matches[(i64)seg * LM_SLOT + m];
                 int tpos = (int)(pk & 0x3ffu), l = (int)(pk >> 20);
-                int p_abs = seg * SEG + (int)((pk >> 10) & 0x3ffu);
+                int p_abs = (seg + seg_base) * SEG + (int)((pk >> 10) & 0x3ffu);
                 for (int x = pe; x < tpos; ++x) *o++ = upper1(tgt[toff + x]);
                 o += write_token(o, absolute ? p_abs : p_abs - pp, l);
                 pp = p_abs; pe = tpos + l;
@@ -687,7 +691,7 @@ __global__ void __launch_bounds__(256) seg_write_k(const u8* __restrict__ tgt, i
             int src = __ffs((int)heavy) - 1; heavy &= heavy - 1;
             int hseg = seg0 + src;
             int hn = __shfl_sync(SCCG_FULL_MASK, nmatch, src);
-            seg_write_coop(tgt, nt, matches, hseg, hn, body + seg_off[hseg], seg_prev_p[hseg], absolute);
+            seg_write_coop(tgt, nt, matches, hseg, hn, body + seg_off[hseg], seg_prev_p[hseg], absolute, seg_base);
         }
     }
 }

@@ -101,26 +101,46 @@ __device__ __forceinline__ int run_item_bytes(int delta, int len, bool last_at_e
     return 3 + dec_len_i32(delta) + dec_len_i32(len);                       // "(d,len)"
 }
 
-__global__ void runs_bytes_k(const int* __restrict__ run_start, const int* __restrict__ run_end, const u32* __restrict__ d_count, i64 n, u32* __restrict__ bytes) {
+// A run list that is produced in pieces (one target slice per GPU, sccg_shard_*): positions are shifted by pos_off, the
+// first `skip_first` runs of the slice continue a run of the previous slice and are not emitted, the last run is
+// lengthened by what the following slices add to it, the first emitted delta refers to prev_start.  The unsharded
+// paths pass the neutral element.
+struct RunCarry { i64 pos_off; i64 prev_start; i64 extra_last; int skip_first; int reaches_end; };   // reaches_end: -1 = "run ends at n"
+static RunCarry run_carry_none() { RunCarry rc; rc.pos_off = 0; rc.prev_start = 0; rc.extra_last = 0; rc.skip_first = 0; rc.reaches_end = -1; return rc; }
+
+__device__ __forceinline__ bool run_item(const int* __restrict__ run_start, const int* __restrict__ run_end, u32 K, u32 k, i64 n, const RunCarry& rc,
+                                         int* delta, int* len, bool* last_at_end) {
+    if (k < (u32)rc.skip_first) return false;
+    const i64 st = (i64)run_start[k] + rc.pos_off;
+    i64 ln = (i64)run_end[k] - (i64)run_start[k];
+    if (k == K - 1) ln += rc.extra_last;
+    const i64 prev = k > (u32)rc.skip_first ? (i64)run_start[k - 1] + rc.pos_off : rc.prev_start;
+    *delta = (int)(st - prev);
+    *len = (int)ln;
+    *last_at_end = k == K - 1 && (rc.reaches_end < 0 ? (i64)run_end[k] == n : rc.reaches_end != 0);
+    return true;
+}
+
+__global__ void runs_bytes_k(const int* __restrict__ run_start, const int* __restrict__ run_end, const u32* __restrict__ d_count, i64 n, u32* __restrict__ bytes,
+                             RunCarry rc) {
     u32 K = *d_count;
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
-    int st = run_start[k], en = run_end[k];
-    int delta = st - (k ? run_start[k - 1] : 0);
-    bytes[k] = (u32)run_item_bytes(delta, en - st, k == K - 1 && (i64)en == n);
+    int delta, len; bool at_end;
+    bytes[k] = run_item(run_start, run_end, K, k, n, rc, &delta, &len, &at_end) ? (u32)run_item_bytes(delta, len, at_end) : 0u;
 }
 
 __global__ void runs_write_k(const int* __restrict__ run_start, const int* __restrict__ run_end, const u32* __restrict__ d_count, i64 n,
-                             const u32* __restrict__ offs, u8* __restrict__ dst) {
+                             const u32* __restrict__ offs, u8* __restrict__ dst, RunCarry rc) {
     u32 K = *d_count;
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
-    int st = run_start[k], en = run_end[k], len = en - st;
-    int delta = st - (k ? run_start[k - 1] : 0);
+    int delta, len; bool at_end;
+    if (!run_item(run_start, run_end, K, k, n, rc, &delta, &len, &at_end)) return;
     u8* o = dst + offs[k];
     if (len == 1) {
         int w = write_dec_i32(o, delta);
-        if (!(k == K - 1 && (i64)en == n)) o[w] = ',';
+        if (!at_end) o[w] = ',';
     } else {
         int w = 0;
         o[w++] = '(';
@@ -150,18 +170,19 @@ static int rle_count(sccg_ctx* c, const u8* d_src, i64 n, int slot_cnt, int slot
 // the text is written at dst (capacity >= 24 * K).
 template <int MODE>
 static int rle_emit(sccg_ctx* c, const u64* pred_mask, i64 n, u32 K, const u32* cnt_s, const u32* cnt_e, const u32* d_count,
-                    int slot_start, int slot_end, int slot_bytes, int** run_start, int** run_end, u8* dst, u32* d_text_len) {
+                    int slot_start, int slot_end, int slot_bytes, int** run_start, int** run_end, u8* dst, u32* d_text_len,
+                    bool materialise_runs = true, RunCarry rc = run_carry_none()) {
     unsigned ntiles = div_up(n > 0 ? n : 1, RLE_TILE);
     SCCG_TRY(buf(c, slot_start, (size_t)K + 1, run_start));
     SCCG_TRY(buf(c, slot_end, (size_t)K + 1, run_end));
     u32* bytes = nullptr;
     SCCG_TRY(buf(c, slot_bytes, (size_t)K + 1, &bytes));
     if (K == 0) { LAUNCH(c, scan_zero_total_k, dim3(1), dim3(1), 0, d_text_len); return SCCG_OK; }
-    LAUNCH(c, rle_write_k, dim3(ntiles), dim3(RLE_T), 0, pred_mask, n, cnt_s, cnt_e, *run_start, *run_end);
+    if (materialise_runs) LAUNCH(c, rle_write_k, dim3(ntiles), dim3(RLE_T), 0, pred_mask, n, cnt_s, cnt_e, *run_start, *run_end);
     unsigned g = div_up(K, 256);
-    LAUNCH(c, runs_bytes_k, dim3(g), dim3(256), 0, (const int*)*run_start, (const int*)*run_end, d_count, n, bytes);
+    LAUNCH(c, runs_bytes_k, dim3(g), dim3(256), 0, (const int*)*run_start, (const int*)*run_end, d_count, n, bytes, rc);
     SCCG_TRY(scan_exclusive_u32(c, bytes, bytes, (i64)K, d_text_len));
-    if (dst) LAUNCH(c, runs_write_k, dim3(g), dim3(256), 0, (const int*)*run_start, (const int*)*run_end, d_count, n, (const u32*)bytes, dst);
+    if (dst) LAUNCH(c, runs_write_k, dim3(g), dim3(256), 0, (const int*)*run_start, (const int*)*run_end, d_count, n, (const u32*)bytes, dst, rc);
     return SCCG_OK;
 }
 

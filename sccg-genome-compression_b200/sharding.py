@@ -21,6 +21,118 @@ def assign_chromosomes(lengths: list[int], world_size: int) -> list[list[int]]:
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# one chromosome over several GPUs: segment-range shards of the local path
+# ------------------------------------------------------------------------------------------------
+SEG = 1000          # segment length L (compression.cpp:375)
+
+
+def segment_ranges(ref_len: int, tgt_len: int, world_size: int) -> list[tuple[int, int]] | None:
+    """Contiguous ranges [a, b) of segment-pair indices, one per rank (compression.cpp:385-392: n = min(#r, #t) pairs).
+    None if the pair is too small to shard (every shard needs >= 8 pairs so that its border windows do not overlap)."""
+    n_iter = min((ref_len + SEG - 1) // SEG, (tgt_len + SEG - 1) // SEG)
+    if world_size < 2 or n_iter < 8 * world_size:
+        return None
+    base, rem = divmod(n_iter, world_size)
+    out, a = [], 0
+    for r in range(world_size):
+        b = a + base + (1 if r < rem else 0)
+        out.append((a, b))
+        a = b
+    return out
+
+
+def shard_slices(ref: bytes, tgt: bytes, rng: tuple[int, int], is_last: bool) -> tuple[bytes, bytes]:
+    """the slices shard [a, b) needs; the last shard's target slice runs to the end of the target (leftover segments, :476-481)"""
+    a, b = rng
+    return ref[a * SEG:b * SEG], (tgt[a * SEG:] if is_last else tgt[a * SEG:b * SEG])
+
+
+def plan_carries(infos: list[dict], ranges: list[tuple[int, int]], tgt_len: int) -> list[dict] | None:
+    """From the border reports of all shards: the carry of every shard, or None when the pair has to take the unsharded
+    path (T2 abort -> global mode, compression.cpp:462-473; '(' in the target -> text-level delta_encode).  Deterministic:
+    every rank computes the same plan from the all-gathered reports."""
+    world = len(infos)
+    if any(i["abort_inside"] or i["has_paren"] for i in infos):
+        return None
+    # T2 windows that cross a shard border: the counter exceeds 4 at a failed, non-all-N segment whose 4 predecessors all
+    # incremented it (:417-424, :454-462).  Every shard has >= 8 segments, so a window touches at most two shards.
+    for r in range(1, world):
+        seq = infos[r - 1]["tail_status"] + infos[r]["head_status"]
+        for e in range(4, 8):
+            if (seq[e] & 2) and all(seq[x] & 1 for x in range(e - 4, e + 1)):
+                return None
+    starts = [a * SEG for a, _ in ranges]
+    ends = [b * SEG for _, b in ranges[:-1]] + [tgt_len]
+    touches_start = [i["n_runs"] > 0 and i["first_run_start"] == starts[r] for r, i in enumerate(infos)]
+    touches_end = [i["n_runs"] > 0 and i["last_run_start"] + i["last_run_len"] == ends[r] for r, i in enumerate(infos)]
+    whole = [infos[r]["n_runs"] == 1 and touches_start[r] and touches_end[r] for r in range(world)]
+    skip = [r > 0 and touches_start[r] and touches_end[r - 1] for r in range(world)]
+
+    def cont_reaches_end(q: int) -> bool:          # a run that enters shard q at its first symbol runs to the end of the target
+        while True:
+            if not (touches_start[q] and whole[q]):
+                return False
+            if q == world - 1:
+                return True
+            q += 1
+
+    carries = []
+    for r in range(world):
+        prev_p = 0
+        for q in range(r - 1, -1, -1):
+            if infos[q]["has_match"]:
+                prev_p = infos[q]["last_p"]
+                break
+        extra = 0
+        if touches_end[r]:
+            q = r + 1
+            while q < world and touches_start[q]:
+                extra += infos[q]["first_run_len"]
+                if not whole[q]:
+                    break
+                q += 1
+        prev_run_start = 0
+        for q in range(r - 1, -1, -1):
+            if infos[q]["n_runs"] - (1 if skip[q] else 0) > 0:     # shard q starts at least one run of its own
+                prev_run_start = infos[q]["last_run_start"]
+                break
+        reaches = touches_end[r] and (r == world - 1 or cont_reaches_end(r + 1))
+        carries.append({"prev_p": prev_p, "skip_first_run": int(skip[r]), "extra_last_len": extra, "prev_run_start": prev_run_start,
+                        "last_run_reaches_end": int(reaches), "reserved": 0})
+    return carries
+
+
+last_path = ""          # "sharded" / "unsharded": which way the most recent compress_sharded call went (tests, logs)
+
+
+def compress_sharded(ctx, ref: bytes, tgt: bytes, header: bytes) -> tuple[bytes, int] | None:
+    """compress_genome for ONE pair with the segment pairs spread over all ranks of the default process group (one GPU /
+    sccg context per rank).  Every rank passes the same pair but only touches -- and only uploads -- its own slices.
+    Returns (compressed_genome.txt image, mode) on rank 0 and None elsewhere.  Pairs that leave the local path (T2 abort,
+    '(' in the target) or are too small to shard are compressed by rank 0 alone."""
+    global last_path
+    world, rank = dist.get_world_size(), dist.get_rank()
+    ranges = segment_ranges(len(ref), len(tgt), world)
+    carries = None
+    if ranges is not None:
+        r_slice, t_slice = shard_slices(ref, tgt, ranges[rank], rank == world - 1)
+        info = ctx.shard_match(r_slice, t_slice, ranges[rank][0], rank == world - 1)
+        infos: list = [None] * world
+        dist.all_gather_object(infos, info)                         # a few dozen bytes per rank: the only exchange
+        carries = plan_carries(infos, ranges, len(tgt))
+    if carries is None:                                             # unsharded fallback on rank 0
+        last_path = "unsharded"
+        return ctx.compress(ref, tgt, header) if rank == 0 else None
+    last_path = "sharded"
+    low, body = ctx.shard_write(carries[rank])
+    parts = gather_streams({2 * rank: low, 2 * rank + 1: body}, dst=0)      # only the encoded streams travel
+    if rank != 0:
+        return None
+    text = (header + b"\n" if header else b"") + b"".join(parts[2 * r] for r in range(world)) + b"\n,\n" + b"".join(parts[2 * r + 1] for r in range(world))
+    return text, 0
+
+
 def _device_for_backend() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 
