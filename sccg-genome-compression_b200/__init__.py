@@ -73,6 +73,13 @@ class Record:
         return f"({self.p},{self.l})" if not self.lit else f"lit[{len(self.lit)}]{self.lit[:24]!r}"
 
 
+def _as_char_p(buf):
+    """bytes stay as they are; numpy uint8 arrays are passed by address (no copy)"""
+    if isinstance(buf, (bytes, bytearray)):
+        return bytes(buf) if isinstance(buf, bytearray) else buf
+    return C.cast(buf.ctypes.data, C.c_char_p) if len(buf) else b""
+
+
 _libs: dict[str, C.CDLL] = {}
 
 
@@ -163,9 +170,10 @@ class Context:
         return buf.raw[:n]
 
     # compress_genome minus file I/O and 7z (compression.cpp:320-579)
-    def compress(self, ref: bytes, tgt: bytes, header: bytes = b"") -> tuple[bytes, int]:
+    def compress(self, ref, tgt, header: bytes = b"") -> tuple[bytes, int]:
+        """ref / tgt: bytes or C-contiguous uint8 numpy arrays (zero-copy)"""
         out = C.c_void_p(); n = C.c_int64(); mode = C.c_int()
-        rc = self.lib.sccg_compress(self.handle, ref, len(ref), tgt, len(tgt), header, len(header), C.byref(out), C.byref(n), C.byref(mode))
+        rc = self.lib.sccg_compress(self.handle, _as_char_p(ref), len(ref), _as_char_p(tgt), len(tgt), header, len(header), C.byref(out), C.byref(n), C.byref(mode))
         if rc == SCCG_E_STOI:
             raise SccgError(rc, self.lib.sccg_last_error().decode(), self._take(out, n.value))
         self._check(rc)
@@ -214,9 +222,11 @@ class Context:
         return out.value or 0, n.value
 
     # one chromosome over several GPUs: segment-range shards (include/sccg.h, sharding.py)
-    def shard_match(self, ref_slice: bytes, tgt_slice: bytes, seg_base: int, is_last: bool) -> dict:
+    def shard_match(self, ref_slice, tgt_slice, seg_base: int, is_last: bool) -> dict:
+        """ref_slice / tgt_slice: bytes, or C-contiguous uint8 numpy arrays (zero-copy; pin them for full PCIe speed)"""
         info = ShardInfo()
-        self._check(self.lib.sccg_shard_match(self.handle, ref_slice, len(ref_slice), tgt_slice, len(tgt_slice), seg_base, int(is_last), C.byref(info)))
+        self._check(self.lib.sccg_shard_match(self.handle, _as_char_p(ref_slice), len(ref_slice), _as_char_p(tgt_slice), len(tgt_slice),
+                                              seg_base, int(is_last), C.byref(info)))
         return info.as_dict()
 
     def shard_write(self, carry: dict) -> tuple[bytes, bytes]:

@@ -42,7 +42,7 @@ def segment_ranges(ref_len: int, tgt_len: int, world_size: int) -> list[tuple[in
     return out
 
 
-def shard_slices(ref: bytes, tgt: bytes, rng: tuple[int, int], is_last: bool) -> tuple[bytes, bytes]:
+def shard_slices(ref, tgt, rng: tuple[int, int], is_last: bool):
     """the slices shard [a, b) needs; the last shard's target slice runs to the end of the target (leftover segments, :476-481)"""
     a, b = rng
     return ref[a * SEG:b * SEG], (tgt[a * SEG:] if is_last else tgt[a * SEG:b * SEG])
@@ -118,8 +118,7 @@ def compress_sharded(ctx, ref: bytes, tgt: bytes, header: bytes) -> tuple[bytes,
     if ranges is not None:
         r_slice, t_slice = shard_slices(ref, tgt, ranges[rank], rank == world - 1)
         info = ctx.shard_match(r_slice, t_slice, ranges[rank][0], rank == world - 1)
-        infos: list = [None] * world
-        dist.all_gather_object(infos, info)                         # a few dozen bytes per rank: the only exchange
+        infos = _all_gather_infos(info, world)                      # 20 integers per rank: the only exchange before the write
         carries = plan_carries(infos, ranges, len(tgt))
     if carries is None:                                             # unsharded fallback on rank 0
         last_path = "unsharded"
@@ -131,6 +130,23 @@ def compress_sharded(ctx, ref: bytes, tgt: bytes, header: bytes) -> tuple[bytes,
         return None
     text = (header + b"\n" if header else b"") + b"".join(parts[2 * r] for r in range(world)) + b"\n,\n" + b"".join(parts[2 * r + 1] for r in range(world))
     return text, 0
+
+
+_INFO_KEYS = ["n_segments", "abort_inside", "has_paren", "has_match", "last_p", "n_runs", "first_run_start", "first_run_len", "last_run_start", "last_run_len"]
+
+
+def _all_gather_infos(info: dict, world: int) -> list[dict]:
+    dev = _device_for_backend()
+    mine = torch.tensor([info[k] for k in _INFO_KEYS] + list(info["head_status"]) + list(info["tail_status"]), dtype=torch.int64, device=dev)
+    allv = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    out = []
+    for v in allv:
+        v = v.cpu().tolist()
+        d = dict(zip(_INFO_KEYS, v[:len(_INFO_KEYS)]))
+        d["head_status"] = v[len(_INFO_KEYS):len(_INFO_KEYS) + 4]; d["tail_status"] = v[len(_INFO_KEYS) + 4:len(_INFO_KEYS) + 8]
+        out.append(d)
+    return out
 
 
 def _device_for_backend() -> torch.device:
