@@ -135,6 +135,25 @@ __device__ __forceinline__ int lane_lcp(const u8* r, int p, const u8* t, int j, 
     return l < maxl ? l : maxl;
 }
 
+__device__ __forceinline__ u32 mad_u32(u32 a, u32 b, u32 c) {
+#if defined(__CUDA_ARCH__)
+    u32 d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));   // one IMAD (the compiler would emit shift + add for b = 2^s)
+    return d;
+#else
+    return a * b + c;
+#endif
+}
+// r[p..p+k) == t[j..j+k)  (k <= 32, both in shared memory with >= 8 bytes of slack)
+__device__ __forceinline__ bool kmer_equal_smem(const u8* r, int p, const u8* t, int j, int k) {
+    for (int o = 0; o < k; o += 4) {
+        u32 d = ld_unaligned32(r, p + o) ^ ld_unaligned32(t, j + o);
+        if (k - o < 4) d &= (1u << (8 * (k - o))) - 1u;
+        if (d) return false;
+    }
+    return true;
+}
+
 // running state of the candidate fold (compression.cpp:114-130 as an order-independent reduction):
 // longest length; among the longest: how many, is p == 0 among them, and min (|p - e| << 16 | p) over p != 0
 struct LmFold { int best_l; int cnt; bool zero_in; u32 best_key; };
@@ -155,8 +174,33 @@ __device__ __forceinline__ void lm_fold_one(LmFold& f, int p, int l, int e) {
 __device__ __forceinline__ int lm_parse(LmWarpSmem& S, const u32 (&wm)[4], int Lr, int Lt, int k, u32 powk) {
     const int Lmin = Lr < Lt ? Lr : Lt;
     const int lane = lane_of();
-    int j = 0, e = -1, nmatch = 0;
+    int j = 0, e = -1, nmatch = 0, misses = 0;
+    const u32 mul = 1u << lm_hash_shift(k);
     while (j < Lt - k + 1) {                                                     // :64
+#ifndef SCCG_NO_LOOKAHEAD
+        if (misses >= 2) {
+            // look-ahead after two literal steps in a row: lane x probes position j + x on its own (hash, bucket, chain,
+            // full k-mer compare).  Positions before the first one that has a candidate are literal steps (:77-81), so
+            // they are skipped 32 at a time; segments without any match (and the literal stretches of divergent ones)
+            // cost 1/32 of the lock-step walk.  (Near-identical segments never get here: one miss per substitution.)
+            const int jj = j + lane;
+            bool hit = false;
+            if (jj < Lt - k + 1) {
+                u32 h = 0u;
+                for (int x = 0; x < k; ++x) h = mad_u32(h, mul, S.t[jj + x]);
+                const u32 hm = lm_mix(h);
+                const u32 qt = lm_tag(hm), t4 = ld_unaligned32(S.t, jj);
+                for (u32 c = S.head[lm_bucket(hm)]; c && !hit;) {
+                    const int p = (int)(c & 0x3ffu) - 1;
+                    if ((c & 0xfc00u) == qt && ld_unaligned32(S.r, p) == t4 && kmer_equal_smem(S.r, p, S.t, jj, k)) hit = true;
+                    c = S.next[p];
+                }
+            }
+            const u32 bal = __ballot_sync(SCCG_FULL_MASK, hit);
+            if (!bal) { j += 32; continue; }
+            j += __ffs((int)bal) - 1;
+        }
+#endif
         u32 term = lane < k ? (u32)S.t[j + lane] * powk : 0u;
         u32 hm = lm_mix(__reduce_add_sync(SCCG_FULL_MASK, term));
         u32 c = S.head[lm_bucket(hm)];
@@ -203,7 +247,8 @@ __device__ __forceinline__ int lm_parse(LmWarpSmem& S, const u32 (&wm)[4], int L
                 }
             }
         }
-        if (f.best_l == 0) { ++j; continue; }                                    // :77-81 literal
+        if (f.best_l == 0) { ++j; ++misses; continue; }                          // :77-81 literal
+        misses = 0;
         // p = 0 survives only when it is the single longest candidate (`pn1 == 0` is "unset", :125)
         int p_sel = (f.cnt == 1 && f.zero_in) ? 0 : (int)(f.best_key & 0xffffu);
         if (lane == 0) S.mlist[nmatch] = (u32)j | ((u32)p_sel << 10) | ((u32)f.best_l << 20);
@@ -236,25 +281,6 @@ static const int DV_QPOS = 512;               // S.next[DV_QPOS + slot]: (window
 // slot of the looked-up-window table: bits 9..17 of the rolling hash mix the last five symbols; slot quality only decides
 // how often two windows collide (-> generic path), never correctness
 __device__ __forceinline__ u32 dv_slot(u32 h) { return (h >> 9) & (u32)(LM_HT - 1); }
-__device__ __forceinline__ u32 mad_u32(u32 a, u32 b, u32 c) {
-#if defined(__CUDA_ARCH__)
-    u32 d;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));   // one IMAD (the compiler would emit shift + add for b = 2^s)
-    return d;
-#else
-    return a * b + c;
-#endif
-}
-// r[p..p+k) == t[j..j+k)  (k <= 32, both in shared memory with >= 8 bytes of slack)
-__device__ __forceinline__ bool kmer_equal_smem(const u8* r, int p, const u8* t, int j, int k) {
-    for (int o = 0; o < k; o += 4) {
-        u32 d = ld_unaligned32(r, p + o) ^ ld_unaligned32(t, j + o);
-        if (k - o < 4) d &= (1u << (8 * (k - o))) - 1u;
-        if (d) return false;
-    }
-    return true;
-}
-
 // returns the number of matches (stored in S.mlist), or 0 when the hypothesis was rejected / not applicable.
 // head_clean (in/out): S.head is all zero.
 __device__ __forceinline__ int lm_diag_parse(LmWarpSmem& S, const u32 (&wm)[4], int L, int k, bool& head_clean) {
@@ -466,14 +492,18 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
         if (++claimed_used >= SCCG_LM_CLAIM) {
             if (lane == 0) {
                 next_seg = (int)atomicAdd(work_counter, 1u) * SCCG_LM_CLAIM + claim_base;
-#ifndef SCCG_NO_EARLY_ABORT
-                // the abort flag lives in its own cache line: reads must not queue behind the claim atomics
-                if (abort_flag && __ldcg(abort_flag)) next_seg = n_iter;
-#endif
             }
             claimed_used = 0;
             next_seg = __shfl_sync(SCCG_FULL_MASK, next_seg, 0);
         }
+#ifndef SCCG_NO_EARLY_ABORT
+        // checked before every segment (the flag lives in its own cache line, away from the claim atomics): a failing
+        // segment is expensive, and after the abort nothing of this launch is used (:466-472)
+        if (abort_flag) {
+            u32 stop = lane == 0 ? __ldcg(abort_flag) : 0u;                   // one lane reads, all lanes agree
+            if (__shfl_sync(SCCG_FULL_MASK, stop, 0)) next_seg = n_iter;
+        }
+#endif
         lm_fetch(ref, nr, tgt, nt, next_seg, n_iter, lane, nrw, ntw);
         if (lane < 2) reinterpret_cast<u64*>(S.r)[128 + lane] = 0ull, reinterpret_cast<u64*>(S.t)[128 + lane] = 0ull;
         __syncwarp();
@@ -495,6 +525,12 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
             for (int pass = 0; pass < 2; ++pass) {
                 const int k = pass ? k2 : k1;
                 if (k <= 0) break;
+#ifndef SCCG_NO_EARLY_ABORT
+                if (abort_flag) {                                                     // the launch is being discarded: do not start an expensive pass
+                    u32 stop = lane == 0 ? __ldcg(abort_flag) : 0u;
+                    if (__shfl_sync(SCCG_FULL_MASK, stop, 0)) break;
+                }
+#endif
                 if (pass) SEG_STAT(3);
                 lm_build_index(S, Lr, k);
                 nmatch = lm_parse(S, wm, Lr, Lt, k, pass ? pow2 : pow1);
