@@ -43,6 +43,19 @@ def ncu_traffic(kernel: str):
         return None
 
 
+def bind_to_gpu_numa_node(index: int) -> str:
+    """Pins this process to the CPUs closest to its GPU (NVML's ideal affinity) so that the page-locked host buffers of the
+    end-to-end legs live on that NUMA node; with 8 ranks the PCIe copies otherwise cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return f"{len(os.sched_getaffinity(0))} cpus"
+    except Exception as e:                               # no NVML / not permitted: run unbound
+        return f"unbound ({type(e).__name__})"
+
+
 def peaks() -> tuple[float, str]:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -218,6 +231,7 @@ def main() -> None:
     import sccg_b200
 
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)             # before any page-locked allocation: first touch puts the buffers next to the GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -342,6 +356,7 @@ def main() -> None:
             "config": {"workload": workload_name(args.size), "bp_per_gpu": nt, "sharding": "one chromosome-sized pair per GPU, no data-path collective",
                        "l2": "inputs (2 x 249 MB) larger than the 126 MB L2, no flush needed", "timing": "CUDA events on the library stream, max over ranks",
                        "concurrency": "the lowercase-run kernels run on a side stream underneath seg_match_k (its kernel_ms includes that sharing)",
+                       "cpu_affinity": numa,
                        "encoded_bytes": enc_len, "mode": "local"},
             "wall_ms_per_step": comp_wall_ms,
             "decompress": {"value": world * nt / (dec_ms / 1e3) / 1e9, "unit": "Gbp/s", "ms_per_step": dec_ms,
