@@ -120,6 +120,13 @@ int sccg_reconstruct_into(sccg_ctx* ctx, const char* ref, int64_t ref_len, const
 int sccg_decompress_into(sccg_ctx* ctx, const char* ref_raw, int64_t ref_len, const char* intermediate, int64_t inter_len,
                          char* out, int64_t out_cap, int64_t* out_len);
 
+/* Output-range sharding of decompression over several GPUs: the part-th of n_parts contiguous pieces of the file image that
+ * sccg_decompress would produce.  out receives the piece, *part_offset its offset inside the image, *part_len its length and
+ * *total_len the length of the whole image.  Only the reference chunks the piece copies from are uploaded (local-mode files),
+ * so N GPUs share the PCIe traffic of one pair; the pieces can be written straight to their offsets of the output file. */
+int sccg_decompress_part(sccg_ctx* ctx, const char* ref_raw, int64_t ref_len, const char* intermediate, int64_t inter_len,
+                         int part, int n_parts, char* out, int64_t out_cap, int64_t* part_offset, int64_t* part_len, int64_t* total_len);
+
 /* FASTA file images in: read_genomes_from_files (compression.cpp:181-220) and the reference reader of decompress_genome
  * (decompression.cpp:47-58) run on the device -- header lines skipped ('>' at a line start; in the target only the first one,
  * which becomes the header line of the output), isspace() bytes removed -- followed by sccg_compress / sccg_decompress.

@@ -111,6 +111,7 @@ def load_library(path: str | os.PathLike | None = None) -> C.CDLL:
     lib.sccg_compress_into.argtypes = [vp, cp, i64, cp, i64, cp, i64, vp, i64, C.POINTER(i64), C.POINTER(C.c_int)]
     lib.sccg_reconstruct_into.argtypes = [vp, cp, i64, cp, i64, cp, i64, cp, i64, vp, i64, C.POINTER(i64)]
     lib.sccg_decompress_into.argtypes = [vp, cp, i64, cp, i64, vp, i64, C.POINTER(i64)]
+    lib.sccg_decompress_part.argtypes = [vp, cp, i64, cp, i64, C.c_int, C.c_int, vp, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     lib.sccg_shard_match.argtypes = [vp, cp, i64, cp, i64, i64, C.c_int, C.POINTER(ShardInfo)]
     lib.sccg_shard_write.argtypes = [vp, C.POINTER(ShardCarry), C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64)]
     lib.sccg_compress_fasta.argtypes = [vp, cp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_int)]
@@ -220,6 +221,20 @@ class Context:
         self._check(self.lib.sccg_reconstruct_device(self.handle, d_ref, ref_len, d_enc, enc_len, d_n, n_len, d_low, low_len,
                                                      C.byref(out), C.byref(n)))
         return out.value or 0, n.value
+
+    def decompress_part(self, ref_raw, intermediate: bytes, part: int, n_parts: int, out_ptr: int = 0, out_cap: int = 0):
+        """the part-th of n_parts pieces of the reconstructed file image -> (offset in the image, piece, total length);
+        with out_ptr / out_cap the piece is written into the caller's (page-locked) buffer and its length is returned instead"""
+        off = C.c_int64(); n = C.c_int64(); total = C.c_int64()
+        if out_ptr:
+            self._check(self.lib.sccg_decompress_part(self.handle, _as_char_p(ref_raw), len(ref_raw), intermediate, len(intermediate), part, n_parts,
+                                                      out_ptr, out_cap, C.byref(off), C.byref(n), C.byref(total)))
+            return off.value, n.value, total.value
+        cap = len(ref_raw) * 2 + len(intermediate) * 2 + 4096            # generous: a piece is at most the whole image
+        buf = C.create_string_buffer(cap)
+        self._check(self.lib.sccg_decompress_part(self.handle, _as_char_p(ref_raw), len(ref_raw), intermediate, len(intermediate), part, n_parts,
+                                                  C.cast(buf, C.c_void_p), cap, C.byref(off), C.byref(n), C.byref(total)))
+        return off.value, buf.raw[:n.value], total.value
 
     # one chromosome over several GPUs: segment-range shards (include/sccg.h, sharding.py)
     def shard_match(self, ref_slice, tgt_slice, seg_base: int, is_last: bool) -> dict:

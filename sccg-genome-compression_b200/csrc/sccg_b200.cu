@@ -396,6 +396,23 @@ int sccg_debug_seg_stats(unsigned long long* out8, int reset) {
     return 0;
 }
 #endif
+int sccg_decompress_part(sccg_ctx* c, const char* ref_raw, int64_t ref_len, const char* inter, int64_t inter_len, int part, int n_parts,
+                         char* out, int64_t out_cap, int64_t* part_offset, int64_t* part_len, int64_t* total_len) {
+    if (!c || !out || !part_offset || !part_len || !total_len || (ref_len > 0 && !ref_raw) || (inter_len > 0 && !inter)) return set_error(SCCG_E_ARG, "null argument");
+    if (n_parts < 1 || part < 0 || part >= n_parts) return set_error(SCCG_E_ARG, "part index out of range");
+    SCCG_TRY(check_sizes(ref_len, inter_len));
+    SCCG_CK(cudaSetDevice(c->device));
+    prof_reset(c);
+    if (n_parts == 1) {
+        *part_offset = 0;
+        int rc = decompress_host(c, ref_raw, ref_len, inter, inter_len, out, out_cap, nullptr, part_len);
+        *total_len = *part_len;
+        return rc;
+    }
+    PartSpec ps; ps.part = part; ps.n_parts = n_parts; ps.part_off = part_offset; ps.total_len = total_len;
+    return decompress_host(c, ref_raw, ref_len, inter, inter_len, out, out_cap, nullptr, part_len, nullptr, &ps);
+}
+
 #ifdef SCCG_SEG_TIMING
 int sccg_debug_seg_timing(void* d_cycles) {
     unsigned long long* p = (unsigned long long*)d_cycles;

@@ -815,14 +815,16 @@ __device__ __forceinline__ i64 out_byte_of_sym(const GatherArgs& a, i64 s) {
     return b + b / WRAP;
 }
 // need_hi[j] = one past the last reference symbol that the tokens feeding output chunk j copy from
-__global__ void dec_need_k(GatherArgs a, const int* __restrict__ tok_len, i64 chunk_bytes, u32* __restrict__ need_hi) {
+// need_lo[j]: the first one (0xffffffff: chunk j copies nothing from the reference)
+__global__ void dec_need_k(GatherArgs a, const int* __restrict__ tok_len, i64 chunk_bytes, u32* __restrict__ need_hi, u32* __restrict__ need_lo) {
     const int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    u32 hi = 0;
+    u32 hi = 0, lo = 0xffffffffu;
     i64 c0 = -1, c1 = -2;
     if (k < a.nseg) {
         const i64 src = a.seg_src[k];
         const i64 s0 = a.seg_dst[k], s1 = k + 1 < a.nseg ? (i64)a.seg_dst[k + 1] : a.Ls;
         if (!(src & SEG_LIT_FLAG) && s1 > s0) {
+            lo = (u32)a.tok_abs[src];
             hi = (u32)((i64)a.tok_abs[src] + (i64)tok_len[src]);
             c0 = out_byte_of_sym(a, s0) / chunk_bytes; c1 = out_byte_of_sym(a, s1 - 1) / chunk_bytes;
         }
@@ -831,10 +833,11 @@ __global__ void dec_need_k(GatherArgs a, const int* __restrict__ tok_len, i64 ch
     const i64 cw = (i64)__reduce_max_sync(SCCG_FULL_MASK, (int)c0);           // chunk of the token segments of this warp (-1: none)
     if (__all_sync(SCCG_FULL_MASK, (c0 == cw && c1 == cw) || c1 < c0)) {
         const u32 m = __reduce_max_sync(SCCG_FULL_MASK, hi);
-        if (lane_of() == 0 && cw >= 0 && m) atomicMax(&need_hi[cw], m);
+        const u32 mlo = __reduce_min_sync(SCCG_FULL_MASK, lo);
+        if (lane_of() == 0 && cw >= 0 && m) { atomicMax(&need_hi[cw], m); atomicMin(&need_lo[cw], mlo); }
         return;
     }
-    for (i64 cj = c0; cj <= c1; ++cj) atomicMax(&need_hi[cj], hi);
+    for (i64 cj = c0; cj <= c1; ++cj) { atomicMax(&need_hi[cj], hi); atomicMin(&need_lo[cj], lo); }
 }
 
 static const int PIPE_MAX_CHUNKS = 64;
@@ -842,8 +845,24 @@ static const int PIPE_MAX_CHUNKS = 64;
 
 // decompress_genome's in-memory part (decompression.cpp:66-110) + reconstruct_genome + main's "<header>\n" (:322)
 // d_raw_in != NULL: the raw reference symbols are already in device memory (FASTA ingest on the device); ref_raw is unused then
+// part / n_parts (n_parts > 1): only the part-th of n_parts contiguous pieces of the file image is produced -- output-range
+// sharding over several GPUs: dst receives the piece, *part_off its offset in the image, *out_len its length,
+// *total_len the length of the whole image; only the reference chunks that piece copies from are uploaded.
+struct PartSpec { int part, n_parts; int64_t* part_off; int64_t* total_len; };
+static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, const char* inter, i64 inter_len, char* dst, i64 dst_cap, char** out, int64_t* out_len,
+                                const u8* d_raw_in, const PartSpec* ps);
 static int decompress_host(sccg_ctx* c, const char* ref_raw, i64 ref_len, const char* inter, i64 inter_len, char* dst, i64 dst_cap, char** out, int64_t* out_len,
-                           const u8* d_raw_in = nullptr) {
+                           const u8* d_raw_in = nullptr, const PartSpec* ps = nullptr) {
+    const int rc = decompress_host_impl(c, ref_raw, ref_len, inter, inter_len, dst, dst_cap, out, out_len, d_raw_in, ps);
+    if (rc != SCCG_OK && c->pipe_ready) {
+        // an error return must not leave copies from / into the caller's buffers in flight
+        cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_d2h); cudaStreamSynchronize(c->main_stream);
+    }
+    return rc;
+}
+static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, const char* inter, i64 inter_len, char* dst, i64 dst_cap, char** out, int64_t* out_len,
+                                const u8* d_raw_in, const PartSpec* ps) {
+    const bool parts = ps && ps->n_parts > 1;
     // ---- the 3 / 4 getline calls (:66-101)
     const char* lines[4] = {inter, inter, inter, inter};
     i64 lens[4] = {0, 0, 0, 0};
@@ -877,15 +896,25 @@ static int decompress_host(sccg_ctx* c, const char* ref_raw, i64 ref_len, const 
     SCCG_TRY(buf(c, B_REF, (size_t)ref_len + 128, &d_ref));
     const i64 rchunk = pipe_chunk_bytes(ref_len);
     const int n_rch = ref_len > 0 ? (int)((ref_len + rchunk - 1) / rchunk) : 0;
-    if (getenv("SCCG_PIPE_POISON")) SCCG_CK(cudaMemsetAsync(d_ref, 0xEE, (size_t)ref_len, c->stream));   // tests: a chunk used before it was prepared shows up
+    if (getenv("SCCG_PIPE_POISON")) {                                        // tests: a chunk used before it was uploaded / prepared shows up
+        SCCG_CK(cudaMemsetAsync(d_ref, 0xEE, (size_t)ref_len, c->stream));
+        if (!d_raw_in) SCCG_CK(cudaMemsetAsync(d_raw, 0xEE, (size_t)ref_len, c->stream));
+    }
     SCCG_CK(cudaEventRecord(c->ev_pipe[0], c->stream));                      // buffers may have been (re)allocated: order the copy stream after it
     SCCG_CK(cudaStreamWaitEvent(c->s_h2d, c->ev_pipe[0], 0));
-    for (int i = 0; i < n_rch; ++i) {
-        const i64 off = (i64)i * rchunk, len = (ref_len - off) < rchunk ? (ref_len - off) : rchunk;
-        if (!d_raw_in) SCCG_CK(cudaMemcpyAsync(d_raw + off, ref_raw + off, (size_t)len, cudaMemcpyHostToDevice, c->s_h2d));
-        SCCG_CK(cudaEventRecord(c->ev_h2d[i], c->s_h2d));
+    auto enqueue_ref = [&](int i0, int i1) -> int {                          // reference chunks [i0, i1) -> device, one event each
+        for (int i = i0; i < i1; ++i) {
+            const i64 off = (i64)i * rchunk, len = (ref_len - off) < rchunk ? (ref_len - off) : rchunk;
+            if (!d_raw_in) SCCG_CK(cudaMemcpyAsync(d_raw + off, ref_raw + off, (size_t)len, cudaMemcpyHostToDevice, c->s_h2d));
+            SCCG_CK(cudaEventRecord(c->ev_h2d[i], c->s_h2d));
+        }
+        return SCCG_OK;
+    };
+    const bool defer_upload = parts && local_mode;                            // a piece of a local-mode file needs a piece of the reference only
+    if (!defer_upload) {
+        SCCG_TRY(enqueue_ref(0, n_rch));
+        SCCG_CK(cudaEventRecord(c->ev[5], c->s_h2d));
     }
-    SCCG_CK(cudaEventRecord(c->ev[5], c->s_h2d));
     u32* sc = nullptr;
     SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
     // ---- reference preparation (:105-110): global mode erases every N (needs the whole reference), local mode only upper-cases
@@ -909,8 +938,11 @@ static int decompress_host(sccg_ctx* c, const char* ref_raw, i64 ref_len, const 
     // ---- result buffer
     const i64 full = n + nh + 1;
     *out_len = full;
+    if (parts) *ps->total_len = full;
     char* h_dst = dst;
-    if (!dst) {
+    if (parts) {
+        if (!dst) return set_error(SCCG_E_ARG, "null argument");
+    } else if (!dst) {
         h_dst = (char*)malloc((size_t)full + 1);
         if (!h_dst) return set_error(SCCG_E_NOMEM, "malloc of the result failed");
         h_dst[full] = 0;
@@ -920,21 +952,45 @@ static int decompress_host(sccg_ctx* c, const char* ref_raw, i64 ref_len, const 
     // ---- which part of the reference does every output chunk need?
     const unsigned tiles_per_chunk = pipe_tiles_per_chunk(plan.ntiles);
     const int n_och = (int)((plan.ntiles + tiles_per_chunk - 1) / tiles_per_chunk);
-    u32 need[PIPE_MAX_CHUNKS];
-    for (int j = 0; j < n_och; ++j) need[j] = 0xffffffffu;
-    if (local_mode && plan.a.nseg > 0 && n_och > 1) {
-        u32* d_need = sc + D_COUNT;                                          // PIPE_MAX_CHUNKS scalars after the decode scalars
+    u32 need[PIPE_MAX_CHUNKS], need_lo[PIPE_MAX_CHUNKS];
+    for (int j = 0; j < n_och; ++j) { need[j] = 0xffffffffu; need_lo[j] = 0u; }
+    if (local_mode && plan.a.nseg > 0 && (n_och > 1 || parts)) {
+        u32* d_need = nullptr;                                               // [0, 64): need_hi, [64, 128): need_lo
+        SCCG_TRY(buf(c, B_NEED, 2 * PIPE_MAX_CHUNKS, &d_need));
         SCCG_CK(cudaMemsetAsync(d_need, 0, sizeof(u32) * PIPE_MAX_CHUNKS, c->stream));
-        LAUNCH(c, dec_need_k, dim3(div_up(plan.a.nseg, 256)), dim3(256), 0, plan.a, (const int*)plan.tok_len, (i64)tiles_per_chunk * GATHER_TILE, d_need);
-        SCCG_CK(cudaMemcpyAsync((char*)c->h_pinned + 8192, d_need, sizeof(u32) * PIPE_MAX_CHUNKS, cudaMemcpyDeviceToHost, c->stream));
+        SCCG_CK(cudaMemsetAsync(d_need + PIPE_MAX_CHUNKS, 0xff, sizeof(u32) * PIPE_MAX_CHUNKS, c->stream));
+        LAUNCH(c, dec_need_k, dim3(div_up(plan.a.nseg, 256)), dim3(256), 0, plan.a, (const int*)plan.tok_len, (i64)tiles_per_chunk * GATHER_TILE, d_need,
+               d_need + PIPE_MAX_CHUNKS);
+        SCCG_CK(cudaMemcpyAsync((char*)c->h_pinned + 8192, d_need, sizeof(u32) * 2 * PIPE_MAX_CHUNKS, cudaMemcpyDeviceToHost, c->stream));
         SCCG_CK(cudaStreamSynchronize(c->stream));
         memcpy(need, (char*)c->h_pinned + 8192, sizeof(u32) * (size_t)n_och);
+        memcpy(need_lo, (char*)c->h_pinned + 8192 + sizeof(u32) * PIPE_MAX_CHUNKS, sizeof(u32) * (size_t)n_och);
+    }
+    // ---- the output chunks of this call: all of them, or the part-th of n_parts contiguous groups
+    int j_begin = 0, j_end = n_och;
+    if (parts) {
+        j_begin = (int)((i64)n_och * ps->part / ps->n_parts); j_end = (int)((i64)n_och * (ps->part + 1) / ps->n_parts);
+        const i64 pb0 = j_begin == 0 ? 0 : (nh + 1) + (i64)j_begin * tiles_per_chunk * GATHER_TILE;       // offsets in the file image
+        i64 pb1 = (nh + 1) + (i64)j_end * tiles_per_chunk * GATHER_TILE; if (pb1 > full || j_end == n_och) pb1 = full;
+        if (j_end <= j_begin) pb1 = pb0;
+        *ps->part_off = pb0; *out_len = pb1 - pb0;
+        if (dst_cap < pb1 - pb0) return set_error(SCCG_E_ARG, "output buffer too small (required size returned in *out_len)");
+        h_dst = dst - pb0;                                                   // image offset x lands at dst[x - pb0]
+        if (defer_upload) {
+            u32 lo = 0xffffffffu, hi = 0u;
+            for (int j = j_begin; j < j_end; ++j) { if (need_lo[j] < lo) lo = need_lo[j]; if (need[j] != 0xffffffffu && need[j] > hi) hi = need[j]; if (need[j] == 0xffffffffu) { lo = 0; hi = (u32)ref_len; } }
+            int i0 = 0, i1 = 0;
+            if (hi > lo) { i0 = (int)(lo / rchunk); i1 = (int)(((i64)hi + 32 + rchunk - 1) / rchunk); if (i1 > n_rch) i1 = n_rch; }
+            SCCG_TRY(enqueue_ref(i0, i1));
+            SCCG_CK(cudaEventRecord(c->ev[5], c->s_h2d));
+            prepared = i0;
+        }
     }
     // ---- gather chunk by chunk; every finished chunk goes home on the D2H stream while the next ones are produced
     int rc = SCCG_OK;
     cudaError_t ce = cudaSuccess;
-    for (int j = 0; j < n_och && rc == SCCG_OK && ce == cudaSuccess; ++j) {
-        i64 want = need[j] == 0xffffffffu ? ref_len : (i64)need[j] + 32;     // reference symbols [0, want) must be resident
+    for (int j = j_begin; j < j_end && rc == SCCG_OK && ce == cudaSuccess; ++j) {
+        i64 want = need[j] == 0xffffffffu ? ref_len : (i64)need[j] + 32;     // reference symbols [.., want) must be resident
         if (want > ref_len) want = ref_len;
         while (prepared < n_rch && (i64)prepared * rchunk < want && rc == SCCG_OK) {
             const i64 off = (i64)prepared * rchunk, len = (ref_len - off) < rchunk ? (ref_len - off) : rchunk;
@@ -949,16 +1005,13 @@ static int decompress_host(sccg_ctx* c, const char* ref_raw, i64 ref_len, const 
         const unsigned tn = plan.ntiles - t0 < tiles_per_chunk ? plan.ntiles - t0 : tiles_per_chunk;
         rc = reconstruct_gather(c, &plan, d_ref, t0, tn);
         if (rc != SCCG_OK) break;
-        if (j == 0) cudaEventRecord(c->ev[6], c->stream);
+        if (j == j_begin) cudaEventRecord(c->ev[6], c->stream);
         ce = cudaEventRecord(c->ev_g[j], c->stream);
         if (ce == cudaSuccess) ce = cudaStreamWaitEvent(c->s_d2h, c->ev_g[j], 0);
         // bytes of the device image [-(nh+1), n): chunk 0 also carries the header line
         const i64 b0 = j == 0 ? -(nh + 1) : (i64)t0 * GATHER_TILE;
         i64 b1 = ((i64)t0 + tn) * GATHER_TILE; if (b1 > n) b1 = n;
         if (ce == cudaSuccess && b1 > b0) ce = cudaMemcpyAsync(h_dst + (nh + 1) + b0, d_text + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, c->s_d2h);
-    }
-    if (n_och == 0 && ce == cudaSuccess) {                                    // cannot happen (the text holds at least "\n"); kept for safety
-        ce = cudaMemcpyAsync(h_dst, d_text - (nh + 1), (size_t)full, cudaMemcpyDeviceToHost, c->stream);
     }
     if (ce == cudaSuccess) ce = cudaEventRecord(c->ev[7], c->s_d2h);
     if (rc == SCCG_OK && ce == cudaSuccess) rc = reconstruct_finish(c, &plan);       // synchronises the compute stream, reads the error flags

@@ -155,3 +155,31 @@ def test_decompress_pipelined_small_chunks(ctx, chunk, monkeypatch):
     inter = b">x\n\n,\n(110000,5000)(-110000,30000)ACGT(60000,100)(-50000,20000)"
     rc, exp = ol.orc_decompress(ref, inter)
     assert rc == 0 and ctx.decompress(ref, inter) == exp
+
+
+@pytest.mark.parametrize("n_parts,chunk", [(2, 4096), (3, 4096), (5, 20000), (8, 1 << 20)])
+def test_decompress_parts_concatenate_to_the_whole(ctx, n_parts, chunk, monkeypatch):
+    """output-range sharding: the pieces of sccg_decompress_part, placed at their offsets, are the whole image; a piece only
+    has the reference chunks it needs (everything else is poisoned)"""
+    from sccg_genome_compression_b200 import synth
+    monkeypatch.setenv("SCCG_PIPE_CHUNK", str(chunk))
+    monkeypatch.setenv("SCCG_PIPE_POISON", "1")
+    cases = []
+    ref, tgt = synth.local_pair(150_000, synth.seed_for(2, 81))
+    cases.append((ref.tobytes(), tgt.tobytes()))
+    ref, tgt = synth.global_gap_pair(90_000, 80_000, synth.seed_for(1, 81))
+    cases.append((ref.tobytes(), tgt.tobytes()))
+    cases.append((rnd(3000, "tinyp"), rnd(3000, "tinyp")[:2100]))         # fewer chunks than parts: some pieces are empty
+    for ref, tgt in cases:
+        rc, inter, mode = ol.orc_compress(ref, tgt, b">parts")
+        assert rc == 0
+        rc, exp = ol.orc_decompress(ref, inter)
+        assert rc == 0
+        image = bytearray(len(exp))
+        covered = 0
+        for p in range(n_parts):
+            off, piece, total = ctx.decompress_part(ref, inter, p, n_parts)
+            assert total == len(exp)
+            image[off:off + len(piece)] = piece
+            covered += len(piece)
+        assert covered == len(exp) and bytes(image) == exp

@@ -106,3 +106,29 @@ def test_decompress_pipelined_small_chunks(ctx, chunk, monkeypatch):
     inter = b">x\n\n,\n(110000,5000)(-110000,30000)ACGT(60000,100)(-50000,20000)"
     rc, exp = ol.orc_decompress(ref, inter)
     assert rc == 0 and ctx.decompress(ref, inter) == exp
+
+
+@pytest.mark.parametrize("n_parts,chunk", [(2, 65536), (8, 1 << 20), (3, 4096)])
+def test_decompress_parts_concatenate_to_the_whole(ctx, n_parts, chunk, monkeypatch):
+    """output-range sharding on the GPU: pieces at their offsets = the whole image; un-needed reference chunks stay poisoned"""
+    from sccg_genome_compression_b200 import synth
+    monkeypatch.setenv("SCCG_PIPE_CHUNK", str(chunk))
+    monkeypatch.setenv("SCCG_PIPE_POISON", "1")
+    cases = []
+    ref, tgt = synth.local_pair(4_000_000, synth.seed_for(2, 81))
+    cases.append((ref.tobytes(), tgt.tobytes()))
+    ref, tgt = synth.global_gap_pair(1_200_000, 1_100_000, synth.seed_for(1, 81))
+    cases.append((ref.tobytes(), tgt.tobytes()))
+    for ref, tgt in cases:
+        rc, inter, mode = ol.orc_compress(ref, tgt, b">parts")
+        assert rc == 0
+        rc, exp = ol.orc_decompress(ref, inter)
+        assert rc == 0
+        image = bytearray(len(exp))
+        covered = 0
+        for p in range(n_parts):
+            off, piece, total = ctx.decompress_part(ref, inter, p, n_parts)
+            assert total == len(exp)
+            image[off:off + len(piece)] = piece
+            covered += len(piece)
+        assert covered == len(exp) and bytes(image) == exp
