@@ -942,11 +942,7 @@ static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, c
     char* h_dst = dst;
     if (parts) {
         if (!dst) return set_error(SCCG_E_ARG, "null argument");
-    } else if (!dst) {
-        h_dst = (char*)malloc((size_t)full + 1);
-        if (!h_dst) return set_error(SCCG_E_NOMEM, "malloc of the result failed");
-        h_dst[full] = 0;
-    } else if (dst_cap < full) {
+    } else if (dst && dst_cap < full) {
         return set_error(SCCG_E_ARG, "output buffer too small (required size returned in *out_len)");
     }
     // ---- which part of the reference does every output chunk need?
@@ -968,6 +964,7 @@ static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, c
     }
     // ---- the output chunks of this call: all of them, or the part-th of n_parts contiguous groups
     int j_begin = 0, j_end = n_och;
+    i64 img_base = 0;                                                        // offset of h_dst[0] inside the file image
     if (parts) {
         j_begin = (int)((i64)n_och * ps->part / ps->n_parts); j_end = (int)((i64)n_och * (ps->part + 1) / ps->n_parts);
         const i64 pb0 = j_begin == 0 ? 0 : (nh + 1) + (i64)j_begin * tiles_per_chunk * GATHER_TILE;       // offsets in the file image
@@ -975,7 +972,7 @@ static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, c
         if (j_end <= j_begin) pb1 = pb0;
         *ps->part_off = pb0; *out_len = pb1 - pb0;
         if (dst_cap < pb1 - pb0) return set_error(SCCG_E_ARG, "output buffer too small (required size returned in *out_len)");
-        h_dst = dst - pb0;                                                   // image offset x lands at dst[x - pb0]
+        img_base = pb0;                                                      // image offset x lands at dst[x - pb0]
         if (defer_upload) {
             u32 lo = 0xffffffffu, hi = 0u;
             for (int j = j_begin; j < j_end; ++j) { if (need_lo[j] < lo) lo = need_lo[j]; if (need[j] != 0xffffffffu && need[j] > hi) hi = need[j]; if (need[j] == 0xffffffffu) { lo = 0; hi = (u32)ref_len; } }
@@ -985,6 +982,11 @@ static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, c
             SCCG_CK(cudaEventRecord(c->ev[5], c->s_h2d));
             prepared = i0;
         }
+    }
+    if (!dst) {                                                              // allocated last: no early return can leak it
+        h_dst = (char*)malloc((size_t)full + 1);
+        if (!h_dst) return set_error(SCCG_E_NOMEM, "malloc of the result failed");
+        h_dst[full] = 0;
     }
     // ---- gather chunk by chunk; every finished chunk goes home on the D2H stream while the next ones are produced
     int rc = SCCG_OK;
@@ -1011,7 +1013,7 @@ static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, c
         // bytes of the device image [-(nh+1), n): chunk 0 also carries the header line
         const i64 b0 = j == 0 ? -(nh + 1) : (i64)t0 * GATHER_TILE;
         i64 b1 = ((i64)t0 + tn) * GATHER_TILE; if (b1 > n) b1 = n;
-        if (ce == cudaSuccess && b1 > b0) ce = cudaMemcpyAsync(h_dst + (nh + 1) + b0, d_text + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, c->s_d2h);
+        if (ce == cudaSuccess && b1 > b0) ce = cudaMemcpyAsync(h_dst + ((nh + 1) + b0 - img_base), d_text + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, c->s_d2h);
     }
     if (ce == cudaSuccess) ce = cudaEventRecord(c->ev[7], c->s_d2h);
     if (rc == SCCG_OK && ce == cudaSuccess) rc = reconstruct_finish(c, &plan);       // synchronises the compute stream, reads the error flags
