@@ -356,21 +356,15 @@ __device__ __forceinline__ int lm_diag_parse(LmWarpSmem& S, const u32 (&wm)[4], 
         int p = lane * chunk;
         u32 h = 0u;
         if (p < nk) {
-#pragma unroll 1
-            for (int x = 0; x < k - 1; x += 4) {                    // hash of r[p .. p+k-1)
-                const u32 w = ld_unaligned32(S.r, p + x);
-                h = mad_u32(h, mul, w & 0xffu);
-                if (x + 1 < k - 1) h = mad_u32(h, mul, (w >> 8) & 0xffu);
-                if (x + 2 < k - 1) h = mad_u32(h, mul, (w >> 16) & 0xffu);
-                if (x + 3 < k - 1) h = mad_u32(h, mul, w >> 24);
-            }
+#pragma unroll 4
+            for (int x = 0; x < k - 1; ++x) h = mad_u32(h, mul, S.r[p + x]);     // hash of r[p .. p+k-1)
 #pragma unroll 1
             for (int st = 0; st < steps; ++st, p += 4) {
-                const u32 w = ld_unaligned32(S.r, p + k - 1);       // the symbols entering at p .. p+3 (zero padding past the end)
-                const u32 h0 = mad_u32(h, mul, w & 0xffu);
-                const u32 h1 = mad_u32(h0, mul, (w >> 8) & 0xffu);
-                const u32 h2 = mad_u32(h1, mul, (w >> 16) & 0xffu);
-                const u32 h3 = mad_u32(h2, mul, w >> 24);
+                const u8* in = S.r + p + k - 1;                       // the symbols entering at p .. p+3 (zero padding past the end);
+                const u32 h0 = mad_u32(h, mul, in[0]);                // byte loads: the LSU has headroom, the ALU pipe does not
+                const u32 h1 = mad_u32(h0, mul, in[1]);
+                const u32 h2 = mad_u32(h1, mul, in[2]);
+                const u32 h3 = mad_u32(h2, mul, in[3]);
                 const u32 e0 = S.head[dv_slot(h0)], e1 = S.head[dv_slot(h1)], e2 = S.head[dv_slot(h2)], e3 = S.head[dv_slot(h3)];
                 h = h3;
                 if ((e0 == h0) | (e1 == h1) | (e2 == h2) | (e3 == h3)) {
@@ -475,6 +469,7 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
 #endif
         u32 wm[4];                                           // diagonal-0 mismatch flags per 8-byte word (uniform)
         const int wv = Lmin >> 3, rem = Lmin & 7;
+        const bool full_pair = Lr == SEG && Lt == SEG;        // words past the end were fetched as 0 on both sides: no masking needed
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             int q = lane + 32 * it;
@@ -484,7 +479,8 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
             reinterpret_cast<u64*>(S.r)[q] = rw;
             reinterpret_cast<u64*>(S.t)[q] = tw;
             u64 diff = rw ^ tw;
-            bool d = q < wv ? diff != 0ull : (q == wv && rem ? (diff & (~0ull >> (64 - 8 * rem))) != 0ull : false);
+            bool d = diff != 0ull;
+            if (!full_pair) d = q < wv ? d : (q == wv && rem ? (diff & (~0ull >> (64 - 8 * rem))) != 0ull : false);
             wm[it] = __ballot_sync(SCCG_FULL_MASK, d);
         }
         // claim the next segment: SCCG_LM_CLAIM consecutive segments per atomic (one hot L2 address for the whole grid)
