@@ -500,8 +500,25 @@ __device__ __forceinline__ void warp_copy_g2s(u8* dst, const u8* __restrict__ sr
     if (lane < head) dst[lane] = src[lane];
     const u32 nw = (n - head) >> 3;
     u64* d64 = reinterpret_cast<u64*>(dst + head);
-    const u8* s = src + head;
-    for (u32 i = lane; i < nw; i += 32) d64[i] = ld_unaligned64(s + 8 * (size_t)i);
+    // the source alignment is the same for every word of the segment: hoisted, and the 64-bit funnel is two 32-bit ones
+    const uintptr_t sa = (uintptr_t)(src + head);
+    const uint2* s2 = reinterpret_cast<const uint2*>(sa & ~(uintptr_t)7);
+    const u32 sb = (u32)(sa & 7u);
+    if (sb == 0) {
+        for (u32 i = lane; i < nw; i += 32) { const uint2 a = s2[i]; d64[i] = (u64)a.x | ((u64)a.y << 32); }
+    } else if (sb < 4) {
+        const u32 sh = sb * 8u;
+        for (u32 i = lane; i < nw; i += 32) {
+            const uint2 a = s2[i], b = s2[i + 1];
+            d64[i] = (u64)__funnelshift_r(a.x, a.y, sh) | ((u64)__funnelshift_r(a.y, b.x, sh) << 32);
+        }
+    } else {
+        const u32 sh = (sb - 4u) * 8u;
+        for (u32 i = lane; i < nw; i += 32) {
+            const uint2 a = s2[i], b = s2[i + 1];
+            d64[i] = (u64)__funnelshift_r(a.y, b.x, sh) | ((u64)__funnelshift_r(b.x, b.y, sh) << 32);
+        }
+    }
     const u32 done = head + (nw << 3);
     if (done + lane < n) dst[done + lane] = src[done + lane];
 }
