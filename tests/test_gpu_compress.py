@@ -140,3 +140,31 @@ def test_compress_large_local_50mbp(ctx):
     got, gmode = ctx.compress(ref, tgt, b">chr50")
     assert (gmode, len(got)) == (mode, len(exp))
     assert got == exp, _report("local_50mbp", got, exp)
+
+
+def test_roundtrip_400mbp_pair(ctx):
+    """larger than any human chromosome: 400 Mbp local pair through the host-pointer ABI and back (size-independent check:
+    the reconstructed FASTA is the target image; text offsets, scans and grids beyond the chr1 sizes)"""
+    import ctypes
+    import numpy as np
+    import torch
+    from sccg_genome_compression_b200 import synth
+    n = 400_000_000
+    ref, tgt = synth.local_pair(n, synth.seed_for(2, 91))
+    header = b">big synthetic pair"
+    h_enc = torch.empty(n // 8, dtype=torch.uint8)
+    h_out = torch.empty(n + n // 50 + 4096, dtype=torch.uint8)
+
+    def cbuf(a):
+        return (ctypes.c_char * a.size).from_address(a.ctypes.data)
+    e_len, mode = ctx.compress_into(cbuf(ref), cbuf(tgt), header, h_enc.data_ptr(), h_enc.numel())
+    assert mode == 0
+    enc = (ctypes.c_char * e_len).from_address(h_enc.data_ptr())
+    d_len = ctx.decompress_into(cbuf(ref), enc, h_out.data_ptr(), h_out.numel())
+    got = h_out[:d_len].numpy()
+    hl = len(header) + 1
+    full = n // 50 * 50
+    assert bytes(got[:hl]) == header + b"\n"
+    body = got[hl:hl + full // 50 * 51].reshape(-1, 51)
+    assert np.array_equal(body[:, :50].reshape(-1), tgt[:full]) and bool((body[:, 50] == 10).all())
+    assert bytes(got[hl + full // 50 * 51:]) == (tgt[full:].tobytes() + b"\n" if n > full else b"")
