@@ -112,7 +112,10 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
     SCCG_TRY(buf(c, B_SEGPREV, (size_t)n_iter + 1, &seg_prev));
     SCCG_CK(cudaEventRecord(c->ev[1], c->stream));
     if (n_iter > 0) {
-        const size_t smem = sizeof(LmWarpSmem) * LM_WARPS;
+#ifndef SCCG_LM_EXTRA_SMEM
+#define SCCG_LM_EXTRA_SMEM 0                  // development aid: occupancy sensitivity experiments
+#endif
+        const size_t smem = sizeof(LmWarpSmem) * LM_WARPS + SCCG_LM_EXTRA_SMEM;
         SCCG_SET_MAX_SMEM(seg_match_k, smem);
         const unsigned cap = (unsigned)c->sm_count * 8u;                    // 8 CTAs of 4 warps fit the 227 KB of shared memory
         SCCG_CK(cudaMemsetAsync(seginfo, 0xff, sizeof(u32) * (size_t)n_iter, c->stream));    // "not done" markers for the early T2 abort

@@ -700,16 +700,23 @@ __global__ void __launch_bounds__(256) seg_write_k(const u8* __restrict__ tgt, i
     u8* body = out + *d_body_base;
     for (int seg0 = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; seg0 < n_iter; seg0 += warps_total * 32) {
         const int seg = seg0 + lane;
-        u32 info = seg < n_iter ? seginfo[seg] : 0u;
+        // everything a light segment needs is fetched up front, in parallel (one round trip instead of a chain of five):
+        // status, text offset, delta carry and the first four matches (the slot is 400 bytes: 16-byte aligned)
+        u32 info = 0u, off0 = 0u; int prev0 = 0;
+        uint4 m4 = make_uint4(0u, 0u, 0u, 0u);
+        if (seg < n_iter) {
+            info = seginfo[seg]; off0 = seg_off[seg]; prev0 = seg_prev_p[seg];
+            m4 = *reinterpret_cast<const uint4*>(matches + (i64)seg * LM_SLOT);
+        }
         const int nmatch = (int)SEGINFO_NMATCH(info);
         const bool light = nmatch > 0 && nmatch <= 6 && SEGINFO_LIT(info) <= 24;
         if (light) {
             const i64 toff = (i64)seg * SEG;
             const int Lt = (int)((nt - toff) < SEG ? (nt - toff) : SEG);
-            u8* o = body + seg_off[seg];
-            int pp = seg_prev_p[seg], pe = 0;
+            u8* o = body + off0;
+            int pp = prev0, pe = 0;
             for (int m = 0; m < nmatch; ++m) {
-                u32 pk = matches[(i64)seg * LM_SLOT + m];
+                u32 pk = m == 0 ? m4.x : m == 1 ? m4.y : m == 2 ? m4.z : m == 3 ? m4.w : matches[(i64)seg * LM_SLOT + m];
                 int tpos = (int)(pk & 0x3ffu), l = (int)(pk >> 20);
                 int p_abs = (seg + seg_base) * SEG + (int)((pk >> 10) & 0x3ffu);
                 for (int x = pe; x < tpos; ++x) *o++ = upper1(tgt[toff + x]);
