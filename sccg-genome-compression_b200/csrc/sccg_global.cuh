@@ -1,7 +1,7 @@
 // Global mode (compression.cpp:484-574): N-run extraction, N-stripping, reference k-mer index and
 // the stateful banded greedy parse  match_sequences(ref, tgt, k = 14, m = 100, global = true)  (:561).
 //
-//   index   : hash32 of every reference k-mer + stable radix sort  ->  (key, position) sorted by key,
+//   index   : 24-bit hash of every reference k-mer + stable radix sort (3 passes)  ->  (key, position) sorted by key,
 //             positions ascending inside a key (the reference's bucket order, :41-47)
 //   parse   : one persistent CTA walks the state (index, prev_match_end) exactly like :64-161.
 //             * until the first match (prev_match_end == -1, every candidate is "in range") and in the
@@ -26,13 +26,15 @@ static const int GP_WIN_BYTES = 288;
 static const int GP_FILTER = 512;
 static const int GP_SHORT = 64;              // per-thread extension before the block-wide one takes over
 
-// 32-bit hash of the k-mer s[0..k), 8 <= k <= 16; the words may come from global or shared memory
+// 24-bit hash of the k-mer s[0..k), 8 <= k <= 16; the words may come from global or shared memory.  24 bits = three radix
+// passes for the index; k-mers that share a hash are told apart by comparing the symbols (every consumer does).
+static const int GP_HASH_BITS = 24;
 __device__ __forceinline__ u32 kmer_hash_words(u64 w0, u64 w1, int k) {
     if (k < 16) w1 &= (k == 8) ? 0ull : (~0ull >> (8 * (16 - k)));
     u64 x = (w0 * 0x9E3779B97F4A7C15ULL) ^ ((w1 + 0x632BE59BD9B4E019ULL) * 0xD6E8FEB86659FD93ULL);
     x ^= x >> 29;
     x *= 0x94D049BB133111EBULL;
-    return (u32)(x >> 32);
+    return (u32)(x >> (64 - GP_HASH_BITS));
 }
 __device__ __forceinline__ bool kmer_equal_words(u64 a0, u64 a1, u64 b0, u64 b1, int k) {
     u64 m1 = (k == 8) ? 0ull : (k < 16 ? (~0ull >> (8 * (16 - k))) : ~0ull);
@@ -566,7 +568,7 @@ struct GlobalMatches { int* tpos; int* p; int* l; u32 count; };
 static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i64 nt, int k, int m, u32* sc, GlobalMatches* out) {
     if (k < 8 || k > 16) return set_error(SCCG_E_ARG, "global match_sequences supports 8 <= k <= 16");
     if (m < 0 || m > GP_MAX_M) return set_error(SCCG_E_ARG, "global match_sequences supports 0 <= m <= 120");
-    // ---- reference k-mer index (:41-47): hash32 keys + stable radix sort
+    // ---- reference k-mer index (:41-47): 24-bit hash keys + stable radix sort
     const i64 nk = nr - k + 1 > 0 ? nr - k + 1 : 0;
     u32 *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr;
     SCCG_TRY(buf(c, B_GKEYS, (size_t)nk + 1, &keys));
@@ -575,7 +577,9 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
     SCCG_TRY(buf(c, B_GVALS2, (size_t)nk + 1, &vals2));
     if (nk > 0) {
         LAUNCH(c, kmer_keys_k, dim3(div_up(nk, 256)), dim3(256), 0, R, nk, k, keys, vals);
-        SCCG_TRY(radix_sort_pairs(c, keys, vals, keys2, vals2, nk, B_GHIST));
+        u32 *sk = nullptr, *sv = nullptr;
+        SCCG_TRY(radix_sort_pairs(c, keys, vals, keys2, vals2, nk, B_GHIST, GP_HASH_BITS / 8, &sk, &sv));
+        keys = sk; vals = sv;
     }
     // ---- chunk-speculative parse (:64-161)
     int chunk = GP_CHUNK_DEFAULT;

@@ -101,14 +101,16 @@ __global__ void __launch_bounds__(RS_T) rs_scatter_k(const u32* __restrict__ key
     }
 }
 
-// sorts (keys, vals) of length n by key; the result ends up in (keys, vals); (keys2, vals2) is scratch of the same size
-static int radix_sort_pairs(sccg_ctx* c, u32* keys, u32* vals, u32* keys2, u32* vals2, i64 n, int slot_hist) {
+// sorts (keys, vals) of length n by the low 8 * passes bits of the key; (keys2, vals2) is scratch of the same size.
+// *out_keys / *out_vals: where the result is (the input arrays for an even number of passes, the scratch arrays otherwise)
+static int radix_sort_pairs(sccg_ctx* c, u32* keys, u32* vals, u32* keys2, u32* vals2, i64 n, int slot_hist, int passes, u32** out_keys, u32** out_vals) {
+    *out_keys = keys; *out_vals = vals;
     if (n <= 1) return SCCG_OK;
     unsigned nblocks = div_up(n, RS_TILE);
     u32* hist = nullptr;
     SCCG_TRY(buf(c, slot_hist, (size_t)nblocks * 256 + 1, &hist));
     u32 *ki = keys, *vi = vals, *ko = keys2, *vo = vals2;
-    for (int pass = 0; pass < 4; ++pass) {
+    for (int pass = 0; pass < passes; ++pass) {
         int shift = pass * 8;
         LAUNCH(c, rs_hist_k, dim3(nblocks), dim3(RS_T), 0, (const u32*)ki, n, shift, hist, nblocks);
         SCCG_TRY(scan_exclusive_u32(c, hist, hist, (i64)nblocks * 256, nullptr));
@@ -116,7 +118,8 @@ static int radix_sort_pairs(sccg_ctx* c, u32* keys, u32* vals, u32* keys2, u32* 
         u32* t = ki; ki = ko; ko = t;
         t = vi; vi = vo; vo = t;
     }
-    return SCCG_OK;          // 4 passes: the data is back in (keys, vals)
+    *out_keys = ki; *out_vals = vi;
+    return SCCG_OK;
 }
 
 }  // namespace sccg
