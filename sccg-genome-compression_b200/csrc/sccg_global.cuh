@@ -29,6 +29,8 @@ static const int GP_SHORT = 64;              // per-thread extension before the 
 // 24-bit hash of the k-mer s[0..k), 8 <= k <= 16; the words may come from global or shared memory.  24 bits = three radix
 // passes for the index; k-mers that share a hash are told apart by comparing the symbols (every consumer does).
 static const int GP_HASH_BITS = 24;
+static const int GP_BUCKET_BITS = 20;         // top bits of the hash that address the offset table (4 MB)
+static const int GP_BUCKET_SHIFT = GP_HASH_BITS - GP_BUCKET_BITS;
 __device__ __forceinline__ u32 kmer_hash_words(u64 w0, u64 w1, int k) {
     if (k < 16) w1 &= (k == 8) ? 0ull : (~0ull >> (8 * (16 - k)));
     u64 x = (w0 * 0x9E3779B97F4A7C15ULL) ^ ((w1 + 0x632BE59BD9B4E019ULL) * 0xD6E8FEB86659FD93ULL);
@@ -48,6 +50,15 @@ __global__ void __launch_bounds__(256) kmer_keys_k(const u8* __restrict__ R, i64
     vals[p] = (u32)p;
 }
 
+// bucket[b] for every b in [0, 2^GP_BUCKET_BITS]: thread i owns the buckets that begin between keys[i-1] and keys[i]
+__global__ void __launch_bounds__(256) kmer_buckets_k(const u32* __restrict__ keys, i64 nk, u32* __restrict__ bucket) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nk) return;
+    const u32 lo = i == 0 ? 0u : (keys[i - 1] >> GP_BUCKET_SHIFT) + 1u;
+    const u32 hi = i == nk ? (1u << GP_BUCKET_BITS) : (keys[i] >> GP_BUCKET_SHIFT);
+    for (u32 b = lo; b <= hi; ++b) bucket[b] = (u32)i;
+}
+
 // ------------------------------------------------------------------------------------------------
 // the persistent parse CTA
 // ------------------------------------------------------------------------------------------------
@@ -64,14 +75,25 @@ struct GpShared {
     unsigned long long best_key;
 };
 
+struct GpArgs;
+__device__ __forceinline__ i64 index_lower_bound(const GpArgs& a, u32 h);
+
 struct GpArgs {
     const u8* R; i64 nr;          // N-stripped, upper-cased reference
     const u8* T; i64 nt;          // N-stripped, upper-cased target
     const u32* keys; const u32* vals; i64 nk;
+    const u32* bucket;            // bucket[b] = first index whose key >> GP_BUCKET_SHIFT is >= b (2^GP_BUCKET_BITS + 1 entries, L2-resident)
     int k, m;
     int* m_tpos; int* m_p; int* m_l;   // out: matches
     u32* d_count;                      // out: number of matches
 };
+
+// first index whose key is >= h: the offset table narrows the search to one bucket (a few dozen entries)
+__device__ __forceinline__ i64 index_lower_bound(const GpArgs& a, u32 h) {
+    i64 lo = a.bucket[h >> GP_BUCKET_SHIFT], hi = a.bucket[(h >> GP_BUCKET_SHIFT) + 1];
+    while (lo < hi) { i64 mid = (lo + hi) >> 1; if (a.keys[mid] < h) lo = mid + 1; else hi = mid; }
+    return lo;
+}
 
 // length of the common prefix of R[p..] and T[j..], capped at cap (cap <= remaining lengths)
 __device__ __forceinline__ int serial_lcp(const u8* __restrict__ R, i64 p, const u8* __restrict__ T, i64 j, int cap) {
@@ -164,8 +186,7 @@ __device__ __forceinline__ void fold_chunk(GpShared& S, const GpArgs& a, i64 p, 
 __device__ __forceinline__ void fold_index_candidates(GpShared& S, const GpArgs& a, i64 j, int e) {
     fold_reset(S);
     u32 h = kmer_hash_words(ld_unaligned64(a.T + j), ld_unaligned64(a.T + j + 8), a.k);
-    i64 lo = 0, hi = a.nk;                                       // lower_bound(keys, h): uniform, every thread computes it
-    while (lo < hi) { i64 mid = (lo + hi) >> 1; if (a.keys[mid] < h) lo = mid + 1; else hi = mid; }
+    const i64 lo = index_lower_bound(a, h);                      // uniform, every thread computes it
     for (i64 base = lo;; base += GP_T) {
         i64 idx = base + threadIdx.x;
         bool valid = idx < a.nk && a.keys[idx] == h;
@@ -193,8 +214,7 @@ __device__ __forceinline__ bool gp_step(GpShared& S, const GpArgs& a, i64& j, in
             if (pos < scan_end) {
                 u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
                 u32 h = kmer_hash_words(w0, w1, k);
-                i64 lo = 0, hi = a.nk;
-                while (lo < hi) { i64 mid = (lo + hi) >> 1; if (a.keys[mid] < h) lo = mid + 1; else hi = mid; }
+                i64 lo = index_lower_bound(a, h);
                 for (; lo < a.nk && a.keys[lo] == h && !hit; ++lo) {
                     const u8* rp = a.R + a.vals[lo];
                     hit = kmer_equal_words(ld_unaligned64(rp), ld_unaligned64(rp + 8), w0, w1, k);
@@ -329,8 +349,7 @@ __global__ void __launch_bounds__(GP_T) gp_spec_k(GpSpecArgs s) {
             i64 pos = B + tid;
             u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
             u32 h = kmer_hash_words(w0, w1, a.k);
-            i64 lo = 0, hi = a.nk;
-            while (lo < hi) { i64 mid = (lo + hi) >> 1; if (a.keys[mid] < h) lo = mid + 1; else hi = mid; }
+            i64 lo = index_lower_bound(a, h);
             int hits = 0;
             for (; lo < a.nk && a.keys[lo] == h && hits < 2; ++lo) {
                 const u8* rp = a.R + a.vals[lo];
@@ -581,6 +600,9 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
         SCCG_TRY(radix_sort_pairs(c, keys, vals, keys2, vals2, nk, B_GHIST, GP_HASH_BITS / 8, &sk, &sv));
         keys = sk; vals = sv;
     }
+    u32* bucket = nullptr;
+    SCCG_TRY(buf(c, B_GBUCKET, ((size_t)1 << GP_BUCKET_BITS) + 2, &bucket));
+    LAUNCH(c, kmer_buckets_k, dim3(div_up(nk + 1, 256)), dim3(256), 0, (const u32*)keys, nk, bucket);
     // ---- chunk-speculative parse (:64-161)
     int chunk = GP_CHUNK_DEFAULT;
     if (const char* env = getenv("SCCG_GP_CHUNK")) { int v = atoi(env); if (v >= 64 && v <= (1 << 24)) chunk = v; }
@@ -600,7 +622,7 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
     h_st.j = 0; h_st.e = -1; h_st.status = GP_RUNNING;
     SCCG_CK(cudaMemcpyAsync(st, &h_st, sizeof h_st, cudaMemcpyHostToDevice, c->stream));
     GpFrontArgs f;
-    f.s.a.R = R; f.s.a.nr = nr; f.s.a.T = T; f.s.a.nt = nt; f.s.a.keys = keys; f.s.a.vals = vals; f.s.a.nk = nk; f.s.a.k = k; f.s.a.m = m;
+    f.s.a.R = R; f.s.a.nr = nr; f.s.a.T = T; f.s.a.nt = nt; f.s.a.keys = keys; f.s.a.vals = vals; f.s.a.nk = nk; f.s.a.bucket = bucket; f.s.a.k = k; f.s.a.m = m;
     f.s.a.m_tpos = nullptr; f.s.a.m_p = nullptr; f.s.a.m_l = nullptr; f.s.a.d_count = nullptr;
     f.s.info = info; f.s.c_tpos = cbuf; f.s.c_p = cbuf + (size_t)2 * nchunks * cap_c; f.s.c_l = cbuf + (size_t)4 * nchunks * cap_c;
     f.s.nchunks = nchunks; f.s.cap_c = cap_c; f.s.chunk = chunk; f.s.slot = 0; f.s.first_chunk = 0; f.s.lost_e = 0;
