@@ -66,3 +66,24 @@ def test_cli_usage_and_errors(env, tmp_path):
     (tmp_path / "bad.txt.7z").write_bytes(b">h\n\n,\n(5,100)")
     r = subprocess.run([str(BIN / "decompress"), str(tmp_path / "bad.txt.7z"), str(tmp_path / "ref.fa"), str(tmp_path / "d")], env=env, capture_output=True)
     assert r.returncode == 1 and b"exceeds reference genome size" in r.stderr
+
+
+def test_cli_batch_mode(env, golden, tmp_path):
+    """additive `--batch <list>`: many pairs in one process (one CUDA context), same files as the one-pair invocations"""
+    fcs = fasta_cases()[:4]
+    clist, dlist = [], []
+    for i, fc in enumerate(fcs):
+        d = tmp_path / f"p{i}"; d.mkdir()
+        (d / "ref.fa").write_bytes(fc.ref_file); (d / "tgt.fa").write_bytes(fc.tgt_file)
+        clist.append(f"{d / 'ref.fa'} {d / 'tgt.fa'} {d / 'out'}")
+        dlist.append(f"{d / 'out' / 'compressed_genome.txt.7z'} {d / 'ref.fa'} {d / 'dec'}")
+    (tmp_path / "c.txt").write_text("\n".join(clist) + "\n\n")
+    (tmp_path / "d.txt").write_text("\n".join(dlist) + "\n")
+    r = subprocess.run([str(BIN / "compress"), "--batch", str(tmp_path / "c.txt")], env=env, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(BIN / "decompress"), "--batch", str(tmp_path / "d.txt")], env=env, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    for i, fc in enumerate(fcs):
+        g = golden["fasta_cases"][fc.name]
+        assert (tmp_path / f"p{i}" / "out" / "compressed_genome.txt").read_bytes() == unpack(g["intermediate_z"])
+        assert (tmp_path / f"p{i}" / "dec" / "reconstructed_genome.fa").read_bytes() == unpack(g["reconstructed_z"])
