@@ -43,4 +43,13 @@ with tempfile.TemporaryDirectory() as d:
     same_d = (d / "ours_dec" / "reconstructed_genome.fa").read_bytes() == (d / "reference_dec" / "reconstructed_genome.fa").read_bytes()
     out["compressed_genome_txt_identical"] = same_c; out["reconstructed_fa_identical"] = same_d
     out["roundtrip_is_target_file"] = (d / "ours_dec" / "reconstructed_genome.fa").read_bytes() == (d / "tgt.fa").read_bytes()
+    # batch mode: the same pair three times in one process (one CUDA context)
+    ours = ROOT / "sccg-genome-compression_b200" / "bin"
+    (d / "c.txt").write_text("".join(f"{d / 'ref.fa'} {d / 'tgt.fa'} {d / ('b%d' % i)}\n" for i in range(3)))
+    (d / "d.txt").write_text("".join(f"{d / ('b%d' % i) / 'compressed_genome.txt.7z'} {d / 'ref.fa'} {d / ('bd%d' % i)}\n" for i in range(3)))
+    t0 = time.perf_counter(); r = subprocess.run([str(ours / "compress"), "--batch", str(d / "c.txt")], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE); t1 = time.perf_counter()
+    r2 = subprocess.run([str(ours / "decompress"), "--batch", str(d / "d.txt")], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE); t2 = time.perf_counter()
+    assert r.returncode == 0 and r2.returncode == 0, (r.stderr[-300:], r2.stderr[-300:])
+    out["ours_batch_of_3"] = {"compress_s": round(t1 - t0, 3), "decompress_s": round(t2 - t1, 3),
+                              "identical": (d / "bd2" / "reconstructed_genome.fa").read_bytes() == (d / "tgt.fa").read_bytes()}
     print(json.dumps(out))
