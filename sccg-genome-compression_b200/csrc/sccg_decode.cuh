@@ -495,6 +495,10 @@ __device__ __forceinline__ void gather_tile_generic(const GatherArgs& a, int* wi
 // step; the source may be read up to 15 bytes past its end (buffers carry that slack).
 __device__ __forceinline__ void warp_copy_g2s(u8* dst, const u8* __restrict__ src, u32 n) {
     const u32 lane = (u32)lane_of();
+    if (n <= 32) {                                                 // literal runs are mostly one symbol: one byte per lane, done
+        if (lane < n) dst[lane] = src[lane];
+        return;
+    }
     u32 head = (u32)((8u - ((u32)(uintptr_t)dst & 7u)) & 7u);
     if (head > n) head = n;
     if (lane < head) dst[lane] = src[lane];
