@@ -733,7 +733,9 @@ static int reconstruct_prepare(sccg_ctx* c, i64 nr, const u8* d_enc, i64 ne, con
         SCCG_TRY(parse_runs(c, d_n, nn, B_NUM4, sc, D_N_ITEMS, sc + D_NSUM, &ns));          // slots B_NUM4, B_NUM5, B_LRUN_S, B_LRUN_E
         SCCG_CK(cudaEventRecord(c->ev_side[3], c->stream));
     }
-    SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[3], 0));
+    // the run tables are needed by the gather only (and the N total by the sizes, global-mode files): the main lane does not
+    // wait for the side lane before it reads the tokenizer totals
+    if (ns.K) SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[3], 0));
     u32 h[D_COUNT];
     SCCG_TRY(read_scalars(c, sc, h, D_COUNT));
     if (h[D_ERR] & DE_FORMAT) return set_error(SCCG_E_FORMAT, "malformed record stream (the reference would throw from stoi)");
@@ -779,6 +781,7 @@ static int reconstruct_prepare(sccg_ctx* c, i64 nr, const u8* d_enc, i64 ne, con
     a.Ls = Ls; a.Lm = Lm; a.total = total; a.out = out + header_reserve; a.tile0 = 0;
     plan->sc = sc; plan->tok_len = tok_len; plan->ntok = ntok; plan->ntiles = div_up(total, GATHER_TILE);
     // resolved segment sources and per-tile entry points: the gather itself starts from two table loads
+    SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[3], 0));                  // run tables complete (device-side wait)
     i64* seg_ptr = nullptr; int4* tile_win = nullptr;
     SCCG_TRY(buf(c, B_SEG_PTR, (size_t)nseg + 1, &seg_ptr));
     SCCG_TRY(buf(c, B_TILE_WIN, (size_t)plan->ntiles + 1, &tile_win));
