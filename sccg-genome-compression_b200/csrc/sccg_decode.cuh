@@ -170,18 +170,6 @@ __global__ void __launch_bounds__(DEC_T) dec_emit_k(const u8* __restrict__ enc, 
     }
 }
 
-// abs[t] = prefix sum of the deltas (decompression.cpp:220-222), bounds check (:223-229)
-__global__ void dec_token_abs_k(const int* __restrict__ tok_delta, const int* __restrict__ tok_len, const u32* __restrict__ delta_excl, u32 ntok, i64 nr,
-                                int* __restrict__ tok_abs, u32* __restrict__ sc) {
-    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntok) return;
-    int a = (int)(delta_excl[t] + (u32)tok_delta[t]);             // prev_abs_start + delta, int arithmetic
-    tok_abs[t] = a;
-    i64 end = (i64)(int)((u32)a + (u32)tok_len[t]);               // `absolute_start + length` is evaluated in int
-    if (end > nr) atomicOr(&sc[D_ERR], (u32)DE_BOUNDS);
-    else if (a < 0) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);         // substr(pos > size) throws out_of_range
-}
-
 // ------------------------------------------------------------------------------------------------
 // run lists (decompression.cpp:126-207): "(d,len)" | "d," | "d"
 // ------------------------------------------------------------------------------------------------
@@ -541,12 +529,20 @@ __device__ __forceinline__ void warp_lower_smem(u8* p, u32 n) {
 
 static const int GATHER_PAD = 64;
 
-// seg_ptr[k]: where segment k copies from (one dependent load less in the gather)
-__global__ void dec_resolve_k(const i64* __restrict__ seg_src, const int* __restrict__ tok_abs, int nseg, i64* __restrict__ seg_ptr) {
+// seg_ptr[k]: where segment k copies from (one dependent load less in the gather).  Token segments: abs = prefix sum of
+// the deltas (decompression.cpp:220-222) and the bounds check (:223-229) happen here (token t belongs to exactly one segment).
+__global__ void dec_resolve_k(const i64* __restrict__ seg_src, const int* __restrict__ tok_delta, const int* __restrict__ tok_len,
+                              const u32* __restrict__ delta_excl, int nseg, i64 nr, int* __restrict__ tok_abs, i64* __restrict__ seg_ptr, u32* __restrict__ sc) {
     int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (k >= nseg) return;
     const i64 src = seg_src[k];
-    seg_ptr[k] = (src & SEG_LIT_FLAG) ? src : (i64)tok_abs[src];
+    if (src & SEG_LIT_FLAG) { seg_ptr[k] = src; return; }
+    const int a = (int)(delta_excl[src] + (u32)tok_delta[src]);   // prev_abs_start + delta, int arithmetic
+    tok_abs[src] = a;
+    const i64 end = (i64)(int)((u32)a + (u32)tok_len[src]);       // `absolute_start + length` is evaluated in int
+    if (end > nr) atomicOr(&sc[D_ERR], (u32)DE_BOUNDS);
+    else if (a < 0) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);         // substr(pos > size) throws out_of_range
+    seg_ptr[k] = (i64)a;
 }
 
 // merged-coordinate symbol range [b0, b1) shown in the text bytes [Q0, Qe)
@@ -754,7 +750,6 @@ static int reconstruct_prepare(sccg_ctx* c, i64 nr, const u8* d_enc, i64 ne, con
     }
     if (ntok > 0) {
         SCCG_TRY(scan_exclusive_u32(c, (const u32*)tok_delta, delta_excl, (i64)ntok, nullptr));
-        LAUNCH(c, dec_token_abs_k, dim3(div_up(ntok, 256)), dim3(256), 0, (const int*)tok_delta, (const int*)tok_len, (const u32*)delta_excl, ntok, nr, tok_abs, sc);
     }
     SCCG_CK(cudaEventRecord(c->ev[1], c->stream));
 
@@ -785,7 +780,8 @@ static int reconstruct_prepare(sccg_ctx* c, i64 nr, const u8* d_enc, i64 ne, con
     i64* seg_ptr = nullptr; int4* tile_win = nullptr;
     SCCG_TRY(buf(c, B_SEG_PTR, (size_t)nseg + 1, &seg_ptr));
     SCCG_TRY(buf(c, B_TILE_WIN, (size_t)plan->ntiles + 1, &tile_win));
-    if (nseg) LAUNCH(c, dec_resolve_k, dim3(div_up(nseg, 256)), dim3(256), 0, (const i64*)seg_src, (const int*)tok_abs, (int)nseg, seg_ptr);
+    if (nseg) LAUNCH(c, dec_resolve_k, dim3(div_up(nseg, 256)), dim3(256), 0, (const i64*)seg_src, (const int*)tok_delta, (const int*)tok_len,
+                     (const u32*)delta_excl, (int)nseg, nr, tok_abs, seg_ptr, sc);
     a.seg_ptr = seg_ptr; a.tile_win = tile_win;
     LAUNCH(c, dec_tile_win_k, dim3(div_up(plan->ntiles, 128)), dim3(128), 0, a, plan->ntiles, tile_win);
     SCCG_CK(cudaEventRecord(c->ev[1], c->stream));                              // everything up to here is "tokenizer" time
