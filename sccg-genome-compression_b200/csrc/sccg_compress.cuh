@@ -117,7 +117,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
 #endif
         const size_t smem = sizeof(LmWarpSmem) * LM_WARPS + SCCG_LM_EXTRA_SMEM;
         SCCG_SET_MAX_SMEM(seg_match_k, smem);
-        const unsigned cap = (unsigned)c->sm_count * 8u;                    // 8 CTAs of 4 warps fit the 227 KB of shared memory
+        const unsigned cap = (unsigned)c->sm_count * (unsigned)LM_CTAS_PER_SM;   // resident CTAs: they claim segments dynamically
         SCCG_CK(cudaMemsetAsync(seginfo, 0xff, sizeof(u32) * (size_t)n_iter, c->stream));    // "not done" markers for the early T2 abort
         // one launch per arrived reference chunk (device-resident inputs: a single launch)
         const int n_launch = arr ? arr->n : 1;

@@ -19,7 +19,11 @@
 
 namespace sccg {
 
-static const int LM_WARPS = 4;                // 4 warps x 6.7 KB: 8 CTAs = 32 warps per SM
+#ifndef SCCG_LM_WARPS
+#define SCCG_LM_WARPS 4
+#endif
+static const int LM_WARPS = SCCG_LM_WARPS;    // 4 warps x 6.6 KB per CTA, 8 CTAs = 32 warps per SM (shared memory and registers both full)
+static const int LM_CTAS_PER_SM = 32 / LM_WARPS;
 static const int LM_HT_BITS = 9;              // 512 chain heads for <= 987 k-mers (false positives die on a 4-byte tag)
 static const int LM_HT = 1 << LM_HT_BITS;
 static const int LM_SEQ_PAD = 1040;
@@ -430,7 +434,7 @@ __device__ __forceinline__ void lm_fetch(const u8* __restrict__ ref, i64 nr, con
 #define SCCG_LM_CLAIM 2             // segments claimed per atomic
 #endif
 #ifndef SCCG_LM_MIN_CTAS
-#define SCCG_LM_MIN_CTAS 8          // 8 CTAs x 128 threads x 64 registers = the whole register file of an SM
+#define SCCG_LM_MIN_CTAS (32 / SCCG_LM_WARPS)   // 32 warps x 32 lanes x 64 registers = the whole register file of an SM
 #endif
 __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(const u8* __restrict__ ref, i64 nr, const u8* __restrict__ tgt, i64 nt,
                                                             int seg_begin, int n_iter, int n_total, int k1, int k2, u32* seginfo, u32* __restrict__ matches,

@@ -43,7 +43,7 @@ static int shard_match(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt, i6
     if (n_iter > 0) {
         const size_t smem = sizeof(LmWarpSmem) * LM_WARPS;
         SCCG_SET_MAX_SMEM(seg_match_k, smem);
-        const unsigned cap = (unsigned)c->sm_count * 8u, w = div_up(n_iter, LM_WARPS);
+        const unsigned cap = (unsigned)c->sm_count * (unsigned)LM_CTAS_PER_SM, w = div_up(n_iter, LM_WARPS);
         SCCG_CK(cudaMemsetAsync(seginfo, 0xff, sizeof(u32) * (size_t)n_iter, c->stream));
         SCCG_CK(cudaMemsetAsync(d_last, 0xff, sizeof(int), c->stream));
         LAUNCH(c, seg_match_k, dim3(w < cap ? w : cap), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, 0, n_iter, n_iter, K1, K2, seginfo, matches,
