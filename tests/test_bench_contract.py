@@ -1,0 +1,35 @@
+"""bench.py contract on the CPU: the reference arm (`--impl reference`) runs the compiled reference on host cores and prints
+one JSON line with the agreed keys (the GPU arm is exercised by the driver on the B200 box)."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+import oracle_lib as ol
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.mark.skipif(not ol.have_reference(), reason="oracle/_ref not built")
+def test_reference_arm_json_line():
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--size", "9000000", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "Mbp/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert "workload" in line["config"]
+
+
+def test_reference_arm_other_ranks_stay_silent(monkeypatch):
+    import os
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--size", "9000000", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
