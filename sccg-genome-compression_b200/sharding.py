@@ -132,6 +132,26 @@ def compress_sharded(ctx, ref: bytes, tgt: bytes, header: bytes) -> tuple[bytes,
     return text, 0
 
 
+def decompress_sharded(ctx, ref_raw, intermediate: bytes, out_path: str) -> int:
+    """decompress for ONE pair with the output spread over all ranks by byte range: every rank produces its
+    piece of reconstructed_genome.fa (sccg_decompress_part: only the reference chunks that piece copies from are uploaded)
+    and writes it at its offset of `out_path`; nothing is gathered.  Returns the length of the whole file."""
+    import os
+    world, rank = dist.get_world_size(), dist.get_rank()
+    off, piece, total = ctx.decompress_part(ref_raw, intermediate, rank, world)
+    if rank == 0:
+        with open(out_path, "wb") as f:
+            f.truncate(total)
+    dist.barrier()                                                  # the file exists with its final size
+    fd = os.open(out_path, os.O_WRONLY)
+    try:
+        os.pwrite(fd, piece, off)
+    finally:
+        os.close(fd)
+    dist.barrier()
+    return total
+
+
 _INFO_KEYS = ["n_segments", "abort_inside", "has_paren", "has_match", "last_p", "n_runs", "first_run_start", "first_run_len", "last_run_start", "last_run_len"]
 
 

@@ -108,6 +108,15 @@ def _shard_worker(rank, world, port, q):
         if rank == 0:
             res[name] = out
             res[name + ":path"] = sharding.last_path
+    # and back: every rank writes its piece of the reconstructed file at its offset
+    import tempfile
+    tmp = os.environ["SCCG_TEST_TMP"]
+    for name, ref, tgt in _shard_cases()[:3]:
+        inter = res.get(name, (None,))[0] if rank == 0 else None
+        box = [inter]
+        dist.broadcast_object_list(box, src=0)
+        path = os.path.join(tmp, name + ".fa")
+        sharding.decompress_sharded(ctx, ref, box[0], path)
     ctx.close()
     if rank == 0:
         q.put(res)
@@ -116,7 +125,9 @@ def _shard_worker(rank, world, port, q):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-def test_compress_sharded_matches_unsharded(world):
+def test_compress_sharded_matches_unsharded(world, tmp_path, monkeypatch):
+    monkeypatch.setenv("SCCG_TEST_TMP", str(tmp_path))
+    monkeypatch.setenv("SCCG_PIPE_CHUNK", "4096")
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import oracle_lib as ol
@@ -138,6 +149,9 @@ def test_compress_sharded_matches_unsharded(world):
         assert got[name] == (exp, mode), name
         fallback = name in ("abort_to_global", "paren_fallback") or (world == 3 and name in ("target_longer", "reference_longer"))
         assert got[name + ":path"] == ("unsharded" if fallback else "sharded"), name
+    for name, ref, tgt in _shard_cases()[:3]:                           # the pieces written by the ranks form the reference's output file
+        rc, exp = ol.orc_decompress(ref, got[name][0])
+        assert rc == 0 and (tmp_path / (name + ".fa")).read_bytes() == exp, name
 
 
 def test_plan_carries_unit():
