@@ -20,8 +20,12 @@
 
 namespace sccg {
 
-static const int GP_T = 512;                 // threads of the parse CTA
+#ifndef SCCG_GP_T
+#define SCCG_GP_T 256
+#endif
+static const int GP_T = SCCG_GP_T;           // threads of the parse CTA
 static const int GP_MAX_M = 120;             // window = 2m+1 <= 241 positions
+static_assert(GP_T >= 64 && GP_T % 32 == 0, "64 diagonal probes, one per thread");
 static const int GP_WIN_BYTES = 288;
 static const int GP_FILTER = 512;
 static const int GP_SHORT = 64;              // per-thread extension before the block-wide one takes over
@@ -43,12 +47,12 @@ __device__ __forceinline__ bool kmer_equal_words(u64 a0, u64 a1, u64 b0, u64 b1,
     return a0 == b0 && ((a1 ^ b1) & m1) == 0ull;
 }
 
-__global__ void __launch_bounds__(256) kmer_keys_k(const u8* __restrict__ R, i64 nk, int k, u32* __restrict__ keys, u32* __restrict__ vals) {
-    i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= nk) return;
-    keys[p] = kmer_hash_words(ld_unaligned64(R + p), ld_unaligned64(R + p + 8), k);
-    vals[p] = (u32)p;
-}
+// the (hash, position) pairs of the reference k-mers, computed where the sort reads them (no 8 B per k-mer staging pass)
+struct KmerPairSource {
+    const u8* R; int k;
+    __device__ __forceinline__ u32 key(i64 p) const { return kmer_hash_words(ld_unaligned64(R + p), ld_unaligned64(R + p + 8), k); }
+    __device__ __forceinline__ u32 val(i64 p) const { return (u32)p; }
+};
 
 // bucket[b] for every b in [0, 2^GP_BUCKET_BITS]: thread i owns the buckets that begin between keys[i-1] and keys[i]
 __global__ void __launch_bounds__(256) kmer_buckets_k(const u32* __restrict__ keys, i64 nk, u32* __restrict__ bucket) {
@@ -68,7 +72,7 @@ struct GpShared {
     u8 f_off[GP_FILTER];
     int i_scratch[8];
     unsigned long long key_scratch;
-    int long_list[GP_T];
+    int long_list[GP_T > 128 ? GP_T : 128];       // also the 64 diagonal votes (i64) of gp_spec_k
     int long_n;
     // accumulators of the candidate fold
     int best_l, cnt, zero_in;
@@ -245,11 +249,11 @@ __device__ __forceinline__ bool gp_step(GpShared& S, const GpArgs& a, i64& j, in
     for (int x = tid; x < GP_FILTER; x += GP_T) S.f_hash[x] = 0u;
     for (int x = tid; x < GP_WIN_BYTES; x += GP_T) S.win[x] = x < wbytes ? a.R[wlo + x] : (u8)0;
     __syncthreads();
-    if (tid < wlen) {
-        u32 h = kmer_hash_words(ld_unaligned64(S.win + tid), ld_unaligned64(S.win + tid + 8), k) | 1u;
+    for (int x = tid; x < wlen; x += GP_T) {
+        u32 h = kmer_hash_words(ld_unaligned64(S.win + x), ld_unaligned64(S.win + x + 8), k) | 1u;
         u32 slot = (h >> 1) & (GP_FILTER - 1);
         while (atomicCAS(&S.f_hash[slot], 0u, h) != 0u) slot = (slot + 1) & (GP_FILTER - 1);
-        S.f_off[slot] = (u8)tid;
+        S.f_off[slot] = (u8)x;
     }
     __syncthreads();
     for (; j < scan_end; j += GP_T) {
@@ -278,13 +282,16 @@ __device__ __forceinline__ bool gp_step(GpShared& S, const GpArgs& a, i64& j, in
     if (found < 0) { j = scan_end; return false; }
     j = found;
     // in-range candidates: the window positions whose k-mer equals T[j..j+k)  (pn2 / ln2, :116-123)
-    i64 cand = -1;
-    if (tid < wlen) {
-        u64 w0 = ld_unaligned64(a.T + j), w1 = ld_unaligned64(a.T + j + 8);
-        if (kmer_equal_words(ld_unaligned64(S.win + tid), ld_unaligned64(S.win + tid + 8), w0, w1, k)) cand = wlo + tid;
-    }
     fold_reset(S);
-    fold_chunk(S, a, cand, j, e);
+    {
+        const u64 w0 = ld_unaligned64(a.T + j), w1 = ld_unaligned64(a.T + j + 8);
+        for (int x0 = 0; x0 < wlen; x0 += GP_T) {                // the fold is order-independent: one thread-wide slice at a time
+            const int x = x0 + tid;
+            i64 cand = -1;
+            if (x < wlen && kmer_equal_words(ld_unaligned64(S.win + x), ld_unaligned64(S.win + x + 8), w0, w1, k)) cand = wlo + x;
+            fold_chunk(S, a, cand, j, e);
+        }
+    }
     sel_p = fold_result_p(S); sel_l = S.best_l;
     __syncthreads();
     if (sel_p == 0) {                                         // `pn2 != 0` fails (:134): unrestricted best over ALL candidates
@@ -595,9 +602,9 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
     SCCG_TRY(buf(c, B_GKEYS2, (size_t)nk + 1, &keys2));
     SCCG_TRY(buf(c, B_GVALS2, (size_t)nk + 1, &vals2));
     if (nk > 0) {
-        LAUNCH(c, kmer_keys_k, dim3(div_up(nk, 256)), dim3(256), 0, R, nk, k, keys, vals);
         u32 *sk = nullptr, *sv = nullptr;
-        SCCG_TRY(radix_sort_pairs(c, keys, vals, keys2, vals2, nk, B_GHIST, GP_HASH_BITS / 8, &sk, &sv));
+        KmerPairSource src{R, k};
+        SCCG_TRY(radix_sort_pairs(c, src, keys, vals, keys2, vals2, nk, B_GHIST, GP_HASH_BITS / 8, &sk, &sv));
         keys = sk; vals = sv;
     }
     u32* bucket = nullptr;
