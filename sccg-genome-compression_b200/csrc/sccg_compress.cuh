@@ -79,6 +79,8 @@ struct ChunkArrival {
     cudaEvent_t ev_tgt;      // the whole target is resident
 };
 
+static const int LM_PROBE_SEGS = 40;             // segments of the abort probe (see compress_device)
+
 static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt, i64 nt, const char* header, i64 nh, CompressResult* res,
                            const ChunkArrival* arr) {
     u32* sc = nullptr;
@@ -119,6 +121,15 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
         SCCG_SET_MAX_SMEM(seg_match_k, smem);
         const unsigned cap = (unsigned)c->sm_count * (unsigned)LM_CTAS_PER_SM;   // resident CTAs: they claim segments dynamically
         SCCG_CK(cudaMemsetAsync(seginfo, 0xff, sizeof(u32) * (size_t)n_iter, c->stream));    // "not done" markers for the early T2 abort
+        // Sequences of different length are usually shifted against each other from some indel / N-gap on, and then the tail
+        // of the common range fails segment after segment.  The T2 abort condition (:454-473) is a property of 5 consecutive
+        // segments, wherever they are, so a small probe launch over the last segments can raise the abort flag before the
+        // main launch starts: every warp of the main launch then leaves after its first flag poll instead of burning one
+        // failing (= most expensive) segment per resident warp.  No abort in the probe range: the main launch runs as usual.
+        if (!arr && n_iter > 4 * LM_PROBE_SEGS && (nr > nt ? nr - nt : nt - nr) >= SEG) {
+            LAUNCH(c, seg_match_k, dim3(div_up(LM_PROBE_SEGS, LM_WARPS)), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, n_iter - LM_PROBE_SEGS, n_iter, n_iter, K1, K2,
+                   seginfo, matches, sc + S_WORK + 31, sc + S_ABORT, (c->use_diag ? LM_FLAG_DIAG : 0) | LM_FLAG_CLAIM1);
+        }
         // one launch per arrived reference chunk (device-resident inputs: a single launch)
         const int n_launch = arr ? arr->n : 1;
         int seg_lo = 0;

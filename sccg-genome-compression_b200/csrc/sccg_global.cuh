@@ -50,8 +50,32 @@ __device__ __forceinline__ bool kmer_equal_words(u64 a0, u64 a1, u64 b0, u64 b1,
 // the (hash, position) pairs of the reference k-mers, computed where the sort reads them (no 8 B per k-mer staging pass)
 struct KmerPairSource {
     const u8* R; int k;
+    static const bool kRun16 = true;
     __device__ __forceinline__ u32 key(i64 p) const { return kmer_hash_words(ld_unaligned64(R + p), ld_unaligned64(R + p + 8), k); }
     __device__ __forceinline__ u32 val(i64 p) const { return (u32)p; }
+    // keys of the 16 consecutive positions p0 .. p0 + 15: 32 bytes loaded once, every 16-byte window cut out with
+    // constant shifts (key() costs 3-4 loads and two variable funnel shifts per position)
+    __device__ __forceinline__ void keys16(i64 p0, u32* out) const {
+        const uintptr_t a = (uintptr_t)(R + p0);
+        const u64* q = reinterpret_cast<const u64*>(a & ~(uintptr_t)7);
+        const u32 sh = (u32)(a & 7) * 8u;
+        u64 W[4];
+        if (sh == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) W[j] = q[j];
+        } else {
+            u64 x = q[0];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const u64 y = q[j + 1]; W[j] = (x >> sh) | (y << (64u - sh)); x = y; }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int j = i >> 3, b = (i & 7) * 8;
+            const u64 w0 = b ? (W[j] >> b) | (W[j + 1] << (64 - b)) : W[j];
+            const u64 w1 = b ? (W[j + 1] >> b) | (W[j + 2] << (64 - b)) : W[j + 1];
+            out[i] = kmer_hash_words(w0, w1, k);
+        }
+    }
 };
 
 // bucket[b] for every b in [0, 2^GP_BUCKET_BITS]: thread i owns the buckets that begin between keys[i-1] and keys[i]

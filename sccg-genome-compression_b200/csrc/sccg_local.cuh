@@ -430,6 +430,7 @@ __device__ __forceinline__ void lm_fetch(const u8* __restrict__ ref, i64 nr, con
 // abort_flag (optional): seginfo must be preset to 0xffffffff ("not done"); as soon as some warp sees the T2 abort
 // condition of the driver (:454-473: a failed, non-all-N segment ending a run of 5 counter increments) among finished
 // segments it raises the flag and every warp stops claiming work -- the local attempt is discarded anyway (:466-472).
+static const int LM_FLAG_DIAG = 1, LM_FLAG_CLAIM1 = 2;      // bits of seg_match_k's `use_diag` argument
 #ifndef SCCG_LM_CLAIM
 #define SCCG_LM_CLAIM 2             // segments claimed per atomic
 #endif
@@ -457,10 +458,11 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
     // segments are claimed dynamically (their cost varies by an order of magnitude) and the next segment's
     // symbols are fetched into registers while the current one is parsed
     u64 nrw[4], ntw[4];
-    const int claim_base = seg_begin + warps_total * SCCG_LM_CLAIM;   // the first warps_total * CLAIM segments are pre-assigned
+    const int claim = (use_diag & LM_FLAG_CLAIM1) ? 1 : SCCG_LM_CLAIM;  // the abort probe wants consecutive segments on different warps
+    const int claim_base = seg_begin + warps_total * claim;            // the first warps_total * claim segments are pre-assigned
     int claimed_used = 0;
     bool head_clean = false;                                  // S.head all zero (kept by the diagonal-hypothesis path)
-    int seg = seg_begin + warp_global * SCCG_LM_CLAIM < n_iter ? seg_begin + warp_global * SCCG_LM_CLAIM : n_iter;
+    int seg = seg_begin + warp_global * claim < n_iter ? seg_begin + warp_global * claim : n_iter;
     lm_fetch(ref, nr, tgt, nt, seg, n_iter, lane, nrw, ntw);
     while (seg < n_iter) {
         const i64 off = (i64)seg * SEG;
@@ -489,9 +491,9 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
         }
         // claim the next segment: SCCG_LM_CLAIM consecutive segments per atomic (one hot L2 address for the whole grid)
         int next_seg = seg + 1;
-        if (++claimed_used >= SCCG_LM_CLAIM) {
+        if (++claimed_used >= claim) {
             if (lane == 0) {
-                next_seg = (int)atomicAdd(work_counter, 1u) * SCCG_LM_CLAIM + claim_base;
+                next_seg = (int)atomicAdd(work_counter, 1u) * claim + claim_base;
             }
             claimed_used = 0;
             next_seg = __shfl_sync(SCCG_FULL_MASK, next_seg, 0);
@@ -514,7 +516,7 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
             if (lane == 0) S.mlist[0] = 0u | (0u << 10) | ((u32)Lt << 20);
             nmatch = 1;
             SEG_STAT(0);
-        } else if (use_diag && Lr == Lt && Lt >= k1 && (nmatch = lm_diag_parse(S, wm, Lt, k1, head_clean)) > 0) {
+        } else if ((use_diag & LM_FLAG_DIAG) && Lr == Lt && Lt >= k1 && (nmatch = lm_diag_parse(S, wm, Lt, k1, head_clean)) > 0) {
             // near-identical segment: parse determined by the mismatch positions, hypothesis proven against all of r
             SEG_STAT(1);
         } else {

@@ -24,6 +24,8 @@ static const int RS_TILE = RS_T * RS_CHUNKS;        // 4096 elements per block
 
 struct RsPairSource {                               // pairs that already sit in memory
     const u32* keys; const u32* vals;
+    static const bool kRun16 = false;               // true: the source has keys16(i0, out) for 16 consecutive indices
+    __device__ __forceinline__ void keys16(i64, u32*) const {}
     __device__ __forceinline__ u32 key(i64 i) const { return keys[i]; }
     __device__ __forceinline__ u32 val(i64 i) const { return vals[i]; }
 };
@@ -35,15 +37,23 @@ __global__ void __launch_bounds__(RS_T) rs_hist_k(const Src src, i64 n, int shif
     __syncthreads();
     const i64 base = (i64)blockIdx.x * RS_TILE;
     u32 kk[RS_CHUNKS];                                  // all loads first: the kernel was latency-bound with load-use pairs
+    if (Src::kRun16 && RS_CHUNKS == 16) {               // the order inside a tile does not matter here: 16 consecutive elements per thread
+        const i64 i0 = base + (i64)threadIdx.x * 16;
+        if (i0 < n) src.keys16(i0, kk);
 #pragma unroll
-    for (int r = 0; r < RS_CHUNKS; ++r) {
-        const i64 i = base + (i64)r * RS_T + threadIdx.x;
-        kk[r] = i < n ? src.key(i) : 0u;
-    }
+        for (int r = 0; r < RS_CHUNKS; ++r)
+            if (i0 + r < n) atomicAdd(&h[(kk[r] >> shift) & 255u], 1u);
+    } else {
 #pragma unroll
-    for (int r = 0; r < RS_CHUNKS; ++r) {
-        const i64 i = base + (i64)r * RS_T + threadIdx.x;
-        if (i < n) atomicAdd(&h[(kk[r] >> shift) & 255u], 1u);
+        for (int r = 0; r < RS_CHUNKS; ++r) {
+            const i64 i = base + (i64)r * RS_T + threadIdx.x;
+            kk[r] = i < n ? src.key(i) : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < RS_CHUNKS; ++r) {
+            const i64 i = base + (i64)r * RS_T + threadIdx.x;
+            if (i < n) atomicAdd(&h[(kk[r] >> shift) & 255u], 1u);
+        }
     }
     __syncthreads();
     if (threadIdx.x < 256u) hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];     // digit-major for the scan
@@ -80,10 +90,28 @@ __global__ void __launch_bounds__(RS_T, SCCG_RS_MINB) rs_scatter_k(const Src src
     const i64 tbase = (i64)blockIdx.x * RS_TILE;
     const i64 wbase = tbase + (i64)w * (RS_CHUNKS * 32);
     u32 k[RS_CHUNKS], rk[RS_CHUNKS];
+    if (Src::kRun16 && RS_CHUNKS == 16) {
+        // every lane computes the keys of 16 consecutive elements of the warp's sub-tile; the part of sk that the warp will
+        // later fill transposes them into the chunk layout (chunk c, lane l = element c * 32 + l)
+        u32* my = sk + w * (RS_CHUNKS * 32);
+        const i64 i0 = wbase + (i64)lane * 16;
+        if (i0 < n) src.keys16(i0, rk);
 #pragma unroll
-    for (int c = 0; c < RS_CHUNKS; ++c) {
-        const i64 i = wbase + c * 32 + lane;
-        k[c] = i < n ? src.key(i) : 0xffffffffu;
+        for (int r = 0; r < 16; ++r) my[lane * 16 + ((r + lane) & 15)] = rk[r];     // rotated: conflict-free columns
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < RS_CHUNKS; ++c) {
+            const int e = c * 32 + lane;                                            // element index inside the sub-tile
+            const u32 kv = my[(e & ~15) + (((e & 15) + (e >> 4)) & 15)];
+            k[c] = wbase + e < n ? kv : 0xffffffffu;
+        }
+        __syncwarp();
+    } else {
+#pragma unroll
+        for (int c = 0; c < RS_CHUNKS; ++c) {
+            const i64 i = wbase + c * 32 + lane;
+            k[c] = i < n ? src.key(i) : 0xffffffffu;
+        }
     }
 #pragma unroll
     for (int c = 0; c < RS_CHUNKS; ++c) rk[c] = digit_peers((k[c] >> shift) & 255u);

@@ -302,3 +302,38 @@ def test_global_speculative_parse_small_chunks(ctx, seed, chunk):
         assert prof["spec_rounds"] >= 1
     finally:
         os.environ.pop("SCCG_GP_CHUNK", None)
+
+
+def _compress_device_emu(ctx, ref: bytes, tgt: bytes, header: bytes):
+    """device-resident entry point under the emulator (device memory is host memory there)"""
+    import numpy as np
+    r = np.frombuffer(ref + bytes(64), dtype=np.uint8).copy(); t = np.frombuffer(tgt + bytes(64), dtype=np.uint8).copy()
+    ptr, n, mode = ctx.compress_device(r.ctypes.data, len(ref), t.ctypes.data, len(tgt), header)
+    return ctx.download(ptr, n), mode
+
+
+@pytest.mark.parametrize("shape", ["shifted_tail", "leftover_only", "reference_insertion", "small_shift", "tail_of_n"])
+def test_compress_device_abort_probe(ctx, shape):
+    """sequences of different length: a probe launch over the last segments may raise the T2 abort before the main launch
+    (device-resident path only).  With and without an abort the file must be the oracle's."""
+    n = 200_000
+    ref = rnd(n, "probe")
+    r = random.Random("probe" + shape)
+    t = bytearray(ref)
+    for p in r.sample(range(n), 150):
+        t[p] = r.choice(b"ACGT")
+    if shape == "shifted_tail":
+        tgt = bytes(t[:60_000]) + bytes(t[63_000:])                    # deletion: everything after it is 3 segments off
+    elif shape == "leftover_only":
+        tgt = bytes(t) + rnd(5_000, "extra")                           # no shift, leftover target segments
+    elif shape == "reference_insertion":
+        tgt = bytes(t); ref = ref[:20_000] + rnd(2_500, "ins") + ref[20_000:]
+    elif shape == "small_shift":
+        tgt = bytes(t[:90_000]) + b"ACGTTGCAAC" * 3 + bytes(t[90_000:]) + rnd(1_200, "tail")   # 30 symbols off: still matches inside the segments
+    else:
+        tgt = bytes(t[:150_000]); ref = ref[:150_000] + b"N" * 50_000  # the probe range is all N on the reference side
+    rc, exp, mode = ol.orc_compress(ref, tgt, b">probe")
+    assert rc == 0
+    got, gmode = _compress_device_emu(ctx, ref, tgt, b">probe")
+    assert (gmode, got) == (mode, exp)
+    assert mode == (1 if shape in ("shifted_tail", "reference_insertion") else 0)
