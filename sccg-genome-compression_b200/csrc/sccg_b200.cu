@@ -205,8 +205,8 @@ int sccg_match_sequences(sccg_ctx* c, const char* Sr, int64_t nr, const char* St
         // the kernel upper-cases on load (the reference driver does so before calling, :369-370); callers pass
         // upper-cased symbols, for which this is the identity
         const size_t smem = sizeof(LmWarpSmem) * LM_WARPS;
-        SCCG_SET_MAX_SMEM(seg_match_k, smem);
-        LAUNCH(c, seg_match_k, dim3(1), dim3(LM_WARPS * 32), smem, (const u8*)d_ref, (i64)(nr > 0 ? nr : 0), (const u8*)d_tgt, nt, 0, 1, 1, k, 0, seginfo, matches, sc + S_WORK, (u32*)nullptr, c->use_diag);
+        SCCG_SET_MAX_SMEM(seg_match_k<SCCG_LM_CLAIM>, smem);
+        LAUNCH(c, seg_match_k<SCCG_LM_CLAIM>, dim3(1), dim3(LM_WARPS * 32), smem, (const u8*)d_ref, (i64)(nr > 0 ? nr : 0), (const u8*)d_tgt, nt, 0, 1, 1, k, 0, seginfo, matches, sc + S_WORK, (u32*)nullptr, c->use_diag);
         u32 info = 0;
         SCCG_CK(cudaMemcpyAsync(&info, seginfo, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
         SCCG_CK(cudaMemcpyAsync(h_matches, matches, sizeof(u32) * LM_SLOT, cudaMemcpyDeviceToHost, c->stream));

@@ -118,7 +118,8 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
 #define SCCG_LM_EXTRA_SMEM 0                  // development aid: occupancy sensitivity experiments
 #endif
         const size_t smem = sizeof(LmWarpSmem) * LM_WARPS + SCCG_LM_EXTRA_SMEM;
-        SCCG_SET_MAX_SMEM(seg_match_k, smem);
+        SCCG_SET_MAX_SMEM(seg_match_k<SCCG_LM_CLAIM>, smem);
+        SCCG_SET_MAX_SMEM(seg_match_k<1>, smem);
         const unsigned cap = (unsigned)c->sm_count * (unsigned)LM_CTAS_PER_SM;   // resident CTAs: they claim segments dynamically
         SCCG_CK(cudaMemsetAsync(seginfo, 0xff, sizeof(u32) * (size_t)n_iter, c->stream));    // "not done" markers for the early T2 abort
         // Sequences of different length are usually shifted against each other from some indel / N-gap on, and then the tail
@@ -127,8 +128,8 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
         // main launch starts: every warp of the main launch then leaves after its first flag poll instead of burning one
         // failing (= most expensive) segment per resident warp.  No abort in the probe range: the main launch runs as usual.
         if (!arr && n_iter > 4 * LM_PROBE_SEGS && (nr > nt ? nr - nt : nt - nr) >= SEG) {
-            LAUNCH(c, seg_match_k, dim3(div_up(LM_PROBE_SEGS, LM_WARPS)), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, n_iter - LM_PROBE_SEGS, n_iter, n_iter, K1, K2,
-                   seginfo, matches, sc + S_WORK + 31, sc + S_ABORT, (c->use_diag ? LM_FLAG_DIAG : 0) | LM_FLAG_CLAIM1);
+            LAUNCH(c, seg_match_k<1>, dim3(div_up(LM_PROBE_SEGS, LM_WARPS)), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, n_iter - LM_PROBE_SEGS, n_iter, n_iter, K1, K2,
+                   seginfo, matches, sc + S_WORK + 31, sc + S_ABORT, c->use_diag);
         }
         // one launch per arrived reference chunk (device-resident inputs: a single launch)
         const int n_launch = arr ? arr->n : 1;
@@ -142,7 +143,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
             if (arr) SCCG_CK(cudaStreamWaitEvent(c->stream, arr->ev_ref[i + 1 < n_launch ? i : arr->n - 1], 0));
             if (seg_hi <= seg_lo) continue;
             const unsigned w = div_up(seg_hi - seg_lo, LM_WARPS);
-            LAUNCH(c, seg_match_k, dim3(w < cap ? w : cap), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, seg_lo, seg_hi, n_iter, K1, K2, seginfo, matches,
+            LAUNCH(c, seg_match_k<SCCG_LM_CLAIM>, dim3(w < cap ? w : cap), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, seg_lo, seg_hi, n_iter, K1, K2, seginfo, matches,
                    sc + S_WORK + (i & 31), sc + S_ABORT, c->use_diag);
             seg_lo = seg_hi;
         }

@@ -430,13 +430,15 @@ __device__ __forceinline__ void lm_fetch(const u8* __restrict__ ref, i64 nr, con
 // abort_flag (optional): seginfo must be preset to 0xffffffff ("not done"); as soon as some warp sees the T2 abort
 // condition of the driver (:454-473: a failed, non-all-N segment ending a run of 5 counter increments) among finished
 // segments it raises the flag and every warp stops claiming work -- the local attempt is discarded anyway (:466-472).
-static const int LM_FLAG_DIAG = 1, LM_FLAG_CLAIM1 = 2;      // bits of seg_match_k's `use_diag` argument
 #ifndef SCCG_LM_CLAIM
 #define SCCG_LM_CLAIM 2             // segments claimed per atomic
 #endif
 #ifndef SCCG_LM_MIN_CTAS
 #define SCCG_LM_MIN_CTAS (32 / SCCG_LM_WARPS)   // 32 warps x 32 lanes x 64 registers = the whole register file of an SM
 #endif
+// CLAIM: consecutive segments per claim (SCCG_LM_CLAIM for the bulk launches; 1 for the abort probe, which wants the
+// segments of a T2 window on different warps)
+template <int CLAIM>
 __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(const u8* __restrict__ ref, i64 nr, const u8* __restrict__ tgt, i64 nt,
                                                             int seg_begin, int n_iter, int n_total, int k1, int k2, u32* seginfo, u32* __restrict__ matches,
                                                             u32* __restrict__ work_counter, u32* abort_flag, int use_diag) {
@@ -458,7 +460,7 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
     // segments are claimed dynamically (their cost varies by an order of magnitude) and the next segment's
     // symbols are fetched into registers while the current one is parsed
     u64 nrw[4], ntw[4];
-    const int claim = (use_diag & LM_FLAG_CLAIM1) ? 1 : SCCG_LM_CLAIM;  // the abort probe wants consecutive segments on different warps
+    const int claim = CLAIM;                                           // compile-time: a run-time claim size cost 15 % (registers in the hot loop)
     const int claim_base = seg_begin + warps_total * claim;            // the first warps_total * claim segments are pre-assigned
     int claimed_used = 0;
     bool head_clean = false;                                  // S.head all zero (kept by the diagonal-hypothesis path)
@@ -516,7 +518,7 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
             if (lane == 0) S.mlist[0] = 0u | (0u << 10) | ((u32)Lt << 20);
             nmatch = 1;
             SEG_STAT(0);
-        } else if ((use_diag & LM_FLAG_DIAG) && Lr == Lt && Lt >= k1 && (nmatch = lm_diag_parse(S, wm, Lt, k1, head_clean)) > 0) {
+        } else if (use_diag && Lr == Lt && Lt >= k1 && (nmatch = lm_diag_parse(S, wm, Lt, k1, head_clean)) > 0) {
             // near-identical segment: parse determined by the mismatch positions, hypothesis proven against all of r
             SEG_STAT(1);
         } else {

@@ -42,11 +42,11 @@ static int shard_match(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt, i6
     int* d_last = (int*)(sc + S_G6);
     if (n_iter > 0) {
         const size_t smem = sizeof(LmWarpSmem) * LM_WARPS;
-        SCCG_SET_MAX_SMEM(seg_match_k, smem);
+        SCCG_SET_MAX_SMEM(seg_match_k<SCCG_LM_CLAIM>, smem);
         const unsigned cap = (unsigned)c->sm_count * (unsigned)LM_CTAS_PER_SM, w = div_up(n_iter, LM_WARPS);
         SCCG_CK(cudaMemsetAsync(seginfo, 0xff, sizeof(u32) * (size_t)n_iter, c->stream));
         SCCG_CK(cudaMemsetAsync(d_last, 0xff, sizeof(int), c->stream));
-        LAUNCH(c, seg_match_k, dim3(w < cap ? w : cap), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, 0, n_iter, n_iter, K1, K2, seginfo, matches,
+        LAUNCH(c, seg_match_k<SCCG_LM_CLAIM>, dim3(w < cap ? w : cap), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, 0, n_iter, n_iter, K1, K2, seginfo, matches,
                sc + S_WORK, sc + S_ABORT, c->use_diag);
         LAUNCH(c, seg_bytes_k, dim3(div_up(n_iter, 256)), dim3(256), 0, (const u32*)seginfo, (const u32*)matches, n_iter, seg_bytes, seg_prev, sc + S_ABORT, 0, 0, 0);
         LAUNCH(c, shard_last_match_k, dim3(div_up(n_iter, 256)), dim3(256), 0, (const u32*)seginfo, n_iter, d_last);
