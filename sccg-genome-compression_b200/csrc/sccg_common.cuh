@@ -112,4 +112,30 @@ __device__ __forceinline__ u32 block_scan_excl(u32 v, u32* smem32, u32* total) {
     return base + incl - v;
 }
 
+// Stream compaction, store side: every thread of the block keeps the bytes of its 16-byte piece (x, y) selected by the
+// mask m; the block's kept bytes (tot of them, this thread's start at excl) go to dst[0 .. tot).  They are packed in shared
+// memory at the same 16-byte phase as dst and leave as aligned 16-byte stores (byte stores only in the first and last
+// partial block), instead of one global byte store per kept byte.  stage: 16-byte aligned, blockDim.x * 16 + 32 bytes.
+__device__ __forceinline__ void block_compact_store(u8* stage, u8* __restrict__ dst, u32 excl, u32 m, u64 x, u64 y, u32 tot) {
+    const u32 a = (u32)((uintptr_t)dst & 15);
+    u32 pos = a + excl;
+    if (m == 0xffffu && (pos & 3u) == 0u) {
+        u32* s32 = reinterpret_cast<u32*>(stage + pos);
+        s32[0] = (u32)x; s32[1] = (u32)(x >> 32); s32[2] = (u32)y; s32[3] = (u32)(y >> 32);
+    } else {
+        while (m) {
+            const int b = __ffs((int)m) - 1; m &= m - 1;
+            const u64 w = b < 8 ? x : y;
+            stage[pos++] = (u8)(w >> (8 * (b & 7)));
+        }
+    }
+    __syncthreads();
+    u8* base = dst - a;                                    // 16-byte aligned; bytes [a, end) of the staged image belong to this block
+    const u32 end = a + tot;
+    for (u32 q = threadIdx.x * 16u; q < end; q += blockDim.x * 16u) {
+        if (q >= a && q + 16u <= end) *reinterpret_cast<uint4*>(base + q) = *reinterpret_cast<const uint4*>(stage + q);
+        else for (u32 b = q > a ? q : a; b < q + 16u && b < end; ++b) base[b] = stage[b];
+    }
+}
+
 }  // namespace sccg

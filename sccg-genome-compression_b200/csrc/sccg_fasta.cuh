@@ -98,21 +98,13 @@ __global__ void __launch_bounds__(FA_T) fasta_count_k(const u8* __restrict__ F, 
 __global__ void __launch_bounds__(FA_T) fasta_write_k(const u8* __restrict__ F, i64 n, const i64* __restrict__ ranges, int nr, const u32* __restrict__ tile_off,
                                                      u8* __restrict__ dst) {
     __shared__ u32 sm[40];
+    __align__(16) __shared__ u8 stage[FA_TILE + 32];
     const i64 i0 = (i64)blockIdx.x * FA_TILE + (i64)threadIdx.x * 16;
     ulonglong2 v; v.x = 0; v.y = 0;
     u32 m = fasta_keep_mask(F, n, i0, ranges, nr, &v);
     u32 tot;
     const u32 excl = block_scan_excl((u32)__popc(m), sm, &tot);
-    u8* o = dst + tile_off[blockIdx.x] + excl;
-    if (m == 0xffffu && (((uintptr_t)o) & 15) == 0) {          // a full, aligned piece of sequence line
-        *reinterpret_cast<ulonglong2*>(o) = v;
-        return;
-    }
-    while (m) {
-        const int b = __ffs((int)m) - 1; m &= m - 1;
-        const u64 w = b < 8 ? v.x : v.y;
-        *o++ = (u8)(w >> (8 * (b & 7)));
-    }
+    block_compact_store(stage, dst + tile_off[blockIdx.x], excl, m, v.x, v.y, tot);
 }
 
 struct FastaSeq { u8* d_seq; i64 len; i64 hdr_start, hdr_end; };   // hdr_*: the target header line inside the file image (-1: none)

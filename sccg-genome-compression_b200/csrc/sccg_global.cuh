@@ -78,13 +78,29 @@ struct KmerPairSource {
     }
 };
 
-// bucket[b] for every b in [0, 2^GP_BUCKET_BITS]: thread i owns the buckets that begin between keys[i-1] and keys[i]
+// bucket[b] for every b in [0, 2^GP_BUCKET_BITS]: index i owns the buckets that begin between keys[i-1] and keys[i]
+// (i = nk: the buckets past the last key).  8 indices per thread (two 16-byte loads; one index per thread was latency-bound).
+static const int KB_SPAN = 8;
 __global__ void __launch_bounds__(256) kmer_buckets_k(const u32* __restrict__ keys, i64 nk, u32* __restrict__ bucket) {
-    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > nk) return;
-    const u32 lo = i == 0 ? 0u : (keys[i - 1] >> GP_BUCKET_SHIFT) + 1u;
-    const u32 hi = i == nk ? (1u << GP_BUCKET_BITS) : (keys[i] >> GP_BUCKET_SHIFT);
-    for (u32 b = lo; b <= hi; ++b) bucket[b] = (u32)i;
+    const i64 i0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * KB_SPAN;
+    if (i0 > nk) return;
+    u32 kk[KB_SPAN];
+    if (i0 + KB_SPAN <= nk) {                                  // keys is a 16-byte aligned allocation
+        const uint4 a = *reinterpret_cast<const uint4*>(keys + i0), b = *reinterpret_cast<const uint4*>(keys + i0 + 4);
+        kk[0] = a.x; kk[1] = a.y; kk[2] = a.z; kk[3] = a.w; kk[4] = b.x; kk[5] = b.y; kk[6] = b.z; kk[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < KB_SPAN; ++j) kk[j] = i0 + j < nk ? keys[i0 + j] : 0u;
+    }
+    u32 prev = i0 == 0 ? 0u : (keys[i0 - 1] >> GP_BUCKET_SHIFT) + 1u;      // first bucket not yet assigned
+#pragma unroll
+    for (int j = 0; j < KB_SPAN; ++j) {
+        const i64 i = i0 + j;
+        if (i > nk) break;
+        const u32 hi = i == nk ? (1u << GP_BUCKET_BITS) : (kk[j] >> GP_BUCKET_SHIFT);
+        for (u32 bkt = prev; bkt <= hi; ++bkt) bucket[bkt] = (u32)i;
+        prev = hi + 1u;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -590,24 +606,33 @@ __global__ void g_write_tokens_k(const int* __restrict__ tpos, const int* __rest
     int prev_p = (i && !absolute) ? mp[i - 1] : 0;
     write_token(out + *d_body_base + offs[i] + (u32)(tpos[i] - prev_end), mp[i] - prev_p, ml[i]);
 }
-// literal symbols: every target position not covered by a match; 16 positions per thread
+// literal symbols: every target position not covered by a match.  GL_SPAN positions per thread: one binary search, then
+// the thread walks the GAPS that intersect its span (a span inside one long match costs the search and nothing else)
+static const int GL_SPAN = 64;
 __global__ void __launch_bounds__(256) g_write_literals_k(const u8* __restrict__ T, i64 nt, const int* __restrict__ tpos, const int* __restrict__ ml, u32 M,
                                                          const u32* __restrict__ offs, const u32* __restrict__ d_tok_total, u8* __restrict__ out,
                                                          const u32* __restrict__ d_body_base) {
-    i64 x0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    const i64 x0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * GL_SPAN;
     if (x0 >= nt) return;
+    const i64 x1 = x0 + GL_SPAN < nt ? x0 + GL_SPAN : nt;
     u8* body = out + *d_body_base;
-    // i = number of matches starting at or before x
+    // i = number of matches starting at or before x0
     int lo = 0, hi = (int)M;
     while (lo < hi) { int mid = (lo + hi) >> 1; if ((i64)tpos[mid] <= x0) lo = mid + 1; else hi = mid; }
     int i = lo;
-    for (int d = 0; d < 16 && x0 + d < nt; ++d) {
-        i64 x = x0 + d;
-        while (i < (int)M && (i64)tpos[i] <= x) ++i;
-        i64 gap_start = i ? (i64)tpos[i - 1] + ml[i - 1] : 0;
-        if (x < gap_start) continue;                              // inside match i-1
-        u32 o = (i < (int)M ? offs[i] : *d_tok_total) + (u32)(x - gap_start);
-        body[o] = T[x];
+    i64 x = x0;
+    while (x < x1) {
+        // invariant: matches 0 .. i-1 start at or before x, match i (if any) starts after x
+        const i64 gap_start = i ? (i64)tpos[i - 1] + ml[i - 1] : 0;       // the gap before match i begins where match i-1 ends
+        const i64 next_start = i < (int)M ? (i64)tpos[i] : nt;
+        if (x < gap_start) x = gap_start;                                  // inside match i-1
+        const i64 lim = next_start < x1 ? next_start : x1;
+        if (x < lim) {
+            const u32 o = (i < (int)M ? offs[i] : *d_tok_total) + (u32)(x - gap_start);
+            for (i64 y = x; y < lim; ++y) body[o + (u32)(y - x)] = T[y];
+        }
+        if (next_start >= x1) break;
+        x = next_start; ++i;                                               // x sits on the first symbol of match i (now "i-1")
     }
 }
 
@@ -633,7 +658,7 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
     }
     u32* bucket = nullptr;
     SCCG_TRY(buf(c, B_GBUCKET, ((size_t)1 << GP_BUCKET_BITS) + 2, &bucket));
-    LAUNCH(c, kmer_buckets_k, dim3(div_up(nk + 1, 256)), dim3(256), 0, (const u32*)keys, nk, bucket);
+    LAUNCH(c, kmer_buckets_k, dim3(div_up(nk + 1, 256 * KB_SPAN)), dim3(256), 0, (const u32*)keys, nk, bucket);
     // ---- chunk-speculative parse (:64-161)
     int chunk = GP_CHUNK_DEFAULT;
     if (const char* env = getenv("SCCG_GP_CHUNK")) { int v = atoi(env); if (v >= 64 && v <= (1 << 24)) chunk = v; }
@@ -760,7 +785,7 @@ static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8
     if (n_text) SCCG_CK(cudaMemcpyAsync(out + hdr_bytes + low_text + 1, ntext, n_text, cudaMemcpyDeviceToDevice, c->stream));
     if (M) LAUNCH(c, g_write_tokens_k, dim3(div_up(M, 256)), dim3(256), 0, (const int*)gm.tpos, (const int*)gm.p, (const int*)gm.l, M,
                   (const u32*)mbytes, out, (const u32*)(sc + S_BODY_BASE), text_delta);
-    if (nt2 > 0) LAUNCH(c, g_write_literals_k, dim3(div_up(nt2, 256 * 16)), dim3(256), 0, (const u8*)T2, nt2, (const int*)gm.tpos, (const int*)gm.l, M,
+    if (nt2 > 0) LAUNCH(c, g_write_literals_k, dim3(div_up(nt2, 256 * GL_SPAN)), dim3(256), 0, (const u8*)T2, nt2, (const int*)gm.tpos, (const int*)gm.l, M,
                         (const u32*)mbytes, (const u32*)(sc + S_G4), out, (const u32*)(sc + S_BODY_BASE));
     SCCG_CK(cudaEventRecord(c->ev[3], c->stream));
     SCCG_CK(cudaStreamSynchronize(c->stream));

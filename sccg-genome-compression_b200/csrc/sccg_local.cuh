@@ -457,16 +457,21 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
         if (lane < k2 && sh < 32) pow2 = 1u << sh;
     }
 
-    // segments are claimed dynamically (their cost varies by an order of magnitude) and the next segment's
-    // symbols are fetched into registers while the current one is parsed
+    // segments are claimed dynamically (their cost varies by an order of magnitude); the next segment is pulled into L2
+    // while the current one is parsed and loaded when its turn comes (31 other warps of the SM cover that L2 latency)
     u64 nrw[4], ntw[4];
     const int claim = CLAIM;                                           // compile-time: a run-time claim size cost 15 % (registers in the hot loop)
     const int claim_base = seg_begin + warps_total * claim;            // the first warps_total * claim segments are pre-assigned
     int claimed_used = 0;
     bool head_clean = false;                                  // S.head all zero (kept by the diagonal-hypothesis path)
     int seg = seg_begin + warp_global * claim < n_iter ? seg_begin + warp_global * claim : n_iter;
+#ifdef SCCG_LM_EARLY_FETCH
     lm_fetch(ref, nr, tgt, nt, seg, n_iter, lane, nrw, ntw);
+#endif
     while (seg < n_iter) {
+#ifndef SCCG_LM_EARLY_FETCH
+        lm_fetch(ref, nr, tgt, nt, seg, n_iter, lane, nrw, ntw);
+#endif
         const i64 off = (i64)seg * SEG;
         const int Lr = (int)((nr - off) < SEG ? (nr - off) : SEG);
         const int Lt = (int)((nt - off) < SEG ? (nt - off) : SEG);
@@ -508,7 +513,18 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
             if (__shfl_sync(SCCG_FULL_MASK, stop, 0)) next_seg = n_iter;
         }
 #endif
+#ifdef SCCG_LM_EARLY_FETCH                                 // the next segment travels in 16 registers across the parse (measured 1 % slower, spills)
         lm_fetch(ref, nr, tgt, nt, next_seg, n_iter, lane, nrw, ntw);
+#else
+        if (next_seg < n_iter && lane < 16) {                 // pull the next segment into L2 only: no registers held across the parse
+            const u8* pf = (lane < 8 ? ref : tgt) + (i64)next_seg * SEG + 128 * (lane & 7);
+#ifndef SCCG_EMU
+            if ((i64)next_seg * SEG + 128 * (lane & 7) < (lane < 8 ? nr : nt)) asm volatile("prefetch.global.L2 [%0];" :: "l"(pf));
+#else
+            (void)pf;
+#endif
+        }
+#endif
         if (lane < 2) reinterpret_cast<u64*>(S.r)[128 + lane] = 0ull, reinterpret_cast<u64*>(S.t)[128 + lane] = 0ull;
         __syncwarp();
 

@@ -1,7 +1,7 @@
 // N-stripping by stream compaction + upper-casing.
 //   compress side (global): toupper, then erase every 'N'   (compression.cpp:523-524, :556-557)  -> drops 'n' and 'N'
 //   decompress side       : erase every 'N', then toupper   (decompression.cpp:105-110)          -> keeps 'n' (becomes 'N')
-// HBM-bound: 1 B read per pass (two passes) + 1 B written per kept symbol.
+// HBM-bound: 1 B read per pass (two passes) + 1 B written per kept symbol (packed in shared memory, stored 16 B at a time).
 #pragma once
 #include "sccg_scan.cuh"
 
@@ -37,19 +37,14 @@ __global__ void __launch_bounds__(STRIP_T) strip_count_k(const u8* __restrict__ 
 template <int UPPER_FIRST>
 __global__ void __launch_bounds__(STRIP_T) strip_write_k(const u8* __restrict__ src, i64 n, const u32* __restrict__ tile_off, u8* __restrict__ dst) {
     __shared__ u32 sm[40];
+    __align__(16) __shared__ u8 stage[STRIP_TILE + 32];
     i64 i = (i64)blockIdx.x * STRIP_TILE + (i64)threadIdx.x * 16;
     ulonglong2 v;
     v.x = 0; v.y = 0;
     u32 m = strip_keep_mask<UPPER_FIRST>(src, n, i, &v);
     u32 tot;
     u32 excl = block_scan_excl((u32)__popc(m), sm, &tot);
-    u8* o = dst + tile_off[blockIdx.x] + excl;
-    u64 ux = upper8(v.x), uy = upper8(v.y);
-    while (m) {
-        int b = __ffs((int)m) - 1; m &= m - 1;
-        u64 w = b < 8 ? ux : uy;
-        *o++ = (u8)(w >> (8 * (b & 7)));
-    }
+    block_compact_store(stage, dst + tile_off[blockIdx.x], excl, m, upper8(v.x), upper8(v.y), tot);
 }
 
 // out[i] = toupper(src[i]), 16 bytes per thread
