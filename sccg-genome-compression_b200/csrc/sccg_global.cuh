@@ -28,6 +28,7 @@ static const int GP_MAX_M = 120;             // window = 2m+1 <= 241 positions
 static_assert(GP_T >= 64 && GP_T % 32 == 0, "64 diagonal probes, one per thread");
 static const int GP_WIN_BYTES = 288;
 static const int GP_FILTER = 512;
+static const int GP_BF = 4;                  // positions tried by brute force before the window filter is built
 static const int GP_SHORT = 64;              // per-thread extension before the block-wide one takes over
 
 // 24-bit hash of the k-mer s[0..k), 8 <= k <= 16; the words may come from global or shared memory.  24 bits = three radix
@@ -111,6 +112,7 @@ struct GpShared {
     u32 f_hash[GP_FILTER];
     u8 f_off[GP_FILTER];
     int i_scratch[8];
+    int bf_hit[4];
     unsigned long long key_scratch;
     int long_list[GP_T > 128 ? GP_T : 128];       // also the 64 diagonal votes (i64) of gp_spec_k
     int long_n;
@@ -288,48 +290,84 @@ __device__ __forceinline__ bool gp_step(GpShared& S, const GpArgs& a, i64& j, in
     const int wbytes = wlen + k - 1;
     for (int x = tid; x < GP_FILTER; x += GP_T) S.f_hash[x] = 0u;
     for (int x = tid; x < GP_WIN_BYTES; x += GP_T) S.win[x] = x < wbytes ? a.R[wlo + x] : (u8)0;
+    if (tid < GP_BF) S.bf_hit[tid] = 0;
     __syncthreads();
-    for (int x = tid; x < wlen; x += GP_T) {
-        u32 h = kmer_hash_words(ld_unaligned64(S.win + x), ld_unaligned64(S.win + x + 8), k) | 1u;
-        u32 slot = (h >> 1) & (GP_FILTER - 1);
-        while (atomicCAS(&S.f_hash[slot], 0u, h) != 0u) slot = (slot + 1) & (GP_FILTER - 1);
-        S.f_off[slot] = (u8)x;
-    }
-    __syncthreads();
-    for (; j < scan_end; j += GP_T) {
-        i64 pos = j + tid;
-        bool hit = false;
-        if (pos < scan_end) {
-            u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
-            u32 h = kmer_hash_words(w0, w1, k) | 1u;
-            u32 slot = (h >> 1) & (GP_FILTER - 1);
-            for (u32 fh; (fh = S.f_hash[slot]) != 0u && !hit; slot = (slot + 1) & (GP_FILTER - 1)) {
-                if (fh == h) {
-                    const u8* wp = S.win + S.f_off[slot];
-                    hit = kmer_equal_words(ld_unaligned64(wp), ld_unaligned64(wp + 8), w0, w1, k);
-                }
+    // The first GP_BF positions by brute force: one thread per window position compares its k-mer with the k-mers at
+    // j .. j + GP_BF - 1.  After a substitution the parse resumes one or two positions later on the same diagonal, and
+    // then neither the filter nor the scan round is needed (the threads that hit ARE the candidate list).
+    bool have_cand = false;
+    i64 cand = -1;
+    if (GP_T >= 2 * GP_MAX_M + 1) {
+        const int np = scan_end - j < GP_BF ? (int)(scan_end - j) : GP_BF;
+        u32 mymask = 0u;
+        if (tid < wlen) {
+            const u64 t0 = ld_unaligned64(a.T + j), t1 = ld_unaligned64(a.T + j + 8), t2 = ld_unaligned64(a.T + j + 16);
+            const u64 w0 = ld_unaligned64(S.win + tid), w1 = ld_unaligned64(S.win + tid + 8);
+#pragma unroll
+            for (int q = 0; q < GP_BF; ++q) {
+                const u64 a0 = q ? (t0 >> (8 * q)) | (t1 << (64 - 8 * q)) : t0;
+                const u64 a1 = q ? (t1 >> (8 * q)) | (t2 << (64 - 8 * q)) : t1;
+                if (q < np && kmer_equal_words(w0, w1, a0, a1, k)) { mymask |= 1u << q; S.bf_hit[q] = 1; }
             }
         }
-        if (tid == 0) S.i_scratch[4] = 0x7fffffff;
-        if (__syncthreads_or(hit)) {
-            if (hit) atomicMin(&S.i_scratch[4], tid);
-            __syncthreads();
-            found = j + S.i_scratch[4];
-            __syncthreads();
-            break;
+        __syncthreads();
+        int first = -1;
+#pragma unroll
+        for (int q = GP_BF - 1; q >= 0; --q) if (q < np && S.bf_hit[q]) first = q;
+        if (first >= 0) {
+            found = j + first;
+            have_cand = true;
+            if ((mymask >> first) & 1u) cand = wlo + tid;
+        } else {
+            j += np;                                           // no candidate in range at these positions: literals
+            if (j >= scan_end) { j = scan_end; __syncthreads(); return false; }       // (bf_hit is rewritten by the next call)
         }
     }
-    if (found < 0) { j = scan_end; return false; }
+    if (!have_cand) {
+        for (int x = tid; x < wlen; x += GP_T) {
+            u32 h = kmer_hash_words(ld_unaligned64(S.win + x), ld_unaligned64(S.win + x + 8), k) | 1u;
+            u32 slot = (h >> 1) & (GP_FILTER - 1);
+            while (atomicCAS(&S.f_hash[slot], 0u, h) != 0u) slot = (slot + 1) & (GP_FILTER - 1);
+            S.f_off[slot] = (u8)x;
+        }
+        __syncthreads();
+        for (; j < scan_end; j += GP_T) {
+            i64 pos = j + tid;
+            bool hit = false;
+            if (pos < scan_end) {
+                u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
+                u32 h = kmer_hash_words(w0, w1, k) | 1u;
+                u32 slot = (h >> 1) & (GP_FILTER - 1);
+                for (u32 fh; (fh = S.f_hash[slot]) != 0u && !hit; slot = (slot + 1) & (GP_FILTER - 1)) {
+                    if (fh == h) {
+                        const u8* wp = S.win + S.f_off[slot];
+                        hit = kmer_equal_words(ld_unaligned64(wp), ld_unaligned64(wp + 8), w0, w1, k);
+                    }
+                }
+            }
+            if (tid == 0) S.i_scratch[4] = 0x7fffffff;
+            if (__syncthreads_or(hit)) {
+                if (hit) atomicMin(&S.i_scratch[4], tid);
+                __syncthreads();
+                found = j + S.i_scratch[4];
+                __syncthreads();
+                break;
+            }
+        }
+        if (found < 0) { j = scan_end; return false; }
+    }
     j = found;
     // in-range candidates: the window positions whose k-mer equals T[j..j+k)  (pn2 / ln2, :116-123)
     fold_reset(S);
-    {
+    if (have_cand) {
+        fold_chunk(S, a, cand, j, e);
+    } else {
         const u64 w0 = ld_unaligned64(a.T + j), w1 = ld_unaligned64(a.T + j + 8);
         for (int x0 = 0; x0 < wlen; x0 += GP_T) {                // the fold is order-independent: one thread-wide slice at a time
             const int x = x0 + tid;
-            i64 cand = -1;
-            if (x < wlen && kmer_equal_words(ld_unaligned64(S.win + x), ld_unaligned64(S.win + x + 8), w0, w1, k)) cand = wlo + x;
-            fold_chunk(S, a, cand, j, e);
+            i64 cd = -1;
+            if (x < wlen && kmer_equal_words(ld_unaligned64(S.win + x), ld_unaligned64(S.win + x + 8), w0, w1, k)) cd = wlo + x;
+            fold_chunk(S, a, cd, j, e);
         }
     }
     sel_p = fold_result_p(S); sel_l = S.best_l;
@@ -607,8 +645,9 @@ __global__ void g_write_tokens_k(const int* __restrict__ tpos, const int* __rest
     write_token(out + *d_body_base + offs[i] + (u32)(tpos[i] - prev_end), mp[i] - prev_p, ml[i]);
 }
 // literal symbols: every target position not covered by a match.  GL_SPAN positions per thread: one binary search, then
-// the thread walks the GAPS that intersect its span (a span inside one long match costs the search and nothing else)
-static const int GL_SPAN = 64;
+// the thread walks the GAPS that intersect its span (a span inside one long match costs the search and nothing else).
+// Long spans suit match-dominated bodies (few searches); literal-dominated bodies want short ones (coalescing).
+template <int GL_SPAN>
 __global__ void __launch_bounds__(256) g_write_literals_k(const u8* __restrict__ T, i64 nt, const int* __restrict__ tpos, const int* __restrict__ ml, u32 M,
                                                          const u32* __restrict__ offs, const u32* __restrict__ d_tok_total, u8* __restrict__ out,
                                                          const u32* __restrict__ d_body_base) {
@@ -785,8 +824,14 @@ static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8
     if (n_text) SCCG_CK(cudaMemcpyAsync(out + hdr_bytes + low_text + 1, ntext, n_text, cudaMemcpyDeviceToDevice, c->stream));
     if (M) LAUNCH(c, g_write_tokens_k, dim3(div_up(M, 256)), dim3(256), 0, (const int*)gm.tpos, (const int*)gm.p, (const int*)gm.l, M,
                   (const u32*)mbytes, out, (const u32*)(sc + S_BODY_BASE), text_delta);
-    if (nt2 > 0) LAUNCH(c, g_write_literals_k, dim3(div_up(nt2, 256 * GL_SPAN)), dim3(256), 0, (const u8*)T2, nt2, (const int*)gm.tpos, (const int*)gm.l, M,
-                        (const u32*)mbytes, (const u32*)(sc + S_G4), out, (const u32*)(sc + S_BODY_BASE));
+    if (nt2 > 0) {
+        if ((i64)body_bytes * 4 > nt2)                            // literal-heavy body
+            LAUNCH(c, g_write_literals_k<16>, dim3(div_up(nt2, 256 * 16)), dim3(256), 0, (const u8*)T2, nt2, (const int*)gm.tpos, (const int*)gm.l, M,
+                   (const u32*)mbytes, (const u32*)(sc + S_G4), out, (const u32*)(sc + S_BODY_BASE));
+        else
+            LAUNCH(c, g_write_literals_k<64>, dim3(div_up(nt2, 256 * 64)), dim3(256), 0, (const u8*)T2, nt2, (const int*)gm.tpos, (const int*)gm.l, M,
+                   (const u32*)mbytes, (const u32*)(sc + S_G4), out, (const u32*)(sc + S_BODY_BASE));
+    }
     SCCG_CK(cudaEventRecord(c->ev[3], c->stream));
     SCCG_CK(cudaStreamSynchronize(c->stream));
     res->d_out = out;
