@@ -34,8 +34,15 @@ static const int GP_SHORT = 64;              // per-thread extension before the 
 // 24-bit hash of the k-mer s[0..k), 8 <= k <= 16; the words may come from global or shared memory.  24 bits = three radix
 // passes for the index; k-mers that share a hash are told apart by comparing the symbols (every consumer does).
 static const int GP_HASH_BITS = 24;
-static const int GP_BUCKET_BITS = 20;         // top bits of the hash that address the offset table (4 MB)
-static const int GP_BUCKET_SHIFT = GP_HASH_BITS - GP_BUCKET_BITS;
+// The offset table over the sorted keys is addressed by the top `bits` bits of the hash: 20 bits (4 MB, L2-resident, a few
+// dozen keys per bucket) for chromosome-sized indexes, fewer for small ones so that filling the table stays proportional
+// to the index.  (All 24 bits -- one bucket per hash value, no search through the keys -- measured no faster.)
+static const int GP_BUCKET_BITS_MAX = 20;
+__host__ __device__ inline int gp_bucket_bits(i64 nk) {
+    int b = 12;
+    while (b < GP_BUCKET_BITS_MAX && ((i64)1 << (b + 1)) <= nk) ++b;
+    return b;
+}
 __device__ __forceinline__ u32 kmer_hash_words(u64 w0, u64 w1, int k) {
     if (k < 16) w1 &= (k == 8) ? 0ull : (~0ull >> (8 * (16 - k)));
     u64 x = (w0 * 0x9E3779B97F4A7C15ULL) ^ ((w1 + 0x632BE59BD9B4E019ULL) * 0xD6E8FEB86659FD93ULL);
@@ -79,10 +86,11 @@ struct KmerPairSource {
     }
 };
 
-// bucket[b] for every b in [0, 2^GP_BUCKET_BITS]: index i owns the buckets that begin between keys[i-1] and keys[i]
+// bucket[b] for every b in [0, 2^bits]: index i owns the buckets that begin between keys[i-1] and keys[i]
 // (i = nk: the buckets past the last key).  8 indices per thread (two 16-byte loads; one index per thread was latency-bound).
 static const int KB_SPAN = 8;
-__global__ void __launch_bounds__(256) kmer_buckets_k(const u32* __restrict__ keys, i64 nk, u32* __restrict__ bucket) {
+__global__ void __launch_bounds__(256) kmer_buckets_k(const u32* __restrict__ keys, i64 nk, u32* __restrict__ bucket, int bits) {
+    const int shift = GP_HASH_BITS - bits;
     const i64 i0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * KB_SPAN;
     if (i0 > nk) return;
     u32 kk[KB_SPAN];
@@ -93,12 +101,12 @@ __global__ void __launch_bounds__(256) kmer_buckets_k(const u32* __restrict__ ke
 #pragma unroll
         for (int j = 0; j < KB_SPAN; ++j) kk[j] = i0 + j < nk ? keys[i0 + j] : 0u;
     }
-    u32 prev = i0 == 0 ? 0u : (keys[i0 - 1] >> GP_BUCKET_SHIFT) + 1u;      // first bucket not yet assigned
+    u32 prev = i0 == 0 ? 0u : (keys[i0 - 1] >> shift) + 1u;                // first bucket not yet assigned
 #pragma unroll
     for (int j = 0; j < KB_SPAN; ++j) {
         const i64 i = i0 + j;
         if (i > nk) break;
-        const u32 hi = i == nk ? (1u << GP_BUCKET_BITS) : (kk[j] >> GP_BUCKET_SHIFT);
+        const u32 hi = i == nk ? (1u << bits) : (kk[j] >> shift);
         for (u32 bkt = prev; bkt <= hi; ++bkt) bucket[bkt] = (u32)i;
         prev = hi + 1u;
     }
@@ -128,7 +136,8 @@ struct GpArgs {
     const u8* R; i64 nr;          // N-stripped, upper-cased reference
     const u8* T; i64 nt;          // N-stripped, upper-cased target
     const u32* keys; const u32* vals; i64 nk;
-    const u32* bucket;            // bucket[b] = first index whose key >> GP_BUCKET_SHIFT is >= b (2^GP_BUCKET_BITS + 1 entries, L2-resident)
+    const u32* bucket;            // bucket[b] = first index whose key >> bucket_shift is >= b (2^bits + 1 entries)
+    int bucket_shift;             // GP_HASH_BITS - bits; 0: a bucket is exactly one key value
     int k, m;
     int* m_tpos; int* m_p; int* m_l;   // out: matches
     u32* d_count;                      // out: number of matches
@@ -136,7 +145,9 @@ struct GpArgs {
 
 // first index whose key is >= h: the offset table narrows the search to one bucket (a few dozen entries)
 __device__ __forceinline__ i64 index_lower_bound(const GpArgs& a, u32 h) {
-    i64 lo = a.bucket[h >> GP_BUCKET_SHIFT], hi = a.bucket[(h >> GP_BUCKET_SHIFT) + 1];
+    i64 lo = a.bucket[h >> a.bucket_shift];
+    if (a.bucket_shift == 0) return lo;                         // the bucket IS the run of this key (empty run: keys[lo] != h)
+    i64 hi = a.bucket[(h >> a.bucket_shift) + 1];
     while (lo < hi) { i64 mid = (lo + hi) >> 1; if (a.keys[mid] < h) lo = mid + 1; else hi = mid; }
     return lo;
 }
@@ -410,7 +421,10 @@ struct GpSpecArgs {
     int lost_e;                 // slot 1: the e every chunk is entered with
 };
 
-__global__ void __launch_bounds__(GP_T) gp_spec_k(GpSpecArgs s) {
+#ifndef SCCG_GP_MINB
+#define SCCG_GP_MINB 6            // 256-thread CTAs: 48 warps/SM at <= 40 registers (measured 4 / 5 / 6 CTAs: 2.60 / 2.51 / 2.47 ms on the gap pair)
+#endif
+__global__ void __launch_bounds__(GP_T, SCCG_GP_MINB) gp_spec_k(GpSpecArgs s) {
     __shared__ GpShared S;
     const GpArgs& a = s.a;
     const int tid = (int)threadIdx.x;
@@ -696,8 +710,10 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
         keys = sk; vals = sv;
     }
     u32* bucket = nullptr;
-    SCCG_TRY(buf(c, B_GBUCKET, ((size_t)1 << GP_BUCKET_BITS) + 2, &bucket));
-    LAUNCH(c, kmer_buckets_k, dim3(div_up(nk + 1, 256 * KB_SPAN)), dim3(256), 0, (const u32*)keys, nk, bucket);
+    int bucket_bits = gp_bucket_bits(nk);
+    if (const char* env = getenv("SCCG_GP_BUCKET_BITS")) { int v = atoi(env); if (v >= 4 && v <= GP_HASH_BITS) bucket_bits = v; }    // tests: small inputs through the 24-bit path
+    SCCG_TRY(buf(c, B_GBUCKET, ((size_t)1 << bucket_bits) + 2, &bucket));
+    LAUNCH(c, kmer_buckets_k, dim3(div_up(nk + 1, 256 * KB_SPAN)), dim3(256), 0, (const u32*)keys, nk, bucket, bucket_bits);
     // ---- chunk-speculative parse (:64-161)
     int chunk = GP_CHUNK_DEFAULT;
     if (const char* env = getenv("SCCG_GP_CHUNK")) { int v = atoi(env); if (v >= 64 && v <= (1 << 24)) chunk = v; }
@@ -717,7 +733,7 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
     h_st.j = 0; h_st.e = -1; h_st.status = GP_RUNNING;
     SCCG_CK(cudaMemcpyAsync(st, &h_st, sizeof h_st, cudaMemcpyHostToDevice, c->stream));
     GpFrontArgs f;
-    f.s.a.R = R; f.s.a.nr = nr; f.s.a.T = T; f.s.a.nt = nt; f.s.a.keys = keys; f.s.a.vals = vals; f.s.a.nk = nk; f.s.a.bucket = bucket; f.s.a.k = k; f.s.a.m = m;
+    f.s.a.R = R; f.s.a.nr = nr; f.s.a.T = T; f.s.a.nt = nt; f.s.a.keys = keys; f.s.a.vals = vals; f.s.a.nk = nk; f.s.a.bucket = bucket; f.s.a.bucket_shift = GP_HASH_BITS - bucket_bits; f.s.a.k = k; f.s.a.m = m;
     f.s.a.m_tpos = nullptr; f.s.a.m_p = nullptr; f.s.a.m_l = nullptr; f.s.a.d_count = nullptr;
     f.s.info = info; f.s.c_tpos = cbuf; f.s.c_p = cbuf + (size_t)2 * nchunks * cap_c; f.s.c_l = cbuf + (size_t)4 * nchunks * cap_c;
     f.s.nchunks = nchunks; f.s.cap_c = cap_c; f.s.chunk = chunk; f.s.slot = 0; f.s.first_chunk = 0; f.s.lost_e = 0;

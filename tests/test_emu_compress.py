@@ -337,3 +337,21 @@ def test_compress_device_abort_probe(ctx, shape):
     got, gmode = _compress_device_emu(ctx, ref, tgt, b">probe")
     assert (gmode, got) == (mode, exp)
     assert mode == (1 if shape in ("shifted_tail", "reference_insertion") else 0)
+
+
+@pytest.mark.parametrize("bits", [4, 16, 24])
+@pytest.mark.parametrize("seed", [1, 2, 3, 6])
+def test_global_index_bucket_table_widths(ctx, seed, bits, monkeypatch):
+    """the offset table over the sorted k-mer index at forced widths: 24 bits = one bucket per hash value (no search through
+    the keys, the width large references get), 4 bits = long binary searches inside a bucket"""
+    monkeypatch.setenv("SCCG_GP_BUCKET_BITS", str(bits))
+    monkeypatch.setenv("SCCG_GP_CHUNK", "300")
+    alphabet = [b"ACGT", b"AC"][seed % 2]                      # AC: many equal k-mers, long candidate runs
+    n = 6000 if alphabet == b"ACGT" else 2500
+    ref, tgt = _mutated_pair(("bkt", seed), n, alphabet, snp=0.01, indel=0.002)
+    r = random.Random(seed)
+    cut = sorted(r.sample(range(len(tgt)), 2))
+    tgt = tgt[cut[1]:] + tgt[cut[0]:cut[1]] + tgt[:cut[0]]     # rearranged: unrestricted lookups after every block boundary
+    exp = [(x.p, x.l, x.lit) for x in ol.orc_match_sequences(ref, tgt, 14, 100, True, 0)]
+    got = [(x.p, x.l, x.lit) for x in ctx.match_sequences(ref, tgt, 14, 100, True, 0)]
+    assert got == exp
