@@ -64,7 +64,7 @@ sccg_ctx* sccg_create(int device) {
     bool ok = cudaStreamCreate(&c->main_stream) == cudaSuccess && cudaStreamCreate(&c->side_stream) == cudaSuccess &&
               cudaMallocHost(&c->h_pinned, c->h_pinned_cap) == cudaSuccess;
     c->stream = c->main_stream;
-    for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreate(&c->ev_side[i]) == cudaSuccess;
+    for (int i = 0; ok && i < 6; ++i) ok = cudaEventCreate(&c->ev_side[i]) == cudaSuccess;
     for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
     if (!ok) { set_error(SCCG_E_CUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError())); sccg_destroy(c); return nullptr; }
     return c;
@@ -78,7 +78,7 @@ void sccg_destroy(sccg_ctx* c) {
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->main_stream) cudaStreamDestroy(c->main_stream);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
-    for (int i = 0; i < 4; ++i) if (c->ev_side[i]) cudaEventDestroy(c->ev_side[i]);
+    for (int i = 0; i < 6; ++i) if (c->ev_side[i]) cudaEventDestroy(c->ev_side[i]);
     if (c->pipe_ready) {
         cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h);
         for (int i = 0; i < 2; ++i) cudaEventDestroy(c->ev_pipe[i]);

@@ -719,9 +719,7 @@ static int reconstruct_prepare(sccg_ctx* c, i64 nr, const u8* d_enc, i64 ne, con
     SCCG_TRY(buf(c, B_TOK_FLAG, th_stride * 3 + 4, &th_sym));
     th_seg = th_sym + th_stride; th_tok = th_seg + th_stride;
     if (ne > 0) LAUNCH(c, dec_count_k, dim3(dblocks), dim3(DEC_T), 0, d_enc, ne, th_sym, th_seg, th_tok, sc);
-    SCCG_TRY(scan_exclusive_u32(c, th_sym, th_sym, nth, sc + D_LS));
-    SCCG_TRY(scan_exclusive_u32(c, th_seg, th_seg, nth, sc + D_NSEG));
-    SCCG_TRY(scan_exclusive_u32(c, th_tok, th_tok, nth, sc + D_NTOK));
+    SCCG_TRY(scan_exclusive_u32x3(c, th_sym, th_stride, nth, sc + D_LS, sc + D_NSEG, sc + D_NTOK));     // three counters, one launch
     // ---- the two run lists are parsed on the side lane while the tokenizer kernels run
     {
         SideLane side(c);
@@ -748,6 +746,7 @@ static int reconstruct_prepare(sccg_ctx* c, i64 nr, const u8* d_enc, i64 ne, con
     if (ne > 0) {
         LAUNCH(c, dec_emit_k, dim3(dblocks), dim3(DEC_T), 0, d_enc, ne, (const u32*)th_sym, (const u32*)th_seg, (const u32*)th_tok, seg_dst, seg_src, tok_delta, tok_len);
     }
+    SCCG_CK(cudaEventRecord(c->ev_side[4], c->stream));                         // seg_dst complete: the per-tile windows can be searched (side lane)
     if (ntok > 0) {
         SCCG_TRY(scan_exclusive_u32(c, (const u32*)tok_delta, delta_excl, (i64)ntok, nullptr));
     }
@@ -776,14 +775,20 @@ static int reconstruct_prepare(sccg_ctx* c, i64 nr, const u8* d_enc, i64 ne, con
     a.Ls = Ls; a.Lm = Lm; a.total = total; a.out = out + header_reserve; a.tile0 = 0;
     plan->sc = sc; plan->tok_len = tok_len; plan->ntok = ntok; plan->ntiles = div_up(total, GATHER_TILE);
     // resolved segment sources and per-tile entry points: the gather itself starts from two table loads
-    SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[3], 0));                  // run tables complete (device-side wait)
     i64* seg_ptr = nullptr; int4* tile_win = nullptr;
     SCCG_TRY(buf(c, B_SEG_PTR, (size_t)nseg + 1, &seg_ptr));
     SCCG_TRY(buf(c, B_TILE_WIN, (size_t)plan->ntiles + 1, &tile_win));
+    a.seg_ptr = seg_ptr; a.tile_win = tile_win;
+    {   // the window searches need the run tables (made on the side lane) and seg_dst: they run there, next to the token scan
+        // and dec_resolve_k of the main lane
+        SideLane side(c);
+        SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[4], 0));
+        LAUNCH(c, dec_tile_win_k, dim3(div_up(plan->ntiles, 128)), dim3(128), 0, a, plan->ntiles, tile_win);
+        SCCG_CK(cudaEventRecord(c->ev_side[5], c->stream));
+    }
     if (nseg) LAUNCH(c, dec_resolve_k, dim3(div_up(nseg, 256)), dim3(256), 0, (const i64*)seg_src, (const int*)tok_delta, (const int*)tok_len,
                      (const u32*)delta_excl, (int)nseg, nr, tok_abs, seg_ptr, sc);
-    a.seg_ptr = seg_ptr; a.tile_win = tile_win;
-    LAUNCH(c, dec_tile_win_k, dim3(div_up(plan->ntiles, 128)), dim3(128), 0, a, plan->ntiles, tile_win);
+    SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[5], 0));                  // run tables + windows complete (device-side wait)
     SCCG_CK(cudaEventRecord(c->ev[1], c->stream));                              // everything up to here is "tokenizer" time
     return SCCG_OK;
 }

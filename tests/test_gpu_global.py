@@ -70,3 +70,47 @@ def test_compress_global_synthetic_vs_oracle(ctx, shape, n):
     back = ctx.decompress(ref, got)
     rc, oback = ol.orc_decompress(ref, exp)
     assert rc == 0 and back == oback
+
+
+def _compress_device(ctx, ref: bytes, tgt: bytes, header: bytes):
+    import torch
+    dr = torch.frombuffer(bytearray(ref + bytes(64)), dtype=torch.uint8).cuda()
+    dt = torch.frombuffer(bytearray(tgt + bytes(64)), dtype=torch.uint8).cuda()
+    ptr, n, mode = ctx.compress_device(dr.data_ptr(), len(ref), dt.data_ptr(), len(tgt), header)
+    return ctx.download(ptr, n), mode, ctx.profile()["launches"]
+
+
+@pytest.mark.parametrize("shape", ["gap", "divergent", "shifted_tail", "leftover_only", "small_shift"])
+def test_compress_device_abort_probe(ctx, shape):
+    """device-resident entry point on pairs of different length: the abort probe over the last segments runs first
+    (DESIGN 4.7c).  Aborting or not, the file is the oracle's."""
+    from sccg_genome_compression_b200 import synth
+    if shape == "gap":
+        ref, tgt = synth.global_gap_pair(3_240_000, 3_000_000, synth.seed_for(1, 9)); ref, tgt = ref.tobytes(), tgt.tobytes()
+    elif shape == "divergent":
+        ref, tgt = synth.divergent_pair(2_000_000, synth.seed_for(3, 9)); ref, tgt = ref.tobytes(), tgt.tobytes()
+    else:
+        ref, t = synth.local_pair(2_000_000, synth.seed_for(2, 9)); ref, t = ref.tobytes(), t.tobytes()
+        if shape == "shifted_tail":
+            tgt = t[:600_000] + t[603_000:]                               # a 3 kb deletion: the rest is three segments off
+        elif shape == "leftover_only":
+            tgt = t + rnd(5_000, "extra")                                 # no shift, leftover target segments
+        else:
+            tgt = t[:900_000] + b"ACGTTGCAAC" * 3 + t[900_000:] + rnd(1_200, "tail")    # 30 symbols off: still matches inside the segments
+    rc, exp, mode = ol.orc_compress(ref, tgt, b">probe")
+    assert rc == 0
+    got, gmode, _ = _compress_device(ctx, ref, tgt, b">probe")
+    assert (gmode, got) == (mode, exp)
+    assert mode == (0 if shape in ("leftover_only", "small_shift") else 1)
+
+
+@pytest.mark.parametrize("bits", [8, 20, 24])
+def test_global_index_bucket_table_widths(ctx, bits, monkeypatch):
+    """offset table over the sorted index at forced widths (24 = one bucket per hash value)"""
+    from sccg_genome_compression_b200 import synth
+    monkeypatch.setenv("SCCG_GP_BUCKET_BITS", str(bits))
+    ref, tgt = synth.divergent_pair(1_500_000, synth.seed_for(3, 11))
+    ref, tgt = ref.tobytes(), tgt.tobytes()
+    rc, exp, mode = ol.orc_compress(ref, tgt, b">bkt")
+    got, gmode = ctx.compress(ref, tgt, b">bkt")
+    assert rc == 0 and (gmode, got) == (mode, exp)
