@@ -127,6 +127,18 @@ int sccg_decompress_into(sccg_ctx* ctx, const char* ref_raw, int64_t ref_len, co
 int sccg_decompress_part(sccg_ctx* ctx, const char* ref_raw, int64_t ref_len, const char* intermediate, int64_t inter_len,
                          int part, int n_parts, char* out, int64_t out_cap, int64_t* part_offset, int64_t* part_len, int64_t* total_len);
 
+/* Many targets against one reference (the reference repository's use case: every individual's chromosome against the same
+ * reference chromosome, one `compress` / `decompress` process per pair -- compression.cpp:591-620, decompression.cpp:325-350 --
+ * each of which re-reads the reference).  sccg_reference_set uploads the raw reference symbols once and keeps them in device
+ * memory; the *_resident calls then move only the target (or the record file and the reconstructed text) over PCIe and give
+ * exactly the bytes of sccg_compress_into / sccg_decompress_into with that reference.  The caller's reference buffer is free
+ * again when sccg_reference_set returns. */
+int sccg_reference_set(sccg_ctx* ctx, const char* ref, int64_t ref_len);
+int sccg_reference_clear(sccg_ctx* ctx);
+int sccg_compress_resident_into(sccg_ctx* ctx, const char* tgt, int64_t tgt_len, const char* header, int64_t header_len,
+                                char* out, int64_t out_cap, int64_t* out_len, int* mode_out);
+int sccg_decompress_resident_into(sccg_ctx* ctx, const char* intermediate, int64_t inter_len, char* out, int64_t out_cap, int64_t* out_len);
+
 /* FASTA file images in: read_genomes_from_files (compression.cpp:181-220) and the reference reader of decompress_genome
  * (decompression.cpp:47-58) run on the device -- header lines skipped ('>' at a line start; in the target only the first one,
  * which becomes the header line of the output), isspace() bytes removed -- followed by sccg_compress / sccg_decompress.

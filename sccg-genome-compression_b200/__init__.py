@@ -114,6 +114,10 @@ def load_library(path: str | os.PathLike | None = None) -> C.CDLL:
     lib.sccg_decompress_part.argtypes = [vp, cp, i64, cp, i64, C.c_int, C.c_int, vp, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     lib.sccg_shard_match.argtypes = [vp, cp, i64, cp, i64, i64, C.c_int, C.POINTER(ShardInfo)]
     lib.sccg_shard_write.argtypes = [vp, C.POINTER(ShardCarry), C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64)]
+    lib.sccg_reference_set.argtypes = [vp, cp, i64]
+    lib.sccg_reference_clear.argtypes = [vp]
+    lib.sccg_compress_resident_into.argtypes = [vp, cp, i64, cp, i64, vp, i64, C.POINTER(i64), C.POINTER(C.c_int)]
+    lib.sccg_decompress_resident_into.argtypes = [vp, cp, i64, vp, i64, C.POINTER(i64)]
     lib.sccg_compress_fasta.argtypes = [vp, cp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_int)]
     lib.sccg_decompress_fasta.argtypes = [vp, cp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64)]
     _libs[key] = lib
@@ -235,6 +239,47 @@ class Context:
         self._check(self.lib.sccg_decompress_part(self.handle, _as_char_p(ref_raw), len(ref_raw), intermediate, len(intermediate), part, n_parts,
                                                   C.cast(buf, C.c_void_p), cap, C.byref(off), C.byref(n), C.byref(total)))
         return off.value, buf.raw[:n.value], total.value
+
+    # many targets against one reference: the reference stays in device memory (include/sccg.h)
+    def set_reference(self, ref) -> None:
+        """ref: bytes or a C-contiguous uint8 numpy array (raw symbols, as read_genomes_from_files yields them)"""
+        self._check(self.lib.sccg_reference_set(self.handle, _as_char_p(ref), len(ref)))
+
+    def clear_reference(self) -> None:
+        self._check(self.lib.sccg_reference_clear(self.handle))
+
+    def compress_resident(self, tgt, header: bytes = b"", out_ptr: int = 0, out_cap: int = 0):
+        """compress against the resident reference -> (file image, mode); with out_ptr / out_cap the image is written into
+        the caller's (page-locked) buffer and (length, mode) is returned"""
+        n = C.c_int64(); mode = C.c_int()
+        if out_ptr:
+            self._check(self.lib.sccg_compress_resident_into(self.handle, _as_char_p(tgt), len(tgt), header, len(header), out_ptr, out_cap, C.byref(n), C.byref(mode)))
+            return n.value, mode.value
+        cap = 2 * len(tgt) + len(header) + 4096
+        while True:
+            buf = C.create_string_buffer(cap)
+            rc = self.lib.sccg_compress_resident_into(self.handle, _as_char_p(tgt), len(tgt), header, len(header), C.cast(buf, C.c_void_p), cap, C.byref(n), C.byref(mode))
+            if rc != 0 and n.value > cap:                       # too small: the required size came back
+                cap = n.value
+                continue
+            self._check(rc)
+            return buf.raw[:n.value], mode.value
+
+    def decompress_resident(self, intermediate: bytes, out_ptr: int = 0, out_cap: int = 0):
+        """decompress against the resident reference -> file image (or its length with out_ptr / out_cap)"""
+        n = C.c_int64()
+        if out_ptr:
+            self._check(self.lib.sccg_decompress_resident_into(self.handle, intermediate, len(intermediate), out_ptr, out_cap, C.byref(n)))
+            return n.value
+        cap = 4096
+        while True:
+            buf = C.create_string_buffer(cap)
+            rc = self.lib.sccg_decompress_resident_into(self.handle, intermediate, len(intermediate), C.cast(buf, C.c_void_p), cap, C.byref(n))
+            if rc != 0 and n.value > cap:
+                cap = n.value + 16
+                continue
+            self._check(rc)
+            return buf.raw[:n.value]
 
     # one chromosome over several GPUs: segment-range shards (include/sccg.h, sharding.py)
     def shard_match(self, ref_slice, tgt_slice, seg_base: int, is_last: bool) -> dict:

@@ -75,6 +75,7 @@ void sccg_destroy(sccg_ctx* c) {
     cudaSetDevice(c->device);
     for (int i = 0; i < B_NSLOTS; ++i) if (c->bufs[i].p) cudaFree(c->bufs[i].p);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->res_ref) cudaFree(c->res_ref);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->main_stream) cudaStreamDestroy(c->main_stream);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
@@ -139,12 +140,16 @@ static int compress_host(sccg_ctx* c, const char* ref, int64_t ref_len, const ch
     SCCG_TRY(pipe_streams(c));
     SCCG_TRY(buf(c, B_REF, (size_t)ref_len + 128, &d_ref));
     SCCG_TRY(buf(c, B_TGT, (size_t)tgt_len + 128, &d_tgt));
+    if (getenv("SCCG_PIPE_POISON")) {                                         // tests: a chunk read before it arrived shows up
+        SCCG_CK(cudaMemsetAsync(d_tgt, 0xEE, (size_t)tgt_len, c->stream));
+        SCCG_CK(cudaMemsetAsync(d_ref, 0xEE, (size_t)ref_len, c->stream));
+    }
     SCCG_CK(cudaEventRecord(c->ev[4], c->stream));
     SCCG_CK(cudaStreamWaitEvent(c->s_h2d, c->ev[4], 0));
     ChunkArrival arr;
     arr.chunk = pipe_chunk_bytes(ref_len);
     arr.n = ref_len > 0 ? (int)((ref_len + arr.chunk - 1) / arr.chunk) : 0;
-    arr.ev_ref = c->ev_h2d; arr.ev_tgt = c->ev_pipe[1];
+    arr.ev_ref = c->ev_h2d; arr.ev_tgt = c->ev_pipe[1]; arr.tgt_chunked = 0;
     if (tgt_len > 0) SCCG_CK(cudaMemcpyAsync(d_tgt, tgt, (size_t)tgt_len, cudaMemcpyHostToDevice, c->s_h2d));
     SCCG_CK(cudaEventRecord(arr.ev_tgt, c->s_h2d));
     for (int i = 0; i < arr.n; ++i) {
@@ -177,6 +182,86 @@ int sccg_compress_into(sccg_ctx* c, const char* ref, int64_t ref_len, const char
                        const char* header, int64_t header_len, char* out, int64_t out_cap, int64_t* out_len, int* mode_out) {
     if (!out) return set_error(SCCG_E_ARG, "null argument");
     return compress_host(c, ref, ref_len, tgt, tgt_len, header, header_len, out, out_cap, nullptr, out_len, mode_out);
+}
+
+// ---- resident reference: many targets against one reference (the reference goes over PCIe once) ------------------------
+int sccg_reference_set(sccg_ctx* c, const char* ref, int64_t ref_len) {
+    if (!c || ref_len < 0 || (ref_len > 0 && !ref)) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_TRY(check_sizes(ref_len, 0));
+    SCCG_CK(cudaSetDevice(c->device));
+    const size_t need = (size_t)ref_len + 128;
+    if (need > c->res_ref_cap) {
+        if (c->res_ref) { SCCG_CK(cudaStreamSynchronize(c->main_stream)); cudaFree(c->res_ref); c->res_ref = nullptr; c->res_ref_cap = 0; }
+        void* p = nullptr;
+        if (cudaMalloc(&p, need) != cudaSuccess) { cudaGetLastError(); c->res_ref_len = -1; return set_error(SCCG_E_NOMEM, "cudaMalloc of the resident reference failed"); }
+        c->res_ref = (u8*)p; c->res_ref_cap = need;
+    }
+    if (ref_len > 0) SCCG_CK(cudaMemcpyAsync(c->res_ref, ref, (size_t)ref_len, cudaMemcpyHostToDevice, c->main_stream));
+    SCCG_CK(cudaMemsetAsync(c->res_ref + ref_len, 0, 128, c->main_stream));
+    SCCG_CK(cudaStreamSynchronize(c->main_stream));                            // the caller's buffer is free again
+    c->res_ref_len = ref_len;
+    c->res_ref_set = 1;
+    return SCCG_OK;
+}
+
+int sccg_reference_clear(sccg_ctx* c) {
+    if (!c) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_CK(cudaSetDevice(c->device));
+    if (c->res_ref) { SCCG_CK(cudaStreamSynchronize(c->main_stream)); cudaFree(c->res_ref); }
+    c->res_ref = nullptr; c->res_ref_cap = 0; c->res_ref_len = 0; c->res_ref_set = 0;
+    return SCCG_OK;
+}
+
+// compress_genome against the resident reference: only the target travels, in chunks, and the matcher starts on every
+// chunk as it lands
+int sccg_compress_resident_into(sccg_ctx* c, const char* tgt, int64_t tgt_len, const char* header, int64_t header_len,
+                                char* dst, int64_t dst_cap, int64_t* out_len, int* mode_out) {
+    if (!c || !dst || !out_len || (tgt_len > 0 && !tgt) || (header_len > 0 && !header)) return set_error(SCCG_E_ARG, "null argument");
+    if (!c->res_ref_set) return set_error(SCCG_E_ARG, "no resident reference (call sccg_reference_set first)");
+    SCCG_TRY(check_sizes(c->res_ref_len, tgt_len));
+    SCCG_TRY(check_header(header, header_len));
+    SCCG_CK(cudaSetDevice(c->device));
+    prof_reset(c);
+    u8* d_tgt = nullptr;
+    SCCG_TRY(pipe_streams(c));
+    SCCG_TRY(buf(c, B_TGT, (size_t)tgt_len + 128, &d_tgt));
+    if (getenv("SCCG_PIPE_POISON")) SCCG_CK(cudaMemsetAsync(d_tgt, 0xEE, (size_t)tgt_len, c->stream));     // tests: a chunk read before it arrived shows up
+    SCCG_CK(cudaEventRecord(c->ev[4], c->stream));
+    SCCG_CK(cudaStreamWaitEvent(c->s_h2d, c->ev[4], 0));
+    ChunkArrival arr;
+    arr.chunk = pipe_chunk_bytes(tgt_len);
+    arr.n = tgt_len > 0 ? (int)((tgt_len + arr.chunk - 1) / arr.chunk) : 0;
+    arr.ev_ref = c->ev_h2d; arr.ev_tgt = c->ev_pipe[1]; arr.tgt_chunked = 1;
+    for (int i = 0; i < arr.n; ++i) {
+        const i64 off = (i64)i * arr.chunk, len = (tgt_len - off) < arr.chunk ? (tgt_len - off) : arr.chunk;
+        SCCG_CK(cudaMemcpyAsync(d_tgt + off, tgt + off, (size_t)len, cudaMemcpyHostToDevice, c->s_h2d));
+        SCCG_CK(cudaEventRecord(arr.ev_ref[i], c->s_h2d));
+    }
+    SCCG_CK(cudaMemsetAsync(d_tgt + tgt_len, 0, 64, c->s_h2d));
+    SCCG_CK(cudaEventRecord(arr.ev_tgt, c->s_h2d));
+    SCCG_CK(cudaEventRecord(c->ev[5], c->s_h2d));
+    CompressResult res;
+    int rc_c = compress_device(c, c->res_ref, c->res_ref_len, d_tgt, tgt_len, header, header_len < 0 ? 0 : header_len, &res, &arr);
+    SCCG_CK(cudaStreamSynchronize(c->s_h2d));                                 // the caller's buffer is no longer in use
+    if (rc_c != SCCG_OK) return rc_c;
+    SCCG_CK(cudaEventRecord(c->ev[6], c->stream));
+    SCCG_TRY(deliver(c, res.d_out, res.out_len, dst, dst_cap, nullptr, out_len));
+    SCCG_CK(cudaEventRecord(c->ev[7], c->stream));
+    SCCG_CK(cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->prof.h2d_ms, c->ev[4], c->ev[5]);
+    cudaEventElapsedTime(&c->prof.d2h_ms, c->ev[6], c->ev[7]);
+    if (mode_out) *mode_out = res.mode;
+    return res.stoi_failed ? stoi_failure() : SCCG_OK;
+}
+
+// decompress_genome against the resident reference: the record file goes up, the text comes back in chunks
+int sccg_decompress_resident_into(sccg_ctx* c, const char* inter, int64_t inter_len, char* out, int64_t out_cap, int64_t* out_len) {
+    if (!c || !out || !out_len || (inter_len > 0 && !inter)) return set_error(SCCG_E_ARG, "null argument");
+    if (!c->res_ref_set) return set_error(SCCG_E_ARG, "no resident reference (call sccg_reference_set first)");
+    SCCG_TRY(check_sizes(c->res_ref_len, inter_len));
+    SCCG_CK(cudaSetDevice(c->device));
+    prof_reset(c);
+    return decompress_host(c, nullptr, c->res_ref_len, inter, inter_len, out, out_cap, nullptr, out_len, c->res_ref);
 }
 
 int sccg_match_sequences(sccg_ctx* c, const char* Sr, int64_t nr, const char* St, int64_t nt,

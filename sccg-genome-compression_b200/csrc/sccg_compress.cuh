@@ -73,10 +73,12 @@ static int write_header(sccg_ctx* c, u8* d_out, const char* header, i64 nh) {
 
 // host entry points: the inputs are still arriving on the copy stream when compress_device starts
 struct ChunkArrival {
-    i64 chunk;               // bytes per reference chunk
-    int n;                   // number of reference chunks
-    cudaEvent_t* ev_ref;     // ev_ref[i]: reference bytes [0, (i + 1) * chunk) are resident
+    i64 chunk;               // bytes per chunk of the sequence that arrives in chunks
+    int n;                   // number of chunks
+    cudaEvent_t* ev_ref;     // ev_ref[i]: bytes [0, (i + 1) * chunk) of the chunked sequence are resident
     cudaEvent_t ev_tgt;      // the whole target is resident
+    int tgt_chunked;         // 0: the target arrives first and whole, the reference in chunks (sccg_compress*)
+                             // 1: the reference is already resident, the TARGET arrives in chunks (sccg_compress_resident*)
 };
 
 static const int LM_PROBE_SEGS = 40;             // segments of the abort probe (see compress_device)
@@ -94,9 +96,9 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
     u64* low_mask = nullptr;
     SCCG_CK(cudaEventRecord(c->ev_side[0], c->stream));
     SCCG_CK(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
-    if (arr) {                                                                // both lanes need the whole target
+    if (arr) {                                                                // the run-list lane needs the whole target
         SCCG_CK(cudaStreamWaitEvent(c->side_stream, arr->ev_tgt, 0));
-        SCCG_CK(cudaStreamWaitEvent(c->stream, arr->ev_tgt, 0));
+        if (!arr->tgt_chunked) SCCG_CK(cudaStreamWaitEvent(c->stream, arr->ev_tgt, 0));     // chunked target: the matcher waits chunk by chunk
     }
     {
         SideLane side(c);
@@ -147,9 +149,11 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
                    sc + S_WORK + (i & 31), sc + S_ABORT, c->use_diag);
             seg_lo = seg_hi;
         }
+        if (arr && arr->tgt_chunked) SCCG_CK(cudaStreamWaitEvent(c->stream, arr->ev_tgt, 0));     // leftover target segments (:476-481) lie past the last launch
         SCCG_CK(cudaEventRecord(c->ev[2], c->stream));
         LAUNCH(c, seg_bytes_k, dim3(div_up(n_iter, 256)), dim3(256), 0, (const u32*)seginfo, (const u32*)matches, n_iter, seg_bytes, seg_prev, sc + S_ABORT, 0, 0, 0);
     } else {
+        if (arr && arr->tgt_chunked) SCCG_CK(cudaStreamWaitEvent(c->stream, arr->ev_tgt, 0));
         SCCG_CK(cudaEventRecord(c->ev[2], c->stream));
     }
     SCCG_TRY(scan_exclusive_u32(c, seg_bytes, seg_bytes, (i64)n_iter, sc + S_BODY_MAIN));

@@ -58,6 +58,7 @@ struct sccg_ctx {
     int scan_counter_ready[2];
     cudaStream_t main_stream, side_stream;   // `stream` is the lane the helpers currently enqueue on (main_stream except inside SideLane)
     cudaEvent_t ev_side[6];
+    unsigned char* res_ref; long long res_ref_len; size_t res_ref_cap; int res_ref_set;      // resident reference (sccg_reference_set): raw symbols, kept across calls
     int use_diag;                  // seg_match_k: try the diagonal-hypothesis parse first (SCCG_NO_DIAG=1 disables it)
     cudaStream_t s_h2d, s_d2h;     // copy streams of the pipelined host entry points (created on first use)
     cudaEvent_t ev_pipe[2], ev_h2d[64], ev_g[64];

@@ -355,3 +355,36 @@ def test_global_index_bucket_table_widths(ctx, seed, bits, monkeypatch):
     exp = [(x.p, x.l, x.lit) for x in ol.orc_match_sequences(ref, tgt, 14, 100, True, 0)]
     got = [(x.p, x.l, x.lit) for x in ctx.match_sequences(ref, tgt, 14, 100, True, 0)]
     assert got == exp
+
+
+def test_resident_reference_round_trips(ctx, monkeypatch):
+    """sccg_reference_set + *_resident calls: the bytes of sccg_compress / sccg_decompress for every target, the reference
+    uploaded once; target chunks smaller than the sequences (matcher launched per chunk, leftovers past the last launch)"""
+    from sccg_genome_compression_b200 import synth
+    monkeypatch.setenv("SCCG_PIPE_CHUNK", "8192")
+    ref, t0 = synth.local_pair(60_000, synth.seed_for(2, 77))
+    ref, t0 = ref.tobytes(), t0.tobytes()
+    g_ref, g_tgt = synth.global_gap_pair(64_000, 60_000, synth.seed_for(1, 77))
+    targets = [t0, t0[:41_234], t0 + rnd(7_777, "left"), t0[:20_000] + t0[23_000:], b"", t0[:999], g_tgt.tobytes()]
+    with pytest.raises(Exception):
+        ctx.compress_resident(t0, b">none")                     # no resident reference yet
+    ctx.set_reference(ref)
+    for i, tgt in enumerate(targets):
+        hdr = b">resident %d" % i
+        rc, exp, mode = ol.orc_compress(ref, tgt, hdr)
+        got, gmode = ctx.compress_resident(tgt, hdr)
+        assert (gmode, got) == (mode, exp), i
+        assert got == ctx.compress(ref, tgt, hdr)[0]
+        if tgt:
+            assert ctx.decompress_resident(got) == ol.orc_decompress(ref, exp)[1], i
+    # a second reference replaces the first (smaller and larger than the allocation)
+    for r2 in (g_ref.tobytes(), ref[:30_000], ref + ref[:10_000]):
+        ctx.set_reference(r2)
+        tgt = g_tgt.tobytes() if r2 is not ref else t0
+        rc, exp, mode = ol.orc_compress(r2, tgt, b">second")
+        got, gmode = ctx.compress_resident(tgt, b">second")
+        assert (gmode, got) == (mode, exp)
+        assert ctx.decompress_resident(got) == ol.orc_decompress(r2, exp)[1]
+    ctx.clear_reference()
+    with pytest.raises(Exception):
+        ctx.decompress_resident(got)

@@ -86,6 +86,33 @@ def test_compress_chunked_upload(ctx, chunk, monkeypatch):
             assert (gmode, got) == (mode, exp), _report(f"chunked_{chunk}_{n}_{cut}", got, exp)
 
 
+@pytest.mark.parametrize("chunk", [65536, 1 << 20])
+def test_resident_reference(ctx, chunk, monkeypatch):
+    """many targets against one resident reference: only the target travels (in chunks, poisoned buffer: a chunk used
+    before it landed would show), results are the bytes of the per-pair calls; decompress against the same reference"""
+    from sccg_genome_compression_b200 import synth
+    monkeypatch.setenv("SCCG_PIPE_CHUNK", str(chunk))
+    monkeypatch.setenv("SCCG_PIPE_POISON", "1")
+    ref, t0 = synth.local_pair(3_000_000, synth.seed_for(2, 43))
+    ref, t0 = ref.tobytes(), t0.tobytes()
+    _, t1 = synth.local_pair(3_000_000, synth.seed_for(2, 43), snp=0.01)
+    g_ref, g_tgt = synth.global_gap_pair(3_200_000, 3_000_000, synth.seed_for(1, 43))
+    ctx.set_reference(ref)
+    for i, tgt in enumerate((t0, t1.tobytes(), t0[:1_234_567], t0 + t0[:50_001], t0[:700_000] + t0[704_000:])):
+        rc, exp, mode = ol.orc_compress(ref, tgt, b">res")
+        assert rc == 0
+        for _ in range(2):
+            got, gmode = ctx.compress_resident(tgt, b">res")
+            assert (gmode, got) == (mode, exp), _report(f"resident_{chunk}_{i}", got, exp)
+        assert ctx.decompress_resident(got) == ol.orc_decompress(ref, exp)[1]
+    ctx.set_reference(g_ref.tobytes())
+    rc, exp, mode = ol.orc_compress(g_ref.tobytes(), g_tgt.tobytes(), b">res")
+    got, gmode = ctx.compress_resident(g_tgt.tobytes(), b">res")
+    assert mode == 1 and (gmode, got) == (mode, exp)
+    assert ctx.decompress_resident(got) == ol.orc_decompress(g_ref.tobytes(), exp)[1]
+    ctx.clear_reference()
+
+
 @pytest.mark.parametrize("seed", range(24))
 def test_text_level_delta_fuzz(ctx, seed):
     ref, tgt = grammar_pair(seed, make_global=(seed % 4 >= 2))

@@ -10,7 +10,7 @@ import json
 d=json.load(open("$O/bench.json"))
 print("compress ms", d["ms_per_step"], "match ms", d["roofline"]["kernel_ms"], "frac", d["roofline"]["frac"])
 print("decompress ms", d["decompress"]["ms_per_step"], "gather ms", d["decompress"]["roofline"]["kernel_ms"], "frac", d["decompress"]["roofline"]["frac"])
-print("e2e compress ms", d["e2e"]["ms_per_step"], "e2e decompress ms", d["decompress"]["e2e"]["ms_per_step"], "launches", d["gpu_launches"])
+print("e2e compress ms", d["e2e"]["ms_per_step"], "e2e decompress ms", d["decompress"]["e2e"]["ms_per_step"], "launches", d["gpu_launches"]); print("resident", d["e2e_resident_reference"]["compress"]["ms_per_step"], d["e2e_resident_reference"]["decompress"]["ms_per_step"])
 PY
 timeout 600 python tools/time_global.py > $O/global.json 2> $O/global.err; echo "global rc=$?"
 python - <<PY
