@@ -74,9 +74,11 @@ class Record:
 
 
 def _as_char_p(buf):
-    """bytes stay as they are; numpy uint8 arrays are passed by address (no copy)"""
+    """bytes and ctypes char arrays stay as they are; numpy uint8 arrays are passed by address (no copy)"""
     if isinstance(buf, (bytes, bytearray)):
         return bytes(buf) if isinstance(buf, bytearray) else buf
+    if isinstance(buf, C.Array):
+        return buf
     return C.cast(buf.ctypes.data, C.c_char_p) if len(buf) else b""
 
 
