@@ -385,6 +385,18 @@ def test_resident_reference_round_trips(ctx, monkeypatch):
         got, gmode = ctx.compress_resident(tgt, b">second")
         assert (gmode, got) == (mode, exp)
         assert ctx.decompress_resident(got) == ol.orc_decompress(r2, exp)[1]
+    # caller-owned buffers, as bench.py passes them: ctypes views in, result written through a raw pointer
+    import ctypes
+    import numpy as np
+    r_np = np.frombuffer(ref, dtype=np.uint8).copy(); t_np = np.frombuffer(t0, dtype=np.uint8).copy()
+    out_np = np.zeros(2 * len(t0) + 4096, dtype=np.uint8)
+    ctx.set_reference((ctypes.c_char * r_np.size).from_address(r_np.ctypes.data))
+    n, gmode = ctx.compress_resident((ctypes.c_char * t_np.size).from_address(t_np.ctypes.data), b">ptr", out_np.ctypes.data, out_np.size)
+    rc, exp, mode = ol.orc_compress(ref, t0, b">ptr")
+    assert (gmode, bytes(out_np[:n])) == (mode, exp)
+    back = np.zeros(2 * len(t0) + 4096, dtype=np.uint8)
+    m = ctx.decompress_resident(exp, back.ctypes.data, back.size)
+    assert bytes(back[:m]) == ol.orc_decompress(ref, exp)[1]
     ctx.clear_reference()
     with pytest.raises(Exception):
         ctx.decompress_resident(got)
