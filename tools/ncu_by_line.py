@@ -20,7 +20,8 @@ for r in rows:
     if r and r[0] == 'Kernel Name': c = {'name': r[1], 'rows': []}; secs.append(c); continue
     if r and r[0] == 'Address': c['hdr'] = r; continue
     if c is not None and len(r) > 10: c['rows'].append(r)
-s = next(x for x in secs if kname in x['name'])
+plain = kname.split('ILi')[0]                      # template instances: mangled name for nvdisasm (seg_match_kILi2), demangled one in the ncu export
+s = next(x for x in secs if kname in x['name'] or plain in x['name'])
 hdr, data = s['hdr'], s['rows']
 iex, ismp = hdr.index('Instructions Executed'), hdr.index('# Samples')
 assert len(data) == len(instrs), (len(data), len(instrs))
