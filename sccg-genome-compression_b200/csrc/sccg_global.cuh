@@ -3,13 +3,14 @@
 //
 //   index   : 24-bit hash of every reference k-mer + stable radix sort (3 passes)  ->  (key, position) sorted by key,
 //             positions ascending inside a key (the reference's bucket order, :41-47)
-//   parse   : one persistent CTA walks the state (index, prev_match_end) exactly like :64-161.
+//   parse   : a CTA walks the state (index, prev_match_end) exactly like :64-161 (gp_step); the target is parsed in
+//             speculative chunks by many CTAs and stitched by an exact front (gp_spec_k / gp_front_k below).
 //             * until the first match (prev_match_end == -1, every candidate is "in range") and in the
 //               `pn2 == 0` fall-through (:134) candidates come from the sorted index (binary search);
 //             * otherwise only candidates with |p - prev_match_end| <= m can be used (:83-96, :116), i.e.
 //               the k-mers of a 2m+1 window of the reference: the CTA stages that window in shared
-//               memory, hashes it into a small filter and scans the target forward 1 position per
-//               thread until a position hits the window ("no k-mer" and "no candidate in range" are
+//               memory, tries the next four positions by brute force, else hashes the window into a small
+//               filter and scans the target forward 1 position per thread until a position hits the window ("no k-mer" and "no candidate in range" are
 //               the same literal step, :77-81 vs :92-96).
 //             * candidate selection is the order-independent form of the ascending-p fold (:114-130).
 //   writer  : tokens "(dp,l)" with the delta chain of delta_encode (:258-292) + literal gaps.

@@ -1,9 +1,10 @@
 // Stable LSD radix sort of (u32 key, u32 value) pairs, 8 bits per pass: the reference k-mer index
 // build of global mode (compression.cpp:41-47 over the whole N-stripped reference).
-//   key   = 32-bit hash of the k-mer at position p,  value = p
+//   key   = hash of the k-mer at position p (24 significant bits -> 3 passes),  value = p
 // Stable + ascending input order  =>  inside every key the positions stay ascending, which is the
 // reference's per-bucket order (vector<int>::push_back in ascending i).
-// Per pass: histogram (read 4 B/elem), scan of 256 x nblocks counters, scatter (read 8 B, write 8 B).
+// Per pass: histogram (read 4 B/elem), scan of 256 x nblocks counters, scatter (read 8 B, write 8 B).  The scatter ranks the
+// keys of a 4096-element tile by digit with ballots, orders the tile in shared memory and stores runs of equal digits.
 // The first pass takes its pairs from a SOURCE functor (key(i), val(i)): the k-mer index computes hash and position on
 // the fly from the sequence instead of materialising 8 B per k-mer first.
 #pragma once
