@@ -128,7 +128,7 @@ int sccg_decompress_part(sccg_ctx* ctx, const char* ref_raw, int64_t ref_len, co
                          int part, int n_parts, char* out, int64_t out_cap, int64_t* part_offset, int64_t* part_len, int64_t* total_len);
 
 /* Many targets against one reference (the reference repository's use case: every individual's chromosome against the same
- * reference chromosome, one `compress` / `decompress` process per pair -- compression.cpp:591-620, decompression.cpp:325-350 --
+ * reference chromosome, one `compress` / `decompress` process per pair -- compression.cpp:584-610, decompression.cpp:281-329 --
  * each of which re-reads the reference).  sccg_reference_set uploads the raw reference symbols once and keeps them in device
  * memory; the *_resident calls then move only the target (or the record file and the reconstructed text) over PCIe and give
  * exactly the bytes of sccg_compress_into / sccg_decompress_into with that reference.  The caller's reference buffer is free
