@@ -129,3 +129,29 @@ def test_grammar_symbols_in_target_cli_level(seed):
         rc_ref, inter = ol.ref_compress_cli(d / "r.fa", d / "t.fa", d / "out")
     assert (rc != 0) == (rc_ref != 0)
     assert inter == exp
+
+
+@pytest.mark.parametrize("shape", ["shifted_tail", "leftover_only", "reference_insertion", "small_shift"])
+def test_length_mismatch_shapes_end_to_end(shape):
+    """pairs of different length, > 160 segment pairs: the shapes for which the GPU path probes the last segments for a T2
+    abort before the bulk launch.  The oracle's verdict (local vs global) and bytes are the reference's."""
+    n = 200_000
+    ref = rnd(n, "probe")
+    r = random.Random("probe" + shape)
+    t = bytearray(ref)
+    for p in r.sample(range(n), 150):
+        t[p] = r.choice(b"ACGT")
+    if shape == "shifted_tail":
+        tgt = bytes(t[:60_000]) + bytes(t[63_000:])
+    elif shape == "leftover_only":
+        tgt = bytes(t) + rnd(5_000, "extra")
+    elif shape == "reference_insertion":
+        tgt = bytes(t); ref = ref[:20_000] + rnd(2_500, "ins") + ref[20_000:]
+    else:
+        tgt = bytes(t[:90_000]) + b"ACGTTGCAAC" * 3 + bytes(t[90_000:]) + rnd(1_200, "tail")
+    res = ol.ref_roundtrip(ref, tgt, b">probe")
+    rc, text, mode = ol.orc_compress(ref, tgt, b">probe")
+    assert rc == 0 and text == res["intermediate"]
+    assert mode == (1 if shape in ("shifted_tail", "reference_insertion") else 0)
+    rc, out = ol.orc_decompress(ref, text)
+    assert res["rc_decompress"] == 0 and rc == 0 and out == res["reconstructed"]
