@@ -195,3 +195,41 @@ def test_roundtrip_400mbp_pair(ctx):
     body = got[hl:hl + full // 50 * 51].reshape(-1, 51)
     assert np.array_equal(body[:, :50].reshape(-1), tgt[:full]) and bool((body[:, 50] == 10).all())
     assert bytes(got[hl + full // 50 * 51:]) == (tgt[full:].tobytes() + b"\n" if n > full else b"")
+
+
+def test_two_contexts_two_threads():
+    """contexts are independent: two of them on one GPU, driven from two host threads (the batch driver of SURVEY 8f.3 overlaps
+    the upload of one pair with the kernels / download of another), give the bytes of the sequential calls"""
+    import threading
+    import sccg_b200
+    from sccg_genome_compression_b200 import synth
+    pairs = []
+    for i in range(6):
+        ref, tgt = synth.local_pair(1_500_000 + 100_003 * i, synth.seed_for(2, 60 + i))
+        pairs.append((ref.tobytes(), tgt.tobytes(), b">pair %d" % i))
+    g_ref, g_tgt = synth.global_gap_pair(1_300_000, 1_200_000, synth.seed_for(1, 60))
+    pairs.append((g_ref.tobytes(), g_tgt.tobytes(), b">gap"))
+    ctxs = [sccg_b200.Context(0), sccg_b200.Context(0)]
+    try:
+        expect = [ctxs[0].compress(r, t, h) for r, t, h in pairs]
+        got = [None] * len(pairs); back = [None] * len(pairs); errs = []
+
+        def worker(w):
+            try:
+                for rep in range(2):
+                    for i in range(w, len(pairs), 2):
+                        r, t, h = pairs[i]
+                        got[i] = ctxs[w].compress(r, t, h)
+                        back[i] = ctxs[w].decompress(r, got[i][0])
+            except Exception as e:          # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=worker, args=(w,)) for w in range(2)]
+        for t in th: t.start()
+        for t in th: t.join()
+        assert not errs, errs
+        assert got == expect
+        for i, (r, t, h) in enumerate(pairs):
+            assert back[i] == ctxs[0].decompress(r, expect[i][0])
+    finally:
+        for c in ctxs:
+            c.close()
