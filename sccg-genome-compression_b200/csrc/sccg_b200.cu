@@ -192,10 +192,12 @@ int sccg_reference_set(sccg_ctx* c, const char* ref, int64_t ref_len) {
     const size_t need = (size_t)ref_len + 128;
     if (need > c->res_ref_cap) {
         if (c->res_ref) { SCCG_CK(cudaStreamSynchronize(c->main_stream)); cudaFree(c->res_ref); c->res_ref = nullptr; c->res_ref_cap = 0; }
+        c->res_ref_set = 0; c->res_ref_len = 0;                                // no resident reference until the new one is complete
         void* p = nullptr;
-        if (cudaMalloc(&p, need) != cudaSuccess) { cudaGetLastError(); c->res_ref_len = -1; return set_error(SCCG_E_NOMEM, "cudaMalloc of the resident reference failed"); }
+        if (cudaMalloc(&p, need) != cudaSuccess) { cudaGetLastError(); return set_error(SCCG_E_NOMEM, "cudaMalloc of the resident reference failed"); }
         c->res_ref = (u8*)p; c->res_ref_cap = need;
     }
+    c->res_ref_set = 0;
     if (ref_len > 0) SCCG_CK(cudaMemcpyAsync(c->res_ref, ref, (size_t)ref_len, cudaMemcpyHostToDevice, c->main_stream));
     SCCG_CK(cudaMemsetAsync(c->res_ref + ref_len, 0, 128, c->main_stream));
     SCCG_CK(cudaStreamSynchronize(c->main_stream));                            // the caller's buffer is free again
