@@ -12,6 +12,9 @@
  *     outputs are allocated by the library and released with sccg_free().
  *   - *_device entry points take DEVICE pointers (inputs already resident in HBM) and leave the
  *     result in device memory owned by the context (valid until the next call on that context).
+ *     Every device input must be 16-byte aligned and have at least 16 READABLE bytes past its
+ *     length (the kernels use 8/16-byte vector loads that may run past the last symbol; the
+ *     content of that slack is irrelevant).  A cudaMalloc'ed buffer of len + 16 bytes qualifies.
  *   - one opaque context per GPU; calls on one context must be serialised by the caller, distinct
  *     contexts may be driven from distinct host threads.
  *   - there is NO CPU fallback: without a usable CUDA device sccg_create() fails.

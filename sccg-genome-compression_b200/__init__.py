@@ -189,8 +189,11 @@ class Context:
     def compress_into(self, ref, tgt, header: bytes, out_ptr: int, out_cap: int) -> tuple[int, int]:
         """result written to the caller's (ideally page-locked) buffer -> (length, mode)"""
         n = C.c_int64(); mode = C.c_int()
-        self._check(self.lib.sccg_compress_into(self.handle, ref, len(ref), tgt, len(tgt), header, len(header), out_ptr, out_cap,
-                                                C.byref(n), C.byref(mode)))
+        rc = self.lib.sccg_compress_into(self.handle, ref, len(ref), tgt, len(tgt), header, len(header), out_ptr, out_cap,
+                                         C.byref(n), C.byref(mode))
+        if rc == SCCG_E_STOI:                                   # the caller's buffer holds the pre-delta image (include/sccg.h)
+            raise SccgError(rc, self.lib.sccg_last_error().decode(), C.string_at(out_ptr, n.value))
+        self._check(rc)
         return n.value, mode.value
 
     def decompress_into(self, ref_raw, intermediate, out_ptr: int, out_cap: int) -> int:
@@ -255,15 +258,20 @@ class Context:
         the caller's (page-locked) buffer and (length, mode) is returned"""
         n = C.c_int64(); mode = C.c_int()
         if out_ptr:
-            self._check(self.lib.sccg_compress_resident_into(self.handle, _as_char_p(tgt), len(tgt), header, len(header), out_ptr, out_cap, C.byref(n), C.byref(mode)))
+            rc = self.lib.sccg_compress_resident_into(self.handle, _as_char_p(tgt), len(tgt), header, len(header), out_ptr, out_cap, C.byref(n), C.byref(mode))
+            if rc == SCCG_E_STOI:
+                raise SccgError(rc, self.lib.sccg_last_error().decode(), C.string_at(out_ptr, n.value))
+            self._check(rc)
             return n.value, mode.value
         cap = 2 * len(tgt) + len(header) + 4096
         while True:
             buf = C.create_string_buffer(cap)
             rc = self.lib.sccg_compress_resident_into(self.handle, _as_char_p(tgt), len(tgt), header, len(header), C.cast(buf, C.c_void_p), cap, C.byref(n), C.byref(mode))
-            if rc != 0 and n.value > cap:                       # too small: the required size came back
+            if rc == SCCG_E_ARG and n.value > cap:              # too small: the required size came back
                 cap = n.value
                 continue
+            if rc == SCCG_E_STOI:
+                raise SccgError(rc, self.lib.sccg_last_error().decode(), buf.raw[:n.value])
             self._check(rc)
             return buf.raw[:n.value], mode.value
 
@@ -277,7 +285,7 @@ class Context:
         while True:
             buf = C.create_string_buffer(cap)
             rc = self.lib.sccg_decompress_resident_into(self.handle, intermediate, len(intermediate), C.cast(buf, C.c_void_p), cap, C.byref(n))
-            if rc != 0 and n.value > cap:
+            if rc == SCCG_E_ARG and n.value > cap:
                 cap = n.value + 16
                 continue
             self._check(rc)

@@ -17,7 +17,9 @@ static int check_sizes(i64 a, i64 b) {
     return SCCG_OK;
 }
 
-static void prof_reset(sccg_ctx* c) { memset(&c->prof, 0, sizeof c->prof); }
+// called at the start of every entry point except sccg_shard_write: besides the profile it invalidates the state that
+// sccg_shard_match leaves behind (the buffers it points into are about to be reused)
+static void prof_reset(sccg_ctx* c) { memset(&c->prof, 0, sizeof c->prof); c->shard.valid = 0; }
 
 // read_genomes_from_files only ever yields a header that starts with '>' (compression.cpp:208-213); delta_encode keys its
 // line skipping on that byte (:237), so anything else would shift the text it rewrites

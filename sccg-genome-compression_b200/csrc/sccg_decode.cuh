@@ -84,6 +84,7 @@ __device__ __forceinline__ int parse_tuple(const u8* __restrict__ s, i64 i, i64 
 // No per-byte side arrays exist: the stream is read twice (2 B per encoded byte) + 24 B per 16-byte chunk.
 // ------------------------------------------------------------------------------------------------
 #define SEG_LIT_FLAG 0x4000000000000000LL
+#define SEG_BAD_PTR (-1LL)               // seg_ptr of a token that failed the bounds check: no reader may dereference it
 static const int DEC_T = 256;
 static const int DEC_PER_THREAD = 16;
 
@@ -382,7 +383,8 @@ __device__ __forceinline__ u8 gather_byte(const GatherArgs& a, const int* win, u
         int sk = bounded_upper_u32(a.seg_dst, win[0], win[1], s);
         i64 src = a.seg_ptr[sk];
         i64 within = s - (i64)a.seg_dst[sk];
-        o = (src & SEG_LIT_FLAG) ? a.enc[(src & ~SEG_LIT_FLAG) + within] : a.ref[src + within];
+        if (src < 0) o = '?';                                     // SEG_BAD_PTR (the call returns an error)
+        else o = (src & SEG_LIT_FLAG) ? a.enc[(src & ~SEG_LIT_FLAG) + within] : a.ref[src + within];
     }
     int lk = bounded_upper_i32(a.l_start, win[4], win[5], bb);
     if (lk >= 0 && bb < (i64)a.l_start[lk] + (i64)a.l_len[lk]) o = lower1(o);
@@ -433,7 +435,7 @@ __device__ __forceinline__ void gather_tile_generic(const GatherArgs& a, int* wi
         i64 s = b - noff;
         sk = bounded_upper_u32(a.seg_dst, win[0], win[1], s);
         i64 seg_end = sk + 1 < a.nseg ? (i64)a.seg_dst[sk + 1] : a.Ls;
-        if (sk < 0 || s + ns > seg_end) fast = false;
+        if (sk < 0 || s + ns > seg_end || a.seg_ptr[sk] < 0) fast = false;
     }
     if (fast) {
         int lk = bounded_upper_i32(a.l_start, win[4], win[5], b + ns - 1);
@@ -539,10 +541,14 @@ __global__ void dec_resolve_k(const i64* __restrict__ seg_src, const int* __rest
     if (src & SEG_LIT_FLAG) { seg_ptr[k] = src; return; }
     const int a = (int)(delta_excl[src] + (u32)tok_delta[src]);   // prev_abs_start + delta, int arithmetic
     tok_abs[src] = a;
-    const i64 end = (i64)(int)((u32)a + (u32)tok_len[src]);       // `absolute_start + length` is evaluated in int
-    if (end > nr) atomicOr(&sc[D_ERR], (u32)DE_BOUNDS);
-    else if (a < 0) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);         // substr(pos > size) throws out_of_range
-    seg_ptr[k] = (i64)a;
+    const int len = tok_len[src];                                 // >= 0 (dec_count_k)
+    const i64 end = (i64)(int)((u32)a + (u32)len);                // `absolute_start + length` is evaluated in int (:223)
+    i64 ptr = (i64)a;
+    if (end > nr) { atomicOr(&sc[D_ERR], (u32)DE_BOUNDS); ptr = SEG_BAD_PTR; }
+    else if (a < 0 || (i64)a + (i64)len > nr) {                   // substr(pos > size) throws out_of_range; a wrapped `end` would read past the reference
+        atomicOr(&sc[D_ERR], (u32)DE_FORMAT); ptr = SEG_BAD_PTR;
+    }
+    seg_ptr[k] = ptr;                                             // SEG_BAD_PTR: the gather copies nothing for this segment (the call fails anyway)
 }
 
 // merged-coordinate symbol range [b0, b1) shown in the text bytes [Q0, Qe)
@@ -629,7 +635,7 @@ __global__ void __launch_bounds__(GATHER_CTA) dec_gather_k(GatherArgs a) {
             const u32 d1 = __shfl_sync(SCCG_FULL_MASK, md1, j);
             const i64 src = __shfl_sync(SCCG_FULL_MASK, mp, j);
             const u32 lo = d0 > s0 ? d0 : s0, hi = d1 < s1 ? d1 : s1;
-            if (hi <= lo) continue;
+            if (hi <= lo || src < 0) continue;                     // src < 0: SEG_BAD_PTR
             const u8* sp = (src & SEG_LIT_FLAG) ? a.enc + (src & ~SEG_LIT_FLAG) : a.ref + src;
             warp_copy_g2s(A + (lo - s0), sp + (lo - d0), hi - lo);
         }
@@ -848,7 +854,7 @@ __global__ void dec_need_k(GatherArgs a, const int* __restrict__ tok_len, i64 ch
     if (k < a.nseg) {
         const i64 src = a.seg_src[k];
         const i64 s0 = a.seg_dst[k], s1 = k + 1 < a.nseg ? (i64)a.seg_dst[k + 1] : a.Ls;
-        if (!(src & SEG_LIT_FLAG) && s1 > s0) {
+        if (!(src & SEG_LIT_FLAG) && s1 > s0 && a.seg_ptr[k] >= 0) {
             lo = (u32)a.tok_abs[src];
             hi = (u32)((i64)a.tok_abs[src] + (i64)tok_len[src]);
             c0 = out_byte_of_sym(a, s0) / chunk_bytes; c1 = out_byte_of_sym(a, s1 - 1) / chunk_bytes;
@@ -956,10 +962,15 @@ static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, c
     u8* d_text = plan.a.out;
     const i64 n = plan.a.total;
     // "<header>\n" right in front of the text (:322; an absent header still yields the "\n")
-    char* hdr_stage = (char*)c->h_pinned + 4096;                              // scalars live in the first bytes of the staging area
-    memcpy(hdr_stage, header, (size_t)nh);
-    hdr_stage[nh] = '\n';
-    SCCG_CK(cudaMemcpyAsync(d_text - (nh + 1), hdr_stage, (size_t)nh + 1, cudaMemcpyHostToDevice, c->stream));
+    // (a header line of any length: it is copied straight from the caller's file image, where its '\n' follows it -- the image
+    // stays valid until the final synchronisation of this call; no header: the lone "\n" comes from the staging area)
+    if (nh > 0) {
+        SCCG_CK(cudaMemcpyAsync(d_text - (nh + 1), header, (size_t)nh + 1, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        char* hdr_stage = (char*)c->h_pinned + 4096;                          // scalars live in the first bytes of the staging area
+        hdr_stage[0] = '\n';
+        SCCG_CK(cudaMemcpyAsync(d_text - 1, hdr_stage, 1, cudaMemcpyHostToDevice, c->stream));
+    }
     // ---- result buffer
     const i64 full = n + nh + 1;
     *out_len = full;

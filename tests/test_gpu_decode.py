@@ -132,3 +132,18 @@ def test_decompress_parts_concatenate_to_the_whole(ctx, n_parts, chunk, monkeypa
             image[off:off + len(piece)] = piece
             covered += len(piece)
         assert covered == len(exp) and bytes(image) == exp
+
+
+def test_far_out_of_range_tokens_fail_cleanly(ctx):
+    import robustness_cases
+    robustness_cases.check_far_out_of_range_tokens(ctx)
+
+
+def test_long_header_line(ctx):
+    import robustness_cases
+    robustness_cases.check_long_header_line(ctx)
+
+
+def test_stale_shard_write_is_rejected(ctx):
+    import robustness_cases
+    robustness_cases.check_stale_shard_write(ctx)
