@@ -182,6 +182,52 @@ int sccg_shard_match(sccg_ctx* ctx, const char* ref_slice, int64_t ref_len, cons
                      int64_t seg_base, int is_last, sccg_shard_info* info);
 int sccg_shard_write(sccg_ctx* ctx, const sccg_shard_carry* carry, char** low_part, int64_t* low_len, char** body_part, int64_t* body_len);
 
+/* ---- Multi-GPU layer (host side in C++, NCCL C API underneath; csrc/sccg_mgpu.cuh) ------------------------------------------
+ * The reference is one single-threaded process per FASTA pair (compression.cpp:584-610, decompression.cpp:281-329); a genome is
+ * 24 invocations.  Here one rank (a process or a host thread) drives one GPU through its own sccg_ctx, and a communicator ties
+ * the ranks of one job together.  NCCL carries only (a) the 128-byte border records of a segment-range sharded pair and (b) the
+ * encoded record streams on their way to rank 0; no collective sits on a kernel's critical path.  libnccl.so.2 is bound at run
+ * time: the single-GPU entry points above do not need it.
+ *   sccg_mgpu_unique_id : rank 0 creates the rendezvous token (ncclGetUniqueId); the caller hands the 128 bytes to the other
+ *                         ranks (torch.distributed / MPI broadcast, a file, or simply memory when the ranks are threads).
+ *   sccg_mgpu_init      : joins the communicator; collective over all ranks.  ctx stays owned by the caller and must outlive it. */
+#define SCCG_MGPU_ID_BYTES 128
+typedef struct sccg_mgpu sccg_mgpu;
+int  sccg_mgpu_unique_id(char* id128);
+int  sccg_mgpu_init(sccg_ctx* ctx, const char* id128, int rank, int world, sccg_mgpu** out);
+void sccg_mgpu_destroy(sccg_mgpu* g);
+int  sccg_mgpu_rank(const sccg_mgpu* g);
+int  sccg_mgpu_world(const sccg_mgpu* g);
+
+/* (1) By chromosome.  sccg_mgpu_assign: longest-processing-time packing of n_items pairs (lengths[] = target symbols) onto
+ * `world` ranks, deterministic; owner[i] = rank of pair i.  Every rank then runs compress_genome (compression.cpp:320-579) on
+ * its own pairs with sccg_mgpu_compress_item (host buffers, pipelined upload) or ..._item_device (inputs resident in HBM): the
+ * encoded image stays in device memory and is appended to the rank's outgoing streams (at most 64 per gather).
+ * sccg_mgpu_gather (collective) moves every rank's streams to rank 0 -- sizes by ncclAllGather, payload by grouped
+ * ncclSend / ncclRecv -- and copies them into `out` back to back; stream k is item_ids[k] at out + item_offs[k], item_lens[k]
+ * bytes long.  On the other ranks out / item_* may be NULL.  Too small a buffer: SCCG_E_ARG with *total / *n_items set. */
+int sccg_mgpu_assign(const int64_t* lengths, int n_items, int world, int32_t* owner);
+int sccg_mgpu_compress_item(sccg_mgpu* g, int32_t item, const char* ref, int64_t ref_len, const char* tgt, int64_t tgt_len,
+                            const char* header, int64_t header_len, int64_t* enc_len, int* mode_out);
+int sccg_mgpu_compress_item_device(sccg_mgpu* g, int32_t item, const void* d_ref, int64_t ref_len, const void* d_tgt, int64_t tgt_len,
+                                   const char* header, int64_t header_len, int64_t* enc_len, int* mode_out);
+int sccg_mgpu_stash_device(sccg_mgpu* g, int32_t item, const void* d_data, int64_t len);
+int sccg_mgpu_gather(sccg_mgpu* g, char* out, int64_t out_cap, int32_t* item_ids, int64_t* item_offs, int64_t* item_lens, int32_t cap_items,
+                     int32_t* n_items, int64_t* total);
+
+/* (2) One pair over all ranks by segment range (the local path, compression.cpp:381-481).  Collective: every rank passes the
+ * same host buffers but uploads and matches only its own slice; the border records travel in one ncclAllGather, every rank
+ * derives the same carries, and the parts of the two text lines go to rank 0, which receives exactly the file sccg_compress
+ * writes (*out_len = its length; 0 on the other ranks).  A pair that leaves the local path (T2 abort -> global mode, a '(' in
+ * the target) or is too small to shard is compressed by rank 0 alone; *sharded_out tells which way it went. */
+int sccg_mgpu_compress_sharded(sccg_mgpu* g, const char* ref, int64_t ref_len, const char* tgt, int64_t tgt_len, const char* header, int64_t header_len,
+                               char* out, int64_t out_cap, int64_t* out_len, int* mode_out, int* sharded_out);
+
+/* (3) Decompression of one pair by output range: this rank's piece of the reconstructed file image (sccg_decompress_part with
+ * part = rank, n_parts = world).  Nothing is gathered: the pieces are written straight to their offsets of the output file. */
+int sccg_mgpu_decompress_sharded(sccg_mgpu* g, const char* ref_raw, int64_t ref_len, const char* intermediate, int64_t inter_len,
+                                 char* out, int64_t out_cap, int64_t* part_offset, int64_t* part_len, int64_t* total_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -122,8 +122,117 @@ def load_library(path: str | os.PathLike | None = None) -> C.CDLL:
     lib.sccg_decompress_resident_into.argtypes = [vp, cp, i64, vp, i64, C.POINTER(i64)]
     lib.sccg_compress_fasta.argtypes = [vp, cp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_int)]
     lib.sccg_decompress_fasta.argtypes = [vp, cp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64)]
+    i32p, i64p = C.POINTER(C.c_int32), C.POINTER(i64)
+    lib.sccg_mgpu_unique_id.argtypes = [C.c_char_p]
+    lib.sccg_mgpu_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.sccg_mgpu_destroy.argtypes = [vp]
+    lib.sccg_mgpu_destroy.restype = None
+    lib.sccg_mgpu_assign.argtypes = [i64p, C.c_int, C.c_int, i32p]
+    lib.sccg_mgpu_compress_item.argtypes = [vp, C.c_int32, cp, i64, cp, i64, cp, i64, i64p, C.POINTER(C.c_int)]
+    lib.sccg_mgpu_compress_item_device.argtypes = [vp, C.c_int32, vp, i64, vp, i64, cp, i64, i64p, C.POINTER(C.c_int)]
+    lib.sccg_mgpu_stash_device.argtypes = [vp, C.c_int32, vp, i64]
+    lib.sccg_mgpu_gather.argtypes = [vp, vp, i64, i32p, i64p, i64p, C.c_int32, i32p, i64p]
+    lib.sccg_mgpu_compress_sharded.argtypes = [vp, cp, i64, cp, i64, cp, i64, vp, i64, i64p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.sccg_mgpu_decompress_sharded.argtypes = [vp, cp, i64, cp, i64, vp, i64, i64p, i64p, i64p]
     _libs[key] = lib
     return lib
+
+
+MGPU_ID_BYTES = 128
+
+
+def mgpu_unique_id(lib_path: str | os.PathLike | None = None) -> bytes:
+    """rendezvous token of a multi-GPU job (rank 0 calls this, everybody gets the bytes): sccg_mgpu_unique_id"""
+    lib = load_library(lib_path)
+    buf = C.create_string_buffer(MGPU_ID_BYTES)
+    rc = lib.sccg_mgpu_unique_id(buf)
+    if rc != SCCG_OK:
+        raise SccgError(rc, lib.sccg_last_error().decode())
+    return buf.raw
+
+
+def mgpu_assign(lengths: list[int], world: int, lib_path: str | os.PathLike | None = None) -> list[int]:
+    """LPT packing of pairs onto ranks (sccg_mgpu_assign) -> owner rank of every pair"""
+    lib = load_library(lib_path)
+    n = len(lengths)
+    arr = (C.c_int64 * max(n, 1))(*lengths)
+    own = (C.c_int32 * max(n, 1))()
+    rc = lib.sccg_mgpu_assign(arr, n, world, own)
+    if rc != SCCG_OK:
+        raise SccgError(rc, lib.sccg_last_error().decode())
+    return list(own[:n])
+
+
+class Mgpu:
+    """One rank of a multi-GPU job (sccg_mgpu, include/sccg.h): C++ host logic over NCCL."""
+
+    def __init__(self, ctx: "Context", unique_id: bytes, rank: int, world: int):
+        self.ctx, self.lib, self.rank, self.world = ctx, ctx.lib, rank, world
+        h = C.c_void_p()
+        rc = self.lib.sccg_mgpu_init(ctx.handle, unique_id, rank, world, C.byref(h))
+        if rc != SCCG_OK:
+            raise SccgError(rc, self.lib.sccg_last_error().decode())
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.sccg_mgpu_destroy(self.handle)
+            self.handle = None
+
+    def _check(self, rc: int):
+        if rc != SCCG_OK:
+            raise SccgError(rc, self.lib.sccg_last_error().decode())
+
+    def compress_item(self, item: int, ref, tgt, header: bytes = b"") -> tuple[int, int]:
+        """compress one pair of this rank (host buffers); its encoded image joins the outgoing streams -> (length, mode)"""
+        n = C.c_int64(); mode = C.c_int()
+        self._check(self.lib.sccg_mgpu_compress_item(self.handle, item, _as_char_p(ref), len(ref), _as_char_p(tgt), len(tgt), header, len(header),
+                                                     C.byref(n), C.byref(mode)))
+        return n.value, mode.value
+
+    def compress_item_device(self, item: int, d_ref: int, ref_len: int, d_tgt: int, tgt_len: int, header: bytes = b"") -> tuple[int, int]:
+        n = C.c_int64(); mode = C.c_int()
+        self._check(self.lib.sccg_mgpu_compress_item_device(self.handle, item, d_ref, ref_len, d_tgt, tgt_len, header, len(header), C.byref(n), C.byref(mode)))
+        return n.value, mode.value
+
+    def gather(self, out_ptr: int = 0, out_cap: int = 0, max_items: int = 64 * 64, max_bytes: int = 1 << 26):
+        """collective; rank 0 -> {item: (offset, length)} into the caller's buffer (out_ptr / out_cap), or {item: bytes} when no
+        buffer is given; other ranks -> None"""
+        ids = (C.c_int32 * max_items)(); offs = (C.c_int64 * max_items)(); lens = (C.c_int64 * max_items)()
+        n = C.c_int32(); total = C.c_int64()
+        own = None
+        if self.rank == 0 and not out_ptr:
+            out_cap = max_bytes
+            own = C.create_string_buffer(out_cap)
+            out_ptr = C.cast(own, C.c_void_p)
+        rc = self.lib.sccg_mgpu_gather(self.handle, out_ptr, out_cap, ids, offs, lens, max_items, C.byref(n), C.byref(total))
+        self._check(rc)
+        if self.rank != 0:
+            return None
+        if own is not None:
+            return {ids[k]: own.raw[offs[k]:offs[k] + lens[k]] for k in range(n.value)}
+        return {ids[k]: (offs[k], lens[k]) for k in range(n.value)}
+
+    def compress_sharded(self, ref, tgt, header: bytes = b"", out_ptr: int = 0, out_cap: int = 0):
+        """collective: one pair over all ranks by segment range -> rank 0: (image or its length, mode, sharded); others: (None, mode, sharded)"""
+        n = C.c_int64(); mode = C.c_int(); sh = C.c_int()
+        own = None
+        if self.rank == 0 and not out_ptr:
+            out_cap = len(tgt) * 2 + len(header) + 4096
+            own = C.create_string_buffer(out_cap)
+            out_ptr = C.cast(own, C.c_void_p)
+        self._check(self.lib.sccg_mgpu_compress_sharded(self.handle, _as_char_p(ref), len(ref), _as_char_p(tgt), len(tgt), header, len(header),
+                                                        out_ptr, out_cap, C.byref(n), C.byref(mode), C.byref(sh)))
+        if self.rank != 0:
+            return None, mode.value, bool(sh.value)
+        return (own.raw[:n.value] if own is not None else n.value), mode.value, bool(sh.value)
+
+    def decompress_sharded(self, ref_raw, intermediate: bytes, out_ptr: int, out_cap: int) -> tuple[int, int, int]:
+        """this rank's piece of the reconstructed image -> (offset in the image, piece length, total length)"""
+        off = C.c_int64(); n = C.c_int64(); total = C.c_int64()
+        self._check(self.lib.sccg_mgpu_decompress_sharded(self.handle, _as_char_p(ref_raw), len(ref_raw), intermediate, len(intermediate),
+                                                          out_ptr, out_cap, C.byref(off), C.byref(n), C.byref(total)))
+        return off.value, n.value, total.value
 
 
 class Context:

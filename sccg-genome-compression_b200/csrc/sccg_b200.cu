@@ -5,6 +5,7 @@
 #include "sccg_decode.cuh"
 #include "sccg_fasta.cuh"
 #include "sccg_shard.cuh"
+#include "sccg_mgpu.cuh"
 
 #include <new>
 
@@ -136,30 +137,9 @@ static int compress_host(sccg_ctx* c, const char* ref, int64_t ref_len, const ch
     SCCG_TRY(check_header(header, header_len));
     SCCG_CK(cudaSetDevice(c->device));
     prof_reset(c);
-    // the target goes up first (the run-list pipeline only needs it), then the reference in chunks: the matcher starts on
-    // every chunk as it lands, so the kernels hide under the PCIe transfer
     u8 *d_ref = nullptr, *d_tgt = nullptr;
-    SCCG_TRY(pipe_streams(c));
-    SCCG_TRY(buf(c, B_REF, (size_t)ref_len + 128, &d_ref));
-    SCCG_TRY(buf(c, B_TGT, (size_t)tgt_len + 128, &d_tgt));
-    if (getenv("SCCG_PIPE_POISON")) {                                         // tests: a chunk read before it arrived shows up
-        SCCG_CK(cudaMemsetAsync(d_tgt, 0xEE, (size_t)tgt_len, c->stream));
-        SCCG_CK(cudaMemsetAsync(d_ref, 0xEE, (size_t)ref_len, c->stream));
-    }
-    SCCG_CK(cudaEventRecord(c->ev[4], c->stream));
-    SCCG_CK(cudaStreamWaitEvent(c->s_h2d, c->ev[4], 0));
     ChunkArrival arr;
-    arr.chunk = pipe_chunk_bytes(ref_len);
-    arr.n = ref_len > 0 ? (int)((ref_len + arr.chunk - 1) / arr.chunk) : 0;
-    arr.ev_ref = c->ev_h2d; arr.ev_tgt = c->ev_pipe[1]; arr.tgt_chunked = 0;
-    if (tgt_len > 0) SCCG_CK(cudaMemcpyAsync(d_tgt, tgt, (size_t)tgt_len, cudaMemcpyHostToDevice, c->s_h2d));
-    SCCG_CK(cudaEventRecord(arr.ev_tgt, c->s_h2d));
-    for (int i = 0; i < arr.n; ++i) {
-        const i64 off = (i64)i * arr.chunk, len = (ref_len - off) < arr.chunk ? (ref_len - off) : arr.chunk;
-        SCCG_CK(cudaMemcpyAsync(d_ref + off, ref + off, (size_t)len, cudaMemcpyHostToDevice, c->s_h2d));
-        SCCG_CK(cudaEventRecord(arr.ev_ref[i], c->s_h2d));
-    }
-    SCCG_CK(cudaEventRecord(c->ev[5], c->s_h2d));
+    SCCG_TRY(enqueue_pair_upload(c, ref, ref_len, tgt, tgt_len, &d_ref, &d_tgt, &arr));
     CompressResult res;
     int rc_c = compress_device(c, d_ref, ref_len, d_tgt, tgt_len, header, header_len < 0 ? 0 : header_len, &res, &arr);
     SCCG_CK(cudaStreamSynchronize(c->s_h2d));                                 // the caller's buffers are no longer in use
@@ -461,9 +441,17 @@ int sccg_shard_match(sccg_ctx* c, const char* ref_slice, int64_t ref_len, const 
     SCCG_CK(cudaSetDevice(c->device));
     prof_reset(c);
     u8 *d_ref = nullptr, *d_tgt = nullptr;
-    SCCG_TRY(upload(c, B_REF, ref_slice, ref_len, &d_ref));
-    SCCG_TRY(upload(c, B_TGT, tgt_slice, tgt_len, &d_tgt));
-    return shard_match(c, d_ref, ref_len, d_tgt, tgt_len, seg_base, is_last, info);
+    ChunkArrival arr;
+    SCCG_TRY(enqueue_pair_upload(c, ref_slice, ref_len, tgt_slice, tgt_len, &d_ref, &d_tgt, &arr));
+    ShardBorder* d_border = nullptr;
+    int rc = shard_match(c, d_ref, ref_len, d_tgt, tgt_len, seg_base, is_last, &arr, &d_border);
+    SCCG_CK(cudaStreamSynchronize(c->s_h2d));                                 // the caller's buffers are no longer in use
+    if (rc != SCCG_OK) { c->shard.valid = 0; return rc; }
+    ShardBorder hb;
+    SCCG_CK(cudaMemcpyAsync(&hb, d_border, sizeof hb, cudaMemcpyDeviceToHost, c->stream));
+    SCCG_CK(cudaStreamSynchronize(c->stream));
+    shard_info_from_border(hb, info);
+    return SCCG_OK;
 }
 
 int sccg_shard_write(sccg_ctx* c, const sccg_shard_carry* carry, char** low_part, int64_t* low_len, char** body_part, int64_t* body_len) {
@@ -476,6 +464,197 @@ int sccg_shard_write(sccg_ctx* c, const sccg_shard_carry* carry, char** low_part
     if (rc != SCCG_OK) { free(*low_part); *low_part = nullptr; return rc; }
     *low_len = nl; *body_len = nb;
     return SCCG_OK;
+}
+
+// ---- multi-GPU layer (csrc/sccg_mgpu.cuh) ---------------------------------------------------------------------------------
+int sccg_mgpu_unique_id(char* id128) {
+    if (!id128) return set_error(SCCG_E_ARG, "null argument");
+    return mg_unique_id(id128);
+}
+
+int sccg_mgpu_init(sccg_ctx* c, const char* id128, int rank, int world, sccg_mgpu** out) {
+    if (!c || !id128 || !out) return set_error(SCCG_E_ARG, "null argument");
+    *out = nullptr;
+    return mg_init(c, id128, rank, world, out);
+}
+
+void sccg_mgpu_destroy(sccg_mgpu* g) { mg_destroy(g); }
+int sccg_mgpu_rank(const sccg_mgpu* g) { return g ? g->rank : -1; }
+int sccg_mgpu_world(const sccg_mgpu* g) { return g ? g->world : 0; }
+
+int sccg_mgpu_assign(const int64_t* lengths, int n_items, int world, int32_t* owner) {
+    if (n_items < 0 || world < 1 || (n_items > 0 && (!lengths || !owner))) return set_error(SCCG_E_ARG, "invalid argument");
+    mg_assign(lengths, n_items, world, owner);
+    return SCCG_OK;
+}
+
+int sccg_mgpu_stash_device(sccg_mgpu* g, int32_t item, const void* d_data, int64_t len) {
+    if (!g || len < 0 || (len > 0 && !d_data)) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_CK(cudaSetDevice(g->ctx->device));
+    return mg_stash(g, item, d_data, len);
+}
+
+// compress_genome of one pair of this rank; the encoded image stays on the device and joins the rank's outgoing streams
+static int mg_compress_item(sccg_mgpu* g, int32_t item, const char* ref, int64_t ref_len, const char* tgt, int64_t tgt_len, const char* header, int64_t header_len,
+                            int device_inputs, int64_t* enc_len, int* mode_out) {
+    sccg_ctx* c = g->ctx;
+    SCCG_TRY(check_sizes(ref_len, tgt_len));
+    SCCG_TRY(check_header(header, header_len));
+    SCCG_CK(cudaSetDevice(c->device));
+    prof_reset(c);
+    CompressResult res;
+    if (device_inputs) {
+        if (((uintptr_t)ref | (uintptr_t)tgt) & 15) return set_error(SCCG_E_ARG, "device inputs must be 16-byte aligned");
+        SCCG_TRY(compress_device(c, (const u8*)ref, ref_len, (const u8*)tgt, tgt_len, header, header_len < 0 ? 0 : header_len, &res, nullptr));
+    } else {
+        u8 *d_ref = nullptr, *d_tgt = nullptr;
+        ChunkArrival arr;
+        SCCG_TRY(enqueue_pair_upload(c, ref, ref_len, tgt, tgt_len, &d_ref, &d_tgt, &arr));
+        int rc_c = compress_device(c, d_ref, ref_len, d_tgt, tgt_len, header, header_len < 0 ? 0 : header_len, &res, &arr);
+        SCCG_CK(cudaStreamSynchronize(c->s_h2d));                             // the caller's buffers are no longer in use
+        if (rc_c != SCCG_OK) return rc_c;
+        cudaEventElapsedTime(&c->prof.h2d_ms, c->ev[4], c->ev[5]);
+    }
+    SCCG_TRY(mg_stash(g, item, res.d_out, res.out_len));
+    if (enc_len) *enc_len = res.out_len;
+    if (mode_out) *mode_out = res.mode;
+    return res.stoi_failed ? stoi_failure() : SCCG_OK;
+}
+
+int sccg_mgpu_compress_item(sccg_mgpu* g, int32_t item, const char* ref, int64_t ref_len, const char* tgt, int64_t tgt_len, const char* header, int64_t header_len,
+                            int64_t* enc_len, int* mode_out) {
+    if (!g || (ref_len > 0 && !ref) || (tgt_len > 0 && !tgt) || (header_len > 0 && !header)) return set_error(SCCG_E_ARG, "null argument");
+    return mg_compress_item(g, item, ref, ref_len, tgt, tgt_len, header, header_len, 0, enc_len, mode_out);
+}
+
+int sccg_mgpu_compress_item_device(sccg_mgpu* g, int32_t item, const void* d_ref, int64_t ref_len, const void* d_tgt, int64_t tgt_len, const char* header,
+                                   int64_t header_len, int64_t* enc_len, int* mode_out) {
+    if (!g || (ref_len > 0 && !d_ref) || (tgt_len > 0 && !d_tgt) || (header_len > 0 && !header)) return set_error(SCCG_E_ARG, "null argument");
+    return mg_compress_item(g, item, (const char*)d_ref, ref_len, (const char*)d_tgt, tgt_len, header, header_len, 1, enc_len, mode_out);
+}
+
+int sccg_mgpu_gather(sccg_mgpu* g, char* out, int64_t out_cap, int32_t* item_ids, int64_t* item_offs, int64_t* item_lens, int32_t cap_items,
+                     int32_t* n_items, int64_t* total) {
+    if (!g) return set_error(SCCG_E_ARG, "null argument");
+    if (g->rank == 0 && (!out || !item_ids || !item_offs || !item_lens)) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_CK(cudaSetDevice(g->ctx->device));
+    return mg_gather(g, out, out_cap, item_ids, item_offs, item_lens, cap_items, n_items, total);
+}
+
+// One pair, segment pairs spread over all ranks (compression.cpp:381-481 sharded by segment range).  Collective: every rank
+// passes the same pair but only touches -- and only uploads -- its own slices.  Rank 0 receives the file image.
+int sccg_mgpu_compress_sharded(sccg_mgpu* g, const char* ref, int64_t ref_len, const char* tgt, int64_t tgt_len, const char* header, int64_t header_len,
+                               char* out, int64_t out_cap, int64_t* out_len, int* mode_out, int* sharded_out) {
+    if (!g || !out_len || (ref_len > 0 && !ref) || (tgt_len > 0 && !tgt) || (header_len > 0 && !header)) return set_error(SCCG_E_ARG, "null argument");
+    sccg_ctx* c = g->ctx;
+    const int W = g->world, rank = g->rank;
+    if (rank == 0 && !out) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_TRY(check_sizes(ref_len, tgt_len));
+    SCCG_TRY(check_header(header, header_len));
+    SCCG_CK(cudaSetDevice(c->device));
+    prof_reset(c);
+    if (header_len < 0) header_len = 0;
+    cudaStream_t s = c->main_stream;
+    std::vector<i64> ra, rb;
+    std::vector<sccg_shard_carry> carries;
+    bool sharded = mg_segment_ranges(ref_len, tgt_len, W, &ra, &rb);
+    if (sharded) {
+        const i64 a = ra[rank], b = rb[rank];
+        const int is_last = rank == W - 1;
+        const i64 r_end = b * SEG < ref_len ? b * SEG : ref_len;
+        const i64 rl = r_end - a * SEG, tl = is_last ? tgt_len - a * SEG : (b - a) * SEG;
+        u8 *d_ref = nullptr, *d_tgt = nullptr;
+        ChunkArrival arr;
+        ShardBorder* d_border = nullptr;
+        int rc = enqueue_pair_upload(c, ref + a * SEG, rl, tgt + a * SEG, tl, &d_ref, &d_tgt, &arr);
+        if (rc == SCCG_OK) rc = shard_match(c, d_ref, rl, d_tgt, tl, a, is_last, &arr, &d_border);
+        if (c->pipe_ready) cudaStreamSynchronize(c->s_h2d);                   // the caller's buffers are no longer in use
+        const void* send = d_border;
+        if (rc != SCCG_OK) {                                                  // a failed rank still takes part in the exchange and tells the others
+            ShardBorder* eb = (ShardBorder*)g->h_meta;
+            memset(eb, 0, sizeof *eb); eb->pad[0] = -1;
+            SCCG_CK(cudaMemcpyAsync(g->d_meta, eb, sizeof *eb, cudaMemcpyHostToDevice, s));
+            send = g->d_meta;
+        }
+        SCCG_TRY(g->tr->all_gather(send, g->d_border_all, sizeof(ShardBorder), s));
+        SCCG_CK(cudaMemcpyAsync(g->h_border, g->d_border_all, sizeof(ShardBorder) * (size_t)W, cudaMemcpyDeviceToHost, s));
+        SCCG_CK(cudaStreamSynchronize(s));
+        if (rc != SCCG_OK) { c->shard.valid = 0; return rc; }
+        for (int r = 0; r < W; ++r) if (g->h_border[r].pad[0] == -1) { c->shard.valid = 0; return set_error(SCCG_E_CUDA, "sharded compress: another rank failed in its match phase"); }
+        sharded = mg_plan_carries(g->h_border, ra, rb, tgt_len, &carries);
+    }
+    g->last_sharded = sharded ? 1 : 0;
+    if (sharded_out) *sharded_out = g->last_sharded;
+    if (!sharded) {                                                           // T2 abort (-> global mode), '(' in the target, tiny pair: rank 0 alone
+        c->shard.valid = 0;
+        *out_len = 0;
+        if (rank != 0) { if (mode_out) *mode_out = -1; return SCCG_OK; }
+        return compress_host(c, ref, ref_len, tgt, tgt_len, header, header_len, out, out_cap, nullptr, out_len, mode_out);
+    }
+    // ---- write phase: sizes first (device), one all-gather tells every rank every size
+    u8 *d_low = nullptr, *d_body = nullptr;
+    i64 my_body = 0;
+    u32* sc = (u32*)c->bufs[B_SCALARS].p;
+    SCCG_TRY(shard_write_sizes(c, &carries[rank], &d_low));
+    SCCG_TRY(g->tr->all_gather(sc, g->d_meta_all, 64, s));
+    const u32* hs = (const u32*)(g->h_meta + MG_META_I64);
+    SCCG_CK(cudaMemcpyAsync((void*)hs, g->d_meta_all, 64 * (size_t)W, cudaMemcpyDeviceToHost, s));
+    SCCG_CK(cudaStreamSynchronize(s));
+    SCCG_TRY(shard_write_body(c, hs[rank * 16 + S_BODY_MAIN], &d_body, &my_body));
+    const i64 n_rseg = (ref_len + SEG - 1) / SEG, n_tseg = (tgt_len + SEG - 1) / SEG, n_iter = n_rseg < n_tseg ? n_rseg : n_tseg;
+    const i64 leftover = n_tseg > n_iter ? tgt_len - n_iter * SEG : 0;
+    std::vector<i64> low_len(W), body_len(W);
+    i64 low_sum = 0, body_sum = 0;
+    for (int r = 0; r < W; ++r) {
+        low_len[r] = hs[r * 16 + S_LOW_TEXT]; body_len[r] = (i64)hs[r * 16 + S_BODY_MAIN] + (r == W - 1 ? leftover : 0);
+        low_sum += low_len[r]; body_sum += body_len[r];
+    }
+    const i64 hdr_bytes = header_len > 0 ? header_len + 1 : 0;
+    const i64 total = hdr_bytes + low_sum + 3 + body_sum;
+    *out_len = rank == 0 ? total : 0;
+    if (mode_out) *mode_out = 0;
+    int rc = SCCG_OK;
+    if (rank == 0) {
+        if (total > out_cap) rc = set_error(SCCG_E_ARG, "output buffer too small (required size returned in *out_len)");
+        SCCG_TRY(mg_grow(&g->d_recv, &g->recv_cap, (size_t)total + 64, 0, s));
+        u8* img = g->d_recv;
+        SCCG_TRY(write_header(c, img, header, header_len));
+        char* sep = (char*)c->h_pinned + 12288;
+        sep[0] = '\n'; sep[1] = ','; sep[2] = '\n';
+        SCCG_CK(cudaMemcpyAsync(img + hdr_bytes + low_sum, sep, 3, cudaMemcpyHostToDevice, s));
+        std::vector<MgP2P> recvs;
+        i64 lo = hdr_bytes, bo = hdr_bytes + low_sum + 3;
+        for (int r = 0; r < W; ++r) {
+            if (r == 0) {
+                if (low_len[0]) SCCG_CK(cudaMemcpyAsync(img + lo, d_low, (size_t)low_len[0], cudaMemcpyDeviceToDevice, s));
+                if (body_len[0]) SCCG_CK(cudaMemcpyAsync(img + bo, d_body, (size_t)body_len[0], cudaMemcpyDeviceToDevice, s));
+            } else {
+                if (low_len[r]) recvs.push_back(MgP2P{img + lo, (size_t)low_len[r], r});
+                if (body_len[r]) recvs.push_back(MgP2P{img + bo, (size_t)body_len[r], r});
+            }
+            lo += low_len[r]; bo += body_len[r];
+        }
+        SCCG_TRY(g->tr->p2p(nullptr, 0, recvs.data(), (int)recvs.size(), s));
+        if (rc == SCCG_OK && total > 0) SCCG_CK(cudaMemcpyAsync(out, img, (size_t)total, cudaMemcpyDeviceToHost, s));
+    } else {
+        MgP2P sends[2]; int ns = 0;
+        if (low_len[rank]) sends[ns++] = MgP2P{d_low, (size_t)low_len[rank], 0};
+        if (body_len[rank]) sends[ns++] = MgP2P{d_body, (size_t)body_len[rank], 0};
+        SCCG_TRY(g->tr->p2p(sends, ns, nullptr, 0, s));
+    }
+    SCCG_CK(cudaStreamSynchronize(s));
+    if (c->pipe_ready) cudaEventElapsedTime(&c->prof.h2d_ms, c->ev[4], c->ev[5]);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]) == cudaSuccess) c->prof.match_ms = ms;
+    return rc;
+}
+
+// the rank-th of world contiguous pieces of the reconstructed file image (sccg_decompress_part); nothing is gathered: every
+// rank writes its piece at *part_offset of the output file
+int sccg_mgpu_decompress_sharded(sccg_mgpu* g, const char* ref_raw, int64_t ref_len, const char* intermediate, int64_t inter_len,
+                                 char* out, int64_t out_cap, int64_t* part_offset, int64_t* part_len, int64_t* total_len) {
+    if (!g) return set_error(SCCG_E_ARG, "null argument");
+    return sccg_decompress_part(g->ctx, ref_raw, ref_len, intermediate, inter_len, g->rank, g->world, out, out_cap, part_offset, part_len, total_len);
 }
 
 #ifdef SCCG_SEG_STATS

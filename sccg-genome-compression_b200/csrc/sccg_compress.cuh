@@ -81,6 +81,36 @@ struct ChunkArrival {
                              // 1: the reference is already resident, the TARGET arrives in chunks (sccg_compress_resident*)
 };
 
+// Host pair -> device, pipelined: the target goes up first (the run-list pipeline only needs it), then the reference in
+// chunks on the copy stream; the matcher starts on every chunk as it lands, so the kernels hide under the PCIe transfer.
+// Records ev[4] (start) and ev[5] (all copies done) for the profile.  The caller synchronises c->s_h2d before it returns.
+static int enqueue_pair_upload(sccg_ctx* c, const char* ref, i64 ref_len, const char* tgt, i64 tgt_len, u8** d_ref_out, u8** d_tgt_out, ChunkArrival* arr) {
+    u8 *d_ref = nullptr, *d_tgt = nullptr;
+    SCCG_TRY(pipe_streams(c));
+    SCCG_TRY(buf(c, B_REF, (size_t)ref_len + 128, &d_ref));
+    SCCG_TRY(buf(c, B_TGT, (size_t)tgt_len + 128, &d_tgt));
+    if (getenv("SCCG_PIPE_POISON")) {                                         // tests: a chunk read before it arrived shows up
+        SCCG_CK(cudaMemsetAsync(d_tgt, 0xEE, (size_t)tgt_len, c->stream));
+        SCCG_CK(cudaMemsetAsync(d_ref, 0xEE, (size_t)ref_len, c->stream));
+    }
+    SCCG_CK(cudaEventRecord(c->ev[4], c->stream));
+    SCCG_CK(cudaStreamWaitEvent(c->s_h2d, c->ev[4], 0));
+    arr->chunk = pipe_chunk_bytes(ref_len);
+    arr->n = ref_len > 0 ? (int)((ref_len + arr->chunk - 1) / arr->chunk) : 0;
+    arr->ev_ref = c->ev_h2d; arr->ev_tgt = c->ev_pipe[1]; arr->tgt_chunked = 0;
+    if (tgt_len > 0) SCCG_CK(cudaMemcpyAsync(d_tgt, tgt, (size_t)tgt_len, cudaMemcpyHostToDevice, c->s_h2d));
+    SCCG_CK(cudaMemsetAsync(d_tgt + tgt_len, 0, 64, c->s_h2d));
+    SCCG_CK(cudaEventRecord(arr->ev_tgt, c->s_h2d));
+    for (int i = 0; i < arr->n; ++i) {
+        const i64 off = (i64)i * arr->chunk, len = (ref_len - off) < arr->chunk ? (ref_len - off) : arr->chunk;
+        SCCG_CK(cudaMemcpyAsync(d_ref + off, ref + off, (size_t)len, cudaMemcpyHostToDevice, c->s_h2d));
+        SCCG_CK(cudaEventRecord(arr->ev_ref[i], c->s_h2d));
+    }
+    SCCG_CK(cudaEventRecord(c->ev[5], c->s_h2d));
+    *d_ref_out = d_ref; *d_tgt_out = d_tgt;
+    return SCCG_OK;
+}
+
 static const int LM_PROBE_SEGS = 40;             // segments of the abort probe (see compress_device)
 
 static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt, i64 nt, const char* header, i64 nh, CompressResult* res,
