@@ -64,6 +64,9 @@ typedef struct {
     int32_t mode;         /* compress: 0 local, 1 global                                */
     int32_t front_steps;  /* global parse: exact steps the sequential front executed itself */
     int32_t spec_rounds;  /* global parse: speculation rounds (1 + number of "lost" re-speculations) */
+    float index_ms;       /* global mode: reference k-mer index (hash + radix sort + bucket table)       */
+    float parse_ms;       /* global mode: speculative chunk parse + exact front + concatenation        */
+    float exchange_ms;    /* multi-GPU layer: the collective(s) of the last sccg_mgpu_* call           */
 } sccg_profile;
 
 sccg_ctx*   sccg_create(int device);                 /* NULL on failure (see sccg_last_error)      */

@@ -69,6 +69,7 @@ sccg_ctx* sccg_create(int device) {
     c->stream = c->main_stream;
     for (int i = 0; ok && i < 6; ++i) ok = cudaEventCreate(&c->ev_side[i]) == cudaSuccess;
     for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+    for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreate(&c->ev_x[i]) == cudaSuccess;
     if (!ok) { set_error(SCCG_E_CUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError())); sccg_destroy(c); return nullptr; }
     return c;
 }
@@ -80,6 +81,7 @@ void sccg_destroy(sccg_ctx* c) {
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->res_ref) cudaFree(c->res_ref);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 4; ++i) if (c->ev_x[i]) cudaEventDestroy(c->ev_x[i]);
     if (c->main_stream) cudaStreamDestroy(c->main_stream);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     for (int i = 0; i < 6; ++i) if (c->ev_side[i]) cudaEventDestroy(c->ev_side[i]);

@@ -52,6 +52,7 @@ struct sccg_ctx {
     void* h_pinned;            // small pinned staging area for scalars
     size_t h_pinned_cap;
     cudaEvent_t ev[8];
+    cudaEvent_t ev_x[4];           // phase marks inside a call (global mode: index / parse; multi-GPU: exchange)
     sccg_profile prof;
     unsigned scan_epoch[2];        // single-pass scan, per lane (0 = main stream, 1 = side stream): epoch of the last launch,
     unsigned scan_counter_base[2]; //   tiles handed out so far

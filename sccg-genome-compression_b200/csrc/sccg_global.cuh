@@ -698,6 +698,7 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
     if (k < 8 || k > 16) return set_error(SCCG_E_ARG, "global match_sequences supports 8 <= k <= 16");
     if (m < 0 || m > GP_MAX_M) return set_error(SCCG_E_ARG, "global match_sequences supports 0 <= m <= 120");
     // ---- reference k-mer index (:41-47): 24-bit hash keys + stable radix sort
+    SCCG_CK(cudaEventRecord(c->ev_x[0], c->stream));
     const i64 nk = nr - k + 1 > 0 ? nr - k + 1 : 0;
     u32 *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr;
     SCCG_TRY(buf(c, B_GKEYS, (size_t)nk + 1, &keys));
@@ -715,6 +716,7 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
     if (const char* env = getenv("SCCG_GP_BUCKET_BITS")) { int v = atoi(env); if (v >= 4 && v <= GP_HASH_BITS) bucket_bits = v; }    // tests: small inputs through the 24-bit path
     SCCG_TRY(buf(c, B_GBUCKET, ((size_t)1 << bucket_bits) + 2, &bucket));
     LAUNCH(c, kmer_buckets_k, dim3(div_up(nk + 1, 256 * KB_SPAN)), dim3(256), 0, (const u32*)keys, nk, bucket, bucket_bits);
+    SCCG_CK(cudaEventRecord(c->ev_x[1], c->stream));
     // ---- chunk-speculative parse (:64-161)
     int chunk = GP_CHUNK_DEFAULT;
     if (const char* env = getenv("SCCG_GP_CHUNK")) { int v = atoi(env); if (v >= 64 && v <= (1 << 24)) chunk = v; }
@@ -770,8 +772,11 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
         unsigned g = np < (unsigned)c->sm_count * 16u ? np : (unsigned)c->sm_count * 16u;
         LAUNCH(c, gp_concat_k, dim3(g), dim3(128), 0, f, (const u32*)pcounts, np, obuf, obuf + cap_all, obuf + 2 * cap_all);
     }
+    SCCG_CK(cudaEventRecord(c->ev_x[2], c->stream));
     u32 h[S_COUNT];
     SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
+    cudaEventElapsedTime(&c->prof.index_ms, c->ev_x[0], c->ev_x[1]);
+    cudaEventElapsedTime(&c->prof.parse_ms, c->ev_x[1], c->ev_x[2]);
     out->tpos = obuf; out->p = obuf + cap_all; out->l = obuf + 2 * cap_all; out->count = h[S_G1];
     c->prof.front_steps = (int32_t)h_st.steps;
     return SCCG_OK;

@@ -373,6 +373,7 @@ static int mg_gather(sccg_mgpu* g, char* out, i64 out_cap, int32_t* ids, int64_t
     sccg_ctx* c = g->ctx;
     cudaStream_t s = c->main_stream;
     const int W = g->world;
+    SCCG_CK(cudaEventRecord(c->ev_x[0], s));
     long long* mine = g->h_meta;                       // [0]: own record, [1 .. W]: everybody's
     memset(mine, 0, sizeof(long long) * MG_META_I64);
     mine[0] = g->n_items; mine[1] = (long long)g->stash_len;
@@ -414,7 +415,11 @@ static int mg_gather(sccg_mgpu* g, char* out, i64 out_cap, int32_t* ids, int64_t
         if (total) *total = 0;
         if (n_items) *n_items = 0;
     }
+    SCCG_CK(cudaEventRecord(c->ev_x[1], s));
     SCCG_CK(cudaStreamSynchronize(s));
+    memset(&c->prof, 0, sizeof c->prof);
+    cudaEventElapsedTime(&c->prof.exchange_ms, c->ev_x[0], c->ev_x[1]);
+    c->prof.kernels_ms = c->prof.exchange_ms;
     g->n_items = 0; g->stash_len = 0;
     return rc;
 }
