@@ -39,6 +39,8 @@ struct LmWarpSmem {
     u32 head[LM_HT];       // 0 = empty, else chain entry: (p + 1) | 6 tag bits of the k-mer hash << 10
     u16 next[1024];        // chain: 0 = end, else entry of the next position
     u32 mlist[LM_SLOT + 4];
+    u16 mis[32];           // diagonal-hypothesis path: mismatching symbols, ascending, + sentinel
+    u16 qv[32];            //   looked-up windows: position | clean << 15
 };
 
 // seginfo layout
@@ -269,130 +271,191 @@ __device__ __forceinline__ int lm_parse(LmWarpSmem& S, const u32 (&wm)[4], int L
 // If every k-mer the greedy parse looks up has no occurrence in r other than the one on diagonal 0 (p == j), the parse is
 // fully determined by the positions where r and t differ: a window t[j..j+k) without a mismatch matches at p = j and
 // extends to the next mismatch (single candidate: no tie, `pn == 0` cannot be displaced, :114-130); a window that
-// contains a mismatch has no candidate and yields a literal (:77-81).  So the warp
-//   1. lists the mismatching symbols from the diagonal bitmap (<= DV_MAX_MIS, else the generic path runs),
-//   2. simulates that parse, collecting the <= 32 windows it looks up (one per lane),
-//   3. PROVES the hypothesis: the looked-up k-mers go into a small hash table and all k-mers of r are streamed past it
-//      (rolling hash, no insertion, no chains); any hit other than a clean window's own diagonal position -- a repeat in
-//      r, an off-diagonal occurrence of a mutated k-mer, or a mere 32-bit hash collision -- rejects the hypothesis.
-// Rejection falls back to the exact generic path (index + parse), so the result is always the reference's; acceptance
-// costs about half of the generic path because nothing is inserted and no candidate list is walked.
+// contains a mismatch has no candidate and yields a literal (:77-81).  With the mismatch positions m_0 < m_1 < ... and the
+// mismatch-free intervals [a_i, b_i) = [m_(i-1) + 1, m_i) between them that parse is, in closed form:
+//     interval of length >= k : one looked-up window at a_i (clean) -> match (a_i, a_i, b_i - a_i), the index jumps to b_i
+//     shorter interval        : every position of it is a looked-up window that contains m_i -> literals
+//     every m_i               : a looked-up window that starts with a mismatch -> literal
+// (windows must start at j <= L - k, :64).  So the warp works lane-parallel, no serial walk:
+//   1. mismatching symbols from the diagonal XOR words it still holds in registers (one packed warp scan orders them),
+//   2. lane i owns interval i: its looked-up windows (<= 32 in total, else the generic path runs) and its match,
+//   3. PROOF of the hypothesis.  An occurrence of a looked-up k-mer t[j..j+k) at r[p..p+k) implies that the 8-byte chunk
+//      of r at the next multiple of 4, a = ceil4(p), equals the 8 bytes of t at u = j + (a - p), u in {j .. j+3}
+//      (u + 8 <= j + k needs k >= 11).  So the <= 4 * 32 chunks t[u..u+8) go into a hash table keyed by content and every
+//      lane probes the 250 four-aligned chunks of r (8 per lane, straight from two 16-byte shared-memory loads): 8
+//      instructions per chunk and no per-position work at all.  A table entry carries u: a hit with a == u is the
+//      diagonal itself (the expected occurrence of a clean window, no occurrence at all for a window with a mismatch) and is
+//      ignored by construction (the XOR below is 0); any other hit is checked symbol by symbol, and a real occurrence --
+//      a repeat in r, an off-diagonal occurrence of a mutated k-mer -- rejects the hypothesis.
+// Rejection falls back to the exact generic path (index + parse), so the result is always the reference's.
 // ------------------------------------------------------------------------------------------------
-static const int DV_MAX_MISWORDS = 12;
-static const int DV_MAX_MIS = 24;
+static const int DV_MAX_MISWORDS = 16;        // mismatching 8-byte words (<= 128 symbols: the packed scan below cannot overflow)
+static const int DV_MAX_MIS = 30;             // mismatching symbols (+ sentinel <= 32 intervals, one per lane)
+static const int DV_TAB = 1024;               // table slots: S.head and S.next together (4 KiB)
 
-static const int DV_QPOS = 512;               // S.next[DV_QPOS + slot]: (window position + 1) | clean << 15
-// slot of the looked-up-window table: bits 9..17 of the rolling hash mix the last five symbols; slot quality only decides
-// how often two windows collide (-> generic path), never correctness
-__device__ __forceinline__ u32 dv_slot(u32 h) { return (h >> 9) & (u32)(LM_HT - 1); }
-// returns the number of matches (stored in S.mlist), or 0 when the hypothesis was rejected / not applicable.
-// head_clean (in/out): S.head is all zero.
-__device__ __forceinline__ int lm_diag_parse(LmWarpSmem& S, const u32 (&wm)[4], int L, int k, bool& head_clean) {
+__device__ __forceinline__ u32 dv_hash(u32 lo, u32 hi) { return (lo * 0x9E3779B1u + hi) * 0x85EBCA6Bu; }
+// table entry / probe value: hash bits 11..31, bit 10 set (an empty slot is 0), symbol position in bits 0..9
+__device__ __forceinline__ u32 dv_slot(u32 e, u32 alt_shift) { return (e >> alt_shift) & (u32)(DV_TAB - 1); }   // alt_shift: 22, or 12 on the retry
+
+// returns the number of matches (written to gmatches, their summed length in covered), or 0 when the hypothesis was
+// rejected / not applicable.  tab_clean (in/out): the 4 KiB table region is all zero.
+__device__ __forceinline__ int lm_diag_parse(LmWarpSmem& S, const u64 (&rw)[4], const u64 (&tw)[4], const u32 (&wm)[4], int L, int k, bool& tab_clean,
+                                             u32* __restrict__ gmatches, int& covered) {
     const int lane = lane_of();
     if (__popc(wm[0]) + __popc(wm[1]) + __popc(wm[2]) + __popc(wm[3]) > DV_MAX_MISWORDS) return 0;
-    // ---- 1. mismatching symbols, ascending (uniform; lane 0 stores)
-    const u64* r64 = reinterpret_cast<const u64*>(S.r);
-    const u64* t64 = reinterpret_cast<const u64*>(S.t);
-    u16* M = S.next;
-    int c = 0;
-#pragma unroll 1
+    // ---- 1. mismatching symbols.  Lane holds the words q = lane + 32 * it; symbol order is it-major.
+    u32 bm[4];
+    u32 cntp = 0u;                                                  // four 8-bit counters, one per `it`
+#pragma unroll
     for (int it = 0; it < 4; ++it) {
-#pragma unroll 1
-        for (u32 m = wm[it]; m; m &= m - 1) {
-            const int q = 32 * it + __ffs((int)m) - 1;
-            u32 bm = movemask8(nonzero_flags8(r64[q] ^ t64[q]));
-            if (8 * q + 8 > L) bm &= (1u << (L - 8 * q)) - 1u;
-#pragma unroll 1
-            for (; bm; bm &= bm - 1) {
-                if (c < DV_MAX_MIS && lane == 0) M[c] = (u16)(8 * q + __ffs((int)bm) - 1);
-                ++c;
+        bm[it] = 0u;
+        if (wm[it]) {                                               // uniform
+            const u64 d = rw[it] ^ tw[it];
+            if (d) {
+                const int q = lane + 32 * it;
+                u32 m = movemask8(nonzero_flags8(d));
+                if (8 * q + 8 > L) m = 8 * q < L ? (m & ((1u << (L - 8 * q)) - 1u)) : 0u;
+                bm[it] = m;
+                cntp |= (u32)__popc(m) << (8 * it);
             }
         }
     }
+    const u32 incl = warp_scan_incl(cntp);
+    const u32 tot = __shfl_sync(SCCG_FULL_MASK, incl, 31);
+    const int c = (int)((tot & 0xffu) + ((tot >> 8) & 0xffu) + ((tot >> 16) & 0xffu) + (tot >> 24));
     if (c > DV_MAX_MIS) return 0;
-    if (lane == 0) M[c] = (u16)L;                                  // sentinel
-    __syncwarp();
-    // ---- 2. the parse under the hypothesis; lane v keeps the v-th looked-up window
-    int j = 0, i = 0, nq = 0, nmatch = 0, myj = 0;
-    bool myclean = false;
-    while (j <= L - k) {
-        const int next = (int)M[i];                                 // first mismatch at or after j
-        const bool clean = next - j >= k;
-        if (nq >= 32) return 0;
-        if (lane == nq) { myj = j; myclean = clean; }
-        ++nq;
-        if (clean) {
-            if (lane == 0) S.mlist[nmatch] = (u32)j | ((u32)j << 10) | ((u32)(next - j) << 20);
-            ++nmatch;
-            j = next;
-        } else {
-            ++j;
-            if (next < j) ++i;
+    {
+        const u32 excl = incl - cntp;
+        u32 base = 0u;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            if (bm[it]) {
+                u32 off = base + ((excl >> (8 * it)) & 0xffu);
+                const int q = lane + 32 * it;
+                for (u32 m = bm[it]; m; m &= m - 1) S.mis[off++] = (u16)(8 * q + __ffs((int)m) - 1);
+            }
+            base += (tot >> (8 * it)) & 0xffu;
         }
     }
-    if (nmatch == 0) return 0;
-    // ---- 3. proof: no other occurrence of any looked-up k-mer in r
-    if (!head_clean) {
-        for (int x = lane; x < LM_HT; x += 32) S.head[x] = 0u;
-        head_clean = true;
-        __syncwarp();
-    }
-    const u32 mul = 1u << lm_hash_shift(k);
-    u32 H = 0u;
-    if (lane < nq) {
-#pragma unroll 2
-        for (int x = 0; x < k; ++x) H = mad_u32(H, mul, S.t[myj + x]);
-    }
-    const u32 slot = dv_slot(H);
-    const u16 tag = (u16)((myj + 1) | (myclean ? 0x8000 : 0));     // which window sits in the slot
-    const u32 valid = nq >= 32 ? 0xffffffffu : ((1u << nq) - 1u);
-    const u32 peers = __match_any_sync(SCCG_FULL_MASK, lane < nq ? H : 0xffffffffu - (u32)lane);
-    if (lane < nq) { S.head[slot] = H; M[DV_QPOS + slot] = tag; }
+    if (lane == 0) S.mis[c] = (u16)L;                               // sentinel
     __syncwarp();
-    // two windows with one hash, two hashes in one slot, or the "empty" value: not provable here
-    bool bad = lane < nq && (H == 0u || (peers & valid) != (1u << lane) || S.head[slot] != H || M[DV_QPOS + slot] != tag);
-    if (!__any_sync(SCCG_FULL_MASK, bad)) {
-        // every lane streams `chunk` + 1 consecutive k-mers of r (the extra one overlaps the next lane: an odd byte stride
-        // keeps the lanes on different banks), four per step: four independent table probes, ONE branch
-        const int nk = L - k + 1;
-        const int chunk = (nk + 31) >> 5;
-        const int steps = (chunk + 4) >> 2;
-        int p = lane * chunk;
-        u32 h = 0u;
-        if (p < nk) {
-#pragma unroll 4
-            for (int x = 0; x < k - 1; ++x) h = mad_u32(h, mul, S.r[p + x]);     // hash of r[p .. p+k-1)
+    // ---- 2. lane i owns the mismatch-free interval [a, b) before mismatch i (i == c: the tail up to L)
+    const bool act = lane <= c;
+    int a = 0, b = L;
+    if (act) { a = lane ? (int)S.mis[lane - 1] + 1 : 0; b = (int)S.mis[lane]; }
+    const int len = b - a;
+    const bool lng = act && len >= k;
+    int nshort = 0;
+    if (act && !lng) { const int hi = b < L - k + 1 ? b : L - k + 1; nshort = hi > a ? hi - a : 0; }
+    const int qmis = (act && lane < c && b <= L - k) ? 1 : 0;       // the window that starts at the mismatch itself
+    const u32 pk = (u32)((lng ? 1 : nshort) + qmis) | (lng ? 0x10000u : 0u);
+    const u32 incl2 = warp_scan_incl(pk);
+    const u32 tot2 = __shfl_sync(SCCG_FULL_MASK, incl2, 31);
+    const int nq = (int)(tot2 & 0xffffu), nmatch = (int)(tot2 >> 16);
+    if (nq > 32 || nmatch == 0) return 0;
+    {
+        u32 qo = (incl2 - pk) & 0xffffu;
+        if (lng) {
+            S.qv[qo++] = (u16)(a | 0x8000);
+            gmatches[(incl2 - pk) >> 16] = (u32)a | ((u32)a << 10) | ((u32)len << 20);
+        } else {
+            for (int x = 0; x < nshort; ++x) S.qv[qo++] = (u16)(a + x);
+        }
+        if (qmis) S.qv[qo] = (u16)b;
+    }
+    covered = (int)__reduce_add_sync(SCCG_FULL_MASK, lng ? (u32)len : 0u);
+    u32* tab = S.head;                                              // head[512] and next[1024] are adjacent: 1024 u32 slots
+    if (!tab_clean) {
+        uint4* t4 = reinterpret_cast<uint4*>(tab);
+#pragma unroll
+        for (int x = 0; x < DV_TAB / 4 / 32; ++x) t4[lane + 32 * x] = make_uint4(0u, 0u, 0u, 0u);
+        tab_clean = true;
+    }
+    __syncwarp();
+    // ---- 3a. the chunks t[u .. u+8), u = j .. j+3, of this lane's looked-up window
+    const bool isq = lane < nq;
+    const int myj = isq ? (int)(S.qv[lane] & 0x3ffu) : 0;
+    u32 e[4];
+    {
+        const u32* t32 = reinterpret_cast<const u32*>(S.t);
+        const int w = myj >> 2;
+        const u32 sh = (u32)(myj & 3) * 8u;
+        const u32 a0 = t32[w], a1 = t32[w + 1], a2 = t32[w + 2], a3 = t32[w + 3];
+        const u32 w0 = __funnelshift_r(a0, a1, sh), w1 = __funnelshift_r(a1, a2, sh), w2 = __funnelshift_r(a2, a3, sh);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const u32 lo = o ? __funnelshift_r(w0, w1, 8u * o) : w0, hi = o ? __funnelshift_r(w1, w2, 8u * o) : w1;
+            e[o] = (dv_hash(lo, hi) & ~1023u) | 1024u | (u32)(myj + o);
+        }
+    }
+    u32 alt = 22u;
+    for (;;) {
+        if (isq) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) tab[dv_slot(e[o], alt)] = e[o];
+        }
+        __syncwarp();
+        bool coll = false;                                          // two different chunks in one slot (equal chunks of neighbouring windows coincide)
+        if (isq) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) coll |= tab[dv_slot(e[o], alt)] != e[o];
+        }
+        if (!__any_sync(SCCG_FULL_MASK, coll)) break;
+        __syncwarp();
+        if (isq) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) tab[dv_slot(e[o], alt)] = 0u;
+        }
+        __syncwarp();
+        if (alt == 12u) return 0;                                   // collides under both slot functions (or equal chunks at different positions): generic path
+        alt = 12u;
+    }
+    // ---- 3b. probe: lane owns the chunks at a = 16 * lane + 4 * x and 512 + 16 * lane + 4 * x, x = 0 .. 3
+    bool bad = false;
+    {
+        const uint4 x0 = reinterpret_cast<const uint4*>(S.r)[lane], x1 = reinterpret_cast<const uint4*>(S.r)[32 + lane];
+        const u32 y0 = reinterpret_cast<const u32*>(S.r)[4 * lane + 4], y1 = reinterpret_cast<const u32*>(S.r)[128 + 4 * lane + 4];
+        const u32 rr[10] = {x0.x, x0.y, x0.z, x0.w, y0, x1.x, x1.y, x1.z, x1.w, y1};
+        const u32 A = (u32)(16 * lane) | 1024u;
+        bool hit = false;
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            const int wi = x < 4 ? x : x + 1;
+            const u32 h = dv_hash(rr[wi], rr[wi + 1]);
+            const u32 ent = tab[(h >> alt) & (u32)(DV_TAB - 1)];
+            const u32 pos = (x < 4 ? 0u : 512u) | (u32)(4 * (x & 3));           // A | pos = 1024 | a (disjoint bits)
+            const u32 xo = ((h & ~1023u) | A) ^ ent ^ pos;                      // 0: the diagonal chunk itself; 1..1023: same content, other position
+            hit |= (xo - 1u) < 1023u;
+        }
+        if (__any_sync(SCCG_FULL_MASK, hit)) {
+            // rare: some chunk of r has the content of a looked-up chunk at another position -- is it a whole k-mer?
+            if (hit) {
 #pragma unroll 1
-            for (int st = 0; st < steps; ++st, p += 4) {
-                const u8* in = S.r + p + k - 1;                       // the symbols entering at p .. p+3 (zero padding past the end);
-                const u32 h0 = mad_u32(h, mul, in[0]);                // byte loads: the LSU has headroom, the ALU pipe does not
-                const u32 h1 = mad_u32(h0, mul, in[1]);
-                const u32 h2 = mad_u32(h1, mul, in[2]);
-                const u32 h3 = mad_u32(h2, mul, in[3]);
-                const u32 e0 = S.head[dv_slot(h0)], e1 = S.head[dv_slot(h1)], e2 = S.head[dv_slot(h2)], e3 = S.head[dv_slot(h3)];
-                h = h3;
-                if ((e0 == h0) | (e1 == h1) | (e2 == h2) | (e3 == h3)) {
-                    // rare: position p + x of r has the hash of a looked-up window (the hash ignores the first
-                    // k - ceil(32/s) symbols, so a mutated window whose substitution sits there lands here once).  The
-                    // own diagonal position of a clean window is expected; anything else counts only if the k-mers are
-                    // really equal.
-                    u32 m = (e0 == h0 ? 1u : 0u) | (e1 == h1 ? 2u : 0u) | (e2 == h2 ? 4u : 0u) | (e3 == h3 ? 8u : 0u);
+                for (int x = 0; x < 8; ++x) {
+                    const int ra = (x < 4 ? 0 : 512) + 16 * lane + 4 * (x & 3);
+                    const u32* r32 = reinterpret_cast<const u32*>(S.r) + (ra >> 2);   // (re-read: indexing the register copy would put it on the stack)
+                    const u32 h = dv_hash(r32[0], r32[1]);
+                    const u32 ent = tab[(h >> alt) & (u32)(DV_TAB - 1)];
+                    const u32 xo = ((h & ~1023u) | 1024u | (u32)ra) ^ ent;
+                    if ((xo - 1u) >= 1023u) continue;
+                    const int u = (int)(ent & 1023u);
 #pragma unroll 1
-                    for (; m; m &= m - 1) {
-                        const int x = __ffs((int)m) - 1;
-                        const u32 hx = x == 0 ? h0 : x == 1 ? h1 : x == 2 ? h2 : h3;
-                        const int px = p + x;
-                        const u32 tg = M[DV_QPOS + dv_slot(hx)];
-                        const int qj = (int)(tg & 0x3ffu) - 1;
-                        if (px >= nk || ((tg & 0x8000u) && qj == px)) continue;
-                        if (kmer_equal_smem(S.r, px, S.t, qj, k)) bad = true;
+                    for (int v = 0; v < nq; ++v) {
+                        const int j = (int)(S.qv[v] & 0x3ffu);
+                        const int d = u - j;
+                        if (d < 0 || d > 3) continue;
+                        const int pp = ra - d;
+                        if (pp >= 0 && pp <= L - k && kmer_equal_smem(S.r, pp, S.t, j, k)) bad = true;
                     }
                 }
             }
         }
     }
     __syncwarp();
-    if (lane < nq) S.head[slot] = 0u;                               // leave the table clean for the next segment
+    if (isq) {                                                      // leave the table clean for the next segment
+#pragma unroll
+        for (int o = 0; o < 4; ++o) tab[dv_slot(e[o], alt)] = 0u;
+    }
     __syncwarp();
     return __any_sync(SCCG_FULL_MASK, bad) ? 0 : nmatch;
 }
@@ -463,15 +526,10 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
     const int claim = CLAIM;                                           // compile-time: a run-time claim size cost 15 % (registers in the hot loop)
     const int claim_base = seg_begin + warps_total * claim;            // the first warps_total * claim segments are pre-assigned
     int claimed_used = 0;
-    bool head_clean = false;                                  // S.head all zero (kept by the diagonal-hypothesis path)
+    bool tab_clean = false;                                   // S.head + S.next all zero (kept by the diagonal-hypothesis path)
     int seg = seg_begin + warp_global * claim < n_iter ? seg_begin + warp_global * claim : n_iter;
-#ifdef SCCG_LM_EARLY_FETCH
-    lm_fetch(ref, nr, tgt, nt, seg, n_iter, lane, nrw, ntw);
-#endif
     while (seg < n_iter) {
-#ifndef SCCG_LM_EARLY_FETCH
         lm_fetch(ref, nr, tgt, nt, seg, n_iter, lane, nrw, ntw);
-#endif
         const i64 off = (i64)seg * SEG;
         const int Lr = (int)((nr - off) < SEG ? (nr - off) : SEG);
         const int Lt = (int)((nt - off) < SEG ? (nt - off) : SEG);
@@ -483,14 +541,14 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
         u32 wm[4];                                           // diagonal-0 mismatch flags per 8-byte word (uniform)
         const int wv = Lmin >> 3, rem = Lmin & 7;
         const bool full_pair = Lr == SEG && Lt == SEG;        // words past the end were fetched as 0 on both sides: no masking needed
+        // upper-case in place (:369-370) and compare on the diagonal, all in registers: an identical pair never touches shared memory
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             int q = lane + 32 * it;
             u64 rw = nrw[it], tw = ntw[it];
             if (rw & 0x2020202020202020ULL) rw = upper8(rw);                 // only bytes with bit 5 can be a-z
             if (tw & 0x2020202020202020ULL) tw = upper8(tw);
-            reinterpret_cast<u64*>(S.r)[q] = rw;
-            reinterpret_cast<u64*>(S.t)[q] = tw;
+            nrw[it] = rw; ntw[it] = tw;
             u64 diff = rw ^ tw;
             bool d = diff != 0ull;
             if (!full_pair) d = q < wv ? d : (q == wv && rem ? (diff & (~0ull >> (64 - 8 * rem))) != 0ull : false);
@@ -513,9 +571,6 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
             if (__shfl_sync(SCCG_FULL_MASK, stop, 0)) next_seg = n_iter;
         }
 #endif
-#ifdef SCCG_LM_EARLY_FETCH                                 // the next segment travels in 16 registers across the parse (measured 1 % slower, spills)
-        lm_fetch(ref, nr, tgt, nt, next_seg, n_iter, lane, nrw, ntw);
-#else
         if (next_seg < n_iter && lane < 16) {                 // pull the next segment into L2 only: no registers held across the parse
             const u8* pf = (lane < 8 ? ref : tgt) + (i64)next_seg * SEG + 128 * (lane & 7);
 #ifndef SCCG_EMU
@@ -524,47 +579,57 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
             (void)pf;
 #endif
         }
-#endif
-        if (lane < 2) reinterpret_cast<u64*>(S.r)[128 + lane] = 0ull, reinterpret_cast<u64*>(S.t)[128 + lane] = 0ull;
-        __syncwarp();
-
-        int nmatch = 0;
+        int nmatch = 0, covered = 0;
+        bool direct = false;                                 // the matches are already in global memory
         if (Lr == Lt && Lt >= k1 && (wm[0] | wm[1] | wm[2] | wm[3]) == 0u) {
             // t_i == r_i: candidate p = 0 extends to Lt; any other p gives l <= Lr - p < Lt -> untied
-            if (lane == 0) S.mlist[0] = 0u | (0u << 10) | ((u32)Lt << 20);
-            nmatch = 1;
+            if (lane == 0) matches[(i64)seg * LM_SLOT] = 0u | (0u << 10) | ((u32)Lt << 20);
+            nmatch = 1; covered = Lt; direct = true;
             SEG_STAT(0);
-        } else if (use_diag && Lr == Lt && Lt >= k1 && (nmatch = lm_diag_parse(S, wm, Lt, k1, head_clean)) > 0) {
-            // near-identical segment: parse determined by the mismatch positions, hypothesis proven against all of r
-            SEG_STAT(1);
         } else {
-            SEG_STAT(2);
-            head_clean = false;
-            // pass 1 with k (compression.cpp:401), pass 2 with k' only if pass 1 found no match (:428); one copy of the code
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                reinterpret_cast<u64*>(S.r)[lane + 32 * it] = nrw[it];
+                reinterpret_cast<u64*>(S.t)[lane + 32 * it] = ntw[it];
+            }
+            if (lane < 2) reinterpret_cast<u64*>(S.r)[128 + lane] = 0ull, reinterpret_cast<u64*>(S.t)[128 + lane] = 0ull;
+            __syncwarp();
+            if (use_diag && Lr == Lt && Lt >= k1 && k1 >= 11 &&
+                (nmatch = lm_diag_parse(S, nrw, ntw, wm, Lt, k1, tab_clean, matches + (i64)seg * LM_SLOT, covered)) > 0) {
+                // near-identical segment: parse determined by the mismatch positions, hypothesis proven against all of r
+                direct = true;
+                SEG_STAT(1);
+            } else {
+                SEG_STAT(2);
+                tab_clean = false;
+                // pass 1 with k (compression.cpp:401), pass 2 with k' only if pass 1 found no match (:428); one copy of the code
 #pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                const int k = pass ? k2 : k1;
-                if (k <= 0) break;
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int k = pass ? k2 : k1;
+                    if (k <= 0) break;
 #ifndef SCCG_NO_EARLY_ABORT
-                if (abort_flag) {                                                     // the launch is being discarded: do not start an expensive pass
-                    u32 stop = lane == 0 ? __ldcg(abort_flag) : 0u;
-                    if (__shfl_sync(SCCG_FULL_MASK, stop, 0)) break;
-                }
+                    if (abort_flag) {                                                     // the launch is being discarded: do not start an expensive pass
+                        u32 stop = lane == 0 ? __ldcg(abort_flag) : 0u;
+                        if (__shfl_sync(SCCG_FULL_MASK, stop, 0)) break;
+                    }
 #endif
-                if (pass) SEG_STAT(3);
-                lm_build_index(S, Lr, k);
-                nmatch = lm_parse(S, wm, Lr, Lt, k, pass ? pow2 : pow1);
-                if (nmatch) break;
+                    if (pass) SEG_STAT(3);
+                    lm_build_index(S, Lr, k);
+                    nmatch = lm_parse(S, wm, Lr, Lt, k, pass ? pow2 : pow1);
+                    if (nmatch) break;
+                }
             }
         }
         __syncwarp();
-        int covered = 0;
-        for (int m = lane; m < nmatch; m += 32) {
-            u32 pk = S.mlist[m];
-            matches[(i64)seg * LM_SLOT + m] = pk;
-            covered += (int)(pk >> 20);
+        if (!direct) {
+            covered = 0;                                     // (a rejected diagonal hypothesis may have left its own sum behind)
+            for (int m = lane; m < nmatch; m += 32) {
+                u32 pk = S.mlist[m];
+                matches[(i64)seg * LM_SLOT + m] = pk;
+                covered += (int)(pk >> 20);
+            }
+            covered = __reduce_add_sync(SCCG_FULL_MASK, covered);
         }
-        covered = __reduce_add_sync(SCCG_FULL_MASK, covered);
         // "segment consists only of N" (:419, :455) matters only where the driver would count the segment: compute it there
         int all_n = 0;
         if (nmatch == 0 || 2 * (Lt - covered) > Lt) {
