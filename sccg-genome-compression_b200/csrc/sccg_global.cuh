@@ -408,6 +408,7 @@ __device__ __forceinline__ bool gp_step(GpShared& S, const GpArgs& a, i64& j, in
 // ------------------------------------------------------------------------------------------------
 static const int GP_CHUNK_DEFAULT = 8192;       // positions per speculative chunk (measured: 21.6 ms vs 29.6 ms at 32768 on the divergent chr21-shaped pair) (SCCG_GP_CHUNK overrides it: tests use tiny chunks)
 static const int GP_DIAG_PROBES = 64;           // must stay 64 (vote encoding)
+static const int GP_WARM = 128;                 // positions before its boundary at which a chunk's diagonal guess is anchored
 
 struct GpChunkInfo { i64 entry_j; i64 exit_j; int entry_e; int exit_e; u32 count; int valid; };
 
@@ -420,7 +421,30 @@ struct GpSpecArgs {
     int slot;                   // 0 DIAG, 1 LOST
     u32 first_chunk;            // chunks >= first_chunk are (re)computed
     int lost_e;                 // slot 1: the e every chunk is entered with
+    u32* ctl;                   // ctl[GP_CTL_CANCEL]: the front got lost, speculation is pointless
 };
+enum { GP_CTL_CANCEL = 0 };
+// GpChunkInfo::valid: 0 = not computed yet (the front may be running concurrently with the second batch of chunks), 1 = usable,
+// 2 = computed but unusable (no diagonal guess, or cancelled).  Written LAST, behind a fence; the front reads chunk records
+// with L2 loads (ld_info) and only trusts the other fields once it has seen valid != 0.
+enum { GP_CHUNK_PENDING = 0, GP_CHUNK_OK = 1, GP_CHUNK_UNUSABLE = 2 };
+__device__ __forceinline__ void gp_publish(GpChunkInfo* info, int valid) {
+    __threadfence();
+    *reinterpret_cast<volatile int*>(&info->valid) = valid;
+}
+__device__ __forceinline__ GpChunkInfo ld_info(const GpChunkInfo* p) {
+    static_assert(sizeof(GpChunkInfo) == 32, "two 16-byte halves");
+    GpChunkInfo ci;
+    const int4 b = __ldcg(reinterpret_cast<const int4*>(p) + 1);          // entry_e, exit_e, count, valid
+    ci.entry_e = b.x; ci.exit_e = b.y; ci.count = (u32)b.z; ci.valid = b.w;
+    ci.entry_j = 0; ci.exit_j = 0;
+    if (b.w == GP_CHUNK_OK) {
+        __threadfence();
+        const int4 a = __ldcg(reinterpret_cast<const int4*>(p));
+        ci.entry_j = (i64)(((u64)(u32)a.y << 32) | (u32)a.x); ci.exit_j = (i64)(((u64)(u32)a.w << 32) | (u32)a.z);
+    }
+    return ci;
+}
 
 #ifndef SCCG_GP_MINB
 #define SCCG_GP_MINB 6            // 256-thread CTAs: 48 warps/SM at <= 40 registers (measured 4 / 5 / 6 CTAs: 2.60 / 2.51 / 2.47 ms on the gap pair)
@@ -438,49 +462,79 @@ __global__ void __launch_bounds__(GP_T, SCCG_GP_MINB) gp_spec_k(GpSpecArgs s) {
     i64 j = B;
     int e = s.lost_e;
     bool valid = true;
+    // the front (running concurrently with the second batch) got lost: everything speculated from here on would be thrown
+    // away (a "lost" parse only comes back by a chance hit, with another e).  The chunk stays invalid (info is zeroed).
+    if (__syncthreads_or(tid == 0 && *reinterpret_cast<volatile u32*>(s.ctl + GP_CTL_CANCEL) != 0u)) {
+        if (tid == 0) gp_publish(info, GP_CHUNK_UNUSABLE);
+        return;
+    }
     if (s.slot == 0 && c == 0) {
         e = -1;                                                   // the true initial state (0, -1): not a guess
     } else if (s.slot == 0) {
-        // diagonal guess: every probe position whose k-mer occurs exactly once in the reference votes for its
-        // diagonal; the most frequent diagonal wins (a k-mer hit by a mutation may be unique somewhere else)
-        i64 my_d = 0;
-        bool have = false;
-        if (tid < GP_DIAG_PROBES && B + tid <= last_j) {
-            i64 pos = B + tid;
-            u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
-            u32 h = kmer_hash_words(w0, w1, a.k);
-            i64 lo = index_lower_bound(a, h);
-            int hits = 0;
-            for (; lo < a.nk && a.keys[lo] == h && hits < 2; ++lo) {
-                const u8* rp = a.R + a.vals[lo];
-                if (kmer_equal_words(ld_unaligned64(rp), ld_unaligned64(rp + 8), w0, w1, a.k)) { ++hits; my_d = (i64)a.vals[lo] - pos; }
-            }
-            have = hits == 1;
-        }
+        // diagonal guess: every probe position whose k-mer occurs exactly once in the reference votes for its diagonal; the
+        // most frequent diagonal wins if probes at least 16 positions apart agree on it (a k-mer hit by a mutation -- or a k-mer
+        // of an inserted stretch -- may be unique somewhere else: one vote, or a few adjacent ones, prove nothing).  Probes come in rounds of 64 positions from the
+        // boundary on, so a chunk that begins inside an insertion still finds the diagonal of its homologous part.
         i64* votes = reinterpret_cast<i64*>(S.long_list);         // GP_DIAG_PROBES diagonals (scratch reuse)
-        if (tid < GP_DIAG_PROBES) votes[tid] = have ? my_d : (i64)0x7fffffffffffffffLL;
-        if (tid == 0) S.i_scratch[5] = -1;
-        __syncthreads();
-        int score = -1;
-        if (have) { score = 0; for (int x = 0; x < GP_DIAG_PROBES; ++x) score += votes[x] == my_d; }
-        if (score > 0) atomicMax(&S.i_scratch[5], score * 64 + (63 - tid));   // most votes, then the earliest probe
-        __syncthreads();
-        int best = S.i_scratch[5];
-        if (best < 0) valid = false;
-        else {
-            i64 d = votes[63 - (best & 63)];
-            i64 p0 = B + d;
-            if (p0 < 0 || p0 >= a.nr) valid = false;
+        i64 Q = B;                                                // first position of the winning round
+        i64 d = 0;
+        valid = false;
+        for (; Q < j_stop && Q <= last_j; Q += GP_DIAG_PROBES) {
+            i64 my_d = 0;
+            bool have = false;
+            if (tid < GP_DIAG_PROBES && Q + tid <= last_j) {
+                i64 pos = Q + tid;
+                u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
+                u32 h = kmer_hash_words(w0, w1, a.k);
+                i64 lo = index_lower_bound(a, h);
+                int hits = 0;
+                for (; lo < a.nk && a.keys[lo] == h && hits < 2; ++lo) {
+                    const u8* rp = a.R + a.vals[lo];
+                    if (kmer_equal_words(ld_unaligned64(rp), ld_unaligned64(rp + 8), w0, w1, a.k)) { ++hits; my_d = (i64)a.vals[lo] - pos; }
+                }
+                have = hits == 1;
+            }
+            if (tid < GP_DIAG_PROBES) votes[tid] = have ? my_d : (i64)0x7fffffffffffffffLL;
+            if (tid == 0) S.i_scratch[5] = -1;
+            __syncthreads();
+            int score = -1, first = GP_DIAG_PROBES, last = -1;
+            if (have) { score = 0; for (int x = 0; x < GP_DIAG_PROBES; ++x) if (votes[x] == my_d) { ++score; if (x < first) first = x; last = x; } }
+            // agreeing probes at least 16 positions apart: a chance match of k+1 or k+2 symbols cannot fake that
+            if (score > 1 && last - first >= 16) atomicMax(&S.i_scratch[5], score * 64 + (63 - tid));   // most votes, then the earliest probe
+            __syncthreads();
+            const int best = S.i_scratch[5];
+            if (best >= 0) { d = votes[63 - (best & 63)]; valid = true; }
+            __syncthreads();
+            if (valid) break;
+        }
+        if (valid) {
+            // The guess is anchored GP_WARM positions BEFORE the boundary ("the parse is inside a match on diagonal d there") and
+            // replayed up to it: two parses on one diagonal meet at the end of the next common match, so by the boundary the
+            // replay has normally become the true parse even where the boundary falls between two matches (divergent pairs: a
+            // third of the chunks otherwise fail to splice and cost the sequential front exact steps).  A diagonal that was only
+            // found further inside the chunk is anchored where it was found.
+            i64 Bw = Q > B ? Q : B - GP_WARM;
+            if (Bw < 0) Bw = 0;
+            if (Bw + d < 0) Bw = -d;
+            i64 p0 = Bw + d;
+            if (Q + d < 0 || p0 >= a.nr || Bw > Q) valid = false;
             else {
-                i64 maxl = (a.nr - p0) < (a.nt - B) ? (a.nr - p0) : (a.nt - B);
-                __syncthreads();
-                i64 l = block_lcp(S, a.R, p0, a.T, B, maxl);       // the match covering the boundary ends at its first mismatch
-                j = B + l;
+                i64 maxl = (a.nr - p0) < (a.nt - Bw) ? (a.nr - p0) : (a.nt - Bw);
+                i64 l = block_lcp(S, a.R, p0, a.T, Bw, maxl);      // the match covering the anchor ends at its first mismatch
+                j = Bw + l;
                 i64 ee = j + d - 1;
                 if (ee < 0 || ee > 0x7fffffff) valid = false; else e = (int)ee;
             }
         }
         __syncthreads();
+        // replay up to the boundary; nothing is recorded (those matches belong to the previous chunk)
+        while (valid && j < B && j <= last_j) {
+            int sel_p = 0, sel_l = 0;
+            const i64 scan_end = B < last_j + 1 ? B : last_j + 1;
+            if (!gp_step(S, a, j, e, scan_end, sel_p, sel_l)) break;     // no candidate before the boundary: j == scan_end
+            e = sel_p + sel_l - 1;
+            j += sel_l;
+        }
     }
     u32 n = 0;
     const i64 entry_j = j;
@@ -494,21 +548,43 @@ __global__ void __launch_bounds__(GP_T, SCCG_GP_MINB) gp_spec_k(GpSpecArgs s) {
             ++n;
             e = sel_p + sel_l - 1;
             j += sel_l;
+            if ((n & 15u) == 0u && __syncthreads_or(tid == 0 && *reinterpret_cast<volatile u32*>(s.ctl + GP_CTL_CANCEL) != 0u)) { valid = false; break; }
         }
     }
-    if (tid == 0) { info->entry_j = entry_j; info->entry_e = entry_e; info->exit_j = j; info->exit_e = e; info->count = n; info->valid = valid ? 1 : 0; }
+    if (tid == 0) {
+        info->entry_j = entry_j; info->entry_e = entry_e; info->exit_j = j; info->exit_e = e; info->count = n;
+        gp_publish(info, valid ? GP_CHUNK_OK : GP_CHUNK_UNUSABLE);          // (the matches were written by this thread too: ordered by the fence)
+    }
 }
 
 // pieces of the final match list, in order: a run of the front's own matches or a suffix of a chunk's speculative list
 struct GpPiece { u32 src; u32 first; u32 count; };          // src: 0xffffffff = front buffer, else slot * nchunks + chunk
-struct GpFrontState { i64 j; int e; int status; u32 npieces; u32 nfront; u32 lost_from_chunk; int lost_e; u32 steps; u32 spliced; };
-enum { GP_RUNNING = 0, GP_DONE = 1, GP_LOST = 2 };
+struct GpFrontState { i64 j; int e; int status; u32 npieces; u32 nfront; u32 rounds; int lost_e; u32 steps; u32 spliced; };     // rounds: front launches that did something
+enum { GP_RUNNING = 0, GP_DONE = 1, GP_LOST = 2, GP_FULL = 3 };
+static const int GP_LOST_STREAK = 3;            // chunk remainders without any usable candidate before the front asks for a scan of the rest
+
+__device__ __forceinline__ unsigned long long gp_now_ns() {
+#if defined(__CUDA_ARCH__)
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+#else
+    return 0ull;
+#endif
+}
+// development aid (SCCG_GP_TRACE=1): trace[0] = entries used, then (kind, begin ns, end ns, info) per front / scan launch
+static const int GP_TRACE_MAX = 120;
+__device__ __forceinline__ void gp_trace(unsigned long long* trace, unsigned long long kind, unsigned long long t0, unsigned long long info) {
+    if (!trace) return;
+    const unsigned long long i = atomicAdd(trace, 1ull);
+    if (i < (unsigned long long)GP_TRACE_MAX) { trace[1 + 4 * i] = kind; trace[2 + 4 * i] = t0; trace[3 + 4 * i] = gp_now_ns(); trace[4 + 4 * i] = info; }
+}
 
 struct GpFrontArgs {
     GpSpecArgs s;
     GpFrontState* st;
     GpPiece* pieces; u32 cap_pieces;
     int* f_tpos; int* f_p; int* f_l;       // the front's own matches
+    unsigned long long* d_hit;             // result of gp_lost_scan_k for the state the previous launch got lost in (the front resets it when it gets lost)
+    unsigned long long* trace;             // development aid, usually NULL
 };
 
 __global__ void __launch_bounds__(GP_T) gp_front_k(GpFrontArgs f) {
@@ -518,24 +594,50 @@ __global__ void __launch_bounds__(GP_T) gp_front_k(GpFrontArgs f) {
     const i64 last_j = a.nt - a.k;
     i64 j = f.st->j;
     int e = f.st->e;
+    // launches are queued ahead of the host's knowledge of the state: a front after the end of the parse returns at once
+    // (uniform: every thread reads the same word, nobody has written yet)
+    const int status_in = f.st->status;
+    if (status_in == GP_DONE || status_in == GP_FULL) return;
+    const unsigned long long t_begin = f.trace ? gp_now_ns() : 0ull;
     u32 npieces = f.st->npieces, nfront = f.st->nfront, steps = f.st->steps, spliced = f.st->spliced;
+    const u32 rounds = f.st->rounds + 1u;
     int lost_streak = 0;
     int status = GP_RUNNING;
+    const bool was_lost = status_in == GP_LOST;                // chance-hit regime: declare "lost" again quickly
+    if (was_lost) {
+        // the previous launch ended "lost" in state (j, e) and gp_lost_scan_k searched the rest of the target for the next
+        // position whose k-mer occurs in the window of e: everything before it is a literal step (:83-96), state unchanged
+        const unsigned long long hit = *f.d_hit;
+        j = hit == ~0ull ? last_j + 1 : (i64)hit;
+    }
     __syncthreads();
+    const GpChunkInfo* inf = f.s.info;
     while (true) {
         if (j > last_j) { status = GP_DONE; break; }
         const u32 c = (u32)(j / f.s.chunk);
+        // The chunk the front stands in may still be in the making (second batch, other stream): while the parse is
+        // synchronised it is worth waiting for -- its CTA is running or about to -- unless speculation has been cancelled.
+        if (tid == 0 && lost_streak == 0) {
+            while (__ldcg(&inf[c].valid) == GP_CHUNK_PENDING && *reinterpret_cast<volatile u32*>(f.s.ctl + GP_CTL_CANCEL) == 0u) __nanosleep(200);
+        }
+        __syncthreads();
         // ---- bulk splice: thread t checks chunk c + t; a run of chunks whose entry state equals the exit state of its
         //      predecessor (the first one: the true state) is accepted in one go
         bool took = false;
-        for (int slot = 0; slot < 2 && !took; ++slot) {
-            const GpChunkInfo* inf = f.s.info + (size_t)slot * f.s.nchunks;
+        {
             const u32 cc = c + (u32)tid;
             bool ok = false;
-            if (cc < f.s.nchunks && inf[cc].valid) {
-                if (tid == 0) ok = inf[cc].entry_j == j && inf[cc].entry_e == e;
-                else ok = inf[cc - 1].valid && inf[cc].entry_j == inf[cc - 1].exit_j && inf[cc].entry_e == inf[cc - 1].exit_e &&
-                          (u32)(inf[cc - 1].exit_j / f.s.chunk) == cc;
+            u32 my_count = 0;
+            if (cc < f.s.nchunks) {
+                const GpChunkInfo ci = ld_info(inf + cc);
+                if (ci.valid == GP_CHUNK_OK) {
+                    my_count = ci.count;
+                    if (tid == 0) ok = ci.entry_j == j && ci.entry_e == e;
+                    else {
+                        const GpChunkInfo pv = ld_info(inf + cc - 1);
+                        ok = pv.valid == GP_CHUNK_OK && ci.entry_j == pv.exit_j && ci.entry_e == pv.exit_e && (u32)(pv.exit_j / f.s.chunk) == cc;
+                    }
+                }
             }
             if (tid == 0) S.i_scratch[5] = GP_T;
             __syncthreads();
@@ -544,10 +646,11 @@ __global__ void __launch_bounds__(GP_T) gp_front_k(GpFrontArgs f) {
             const int run = S.i_scratch[5];                        // chunks c .. c + run - 1 splice
             __syncthreads();
             if (run > 0) {
-                if (npieces + (u32)run + 2 >= f.cap_pieces) break;
-                if (tid < run) { GpPiece pc; pc.src = (u32)slot * f.s.nchunks + cc; pc.first = 0; pc.count = inf[cc].count; f.pieces[npieces + tid] = pc; }
+                if (npieces + (u32)run + 2 >= f.cap_pieces) { status = GP_FULL; break; }
+                if (tid < run) { GpPiece pc; pc.src = cc; pc.first = 0; pc.count = my_count; f.pieces[npieces + tid] = pc; }
                 npieces += (u32)run;
-                j = inf[c + run - 1].exit_j; e = inf[c + run - 1].exit_e;
+                const GpChunkInfo lastc = ld_info(inf + c + run - 1);
+                j = lastc.exit_j; e = lastc.exit_e;
                 took = true; spliced += (u32)run;
                 lost_streak = 0;
                 __syncthreads();
@@ -555,35 +658,40 @@ __global__ void __launch_bounds__(GP_T) gp_front_k(GpFrontArgs f) {
         }
         if (took) continue;
         // ---- splice into the middle of a speculative run: does chunk c pass through the true state (j, e) after one of its matches?
-        for (int slot = 0; slot < 2 && !took; ++slot) {
-            const GpChunkInfo ci = f.s.info[(size_t)slot * f.s.nchunks + c];
-            if (!ci.valid) continue;
-            const size_t base = ((size_t)slot * f.s.nchunks + c) * f.s.cap_c;
-            int first = -1;
-            if (ci.count) {
-                // the state after match i is (tpos + l, p + l - 1); tpos + l is increasing: binary search
-                int lo = 0, hi = (int)ci.count;
-                while (lo < hi) { int mid = (lo + hi) >> 1; if ((i64)f.s.c_tpos[base + mid] + f.s.c_l[base + mid] < j) lo = mid + 1; else hi = mid; }
-                if (lo < (int)ci.count && (i64)f.s.c_tpos[base + lo] + f.s.c_l[base + lo] == j && f.s.c_p[base + lo] + f.s.c_l[base + lo] - 1 == e)
-                    first = lo + 1;
-            }
-            if (first >= 0) {
-                if ((u32)first < ci.count) {
-                    if (tid == 0) { GpPiece pc; pc.src = (u32)slot * f.s.nchunks + c; pc.first = (u32)first; pc.count = ci.count - (u32)first; f.pieces[npieces] = pc; }
-                    ++npieces;
+        {
+            const GpChunkInfo ci = ld_info(inf + c);
+            if (ci.valid == GP_CHUNK_OK) {
+                const size_t base = (size_t)c * f.s.cap_c;
+                int first = -1;
+                if (ci.count) {
+                    // the state after match i is (tpos + l, p + l - 1); tpos + l is increasing: binary search
+                    int lo = 0, hi = (int)ci.count;
+                    while (lo < hi) { int mid = (lo + hi) >> 1; if ((i64)__ldcg(f.s.c_tpos + base + mid) + __ldcg(f.s.c_l + base + mid) < j) lo = mid + 1; else hi = mid; }
+                    if (lo < (int)ci.count) {
+                        const int tp = __ldcg(f.s.c_tpos + base + lo), ll = __ldcg(f.s.c_l + base + lo), pp = __ldcg(f.s.c_p + base + lo);
+                        if ((i64)tp + ll == j && pp + ll - 1 == e) first = lo + 1;
+                    }
                 }
-                j = ci.exit_j; e = ci.exit_e;
-                took = true; ++spliced;
-                lost_streak = 0;
+                if (first >= 0) {
+                    if ((u32)first < ci.count) {
+                        if (tid == 0) { GpPiece pc; pc.src = c; pc.first = (u32)first; pc.count = ci.count - (u32)first; f.pieces[npieces] = pc; }
+                        ++npieces;
+                    }
+                    j = ci.exit_j; e = ci.exit_e;
+                    took = true; ++spliced;
+                    lost_streak = 0;
+                }
             }
         }
-        if (took) { if (npieces + 2 >= f.cap_pieces) { status = GP_LOST; break; } continue; }
+        if (took) { if (npieces + 2 >= f.cap_pieces) { status = GP_FULL; break; } continue; }
 #ifdef SCCG_EMU_TRACE
-        if (tid == 0) { const GpChunkInfo ci = f.s.info[c]; printf("front: no splice at j=%lld e=%d chunk %u: valid=%d entry=(%lld,%d) exit=(%lld,%d) count=%u\n", (long long)j, e, c, ci.valid, (long long)ci.entry_j, ci.entry_e, (long long)ci.exit_j, ci.exit_e, ci.count); }
+        if (tid == 0) { const GpChunkInfo ci = ld_info(inf + c); const GpChunkInfo cn = c + 1 < f.s.nchunks ? ld_info(inf + c + 1) : ci;
+            printf("front: no splice at j=%lld e=%d chunk %u: valid=%d entry=(%lld,%d) exit=(%lld,%d) count=%u | next entry=(%lld,%d) valid=%d\n", (long long)j, e, c, ci.valid, (long long)ci.entry_j, ci.entry_e, (long long)ci.exit_j, ci.exit_e, ci.count, (long long)cn.entry_j, cn.entry_e, cn.valid); }
 #endif
         // ---- exact step of the sequential parse, at most to the end of this chunk
         int sel_p = 0, sel_l = 0;
         i64 scan_end = (i64)(c + 1) * f.s.chunk;
+        if (was_lost && scan_end > j + GP_T) scan_end = j + GP_T;    // after a chance hit: look one round ahead, then hand the search back to the scan kernel
         if (scan_end > last_j + 1) scan_end = last_j + 1;
         const i64 j_before = j;
         ++steps;
@@ -604,22 +712,77 @@ __global__ void __launch_bounds__(GP_T) gp_front_k(GpFrontArgs f) {
             e = sel_p + sel_l - 1;
             j += sel_l;
             lost_streak = 0;
-        } else if (e != -1 && j - j_before >= f.s.chunk / 2) {
-            // a long stretch without any usable candidate: the parse is "lost" with this e; let the host re-speculate
-            // the following chunks under that assumption (slot 1) unless they already are
-            if (++lost_streak >= 2) {
-                const u32 nc = (u32)(j / f.s.chunk);
-                bool have = nc < f.s.nchunks && f.s.info[(size_t)f.s.nchunks + nc].valid && f.s.info[(size_t)f.s.nchunks + nc].entry_e == e &&
-                            f.s.info[(size_t)f.s.nchunks + nc].entry_j == j;
-                if (!have && nc < f.s.nchunks) { status = GP_LOST; break; }
+        } else if (e != -1) {
+            // no usable candidate up to the end of the chunk.  A few chunks are walked exactly (an insertion of a few kb in the
+            // target); then the parse counts as "lost" with this e and the rest of the target is searched by many CTAs at once
+            (void)j_before;
+            if (++lost_streak >= (was_lost ? 1 : GP_LOST_STREAK) && j <= last_j) {
+                if (tid == 0) *reinterpret_cast<volatile u32*>(f.s.ctl + GP_CTL_CANCEL) = 1u;     // whatever is still being speculated is useless now
+                status = GP_LOST; break;
             }
         }
-        if (npieces + 2 >= f.cap_pieces) { status = GP_LOST; break; }
+        if (npieces + 2 >= f.cap_pieces) { status = GP_FULL; break; }
     }
     if (tid == 0) {
         f.st->j = j; f.st->e = e; f.st->status = status; f.st->npieces = npieces; f.st->nfront = nfront; f.st->steps = steps; f.st->spliced = spliced;
-        f.st->lost_from_chunk = (u32)(j / f.s.chunk); f.st->lost_e = e;
+        f.st->rounds = rounds; f.st->lost_e = e;
+        if (status == GP_LOST) *f.d_hit = ~0ull;                   // gp_lost_scan_k (next in the stream) lowers it to the first hit
+        gp_trace(f.trace, 1ull, t_begin, ((unsigned long long)steps << 32) | (unsigned long long)(u32)status);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// "Lost" scan.  From a state (j0, e) without a usable candidate nearby the next event of the parse is the first position
+// j >= j0 whose k-mer occurs in the window R'[e-m .. e+m+k) (:83-96: every position before it is a literal step and the
+// state does not change).  On a divergent pair that position is a chance hit a million symbols ahead, so instead of one CTA
+// walking there, many CTAs search the rest of the target in interleaved tiles, nearest tiles first; the smallest hit wins
+// (atomicMin) and tiles beyond it are not looked at.  The front resumes exactly there.
+// ------------------------------------------------------------------------------------------------
+struct GpScanArgs { GpArgs a; const GpFrontState* st; unsigned long long* d_hit; unsigned long long* trace; };
+static const int GP_SCAN_ROUNDS = 16;
+static const int GP_SCAN_TILE = GP_T * GP_SCAN_ROUNDS;
+
+__global__ void __launch_bounds__(GP_T) gp_lost_scan_k(GpScanArgs s) {
+    __shared__ GpShared S;
+    const GpArgs& a = s.a;
+    const int tid = (int)threadIdx.x, k = a.k;
+    if (s.st->status != GP_LOST) return;                      // queued behind a front that did not get lost
+    const unsigned long long t_begin = s.trace ? gp_now_ns() : 0ull;
+    const i64 j0 = s.st->j, last_j = a.nt - k;
+    const int e = s.st->e;
+    i64 wlo = (i64)e - a.m; if (wlo < 0) wlo = 0;
+    i64 whi = (i64)e + a.m; if (whi > a.nr - k) whi = a.nr - k;
+    if (whi < wlo) return;                                   // no reference k-mer can be in range: literals to the end
+    const int wlen = (int)(whi - wlo + 1), wbytes = wlen + k - 1;
+    for (int x = tid; x < GP_FILTER; x += GP_T) S.f_hash[x] = 0u;
+    for (int x = tid; x < GP_WIN_BYTES; x += GP_T) S.win[x] = x < wbytes ? a.R[wlo + x] : (u8)0;
+    __syncthreads();
+    for (int x = tid; x < wlen; x += GP_T) {
+        u32 h = kmer_hash_words(ld_unaligned64(S.win + x), ld_unaligned64(S.win + x + 8), k) | 1u;
+        u32 slot = (h >> 1) & (GP_FILTER - 1);
+        while (atomicCAS(&S.f_hash[slot], 0u, h) != 0u) slot = (slot + 1) & (GP_FILTER - 1);
+        S.f_off[slot] = (u8)x;
+    }
+    __syncthreads();
+    for (i64 tile = blockIdx.x;; tile += gridDim.x) {
+        const i64 t0 = j0 + tile * GP_SCAN_TILE;
+        if (t0 > last_j || (unsigned long long)t0 >= *reinterpret_cast<volatile unsigned long long*>(s.d_hit)) break;
+#pragma unroll 4
+        for (int r = 0; r < GP_SCAN_ROUNDS; ++r) {
+            const i64 pos = t0 + (i64)r * GP_T + tid;
+            if (pos > last_j) break;
+            const u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
+            const u32 h = kmer_hash_words(w0, w1, k) | 1u;
+            u32 slot = (h >> 1) & (GP_FILTER - 1);
+            for (u32 fh; (fh = S.f_hash[slot]) != 0u; slot = (slot + 1) & (GP_FILTER - 1)) {
+                if (fh == h) {
+                    const u8* wp = S.win + S.f_off[slot];
+                    if (kmer_equal_words(ld_unaligned64(wp), ld_unaligned64(wp + 8), w0, w1, k)) { atomicMin(s.d_hit, (unsigned long long)pos); break; }
+                }
+            }
+        }
+    }
+    if (s.trace && blockIdx.x == 0 && tid == 0) gp_trace(s.trace, 2ull, t_begin, (unsigned long long)j0);
 }
 
 // final match list = concatenation of the pieces
@@ -730,7 +893,7 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
     SCCG_TRY(buf(c, B_GTMP2, cap_all * 3 + 1, &fbuf));
     SCCG_TRY(buf(c, B_GREC, cap_all * 3 + 1, &obuf));
     SCCG_TRY(buf(c, B_GTMP3, (size_t)cap_pieces + 1, &pieces));
-    SCCG_TRY(buf(c, B_GOFFS, 4, &st));
+    SCCG_TRY(buf(c, B_GOFFS, 16, &st));                     // + the scan result 256 bytes behind the state
     SCCG_CK(cudaMemsetAsync(info, 0, sizeof(GpChunkInfo) * 2 * nchunks, c->stream));
     GpFrontState h_st; memset(&h_st, 0, sizeof h_st);
     h_st.j = 0; h_st.e = -1; h_st.status = GP_RUNNING;
@@ -741,28 +904,61 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
     f.s.info = info; f.s.c_tpos = cbuf; f.s.c_p = cbuf + (size_t)2 * nchunks * cap_c; f.s.c_l = cbuf + (size_t)4 * nchunks * cap_c;
     f.s.nchunks = nchunks; f.s.cap_c = cap_c; f.s.chunk = chunk; f.s.slot = 0; f.s.first_chunk = 0; f.s.lost_e = 0;
     f.st = st; f.pieces = pieces; f.cap_pieces = cap_pieces; f.f_tpos = fbuf; f.f_p = fbuf + cap_all; f.f_l = fbuf + 2 * cap_all;
-    LAUNCH(c, gp_spec_k, dim3(nchunks), dim3(GP_T), 0, f.s);                             // slot 0: chunk 0 exact, diagonal guesses for the others
-    for (int round = 0;; ++round) {
-        c->prof.spec_rounds = round + 1;
-        LAUNCH(c, gp_front_k, dim3(1), dim3(GP_T), 0, f);
+    unsigned long long* d_hit = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(st) + 256);
+    u32* ctl = reinterpret_cast<u32*>(reinterpret_cast<char*>(st) + 384);
+    SCCG_CK(cudaMemsetAsync(ctl, 0, 2 * sizeof(u32), c->stream));
+    f.d_hit = d_hit; f.s.ctl = ctl;
+    // Speculation in two batches: a small one on this stream, the rest on the side stream UNDERNEATH the front, which follows the
+    // chunks as they are published (per-chunk ready flags).  A synchronised parse (the usual pair) splices through at the pace
+    // of the speculation; a parse that gets lost (divergent pair) cancels what has not started yet: those chunks return at once.
+    // (The second batch is enqueued before the front: tools that serialise kernels run it first and the front never waits.)
+    u32 batch0 = (u32)c->sm_count * 2u;
+    if (const char* env = getenv("SCCG_GP_BATCH0")) { int v = atoi(env); if (v >= 1) batch0 = (u32)v; }              // tests
+    if (batch0 > nchunks) batch0 = nchunks;
+    LAUNCH(c, gp_spec_k, dim3(batch0), dim3(GP_T), 0, f.s);                              // slot 0: chunk 0 exact, diagonal guesses for the others
+    bool side_busy = false;
+    if (nchunks > batch0) {
+        SCCG_CK(cudaEventRecord(c->ev_side[0], c->stream));
+        SCCG_CK(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+        GpSpecArgs rest = f.s; rest.first_chunk = batch0;
+        SideLane side(c);
+        LAUNCH(c, gp_spec_k, dim3(nchunks - batch0), dim3(GP_T), 0, rest);
+        SCCG_CK(cudaEventRecord(c->ev_side[1], c->stream));
+        side_busy = true;
+    }
+    // The host does not sit between the rounds: a group of [front, scan] pairs is queued at once and every kernel decides from the
+    // state in device memory whether it has anything to do (front: not after the end; scan: only behind a front that got lost).
+    int chain = 4;
+    if (const char* env = getenv("SCCG_GP_CHAIN")) { int v = atoi(env); if (v >= 1 && v <= 64) chain = v; }              // tests
+    unsigned scan_grid = (unsigned)c->sm_count * 4u;
+    if (const char* env = getenv("SCCG_GP_SCAN_GRID")) { int v = atoi(env); if (v >= 1) scan_grid = (unsigned)v; }       // tests: tiny grids
+    unsigned long long* d_trace = nullptr;
+    const bool tracing = getenv("SCCG_GP_TRACE") != nullptr;
+    if (tracing) { SCCG_TRY(buf(c, B_GHIST, (size_t)(2 * (1 + 4 * GP_TRACE_MAX)), (u32**)&d_trace)); SCCG_CK(cudaMemsetAsync(d_trace, 0, 8 * (1 + 4 * GP_TRACE_MAX), c->stream)); }
+    f.trace = d_trace;
+    GpScanArgs sa; sa.a = f.s.a; sa.st = st; sa.d_hit = d_hit; sa.trace = d_trace;
+    for (int group = 0;; ++group) {
+        for (int r = 0; r < (group == 0 ? 1 : chain); ++r) {         // the usual pair is done after the first front
+            LAUNCH(c, gp_front_k, dim3(1), dim3(GP_T), 0, f);
+            LAUNCH(c, gp_lost_scan_k, dim3(scan_grid), dim3(GP_T), 0, sa);
+        }
         SCCG_CK(cudaMemcpyAsync(c->h_pinned, st, sizeof h_st, cudaMemcpyDeviceToHost, c->stream));
         SCCG_CK(cudaStreamSynchronize(c->stream));
         memcpy(&h_st, c->h_pinned, sizeof h_st);
+        c->prof.spec_rounds = (int32_t)h_st.rounds;
         if (h_st.status == GP_DONE) break;
-        if (h_st.npieces + 2 >= cap_pieces) return set_error(SCCG_E_NOMEM, "internal: piece list overflow in the global parse");
-        if (h_st.status != GP_LOST || round > 1000000) return set_error(SCCG_E_CUDA, "internal: global parse did not terminate");
-        // lost with e = lost_e: speculate the remaining chunks under that assumption (slot 1)
-        GpSpecArgs ls = f.s;
-        ls.slot = 1; ls.first_chunk = h_st.lost_from_chunk; ls.lost_e = h_st.lost_e;
-        // ... but only for a window of chunks: the state changes again at the next re-synchronisation, and a stale window
-        // entry is harmless (the front accepts a chunk only if its entry state is the true state)
-        if (ls.first_chunk < nchunks) {
-            u32 window = (u32)c->sm_count * 2u;
-            if (const char* env = getenv("SCCG_GP_WINDOW")) { int v = atoi(env); if (v >= 1) window = (u32)v; }
-            const u32 todo = nchunks - ls.first_chunk;
-            LAUNCH(c, gp_spec_k, dim3(todo < window ? todo : window), dim3(GP_T), 0, ls);
-        }
+        if (h_st.status == GP_FULL || h_st.npieces + 2 >= cap_pieces) return set_error(SCCG_E_NOMEM, "internal: piece list overflow in the global parse");
+        if (h_st.status != GP_LOST || group > 1000000) return set_error(SCCG_E_CUDA, "internal: global parse did not terminate");
     }
+    if (tracing) {
+        static unsigned long long h_tr[1 + 4 * GP_TRACE_MAX];
+        cudaMemcpy(h_tr, d_trace, sizeof h_tr, cudaMemcpyDeviceToHost);
+        const unsigned long long n = h_tr[0] < (unsigned long long)GP_TRACE_MAX ? h_tr[0] : GP_TRACE_MAX;
+        for (unsigned long long i = 0; i < n; ++i)
+            fprintf(stderr, "gp_trace %s begin %+9.1f us  dur %8.1f us  info %llx\n", h_tr[1 + 4 * i] == 1 ? "front" : "scan ", (double)(long long)(h_tr[2 + 4 * i] - h_tr[2]) / 1e3,
+                    (double)(h_tr[3 + 4 * i] - h_tr[2 + 4 * i]) / 1e3, h_tr[4 + 4 * i]);
+    }
+    if (side_busy) SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));               // (cancelled or not, the second batch must be off the buffers)
     // ---- concatenate the accepted pieces
     const u32 np = h_st.npieces;
     SCCG_TRY(buf(c, B_GTMP0, (size_t)np + 1, &pcounts));

@@ -472,17 +472,22 @@ __device__ unsigned long long g_seg_stats[8];      // 0 identical, 1 diagonal ac
 #define SEG_STAT(i) do { } while (0)
 #endif
 
-// raw (not yet upper-cased) 8-byte words of segment `seg`: lane holds words lane, lane+32, lane+64, lane+96
-__device__ __forceinline__ void lm_fetch(const u8* __restrict__ ref, i64 nr, const u8* __restrict__ tgt, i64 nt, int seg, int n_iter, int lane,
-                                         u64 (&rw)[4], u64 (&tw)[4]) {
-    const i64 off = (i64)seg * SEG;
-    const int Lr = seg < n_iter ? (int)((nr - off) < SEG ? (nr - off) : SEG) : 0;
-    const int Lt = seg < n_iter ? (int)((nt - off) < SEG ? (nt - off) : SEG) : 0;
+// raw (not yet upper-cased) 8-byte words of the segment pair at symbol offset off: lane holds words lane, lane+32, lane+64, lane+96
+__device__ __forceinline__ void lm_fetch(const u8* __restrict__ ref, const u8* __restrict__ tgt, i64 off, int Lr, int Lt, int lane, u64 (&rw)[4], u64 (&tw)[4]) {
+    const u64* pr = reinterpret_cast<const u64*>(ref + off) + lane;
+    const u64* pt = reinterpret_cast<const u64*>(tgt + off) + lane;
+    if (Lr == SEG && Lt == SEG) {                              // uniform; 1000 symbols = 125 words: no per-word guards
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        int b0 = 8 * (lane + 32 * it);
-        rw[it] = b0 < Lr ? __ldg(reinterpret_cast<const u64*>(ref + off + b0)) : 0ull;
-        tw[it] = b0 < Lt ? __ldg(reinterpret_cast<const u64*>(tgt + off + b0)) : 0ull;
+        for (int it = 0; it < 3; ++it) { rw[it] = __ldg(pr + 32 * it); tw[it] = __ldg(pt + 32 * it); }
+        rw[3] = 0ull; tw[3] = 0ull;
+        if (lane < SEG / 8 - 96) { rw[3] = __ldg(pr + 96); tw[3] = __ldg(pt + 96); }
+    } else {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int b0 = 8 * (lane + 32 * it);
+            rw[it] = b0 < Lr ? __ldg(pr + 32 * it) : 0ull;
+            tw[it] = b0 < Lt ? __ldg(pt + 32 * it) : 0ull;
+        }
     }
 }
 
@@ -529,30 +534,36 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
     bool tab_clean = false;                                   // S.head + S.next all zero (kept by the diagonal-hypothesis path)
     int seg = seg_begin + warp_global * claim < n_iter ? seg_begin + warp_global * claim : n_iter;
     while (seg < n_iter) {
-        lm_fetch(ref, nr, tgt, nt, seg, n_iter, lane, nrw, ntw);
         const i64 off = (i64)seg * SEG;
         const int Lr = (int)((nr - off) < SEG ? (nr - off) : SEG);
         const int Lt = (int)((nt - off) < SEG ? (nt - off) : SEG);
         const int Lmin = Lr < Lt ? Lr : Lt;
+        lm_fetch(ref, tgt, off, Lr, Lt, lane, nrw, ntw);
         __syncwarp();                                        // previous segment fully consumed
 #ifdef SCCG_SEG_TIMING
         const long long t_begin = clock64();
 #endif
         u32 wm[4];                                           // diagonal-0 mismatch flags per 8-byte word (uniform)
-        const int wv = Lmin >> 3, rem = Lmin & 7;
-        const bool full_pair = Lr == SEG && Lt == SEG;        // words past the end were fetched as 0 on both sides: no masking needed
         // upper-case in place (:369-370) and compare on the diagonal, all in registers: an identical pair never touches shared memory
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-            int q = lane + 32 * it;
             u64 rw = nrw[it], tw = ntw[it];
             if (rw & 0x2020202020202020ULL) rw = upper8(rw);                 // only bytes with bit 5 can be a-z
             if (tw & 0x2020202020202020ULL) tw = upper8(tw);
             nrw[it] = rw; ntw[it] = tw;
-            u64 diff = rw ^ tw;
-            bool d = diff != 0ull;
-            if (!full_pair) d = q < wv ? d : (q == wv && rem ? (diff & (~0ull >> (64 - 8 * rem))) != 0ull : false);
-            wm[it] = __ballot_sync(SCCG_FULL_MASK, d);
+            wm[it] = __ballot_sync(SCCG_FULL_MASK, rw != tw);
+        }
+        if (Lr != SEG || Lt != SEG) {
+            // a shorter (last) pair: only the first Lmin symbols are on the diagonal (full pairs: the words past the end were
+            // fetched as 0 on both sides, nothing to mask)
+            const int wv = Lmin >> 3, rem = Lmin & 7;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int q = lane + 32 * it;
+                const u64 diff = nrw[it] ^ ntw[it];
+                const bool d = q < wv ? diff != 0ull : (q == wv && rem ? (diff & (~0ull >> (64 - 8 * rem))) != 0ull : false);
+                wm[it] = __ballot_sync(SCCG_FULL_MASK, d);
+            }
         }
         // claim the next segment: SCCG_LM_CLAIM consecutive segments per atomic (one hot L2 address for the whole grid)
         int next_seg = seg + 1;
@@ -571,10 +582,10 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
             if (__shfl_sync(SCCG_FULL_MASK, stop, 0)) next_seg = n_iter;
         }
 #endif
-        if (next_seg < n_iter && lane < 16) {                 // pull the next segment into L2 only: no registers held across the parse
+        if (next_seg + 1 < n_iter && lane < 16) {             // pull the next segment (a full pair: not the last one) into L2 only: no registers held across the parse
             const u8* pf = (lane < 8 ? ref : tgt) + (i64)next_seg * SEG + 128 * (lane & 7);
 #ifndef SCCG_EMU
-            if ((i64)next_seg * SEG + 128 * (lane & 7) < (lane < 8 ? nr : nt)) asm volatile("prefetch.global.L2 [%0];" :: "l"(pf));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(pf));
 #else
             (void)pf;
 #endif

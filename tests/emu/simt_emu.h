@@ -113,6 +113,7 @@ inline int __syncthreads_or(int pred) { return emu::block_barrier_count(pred) !=
 inline int __syncthreads_and(int pred) { return emu::block_barrier_count(!pred) == 0; }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::Slot* s = emu::collective_arrive(mask, 0); emu::collective_release(s); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __nanosleep(unsigned) {}
 inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 template <typename T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {

@@ -304,6 +304,42 @@ def test_global_speculative_parse_small_chunks(ctx, seed, chunk):
         os.environ.pop("SCCG_GP_CHUNK", None)
 
 
+def lost_scan_pair(seed, junk=40_000):
+    """a pair whose global parse gets LOST (a long unrelated stretch) and is picked up again by planted hits: k-mers of the
+    window around the last match end that reappear far ahead -- in range (resumes the parse there) or followed by more of
+    the same diagonal (a real continuation)"""
+    r = random.Random(repr(("lost", seed)))
+    ref = rnd(30_000, ("lostref", seed))
+    a_len = r.randint(2_000, 6_000)
+    tgt = bytearray(ref[:a_len])                                # parse ends this block with e = a_len - 1
+    j = bytearray(rnd(junk, ("lostjunk", seed)))
+    for _ in range(r.randint(1, 4)):                            # chance-like hits: a k-mer from the window of e, somewhere in the junk
+        w = a_len - 1 + r.randint(-100, 100)
+        at = r.randrange(0, junk - 200)
+        ln = r.choice([14, 14, 15, 40])
+        j[at:at + ln] = ref[w:w + ln]
+    tgt += j
+    if seed % 2:
+        tgt += ref[a_len + r.randint(-50, 50):a_len + 9_000]    # the true continuation, in range of e after all that junk
+    tgt += rnd(r.randint(0, 3000), ("losttail", seed))
+    return ref, bytes(tgt)
+
+
+@pytest.mark.parametrize("grid", [1, 3, 0])
+@pytest.mark.parametrize("seed", range(6))
+def test_global_lost_scan(ctx, seed, grid, monkeypatch):
+    """the front gets lost, gp_lost_scan_k finds the next position with a candidate in the window of e (tiles interleaved
+    over 1 / 3 / the default number of CTAs), the front resumes there: identical to the sequential parse"""
+    monkeypatch.setenv("SCCG_GP_CHUNK", "2048")
+    if grid:
+        monkeypatch.setenv("SCCG_GP_SCAN_GRID", str(grid))
+    ref, tgt = lost_scan_pair(seed)
+    exp = [(x.p, x.l, x.lit) for x in ol.orc_match_sequences(ref, tgt, 14, 100, True, 0)]
+    got = [(x.p, x.l, x.lit) for x in ctx.match_sequences(ref, tgt, 14, 100, True, 0)]
+    assert got == exp
+    assert ctx.profile()["spec_rounds"] >= 2                    # at least one lost scan happened
+
+
 def _compress_device_emu(ctx, ref: bytes, tgt: bytes, header: bytes):
     """device-resident entry point under the emulator (device memory is host memory there)"""
     import numpy as np

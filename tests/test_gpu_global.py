@@ -114,3 +114,33 @@ def test_global_index_bucket_table_widths(ctx, bits, monkeypatch):
     rc, exp, mode = ol.orc_compress(ref, tgt, b">bkt")
     got, gmode = ctx.compress(ref, tgt, b">bkt")
     assert rc == 0 and (gmode, got) == (mode, exp)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_global_lost_scan(ctx, seed, monkeypatch):
+    """lost state + gp_lost_scan_k (see test_emu_compress.lost_scan_pair), default chunk size and a long unrelated stretch"""
+    from test_emu_compress import lost_scan_pair
+    ref, tgt = lost_scan_pair(seed, junk=400_000)
+    exp = [(x.p, x.l, x.lit) for x in ol.orc_match_sequences(ref, tgt, 14, 100, True, 0)]
+    got = [(x.p, x.l, x.lit) for x in ctx.match_sequences(ref, tgt, 14, 100, True, 0)]
+    assert got == exp
+    assert ctx.profile()["spec_rounds"] >= 2
+
+
+@pytest.mark.parametrize("batch0", [1, 3, 40])
+@pytest.mark.parametrize("shape", ["gap", "divergent"])
+def test_global_two_batch_speculation(ctx, shape, batch0, monkeypatch):
+    """tiny first speculation batch: the front reaches the second batch while it is still running (GP_WAIT), or cancels it when
+    the parse gets lost early; either way the file is the oracle's"""
+    from sccg_genome_compression_b200 import synth
+    monkeypatch.setenv("SCCG_GP_BATCH0", str(batch0))
+    if shape == "gap":
+        ref, tgt = synth.global_gap_pair(3_240_000, 3_000_000, synth.seed_for(1, 13))
+    else:
+        ref, tgt = synth.divergent_pair(2_500_000, synth.seed_for(3, 13))
+    ref, tgt = ref.tobytes(), tgt.tobytes()
+    rc, exp, mode = ol.orc_compress(ref, tgt, b">two batches")
+    assert rc == 0 and mode == 1
+    for rep in range(3):                                     # timing varies from run to run: the result must not
+        got, gmode = ctx.compress(ref, tgt, b">two batches")
+        assert (gmode, got) == (mode, exp)
