@@ -36,9 +36,11 @@ def run_ranks(world, body):
         finally:
             if mg: mg.close()
             if ctx: ctx.close()
-    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    assert BACKEND["devices"] is None or world <= len(BACKEND["devices"]), "more ranks than devices"
+    th = [threading.Thread(target=worker, args=(r,), daemon=True) for r in range(world)]
     for t in th: t.start()
-    for t in th: t.join(timeout=600)
+    for t in th: t.join(timeout=300)
+    assert not any(t.is_alive() for t in th), "a rank is stuck"
     assert not errs, errs
     return out
 
@@ -140,7 +142,7 @@ def test_compress_sharded_fallbacks():
         assert not sharded and (gmode, got) == (mode, exp)
 
 
-def test_decompress_sharded_pieces():
+def test_decompress_sharded_pieces(world=3):
     ref, tgt = synth.local_pair(150_000, synth.seed_for(2, 58))
     ref, tgt = ref.tobytes(), tgt.tobytes()
     rc, inter, mode = ol.orc_compress(ref, tgt, b">parts")
@@ -153,7 +155,7 @@ def test_decompress_sharded_pieces():
     import os
     os.environ["SCCG_PIPE_CHUNK"] = "20000"
     try:
-        res = run_ranks(3, body)
+        res = run_ranks(world, body)
     finally:
         del os.environ["SCCG_PIPE_CHUNK"]
     image = bytearray(len(exp))

@@ -55,11 +55,11 @@ def test_compress_sharded(backend, world):
 
 
 def test_compress_sharded_fallbacks(backend):
-    T.test_compress_sharded_fallbacks()
+    T.test_compress_sharded_fallbacks()                     # (2 ranks)
 
 
 def test_decompress_sharded(backend):
-    T.test_decompress_sharded_pieces()
+    T.test_decompress_sharded_pieces(_world(backend, 3))
 
 
 def test_compress_sharded_chromosome_sized(backend):
