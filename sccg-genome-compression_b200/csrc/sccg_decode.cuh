@@ -15,6 +15,7 @@
 #pragma once
 #include "sccg_compress.cuh"
 #include "sccg_strip.cuh"
+#include "sccg_bulk.cuh"
 
 namespace sccg {
 
@@ -599,9 +600,24 @@ __global__ void dec_tile_win_k(GatherArgs a, unsigned ntiles, int4* __restrict__
 #endif
 static const int GATHER_CTA = SCCG_GATHER_CTA;             // threads per 4 KiB tile: fewer threads per tile = more tiles in flight per SM
 static const int GATHER_ROUNDS = GATHER_TILE / 16 / GATHER_CTA;
+// Copy-engine version of the segment copy: when source and destination have the same 16-byte phase (the image is placed so
+// that this holds for every token on diagonal 0, i.e. nearly all of a local-mode file) the aligned middle of the segment is
+// ONE cp.async.bulk issued by one lane; the lanes only move the <= 15 bytes before and after it.
+__device__ __forceinline__ void warp_copy_g2s_bulk(u8* dst, const u8* __restrict__ src, u32 n, u64* bar) {
+    const u32 lane = (u32)lane_of();
+    if (n < 64u || (((u32)(uintptr_t)src ^ smem_phase16(dst)) & 15u) != 0u) { warp_copy_g2s(dst, src, n); return; }
+    const u32 head = (16u - ((u32)(uintptr_t)src & 15u)) & 15u;
+    const u32 mid = (n - head) & ~15u, tail = n - head - mid;
+    if (lane == 0) { mbar_expect_tx(bar, mid); bulk_g2s(dst + head, src + head, mid, bar); }
+    if (lane < head) dst[lane] = src[lane];
+    if (lane >= 16u && lane - 16u < tail) dst[head + mid + (lane - 16u)] = src[head + mid + (lane - 16u)];
+}
+
 __global__ void __launch_bounds__(GATHER_CTA) dec_gather_k(GatherArgs a) {
     __shared__ int win[6];
-    __align__(16) __shared__ u8 A[GATHER_TILE + GATHER_PAD];
+    __align__(16) __shared__ u8 Araw[GATHER_TILE + GATHER_PAD + 16];     // symbols of the tile (no newlines yet)
+    __align__(16) __shared__ u8 O[GATHER_TILE];                          // the tile as it goes to memory
+    __align__(8) __shared__ u64 bar;
     const int warp = (int)(threadIdx.x >> 5);
     const unsigned tile = blockIdx.x + a.tile0;
     const i64 Q0 = (i64)tile * GATHER_TILE;
@@ -615,10 +631,15 @@ __global__ void __launch_bounds__(GATHER_CTA) dec_gather_k(GatherArgs a) {
         }
         return;
     }
+    if (threadIdx.x == 0) mbar_init(&bar, 1u);
     u32 b0, b1;
     tile_symbols(Q0, Qe, a.Lm, &b0, &b1);
     const u32 noff = (u32)tw.z;
     const u32 s0 = b0 - noff, s1 = b1 - noff;                                         // N-free coordinates of the tile's symbols
+    // the image starts at the 16-byte phase of its first symbol's coordinate: a token that copies reference symbol x to decoded
+    // symbol x (diagonal 0) then has equally aligned source and destination
+    u8* const A = Araw + (s0 & 15u);
+    __syncthreads();                                                                  // the mbarrier is initialised
     // ---- 1. copy segments -> image.  Warp w owns the segments first + w, first + w + NW, ...; their descriptors are fetched
     //      32 at a time, one per lane (one memory round trip), and handed out by shuffles
     const int lane = lane_of();
@@ -637,7 +658,7 @@ __global__ void __launch_bounds__(GATHER_CTA) dec_gather_k(GatherArgs a) {
             const u32 lo = d0 > s0 ? d0 : s0, hi = d1 < s1 ? d1 : s1;
             if (hi <= lo || src < 0) continue;                     // src < 0: SEG_BAD_PTR
             const u8* sp = (src & SEG_LIT_FLAG) ? a.enc + (src & ~SEG_LIT_FLAG) : a.ref + src;
-            warp_copy_g2s(A + (lo - s0), sp + (lo - d0), hi - lo);
+            warp_copy_g2s_bulk(A + (lo - s0), sp + (lo - d0), hi - lo, &bar);
         }
         if (done) break;
     }
@@ -645,7 +666,9 @@ __global__ void __launch_bounds__(GATHER_CTA) dec_gather_k(GatherArgs a) {
     int lkk = tw.y + warp + lane * NW;
     i64 ml0 = 0x7fffffffffffffffLL, ml1 = 0;
     if (lkk < a.l_k) { ml0 = a.l_start[lkk]; ml1 = ml0 + a.l_len[lkk]; }
-    __syncthreads();
+    __syncthreads();                                              // every copy has been issued ...
+    if (threadIdx.x == 0) mbar_arrive(&bar);
+    mbar_wait(&bar, 0u);                                          // ... and has landed
     // ---- 2. lowercase runs (merged coordinates; image offset = b - b0)
     for (int lb = tw.y + warp; lb < a.l_k; lb += 32 * NW) {
         bool done = false;
@@ -662,17 +685,20 @@ __global__ void __launch_bounds__(GATHER_CTA) dec_gather_k(GatherArgs a) {
         if (lkk < a.l_k) { ml0 = a.l_start[lkk]; ml1 = ml0 + a.l_len[lkk]; }
     }
     __syncthreads();
-    // ---- 3. format: GATHER_ROUNDS x 16 bytes of text per thread
+    // ---- 3. format: GATHER_ROUNDS x 16 bytes of text per thread, staged in O; a full tile leaves as ONE bulk store
+    const bool full_tile = Qe - Q0 == GATHER_TILE && Qe < a.total;                    // (the last tile of the text carries the final newline: direct stores)
+    const u32 aph = s0 & 15u;                                                         // phase of the image inside Araw
 #pragma unroll
     for (int half = 0; half < GATHER_ROUNDS; ++half) {
-        const i64 q0 = Q0 + ((i64)threadIdx.x + half * GATHER_CTA) * 16;
-        if (q0 >= a.total) return;
+        const u32 t16 = (u32)threadIdx.x + (u32)half * GATHER_CTA;
+        const i64 q0 = Q0 + (i64)t16 * 16;
+        if (q0 >= a.total) break;
         const u32 line0 = (u32)q0 / (u32)(WRAP + 1);
         const int col0 = (int)((u32)q0 - line0 * (u32)(WRAP + 1));
         const int c = WRAP - col0;                                   // offset of the '\n' inside this piece if < 16
-        const u32 ao = line0 * WRAP + (u32)col0 - b0;                // image offset of the first symbol of the piece
+        const u32 ao = line0 * WRAP + (u32)col0 - b0 + aph;          // offset of the first symbol of the piece inside Araw
         if (q0 + 16 <= a.total - 1) {
-            const u32* A32 = reinterpret_cast<const u32*>(A);
+            const u32* A32 = reinterpret_cast<const u32*>(Araw);
             const u32 i = ao >> 2, sh = (ao & 3u) * 8u;
             const u32 x0 = A32[i], x1 = A32[i + 1], x2 = A32[i + 2], x3 = A32[i + 3], x4 = A32[i + 4];
             u64 w0 = (u64)__funnelshift_r(x0, x1, sh) | ((u64)__funnelshift_r(x1, x2, sh) << 32);
@@ -688,16 +714,22 @@ __global__ void __launch_bounds__(GATHER_CTA) dec_gather_k(GatherArgs a) {
                 w1 = (w1 & lowmask) | ((u64)'\n' << (8 * cc)) | ((w1 & ~lowmask) << 8);
             }
             ulonglong2 v; v.x = w0; v.y = w1;
-            *reinterpret_cast<ulonglong2*>(a.out + q0) = v;
+            if (full_tile) *reinterpret_cast<ulonglong2*>(O + t16 * 16u) = v;
+            else *reinterpret_cast<ulonglong2*>(a.out + q0) = v;
         } else {
             // the piece(s) at the very end of the text: the final newline (:274) does not sit on a line border
             u32 sym = ao;
             for (int d = 0; d < 16 && q0 + d < a.total; ++d) {
                 const bool nl = (q0 + d == a.total - 1) || (col0 + d) % (WRAP + 1) == WRAP;
-                a.out[q0 + d] = nl ? (u8)'\n' : A[sym];
+                a.out[q0 + d] = nl ? (u8)'\n' : Araw[sym];
                 if (!nl) ++sym;
             }
         }
+    }
+    if (full_tile) {
+        fence_smem_to_async();
+        __syncthreads();
+        if (threadIdx.x == 0) { bulk_s2g(a.out + Q0, O, (u32)GATHER_TILE); bulk_wait_read(); }
     }
 }
 
