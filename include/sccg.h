@@ -154,6 +154,25 @@ int sccg_compress_fasta(sccg_ctx* ctx, const char* ref_file, int64_t ref_file_le
 int sccg_decompress_fasta(sccg_ctx* ctx, const char* ref_file, int64_t ref_file_len, const char* intermediate, int64_t inter_len,
                           char** out, int64_t* out_len);
 
+/* *_into variants of the FASTA entry points, and page-locked host memory for their buffers (cudaMallocHost: copies run at full
+ * PCIe speed and overlap with kernels; the batch drivers read the files straight into such buffers). */
+void* sccg_pinned_alloc(int64_t bytes);              /* NULL on failure */
+void  sccg_pinned_free(void* p);
+int sccg_compress_fasta_into(sccg_ctx* ctx, const char* ref_file, int64_t ref_file_len, const char* tgt_file, int64_t tgt_file_len,
+                             char* out, int64_t out_cap, int64_t* out_len, int* mode_out);
+int sccg_decompress_fasta_into(sccg_ctx* ctx, const char* ref_file, int64_t ref_file_len, const char* intermediate, int64_t inter_len,
+                               char* out, int64_t out_cap, int64_t* out_len);
+
+/* Streaming decompression: the reconstructed_genome.fa image (decompression.cpp:316-323) is handed to `sink` piece by piece, in
+ * order (offset = position of the piece in the image), from a page-locked double buffer owned by the context: while the sink
+ * writes piece j to the output file, piece j + 1 crosses PCIe.  A non-zero return of the sink aborts the call.  Every error of
+ * the record stream (SCCG_E_FORMAT / SCCG_E_BOUNDS) is reported BEFORE the first piece is delivered. */
+typedef int (*sccg_sink_fn)(void* user, int64_t offset, const char* data, int64_t len);
+int sccg_decompress_stream(sccg_ctx* ctx, const char* ref_raw, int64_t ref_len, const char* intermediate, int64_t inter_len,
+                           sccg_sink_fn sink, void* user, int64_t* total_len);
+int sccg_decompress_fasta_stream(sccg_ctx* ctx, const char* ref_file, int64_t ref_file_len, const char* intermediate, int64_t inter_len,
+                                 sccg_sink_fn sink, void* user, int64_t* total_len);
+
 /* One chromosome over several GPUs (the local segment-matching path, compression.cpp:381-481, sharded by segment range).
  * Shard r owns the segment pairs [seg_base, seg_base + n) and is given exactly the matching slices: ref[seg_base*1000 ..),
  * tgt[seg_base*1000 ..); the last shard's target slice runs to the end of the target.  sccg_shard_match does the matching and

@@ -82,6 +82,8 @@ def _as_char_p(buf):
     return C.cast(buf.ctypes.data, C.c_char_p) if len(buf) else b""
 
 
+SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64)       # sccg_sink_fn (include/sccg.h)
+
 _libs: dict[str, C.CDLL] = {}
 
 
@@ -123,6 +125,14 @@ def load_library(path: str | os.PathLike | None = None) -> C.CDLL:
     lib.sccg_compress_fasta.argtypes = [vp, cp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_int)]
     lib.sccg_decompress_fasta.argtypes = [vp, cp, i64, cp, i64, C.POINTER(vp), C.POINTER(i64)]
     i32p, i64p = C.POINTER(C.c_int32), C.POINTER(i64)
+    lib.sccg_pinned_alloc.restype = vp
+    lib.sccg_pinned_alloc.argtypes = [i64]
+    lib.sccg_pinned_free.argtypes = [vp]
+    lib.sccg_pinned_free.restype = None
+    lib.sccg_compress_fasta_into.argtypes = [vp, cp, i64, cp, i64, vp, i64, i64p, C.POINTER(C.c_int)]
+    lib.sccg_decompress_fasta_into.argtypes = [vp, cp, i64, cp, i64, vp, i64, i64p]
+    lib.sccg_decompress_stream.argtypes = [vp, cp, i64, cp, i64, SINK_FN, vp, i64p]
+    lib.sccg_decompress_fasta_stream.argtypes = [vp, cp, i64, cp, i64, SINK_FN, vp, i64p]
     lib.sccg_mgpu_unique_id.argtypes = [C.c_char_p]
     lib.sccg_mgpu_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
     lib.sccg_mgpu_destroy.argtypes = [vp]
@@ -428,6 +438,28 @@ class Context:
         out = C.c_void_p(); n = C.c_int64()
         self._check(self.lib.sccg_decompress_fasta(self.handle, ref_file, len(ref_file), intermediate, len(intermediate), C.byref(out), C.byref(n)))
         return self._take(out, n.value)
+
+    def compress_fasta_into(self, ref_file, tgt_file, out_ptr: int, out_cap: int) -> tuple[int, int]:
+        """FASTA file images in (ideally in page-locked memory), compressed_genome.txt image into the caller's buffer -> (length, mode)"""
+        n = C.c_int64(); mode = C.c_int()
+        self._check(self.lib.sccg_compress_fasta_into(self.handle, _as_char_p(ref_file), len(ref_file), _as_char_p(tgt_file), len(tgt_file), out_ptr, out_cap,
+                                                      C.byref(n), C.byref(mode)))
+        return n.value, mode.value
+
+    def decompress_stream(self, ref, intermediate: bytes, fasta: bool = False) -> list[tuple[int, bytes]]:
+        """streaming decompression (sccg_decompress_stream / sccg_decompress_fasta_stream) -> the pieces [(offset, bytes)] in the
+        order the sink received them; ref: raw symbols, or the reference FASTA file image with fasta=True"""
+        pieces = []
+
+        def sink(user, off, data, n):
+            pieces.append((off, C.string_at(data, n)))
+            return 0
+        cb = SINK_FN(sink)
+        total = C.c_int64()
+        fn = self.lib.sccg_decompress_fasta_stream if fasta else self.lib.sccg_decompress_stream
+        self._check(fn(self.handle, _as_char_p(ref), len(ref), intermediate, len(intermediate), cb, None, C.byref(total)))
+        assert sum(len(p) for _, p in pieces) == total.value
+        return pieces
 
     # decompress_genome (in-memory part) + reconstruct_genome + header line (decompression.cpp:66-110, :117-279, :322)
     def decompress(self, ref_raw: bytes, intermediate: bytes) -> bytes:

@@ -88,7 +88,10 @@ void sccg_destroy(sccg_ctx* c) {
     if (c->pipe_ready) {
         cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h);
         for (int i = 0; i < 2; ++i) cudaEventDestroy(c->ev_pipe[i]);
-        for (int i = 0; i < 64; ++i) { cudaEventDestroy(c->ev_h2d[i]); cudaEventDestroy(c->ev_g[i]); }
+        for (int i = 0; i < 64; ++i) { cudaEventDestroy(c->ev_h2d[i]); cudaEventDestroy(c->ev_g[i]); cudaEventDestroy(c->ev_d2h[i]); }
+    }
+    for (int i = 0; i < 2; ++i) if (c->h_stream[i]) cudaFreeHost(c->h_stream[i]);
+    {
     }
     delete c;
 }
@@ -391,28 +394,42 @@ static int upload_file(sccg_ctx* c, int slot, const char* h, int64_t n, u8** d) 
     return SCCG_OK;
 }
 
-int sccg_compress_fasta(sccg_ctx* c, const char* ref_file, int64_t ref_file_len, const char* tgt_file, int64_t tgt_file_len,
-                        char** out, int64_t* out_len, int* mode_out) {
-    if (!c || !out || !out_len || (ref_file_len > 0 && !ref_file) || (tgt_file_len > 0 && !tgt_file)) return set_error(SCCG_E_ARG, "null argument");
+// the two file images travel on the copy stream -- target first -- while the compute stream already strips the target; with
+// page-locked sources (sccg_pinned_alloc) the copies run at full PCIe speed and asynchronously
+static int compress_fasta_impl(sccg_ctx* c, const char* ref_file, int64_t ref_file_len, const char* tgt_file, int64_t tgt_file_len,
+                               char* dst, int64_t dst_cap, char** out, int64_t* out_len, int* mode_out) {
+    if (!c || !out_len || (ref_file_len > 0 && !ref_file) || (tgt_file_len > 0 && !tgt_file)) return set_error(SCCG_E_ARG, "null argument");
     SCCG_TRY(check_sizes(ref_file_len, tgt_file_len));
     SCCG_CK(cudaSetDevice(c->device));
     prof_reset(c);
+    SCCG_TRY(pipe_streams(c));
     u8 *d_rf = nullptr, *d_tf = nullptr;
     u32* sc = nullptr;
     SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
+    SCCG_TRY(buf(c, B_FILE_R, (size_t)(ref_file_len > 0 ? ref_file_len : 1) + 128, &d_rf));
+    SCCG_TRY(buf(c, B_FILE_T, (size_t)(tgt_file_len > 0 ? tgt_file_len : 1) + 128, &d_tf));
     SCCG_CK(cudaEventRecord(c->ev[4], c->stream));
-    SCCG_TRY(upload_file(c, B_FILE_R, ref_file, ref_file_len, &d_rf));
-    SCCG_TRY(upload_file(c, B_FILE_T, tgt_file, tgt_file_len, &d_tf));
-    SCCG_CK(cudaEventRecord(c->ev[5], c->stream));
+    SCCG_CK(cudaStreamWaitEvent(c->s_h2d, c->ev[4], 0));                      // (the buffers may just have been reallocated)
+    if (tgt_file_len > 0) SCCG_CK(cudaMemcpyAsync(d_tf, tgt_file, (size_t)tgt_file_len, cudaMemcpyHostToDevice, c->s_h2d));
+    SCCG_CK(cudaMemsetAsync(d_tf + (tgt_file_len > 0 ? tgt_file_len : 0), 0, 64, c->s_h2d));
+    SCCG_CK(cudaEventRecord(c->ev_pipe[1], c->s_h2d));
+    if (ref_file_len > 0) SCCG_CK(cudaMemcpyAsync(d_rf, ref_file, (size_t)ref_file_len, cudaMemcpyHostToDevice, c->s_h2d));
+    SCCG_CK(cudaMemsetAsync(d_rf + (ref_file_len > 0 ? ref_file_len : 0), 0, 64, c->s_h2d));
+    SCCG_CK(cudaEventRecord(c->ev[5], c->s_h2d));
     FastaSeq R, T;
-    SCCG_TRY(fasta_ingest(c, d_rf, ref_file_len, false, B_REF, B_FA_TMP, B_FA_RNG, sc + S_G7, &R));      // compression.cpp:193-200
-    SCCG_TRY(fasta_ingest(c, d_tf, tgt_file_len, true, B_TGT, B_FA_TMP, B_FA_RNG, sc + S_G7, &T));       // :207-219
-    const char* header = T.hdr_start >= 0 ? tgt_file + T.hdr_start : "";
-    const int64_t nh = T.hdr_start >= 0 ? T.hdr_end - T.hdr_start : 0;
+    SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_pipe[1], 0));
+    int rc = fasta_ingest(c, d_tf, tgt_file_len, true, B_TGT, B_FA_TMP, B_FA_RNG, sc + S_G7, &T);       // :207-219
+    if (rc == SCCG_OK) { SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev[5], 0)); rc = fasta_ingest(c, d_rf, ref_file_len, false, B_REF, B_FA_TMP, B_FA_RNG, sc + S_G7, &R); }   // compression.cpp:193-200
     CompressResult res;
-    SCCG_TRY(compress_device(c, R.d_seq, R.len, T.d_seq, T.len, header, nh, &res, nullptr));
+    if (rc == SCCG_OK) {
+        const char* header = T.hdr_start >= 0 ? tgt_file + T.hdr_start : "";
+        const int64_t nh = T.hdr_start >= 0 ? T.hdr_end - T.hdr_start : 0;
+        rc = compress_device(c, R.d_seq, R.len, T.d_seq, T.len, header, nh, &res, nullptr);
+    }
+    SCCG_CK(cudaStreamSynchronize(c->s_h2d));                                 // the caller's buffers are no longer in use
+    if (rc != SCCG_OK) return rc;
     SCCG_CK(cudaEventRecord(c->ev[6], c->stream));
-    SCCG_TRY(deliver(c, res.d_out, res.out_len, nullptr, 0, out, out_len));
+    SCCG_TRY(deliver(c, res.d_out, res.out_len, dst, dst_cap, out, out_len));
     SCCG_CK(cudaEventRecord(c->ev[7], c->stream));
     SCCG_CK(cudaStreamSynchronize(c->stream));
     cudaEventElapsedTime(&c->prof.h2d_ms, c->ev[4], c->ev[5]);
@@ -421,8 +438,21 @@ int sccg_compress_fasta(sccg_ctx* c, const char* ref_file, int64_t ref_file_len,
     return res.stoi_failed ? stoi_failure() : SCCG_OK;
 }
 
-int sccg_decompress_fasta(sccg_ctx* c, const char* ref_file, int64_t ref_file_len, const char* inter, int64_t inter_len, char** out, int64_t* out_len) {
-    if (!c || !out || !out_len || (ref_file_len > 0 && !ref_file) || (inter_len > 0 && !inter)) return set_error(SCCG_E_ARG, "null argument");
+int sccg_compress_fasta(sccg_ctx* c, const char* ref_file, int64_t ref_file_len, const char* tgt_file, int64_t tgt_file_len,
+                        char** out, int64_t* out_len, int* mode_out) {
+    if (!out) return set_error(SCCG_E_ARG, "null argument");
+    return compress_fasta_impl(c, ref_file, ref_file_len, tgt_file, tgt_file_len, nullptr, 0, out, out_len, mode_out);
+}
+
+int sccg_compress_fasta_into(sccg_ctx* c, const char* ref_file, int64_t ref_file_len, const char* tgt_file, int64_t tgt_file_len,
+                             char* out, int64_t out_cap, int64_t* out_len, int* mode_out) {
+    if (!out) return set_error(SCCG_E_ARG, "null argument");
+    return compress_fasta_impl(c, ref_file, ref_file_len, tgt_file, tgt_file_len, out, out_cap, nullptr, out_len, mode_out);
+}
+
+static int decompress_fasta_impl(sccg_ctx* c, const char* ref_file, int64_t ref_file_len, const char* inter, int64_t inter_len, char* dst, int64_t dst_cap,
+                                 char** out, int64_t* out_len, const SinkSpec* sink) {
+    if (!c || !out_len || (ref_file_len > 0 && !ref_file) || (inter_len > 0 && !inter)) return set_error(SCCG_E_ARG, "null argument");
     SCCG_TRY(check_sizes(ref_file_len, inter_len));
     SCCG_CK(cudaSetDevice(c->device));
     prof_reset(c);
@@ -432,8 +462,42 @@ int sccg_decompress_fasta(sccg_ctx* c, const char* ref_file, int64_t ref_file_le
     SCCG_TRY(upload_file(c, B_FILE_R, ref_file, ref_file_len, &d_rf));
     FastaSeq R;
     SCCG_TRY(fasta_ingest(c, d_rf, ref_file_len, false, B_TGT, B_FA_TMP, B_FA_RNG, sc + S_G7, &R));      // decompression.cpp:47-58
-    return decompress_host(c, nullptr, R.len, inter, inter_len, nullptr, 0, out, out_len, R.d_seq);
+    return decompress_host(c, nullptr, R.len, inter, inter_len, dst, dst_cap, out, out_len, R.d_seq, nullptr, sink);
 }
+
+int sccg_decompress_fasta(sccg_ctx* c, const char* ref_file, int64_t ref_file_len, const char* inter, int64_t inter_len, char** out, int64_t* out_len) {
+    if (!out) return set_error(SCCG_E_ARG, "null argument");
+    return decompress_fasta_impl(c, ref_file, ref_file_len, inter, inter_len, nullptr, 0, out, out_len, nullptr);
+}
+
+int sccg_decompress_fasta_into(sccg_ctx* c, const char* ref_file, int64_t ref_file_len, const char* inter, int64_t inter_len, char* out, int64_t out_cap,
+                               int64_t* out_len) {
+    if (!out) return set_error(SCCG_E_ARG, "null argument");
+    return decompress_fasta_impl(c, ref_file, ref_file_len, inter, inter_len, out, out_cap, nullptr, out_len, nullptr);
+}
+
+int sccg_decompress_fasta_stream(sccg_ctx* c, const char* ref_file, int64_t ref_file_len, const char* inter, int64_t inter_len, sccg_sink_fn sink, void* user,
+                                 int64_t* total_len) {
+    if (!sink) return set_error(SCCG_E_ARG, "null argument");
+    SinkSpec sp{sink, user};
+    return decompress_fasta_impl(c, ref_file, ref_file_len, inter, inter_len, nullptr, 0, nullptr, total_len, &sp);
+}
+
+int sccg_decompress_stream(sccg_ctx* c, const char* ref_raw, int64_t ref_len, const char* inter, int64_t inter_len, sccg_sink_fn sink, void* user, int64_t* total_len) {
+    if (!c || !sink || !total_len || (ref_len > 0 && !ref_raw) || (inter_len > 0 && !inter)) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_TRY(check_sizes(ref_len, inter_len));
+    SCCG_CK(cudaSetDevice(c->device));
+    prof_reset(c);
+    SinkSpec sp{sink, user};
+    return decompress_host(c, ref_raw, ref_len, inter, inter_len, nullptr, 0, nullptr, total_len, nullptr, nullptr, &sp);
+}
+
+void* sccg_pinned_alloc(int64_t bytes) {
+    void* p = nullptr;
+    if (bytes <= 0 || cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); set_error(SCCG_E_NOMEM, "page-locked allocation failed"); return nullptr; }
+    return p;
+}
+void sccg_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
 int sccg_shard_match(sccg_ctx* c, const char* ref_slice, int64_t ref_len, const char* tgt_slice, int64_t tgt_len, int64_t seg_base, int is_last,
                      sccg_shard_info* info) {

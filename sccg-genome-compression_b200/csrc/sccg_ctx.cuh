@@ -62,7 +62,8 @@ struct sccg_ctx {
     unsigned char* res_ref; long long res_ref_len; size_t res_ref_cap; int res_ref_set;      // resident reference (sccg_reference_set): raw symbols, kept across calls
     int use_diag;                  // seg_match_k: try the diagonal-hypothesis parse first (SCCG_NO_DIAG=1 disables it)
     cudaStream_t s_h2d, s_d2h;     // copy streams of the pipelined host entry points (created on first use)
-    cudaEvent_t ev_pipe[2], ev_h2d[64], ev_g[64];
+    cudaEvent_t ev_pipe[2], ev_h2d[64], ev_g[64], ev_d2h[64];
+    void* h_stream[2]; size_t h_stream_cap;      // page-locked double buffer of the streaming decompressor (sccg_decompress*_stream)
     int pipe_ready;
     sccg::ShardState shard;
 };
@@ -137,7 +138,7 @@ static int pipe_streams(sccg_ctx* c) {
     SCCG_CK(cudaStreamCreate(&c->s_h2d));
     SCCG_CK(cudaStreamCreate(&c->s_d2h));
     for (int i = 0; i < 2; ++i) SCCG_CK(cudaEventCreate(&c->ev_pipe[i]));
-    for (int i = 0; i < 64; ++i) { SCCG_CK(cudaEventCreate(&c->ev_h2d[i])); SCCG_CK(cudaEventCreate(&c->ev_g[i])); }
+    for (int i = 0; i < 64; ++i) { SCCG_CK(cudaEventCreate(&c->ev_h2d[i])); SCCG_CK(cudaEventCreate(&c->ev_g[i])); SCCG_CK(cudaEventCreate(&c->ev_d2h[i])); }
     c->pipe_ready = 1;
     return SCCG_OK;
 }

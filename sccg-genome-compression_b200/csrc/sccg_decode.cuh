@@ -912,11 +912,14 @@ static const int PIPE_MAX_CHUNKS = 64;
 // sharding over several GPUs: dst receives the piece, *part_off its offset in the image, *out_len its length,
 // *total_len the length of the whole image; only the reference chunks that piece copies from are uploaded.
 struct PartSpec { int part, n_parts; int64_t* part_off; int64_t* total_len; };
+// streaming delivery (sccg_decompress*_stream): the image is handed to fn piece by piece, in order, from a page-locked double
+// buffer: while fn works on piece j (writes it to the output file), piece j + 1 is on its way over PCIe
+struct SinkSpec { sccg_sink_fn fn; void* user; };
 static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, const char* inter, i64 inter_len, char* dst, i64 dst_cap, char** out, int64_t* out_len,
-                                const u8* d_raw_in, const PartSpec* ps);
+                                const u8* d_raw_in, const PartSpec* ps, const SinkSpec* sink);
 static int decompress_host(sccg_ctx* c, const char* ref_raw, i64 ref_len, const char* inter, i64 inter_len, char* dst, i64 dst_cap, char** out, int64_t* out_len,
-                           const u8* d_raw_in = nullptr, const PartSpec* ps = nullptr) {
-    const int rc = decompress_host_impl(c, ref_raw, ref_len, inter, inter_len, dst, dst_cap, out, out_len, d_raw_in, ps);
+                           const u8* d_raw_in = nullptr, const PartSpec* ps = nullptr, const SinkSpec* sink = nullptr) {
+    const int rc = decompress_host_impl(c, ref_raw, ref_len, inter, inter_len, dst, dst_cap, out, out_len, d_raw_in, ps, sink);
     if (rc != SCCG_OK && c->pipe_ready) {
         // an error return must not leave copies from / into the caller's buffers in flight
         cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_d2h); cudaStreamSynchronize(c->main_stream);
@@ -924,8 +927,9 @@ static int decompress_host(sccg_ctx* c, const char* ref_raw, i64 ref_len, const 
     return rc;
 }
 static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, const char* inter, i64 inter_len, char* dst, i64 dst_cap, char** out, int64_t* out_len,
-                                const u8* d_raw_in, const PartSpec* ps) {
+                                const u8* d_raw_in, const PartSpec* ps, const SinkSpec* sink) {
     const bool parts = ps && ps->n_parts > 1;
+    if (sink && parts) return set_error(SCCG_E_ARG, "streaming and output-range sharding cannot be combined");
     // ---- the 3 / 4 getline calls (:66-101)
     const char* lines[4] = {inter, inter, inter, inter};
     i64 lens[4] = {0, 0, 0, 0};
@@ -1008,7 +1012,14 @@ static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, c
     *out_len = full;
     if (parts) *ps->total_len = full;
     char* h_dst = dst;
-    if (parts) {
+    if (sink) {
+        // the error flags are all set by now (tokenizer, run lists, bounds check of every token): nothing reaches the sink
+        // unless the whole image is going to be good
+        u32 hf[D_COUNT];
+        SCCG_TRY(read_scalars(c, sc, hf, D_COUNT));
+        if (hf[D_ERR] & DE_BOUNDS) return set_error(SCCG_E_BOUNDS, "ERROR: absolute_start + length exceeds reference genome size");
+        if (hf[D_ERR]) return set_error(SCCG_E_FORMAT, "malformed record stream or run list");
+    } else if (parts) {
         if (!dst) return set_error(SCCG_E_ARG, "null argument");
     } else if (dst && dst_cap < full) {
         return set_error(SCCG_E_ARG, "output buffer too small (required size returned in *out_len)");
@@ -1051,7 +1062,15 @@ static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, c
             prepared = i0;
         }
     }
-    if (!dst) {                                                              // allocated last: no early return can leak it
+    if (sink) {
+        const size_t need = (size_t)tiles_per_chunk * GATHER_TILE + (size_t)nh + 64;
+        if (c->h_stream_cap < need) {
+            for (int i = 0; i < 2; ++i) { if (c->h_stream[i]) cudaFreeHost(c->h_stream[i]); c->h_stream[i] = nullptr; }
+            c->h_stream_cap = 0;
+            for (int i = 0; i < 2; ++i) if (cudaMallocHost(&c->h_stream[i], need) != cudaSuccess) { cudaGetLastError(); return set_error(SCCG_E_NOMEM, "page-locked stream buffers"); }
+            c->h_stream_cap = need;
+        }
+    } else if (!dst) {                                                       // allocated last: no early return can leak it
         h_dst = (char*)malloc((size_t)full + 1);
         if (!h_dst) return set_error(SCCG_E_NOMEM, "malloc of the result failed");
         h_dst[full] = 0;
@@ -1081,7 +1100,31 @@ static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, c
         // bytes of the device image [-(nh+1), n): chunk 0 also carries the header line
         const i64 b0 = j == 0 ? -(nh + 1) : (i64)t0 * GATHER_TILE;
         i64 b1 = ((i64)t0 + tn) * GATHER_TILE; if (b1 > n) b1 = n;
+        if (sink) continue;                                                  // the pieces go home below, two in flight at most
         if (ce == cudaSuccess && b1 > b0) ce = cudaMemcpyAsync(h_dst + ((nh + 1) + b0 - img_base), d_text + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, c->s_d2h);
+    }
+    if (sink && rc == SCCG_OK && ce == cudaSuccess) {
+        auto piece = [&](int j, i64* b0, i64* b1) {                          // bytes [b0, b1) of the device image [-(nh+1), n)
+            const unsigned t0 = (unsigned)j * tiles_per_chunk;
+            const unsigned tn = plan.ntiles - t0 < tiles_per_chunk ? plan.ntiles - t0 : tiles_per_chunk;
+            *b0 = j == 0 ? -(nh + 1) : (i64)t0 * GATHER_TILE;
+            *b1 = ((i64)t0 + tn) * GATHER_TILE; if (*b1 > n) *b1 = n;
+        };
+        auto send_home = [&](int j) -> cudaError_t {
+            i64 b0, b1; piece(j, &b0, &b1);
+            cudaError_t e2 = cudaStreamWaitEvent(c->s_d2h, c->ev_g[j], 0);
+            if (e2 == cudaSuccess && b1 > b0) e2 = cudaMemcpyAsync(c->h_stream[j & 1], d_text + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, c->s_d2h);
+            if (e2 == cudaSuccess) e2 = cudaEventRecord(c->ev_d2h[j], c->s_d2h);
+            return e2;
+        };
+        for (int j = 0; j < n_och && j < 2 && ce == cudaSuccess; ++j) ce = send_home(j);
+        for (int j = 0; j < n_och && ce == cudaSuccess && rc == SCCG_OK; ++j) {
+            ce = cudaEventSynchronize(c->ev_d2h[j]);
+            if (ce != cudaSuccess) break;
+            i64 b0, b1; piece(j, &b0, &b1);
+            if (b1 > b0 && sink->fn(sink->user, (nh + 1) + b0, (const char*)c->h_stream[j & 1], b1 - b0) != 0) rc = set_error(SCCG_E_ARG, "the output sink reported a failure");
+            if (j + 2 < n_och && rc == SCCG_OK) ce = send_home(j + 2);        // this buffer is free again
+        }
     }
     if (ce == cudaSuccess) ce = cudaEventRecord(c->ev[7], c->s_d2h);
     if (rc == SCCG_OK && ce == cudaSuccess) rc = reconstruct_finish(c, &plan);       // synchronises the compute stream, reads the error flags
@@ -1089,8 +1132,8 @@ static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, c
     cudaError_t ce3 = cudaStreamSynchronize(c->s_h2d);
     if (rc == SCCG_OK && (ce != cudaSuccess || ce2 != cudaSuccess || ce3 != cudaSuccess))
         rc = set_error(SCCG_E_CUDA, "pipelined decompression failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : (ce2 != cudaSuccess ? ce2 : ce3)));
-    if (rc != SCCG_OK) { if (!dst) free(h_dst); return rc; }
-    if (!dst) *out = h_dst;
+    if (rc != SCCG_OK) { if (!dst && !sink) free(h_dst); return rc; }
+    if (!dst && !sink) *out = h_dst;
     cudaEventElapsedTime(&c->prof.h2d_ms, c->ev[4], c->ev[5]);
     cudaEventElapsedTime(&c->prof.d2h_ms, c->ev[6], c->ev[7]);
     return SCCG_OK;

@@ -236,5 +236,5 @@ cudaError_t cudaPeekAtLastError() { return 0; }
 const char* cudaGetErrorString(cudaError_t) { return "emu: no error"; }
 cudaError_t cudaSetDevice(int) { return 0; }
 cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
-cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
+cudaError_t cudaGetDeviceCount(int* n) { const char* e = getenv("SCCG_EMU_DEVICES"); *n = e && atoi(e) > 0 ? atoi(e) : 1; return 0; }      // tests of the multi-GPU host logic
 cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 8; return 0; }

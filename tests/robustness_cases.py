@@ -56,3 +56,46 @@ def check_stale_shard_write(ctx):
     with pytest.raises(sccg_b200.SccgError) as e:
         ctx.shard_write({"prev_p": 0, "skip_first_run": 0, "extra_last_len": 0, "prev_run_start": 0, "last_run_reaches_end": 0, "reserved": 0})
     assert e.value.code == sccg_b200.SCCG_E_ARG
+
+
+def check_streaming_and_fasta_into(ctx, chunk_env=None):
+    """sccg_decompress_stream / _fasta_stream deliver the image of sccg_decompress in order from the double buffer; errors come
+    before the first piece; sccg_compress_fasta_into == sccg_compress_fasta"""
+    import os
+    from sccg_genome_compression_b200 import synth
+    old = os.environ.get("SCCG_PIPE_CHUNK")
+    if chunk_env:
+        os.environ["SCCG_PIPE_CHUNK"] = str(chunk_env)
+    try:
+        for shape in ("local", "gap"):
+            if shape == "local":
+                ref, tgt = synth.local_pair(230_000, synth.seed_for(2, 95))
+            else:
+                ref, tgt = synth.global_gap_pair(160_000, 150_000, synth.seed_for(1, 95))
+            ref, tgt = ref.tobytes(), tgt.tobytes()
+            rc, inter, mode = ol.orc_compress(ref, tgt, b">stream me")
+            rc, exp = ol.orc_decompress(ref, inter)
+            assert rc == 0
+            pieces = ctx.decompress_stream(ref, inter)
+            assert [o for o, _ in pieces] == sorted(o for o, _ in pieces) and pieces[0][0] == 0
+            assert b"".join(p for _, p in pieces) == exp
+            if chunk_env:
+                assert len(pieces) > 2                                           # both buffers were reused
+            # FASTA file images
+            ref_fa = b">ref\n" + b"\n".join(ref[i:i + 60] for i in range(0, len(ref), 60)) + b"\n"
+            tgt_fa = b">stream me\n" + b"\n".join(tgt[i:i + 50] for i in range(0, len(tgt), 50)) + b"\n"
+            pieces = ctx.decompress_stream(ref_fa, inter, fasta=True)
+            assert b"".join(p for _, p in pieces) == exp
+            buf = C.create_string_buffer(len(inter) + 4096)
+            n, m = ctx.compress_fasta_into(ref_fa, tgt_fa, C.cast(buf, C.c_void_p).value, len(inter) + 4096)
+            assert (m, buf.raw[:n]) == (mode, inter)
+        ref = rnd(500, "far")
+        for bad in (b">h\n\n,\n(400,200)", b">h\n\n,\n(a,5)"):
+            with pytest.raises(sccg_b200.SccgError):
+                ctx.decompress_stream(ref, bad)
+    finally:
+        if chunk_env:
+            if old is None:
+                os.environ.pop("SCCG_PIPE_CHUNK", None)
+            else:
+                os.environ["SCCG_PIPE_CHUNK"] = old

@@ -147,3 +147,9 @@ def test_long_header_line(ctx):
 def test_stale_shard_write_is_rejected(ctx):
     import robustness_cases
     robustness_cases.check_stale_shard_write(ctx)
+
+
+@pytest.mark.parametrize("chunk", [None, 20000])
+def test_streaming_decompress_and_fasta_into(ctx, chunk):
+    import robustness_cases
+    robustness_cases.check_streaming_and_fasta_into(ctx, chunk)

@@ -31,6 +31,7 @@ with tempfile.TemporaryDirectory() as d:
     out = {"bp": n}
     for name, bindir in (("ours", ROOT / "sccg-genome-compression_b200" / "bin"), ("reference", ol.REF_DIR)):
         for rep in range(2 if name == "ours" else 1):                  # ours twice: the first run pays the CUDA context / page cache warm-up
+            env["SCCG_TIMING"] = "1"                                   # ours: context / read / gpu / write breakdown on stderr
             t0 = time.perf_counter()
             r = subprocess.run([str(bindir / "compress"), str(d / "ref.fa"), str(d / "tgt.fa"), str(d / name)], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
             t1 = time.perf_counter()
@@ -39,6 +40,9 @@ with tempfile.TemporaryDirectory() as d:
             t2 = time.perf_counter()
             assert r.returncode == 0 and r2.returncode == 0, (r.stderr[-300:], r2.stderr[-300:])
         out[name] = {"compress_s": round(t1 - t0, 3), "decompress_s": round(t2 - t1, 3)}
+        if name == "ours":
+            out[name]["compress_breakdown"] = [l for l in r.stderr.decode().splitlines() if l.startswith("timing:")]
+            out[name]["decompress_breakdown"] = [l for l in r2.stderr.decode().splitlines() if l.startswith("timing:")]
     same_c = (d / "ours" / "compressed_genome.txt").read_bytes() == (d / "reference" / "compressed_genome.txt").read_bytes()
     same_d = (d / "ours_dec" / "reconstructed_genome.fa").read_bytes() == (d / "reference_dec" / "reconstructed_genome.fa").read_bytes()
     out["compressed_genome_txt_identical"] = same_c; out["reconstructed_fa_identical"] = same_d
