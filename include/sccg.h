@@ -92,8 +92,9 @@ int sccg_compress_device(sccg_ctx* ctx, const void* d_ref, int64_t ref_len, cons
                          const char* header, int64_t header_len, void** d_out, int64_t* out_len, int* mode_out);
 
 /* match_sequences(Sr, St, k, m, global, offset)  (compression.cpp:36-179).
- * global == 0: one segment pair, nr and nt <= 1000 (the reference's own call sites :401, :428).
- * global != 0: whole sequences, any length < 2^31 (:561). */
+ * global == 0: one segment pair, nr and nt <= 1000 and 10 <= k <= 32 (the reference's own call sites, :401 k = 14 and :428
+ *              k = 10; its match_sequences has no such limits, larger local inputs return SCCG_E_ARG here).
+ * global != 0: whole sequences, any length < 2^31, 8 <= k <= 16 and 0 <= m <= 120 (:561 calls it with k = 14, m = 100). */
 int sccg_match_sequences(sccg_ctx* ctx, const char* Sr, int64_t nr, const char* St, int64_t nt,
                          int k, int m, int global, int offset, sccg_records* out);
 

@@ -8,6 +8,7 @@
 #include "sccg_mgpu.cuh"
 
 #include <new>
+#include <time.h>
 
 using namespace sccg;
 
@@ -47,15 +48,22 @@ const char* sccg_version(void) {
 
 const char* sccg_last_error(void) { return g_last_error.c_str(); }
 
+static double wall_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
+
 sccg_ctx* sccg_create(int device) {
+    const bool timing = getenv("SCCG_TIMING") != nullptr;
+    const double t_begin = wall_s();
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
+    const double t_count = wall_s();
     if (e != cudaSuccess || ndev <= 0) {
         set_error(SCCG_E_CUDA, "no CUDA device available (%s): this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
         return nullptr;
     }
     if (device < 0 || device >= ndev) { set_error(SCCG_E_ARG, "device index out of range"); return nullptr; }
     if (cudaSetDevice(device) != cudaSuccess) { set_error(SCCG_E_CUDA, "cudaSetDevice failed"); return nullptr; }
+    cudaFree(0);                                                               // forces the primary context into existence here (timed below)
+    const double t_ctx = wall_s();
     sccg_ctx* c = new (std::nothrow) sccg_ctx();
     if (!c) { set_error(SCCG_E_NOMEM, "out of host memory"); return nullptr; }
     memset(c, 0, sizeof *c);
@@ -71,6 +79,7 @@ sccg_ctx* sccg_create(int device) {
     for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
     for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreate(&c->ev_x[i]) == cudaSuccess;
     if (!ok) { set_error(SCCG_E_CUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError())); sccg_destroy(c); return nullptr; }
+    if (timing) fprintf(stderr, "timing: sccg_create: driver init %.3f s, device context %.3f s, streams / events / staging %.3f s\n", t_count - t_begin, t_ctx - t_count, wall_s() - t_ctx);
     return c;
 }
 

@@ -17,12 +17,17 @@
 #include "sccg_strip.cuh"
 #include "sccg_bulk.cuh"
 
+#include <algorithm>
+#include <utility>
+#include <vector>
+
 namespace sccg {
 
 static const int TOK_MAX = 25;        // "(-2147483648,2147483647)" is 24 characters
 
 enum DecScalar { D_ERR = 0, D_NSEG, D_NTOK, D_LS, D_LOW_ITEMS, D_N_ITEMS, D_NSUM, D_LSUM, D_STRIP, D_COUNT = 16 };
-enum DecErr { DE_FORMAT = 1, DE_BOUNDS = 2 };
+enum DecErr { DE_FORMAT = 1, DE_BOUNDS = 2, DE_LOW_UNSORTED = 4, DE_N_UNSORTED = 8 };   // the last two are no errors yet: reconstruct_normalize decides
+static const u32 DE_HARD = DE_FORMAT | DE_BOUNDS, DE_SOFT = DE_LOW_UNSORTED | DE_N_UNSORTED;
 
 __device__ __forceinline__ bool is_digit(u8 c) { return c >= '0' && c <= '9'; }
 
@@ -223,22 +228,25 @@ __global__ void runs_compact_k(const u8* __restrict__ s, i64 n, const u32* __res
 }
 
 // start[k] = prefix sum of deltas; validates ascending, non-overlapping runs
+// start[k] = prefix sum of deltas.  The compressor only writes ascending, non-overlapping runs; the reference's parser expands
+// whatever it reads into single positions and sorts them (decompression.cpp:138-164), so a list that is out of order or
+// overlaps is legal input: it raises a soft flag and reconstruct_normalize puts it in order before it is used.
 __global__ void runs_finish_k(const int* __restrict__ delta, const int* __restrict__ len, const u32* __restrict__ delta_excl, u32 K,
-                              int* __restrict__ start, u32* __restrict__ sc) {
+                              int* __restrict__ start, u32* __restrict__ sc, u32 soft_bit) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
     int st = (int)(delta_excl[k] + (u32)delta[k]);
     start[k] = st;
-    if (st < 0 || len[k] < 0) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);
+    if ((st < 0 && len[k] > 0) || len[k] < 0) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);       // a negative position: undefined behaviour in the reference (:257)
     if (k > 0) {
         int pst = (int)delta_excl[k];                             // previous start
-        if ((i64)st < (i64)pst + (i64)len[k - 1]) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);
+        if ((i64)st < (i64)pst + (i64)len[k - 1]) atomicOr(&sc[D_ERR], soft_bit);
     }
 }
 
 struct RunTable { int* start; int* len; u32* cum; u32 K; };        // cum[k] = sum of len[0..k)
 
-static int parse_runs(sccg_ctx* c, const u8* d_text, i64 n, int slot_base, u32* sc, int sc_items, u32* sc_sum, RunTable* out) {
+static int parse_runs(sccg_ctx* c, const u8* d_text, i64 n, int slot_base, u32* sc, int sc_items, u32* sc_sum, u32 soft_bit, RunTable* out) {
     // slot_base: 4 consecutive buffer slots
     out->start = nullptr; out->len = nullptr; out->cum = nullptr; out->K = 0;
     if (n <= 0) {
@@ -254,7 +262,7 @@ static int parse_runs(sccg_ctx* c, const u8* d_text, i64 n, int slot_base, u32* 
     SCCG_TRY(scan_exclusive_u32(c, isitem, isitem, n, sc + sc_items));
     u32 h[D_COUNT];
     SCCG_TRY(read_scalars(c, sc, h, D_COUNT));
-    if (h[D_ERR]) return set_error(SCCG_E_FORMAT, "malformed run list (the reference would throw from stoi or misbehave)");
+    if (h[D_ERR] & DE_HARD) return set_error(SCCG_E_FORMAT, "malformed run list (the reference would throw from stoi or misbehave)");
     u32 K = h[sc_items];
     int *delta = nullptr;
     u32* excl = nullptr;
@@ -267,7 +275,7 @@ static int parse_runs(sccg_ctx* c, const u8* d_text, i64 n, int slot_base, u32* 
     if (K == 0) return SCCG_OK;
     LAUNCH(c, runs_compact_k, dim3(g), dim3(256), 0, d_text, n, (const u32*)isitem, delta, out->len);
     SCCG_TRY(scan_exclusive_u32(c, (const u32*)delta, excl, (i64)K, nullptr));
-    LAUNCH(c, runs_finish_k, dim3(div_up(K, 256)), dim3(256), 0, (const int*)delta, (const int*)out->len, (const u32*)excl, K, out->start, sc);
+    LAUNCH(c, runs_finish_k, dim3(div_up(K, 256)), dim3(256), 0, (const int*)delta, (const int*)out->len, (const u32*)excl, K, out->start, sc, soft_bit);
     SCCG_TRY(scan_exclusive_u32(c, (const u32*)out->len, out->cum, (i64)K, sc_sum));
     return SCCG_OK;
 }
@@ -735,7 +743,7 @@ __global__ void __launch_bounds__(GATHER_CTA) dec_gather_k(GatherArgs a) {
 
 // reconstruct_genome.  header_reserve bytes are left free in front of the text (multiple of 16) so that the caller
 // can place "<header>\n" right before it.  *d_out points at the text itself.
-struct ReconPlan { GatherArgs a; u32* sc; int* tok_len; u32 ntok; unsigned ntiles; };
+struct ReconPlan { GatherArgs a; u32* sc; int* tok_len; u32 ntok; unsigned ntiles; RunTable lows, ns; u32 soft; };
 
 // everything of reconstruct_genome that does not read the reference symbols: run lists, tokenizer, sizes, output buffer
 static int reconstruct_prepare(sccg_ctx* c, i64 nr, const u8* d_enc, i64 ne, const u8* d_n, i64 nn, const u8* d_low, i64 nl,
@@ -761,8 +769,8 @@ static int reconstruct_prepare(sccg_ctx* c, i64 nr, const u8* d_enc, i64 ne, con
     // ---- the two run lists are parsed on the side lane while the tokenizer kernels run
     {
         SideLane side(c);
-        SCCG_TRY(parse_runs(c, d_low, nl, B_NUM0, sc, D_LOW_ITEMS, sc + D_LSUM, &lows));     // slots B_NUM0..B_NUM3
-        SCCG_TRY(parse_runs(c, d_n, nn, B_NUM4, sc, D_N_ITEMS, sc + D_NSUM, &ns));          // slots B_NUM4, B_NUM5, B_LRUN_S, B_LRUN_E
+        SCCG_TRY(parse_runs(c, d_low, nl, B_NUM0, sc, D_LOW_ITEMS, sc + D_LSUM, DE_LOW_UNSORTED, &lows));     // slots B_NUM0..B_NUM3
+        SCCG_TRY(parse_runs(c, d_n, nn, B_NUM4, sc, D_N_ITEMS, sc + D_NSUM, DE_N_UNSORTED, &ns));          // slots B_NUM4, B_NUM5, B_LRUN_S, B_LRUN_E
         SCCG_CK(cudaEventRecord(c->ev_side[3], c->stream));
     }
     // the run tables are needed by the gather only (and the N total by the sizes, global-mode files): the main lane does not
@@ -806,6 +814,7 @@ static int reconstruct_prepare(sccg_ctx* c, i64 nr, const u8* d_enc, i64 ne, con
     if (total >= 0xffffffffLL) return set_error(SCCG_E_ARG, "decoded output would exceed 4 GiB");
     u8* out = nullptr;
     SCCG_TRY(buf(c, B_OUT, (size_t)(header_reserve + total + 32), &out));
+    plan->lows = lows; plan->ns = ns; plan->soft = 0;
     GatherArgs& a = plan->a;
     a.ref = nullptr; a.enc = d_enc; a.seg_dst = seg_dst; a.seg_src = seg_src; a.tok_abs = tok_abs; a.nseg = (int)nseg;
     a.n_start = ns.start; a.n_len = ns.len; a.n_cum = ns.cum; a.n_k = (int)ns.K;
@@ -831,6 +840,51 @@ static int reconstruct_prepare(sccg_ctx* c, i64 nr, const u8* d_enc, i64 ne, con
     return SCCG_OK;
 }
 
+// Run lists the compressor cannot have written but the reference's parser accepts (positions are expanded and SORTED there,
+// decompression.cpp:138-164 / :176-207): runs out of order, lowercase runs that overlap.  Rare and off the hot path: the
+// (start, length) tables come to the host, are sorted -- lowercase: overlapping runs united (tolower is idempotent); N: an
+// overlap or a run past the end makes the reference's merge loop read out of range (:244-252) and stays an error -- and go
+// back; the per-tile windows are searched again.  Clears the soft flags.
+static int reconstruct_normalize(sccg_ctx* c, ReconPlan* plan) {
+    GatherArgs& a = plan->a;
+    for (int which = 0; which < 2; ++which) {
+        const u32 bit = which == 0 ? DE_LOW_UNSORTED : DE_N_UNSORTED;
+        if (!(plan->soft & bit)) continue;
+        RunTable& t = which == 0 ? plan->lows : plan->ns;
+        const u32 K = t.K;
+        std::vector<int> st(K), ln(K);
+        SCCG_CK(cudaMemcpyAsync(st.data(), t.start, sizeof(int) * K, cudaMemcpyDeviceToHost, c->stream));
+        SCCG_CK(cudaMemcpyAsync(ln.data(), t.len, sizeof(int) * K, cudaMemcpyDeviceToHost, c->stream));
+        SCCG_CK(cudaStreamSynchronize(c->stream));
+        std::vector<std::pair<i64, i64>> runs;                      // [start, end)
+        for (u32 k = 0; k < K; ++k) if (ln[k] > 0) runs.push_back(std::make_pair((i64)st[k], (i64)st[k] + ln[k]));
+        std::sort(runs.begin(), runs.end());
+        std::vector<std::pair<i64, i64>> outr;
+        for (const auto& r : runs) {
+            if (!outr.empty() && r.first < outr.back().second) {
+                if (which == 1) return set_error(SCCG_E_FORMAT, "N run list with overlapping runs (the reference reads out of range)");
+                if (r.second > outr.back().second) outr.back().second = r.second;
+            } else outr.push_back(r);
+        }
+        if (which == 1 && !outr.empty() && outr.back().second > a.Lm) return set_error(SCCG_E_FORMAT, "N run list reaches past the end of the decoded sequence");
+        const u32 K2 = (u32)outr.size();                          // <= K: the tables are large enough
+        std::vector<u32> cum(K2 + 1, 0u);
+        for (u32 k = 0; k < K2; ++k) { st[k] = (int)outr[k].first; ln[k] = (int)(outr[k].second - outr[k].first); cum[k + 1] = cum[k] + (u32)ln[k]; }
+        if (K2) {
+            SCCG_CK(cudaMemcpyAsync(t.start, st.data(), sizeof(int) * K2, cudaMemcpyHostToDevice, c->stream));
+            SCCG_CK(cudaMemcpyAsync(t.len, ln.data(), sizeof(int) * K2, cudaMemcpyHostToDevice, c->stream));
+            SCCG_CK(cudaMemcpyAsync(t.cum, cum.data(), sizeof(u32) * K2, cudaMemcpyHostToDevice, c->stream));
+        }
+        SCCG_CK(cudaStreamSynchronize(c->stream));                  // (pageable sources)
+        t.K = K2;
+        if (which == 0) a.l_k = (int)K2; else a.n_k = (int)K2;
+    }
+    plan->soft = 0;
+    SCCG_CK(cudaMemsetAsync(plan->sc + D_ERR, 0, sizeof(u32), c->stream));
+    LAUNCH(c, dec_tile_win_k, dim3(div_up(plan->ntiles, 128)), dim3(128), 0, a, plan->ntiles, const_cast<int4*>(a.tile_win));
+    return SCCG_OK;
+}
+
 // tiles [tile0, tile0 + ntiles) of the final text
 static int reconstruct_gather(sccg_ctx* c, const ReconPlan* plan, const u8* d_ref, unsigned tile0, unsigned ntiles) {
     GatherArgs a = plan->a;
@@ -844,7 +898,8 @@ static int reconstruct_finish(sccg_ctx* c, const ReconPlan* plan) {
     u32 h[D_COUNT];
     SCCG_TRY(read_scalars(c, plan->sc, h, D_COUNT));
     if (h[D_ERR] & DE_BOUNDS) return set_error(SCCG_E_BOUNDS, "ERROR: absolute_start + length exceeds reference genome size");
-    if (h[D_ERR]) return set_error(SCCG_E_FORMAT, "malformed record stream or run list");
+    if (h[D_ERR] & DE_HARD) return set_error(SCCG_E_FORMAT, "malformed record stream or run list");
+    const_cast<ReconPlan*>(plan)->soft = h[D_ERR] & DE_SOFT;       // a run list out of order: the caller normalises it and gathers again
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[2]); c->prof.kernels_ms = ms;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->prof.serialize_ms = ms;
@@ -859,6 +914,11 @@ static int reconstruct_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_
     SCCG_TRY(reconstruct_prepare(c, nr, d_enc, ne, d_n, nn, d_low, nl, header_reserve, &plan));
     SCCG_TRY(reconstruct_gather(c, &plan, d_ref, 0, plan.ntiles));
     SCCG_TRY(reconstruct_finish(c, &plan));
+    if (plan.soft) {                                               // a run list out of order (legal for the reference's parser): once more, in order
+        SCCG_TRY(reconstruct_normalize(c, &plan));
+        SCCG_TRY(reconstruct_gather(c, &plan, d_ref, 0, plan.ntiles));
+        SCCG_TRY(reconstruct_finish(c, &plan));
+    }
     *d_out = plan.a.out;
     *out_len = plan.a.total;
     return SCCG_OK;
@@ -1018,7 +1078,8 @@ static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, c
         u32 hf[D_COUNT];
         SCCG_TRY(read_scalars(c, sc, hf, D_COUNT));
         if (hf[D_ERR] & DE_BOUNDS) return set_error(SCCG_E_BOUNDS, "ERROR: absolute_start + length exceeds reference genome size");
-        if (hf[D_ERR]) return set_error(SCCG_E_FORMAT, "malformed record stream or run list");
+        if (hf[D_ERR] & DE_HARD) return set_error(SCCG_E_FORMAT, "malformed record stream or run list");
+        if (hf[D_ERR] & DE_SOFT) { plan.soft = hf[D_ERR] & DE_SOFT; SCCG_TRY(reconstruct_normalize(c, &plan)); }
     } else if (parts) {
         if (!dst) return set_error(SCCG_E_ARG, "null argument");
     } else if (dst && dst_cap < full) {
@@ -1128,6 +1189,22 @@ static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, c
     }
     if (ce == cudaSuccess) ce = cudaEventRecord(c->ev[7], c->s_d2h);
     if (rc == SCCG_OK && ce == cudaSuccess) rc = reconstruct_finish(c, &plan);       // synchronises the compute stream, reads the error flags
+    if (rc == SCCG_OK && ce == cudaSuccess && plan.soft && !sink) {
+        // a run list out of order (legal for the reference's parser, never written by a compressor): put it in order and
+        // produce the same chunks once more, without the pipeline
+        cudaStreamSynchronize(c->s_d2h);
+        rc = reconstruct_normalize(c, &plan);
+        for (int j = j_begin; j < j_end && rc == SCCG_OK; ++j) {
+            const unsigned t0 = (unsigned)j * tiles_per_chunk;
+            const unsigned tn = plan.ntiles - t0 < tiles_per_chunk ? plan.ntiles - t0 : tiles_per_chunk;
+            rc = reconstruct_gather(c, &plan, d_ref, t0, tn);
+            const i64 b0 = j == 0 ? -(nh + 1) : (i64)t0 * GATHER_TILE;
+            i64 b1 = ((i64)t0 + tn) * GATHER_TILE; if (b1 > n) b1 = n;
+            if (rc == SCCG_OK && b1 > b0 && cudaMemcpyAsync(h_dst + ((nh + 1) + b0 - img_base), d_text + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+                rc = set_error(SCCG_E_CUDA, "download of the reconstructed text failed");
+        }
+        if (rc == SCCG_OK) rc = reconstruct_finish(c, &plan);
+    }
     cudaError_t ce2 = cudaStreamSynchronize(c->s_d2h);
     cudaError_t ce3 = cudaStreamSynchronize(c->s_h2d);
     if (rc == SCCG_OK && (ce != cudaSuccess || ce2 != cudaSuccess || ce3 != cudaSuccess))

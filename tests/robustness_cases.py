@@ -99,3 +99,56 @@ def check_streaming_and_fasta_into(ctx, chunk_env=None):
                 os.environ.pop("SCCG_PIPE_CHUNK", None)
             else:
                 os.environ["SCCG_PIPE_CHUNK"] = old
+
+
+def check_decoder_tolerance(ctx):
+    """streams the reference accepts although no compressor writes them (decompression.cpp:126-207 expands the run lists into
+    positions and SORTS them; an out-of-range lowercase position is only a warning, :255-262): same bytes as the oracle.
+    Streams on which the reference runs into undefined behaviour or throws are errors in both.  The ONE pinned divergence is
+    a negative token length (`substr` wraps to "rest of the reference" there, SCCG_E_FORMAT here)."""
+    import random
+    ref = rnd(6000, "tol")
+    body = b"(0,1000)ACGT(1000,2000)TT(2100,1500)"
+    cases = [
+        (body, b"", b"(50,10)(-45,3),(12,20)(30,100)"),                    # lowercase runs out of order and overlapping
+        (body, b"", b"(4400,50)(-4400,10)4600,"),                          # ... and past the end of the sequence (warning only)
+        (body, b"(100,2)(-95,3),50", b"(60,10)(-58,3)"),                   # N runs out of order (distinct positions)
+        (body, b"(4000,3)(-3990,2)", b"(10,4000)"),
+        (b"(0,100)ACGT(50,20)", b"2,(5,3)(100,2)", b"(3,4)10,200"),        # optional commas, singles
+        (body, b"(10,5)(2,5)", b""),                                       # overlapping N runs: out-of-range read in the reference
+        (body, b"", b"(50,10)(-60,3)"),                                    # negative lowercase position: undefined behaviour
+        (body, b"(5000,10)", b""),                                         # N run past the end
+    ]
+    r = random.Random("tolerance")
+    runs = []
+    pos = 0
+    for _ in range(3000):                                                  # many runs, shuffled: several tiles and scan blocks
+        pos += r.randint(1, 3); ln = r.randint(1, 2); runs.append((pos, ln)); pos += ln
+    big_body = b"(0,6000)" + b"(-100,6000)" * 2
+    for which in ("low", "n"):
+        rr = runs[:]; r.shuffle(rr)
+        if which == "low":
+            rr += [(x + 1, 3) for x, _ in rr[:200]]                        # overlaps (lowercase only)
+        text = bytearray(); prev = 0
+        for st, ln in rr:
+            text += (b"%d," % (st - prev)) if ln == 1 and r.random() < 0.7 else b"(%d,%d)" % (st - prev, ln)
+            prev = st
+        cases.append((big_body, bytes(text) if which == "n" else b"", bytes(text) if which == "low" else b""))
+    for enc, nidx, low in cases:
+        rc_o, out_o = ol.orc_reconstruct(ref, enc, nidx, low)
+        if rc_o != 0:
+            with pytest.raises(sccg_b200.SccgError):
+                ctx.reconstruct(ref, enc, nidx, low)
+            continue
+        assert ctx.reconstruct(ref, enc, nidx, low) == out_o, (enc[:40], nidx[:40], low[:40])
+        inter = b">tolerant\n" + low + b"\n" + (nidx if nidx else b"") + b"\n" + enc
+        if nidx:                                                            # the file-level entry points (pipelined, streaming) take the same road
+            rc2, exp2 = ol.orc_decompress(ref, inter)
+            assert rc2 == 0 and ctx.decompress(ref, inter) == exp2
+            assert b"".join(p for _, p in ctx.decompress_stream(ref, inter)) == exp2
+    # pinned divergence
+    rc_o, out_o = ol.orc_reconstruct(ref, b"AC(10,-3)GT", b"", b"")
+    assert rc_o == 0 and out_o.startswith(b"AC" + ref[10:48].upper())
+    with pytest.raises(sccg_b200.SccgError) as e:
+        ctx.reconstruct(ref, b"AC(10,-3)GT", b"", b"")
+    assert e.value.code == sccg_b200.SCCG_E_FORMAT

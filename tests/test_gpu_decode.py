@@ -153,3 +153,8 @@ def test_stale_shard_write_is_rejected(ctx):
 def test_streaming_decompress_and_fasta_into(ctx, chunk):
     import robustness_cases
     robustness_cases.check_streaming_and_fasta_into(ctx, chunk)
+
+
+def test_decoder_tolerance(ctx):
+    import robustness_cases
+    robustness_cases.check_decoder_tolerance(ctx)
