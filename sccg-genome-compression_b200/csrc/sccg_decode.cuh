@@ -307,6 +307,7 @@ struct GatherArgs {
     i64 total;       // bytes of wrapped text
     u8* out;
     u32 tile0;       // first tile of this launch (the text may be produced in several launches, see decompress_host)
+    const u32* err;  // the decoder's error word: while a run list awaits normalisation (DE_SOFT) the tables must not be used
 };
 
 static const int GATHER_T = 256;
@@ -573,7 +574,7 @@ __device__ __forceinline__ void tile_symbols(i64 Q0, i64 Qe, i64 Lm, u32* b0, u3
 // per tile: where its copy segments and lowercase runs start (the searches leave the gather's critical path)
 __global__ void dec_tile_win_k(GatherArgs a, unsigned ntiles, int4* __restrict__ tile_win) {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntiles) return;
+    if (t >= ntiles || (*a.err & DE_SOFT)) return;
     const i64 Q0 = (i64)t * GATHER_TILE;
     const i64 Qe = Q0 + GATHER_TILE < a.total ? Q0 + GATHER_TILE : a.total;
     int4 w = make_int4(0, 0, 0, 0);
@@ -630,6 +631,7 @@ __global__ void __launch_bounds__(GATHER_CTA) dec_gather_k(GatherArgs a) {
     const unsigned tile = blockIdx.x + a.tile0;
     const i64 Q0 = (i64)tile * GATHER_TILE;
     const i64 Qe = Q0 + GATHER_TILE < a.total ? Q0 + GATHER_TILE : a.total;           // exclusive
+    if (*a.err & DE_SOFT) return;                                 // a run list is out of order: the caller normalises it and launches again
     const int4 tw = a.tile_win[tile];
     if (!tw.w) {
         // generic path: one 16-byte piece per thread and round
@@ -819,7 +821,7 @@ static int reconstruct_prepare(sccg_ctx* c, i64 nr, const u8* d_enc, i64 ne, con
     a.ref = nullptr; a.enc = d_enc; a.seg_dst = seg_dst; a.seg_src = seg_src; a.tok_abs = tok_abs; a.nseg = (int)nseg;
     a.n_start = ns.start; a.n_len = ns.len; a.n_cum = ns.cum; a.n_k = (int)ns.K;
     a.l_start = lows.start; a.l_len = lows.len; a.l_k = (int)lows.K;
-    a.Ls = Ls; a.Lm = Lm; a.total = total; a.out = out + header_reserve; a.tile0 = 0;
+    a.Ls = Ls; a.Lm = Lm; a.total = total; a.out = out + header_reserve; a.tile0 = 0; a.err = sc + D_ERR;
     plan->sc = sc; plan->tok_len = tok_len; plan->ntok = ntok; plan->ntiles = div_up(total, GATHER_TILE);
     // resolved segment sources and per-tile entry points: the gather itself starts from two table loads
     i64* seg_ptr = nullptr; int4* tile_win = nullptr;
@@ -943,6 +945,7 @@ __global__ void dec_need_k(GatherArgs a, const int* __restrict__ tok_len, i64 ch
     const int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     u32 hi = 0, lo = 0xffffffffu;
     i64 c0 = -1, c1 = -2;
+    if (*a.err & DE_SOFT) return;                                 // (uniform) tables not usable yet
     if (k < a.nseg) {
         const i64 src = a.seg_src[k];
         const i64 s0 = a.seg_dst[k], s1 = k + 1 < a.nseg ? (i64)a.seg_dst[k + 1] : a.Ls;
@@ -1073,13 +1076,7 @@ static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, c
     if (parts) *ps->total_len = full;
     char* h_dst = dst;
     if (sink) {
-        // the error flags are all set by now (tokenizer, run lists, bounds check of every token): nothing reaches the sink
-        // unless the whole image is going to be good
-        u32 hf[D_COUNT];
-        SCCG_TRY(read_scalars(c, sc, hf, D_COUNT));
-        if (hf[D_ERR] & DE_BOUNDS) return set_error(SCCG_E_BOUNDS, "ERROR: absolute_start + length exceeds reference genome size");
-        if (hf[D_ERR] & DE_HARD) return set_error(SCCG_E_FORMAT, "malformed record stream or run list");
-        if (hf[D_ERR] & DE_SOFT) { plan.soft = hf[D_ERR] & DE_SOFT; SCCG_TRY(reconstruct_normalize(c, &plan)); }
+        // pieces are sized by the library: nothing to check
     } else if (parts) {
         if (!dst) return set_error(SCCG_E_ARG, "null argument");
     } else if (dst && dst_cap < full) {
@@ -1090,17 +1087,35 @@ static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, c
     const int n_och = (int)((plan.ntiles + tiles_per_chunk - 1) / tiles_per_chunk);
     u32 need[PIPE_MAX_CHUNKS], need_lo[PIPE_MAX_CHUNKS];
     for (int j = 0; j < n_och; ++j) { need[j] = 0xffffffffu; need_lo[j] = 0u; }
-    if (local_mode && plan.a.nseg > 0 && (n_och > 1 || parts)) {
+    {
+        // one host round trip: the decoder's error word (every flag is set by now: tokenizer, run lists, bounds check of every
+        // token -- nothing is gathered, let alone delivered, from a malformed file) and, for files of several chunks, the
+        // reference range every output chunk needs
+        const bool need_block = local_mode && plan.a.nseg > 0 && (n_och > 1 || parts);
         u32* d_need = nullptr;                                               // [0, 64): need_hi, [64, 128): need_lo
         SCCG_TRY(buf(c, B_NEED, 2 * PIPE_MAX_CHUNKS, &d_need));
-        SCCG_CK(cudaMemsetAsync(d_need, 0, sizeof(u32) * PIPE_MAX_CHUNKS, c->stream));
-        SCCG_CK(cudaMemsetAsync(d_need + PIPE_MAX_CHUNKS, 0xff, sizeof(u32) * PIPE_MAX_CHUNKS, c->stream));
-        LAUNCH(c, dec_need_k, dim3(div_up(plan.a.nseg, 256)), dim3(256), 0, plan.a, (const int*)plan.tok_len, (i64)tiles_per_chunk * GATHER_TILE, d_need,
-               d_need + PIPE_MAX_CHUNKS);
-        SCCG_CK(cudaMemcpyAsync((char*)c->h_pinned + 8192, d_need, sizeof(u32) * 2 * PIPE_MAX_CHUNKS, cudaMemcpyDeviceToHost, c->stream));
-        SCCG_CK(cudaStreamSynchronize(c->stream));
-        memcpy(need, (char*)c->h_pinned + 8192, sizeof(u32) * (size_t)n_och);
-        memcpy(need_lo, (char*)c->h_pinned + 8192 + sizeof(u32) * PIPE_MAX_CHUNKS, sizeof(u32) * (size_t)n_och);
+        u32* h_need = (u32*)((char*)c->h_pinned + 8192);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            if (need_block) {
+                SCCG_CK(cudaMemsetAsync(d_need, 0, sizeof(u32) * PIPE_MAX_CHUNKS, c->stream));
+                SCCG_CK(cudaMemsetAsync(d_need + PIPE_MAX_CHUNKS, 0xff, sizeof(u32) * PIPE_MAX_CHUNKS, c->stream));
+                LAUNCH(c, dec_need_k, dim3(div_up(plan.a.nseg, 256)), dim3(256), 0, plan.a, (const int*)plan.tok_len, (i64)tiles_per_chunk * GATHER_TILE, d_need,
+                       d_need + PIPE_MAX_CHUNKS);
+                SCCG_CK(cudaMemcpyAsync(h_need, d_need, sizeof(u32) * 2 * PIPE_MAX_CHUNKS, cudaMemcpyDeviceToHost, c->stream));
+            }
+            SCCG_CK(cudaMemcpyAsync(h_need + 2 * PIPE_MAX_CHUNKS, sc + D_ERR, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+            SCCG_CK(cudaStreamSynchronize(c->stream));
+            const u32 flags = h_need[2 * PIPE_MAX_CHUNKS];
+            if (flags & DE_BOUNDS) return set_error(SCCG_E_BOUNDS, "ERROR: absolute_start + length exceeds reference genome size");
+            if (flags & DE_HARD) return set_error(SCCG_E_FORMAT, "malformed record stream or run list");
+            if (!(flags & DE_SOFT)) break;
+            plan.soft = flags & DE_SOFT;                                     // a run list out of order (legal for the reference's parser): sort it, ask again
+            SCCG_TRY(reconstruct_normalize(c, &plan));
+        }
+        if (need_block) {
+            memcpy(need, h_need, sizeof(u32) * (size_t)n_och);
+            memcpy(need_lo, h_need + PIPE_MAX_CHUNKS, sizeof(u32) * (size_t)n_och);
+        }
     }
     // ---- the output chunks of this call: all of them, or the part-th of n_parts contiguous groups
     int j_begin = 0, j_end = n_och;
@@ -1124,12 +1139,12 @@ static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, c
         }
     }
     if (sink) {
-        const size_t need = (size_t)tiles_per_chunk * GATHER_TILE + (size_t)nh + 64;
-        if (c->h_stream_cap < need) {
+        const size_t need_bytes = (size_t)tiles_per_chunk * GATHER_TILE + (size_t)nh + 64;
+        if (c->h_stream_cap < need_bytes) {
             for (int i = 0; i < 2; ++i) { if (c->h_stream[i]) cudaFreeHost(c->h_stream[i]); c->h_stream[i] = nullptr; }
             c->h_stream_cap = 0;
-            for (int i = 0; i < 2; ++i) if (cudaMallocHost(&c->h_stream[i], need) != cudaSuccess) { cudaGetLastError(); return set_error(SCCG_E_NOMEM, "page-locked stream buffers"); }
-            c->h_stream_cap = need;
+            for (int i = 0; i < 2; ++i) if (cudaMallocHost(&c->h_stream[i], need_bytes) != cudaSuccess) { cudaGetLastError(); return set_error(SCCG_E_NOMEM, "page-locked stream buffers"); }
+            c->h_stream_cap = need_bytes;
         }
     } else if (!dst) {                                                       // allocated last: no early return can leak it
         h_dst = (char*)malloc((size_t)full + 1);
@@ -1189,22 +1204,6 @@ static int decompress_host_impl(sccg_ctx* c, const char* ref_raw, i64 ref_len, c
     }
     if (ce == cudaSuccess) ce = cudaEventRecord(c->ev[7], c->s_d2h);
     if (rc == SCCG_OK && ce == cudaSuccess) rc = reconstruct_finish(c, &plan);       // synchronises the compute stream, reads the error flags
-    if (rc == SCCG_OK && ce == cudaSuccess && plan.soft && !sink) {
-        // a run list out of order (legal for the reference's parser, never written by a compressor): put it in order and
-        // produce the same chunks once more, without the pipeline
-        cudaStreamSynchronize(c->s_d2h);
-        rc = reconstruct_normalize(c, &plan);
-        for (int j = j_begin; j < j_end && rc == SCCG_OK; ++j) {
-            const unsigned t0 = (unsigned)j * tiles_per_chunk;
-            const unsigned tn = plan.ntiles - t0 < tiles_per_chunk ? plan.ntiles - t0 : tiles_per_chunk;
-            rc = reconstruct_gather(c, &plan, d_ref, t0, tn);
-            const i64 b0 = j == 0 ? -(nh + 1) : (i64)t0 * GATHER_TILE;
-            i64 b1 = ((i64)t0 + tn) * GATHER_TILE; if (b1 > n) b1 = n;
-            if (rc == SCCG_OK && b1 > b0 && cudaMemcpyAsync(h_dst + ((nh + 1) + b0 - img_base), d_text + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
-                rc = set_error(SCCG_E_CUDA, "download of the reconstructed text failed");
-        }
-        if (rc == SCCG_OK) rc = reconstruct_finish(c, &plan);
-    }
     cudaError_t ce2 = cudaStreamSynchronize(c->s_d2h);
     cudaError_t ce3 = cudaStreamSynchronize(c->s_h2d);
     if (rc == SCCG_OK && (ce != cudaSuccess || ce2 != cudaSuccess || ce3 != cudaSuccess))

@@ -151,4 +151,4 @@ def check_decoder_tolerance(ctx):
     assert rc_o == 0 and out_o.startswith(b"AC" + ref[10:48].upper())
     with pytest.raises(sccg_b200.SccgError) as e:
         ctx.reconstruct(ref, b"AC(10,-3)GT", b"", b"")
-    assert e.value.code == sccg_b200.SCCG_E_FORMAT
+    assert e.value.code == sccg_b200.SCCG_E_FORMAT, str(e.value)
