@@ -379,7 +379,9 @@ def main() -> None:
             else:
                 mg.compress_item(i, _cbuf(p["h_ref"], p["nr"]), _cbuf(p["h_tgt"], p["n"]), p["header"])
             pr = ctx.profile(); dev_ms += pr["kernels_ms"]; nl += pr["launches"]
-        items = mg.gather(h_gather.data_ptr(), h_gather.numel())
+        # inputs resident in HBM: the gathered streams stay in rank 0's HBM as well (like sccg_compress_device's image); from host
+        # buffers: they go on to rank 0's page-locked buffer
+        items = mg.gather_device() if device_resident else mg.gather(h_gather.data_ptr(), h_gather.numel())
         dev_ms += ctx.profile()["exchange_ms"]
         return dev_ms, nl, items
 
@@ -482,6 +484,23 @@ def main() -> None:
         barrier()
     launches = int(reduce(float(launches), "sum"))
 
+    # ---- the host's PCIe ceiling with all ranks copying at once (plain cudaMemcpyAsync from / to page-locked memory, no kernels):
+    #      what the end-to-end numbers above can reach at most on this box
+    pcie = {}
+    nbytes = 256 << 20
+    h_probe = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_probe = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    for name, fn in (("h2d", lambda: d_probe.copy_(h_probe, non_blocking=True)), ("d2h", lambda: h_probe.copy_(d_probe, non_blocking=True))):
+        fn(); barrier()
+        t0 = time.perf_counter()
+        for _ in range(8):
+            fn()
+        barrier()
+        dt = reduce(time.perf_counter() - t0)
+        pcie[name + "_gbs_aggregate"] = world * 8 * nbytes / dt / 1e9
+    pcie["note"] = f"{world} rank(s) copying simultaneously, 8 x 256 MiB each; e2e compress moves {2 * total_bp / 1e9:.2f} GB host->device per step"
+    del h_probe, d_probe
+
     # ---- untimed verification of what was timed
     verified = parity_ref = None
     if not args.no_verify:
@@ -551,7 +570,8 @@ def main() -> None:
             "metric": METRIC, "value": total_bp / (c_dev_ms / 1e3) / 1e6, "unit": "Mbp/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": c_dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_name(args.scale), "bp_per_step": total_bp, "pairs": len(lengths),
-                       "sharding": "pairs LPT-packed onto the ranks (sccg_mgpu_assign), encoded streams gathered to rank 0 over NCCL (sccg_mgpu_gather) inside the timed region",
+                       "sharding": "pairs LPT-packed onto the ranks (sccg_mgpu_assign), encoded streams gathered to rank 0 over NCCL inside the timed region "
+                                   "(value: sccg_mgpu_gather_device, into rank 0's HBM; e2e: sccg_mgpu_gather, on to rank 0's page-locked host buffer)",
                        "pairs_per_rank": [owner.count(r) for r in range(world)], "bp_on_busiest_rank": max(sum(lengths[i] for i in range(len(lengths)) if owner[i] == r) for r in range(world)),
                        "l2": "every pair (2 x 48..249 MB) is larger than the 126 MB L2 and 24 pairs (6.2 GB) are cycled through, no flush needed",
                        "timing": "value: per rank, CUDA events on the library stream around every call (first launch to last completion) + the gather, summed, max over ranks; "
@@ -566,7 +586,7 @@ def main() -> None:
             "roofline": roof_c,
             "cpu_baseline": cpu,
             "e2e": {"value": total_bp / (c_e2e_ms / 1e3) / 1e6, "unit": "Mbp/s", "h2d_bytes_per_step": h2d_genome, "d2h_bytes_per_step": enc_total,
-                    "ms_per_step": c_e2e_ms,
+                    "ms_per_step": c_e2e_ms, "frac_of_pcie_ceiling": (h2d_genome / (c_e2e_ms / 1e3) / 1e9) / pcie["h2d_gbs_aggregate"],
                     "api": "sccg_mgpu_compress_item per pair (pinned host buffers in, pipelined upload) + sccg_mgpu_gather (NCCL) -> pinned buffer on rank 0"},
             "chr1_local": {
                 "workload": "chr1-sized pair (249,250,621 bp), BASELINE configs[1], one GPU" if full else "pair 0 (reduced)",
@@ -579,6 +599,7 @@ def main() -> None:
                                        "h2d_bytes_per_step": p["nr"] + len(p["enc"]), "d2h_bytes_per_step": chr1["d_len"], "h2d_ms": chr1["e2e_dprof"]["h2d_ms"],
                                        "d2h_ms": chr1["e2e_dprof"]["d2h_ms"], "api": "sccg_decompress_into"}}},
             "gpu_launches": launches,
+            "pcie_ceiling": pcie,
             "clocks": clocks.summary(),
         }
         line.update(glob)

@@ -237,6 +237,10 @@ int sccg_mgpu_compress_item_device(sccg_mgpu* g, int32_t item, const void* d_ref
 int sccg_mgpu_stash_device(sccg_mgpu* g, int32_t item, const void* d_data, int64_t len);
 int sccg_mgpu_gather(sccg_mgpu* g, char* out, int64_t out_cap, int32_t* item_ids, int64_t* item_offs, int64_t* item_lens, int32_t cap_items,
                      int32_t* n_items, int64_t* total);
+/* same, but the gathered streams stay in rank 0's device memory (*d_out: owned by the communicator, valid until its next gather;
+ * sccg_download fetches pieces of it): the counterpart of sccg_compress_device for a job whose inputs are resident in HBM */
+int sccg_mgpu_gather_device(sccg_mgpu* g, void** d_out, int32_t* item_ids, int64_t* item_offs, int64_t* item_lens, int32_t cap_items,
+                            int32_t* n_items, int64_t* total);
 
 /* (2) One pair over all ranks by segment range (the local path, compression.cpp:381-481).  Collective: every rank passes the
  * same host buffers but uploads and matches only its own slice; the border records travel in one ncclAllGather, every rank

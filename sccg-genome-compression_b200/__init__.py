@@ -142,6 +142,7 @@ def load_library(path: str | os.PathLike | None = None) -> C.CDLL:
     lib.sccg_mgpu_compress_item_device.argtypes = [vp, C.c_int32, vp, i64, vp, i64, cp, i64, i64p, C.POINTER(C.c_int)]
     lib.sccg_mgpu_stash_device.argtypes = [vp, C.c_int32, vp, i64]
     lib.sccg_mgpu_gather.argtypes = [vp, vp, i64, i32p, i64p, i64p, C.c_int32, i32p, i64p]
+    lib.sccg_mgpu_gather_device.argtypes = [vp, C.POINTER(vp), i32p, i64p, i64p, C.c_int32, i32p, i64p]
     lib.sccg_mgpu_compress_sharded.argtypes = [vp, cp, i64, cp, i64, cp, i64, vp, i64, i64p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.sccg_mgpu_decompress_sharded.argtypes = [vp, cp, i64, cp, i64, vp, i64, i64p, i64p, i64p]
     _libs[key] = lib
@@ -222,6 +223,15 @@ class Mgpu:
         if own is not None:
             return {ids[k]: own.raw[offs[k]:offs[k] + lens[k]] for k in range(n.value)}
         return {ids[k]: (offs[k], lens[k]) for k in range(n.value)}
+
+    def gather_device(self, max_items: int = 64 * 64):
+        """collective; the gathered streams stay in rank 0's device memory -> rank 0: (device pointer, {item: (offset, length)}); others: None"""
+        ids = (C.c_int32 * max_items)(); offs = (C.c_int64 * max_items)(); lens = (C.c_int64 * max_items)()
+        n = C.c_int32(); total = C.c_int64(); d = C.c_void_p()
+        self._check(self.lib.sccg_mgpu_gather_device(self.handle, C.byref(d), ids, offs, lens, max_items, C.byref(n), C.byref(total)))
+        if self.rank != 0:
+            return None
+        return d.value or 0, {ids[k]: (offs[k], lens[k]) for k in range(n.value)}
 
     def compress_sharded(self, ref, tgt, header: bytes = b"", out_ptr: int = 0, out_cap: int = 0):
         """collective: one pair over all ranks by segment range -> rank 0: (image or its length, mode, sharded); others: (None, mode, sharded)"""

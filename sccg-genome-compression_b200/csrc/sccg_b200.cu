@@ -613,7 +613,15 @@ int sccg_mgpu_gather(sccg_mgpu* g, char* out, int64_t out_cap, int32_t* item_ids
     if (!g) return set_error(SCCG_E_ARG, "null argument");
     if (g->rank == 0 && (!out || !item_ids || !item_offs || !item_lens)) return set_error(SCCG_E_ARG, "null argument");
     SCCG_CK(cudaSetDevice(g->ctx->device));
-    return mg_gather(g, out, out_cap, item_ids, item_offs, item_lens, cap_items, n_items, total);
+    return mg_gather(g, out, out_cap, nullptr, item_ids, item_offs, item_lens, cap_items, n_items, total);
+}
+
+int sccg_mgpu_gather_device(sccg_mgpu* g, void** d_out, int32_t* item_ids, int64_t* item_offs, int64_t* item_lens, int32_t cap_items,
+                            int32_t* n_items, int64_t* total) {
+    if (!g) return set_error(SCCG_E_ARG, "null argument");
+    if (g->rank == 0 && (!d_out || !item_ids || !item_offs || !item_lens)) return set_error(SCCG_E_ARG, "null argument");
+    SCCG_CK(cudaSetDevice(g->ctx->device));
+    return mg_gather(g, nullptr, 0, d_out, item_ids, item_offs, item_lens, cap_items, n_items, total);
 }
 
 // One pair, segment pairs spread over all ranks (compression.cpp:381-481 sharded by segment range).  Collective: every rank

@@ -225,7 +225,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
     SCCG_TRY(buf(c, B_OUT, cap + 16, &out));
     SCCG_TRY(write_header(c, out, header, nh));
     SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));                // the run-list text is ready
-    if (low_k) LAUNCH(c, copy_text_k, dim3(low_k < 4096 ? 8 : 128), dim3(256), 0, out + hdr_bytes, (const u8*)low_text, (const u32*)(sc + S_LOW_TEXT));
+    if (low_k) LAUNCH(c, copy_text_k, dim3(low_k < 4096 ? 8 : (unsigned)c->sm_count * 16u), dim3(256), 0, out + hdr_bytes, (const u8*)low_text, (const u32*)(sc + S_LOW_TEXT));
     LAUNCH(c, put_separators_k, dim3(1), dim3(1), 0, out, (u32)hdr_bytes, sc, 0);
     if (n_iter > 0) {
         unsigned want = div_up(n_iter, 8 * 32);                              // 8 warps per CTA, 32 segments per warp

@@ -1030,7 +1030,7 @@ static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8
     SCCG_TRY(write_header(c, out, header, nh));
     int *nrun_s = nullptr, *nrun_e = nullptr;
     // the lowercase-run text was produced on the side lane of compress_device (sc[S_LOW_TEXT] holds its length)
-    if (low_k) LAUNCH(c, copy_text_k, dim3(low_k < 4096 ? 8 : 128), dim3(256), 0, out + hdr_bytes, d_low_text, (const u32*)(sc + S_LOW_TEXT));
+    if (low_k) LAUNCH(c, copy_text_k, dim3(low_k < 4096 ? 8 : (unsigned)c->sm_count * 16u), dim3(256), 0, out + hdr_bytes, d_low_text, (const u32*)(sc + S_LOW_TEXT));
     // the N-run text goes right after "<low>\n": its position depends on the (device-side) length of the lowercase text
     u8* ntext = nullptr;
     SCCG_TRY(buf(c, B_NRUN_TEXT, 24ull * n_k + 16, &ntext));

@@ -369,7 +369,8 @@ static int mg_stash(sccg_mgpu* g, int32_t item, const void* d_data, i64 len) {
 }
 
 // collective.  Rank 0: out receives the streams back to back, (ids, offs, lens) describe them in (rank, stash order).
-static int mg_gather(sccg_mgpu* g, char* out, i64 out_cap, int32_t* ids, int64_t* offs, int64_t* lens, int32_t cap_items, int32_t* n_items, int64_t* total) {
+// out == NULL with d_out != NULL: the gathered streams stay in rank 0's device memory (*d_out, owned by the communicator, valid until its next gather)
+static int mg_gather(sccg_mgpu* g, char* out, i64 out_cap, void** d_out, int32_t* ids, int64_t* offs, int64_t* lens, int32_t cap_items, int32_t* n_items, int64_t* total) {
     sccg_ctx* c = g->ctx;
     cudaStream_t s = c->main_stream;
     const int W = g->world;
@@ -391,7 +392,7 @@ static int mg_gather(sccg_mgpu* g, char* out, i64 out_cap, int32_t* ids, int64_t
         for (int r = 0; r < W; ++r) { roff[r] = sum; sum += all[r * MG_META_I64 + 1]; cnt += (int)all[r * MG_META_I64]; }
         if (total) *total = sum;
         if (n_items) *n_items = cnt;
-        if (cnt > cap_items || sum > out_cap) rc = set_error(SCCG_E_ARG, "gather: output arrays too small (required sizes returned)");
+        if (cnt > cap_items || (out && sum > out_cap)) rc = set_error(SCCG_E_ARG, "gather: output arrays too small (required sizes returned)");
         // the receives are posted even when the caller's buffers are too small: the other ranks are already sending
         SCCG_TRY(mg_grow(&g->d_recv, &g->recv_cap, (size_t)sum + 64, 0, s));
         std::vector<MgP2P> recvs;
@@ -399,7 +400,8 @@ static int mg_gather(sccg_mgpu* g, char* out, i64 out_cap, int32_t* ids, int64_t
         if (g->stash_len) SCCG_CK(cudaMemcpyAsync(g->d_recv, g->d_stash, g->stash_len, cudaMemcpyDeviceToDevice, s));
         SCCG_TRY(g->tr->p2p(nullptr, 0, recvs.data(), (int)recvs.size(), s));
         if (rc == SCCG_OK) {
-            if (sum > 0) SCCG_CK(cudaMemcpyAsync(out, g->d_recv, (size_t)sum, cudaMemcpyDeviceToHost, s));
+            if (sum > 0 && out) SCCG_CK(cudaMemcpyAsync(out, g->d_recv, (size_t)sum, cudaMemcpyDeviceToHost, s));
+            if (d_out) *d_out = g->d_recv;
             int k = 0;
             for (int r = 0; r < W; ++r) {
                 i64 o = roff[r];

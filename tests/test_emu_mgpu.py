@@ -74,6 +74,14 @@ def test_whole_genome_gather(world):
                 if owner[i] == rank:
                     mg.compress_item(i, r, t, h)
             got = mg.gather()
+        # the device-side variant: same streams, left in rank 0's device memory
+        for i, (r, t, h) in enumerate(pairs):
+            if owner[i] == rank:
+                mg.compress_item(i, r, t, h)
+        dev = mg.gather_device()
+        if rank == 0:
+            ptr, where = dev
+            assert {i: ctx.download(ptr + o, n) for i, (o, n) in where.items()} == got
         return got
     res = run_ranks(world, body)
     assert all(x is None for x in res[1:])

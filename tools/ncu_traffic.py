@@ -4,7 +4,7 @@ of `ncu --set full` captures of `bench.py --steps 1 --warmup 1`.  usage: ncu_tra
 import csv, json, re, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
-out = {"source": "ncu --set full --clock-control none, bench.py --steps 1 --warmup 1 (chr1-sized synthetic local pair); dram__bytes_read.sum + dram__bytes_write.sum", "kernels": {}}
+out = {"source": "ncu --set full --clock-control none, tools/one_chr1.py (chr1-sized synthetic local pair, second launch of each kernel); dram__bytes_read.sum + dram__bytes_write.sum", "kernels": {}}
 unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 for f in sys.argv[1:]:
     rows = list(csv.reader(open(f)))
