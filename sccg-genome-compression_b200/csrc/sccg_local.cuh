@@ -532,6 +532,7 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
     const int claim_base = seg_begin + warps_total * claim;            // the first warps_total * claim segments are pre-assigned
     int claimed_used = 0;
     bool tab_clean = false;                                   // S.head + S.next all zero (kept by the diagonal-hypothesis path)
+    const u8* const pf_base = (lane < 8 ? ref : tgt) + 128 * (lane & 7);      // L2 prefetch of the next pair: lanes 0-7 the reference, 8-15 the target
     int seg = seg_begin + warp_global * claim < n_iter ? seg_begin + warp_global * claim : n_iter;
     while (seg < n_iter) {
         const i64 off = (i64)seg * SEG;
@@ -577,17 +578,13 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
 #ifndef SCCG_NO_EARLY_ABORT
         // checked before every segment (the flag lives in its own cache line, away from the claim atomics): a failing
         // segment is expensive, and after the abort nothing of this launch is used (:466-472)
-        if (abort_flag) {
-            u32 stop = lane == 0 ? __ldcg(abort_flag) : 0u;                   // one lane reads, all lanes agree
-            if (__shfl_sync(SCCG_FULL_MASK, stop, 0)) next_seg = n_iter;
-        }
+        if (abort_flag && __ldcg(abort_flag)) next_seg = n_iter;              // (one load instruction of the warp: every lane sees the same value)
 #endif
         if (next_seg + 1 < n_iter && lane < 16) {             // pull the next segment (a full pair: not the last one) into L2 only: no registers held across the parse
-            const u8* pf = (lane < 8 ? ref : tgt) + (i64)next_seg * SEG + 128 * (lane & 7);
 #ifndef SCCG_EMU
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(pf));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(pf_base + (i64)next_seg * SEG));
 #else
-            (void)pf;
+            (void)pf_base;
 #endif
         }
         int nmatch = 0, covered = 0;
