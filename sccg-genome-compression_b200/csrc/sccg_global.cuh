@@ -138,19 +138,25 @@ struct GpArgs {
     const u8* T; i64 nt;          // N-stripped, upper-cased target
     const u32* keys; const u32* vals; i64 nk;
     const u32* bucket;            // bucket[b] = first index whose key >> bucket_shift is >= b (2^bits + 1 entries)
-    int bucket_shift;             // GP_HASH_BITS - bits; 0: a bucket is exactly one key value
+    int bucket_shift;             // GP_HASH_BITS - bits
     int k, m;
     int* m_tpos; int* m_p; int* m_l;   // out: matches
     u32* d_count;                      // out: number of matches
 };
 
-// first index whose key is >= h: the offset table narrows the search to one bucket (a few dozen entries)
+// first index whose key is >= h (sorted index): the offset table narrows the search to one bucket (a few dozen entries)
 __device__ __forceinline__ i64 index_lower_bound(const GpArgs& a, u32 h) {
-    i64 lo = a.bucket[h >> a.bucket_shift];
-    if (a.bucket_shift == 0) return lo;                         // the bucket IS the run of this key (empty run: keys[lo] != h)
-    i64 hi = a.bucket[(h >> a.bucket_shift) + 1];
+    const u32 b = h >> a.bucket_shift;
+    if (b >= (1u << (GP_HASH_BITS - a.bucket_shift))) return a.nk;      // h == 2^24: one past the last key
+    i64 lo = a.bucket[b];
+    i64 hi = a.bucket[b + 1];
     while (lo < hi) { i64 mid = (lo + hi) >> 1; if (a.keys[mid] < h) lo = mid + 1; else hi = mid; }
     return lo;
+}
+// vals[lo .. hi): the reference positions whose k-mer has the 24-bit hash h, ascending.  Every consumer compares the symbols.
+__device__ __forceinline__ void index_range(const GpArgs& a, u32 h, i64* lo, i64* hi) {
+    *lo = index_lower_bound(a, h);
+    *hi = index_lower_bound(a, h + 1u);
 }
 
 // length of the common prefix of R[p..] and T[j..], capped at cap (cap <= remaining lengths)
@@ -244,12 +250,11 @@ __device__ __forceinline__ void fold_chunk(GpShared& S, const GpArgs& a, i64 p, 
 __device__ __forceinline__ void fold_index_candidates(GpShared& S, const GpArgs& a, i64 j, int e) {
     fold_reset(S);
     u32 h = kmer_hash_words(ld_unaligned64(a.T + j), ld_unaligned64(a.T + j + 8), a.k);
-    const i64 lo = index_lower_bound(a, h);                      // uniform, every thread computes it
-    for (i64 base = lo;; base += GP_T) {
-        i64 idx = base + threadIdx.x;
-        bool valid = idx < a.nk && a.keys[idx] == h;
-        fold_chunk(S, a, valid ? (i64)a.vals[idx] : -1, j, e);
-        if (!__syncthreads_and(valid)) break;                    // the key range ended inside this chunk
+    i64 lo, hi;
+    index_range(a, h, &lo, &hi);                                 // uniform, every thread computes it
+    for (i64 base = lo; base < hi; base += GP_T) {
+        const i64 idx = base + threadIdx.x;
+        fold_chunk(S, a, idx < hi ? (i64)a.vals[idx] : -1, j, e);  // (fold_chunk extends from offset 0: entries of other k-mers drop out there)
     }
 }
 
@@ -272,8 +277,9 @@ __device__ __forceinline__ bool gp_step(GpShared& S, const GpArgs& a, i64& j, in
             if (pos < scan_end) {
                 u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
                 u32 h = kmer_hash_words(w0, w1, k);
-                i64 lo = index_lower_bound(a, h);
-                for (; lo < a.nk && a.keys[lo] == h && !hit; ++lo) {
+                i64 lo, hi;
+                index_range(a, h, &lo, &hi);
+                for (; lo < hi && !hit; ++lo) {
                     const u8* rp = a.R + a.vals[lo];
                     hit = kmer_equal_words(ld_unaligned64(rp), ld_unaligned64(rp + 8), w0, w1, k);
                 }
@@ -486,9 +492,10 @@ __global__ void __launch_bounds__(GP_T, SCCG_GP_MINB) gp_spec_k(GpSpecArgs s) {
                 i64 pos = Q + tid;
                 u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
                 u32 h = kmer_hash_words(w0, w1, a.k);
-                i64 lo = index_lower_bound(a, h);
+                i64 lo, hi;
+                index_range(a, h, &lo, &hi);
                 int hits = 0;
-                for (; lo < a.nk && a.keys[lo] == h && hits < 2; ++lo) {
+                for (; lo < hi && hits < 2; ++lo) {
                     const u8* rp = a.R + a.vals[lo];
                     if (kmer_equal_words(ld_unaligned64(rp), ld_unaligned64(rp + 8), w0, w1, a.k)) { ++hits; my_d = (i64)a.vals[lo] - pos; }
                 }
@@ -860,10 +867,14 @@ struct GlobalMatches { int* tpos; int* p; int* l; u32 count; };
 static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i64 nt, int k, int m, u32* sc, GlobalMatches* out) {
     if (k < 8 || k > 16) return set_error(SCCG_E_ARG, "global match_sequences supports 8 <= k <= 16");
     if (m < 0 || m > GP_MAX_M) return set_error(SCCG_E_ARG, "global match_sequences supports 0 <= m <= 120");
-    // ---- reference k-mer index (:41-47): 24-bit hash keys + stable radix sort
+    // ---- reference k-mer index (:41-47)
     SCCG_CK(cudaEventRecord(c->ev_x[0], c->stream));
     const i64 nk = nr - k + 1 > 0 ? nr - k + 1 : 0;
-    u32 *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr;
+    // 24-bit hash keys + stable radix sort: positions ascending inside every key, the reference's per-bucket order.
+    // (Measured alternative: a counting sort by hash bucket -- count, scan, fill with atomics -- needs 3.9 ms for the 59 M
+    // k-mers of the chr19-shaped pair where the three radix passes need 1.4 ms: scattered 4-byte writes and 2 x 59 M global
+    // atomics lose against coalesced tile-ordered stores.)
+    u32 *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr, *bucket = nullptr;
     SCCG_TRY(buf(c, B_GKEYS, (size_t)nk + 1, &keys));
     SCCG_TRY(buf(c, B_GVALS, (size_t)nk + 1, &vals));
     SCCG_TRY(buf(c, B_GKEYS2, (size_t)nk + 1, &keys2));
@@ -874,7 +885,6 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
         SCCG_TRY(radix_sort_pairs(c, src, keys, vals, keys2, vals2, nk, B_GHIST, GP_HASH_BITS / 8, &sk, &sv));
         keys = sk; vals = sv;
     }
-    u32* bucket = nullptr;
     int bucket_bits = gp_bucket_bits(nk);
     if (const char* env = getenv("SCCG_GP_BUCKET_BITS")) { int v = atoi(env); if (v >= 4 && v <= GP_HASH_BITS) bucket_bits = v; }    // tests: small inputs through the 24-bit path
     SCCG_TRY(buf(c, B_GBUCKET, ((size_t)1 << bucket_bits) + 2, &bucket));

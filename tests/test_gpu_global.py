@@ -144,3 +144,4 @@ def test_global_two_batch_speculation(ctx, shape, batch0, monkeypatch):
     for rep in range(3):                                     # timing varies from run to run: the result must not
         got, gmode = ctx.compress(ref, tgt, b">two batches")
         assert (gmode, got) == (mode, exp)
+
