@@ -5,7 +5,7 @@
 // tests/emu/build_emu.sh: g++ -DSCCG_EMU -- kernel LOGIC tests in the GPU-less build container.
 #include "simt_emu.h"
 #define SCCG_LAUNCH(kernel, grid, block, smem, stream, ...) \
-    emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
+    (emu::g_kernel_name = #kernel, emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); }))
 #define SCCG_DYN_SMEM(name) unsigned char* name = emu::dyn_smem()
 #define SCCG_SET_MAX_SMEM(kernel, bytes) ((void)0)
 // inter-block flags (blocks run on concurrent host threads in the emulator)

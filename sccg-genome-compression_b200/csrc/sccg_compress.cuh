@@ -15,10 +15,17 @@ enum Scalar {
 
 // writes the separator after the lowercase line and publishes where the body starts
 //   local : "<low>\n,\n<body>"   (compression.cpp:368)      global: "<low>\n<nruns>\n<body>" (:522, :555)
-__global__ void put_separators_k(u8* out, u32 hdr_bytes, u32* scalars, int global_mode) {
+// Local mode is assembled BEFORE the host knows the outcome of the matcher: out_cap is the capacity the host reserved on a
+// guess.  If the matcher aborted (-> global mode) or the body does not fit, the body base becomes BODY_BASE_NONE and the
+// writer kernels behind this one return at once; the host reads the scalars once, at the end, and repeats the assembly
+// in a larger buffer in the rare second case.
+static const u32 BODY_BASE_NONE = 0xffffffffu;
+__global__ void put_separators_k(u8* out, u32 hdr_bytes, u32* scalars, int global_mode, u32 out_cap, u32 leftover) {
     u32 low = scalars[S_LOW_TEXT];
     u8* o = out + hdr_bytes + low;
     if (!global_mode) {
+        const unsigned long long need = (unsigned long long)hdr_bytes + low + 3ull + scalars[S_BODY_MAIN] + leftover;
+        if (scalars[S_ABORT] || need > out_cap) { scalars[S_BODY_BASE] = BODY_BASE_NONE; return; }
         o[0] = '\n'; o[1] = ','; o[2] = '\n';
         scalars[S_BODY_BASE] = hdr_bytes + low + 3u;
     } else {
@@ -188,9 +195,23 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
     }
     SCCG_TRY(scan_exclusive_u32(c, seg_bytes, seg_bytes, (i64)n_iter, sc + S_BODY_MAIN));
 
-    // side lane, while the matcher runs: run count -> runs -> "<lowercase runs>" text in a staging buffer
+    // side lane, while the matcher runs: run count -> runs -> "<lowercase runs>" text, staged (the global path places it
+    // itself) and copied behind the header of the local-mode image.  The image buffer is reserved HERE, before the matcher
+    // has finished: header + run text are known, the body is a guess (what the buffer already holds from earlier pairs, at
+    // least 1/16 of the target); put_separators_k checks the guess on the device.
+    const i64 leftover = n_tseg > n_iter ? nt - (i64)n_iter * SEG : 0;        // :476-481
+    const size_t hdr_bytes = nh > 0 ? (size_t)nh + 1 : 0;
     u32 h[S_COUNT];
-    u8* low_text = nullptr;
+    u8 *low_text = nullptr, *out = nullptr;
+    size_t out_cap = 0;
+    auto reserve_out = [&](u32 low_k, size_t body) -> int {
+        const size_t want = hdr_bytes + 24ull * low_k + 3 + body + (size_t)leftover;
+        if (want >= 0xffffffffull) return set_error(SCCG_E_ARG, "encoded output would exceed 4 GiB");
+        SCCG_TRY(buf(c, B_OUT, want + 16, &out));
+        out_cap = c->bufs[B_OUT].cap - 80;                                    // buf() keeps 64 bytes of slack, we asked for 16 more
+        if (out_cap > 0xfffffff0ull) out_cap = 0xfffffff0ull;
+        return SCCG_OK;
+    };
     {
         SideLane side(c);
         SCCG_TRY(read_scalars(c, sc, h, S_COUNT));                            // synchronises the side stream only
@@ -199,55 +220,68 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
         int *run_s = nullptr, *run_e = nullptr;
         SCCG_TRY(buf(c, B_RUN_TEXT, 24ull * low_k + 16, &low_text));
         SCCG_TRY(rle_emit<0>(c, low_mask, nt, low_k, cnt_s, cnt_e, sc + S_LOW_K, B_RUN_START, B_RUN_END, B_RUN_BYTES, &run_s, &run_e, low_text, sc + S_LOW_TEXT));
+        size_t guess = (size_t)(nt / 16) + 65536;
+        const char* env = getenv("SCCG_OUT_GUESS");                           // tests: a body guess in bytes, taken literally (forces the second assembly)
+        if (env && atoll(env) >= 0) guess = (size_t)atoll(env);
+        SCCG_TRY(reserve_out(low_k, guess));
+        if (env) out_cap = hdr_bytes + 24ull * low_k + 3 + guess + (size_t)leftover;      // ... without the slack of the buffer
+        if (low_k) LAUNCH(c, copy_text_k, dim3(low_k < 4096 ? 8 : (unsigned)c->sm_count * 16u), dim3(256), 0, out + hdr_bytes, (const u8*)low_text, (const u32*)(sc + S_LOW_TEXT));
         SCCG_CK(cudaEventRecord(c->ev_side[1], c->stream));
     }
     const u32 low_k = h[S_LOW_K];
     const int text_delta = h[S_PAREN] != 0;                                   // set by rle_count_k on the side lane (finished: the host waited for it)
-    SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
-    if (h[S_ABORT]) {                                                         // :462-473 -> global (:484-574)
-        SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));
-        if (arr && arr->n > 0) SCCG_CK(cudaStreamWaitEvent(c->stream, arr->ev_ref[arr->n - 1], 0));     // the global parse reads all of the reference
-        return compress_global_device(c, d_ref, nr, d_tgt, nt, header, nh, low_k, low_text, text_delta, res);
-    }
     // a '(' somewhere in the target: tokens are written with absolute p and delta_encode is replayed at text level
     if (text_delta && n_iter > 0) {
         LAUNCH(c, seg_bytes_k, dim3(div_up(n_iter, 256)), dim3(256), 0, (const u32*)seginfo, (const u32*)matches, n_iter, seg_bytes, seg_prev, sc + S_ABORT, 1, 0, 0);
         SCCG_TRY(scan_exclusive_u32(c, seg_bytes, seg_bytes, (i64)n_iter, sc + S_BODY_MAIN));
-        SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
     }
 
-    // ---- assemble "<header>\n<lowercase runs>\n,\n<body>"
-    const i64 leftover = n_tseg > n_iter ? nt - (i64)n_iter * SEG : 0;        // :476-481
-    const size_t hdr_bytes = nh > 0 ? (size_t)nh + 1 : 0;
-    const size_t cap = hdr_bytes + 24ull * low_k + 3 + h[S_BODY_MAIN] + (size_t)leftover;
-    if (cap >= 0xffffffffull) return set_error(SCCG_E_ARG, "encoded output would exceed 4 GiB");
-    u8* out = nullptr;
-    SCCG_TRY(buf(c, B_OUT, cap + 16, &out));
-    SCCG_TRY(write_header(c, out, header, nh));
-    SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));                // the run-list text is ready
-    if (low_k) LAUNCH(c, copy_text_k, dim3(low_k < 4096 ? 8 : (unsigned)c->sm_count * 16u), dim3(256), 0, out + hdr_bytes, (const u8*)low_text, (const u32*)(sc + S_LOW_TEXT));
-    LAUNCH(c, put_separators_k, dim3(1), dim3(1), 0, out, (u32)hdr_bytes, sc, 0);
-    if (n_iter > 0) {
-        unsigned want = div_up(n_iter, 8 * 32);                              // 8 warps per CTA, 32 segments per warp
-        unsigned capg = (unsigned)c->sm_count * 8u;
-        LAUNCH(c, seg_write_k, dim3(want < capg ? want : capg), dim3(256), 0, d_tgt, nt, (const u32*)seginfo, (const u32*)matches,
-               (const u32*)seg_bytes, (const int*)seg_prev, n_iter, out, (const u32*)(sc + S_BODY_BASE), text_delta, 0);
+    // ---- assemble "<header>\n<lowercase runs>\n,\n<body>" (no host round trip between the matcher and the writers)
+    auto assemble = [&](bool place_text) -> int {
+        SCCG_TRY(write_header(c, out, header, nh));
+        if (place_text && low_k) LAUNCH(c, copy_text_k, dim3(low_k < 4096 ? 8 : (unsigned)c->sm_count * 16u), dim3(256), 0, out + hdr_bytes, (const u8*)low_text, (const u32*)(sc + S_LOW_TEXT));
+        LAUNCH(c, put_separators_k, dim3(1), dim3(1), 0, out, (u32)hdr_bytes, sc, 0, (u32)out_cap, (u32)leftover);
+        if (n_iter > 0) {
+            unsigned want = div_up(n_iter, 8 * 32);                              // 8 warps per CTA, 32 segments per warp
+            unsigned capg = (unsigned)c->sm_count * 8u;
+            LAUNCH(c, seg_write_k, dim3(want < capg ? want : capg), dim3(256), 0, d_tgt, nt, (const u32*)seginfo, (const u32*)matches,
+                   (const u32*)seg_bytes, (const int*)seg_prev, n_iter, out, (const u32*)(sc + S_BODY_BASE), text_delta, 0);
+        }
+        if (leftover > 0) {
+            unsigned g = div_up(leftover, 256 * 16);
+            unsigned capg = (unsigned)c->sm_count * 8u;
+            LAUNCH(c, upper_copy_k, dim3(g < capg ? g : capg), dim3(256), 0, d_tgt + (i64)n_iter * SEG, leftover, out,
+                   (const u32*)(sc + S_BODY_BASE), 0u, (const u32*)(sc + S_BODY_MAIN));
+        }
+        SCCG_CK(cudaEventRecord(c->ev[3], c->stream));
+        return read_scalars(c, sc, h, S_COUNT);
+    };
+    const bool step_trace = getenv("SCCG_STEP_TRACE") != nullptr;             // development aid: where the step's time goes
+    if (step_trace) SCCG_CK(cudaEventRecord(c->ev_x[0], c->stream));
+    SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));                // the run-list text is in place
+    if (step_trace) SCCG_CK(cudaEventRecord(c->ev_x[1], c->stream));
+    SCCG_TRY(assemble(false));
+    if (step_trace) {
+        float a = 0, b = 0, d = 0, e = 0, f = 0;
+        cudaEventElapsedTime(&a, c->ev[0], c->ev[1]); cudaEventElapsedTime(&b, c->ev[1], c->ev[2]); cudaEventElapsedTime(&d, c->ev[2], c->ev_x[0]);
+        cudaEventElapsedTime(&e, c->ev_x[0], c->ev_x[1]); cudaEventElapsedTime(&f, c->ev_x[1], c->ev[3]);
+        fprintf(stderr, "step_trace: pre %.1f us, matcher %.1f, sizes %.1f, wait for the run-list lane %.1f, writers %.1f\n", a * 1e3, b * 1e3, d * 1e3, e * 1e3, f * 1e3);
     }
-    if (leftover > 0) {
-        unsigned g = div_up(leftover, 256 * 16);
-        unsigned capg = (unsigned)c->sm_count * 8u;
-        LAUNCH(c, upper_copy_k, dim3(g < capg ? g : capg), dim3(256), 0, d_tgt + (i64)n_iter * SEG, leftover, out,
-               (const u32*)(sc + S_BODY_BASE), h[S_BODY_MAIN]);
+    if (h[S_ABORT]) {                                                         // :462-473 -> global (:484-574)
+        if (arr && arr->n > 0) SCCG_CK(cudaStreamWaitEvent(c->stream, arr->ev_ref[arr->n - 1], 0));     // the global parse reads all of the reference
+        return compress_global_device(c, d_ref, nr, d_tgt, nt, header, nh, low_k, low_text, text_delta, res);
     }
-    SCCG_CK(cudaEventRecord(c->ev[3], c->stream));
-    u32 h2[8];
-    SCCG_TRY(read_scalars(c, sc, h2, 8));
+    if (h[S_BODY_BASE] == BODY_BASE_NONE) {                                   // the guess was too small: now the size is known
+        SCCG_TRY(reserve_out(low_k, (size_t)h[S_BODY_MAIN]));
+        SCCG_TRY(assemble(true));
+        if (h[S_BODY_BASE] == BODY_BASE_NONE) return set_error(SCCG_E_CUDA, "internal: the encoded image does not fit its buffer");
+    }
     res->d_out = out;
-    res->out_len = (i64)hdr_bytes + h2[S_LOW_TEXT] + 3 + h[S_BODY_MAIN] + leftover;
+    res->out_len = (i64)hdr_bytes + h[S_LOW_TEXT] + 3 + h[S_BODY_MAIN] + leftover;
     res->mode = 0;
     res->stoi_failed = 0;
     if (text_delta) {
-        SCCG_TRY(finish_text_delta(c, sc, (u32)(hdr_bytes + h2[S_LOW_TEXT] + 3), res));
+        SCCG_TRY(finish_text_delta(c, sc, (u32)(hdr_bytes + h[S_LOW_TEXT] + 3), res));
         SCCG_CK(cudaEventRecord(c->ev[3], c->stream));
         SCCG_CK(cudaStreamSynchronize(c->stream));
     }

@@ -1046,7 +1046,7 @@ static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8
     SCCG_TRY(buf(c, B_NRUN_TEXT, 24ull * n_k + 16, &ntext));
     SCCG_TRY(rle_emit<1>(c, n_mask, nt, n_k, ncnt_s, ncnt_e, sc + S_N_K, B_NRUN_START, B_NRUN_END, B_NRUN_BYTES, &nrun_s, &nrun_e,
                          ntext, sc + S_N_TEXT));
-    LAUNCH(c, put_separators_k, dim3(1), dim3(1), 0, out, (u32)hdr_bytes, sc, 1);
+    LAUNCH(c, put_separators_k, dim3(1), dim3(1), 0, out, (u32)hdr_bytes, sc, 1, 0u, 0u);
     SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
     const u32 low_text = h[S_LOW_TEXT], n_text = h[S_N_TEXT];
     if (n_text) SCCG_CK(cudaMemcpyAsync(out + hdr_bytes + low_text + 1, ntext, n_text, cudaMemcpyDeviceToDevice, c->stream));

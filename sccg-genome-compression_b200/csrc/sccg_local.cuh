@@ -578,7 +578,9 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
 #ifndef SCCG_NO_EARLY_ABORT
         // checked before every segment (the flag lives in its own cache line, away from the claim atomics): a failing
         // segment is expensive, and after the abort nothing of this launch is used (:466-472)
-        if (abort_flag && __ldcg(abort_flag)) next_seg = n_iter;              // (one load instruction of the warp: every lane sees the same value)
+        // (the vote makes the decision warp-uniform by construction: lanes that disagreed about the flag would leave the loop
+        // at different segments and hang the collectives below)
+        if (abort_flag && __any_sync(SCCG_FULL_MASK, __ldcg(abort_flag) != 0u)) next_seg = n_iter;
 #endif
         if (next_seg + 1 < n_iter && lane < 16) {             // pull the next segment (a full pair: not the last one) into L2 only: no registers held across the parse
 #ifndef SCCG_EMU
@@ -794,6 +796,7 @@ __global__ void __launch_bounds__(256) seg_write_k(const u8* __restrict__ tgt, i
                                                    u8* __restrict__ out, const u32* __restrict__ d_body_base, int absolute, int seg_base) {
     const int lane = lane_of();
     const int warps_total = (int)(gridDim.x * (blockDim.x >> 5));
+    if (*d_body_base == 0xffffffffu) return;                       // BODY_BASE_NONE: no local-mode image (abort) or not in this buffer
     u8* body = out + *d_body_base;
     for (int seg0 = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; seg0 < n_iter; seg0 += warps_total * 32) {
         const int seg = seg0 + lane;
@@ -833,8 +836,9 @@ __global__ void __launch_bounds__(256) seg_write_k(const u8* __restrict__ tgt, i
 }
 
 // out[i] = toupper(src[i])  (leftover target segments, compression.cpp:476-481; global literals)
-__global__ void upper_copy_k(const u8* __restrict__ src, i64 n, u8* __restrict__ out, const u32* __restrict__ d_base, u32 extra) {
-    u8* dst = out + (d_base ? *d_base : 0u) + extra;
+__global__ void upper_copy_k(const u8* __restrict__ src, i64 n, u8* __restrict__ out, const u32* __restrict__ d_base, u32 extra, const u32* __restrict__ d_extra) {
+    if (d_base && *d_base == 0xffffffffu) return;                  // BODY_BASE_NONE (see put_separators_k)
+    u8* dst = out + (d_base ? *d_base : 0u) + extra + (d_extra ? *d_extra : 0u);
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) dst[i] = upper1(src[i]);
 }
 

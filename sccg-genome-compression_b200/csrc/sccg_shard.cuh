@@ -208,7 +208,7 @@ static int shard_write_body(sccg_ctx* c, u32 body_main, u8** d_body, i64* body_l
     }
     if (st.leftover > 0 && st.is_last) {                                      // :476-481 (only the last shard can have leftover target segments)
         unsigned g = div_up(st.leftover, 256 * 16), capg = (unsigned)c->sm_count * 8u;
-        LAUNCH(c, upper_copy_k, dim3(g < capg ? g : capg), dim3(256), 0, st.d_tgt + (i64)n_iter * SEG, st.leftover, out, (const u32*)(sc + S_BODY_BASE), body_main);
+        LAUNCH(c, upper_copy_k, dim3(g < capg ? g : capg), dim3(256), 0, st.d_tgt + (i64)n_iter * SEG, st.leftover, out, (const u32*)(sc + S_BODY_BASE), body_main, (const u32*)nullptr);
     }
     *d_body = out; *body_len = (i64)body_main + (st.is_last ? st.leftover : 0);
     st.valid = 0;

@@ -34,6 +34,7 @@ emu_ctx_switch:
 
 namespace emu {
 thread_local BlockCtx* g_blk = nullptr;
+const char* g_kernel_name = "?";
 
 static const size_t kStackBytes = 64 * 1024;
 
@@ -177,7 +178,7 @@ static void run_block(Worker& w, dim3 grid, dim3 block, uint3 bidx, size_t smem_
             emu_ctx_switch(&b.sched_sp, f.sp);
         }
         if (b.progress == before && b.alive > 0) {
-            fprintf(stderr, "[simt_emu] deadlock in block (%u,%u,%u): %d threads alive, barrier count %d, sweep %llu\n", bidx.x, bidx.y, bidx.z, b.alive, b.bar_count, sweeps);
+            fprintf(stderr, "[simt_emu] %s: deadlock in block (%u,%u,%u): %d threads alive, barrier count %d, sweep %llu\n", g_kernel_name, bidx.x, bidx.y, bidx.z, b.alive, b.bar_count, sweeps);
             fail("deadlock (divergent barrier / collective with exited or non-arriving lanes)");
         }
         ++sweeps;

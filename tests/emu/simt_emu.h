@@ -83,6 +83,7 @@ struct BlockCtx {
 extern thread_local BlockCtx* g_blk;
 
 void yield();
+extern const char* g_kernel_name;      // diagnostics: the kernel of the current launch
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body);
 Slot* collective_arrive(uint32_t mask, uint64_t val);   // blocks until every lane of mask arrived
 void collective_release(Slot* s);

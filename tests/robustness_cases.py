@@ -152,3 +152,39 @@ def check_decoder_tolerance(ctx):
     with pytest.raises(sccg_b200.SccgError) as e:
         ctx.reconstruct(ref, b"AC(10,-3)GT", b"", b"")
     assert e.value.code == sccg_b200.SCCG_E_FORMAT, str(e.value)
+
+
+def check_output_guess(make_ctx, monkeypatch):
+    """compress_device assembles the local-mode image into a buffer whose size is a GUESS made before the matcher has finished
+    (no host round trip in between); the device refuses a guess that is too small and the host assembles again.  Forced
+    here with a guess of 0 bytes on fresh contexts: plain local pair with a leftover tail, a target with literal '('
+    (text-level delta pass), a pair that falls back to global mode; then the same context again with the normal guess."""
+    import random
+    from sccg_genome_compression_b200 import synth
+    ref, tgt = synth.local_pair(60_000, synth.seed_for(2, 41))
+    ref, tgt = ref.tobytes(), tgt.tobytes()
+    r = random.Random(41)
+    paren = bytearray(tgt)
+    for piece in (b"(12,3)", b"(", b")(7,", b"(5,"):
+        at = r.randrange(0, len(paren) - 16); paren[at:at + len(piece)] = piece
+    gref, gtgt = synth.global_gap_pair(90_000, 80_000, synth.seed_for(1, 41))
+    pairs = [(ref, tgt + rnd(2500, "tail")), (ref, bytes(paren) + b"(ACGT"), (gref.tobytes(), gtgt.tobytes()), (ref[:999], tgt[:700]), (b"", tgt[:100])]
+    for rf, tg in pairs:
+        rc, exp, mode = ol.orc_compress(rf, tg, b">guess")
+        for guess in ("0", "17", None):
+            ctx = make_ctx()
+            try:
+                if guess is None: monkeypatch.delenv("SCCG_OUT_GUESS", raising=False)
+                else: monkeypatch.setenv("SCCG_OUT_GUESS", guess)
+                for _ in range(2):                                                   # second call: the buffer has grown, the env guess still applies
+                    if rc != 0:
+                        with pytest.raises(sccg_b200.SccgError) as e:
+                            ctx.compress(rf, tg, b">guess")
+                        assert e.value.code == sccg_b200.SCCG_E_STOI and e.value.partial == exp
+                    else:
+                        assert ctx.compress(rf, tg, b">guess") == (exp, mode)
+                monkeypatch.delenv("SCCG_OUT_GUESS", raising=False)
+                if rc == 0:
+                    assert ctx.compress(rf, tg, b">guess") == (exp, mode)
+            finally:
+                ctx.close()

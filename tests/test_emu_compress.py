@@ -436,3 +436,8 @@ def test_resident_reference_round_trips(ctx, monkeypatch):
     ctx.clear_reference()
     with pytest.raises(Exception):
         ctx.decompress_resident(got)
+
+
+def test_output_buffer_guess_too_small(monkeypatch):
+    import robustness_cases
+    robustness_cases.check_output_guess(emu_context, monkeypatch)

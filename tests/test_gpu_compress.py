@@ -233,3 +233,9 @@ def test_two_contexts_two_threads():
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_output_buffer_guess_too_small(monkeypatch):
+    import robustness_cases
+    import sccg_b200
+    robustness_cases.check_output_guess(lambda: sccg_b200.Context(0), monkeypatch)
