@@ -188,3 +188,46 @@ def check_output_guess(make_ctx, monkeypatch):
                     assert ctx.compress(rf, tg, b">guess") == (exp, mode)
             finally:
                 ctx.close()
+
+
+def check_lowercase_line_shapes(ctx):
+    """the lowercase-run line (compression.cpp:341-367) on shapes that stress tile and word borders of the run-list kernels: runs
+    that span several tiles, tiles without any run between two runs, one-symbol runs on 64-symbol word and tile borders, a run
+    that ends with the sequence, no run at all / everything lowercase"""
+    import random
+    r = random.Random(20261018)
+    T = 131072
+    def build(n, runs):
+        t = bytearray(rnd(n, ("lowline", n)))
+        for a, b in runs:
+            t[a:b] = bytes(t[a:b]).lower()
+        return bytes(t)
+    shapes = []
+    n = 5 * T + 777
+    shapes.append((n, [(100, 4 * T + 5)]))                                        # one run over four tile borders
+    shapes.append((n, [(T - 1, T), (T, T + 1)]))                                  # (adjacent: really one run of two over the border)
+    shapes.append((n, [(T - 1, T), (T + 1, T + 2), (2 * T - 1, 2 * T + 1), (3 * T + 63, 3 * T + 64), (3 * T + 64, 3 * T + 66)]))
+    shapes.append((n, [(5, 6), (4 * T + 700, 4 * T + 701)]))                      # three empty tiles between two one-symbol runs
+    shapes.append((n, [(0, 1), (n - 1, n)]))                                      # first and last symbol
+    shapes.append((n, [(0, n)]))                                                  # everything
+    shapes.append((n, []))                                                        # nothing
+    shapes.append((n, [(2 * T + 64 * k, 2 * T + 64 * k + 63) for k in range(40)]))  # a run in every chunk, ending one before the chunk border
+    shapes.append((n, [(63 + 64 * k, 65 + 64 * k) for k in range(0, 600, 3)]))    # runs across chunk borders
+    shapes.append((n, [(n - 3, n)]))                                              # ends with the sequence (longer than one symbol)
+    shapes.append((T, [(T - 1, T)]))                                              # exactly one tile, last symbol
+    shapes.append((3 * T, [(T, 2 * T)]))                                          # tile-aligned run
+    for _ in range(6):                                                            # random mixtures, many tiles
+        n = r.randrange(2 * T, 5 * T)
+        runs, p = [], 0
+        while p < n:
+            p += r.choice([1, 2, 7, 64, 500, 20000, 140000])
+            ln = r.choice([1, 1, 2, 3, 63, 64, 65, 1000, 17000, 135000, 270000])
+            if p < n: runs.append((p, min(n, p + ln)))
+            p += ln
+        shapes.append((n, runs))
+    for n, runs in shapes:
+        tgt = build(n, runs)
+        ref = tgt.upper()
+        rc, exp, mode = ol.orc_compress(ref, tgt, b">low")
+        assert rc == 0 and mode == 0
+        assert ctx.compress(ref, tgt, b">low") == (exp, mode), (n, runs[:4])

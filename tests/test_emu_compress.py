@@ -441,3 +441,12 @@ def test_resident_reference_round_trips(ctx, monkeypatch):
 def test_output_buffer_guess_too_small(monkeypatch):
     import robustness_cases
     robustness_cases.check_output_guess(emu_context, monkeypatch)
+
+
+def test_lowercase_line_shapes(sweep_order):
+    import robustness_cases
+    c = emu_context()
+    try:
+        robustness_cases.check_lowercase_line_shapes(c)
+    finally:
+        c.close()

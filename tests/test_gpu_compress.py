@@ -239,3 +239,8 @@ def test_output_buffer_guess_too_small(monkeypatch):
     import robustness_cases
     import sccg_b200
     robustness_cases.check_output_guess(lambda: sccg_b200.Context(0), monkeypatch)
+
+
+def test_lowercase_line_shapes(ctx):
+    import robustness_cases
+    robustness_cases.check_lowercase_line_shapes(ctx)
