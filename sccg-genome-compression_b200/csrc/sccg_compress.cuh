@@ -245,7 +245,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
             unsigned want = div_up(n_iter, 8 * 32);                              // 8 warps per CTA, 32 segments per warp
             unsigned capg = (unsigned)c->sm_count * 8u;
             LAUNCH(c, seg_write_k, dim3(want < capg ? want : capg), dim3(256), 0, d_tgt, nt, (const u32*)seginfo, (const u32*)matches,
-                   (const u32*)seg_bytes, (const int*)seg_prev, n_iter, out, (const u32*)(sc + S_BODY_BASE), text_delta, 0);
+                   (const u32*)seg_bytes, (const int*)seg_prev, n_iter, out, (const u32*)(sc + S_BODY_BASE), text_delta, 0, (const u32*)(sc + S_BODY_MAIN));
         }
         if (leftover > 0) {
             unsigned g = div_up(leftover, 256 * 16);

@@ -204,7 +204,7 @@ static int shard_write_body(sccg_ctx* c, u32 body_main, u8** d_body, i64* body_l
     if (n_iter > 0) {
         unsigned want = div_up(n_iter, 8 * 32), capg = (unsigned)c->sm_count * 8u;
         LAUNCH(c, seg_write_k, dim3(want < capg ? want : capg), dim3(256), 0, st.d_tgt, st.nt, (const u32*)seginfo, (const u32*)matches,
-               (const u32*)seg_bytes, (const int*)seg_prev, n_iter, out, (const u32*)(sc + S_BODY_BASE), 0, (int)st.seg_base);
+               (const u32*)seg_bytes, (const int*)seg_prev, n_iter, out, (const u32*)(sc + S_BODY_BASE), 0, (int)st.seg_base, (const u32*)(sc + S_BODY_MAIN));
     }
     if (st.leftover > 0 && st.is_last) {                                      // :476-481 (only the last shard can have leftover target segments)
         unsigned g = div_up(st.leftover, 256 * 16), capg = (unsigned)c->sm_count * 8u;
