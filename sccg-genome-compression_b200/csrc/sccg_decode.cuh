@@ -180,50 +180,90 @@ __global__ void __launch_bounds__(DEC_T) dec_emit_k(const u8* __restrict__ enc, 
 // ------------------------------------------------------------------------------------------------
 // run lists (decompression.cpp:126-207): "(d,len)" | "d," | "d"
 // ------------------------------------------------------------------------------------------------
-__global__ void runs_classify_k(const u8* __restrict__ s, i64 n, u32* __restrict__ isitem, u32* __restrict__ sc) {
-    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    u8 c = s[i];
-    bool inside = inside_token(s, i);
-    u32 item = 0;
-    if (inside) {
-        if (!(is_digit(c) || c == '-' || c == ',' || c == ')')) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);
-    } else if (c == '(') {
-        int d, l;
-        if (!parse_tuple(s, i, n, &d, &l) || l < 0) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);
-        item = 1;
-    } else if (is_digit(c) || c == '-') {
-        bool start = (i == 0) || !(is_digit(s[i - 1]) || s[i - 1] == '-');
-        if (start) {
-            int d;
-            int w = parse_int(s, i, n, &d);
-            if (!w || (i + w < n && s[i + w] != ',')) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);
-            item = 1;
+// 16 bytes of the list per thread, classified on bit masks like the body tokenizer above (a thread per byte and a flag word per
+// byte cost 19 + 13 + 18 us on the 1.5 MB list of a chr1-sized file).  Same grammar checks as the reference's stoi / substr
+// calls would make (decompression.cpp:126-207):
+//   inside "(...)"  : digits, '-', ',' and the closing ')' only
+//   outside         : '(' starts a tuple "(d,len)", len >= 0; a digit or '-' whose predecessor is neither starts a single "d"
+//                     that must be followed by ',' or the end; ',' must follow a digit or ')'; nothing else
+struct RunChunk { u32 items, tuples, err; };      // bit b <=> byte i0 + b: item start / tuple start / grammar error
+__device__ __forceinline__ u64 digit_flags8(u64 w) {
+    u64 x = w & SCCG_B7F;
+    u64 ge = x + (u64)(0x80 - '0') * SCCG_B01, gt = x + (u64)(0x80 - '9' - 1) * SCCG_B01;
+    return ge & ~gt & ~w & SCCG_B80;
+}
+__device__ __forceinline__ u32 eq_mask16(u64 lo, u64 hi, u8 ch) { return movemask8(eq_flags8(lo, ch)) | (movemask8(eq_flags8(hi, ch)) << 8); }
+// s may have any alignment (it points into the file image); i0 is a multiple of 16 and < n; 16 readable bytes past n
+__device__ __forceinline__ RunChunk run_chunk(const u8* __restrict__ s, i64 n, i64 i0) {
+    const u64 a0 = ld_unaligned64(s + i0), a1 = ld_unaligned64(s + i0 + 8);
+    const i64 left = n - i0;
+    const u32 V = left >= 16 ? 0xffffu : ((1u << (int)left) - 1u);
+    const u32 O = eq_mask16(a0, a1, '(') & V, C = eq_mask16(a0, a1, ')') & V, M = eq_mask16(a0, a1, ',') & V;
+    const u32 Dg = (movemask8(digit_flags8(a0)) | (movemask8(digit_flags8(a1)) << 8)) & V;
+    const u32 D = Dg | (eq_mask16(a0, a1, '-') & V);
+    u32 Op = 0, Cp = 0;                                       // the 32 bytes before the chunk (bit j <=> byte i0 - 32 + j)
+    if (i0 >= 16) {
+        const u64 p2 = ld_unaligned64(s + i0 - 16), p3 = ld_unaligned64(s + i0 - 8);
+        Op = eq_mask16(p2, p3, '(') << 16; Cp = eq_mask16(p2, p3, ')') << 16;
+        if (i0 >= 32) {
+            const u64 p0 = ld_unaligned64(s + i0 - 32), p1 = ld_unaligned64(s + i0 - 24);
+            Op |= eq_mask16(p0, p1, '('); Cp |= eq_mask16(p0, p1, ')');
         }
-    } else if (c == ',') {
-        // separator after a single, or the optional one after a tuple (:143-144)
-        if (i == 0 || !(is_digit(s[i - 1]) || s[i - 1] == ')')) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);
-    } else {
-        atomicOr(&sc[D_ERR], (u32)DE_FORMAT);
     }
-    isitem[i] = item;
+    bool in = (Op & 0xffffff80u) > (Cp & 0xffffff80u);        // inside_token(i0)
+    u32 inside = 0;
+    int last = 0;
+    for (u32 pp = O | C; pp; pp &= pp - 1) {
+        const int b = __ffs((int)pp) - 1;
+        const bool is_open = (O >> b) & 1u;
+        if (in) { inside |= (2u << b) - (1u << last); if (!is_open) in = false; }
+        else if (is_open) in = true;
+        last = b + 1;
+    }
+    if (in) inside |= 0x10000u - (1u << last);
+    inside &= V;
+    const u8 pb = i0 > 0 ? s[i0 - 1] : (u8)0;
+    const u32 p_dg = is_digit(pb) ? 1u : 0u, p_dl = (is_digit(pb) || pb == '-') ? 1u : 0u, p_cl = pb == ')' ? 1u : 0u;
+    RunChunk c;
+    c.tuples = O & ~inside;
+    const u32 lit = V & ~inside & ~c.tuples;
+    c.items = c.tuples | (lit & D & ~((D << 1) | p_dl));
+    c.err = (inside & ~(D | M | C)) | (lit & ~(D | M)) | (lit & M & ~((Dg << 1) | p_dg | (C << 1) | p_cl));
+    return c;
 }
 
-__global__ void runs_compact_k(const u8* __restrict__ s, i64 n, const u32* __restrict__ itemidx, int* __restrict__ delta, int* __restrict__ len) {
-    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    u8 c = s[i];
-    if (inside_token(s, i)) return;
-    if (c == '(') {
+static const int RUNS_T = 256;
+__global__ void __launch_bounds__(RUNS_T) runs_count16_k(const u8* __restrict__ s, i64 n, u32* __restrict__ cnt, u32* __restrict__ masks, u32* __restrict__ sc) {
+    const i64 t = (i64)blockIdx.x * RUNS_T + threadIdx.x;
+    const i64 i0 = t * 16;
+    if (i0 >= n) return;
+    const RunChunk c = run_chunk(s, n, i0);
+    bool bad = c.err != 0u;
+    for (u32 m = c.items; m; m &= m - 1) {
+        const int b = __ffs((int)m) - 1;
         int d = 0, l = 0;
-        if (!parse_tuple(s, i, n, &d, &l)) return;
-        delta[itemidx[i]] = d; len[itemidx[i]] = l;
-    } else if (is_digit(c) || c == '-') {
-        bool start = (i == 0) || !(is_digit(s[i - 1]) || s[i - 1] == '-');
-        if (!start) return;
-        int d = 0;
-        if (!parse_int(s, i, n, &d)) return;
-        delta[itemidx[i]] = d; len[itemidx[i]] = 1;
+        if ((c.tuples >> b) & 1u) { if (!parse_tuple(s, i0 + b, n, &d, &l) || l < 0) bad = true; }
+        else { const int w = parse_int(s, i0 + b, n, &d); if (!w || (i0 + b + w < n && s[i0 + b + w] != ',')) bad = true; }
+    }
+    if (bad) atomicOr(&sc[D_ERR], (u32)DE_FORMAT);
+    cnt[t] = (u32)__popc(c.items);
+    masks[t] = c.items | (c.tuples << 16);
+}
+// cnt holds the exclusive prefix by now
+__global__ void __launch_bounds__(RUNS_T) runs_emit16_k(const u8* __restrict__ s, i64 n, const u32* __restrict__ cnt, const u32* __restrict__ masks,
+                                                        int* __restrict__ delta, int* __restrict__ len) {
+    const i64 t = (i64)blockIdx.x * RUNS_T + threadIdx.x;
+    const i64 i0 = t * 16;
+    if (i0 >= n) return;
+    const u32 mk = masks[t];
+    u32 k = cnt[t];
+    for (u32 m = mk & 0xffffu; m; m &= m - 1) {
+        const int b = __ffs((int)m) - 1;
+        int d = 0, l = 1;
+        if ((mk >> (16 + b)) & 1u) { if (!parse_tuple(s, i0 + b, n, &d, &l)) { d = 0; l = 0; } }   // (validated by runs_count16_k; the caller does not get here after an error)
+        else if (!parse_int(s, i0 + b, n, &d)) { d = 0; l = 0; }
+        delta[k] = d; len[k] = l;
+        ++k;
     }
 }
 
@@ -255,11 +295,13 @@ static int parse_runs(sccg_ctx* c, const u8* d_text, i64 n, int slot_base, u32* 
         SCCG_TRY(buf(c, slot_base + 3, 4, &out->cum));
         return SCCG_OK;
     }
-    u32* isitem = nullptr;
-    SCCG_TRY(buf(c, slot_base, (size_t)n + 1, &isitem));
-    unsigned g = div_up(n, 256);
-    LAUNCH(c, runs_classify_k, dim3(g), dim3(256), 0, d_text, n, isitem, sc);
-    SCCG_TRY(scan_exclusive_u32(c, isitem, isitem, n, sc + sc_items));
+    const i64 nch = (n + 15) / 16;
+    u32* cnt = nullptr;
+    SCCG_TRY(buf(c, slot_base, (size_t)nch * 2 + 2, &cnt));
+    u32* masks = cnt + nch + 1;
+    unsigned g = div_up(nch, RUNS_T);
+    LAUNCH(c, runs_count16_k, dim3(g), dim3(RUNS_T), 0, d_text, n, cnt, masks, sc);
+    SCCG_TRY(scan_exclusive_u32(c, cnt, cnt, nch, sc + sc_items));
     u32 h[D_COUNT];
     SCCG_TRY(read_scalars(c, sc, h, D_COUNT));
     if (h[D_ERR] & DE_HARD) return set_error(SCCG_E_FORMAT, "malformed run list (the reference would throw from stoi or misbehave)");
@@ -273,7 +315,7 @@ static int parse_runs(sccg_ctx* c, const u8* d_text, i64 n, int slot_base, u32* 
     SCCG_TRY(buf(c, B_TILE1, (size_t)K + 1, &excl));
     out->K = K;
     if (K == 0) return SCCG_OK;
-    LAUNCH(c, runs_compact_k, dim3(g), dim3(256), 0, d_text, n, (const u32*)isitem, delta, out->len);
+    LAUNCH(c, runs_emit16_k, dim3(g), dim3(RUNS_T), 0, d_text, n, (const u32*)cnt, (const u32*)masks, delta, out->len);
     SCCG_TRY(scan_exclusive_u32(c, (const u32*)delta, excl, (i64)K, nullptr));
     LAUNCH(c, runs_finish_k, dim3(div_up(K, 256)), dim3(256), 0, (const int*)delta, (const int*)out->len, (const u32*)excl, K, out->start, sc, soft_bit);
     SCCG_TRY(scan_exclusive_u32(c, (const u32*)out->len, out->cum, (i64)K, sc_sum));

@@ -104,8 +104,10 @@ def check_streaming_and_fasta_into(ctx, chunk_env=None):
 def check_decoder_tolerance(ctx):
     """streams the reference accepts although no compressor writes them (decompression.cpp:126-207 expands the run lists into
     positions and SORTS them; an out-of-range lowercase position is only a warning, :255-262): same bytes as the oracle.
-    Streams on which the reference runs into undefined behaviour or throws are errors in both.  The ONE pinned divergence is
-    a negative token length (`substr` wraps to "rest of the reference" there, SCCG_E_FORMAT here)."""
+    Streams on which the reference runs into undefined behaviour or throws are errors in both.  Two pinned divergences
+    (INTEGRATION.md section 5): a negative token length (`substr` wraps to "rest of the reference" there, SCCG_E_FORMAT here),
+    and run-list TEXT outside the grammar that the reference's find / stoi splitter happens to digest (stoi ignores what follows
+    a number: "38,1)3,36," reads as 38, 1, 36 there; SCCG_E_FORMAT here)."""
     import random
     ref = rnd(6000, "tol")
     body = b"(0,1000)ACGT(1000,2000)TT(2100,1500)"
@@ -152,6 +154,13 @@ def check_decoder_tolerance(ctx):
     with pytest.raises(sccg_b200.SccgError) as e:
         ctx.reconstruct(ref, b"AC(10,-3)GT", b"", b"")
     assert e.value.code == sccg_b200.SCCG_E_FORMAT, str(e.value)
+    for low in (b"38,1)3,36,", b"(20,17)(41,1)(3,17)(23(,1)", b"12,(41,3,(36,1)4,", b"5,,7,"):
+        rc_o, _ = ol.orc_reconstruct(ref, body, b"", low)
+        assert rc_o == 0, low                                                # stoi stops at the first non-digit, find(')') / find(',') skip ahead
+        with pytest.raises(sccg_b200.SccgError) as e:
+            ctx.reconstruct(ref, body, b"", low)
+        assert e.value.code == sccg_b200.SCCG_E_FORMAT, (low, str(e.value))
+    assert ctx.reconstruct(ref, body, b"", b"(50,10)") == ol.orc_reconstruct(ref, body, b"", b"(50,10)")[1]      # the context survived
 
 
 def check_output_guess(make_ctx, monkeypatch):
