@@ -992,6 +992,8 @@ static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8
                                   u32 low_k, const u8* d_low_text, int text_delta, CompressResult* res) {
     u32* sc = nullptr;
     SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
+    const bool step_trace = getenv("SCCG_STEP_TRACE") != nullptr;             // development aid: where the call's time goes
+    if (step_trace) SCCG_CK(cudaEventRecord(c->ev_side[2], c->stream));
     // ---- N runs of the upper-cased target, original coordinates (:527-554): count
     u32 *ncnt_s = nullptr, *ncnt_e = nullptr;
     u64* n_mask = nullptr;
@@ -1027,28 +1029,27 @@ static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8
         SCCG_CK(cudaMemcpyAsync(&last[0], gm.tpos + (M - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         SCCG_CK(cudaMemcpyAsync(&last[1], gm.l + (M - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     }
-    SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
-    const i64 trailing = nt2 - ((i64)last[0] + (i64)last[1]);
-    const u64 body_bytes = (u64)h[S_G4] + (u64)trailing;
-
-    // ---- assemble "<header>\n<lowercase runs>\n<N runs>\n<body>"
-    const size_t hdr_bytes = nh > 0 ? (size_t)nh + 1 : 0;
-    const size_t cap = hdr_bytes + 24ull * low_k + 1 + 24ull * n_k + 1 + body_bytes;
-    if (cap >= 0xffffffffull) return set_error(SCCG_E_ARG, "encoded output would exceed 4 GiB");
-    u8* out = nullptr;
-    SCCG_TRY(buf(c, B_OUT, cap + 16, &out));
-    SCCG_TRY(write_header(c, out, header, nh));
+    // the N-run text (staged: its place in the image depends on the length of the lowercase text)
     int *nrun_s = nullptr, *nrun_e = nullptr;
-    // the lowercase-run text was produced on the side lane of compress_device (sc[S_LOW_TEXT] holds its length)
-    if (low_k) LAUNCH(c, copy_text_k, dim3(low_k < 4096 ? 8 : (unsigned)c->sm_count * 16u), dim3(256), 0, out + hdr_bytes, d_low_text, (const u32*)(sc + S_LOW_TEXT));
-    // the N-run text goes right after "<low>\n": its position depends on the (device-side) length of the lowercase text
     u8* ntext = nullptr;
     SCCG_TRY(buf(c, B_NRUN_TEXT, 24ull * n_k + 16, &ntext));
     SCCG_TRY(rle_emit<1>(c, n_mask, nt, n_k, ncnt_s, ncnt_e, sc + S_N_K, B_NRUN_START, B_NRUN_END, B_NRUN_BYTES, &nrun_s, &nrun_e,
                          ntext, sc + S_N_TEXT));
-    LAUNCH(c, put_separators_k, dim3(1), dim3(1), 0, out, (u32)hdr_bytes, sc, 1, 0u, 0u);
-    SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
+    SCCG_TRY(read_scalars(c, sc, h, S_COUNT));                    // body size and the lengths of both run-list texts, one round trip
+    const i64 trailing = nt2 - ((i64)last[0] + (i64)last[1]);
+    const u64 body_bytes = (u64)h[S_G4] + (u64)trailing;
     const u32 low_text = h[S_LOW_TEXT], n_text = h[S_N_TEXT];
+
+    // ---- assemble "<header>\n<lowercase runs>\n<N runs>\n<body>"
+    const size_t hdr_bytes = nh > 0 ? (size_t)nh + 1 : 0;
+    const size_t cap = hdr_bytes + (size_t)low_text + 1 + (size_t)n_text + 1 + body_bytes;
+    if (cap >= 0xffffffffull) return set_error(SCCG_E_ARG, "encoded output would exceed 4 GiB");
+    u8* out = nullptr;
+    SCCG_TRY(buf(c, B_OUT, cap + 16, &out));
+    SCCG_TRY(write_header(c, out, header, nh));
+    // the lowercase-run text was produced on the side lane of compress_device (sc[S_LOW_TEXT] holds its length)
+    if (low_k) LAUNCH(c, copy_text_k, dim3(low_k < 4096 ? 8 : (unsigned)c->sm_count * 16u), dim3(256), 0, out + hdr_bytes, d_low_text, (const u32*)(sc + S_LOW_TEXT));
+    LAUNCH(c, put_separators_k, dim3(1), dim3(1), 0, out, (u32)hdr_bytes, sc, 1, 0u, 0u);
     if (n_text) SCCG_CK(cudaMemcpyAsync(out + hdr_bytes + low_text + 1, ntext, n_text, cudaMemcpyDeviceToDevice, c->stream));
     if (M) LAUNCH(c, g_write_tokens_k, dim3(div_up(M, 256)), dim3(256), 0, (const int*)gm.tpos, (const int*)gm.p, (const int*)gm.l, M,
                   (const u32*)mbytes, out, (const u32*)(sc + S_BODY_BASE), text_delta);
@@ -1072,6 +1073,12 @@ static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8
         SCCG_CK(cudaStreamSynchronize(c->stream));
     }
     float ms = 0.f;
+    if (step_trace) {
+        float a = 0, b = 0, d = 0;
+        cudaEventElapsedTime(&a, c->ev[0], c->ev_side[2]); cudaEventElapsedTime(&b, c->ev_side[2], c->ev[1]); cudaEventElapsedTime(&d, c->ev[2], c->ev[3]);
+        fprintf(stderr, "step_trace (global): local attempt %.1f us, N runs + strip %.1f, index %.1f, parse %.1f, sizes + writers %.1f\n", a * 1e3, b * 1e3,
+                c->prof.index_ms * 1e3, c->prof.parse_ms * 1e3, d * 1e3);
+    }
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); c->prof.kernels_ms = ms;
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->prof.match_ms = ms;
     c->prof.serialize_ms = c->prof.kernels_ms - c->prof.match_ms;
