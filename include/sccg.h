@@ -67,6 +67,7 @@ typedef struct {
     float index_ms;       /* global mode: reference k-mer index (hash + radix sort + bucket table)       */
     float parse_ms;       /* global mode: speculative chunk parse + exact front + concatenation        */
     float exchange_ms;    /* multi-GPU layer: the collective(s) of the last sccg_mgpu_* call           */
+    int32_t index_stride; /* global mode: 1 = index of every reference k-mer, n = sampled index (every n-th position) */
 } sccg_profile;
 
 sccg_ctx*   sccg_create(int device);                 /* NULL on failure (see sccg_last_error)      */

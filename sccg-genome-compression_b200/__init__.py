@@ -38,7 +38,7 @@ class _Records(C.Structure):
 class Profile(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("kernels_ms", C.c_float), ("d2h_ms", C.c_float), ("match_ms", C.c_float),
                 ("serialize_ms", C.c_float), ("gather_ms", C.c_float), ("launches", C.c_int32), ("mode", C.c_int32),
-                ("front_steps", C.c_int32), ("spec_rounds", C.c_int32), ("index_ms", C.c_float), ("parse_ms", C.c_float), ("exchange_ms", C.c_float)]
+                ("front_steps", C.c_int32), ("spec_rounds", C.c_int32), ("index_ms", C.c_float), ("parse_ms", C.c_float), ("exchange_ms", C.c_float), ("index_stride", C.c_int32)]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}

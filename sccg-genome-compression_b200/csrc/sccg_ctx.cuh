@@ -31,7 +31,7 @@ enum Slot {
     B_RUN_CNT, B_RUN_MASK, B_NRUN_MASK, B_RUN_START, B_RUN_END, B_RUN_BYTES, B_RUN_TEXT, B_NRUN_CNT, B_NRUN_START, B_NRUN_END, B_NRUN_BYTES, B_NRUN_TEXT,
     B_ENC, B_NIDX, B_LOW, B_TOK_FLAG, B_TOK_POS, B_ITEM_OFF, B_ITEM_SRC, B_NUM0, B_NUM1, B_NUM2, B_NUM3, B_NUM4, B_NUM5,
     B_LRUN_S, B_LRUN_E, B_NRUNS_S, B_NRUNS_E, B_NRUNS_CUM, B_TILE0, B_TILE1, B_TILE2, B_TILE3, B_SEG_PTR, B_TILE_WIN, B_FILE_R, B_FILE_T, B_FA_TMP, B_FA_RNG, B_NEED,
-    B_GREF, B_GTGT, B_GKEYS, B_GVALS, B_GKEYS2, B_GVALS2, B_GHIST, B_GOFFS, B_GBUCKET, B_GREC, B_GLIT, B_GTMP0, B_GTMP1, B_GTMP2, B_GTMP3, B_SHARD,
+    B_GREF, B_GTGT, B_GKEYS, B_GVALS, B_GKEYS2, B_GVALS2, B_GHIST, B_GOFFS, B_GBUCKET, B_GREC, B_GLIT, B_GTMP0, B_GTMP1, B_GTMP2, B_GTMP3, B_GFIRST, B_SHARD,
     B_NSLOTS
 };
 

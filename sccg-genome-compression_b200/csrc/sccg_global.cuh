@@ -35,6 +35,9 @@ static const int GP_SHORT = 64;              // per-thread extension before the 
 // 24-bit hash of the k-mer s[0..k), 8 <= k <= 16; the words may come from global or shared memory.  24 bits = three radix
 // passes for the index; k-mers that share a hash are told apart by comparing the symbols (every consumer does).
 static const int GP_HASH_BITS = 24;
+static const unsigned GP_FIRST_CAP = 4096;     // sampled index mode: capacity of the occurrence list of the first matching target k-mer
+static const int GP_FIRST_W = 256;             //   target positions searched for it
+enum { GP_FIRST_N0 = 0, GP_FIRST_J = 1, GP_FIRST_N1 = 2 };
 // The offset table over the sorted keys is addressed by the top `bits` bits of the hash: 20 bits (4 MB, L2-resident, a few
 // dozen keys per bucket) for chromosome-sized indexes, fewer for small ones so that filling the table stays proportional
 // to the index.  (All 24 bits -- one bucket per hash value, no search through the keys -- measured no faster.)
@@ -87,6 +90,17 @@ struct KmerPairSource {
     }
 };
 
+// SAMPLED index: only the reference positions 0, stride, 2 * stride, ... (element i = position i * stride).  Enough for the
+// diagonal guesses of gp_spec_k (64 consecutive probe positions meet 64 / stride sampled positions of the true diagonal);
+// lookups that must see EVERY occurrence are served otherwise (gp_first_k) or make the host build the full index.
+struct KmerSampledSource {
+    const u8* R; int k; int stride;
+    static const bool kRun16 = false;
+    __device__ __forceinline__ void keys16(i64, u32*) const {}
+    __device__ __forceinline__ u32 key(i64 i) const { const u8* q = R + i * stride; return kmer_hash_words(ld_unaligned64(q), ld_unaligned64(q + 8), k); }
+    __device__ __forceinline__ u32 val(i64 i) const { return (u32)(i * stride); }
+};
+
 // bucket[b] for every b in [0, 2^bits]: index i owns the buckets that begin between keys[i-1] and keys[i]
 // (i = nk: the buckets past the last key).  8 indices per thread (two 16-byte loads; one index per thread was latency-bound).
 static const int KB_SPAN = 8;
@@ -111,6 +125,47 @@ __global__ void __launch_bounds__(256) kmer_buckets_k(const u32* __restrict__ ke
         for (u32 bkt = prev; bkt <= hi; ++bkt) bucket[bkt] = (u32)i;
         prev = hi + 1u;
     }
+}
+
+// Sampled mode: every reference position whose k-mer equals the FIRST k-mer of the target, T[0..k) -- the candidates of
+// the parse's first step (prev_match_end == -1: all of them are in range, :87).  One pass over the reference with all SMs,
+// 16 positions per thread: the 4-byte window at every position (one funnel shift) against the first 4 symbols of the k-mer,
+// the rare survivors symbol by symbol.  The list is unordered (the candidate fold does not depend on the order).
+// R must be 16-byte aligned (device buffers are); 24 bytes are read per thread (buffers carry >= 64 bytes of slack).
+__device__ __forceinline__ void first_windows(const u8* __restrict__ R, i64 p0, u32* x) {
+    const uint4 v = *reinterpret_cast<const uint4*>(R + p0);
+    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    const uint2 w = *reinterpret_cast<const uint2*>(R + p0 + 16);
+    x[4] = w.x; x[5] = w.y;
+}
+__device__ __forceinline__ void first_occurrences16(const u8* __restrict__ R, i64 nk, i64 p0, const u8* __restrict__ tj, int k, u32* __restrict__ list, u32 cap, u32* __restrict__ d_n) {
+    const u64 t0 = ld_unaligned64(tj), t1 = ld_unaligned64(tj + 8);
+    const u32 t32 = (u32)t0;
+    u32 x[6];
+    first_windows(R, p0, x);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const u32 w = (i & 3) ? __funnelshift_r(x[i >> 2], x[(i >> 2) + 1], 8 * (i & 3)) : x[i >> 2];
+        if (w == t32 && p0 + i < nk) {
+            const u8* q = R + p0 + i;
+            if (kmer_equal_words(ld_unaligned64(q), ld_unaligned64(q + 8), t0, t1, k)) {
+                const u32 at = atomicAdd(d_n, 1u);
+                if (at < cap) list[at] = (u32)(p0 + i);
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(256) gp_first_k(const u8* __restrict__ R, i64 nk, const u8* __restrict__ T, int k, u32* __restrict__ list, u32 cap, u32* __restrict__ first) {
+    const i64 p0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (p0 >= nk) return;
+    first_occurrences16(R, nk, p0, T, k, list, cap, first + GP_FIRST_N0);
+}
+// ... of T[j..j+k) where j is the position gp_first_scan_k found; does nothing when T[0..k) had occurrences or the scan found none
+__global__ void __launch_bounds__(256) gp_first_collect_k(const u8* __restrict__ R, i64 nk, const u8* __restrict__ T, int k, u32* __restrict__ list, u32 cap, u32* __restrict__ first) {
+    if (first[GP_FIRST_N0] != 0u || first[GP_FIRST_J] == 0xffffffffu) return;        // (nobody writes these two words any more)
+    const i64 p0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (p0 >= nk) return;
+    first_occurrences16(R, nk, p0, T + first[GP_FIRST_J], k, list, cap, first + GP_FIRST_N1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -140,6 +195,11 @@ struct GpArgs {
     const u32* bucket;            // bucket[b] = first index whose key >> bucket_shift is >= b (2^bits + 1 entries)
     int bucket_shift;             // GP_HASH_BITS - bits
     int k, m;
+    int full;                     // 1: (keys, vals) index every reference k-mer; 0: a sampled index (guesses only)
+    const u32* first_list;        // sampled mode: the reference positions of the first target k-mer that occurs in the reference at all, unordered
+    const u32* first;             //   first[GP_FIRST_N0]: occurrences of T[0..k) (gp_first_k); if 0: first[GP_FIRST_J] = first position < GP_FIRST_W
+                                  //   whose k-mer occurs (gp_first_scan_k, ~0u = none), first[GP_FIRST_N1] = its occurrences (gp_first_collect_k)
+    u32* need_full;               //   raised by a lookup that the sampled mode cannot serve: the host repeats the parse with the full index
     int* m_tpos; int* m_p; int* m_l;   // out: matches
     u32* d_count;                      // out: number of matches
 };
@@ -258,6 +318,15 @@ __device__ __forceinline__ void fold_index_candidates(GpShared& S, const GpArgs&
     }
 }
 
+// the same fold over the occurrence list of the FIRST target k-mer (sampled mode; the fold is order-independent)
+__device__ __forceinline__ void fold_first_candidates(GpShared& S, const GpArgs& a, u32 n, i64 j, int e) {
+    fold_reset(S);
+    for (u32 base = 0; base < n; base += GP_T) {
+        const u32 idx = base + threadIdx.x;
+        fold_chunk(S, a, idx < n ? (i64)a.first_list[idx] : -1, j, e);
+    }
+}
+
 __device__ __forceinline__ int fold_result_p(const GpShared& S) {
     return (S.cnt == 1 && S.zero_in) ? 0 : (int)(S.best_key & 0xffffffffULL);
 }
@@ -269,6 +338,25 @@ __device__ __forceinline__ bool gp_step(GpShared& S, const GpArgs& a, i64& j, in
     const int tid = (int)threadIdx.x;
     const int k = a.k;
     i64 found = -1;
+    if (e == -1 && !a.full) {
+        // ---- sampled mode, no match yet: the first position whose k-mer occurs anywhere in the reference (:77) and its
+        //      occurrences were found by brute force (position 0 for the usual pair, else one of the next GP_FIRST_W - 1);
+        //      a target that begins with more unmatched symbols than that needs the full index
+        u32 n = a.first[GP_FIRST_N0];
+        i64 fj = 0;
+        if (n == 0u && a.first[GP_FIRST_J] != 0xffffffffu) { fj = (i64)a.first[GP_FIRST_J]; n = a.first[GP_FIRST_N1]; }
+        if (j > fj || n == 0u || n > GP_FIRST_CAP) {
+            if (tid == 0) *reinterpret_cast<volatile u32*>(a.need_full) = 1u;
+            j = scan_end;
+            return false;
+        }
+        if (fj >= scan_end) { j = scan_end; return false; }      // literal steps, the state stays (.., -1)
+        j = fj;
+        fold_first_candidates(S, a, n, j, e);
+        sel_p = fold_result_p(S); sel_l = S.best_l;
+        __syncthreads();
+        return true;
+    }
     if (e == -1) {
         // ---- no match yet: first position whose k-mer occurs anywhere in the reference (:77, all candidates in range :87)
         for (; j < scan_end; j += GP_T) {
@@ -390,7 +478,9 @@ __device__ __forceinline__ bool gp_step(GpShared& S, const GpArgs& a, i64& j, in
     }
     sel_p = fold_result_p(S); sel_l = S.best_l;
     __syncthreads();
-    if (sel_p == 0) {                                         // `pn2 != 0` fails (:134): unrestricted best over ALL candidates
+    if (sel_p == 0 && !a.full) {                              // (sampled mode cannot serve this: the result of this parse will be discarded)
+        if (tid == 0) *reinterpret_cast<volatile u32*>(a.need_full) = 1u;
+    } else if (sel_p == 0) {                                  // `pn2 != 0` fails (:134): unrestricted best over ALL candidates
         fold_index_candidates(S, a, j, e);
         sel_p = fold_result_p(S); sel_l = S.best_l;
         __syncthreads();
@@ -429,7 +519,7 @@ struct GpSpecArgs {
     int lost_e;                 // slot 1: the e every chunk is entered with
     u32* ctl;                   // ctl[GP_CTL_CANCEL]: the front got lost, speculation is pointless
 };
-enum { GP_CTL_CANCEL = 0 };
+enum { GP_CTL_CANCEL = 0, GP_CTL_NEED_FULL = 1 };
 // GpChunkInfo::valid: 0 = not computed yet (the front may be running concurrently with the second batch of chunks), 1 = usable,
 // 2 = computed but unusable (no diagonal guess, or cancelled).  Written LAST, behind a fence; the front reads chunk records
 // with L2 loads (ld_info) and only trusts the other fields once it has seen valid != 0.
@@ -719,6 +809,14 @@ __global__ void __launch_bounds__(GP_T) gp_front_k(GpFrontArgs f) {
             e = sel_p + sel_l - 1;
             j += sel_l;
             lost_streak = 0;
+        } else if (e == -1 && !a.full) {
+            // sampled mode: literal steps up to the first matching position -- or that position is out of reach: need_full is
+            // raised, the host repeats the parse with the full index
+            __syncthreads();
+            if (*reinterpret_cast<volatile u32*>(a.need_full) != 0u) {
+                if (tid == 0) *reinterpret_cast<volatile u32*>(f.s.ctl + GP_CTL_CANCEL) = 1u;
+                status = GP_DONE; break;
+            }
         } else if (e != -1) {
             // no usable candidate up to the end of the chunk.  A few chunks are walked exactly (an insertion of a few kb in the
             // target); then the parse counts as "lost" with this e and the rest of the target is searched by many CTAs at once
@@ -790,6 +888,48 @@ __global__ void __launch_bounds__(GP_T) gp_lost_scan_k(GpScanArgs s) {
         }
     }
     if (s.trace && blockIdx.x == 0 && tid == 0) gp_trace(s.trace, 2ull, t_begin, (unsigned long long)j0);
+}
+
+// Sampled index mode, T[0..k) does not occur in the reference: the smallest j in [1, GP_FIRST_W) whose k-mer does (:77-81:
+// the positions before it are literal steps).  Roles swapped against gp_lost_scan_k: the filter holds the target k-mers
+// (keyed by their first 8 symbols: two 4-byte windows and two multiplications per reference position instead of a k-mer
+// hash), all SMs run over the reference, 16 positions per thread.  Does nothing when gp_first_k found occurrences.
+__device__ __forceinline__ u32 first_key(u32 wa, u32 wb) { return (wa * 0x9E3779B1u + wb * 0x85EBCA77u) | 1u; }
+__global__ void __launch_bounds__(GP_T) gp_first_scan_k(GpArgs a, u32* first) {
+    __shared__ GpShared S;
+    if (first[GP_FIRST_N0] != 0u) return;
+    const int tid = (int)threadIdx.x, k = a.k;
+    const i64 last_j = a.nt - k, nk = a.nr - k + 1;
+    const int w = last_j + 1 < GP_FIRST_W ? (int)(last_j + 1) : GP_FIRST_W;
+    for (int x = tid; x < GP_FILTER; x += GP_T) S.f_hash[x] = 0u;
+    __syncthreads();
+    for (int x = 1 + tid; x < w; x += GP_T) {
+        const u64 t0 = ld_unaligned64(a.T + x);
+        const u32 h = first_key((u32)t0, (u32)(t0 >> 32));
+        u32 slot = (h >> 23) & (GP_FILTER - 1);
+        while (atomicCAS(&S.f_hash[slot], 0u, h) != 0u) slot = (slot + 1) & (GP_FILTER - 1);
+        S.f_off[slot] = (u8)x;
+    }
+    __syncthreads();
+    for (i64 p0 = ((i64)blockIdx.x * GP_T + tid) * 16; p0 < nk; p0 += (i64)gridDim.x * GP_T * 16) {
+        u32 x[6];
+        first_windows(a.R, p0, x);
+        u32 wv[20];
+#pragma unroll
+        for (int i = 0; i < 20; ++i) wv[i] = (i & 3) ? __funnelshift_r(x[i >> 2], x[(i >> 2) + 1], 8 * (i & 3)) : x[i >> 2];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const u32 h = first_key(wv[i], wv[i + 4]);
+            u32 slot = (h >> 23) & (GP_FILTER - 1);
+            for (u32 fh; (fh = S.f_hash[slot]) != 0u; slot = (slot + 1) & (GP_FILTER - 1)) {      // every entry: equal k-mers sit at several offsets
+                if (fh == h && p0 + i < nk) {
+                    const u8* tp = a.T + S.f_off[slot];
+                    const u8* q = a.R + p0 + i;
+                    if (kmer_equal_words(ld_unaligned64(tp), ld_unaligned64(tp + 8), ld_unaligned64(q), ld_unaligned64(q + 8), k)) atomicMin(first + GP_FIRST_J, (u32)S.f_off[slot]);
+                }
+            }
+        }
+    }
 }
 
 // final match list = concatenation of the pieces
@@ -864,32 +1004,47 @@ __global__ void __launch_bounds__(256) g_write_literals_k(const u8* __restrict__
 // (m_tpos, m_p, m_l) and their number in *h_count.
 struct GlobalMatches { int* tpos; int* p; int* l; u32 count; };
 
-static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i64 nt, int k, int m, u32* sc, GlobalMatches* out) {
+// Index modes.  FULL: every reference k-mer (what the reference builds, :41-47).  SAMPLED (references of a million k-mers and
+// more): every GP_STRIDE-th position only -- an eighth of the sort.  The parse itself needs the whole-reference index in
+// three places: the diagonal guesses (heuristic: a sampled index serves them), the first step
+// (prev_match_end == -1: the occurrences of T[0..k) come from one brute-force pass, gp_first_k) and two rare events --
+// no occurrence of the first k-mer at all, or the `pn2 == 0` fall-through of :134 -- which raise need_full: the parse is
+// repeated with the full index, so the result never depends on the mode.
+static const int GP_STRIDE = 8;
+static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i64 nt, int k, int m, u32* sc, GlobalMatches* out, bool force_full = false) {
     if (k < 8 || k > 16) return set_error(SCCG_E_ARG, "global match_sequences supports 8 <= k <= 16");
     if (m < 0 || m > GP_MAX_M) return set_error(SCCG_E_ARG, "global match_sequences supports 0 <= m <= 120");
     // ---- reference k-mer index (:41-47)
     SCCG_CK(cudaEventRecord(c->ev_x[0], c->stream));
     const i64 nk = nr - k + 1 > 0 ? nr - k + 1 : 0;
+    int stride = nk >= ((i64)1 << 20) ? GP_STRIDE : 1;
+    if (const char* env = getenv("SCCG_GP_STRIDE")) { int v = atoi(env); if (v >= 1 && v <= 64) stride = v; }          // tests; 1 = always the full index
+    if (force_full || nt < k || ((uintptr_t)R & 15u)) stride = 1;         // (the brute-force passes of the sampled mode read aligned 16-byte vectors)
+    const i64 nidx = stride > 1 ? (nk + stride - 1) / stride : nk;
     // 24-bit hash keys + stable radix sort: positions ascending inside every key, the reference's per-bucket order.
     // (Measured alternative: a counting sort by hash bucket -- count, scan, fill with atomics -- needs 3.9 ms for the 59 M
     // k-mers of the chr19-shaped pair where the three radix passes need 1.4 ms: scattered 4-byte writes and 2 x 59 M global
     // atomics lose against coalesced tile-ordered stores.)
     u32 *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr, *bucket = nullptr;
-    SCCG_TRY(buf(c, B_GKEYS, (size_t)nk + 1, &keys));
-    SCCG_TRY(buf(c, B_GVALS, (size_t)nk + 1, &vals));
-    SCCG_TRY(buf(c, B_GKEYS2, (size_t)nk + 1, &keys2));
-    SCCG_TRY(buf(c, B_GVALS2, (size_t)nk + 1, &vals2));
-    if (nk > 0) {
+    SCCG_TRY(buf(c, B_GKEYS, (size_t)nidx + 1, &keys));
+    SCCG_TRY(buf(c, B_GVALS, (size_t)nidx + 1, &vals));
+    SCCG_TRY(buf(c, B_GKEYS2, (size_t)nidx + 1, &keys2));
+    SCCG_TRY(buf(c, B_GVALS2, (size_t)nidx + 1, &vals2));
+    if (nidx > 0) {
         u32 *sk = nullptr, *sv = nullptr;
-        KmerPairSource src{R, k};
-        SCCG_TRY(radix_sort_pairs(c, src, keys, vals, keys2, vals2, nk, B_GHIST, GP_HASH_BITS / 8, &sk, &sv));
+        if (stride > 1) {
+            KmerSampledSource src{R, k, stride};
+            SCCG_TRY(radix_sort_pairs(c, src, keys, vals, keys2, vals2, nidx, B_GHIST, GP_HASH_BITS / 8, &sk, &sv));
+        } else {
+            KmerPairSource src{R, k};
+            SCCG_TRY(radix_sort_pairs(c, src, keys, vals, keys2, vals2, nidx, B_GHIST, GP_HASH_BITS / 8, &sk, &sv));
+        }
         keys = sk; vals = sv;
     }
-    int bucket_bits = gp_bucket_bits(nk);
+    int bucket_bits = gp_bucket_bits(nidx);
     if (const char* env = getenv("SCCG_GP_BUCKET_BITS")) { int v = atoi(env); if (v >= 4 && v <= GP_HASH_BITS) bucket_bits = v; }    // tests: small inputs through the 24-bit path
     SCCG_TRY(buf(c, B_GBUCKET, ((size_t)1 << bucket_bits) + 2, &bucket));
-    LAUNCH(c, kmer_buckets_k, dim3(div_up(nk + 1, 256 * KB_SPAN)), dim3(256), 0, (const u32*)keys, nk, bucket, bucket_bits);
-    SCCG_CK(cudaEventRecord(c->ev_x[1], c->stream));
+    LAUNCH(c, kmer_buckets_k, dim3(div_up(nidx + 1, 256 * KB_SPAN)), dim3(256), 0, (const u32*)keys, nidx, bucket, bucket_bits);
     // ---- chunk-speculative parse (:64-161)
     int chunk = GP_CHUNK_DEFAULT;
     if (const char* env = getenv("SCCG_GP_CHUNK")) { int v = atoi(env); if (v >= 64 && v <= (1 << 24)) chunk = v; }
@@ -909,15 +1064,29 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
     h_st.j = 0; h_st.e = -1; h_st.status = GP_RUNNING;
     SCCG_CK(cudaMemcpyAsync(st, &h_st, sizeof h_st, cudaMemcpyHostToDevice, c->stream));
     GpFrontArgs f;
-    f.s.a.R = R; f.s.a.nr = nr; f.s.a.T = T; f.s.a.nt = nt; f.s.a.keys = keys; f.s.a.vals = vals; f.s.a.nk = nk; f.s.a.bucket = bucket; f.s.a.bucket_shift = GP_HASH_BITS - bucket_bits; f.s.a.k = k; f.s.a.m = m;
+    f.s.a.R = R; f.s.a.nr = nr; f.s.a.T = T; f.s.a.nt = nt; f.s.a.keys = keys; f.s.a.vals = vals; f.s.a.nk = nidx; f.s.a.bucket = bucket; f.s.a.bucket_shift = GP_HASH_BITS - bucket_bits; f.s.a.k = k; f.s.a.m = m;
     f.s.a.m_tpos = nullptr; f.s.a.m_p = nullptr; f.s.a.m_l = nullptr; f.s.a.d_count = nullptr;
     f.s.info = info; f.s.c_tpos = cbuf; f.s.c_p = cbuf + (size_t)2 * nchunks * cap_c; f.s.c_l = cbuf + (size_t)4 * nchunks * cap_c;
     f.s.nchunks = nchunks; f.s.cap_c = cap_c; f.s.chunk = chunk; f.s.slot = 0; f.s.first_chunk = 0; f.s.lost_e = 0;
     f.st = st; f.pieces = pieces; f.cap_pieces = cap_pieces; f.f_tpos = fbuf; f.f_p = fbuf + cap_all; f.f_l = fbuf + 2 * cap_all;
     unsigned long long* d_hit = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(st) + 256);
     u32* ctl = reinterpret_cast<u32*>(reinterpret_cast<char*>(st) + 384);
-    SCCG_CK(cudaMemsetAsync(ctl, 0, 2 * sizeof(u32), c->stream));
+    SCCG_CK(cudaMemsetAsync(ctl, 0, 8 * sizeof(u32), c->stream));
+    u32* first = ctl + 4;
+    SCCG_CK(cudaMemsetAsync(first + GP_FIRST_J, 0xff, sizeof(u32), c->stream));
     f.d_hit = d_hit; f.s.ctl = ctl;
+    f.s.a.full = stride > 1 ? 0 : 1; f.s.a.first_list = nullptr; f.s.a.first = first; f.s.a.need_full = ctl + GP_CTL_NEED_FULL;
+    if (stride > 1) {
+        // the first step of the parse (state (0, -1): every occurrence is a candidate) by brute force over the reference; the
+        // second and third kernel return at once unless T[0..k) has no occurrence (a target that begins with a mutation)
+        u32* first_list = nullptr;
+        SCCG_TRY(buf(c, B_GFIRST, (size_t)GP_FIRST_CAP + 1, &first_list));
+        f.s.a.first_list = first_list;
+        LAUNCH(c, gp_first_k, dim3(div_up(nk, 256 * 16)), dim3(256), 0, R, nk, T, k, first_list, GP_FIRST_CAP, first);
+        LAUNCH(c, gp_first_scan_k, dim3((unsigned)c->sm_count * 8u), dim3(GP_T), 0, f.s.a, first);
+        LAUNCH(c, gp_first_collect_k, dim3(div_up(nk, 256 * 16)), dim3(256), 0, R, nk, T, k, first_list, GP_FIRST_CAP, first);
+    }
+    SCCG_CK(cudaEventRecord(c->ev_x[1], c->stream));
     // Speculation in two batches: a small one on this stream, the rest on the side stream UNDERNEATH the front, which follows the
     // chunks as they are published (per-chunk ready flags).  A synchronised parse (the usual pair) splices through at the pace
     // of the speculation; a parse that gets lost (divergent pair) cancels what has not started yet: those chunks return at once.
@@ -952,10 +1121,15 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
             LAUNCH(c, gp_front_k, dim3(1), dim3(GP_T), 0, f);
             LAUNCH(c, gp_lost_scan_k, dim3(scan_grid), dim3(GP_T), 0, sa);
         }
-        SCCG_CK(cudaMemcpyAsync(c->h_pinned, st, sizeof h_st, cudaMemcpyDeviceToHost, c->stream));
+        SCCG_CK(cudaMemcpyAsync(c->h_pinned, st, 416, cudaMemcpyDeviceToHost, c->stream));     // state, scan result, control words
         SCCG_CK(cudaStreamSynchronize(c->stream));
         memcpy(&h_st, c->h_pinned, sizeof h_st);
         c->prof.spec_rounds = (int32_t)h_st.rounds;
+        if (reinterpret_cast<const u32*>(static_cast<const char*>(c->h_pinned) + 384)[GP_CTL_NEED_FULL] != 0u && stride > 1) {
+            // the sampled mode met a lookup it cannot serve: same parse again with the index of every k-mer
+            if (side_busy) SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));
+            return global_match_device(c, R, nr, T, nt, k, m, sc, out, true);
+        }
         if (h_st.status == GP_DONE) break;
         if (h_st.status == GP_FULL || h_st.npieces + 2 >= cap_pieces) return set_error(SCCG_E_NOMEM, "internal: piece list overflow in the global parse");
         if (h_st.status != GP_LOST || group > 1000000) return set_error(SCCG_E_CUDA, "internal: global parse did not terminate");
@@ -985,6 +1159,7 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
     cudaEventElapsedTime(&c->prof.parse_ms, c->ev_x[1], c->ev_x[2]);
     out->tpos = obuf; out->p = obuf + cap_all; out->l = obuf + 2 * cap_all; out->count = h[S_G1];
     c->prof.front_steps = (int32_t)h_st.steps;
+    c->prof.index_stride = stride;
     return SCCG_OK;
 }
 
@@ -994,21 +1169,29 @@ static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8
     SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
     const bool step_trace = getenv("SCCG_STEP_TRACE") != nullptr;             // development aid: where the call's time goes
     if (step_trace) SCCG_CK(cudaEventRecord(c->ev_side[2], c->stream));
-    // ---- N runs of the upper-cased target, original coordinates (:527-554): count
+    // ---- N runs of the upper-cased target, original coordinates (:527-554): count; toupper + erase every 'N' from both
+    //      sequences (:523-524, :556-557).  Two lanes (the target's two passes on the side stream, the reference on this one:
+    //      either alone leaves half of the HBM bandwidth idle at chromosome size), one host round trip for all the counts.
     u32 *ncnt_s = nullptr, *ncnt_e = nullptr;
     u64* n_mask = nullptr;
-    SCCG_TRY(rle_count<1>(c, d_tgt, nt, B_NRUN_CNT, B_NRUN_MASK, &ncnt_s, &ncnt_e, &n_mask, sc + S_N_K, sc + S_N_KE));
-    // ---- toupper + erase every 'N' from both sequences (:523-524, :556-557)
     u8 *R2 = nullptr, *T2 = nullptr;
     SCCG_TRY(buf(c, B_GREF, (size_t)nr + 64, &R2));
     SCCG_TRY(buf(c, B_GTGT, (size_t)nt + 64, &T2));
-    i64 nr2 = 0, nt2 = 0;
-    SCCG_TRY(strip_n<1>(c, d_ref, nr, R2, B_TILE3, sc + S_G2, &nr2));
-    SCCG_TRY(strip_n<1>(c, d_tgt, nt, T2, B_TILE3, sc + S_G3, &nt2));
-    SCCG_CK(cudaMemsetAsync(R2 + nr2, 0, 64, c->stream));          // unaligned word loads run up to 15 B past the end
-    SCCG_CK(cudaMemsetAsync(T2 + nt2, 0, 64, c->stream));
+    SCCG_CK(cudaEventRecord(c->ev_side[0], c->stream));
+    SCCG_CK(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+    {
+        SideLane side(c);
+        SCCG_TRY(strip_n_enqueue<1>(c, d_tgt, nt, T2, B_TILE2, sc + S_G3));
+        SCCG_TRY(rle_count<1>(c, d_tgt, nt, B_NRUN_CNT, B_NRUN_MASK, &ncnt_s, &ncnt_e, &n_mask, sc + S_N_K, sc + S_N_KE));
+        SCCG_CK(cudaEventRecord(c->ev_side[1], c->stream));
+    }
+    SCCG_TRY(strip_n_enqueue<1>(c, d_ref, nr, R2, B_TILE3, sc + S_G2));
+    SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));
     u32 h[S_COUNT];
     SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
+    const i64 nr2 = (i64)h[S_G2], nt2 = (i64)h[S_G3];
+    SCCG_CK(cudaMemsetAsync(R2 + nr2, 0, 64, c->stream));          // unaligned word loads run up to 15 B past the end
+    SCCG_CK(cudaMemsetAsync(T2 + nt2, 0, 64, c->stream));
     if (h[S_N_K] != h[S_N_KE]) return set_error(SCCG_E_CUDA, "internal: N-run start/end counts differ");
     const u32 n_k = h[S_N_K];
 

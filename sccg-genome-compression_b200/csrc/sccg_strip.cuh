@@ -56,16 +56,24 @@ __global__ void __launch_bounds__(256) upper_k(const u8* __restrict__ src, i64 n
     *reinterpret_cast<ulonglong2*>(dst + i) = v;                     // buffers are padded to 16 B
 }
 
-// dst <- N-stripped, upper-cased src; *d_count (device) and *h_count receive the kept length
+// dst <- N-stripped, upper-cased src on the current lane; *d_count (device) receives the kept length.  No host round trip.
 template <int UPPER_FIRST>
-static int strip_n(sccg_ctx* c, const u8* d_src, i64 n, u8* d_dst, int slot_cnt, u32* d_count, i64* h_count) {
-    if (n <= 0) { *h_count = 0; return SCCG_OK; }
+static int strip_n_enqueue(sccg_ctx* c, const u8* d_src, i64 n, u8* d_dst, int slot_cnt, u32* d_count) {
+    if (n <= 0) { SCCG_CK(cudaMemsetAsync(d_count, 0, sizeof(u32), c->stream)); return SCCG_OK; }
     unsigned ntiles = div_up(n, STRIP_TILE);
     u32* cnt = nullptr;
     SCCG_TRY(buf(c, slot_cnt, (size_t)ntiles + 1, &cnt));
     LAUNCH(c, strip_count_k<UPPER_FIRST>, dim3(ntiles), dim3(STRIP_T), 0, d_src, n, cnt);
     SCCG_TRY(scan_exclusive_u32(c, cnt, cnt, (i64)ntiles, d_count));
     LAUNCH(c, strip_write_k<UPPER_FIRST>, dim3(ntiles), dim3(STRIP_T), 0, d_src, n, (const u32*)cnt, d_dst);
+    return SCCG_OK;
+}
+
+// same; *h_count receives the kept length as well (one host round trip)
+template <int UPPER_FIRST>
+static int strip_n(sccg_ctx* c, const u8* d_src, i64 n, u8* d_dst, int slot_cnt, u32* d_count, i64* h_count) {
+    if (n <= 0) { *h_count = 0; return SCCG_OK; }
+    SCCG_TRY(strip_n_enqueue<UPPER_FIRST>(c, d_src, n, d_dst, slot_cnt, d_count));
     SCCG_CK(cudaMemcpyAsync(c->h_pinned, d_count, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
     SCCG_CK(cudaStreamSynchronize(c->stream));
     *h_count = (i64)*(u32*)c->h_pinned;

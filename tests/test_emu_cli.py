@@ -32,8 +32,10 @@ def env(tmp_path_factory):
         out = BIN / name
         srcs = [HOST / f"{name}.cpp", HOST / "batch.hpp", ROOT / "include" / "sccg.h", EMU_DIR / "libsccg_b200_emu.so"]
         if not out.exists() or any(s.stat().st_mtime > out.stat().st_mtime for s in srcs):
+            tmp = BIN / f"{name}.tmp.{os.getpid()}"         # built next to the target and renamed: parallel test workers never run a half-written program
             subprocess.check_call(["/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++", "-O1", "-std=c++17", "-pthread", f"-I{ROOT / 'include'}",
-                                   str(HOST / f"{name}.cpp"), "-o", str(out), f"-L{EMU_DIR}", "-lsccg_b200_emu", f"-Wl,-rpath,{EMU_DIR}"])
+                                   str(HOST / f"{name}.cpp"), "-o", str(tmp), f"-L{EMU_DIR}", "-lsccg_b200_emu", f"-Wl,-rpath,{EMU_DIR}"])
+            os.replace(tmp, out)
     d = tmp_path_factory.mktemp("shim")
     shutil.copy(ROOT / "oracle" / "7z_shim.sh", d / "7z")
     os.chmod(d / "7z", 0o755)

@@ -393,6 +393,75 @@ def test_global_index_bucket_table_widths(ctx, seed, bits, monkeypatch):
     assert got == exp
 
 
+@pytest.mark.parametrize("stride", [2, 8, 16])
+@pytest.mark.parametrize("seed", range(8))
+def test_global_sampled_index(ctx, seed, stride, monkeypatch):
+    """sampled reference index (every stride-th position; what references of a million k-mers and more get): the diagonal
+    guesses come from the sampled index, the first step from the brute-force occurrence list -- same records as the
+    sequential parse, and the sampled mode is the one that produced them"""
+    monkeypatch.setenv("SCCG_GP_STRIDE", str(stride))
+    monkeypatch.setenv("SCCG_GP_CHUNK", ["300", "1024"][seed % 2])
+    alphabet = [b"ACGT", b"ACGT", b"ACGT", b"AC"][seed % 4]
+    n = 9000 if alphabet == b"ACGT" else 2500
+    ref, tgt = _mutated_pair(("samp", seed), n, alphabet, snp=[0.002, 0.02][seed % 2], indel=0.002)
+    r = random.Random(seed)
+    if seed % 3 == 1:
+        cut = sorted(r.sample(range(100, len(tgt)), 2))
+        tgt = tgt[:cut[0]] + tgt[cut[1]:] + tgt[cut[0]:cut[1]]                   # rearranged behind a common beginning
+    if seed % 3 == 2:
+        tgt = tgt[:len(tgt) // 2] + rnd(3000, ("sjunk", seed)) + tgt[len(tgt) // 2:]
+    tgt = ref[300:340] + tgt                                                    # the first k-mer occurs in the reference
+    exp = [(x.p, x.l, x.lit) for x in ol.orc_match_sequences(ref, tgt, 14, 100, True, 0)]
+    got = [(x.p, x.l, x.lit) for x in ctx.match_sequences(ref, tgt, 14, 100, True, 0)]
+    assert got == exp
+    if alphabet == b"ACGT":
+        assert ctx.profile()["index_stride"] == stride
+
+
+SAMPLED_FALLBACK_SHAPES = ["first_kmer_absent", "first_kmers_repeat", "long_unmatched_start", "first_kmer_everywhere", "p0_fallthrough", "first_kmer_twice"]
+
+
+def sampled_fallback_pair(shape):
+    """pairs around the lookups the sampled index mode cannot serve; returns (ref, tgt, stride that must have produced the result
+    when 8 was asked for)"""
+    ref = rnd(12_000, "fbref")
+    body = bytearray(ref[200:9000])
+    for p in random.Random("fb").sample(range(len(body)), 40):
+        body[p] = ord("A")
+    if shape == "first_kmer_absent":
+        return ref, b"T" * 30 + bytes(body), 8                                  # found by the scan of the first 256 target positions
+    if shape == "first_kmers_repeat":
+        # equal k-mers at several of the first positions (the scan must report the smallest), several occurrences in the reference
+        ref = ref[:3000] + b"ACGTACGTACGTACGTACGTAC" + ref[3000:7000] + b"ACGTACGTACGTACGTACGTAC" + ref[7000:]
+        return ref, b"TTTTTTT" + b"ACGTACGTACGTACGTACGTAC" + bytes(body), 8
+    if shape == "long_unmatched_start":
+        return ref, rnd(400, "fbjunk") + bytes(body), 1                         # nothing in the first 256 positions: full index
+    if shape == "first_kmer_everywhere":
+        return b"AC" * 6000 + ref, b"AC" * 20 + bytes(body), 1                 # 6,000 occurrences of the first k-mer > list capacity
+    if shape == "p0_fallthrough":
+        # first match ends near the start of the reference, the next k-mer of the target is the reference's first one:
+        # candidate p = 0 is in range and chosen -> `pn2 != 0` fails -> unrestricted best over all candidates
+        return ref, ref[20:60] + ref[0:30] + bytes(body), 1
+    ref = ref[:5000] + ref[100:160] + ref[5000:]                                # two occurrences: both in the list, sampled mode stays
+    return ref, ref[100:160] + bytes(body), 8
+
+
+@pytest.mark.parametrize("chunk", [64, 300])
+@pytest.mark.parametrize("shape", SAMPLED_FALLBACK_SHAPES)
+def test_global_sampled_index_falls_back(ctx, shape, chunk, monkeypatch):
+    """the first step of the parse in sampled mode (occurrences of the first target k-mer that has any, by brute force) and
+    the lookups the sampled mode cannot serve, which repeat the parse with the full index: nothing matches in the first 256
+    target positions, more occurrences than the list holds, and the `pn2 == 0` fall-through of compression.cpp:134 (the
+    chosen in-range candidate is reference position 0)"""
+    monkeypatch.setenv("SCCG_GP_STRIDE", "8")
+    monkeypatch.setenv("SCCG_GP_CHUNK", str(chunk))
+    ref, tgt, expect_stride = sampled_fallback_pair(shape)
+    exp = [(x.p, x.l, x.lit) for x in ol.orc_match_sequences(ref, tgt, 14, 100, True, 0)]
+    got = [(x.p, x.l, x.lit) for x in ctx.match_sequences(ref, tgt, 14, 100, True, 0)]
+    assert got == exp
+    assert ctx.profile()["index_stride"] == expect_stride
+
+
 def test_resident_reference_round_trips(ctx, monkeypatch):
     """sccg_reference_set + *_resident calls: the bytes of sccg_compress / sccg_decompress for every target, the reference
     uploaded once; target chunks smaller than the sequences (matcher launched per chunk, leftovers past the last launch)"""

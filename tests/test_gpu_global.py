@@ -145,3 +145,34 @@ def test_global_two_batch_speculation(ctx, shape, batch0, monkeypatch):
         got, gmode = ctx.compress(ref, tgt, b">two batches")
         assert (gmode, got) == (mode, exp)
 
+
+
+@pytest.mark.parametrize("stride", [1, 4, 8])
+@pytest.mark.parametrize("shape", ["gap", "divergent"])
+def test_global_index_modes(ctx, shape, stride, monkeypatch):
+    """index of every reference k-mer (stride 1) against the sampled index references of a million k-mers and more get (8):
+    same file, and the asked-for mode is the one that produced it"""
+    from sccg_genome_compression_b200 import synth
+    monkeypatch.setenv("SCCG_GP_STRIDE", str(stride))
+    if shape == "gap":
+        ref, tgt = synth.global_gap_pair(2_160_000, 2_000_000, synth.seed_for(1, 17))
+    else:
+        ref, tgt = synth.divergent_pair(1_800_000, synth.seed_for(3, 17))
+    ref, tgt = ref.tobytes(), tgt.tobytes()
+    rc, exp, mode = ol.orc_compress(ref, tgt, b">index modes")
+    assert rc == 0 and mode == 1
+    got, gmode = ctx.compress(ref, tgt, b">index modes")
+    assert (gmode, got) == (mode, exp)
+    assert ctx.profile()["index_stride"] == stride
+
+
+@pytest.mark.parametrize("shape", ["first_kmer_absent", "first_kmers_repeat", "long_unmatched_start", "first_kmer_everywhere", "p0_fallthrough", "first_kmer_twice"])
+def test_global_sampled_index_falls_back(ctx, shape, monkeypatch):
+    """lookups the sampled mode cannot serve (tests/test_emu_compress.sampled_fallback_pair) repeat the parse with the full index"""
+    from test_emu_compress import sampled_fallback_pair
+    monkeypatch.setenv("SCCG_GP_STRIDE", "8")
+    ref, tgt, expect_stride = sampled_fallback_pair(shape)
+    exp = [(x.p, x.l, x.lit) for x in ol.orc_match_sequences(ref, tgt, 14, 100, True, 0)]
+    got = [(x.p, x.l, x.lit) for x in ctx.match_sequences(ref, tgt, 14, 100, True, 0)]
+    assert got == exp
+    assert ctx.profile()["index_stride"] == expect_stride

@@ -13,7 +13,8 @@ import torch
 import sccg_b200
 from sccg_genome_compression_b200 import synth
 
-scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+scale = float(args[0]) if args else 1.0
 verify = "--verify" in sys.argv
 ctx = sccg_b200.Context(0)
 for name, (ref, tgt) in {
