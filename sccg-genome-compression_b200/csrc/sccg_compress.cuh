@@ -137,14 +137,16 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
         SCCG_CK(cudaStreamWaitEvent(c->side_stream, arr->ev_tgt, 0));
         if (!arr->tgt_chunked) SCCG_CK(cudaStreamWaitEvent(c->stream, arr->ev_tgt, 0));     // chunked target: the matcher waits chunk by chunk
     }
+    // ---- local segment matching (:381-474)
+    const i64 n_rseg = (nr + SEG - 1) / SEG, n_tseg = (nt + SEG - 1) / SEG;
+    const int n_iter = (int)(n_rseg < n_tseg ? n_rseg : n_tseg);             // :392
+    // (Measured and dropped: preparing the inputs of global mode -- N-strip of both sequences -- on the side lane underneath the
+    // probe for pairs of different length: the local attempt gets as much slower as the preparation takes, 1.19 ms either way.)
+    const bool probe = !arr && n_iter > 4 * LM_PROBE_SEGS && (nr > nt ? nr - nt : nt - nr) >= SEG;
     {
         SideLane side(c);
         SCCG_TRY(rle_count<0>(c, d_tgt, nt, B_RUN_CNT, B_RUN_MASK, &cnt_s, &cnt_e, &low_mask, sc + S_LOW_K, sc + S_LOW_KE, sc + S_PAREN));
     }
-
-    // ---- local segment matching (:381-474)
-    const i64 n_rseg = (nr + SEG - 1) / SEG, n_tseg = (nt + SEG - 1) / SEG;
-    const int n_iter = (int)(n_rseg < n_tseg ? n_rseg : n_tseg);             // :392
     u32 *seginfo = nullptr, *matches = nullptr, *seg_bytes = nullptr;
     int* seg_prev = nullptr;
     SCCG_TRY(buf(c, B_SEGINFO, (size_t)n_iter + 1, &seginfo));
@@ -166,7 +168,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
         // segments, wherever they are, so a small probe launch over the last segments can raise the abort flag before the
         // main launch starts: every warp of the main launch then leaves after its first flag poll instead of burning one
         // failing (= most expensive) segment per resident warp.  No abort in the probe range: the main launch runs as usual.
-        if (!arr && n_iter > 4 * LM_PROBE_SEGS && (nr > nt ? nr - nt : nt - nr) >= SEG) {
+        if (probe) {
             LAUNCH(c, seg_match_k<1>, dim3(div_up(LM_PROBE_SEGS, LM_WARPS)), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, n_iter - LM_PROBE_SEGS, n_iter, n_iter, K1, K2,
                    seginfo, matches, sc + S_WORK + 31, sc + S_ABORT, c->use_diag);
         }

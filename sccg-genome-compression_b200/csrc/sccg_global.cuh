@@ -394,6 +394,8 @@ __device__ __forceinline__ bool gp_step(GpShared& S, const GpArgs& a, i64& j, in
     if (whi < wlo) { j = scan_end; return false; }            // no reference k-mer can be in range: literals only
     const int wlen = (int)(whi - wlo + 1);
     const int wbytes = wlen + k - 1;
+    // (the target words of the brute-force step are requested before the window is staged: one memory latency instead of two)
+    const u64 bt0 = ld_unaligned64(a.T + j), bt1 = ld_unaligned64(a.T + j + 8), bt2 = ld_unaligned64(a.T + j + 16);
     for (int x = tid; x < GP_FILTER; x += GP_T) S.f_hash[x] = 0u;
     for (int x = tid; x < GP_WIN_BYTES; x += GP_T) S.win[x] = x < wbytes ? a.R[wlo + x] : (u8)0;
     if (tid < GP_BF) S.bf_hit[tid] = 0;
@@ -407,7 +409,7 @@ __device__ __forceinline__ bool gp_step(GpShared& S, const GpArgs& a, i64& j, in
         const int np = scan_end - j < GP_BF ? (int)(scan_end - j) : GP_BF;
         u32 mymask = 0u;
         if (tid < wlen) {
-            const u64 t0 = ld_unaligned64(a.T + j), t1 = ld_unaligned64(a.T + j + 8), t2 = ld_unaligned64(a.T + j + 16);
+            const u64 t0 = bt0, t1 = bt1, t2 = bt2;
             const u64 w0 = ld_unaligned64(S.win + tid), w1 = ld_unaligned64(S.win + tid + 8);
 #pragma unroll
             for (int q = 0; q < GP_BF; ++q) {
@@ -464,6 +466,25 @@ __device__ __forceinline__ bool gp_step(GpShared& S, const GpArgs& a, i64& j, in
     }
     j = found;
     // in-range candidates: the window positions whose k-mer equals T[j..j+k)  (pn2 / ln2, :116-123)
+    if (have_cand && __syncthreads_count(cand >= 0) == 1) {
+        // the usual step (the parse resumes on its diagonal behind a substitution): ONE candidate, whose k-mer the brute-force
+        // compare has verified -- it is chosen whatever its length (:118-122 with a single p), so the fold and its barriers
+        // are skipped and the whole CTA extends it at once
+        if (cand >= 0) { S.i_scratch[2] = (int)(cand & 0xffffffff); S.i_scratch[3] = (int)(cand >> 32); }
+        __syncthreads();
+        const i64 pp = ((i64)S.i_scratch[3] << 32) | (u32)S.i_scratch[2];
+        const i64 maxl = (a.nr - pp) < (a.nt - j) ? (a.nr - pp) : (a.nt - j);
+        sel_p = (int)pp;
+        sel_l = (int)block_lcp(S, a.R, pp, a.T, j, maxl);
+        if (sel_p == 0 && !a.full) {
+            if (tid == 0) *reinterpret_cast<volatile u32*>(a.need_full) = 1u;
+        } else if (sel_p == 0) {
+            fold_index_candidates(S, a, j, e);
+            sel_p = fold_result_p(S); sel_l = S.best_l;
+            __syncthreads();
+        }
+        return true;
+    }
     fold_reset(S);
     if (have_cand) {
         fold_chunk(S, a, cand, j, e);
@@ -582,10 +603,10 @@ __global__ void __launch_bounds__(GP_T, SCCG_GP_MINB) gp_spec_k(GpSpecArgs s) {
                 i64 pos = Q + tid;
                 u64 w0 = ld_unaligned64(a.T + pos), w1 = ld_unaligned64(a.T + pos + 8);
                 u32 h = kmer_hash_words(w0, w1, a.k);
-                i64 lo, hi;
-                index_range(a, h, &lo, &hi);
+                i64 lo = index_lower_bound(a, h);                     // entries of one key are contiguous: no second search for the end
+                const i64 hi = (i64)a.bucket[(h >> a.bucket_shift) + 1u];
                 int hits = 0;
-                for (; lo < hi && hits < 2; ++lo) {
+                for (; lo < hi && hits < 2 && a.keys[lo] == h; ++lo) {
                     const u8* rp = a.R + a.vals[lo];
                     if (kmer_equal_words(ld_unaligned64(rp), ld_unaligned64(rp + 8), w0, w1, a.k)) { ++hits; my_d = (i64)a.vals[lo] - pos; }
                 }
@@ -1163,32 +1184,40 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
     return SCCG_OK;
 }
 
+struct GlobalPrep { u8* R2; u8* T2; u32* ncnt_s; u32* ncnt_e; u64* n_mask; };
+// N runs of the upper-cased target, original coordinates (:527-554): count; toupper + erase every 'N' from both sequences
+// (:523-524, :556-557).  Two lanes: the target's passes go to the side stream, the reference's stay on this one (either alone
+// leaves half of the HBM bandwidth idle at chromosome size); no host round trip: sc[S_G2] / sc[S_G3] receive the stripped
+// lengths, sc[S_N_K] / sc[S_N_KE] the run count.
+static int global_prepare_enqueue(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt, i64 nt, u32* sc, GlobalPrep* gp) {
+    SCCG_TRY(buf(c, B_GREF, (size_t)nr + 64, &gp->R2));
+    SCCG_TRY(buf(c, B_GTGT, (size_t)nt + 64, &gp->T2));
+    SCCG_CK(cudaEventRecord(c->ev_side[0], c->stream));
+    SCCG_CK(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
+    {
+        SideLane side(c);
+        SCCG_TRY(strip_n_enqueue<1>(c, d_tgt, nt, gp->T2, B_TILE2, sc + S_G3));
+        SCCG_TRY(rle_count<1>(c, d_tgt, nt, B_NRUN_CNT, B_NRUN_MASK, &gp->ncnt_s, &gp->ncnt_e, &gp->n_mask, sc + S_N_K, sc + S_N_KE));
+        SCCG_CK(cudaEventRecord(c->ev_side[1], c->stream));
+    }
+    SCCG_TRY(strip_n_enqueue<1>(c, d_ref, nr, gp->R2, B_TILE3, sc + S_G2));
+    SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));
+    return SCCG_OK;
+}
+
 static int compress_global_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt, i64 nt, const char* header, i64 nh,
                                   u32 low_k, const u8* d_low_text, int text_delta, CompressResult* res) {
     u32* sc = nullptr;
     SCCG_TRY(buf(c, B_SCALARS, (size_t)S_COUNT, &sc));
     const bool step_trace = getenv("SCCG_STEP_TRACE") != nullptr;             // development aid: where the call's time goes
     if (step_trace) SCCG_CK(cudaEventRecord(c->ev_side[2], c->stream));
-    // ---- N runs of the upper-cased target, original coordinates (:527-554): count; toupper + erase every 'N' from both
-    //      sequences (:523-524, :556-557).  Two lanes (the target's two passes on the side stream, the reference on this one:
-    //      either alone leaves half of the HBM bandwidth idle at chromosome size), one host round trip for all the counts.
-    u32 *ncnt_s = nullptr, *ncnt_e = nullptr;
-    u64* n_mask = nullptr;
-    u8 *R2 = nullptr, *T2 = nullptr;
-    SCCG_TRY(buf(c, B_GREF, (size_t)nr + 64, &R2));
-    SCCG_TRY(buf(c, B_GTGT, (size_t)nt + 64, &T2));
-    SCCG_CK(cudaEventRecord(c->ev_side[0], c->stream));
-    SCCG_CK(cudaStreamWaitEvent(c->side_stream, c->ev_side[0], 0));
-    {
-        SideLane side(c);
-        SCCG_TRY(strip_n_enqueue<1>(c, d_tgt, nt, T2, B_TILE2, sc + S_G3));
-        SCCG_TRY(rle_count<1>(c, d_tgt, nt, B_NRUN_CNT, B_NRUN_MASK, &ncnt_s, &ncnt_e, &n_mask, sc + S_N_K, sc + S_N_KE));
-        SCCG_CK(cudaEventRecord(c->ev_side[1], c->stream));
-    }
-    SCCG_TRY(strip_n_enqueue<1>(c, d_ref, nr, R2, B_TILE3, sc + S_G2));
-    SCCG_CK(cudaStreamWaitEvent(c->stream, c->ev_side[1], 0));
+    GlobalPrep gp; memset(&gp, 0, sizeof gp);
     u32 h[S_COUNT];
-    SCCG_TRY(read_scalars(c, sc, h, S_COUNT));
+    SCCG_TRY(global_prepare_enqueue(c, d_ref, nr, d_tgt, nt, sc, &gp));
+    SCCG_TRY(read_scalars(c, sc, h, S_COUNT));                                // one host round trip for all the counts
+    u8 *R2 = gp.R2, *T2 = gp.T2;
+    u32 *ncnt_s = gp.ncnt_s, *ncnt_e = gp.ncnt_e;
+    u64* n_mask = gp.n_mask;
     const i64 nr2 = (i64)h[S_G2], nt2 = (i64)h[S_G3];
     SCCG_CK(cudaMemsetAsync(R2 + nr2, 0, 64, c->stream));          // unaligned word loads run up to 15 B past the end
     SCCG_CK(cudaMemsetAsync(T2 + nt2, 0, 64, c->stream));

@@ -515,6 +515,10 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
     const int lane = lane_of();
     const int warps_total = (int)(gridDim.x * (blockDim.x >> 5));
     const int warp_global = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+#ifndef SCCG_NO_EARLY_ABORT
+    // the abort probe (or an earlier launch of the same attempt) has already raised the flag: nothing of this launch is used
+    if (abort_flag && __any_sync(SCCG_FULL_MASK, __ldcg(abort_flag) != 0u)) return;
+#endif
 
     // 2^(s*(k-1-lane)) for the cooperative k-mer hash of a target position (0 once the symbol has left the register)
     u32 pow1 = 0u, pow2 = 0u;
