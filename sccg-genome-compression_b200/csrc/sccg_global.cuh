@@ -865,7 +865,10 @@ __global__ void __launch_bounds__(GP_T) gp_front_k(GpFrontArgs f) {
 // (atomicMin) and tiles beyond it are not looked at.  The front resumes exactly there.
 // ------------------------------------------------------------------------------------------------
 struct GpScanArgs { GpArgs a; const GpFrontState* st; unsigned long long* d_hit; unsigned long long* trace; };
-static const int GP_SCAN_ROUNDS = 16;
+#ifndef SCCG_GP_SCAN_ROUNDS
+#define SCCG_GP_SCAN_ROUNDS 4            // positions per thread and tile (measured on the divergent pair, same positions per wave: 16 rounds x 4 CTAs/SM 2.22 ms of parse, 4 x 16: 2.11)
+#endif
+static const int GP_SCAN_ROUNDS = SCCG_GP_SCAN_ROUNDS;
 static const int GP_SCAN_TILE = GP_T * GP_SCAN_ROUNDS;
 
 __global__ void __launch_bounds__(GP_T) gp_lost_scan_k(GpScanArgs s) {
@@ -1130,7 +1133,7 @@ static int global_match_device(sccg_ctx* c, const u8* R, i64 nr, const u8* T, i6
     // state in device memory whether it has anything to do (front: not after the end; scan: only behind a front that got lost).
     int chain = 4;
     if (const char* env = getenv("SCCG_GP_CHAIN")) { int v = atoi(env); if (v >= 1 && v <= 64) chain = v; }              // tests
-    unsigned scan_grid = (unsigned)c->sm_count * 4u;
+    unsigned scan_grid = (unsigned)c->sm_count * 16u;
     if (const char* env = getenv("SCCG_GP_SCAN_GRID")) { int v = atoi(env); if (v >= 1) scan_grid = (unsigned)v; }       // tests: tiny grids
     unsigned long long* d_trace = nullptr;
     const bool tracing = getenv("SCCG_GP_TRACE") != nullptr;
