@@ -10,7 +10,7 @@ namespace sccg {
 // device scalars (u32 each)
 enum Scalar {
     S_LOW_K = 0, S_LOW_KE, S_LOW_TEXT, S_ABORT, S_BODY_MAIN, S_BODY_BASE, S_N_K, S_N_KE, S_N_TEXT,
-    S_G0, S_G1, S_G2, S_G3, S_G4, S_G5, S_G6, S_G7, S_PAREN, S_DT = 24 /* 4 slots */, S_WORK = 64, S_COUNT = 128   // S_WORK: own 128-byte line (hot atomic)
+    S_G0, S_G1, S_G2, S_G3, S_G4, S_G5, S_G6, S_G7, S_PAREN, S_DT = 24 /* 4 slots */, S_QUEUE = 32 /* own 128-byte line: number of queued segments */, S_WORK = 64, S_COUNT = 128   // S_WORK: own 128-byte line (hot atomic)
 };
 
 // writes the separator after the lowercase line and publishes where the body starts
@@ -119,6 +119,9 @@ static int enqueue_pair_upload(sccg_ctx* c, const char* ref, i64 ref_len, const 
 }
 
 static const int LM_PROBE_SEGS = 40;             // segments of the abort probe (see compress_device)
+// two-phase matcher launches (sccg_local.cuh, LM_DEFER / LM_QUEUE) for pairs of this many segments and more
+static inline int lm_two_phase_min() { const char* e = getenv("SCCG_LM_TWO_PHASE_MIN"); return e ? atoi(e) : 65536; }    // segments; tests force 0 / a huge value
+static inline int lm_queue_ctas() { const char* e = getenv("SCCG_LM_QUEUE_CTAS"); int v = e ? atoi(e) : 0; return v >= 1 && v <= LM_CTAS_PER_SM ? v : LM_CTAS_PER_SM; }
 
 static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt, i64 nt, const char* header, i64 nh, CompressResult* res,
                            const ChunkArrival* arr) {
@@ -184,6 +187,17 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
             if (arr) SCCG_CK(cudaStreamWaitEvent(c->stream, arr->ev_ref[i + 1 < n_launch ? i : arr->n - 1], 0));
             if (seg_hi <= seg_lo) continue;
             const unsigned w = div_up(seg_hi - seg_lo, LM_WARPS);
+            if (!arr && c->use_diag && n_iter >= lm_two_phase_min()) {
+                // device-resident pair: the bulk launch queues the segments that need the generic path (the queue lives in
+                // seg_bytes until seg_bytes_k overwrites it), a second launch with fewer warps per SM works them off
+                SCCG_SET_MAX_SMEM(seg_match_defer_k, smem);
+                SCCG_SET_MAX_SMEM(seg_match_queue_k, smem);
+                LAUNCH(c, seg_match_defer_k, dim3(w < cap ? w : cap), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, seg_lo, seg_hi, n_iter, K1, K2, seginfo, matches,
+                       sc + S_WORK + (i & 31), sc + S_ABORT, c->use_diag, seg_bytes, sc + S_QUEUE);
+                const unsigned qg = (unsigned)c->sm_count * (unsigned)lm_queue_ctas();
+                LAUNCH(c, seg_match_queue_k, dim3(w < qg ? w : qg), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, n_iter, K1, K2, seginfo, matches,
+                       sc + S_WORK + 30, sc + S_ABORT, seg_bytes, sc + S_QUEUE);
+            } else
             LAUNCH(c, seg_match_k<SCCG_LM_CLAIM>, dim3(w < cap ? w : cap), dim3(LM_WARPS * 32), smem, d_ref, nr, d_tgt, nt, seg_lo, seg_hi, n_iter, K1, K2, seginfo, matches,
                    sc + S_WORK + (i & 31), sc + S_ABORT, c->use_diag);
             seg_lo = seg_hi;

@@ -213,6 +213,7 @@ __device__ __forceinline__ int lm_parse(LmWarpSmem& S, const u32 (&wm)[4], int L
         const u32 qtag = lm_tag(hm);                                             // already positioned at bit 10
         const u32 tag = ld_unaligned32(S.t, j);
         LmFold f; f.best_l = 0; f.cnt = 0; f.zero_in = false; f.best_key = 0xffffffffu;
+        bool diag_folded = false;                                                // the diagonal candidate (p == j) has been folded: crowded buckets take it ahead of its turn
         while (c) {                                                              // :114 every candidate of the bucket
             // gather up to 32 chain entries whose first 4 symbols match (hash-chain false positives die here)
             int myp = -1, nb = 0;
@@ -226,17 +227,32 @@ __device__ __forceinline__ int lm_parse(LmWarpSmem& S, const u32 (&wm)[4], int L
                 // the common case: extend cooperatively, 128 symbols per step (extend_alignment :27-34)
                 for (int i = 0; i < nb; ++i) {
                     int p = __shfl_sync(SCCG_FULL_MASK, myp, i);
+                    if (p == j) { if (diag_folded) continue; diag_folded = true; }
                     int maxl = (Lr - p) < (Lt - j) ? (Lr - p) : (Lt - j);
                     int l = (p == j) ? diag_lcp(S, wm, j, Lmin) : warp_lcp(S.r, p, S.t, j, maxl);
                     if (l >= k) lm_fold_one(f, p, l, e);
                 }
             } else {
-                // crowded bucket (low-complexity sequence): one candidate per lane
+                // crowded bucket (low-complexity sequence, the border of an N run): one candidate per lane.  A candidate can
+                // only enter the fold if it reaches the best length so far (best_l never shrinks), so the diagonal candidate --
+                // usually the longest by far, and free to extend -- is folded first and every other candidate is dropped by one
+                // 4-byte compare at the far end of that length unless it really gets there.  (Without this the border segment of
+                // the chr1-sized pair's N block, 297 occurrences of N^14, took 117 us and was the last warp of the launch.)
+                if (!diag_folded) {
+                    diag_folded = true;                                          // (or it is no candidate at all: same thing for the lanes below)
+                    if (j < Lmin - k + 1 && kmer_equal_smem(S.r, j, S.t, j, k)) {
+                        const int ld = diag_lcp(S, wm, j, Lmin);
+                        if (ld >= k) lm_fold_one(f, j, ld, e);
+                    }
+                }
                 int l = 0;
-                if (myp >= 0) {
+                if (myp >= 0 && myp != j) {
                     int maxl = (Lr - myp) < (Lt - j) ? (Lr - myp) : (Lt - j);
-                    l = lane_lcp(S.r, myp, S.t, j, maxl);
-                    if (l < k) l = 0;
+                    const int need = f.best_l;                                   // >= 4 whenever it is set (k >= 10)
+                    if (maxl >= need && (need < 4 || ld_unaligned32(S.r, myp + need - 4) == ld_unaligned32(S.t, j + need - 4))) {
+                        l = lane_lcp(S.r, myp, S.t, j, maxl);
+                        if (l < k) l = 0;
+                    }
                 }
                 int bmax = (int)__reduce_max_sync(SCCG_FULL_MASK, (u32)l);
                 if (bmax > 0) {
@@ -506,10 +522,20 @@ __device__ __forceinline__ void lm_fetch(const u8* __restrict__ ref, const u8* _
 #endif
 // CLAIM: consecutive segments per claim (SCCG_LM_CLAIM for the bulk launches; 1 for the abort probe, which wants the
 // segments of a T2 window on different warps)
-template <int CLAIM>
-__global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(const u8* __restrict__ ref, i64 nr, const u8* __restrict__ tgt, i64 nt,
-                                                            int seg_begin, int n_iter, int n_total, int k1, int k2, u32* seginfo, u32* __restrict__ matches,
-                                                            u32* __restrict__ work_counter, u32* abort_flag, int use_diag) {
+// MODE (two-phase launches, device-resident pairs of 64 K segments and more).  6 % of the segments of a near-identical pair take
+// the generic path at 20-90 k cycles each, everything else 2-6 k.  The bulk launch (LM_DEFER) only QUEUES those segments and a
+// second launch (LM_QUEUE) works the queue off.  Measured on the chr1-sized pair: the two launches alone take as long as the
+// single one did (175 + 48 us against 208 -- the work is issue-bound, and neither fewer warps per SM nor heaviest-first order
+// in the second launch changed that), but the queue launch leaves room for the run-list kernels of the side lane, which
+// otherwise only start when the persistent CTAs of the matcher retire: compress step 0.359 -> 0.337 ms.
+//   LM_INLINE: everything in one launch (abort probe, pipelined uploads, small pairs, function-level calls)
+//   LM_DEFER : queue[atomicAdd(q_ctl, 1)] = seg for every segment that is neither identical nor decided by the diagonal path
+//   LM_QUEUE : segment ids come from queue[0 .. *q_ctl); CLAIM 1, work_counter a fresh counter
+enum { LM_INLINE = 0, LM_DEFER = 1, LM_QUEUE = 2 };
+template <int CLAIM, int MODE>
+__device__ __forceinline__ void seg_match_body(const u8* __restrict__ ref, i64 nr, const u8* __restrict__ tgt, i64 nt,
+                                               int seg_begin, int n_iter, int n_total, int k1, int k2, u32* seginfo, u32* __restrict__ matches,
+                                               u32* __restrict__ work_counter, u32* abort_flag, int use_diag, u32* queue, u32* q_ctl) {
     SCCG_DYN_SMEM(smem_raw);
     LmWarpSmem& S = reinterpret_cast<LmWarpSmem*>(smem_raw)[threadIdx.x >> 5];
     const int lane = lane_of();
@@ -538,6 +564,9 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
     bool tab_clean = false;                                   // S.head + S.next all zero (kept by the diagonal-hypothesis path)
     const u8* const pf_base = (lane < 8 ? ref : tgt) + 128 * (lane & 7);      // L2 prefetch of the next pair: lanes 0-7 the reference, 8-15 the target
     int seg = seg_begin + warp_global * claim < n_iter ? seg_begin + warp_global * claim : n_iter;
+    const int nq = MODE == LM_QUEUE ? (int)*q_ctl : 0;                   // (written by the launch before this one)
+    if (MODE == LM_QUEUE) seg = warp_global < nq ? (int)queue[warp_global] : n_iter;
+    if (MODE == LM_QUEUE) use_diag = 0;                                  // queued segments have been through the cheap paths
     while (seg < n_iter) {
         const i64 off = (i64)seg * SEG;
         const int Lr = (int)((nr - off) < SEG ? (nr - off) : SEG);
@@ -579,6 +608,7 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
             claimed_used = 0;
             next_seg = __shfl_sync(SCCG_FULL_MASK, next_seg, 0);
         }
+        if (MODE == LM_QUEUE) next_seg = next_seg < nq ? (int)queue[next_seg] : n_iter;      // (claim_base = warps in the grid: queue index -> segment)
 #ifndef SCCG_NO_EARLY_ABORT
         // checked before every segment (the flag lives in its own cache line, away from the claim atomics): a failing
         // segment is expensive, and after the abort nothing of this launch is used (:466-472)
@@ -613,6 +643,11 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
                 // near-identical segment: parse determined by the mismatch positions, hypothesis proven against all of r
                 direct = true;
                 SEG_STAT(1);
+            } else if (MODE == LM_DEFER) {
+                if (lane == 0) queue[atomicAdd(q_ctl, 1u)] = (u32)seg;
+                tab_clean = false;
+                seg = next_seg;
+                continue;                                     // seginfo[seg] stays "not done" until the queue launch
             } else {
                 SEG_STAT(2);
                 tab_clean = false;
@@ -688,6 +723,24 @@ __global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(c
 #endif
         seg = next_seg;
     }
+}
+
+template <int CLAIM>
+__global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_k(const u8* __restrict__ ref, i64 nr, const u8* __restrict__ tgt, i64 nt,
+                                                            int seg_begin, int n_iter, int n_total, int k1, int k2, u32* seginfo, u32* __restrict__ matches,
+                                                            u32* __restrict__ work_counter, u32* abort_flag, int use_diag) {
+    seg_match_body<CLAIM, LM_INLINE>(ref, nr, tgt, nt, seg_begin, n_iter, n_total, k1, k2, seginfo, matches, work_counter, abort_flag, use_diag, nullptr, nullptr);
+}
+// the two launches of a device-resident pair
+__global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_defer_k(const u8* __restrict__ ref, i64 nr, const u8* __restrict__ tgt, i64 nt,
+                                                            int seg_begin, int n_iter, int n_total, int k1, int k2, u32* seginfo, u32* __restrict__ matches,
+                                                            u32* __restrict__ work_counter, u32* abort_flag, int use_diag, u32* queue, u32* q_ctl) {
+    seg_match_body<SCCG_LM_CLAIM, LM_DEFER>(ref, nr, tgt, nt, seg_begin, n_iter, n_total, k1, k2, seginfo, matches, work_counter, abort_flag, use_diag, queue, q_ctl);
+}
+__global__ void __launch_bounds__(LM_WARPS * 32, SCCG_LM_MIN_CTAS) seg_match_queue_k(const u8* __restrict__ ref, i64 nr, const u8* __restrict__ tgt, i64 nt,
+                                                            int n_total, int k1, int k2, u32* seginfo, u32* __restrict__ matches,
+                                                            u32* __restrict__ work_counter, u32* abort_flag, u32* queue, u32* q_ctl) {
+    seg_match_body<1, LM_QUEUE>(ref, nr, tgt, nt, 0, n_total, n_total, k1, k2, seginfo, matches, work_counter, abort_flag, 0, queue, q_ctl);
 }
 
 // Segment driver bookkeeping (compression.cpp:395-474): T2 abort test, delta chain carry, text size.

@@ -1,7 +1,7 @@
 // N-stripping by stream compaction + upper-casing.
 //   compress side (global): toupper, then erase every 'N'   (compression.cpp:523-524, :556-557)  -> drops 'n' and 'N'
 //   decompress side       : erase every 'N', then toupper   (decompression.cpp:105-110)          -> keeps 'n' (becomes 'N')
-// HBM-bound: 1 B read per pass (two passes) + 1 B written per kept symbol (packed in shared memory, stored 16 B at a time).
+// HBM-bound: 1 B read + 1 B written per kept symbol (packed in shared memory, stored 16 B at a time), one pass.
 #pragma once
 #include "sccg_scan.cuh"
 
@@ -23,30 +23,6 @@ template <int UPPER_FIRST> __device__ __forceinline__ u32 strip_keep_mask(const 
     return m;
 }
 
-template <int UPPER_FIRST>
-__global__ void __launch_bounds__(STRIP_T) strip_count_k(const u8* __restrict__ src, i64 n, u32* __restrict__ cnt) {
-    __shared__ u32 sm[40];
-    i64 i = (i64)blockIdx.x * STRIP_TILE + (i64)threadIdx.x * 16;
-    ulonglong2 v;
-    u32 m = strip_keep_mask<UPPER_FIRST>(src, n, i, &v);
-    u32 tot;
-    block_scan_excl((u32)__popc(m), sm, &tot);
-    if (threadIdx.x == 0) cnt[blockIdx.x] = tot;
-}
-
-template <int UPPER_FIRST>
-__global__ void __launch_bounds__(STRIP_T) strip_write_k(const u8* __restrict__ src, i64 n, const u32* __restrict__ tile_off, u8* __restrict__ dst) {
-    __shared__ u32 sm[40];
-    __align__(16) __shared__ u8 stage[STRIP_TILE + 32];
-    i64 i = (i64)blockIdx.x * STRIP_TILE + (i64)threadIdx.x * 16;
-    ulonglong2 v;
-    v.x = 0; v.y = 0;
-    u32 m = strip_keep_mask<UPPER_FIRST>(src, n, i, &v);
-    u32 tot;
-    u32 excl = block_scan_excl((u32)__popc(m), sm, &tot);
-    block_compact_store(stage, dst + tile_off[blockIdx.x], excl, m, upper8(v.x), upper8(v.y), tot);
-}
-
 // out[i] = toupper(src[i]), 16 bytes per thread
 __global__ void __launch_bounds__(256) upper_k(const u8* __restrict__ src, i64 n, u8* __restrict__ dst) {
     i64 i = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 16;
@@ -56,16 +32,72 @@ __global__ void __launch_bounds__(256) upper_k(const u8* __restrict__ src, i64 n
     *reinterpret_cast<ulonglong2*>(dst + i) = v;                     // buffers are padded to 16 B
 }
 
+// Count, offsets and compaction in ONE pass over the source: a CTA owns STRIP_SUB consecutive 4 KiB blocks, counts what it
+// keeps, learns where its output begins by decoupled look-back over the tiles before it (the descriptors and the tile
+// counter of sccg_scan.cuh: tiles are numbered in start order, a tile only waits for tiles that are running) and stores.
+// 1 B read + 1 B written per symbol instead of 2 B read + 1 B written and a scan launch in between.
+static const int STRIP_SUB = 4;
+template <int UPPER_FIRST>
+__global__ void __launch_bounds__(STRIP_T) strip_onepass_k(const u8* __restrict__ src, i64 n, u8* __restrict__ dst, u64* desc, u32* counter, u32 counter_base,
+                                                           u32 epoch, u32* __restrict__ total_out) {
+    __shared__ u32 sm[40];
+    __shared__ u32 s_tile, s_prefix;
+    __align__(16) __shared__ u8 stage[STRIP_TILE + 32];
+    if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1u) - counter_base;
+    __syncthreads();
+    const u32 tile = s_tile;
+    const i64 base = (i64)tile * (STRIP_TILE * STRIP_SUB) + (i64)threadIdx.x * 16;
+    ulonglong2 v[STRIP_SUB];
+    u32 m[STRIP_SUB], excl[STRIP_SUB], sub_tot[STRIP_SUB];
+#pragma unroll
+    for (int q = 0; q < STRIP_SUB; ++q) { v[q].x = 0; v[q].y = 0; m[q] = strip_keep_mask<UPPER_FIRST>(src, n, base + (i64)q * STRIP_TILE, &v[q]); }
+    u32 tot = 0;
+#pragma unroll
+    for (int q = 0; q < STRIP_SUB; ++q) { excl[q] = block_scan_excl((u32)__popc(m[q]), sm, &sub_tot[q]); tot += sub_tot[q]; }
+    if (threadIdx.x < 32) {
+        const int lane = lane_of();
+        u32 prefix = 0;
+        if (tile == 0) {
+            if (lane == 0) SCCG_ST_RELAXED_U64(desc, scan_desc(epoch, 1u, tot));
+        } else {
+            if (lane == 0) SCCG_ST_RELAXED_U64(desc + tile, scan_desc(epoch, 0u, tot));
+            for (i64 top = (i64)tile - 1; top >= 0; top -= 32) {
+                const i64 idx = top - lane;
+                u64 d = scan_desc(epoch, 1u, 0u);
+                if (idx >= 0) { do { d = SCCG_LD_RELAXED_U64(desc + idx); } while ((u32)(d >> 33) != epoch); }
+                const u32 is_prefix = (u32)(d >> 32) & 1u;
+                const u32 bal = __ballot_sync(SCCG_FULL_MASK, is_prefix != 0u);
+                const int stop = bal ? __ffs((int)bal) - 1 : 31;
+                prefix += __reduce_add_sync(SCCG_FULL_MASK, lane <= stop ? (u32)d : 0u);
+                if (bal) break;
+            }
+            if (lane == 0) SCCG_ST_RELAXED_U64(desc + tile, scan_desc(epoch, 1u, prefix + tot));
+        }
+        if (lane == 0) {
+            s_prefix = prefix;
+            if ((i64)(tile + 1) * (STRIP_TILE * STRIP_SUB) >= n) *total_out = prefix + tot;
+        }
+    }
+    __syncthreads();
+    u32 off = s_prefix;
+#pragma unroll
+    for (int q = 0; q < STRIP_SUB; ++q) {
+        block_compact_store(stage, dst + off, excl[q], m[q], upper8(v[q].x), upper8(v[q].y), sub_tot[q]);
+        off += sub_tot[q];
+        __syncthreads();                                              // the staging area is refilled by the next block
+    }
+}
+
 // dst <- N-stripped, upper-cased src on the current lane; *d_count (device) receives the kept length.  No host round trip.
 template <int UPPER_FIRST>
 static int strip_n_enqueue(sccg_ctx* c, const u8* d_src, i64 n, u8* d_dst, int slot_cnt, u32* d_count) {
+    (void)slot_cnt;
     if (n <= 0) { SCCG_CK(cudaMemsetAsync(d_count, 0, sizeof(u32), c->stream)); return SCCG_OK; }
-    unsigned ntiles = div_up(n, STRIP_TILE);
-    u32* cnt = nullptr;
-    SCCG_TRY(buf(c, slot_cnt, (size_t)ntiles + 1, &cnt));
-    LAUNCH(c, strip_count_k<UPPER_FIRST>, dim3(ntiles), dim3(STRIP_T), 0, d_src, n, cnt);
-    SCCG_TRY(scan_exclusive_u32(c, cnt, cnt, (i64)ntiles, d_count));
-    LAUNCH(c, strip_write_k<UPPER_FIRST>, dim3(ntiles), dim3(STRIP_T), 0, d_src, n, (const u32*)cnt, d_dst);
+    const unsigned ntiles = div_up(n, STRIP_TILE * STRIP_SUB);
+    u64* desc = nullptr; u32* counter = nullptr; int ln = 0;
+    SCCG_TRY(scan_state(c, (size_t)ntiles, &desc, &counter, &ln));
+    LAUNCH(c, strip_onepass_k<UPPER_FIRST>, dim3(ntiles), dim3(STRIP_T), 0, d_src, n, d_dst, desc, counter, c->scan_counter_base[ln], c->scan_epoch[ln], d_count);
+    c->scan_counter_base[ln] += ntiles;                          // modulo 2^32, like the device counter
     return SCCG_OK;
 }
 

@@ -197,6 +197,51 @@ def test_diag_hypothesis_fuzz(ctx, seed):
         assert (gmode, got) == (mode, exp), (seed, it, ref, tgt)
 
 
+def crowded_bucket_pair(r: random.Random) -> tuple[bytes, bytes]:
+    """one segment pair whose k-mer index has a crowded bucket: a long run of one symbol (the border of an N block), a
+    short-period repeat or several copies of a stretch, with substitutions / small indels in and around it"""
+    n = r.choice([1000, 1000, 1000, r.randint(200, 999)])
+    ref = bytearray(r.choice(b"ACGT") for _ in range(n))
+    kind = r.randrange(4)
+    if kind == 0:                                   # run at the start / end / in the middle
+        ln = r.randint(20, min(700, n - 20)); at = r.choice([0, n - ln, r.randint(0, n - ln)])
+        ref[at:at + ln] = bytes([r.choice(b"NNNA")]) * ln
+    elif kind == 1:                                 # short-period repeat
+        unit = bytes(r.choice(b"ACGT") for _ in range(r.randint(2, 5)))
+        ln = r.randint(40, min(600, n - 20)); at = r.randint(0, n - ln)
+        ref[at:at + ln] = (unit * (ln // len(unit) + 1))[:ln]
+    elif kind == 2:                                 # two runs of the same symbol
+        for _ in range(2):
+            ln = r.randint(20, 200); at = r.randint(0, n - ln)
+            ref[at:at + ln] = b"N" * ln
+    else:                                           # many copies of one 40-mer
+        w = bytes(r.choice(b"ACGT") for _ in range(40))
+        for _ in range(r.randint(3, 12)):
+            at = r.randint(0, n - 40); ref[at:at + 40] = w
+    tgt = bytearray(ref)
+    for _ in range(r.randint(0, 6)):
+        x = r.randrange(len(tgt)); tgt[x] = r.choice(b"ACGTN")
+    if r.random() < 0.3:
+        x = r.randrange(len(tgt)); d = r.randint(1, 6)
+        tgt[x:x] = bytes(r.choice(b"ACGTN") for _ in range(d)); del tgt[-d:]
+    if r.random() < 0.2:
+        tgt = tgt[r.randint(1, 30):] + bytearray(r.choice(b"ACGT") for _ in range(10))
+    return bytes(ref), bytes(tgt[:1000])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_crowded_buckets_vs_oracle(ctx, seed):
+    """low-complexity segments: dozens to hundreds of candidates per looked-up k-mer, ties between them (the tie-break of
+    compression.cpp:114-130 decides), the diagonal candidate folded ahead of its turn and the rest pruned by length"""
+    r = random.Random(repr(("crowd", seed)))
+    for it in range(40):
+        ref, tgt = crowded_bucket_pair(r)
+        for k in (14, 10):
+            exp = [(x.p, x.l, x.lit) for x in ol.orc_match_sequences(ref, tgt, k, 0, False, 0)]
+            got = [(x.p, x.l, x.lit) for x in ctx.match_sequences(ref, tgt, k, 0, False, 0)]
+            assert got == exp, (seed, it, k, ref, tgt)
+
+
 @pytest.mark.parametrize("chunk", [4096, 50000])
 def test_compress_chunked_upload(ctx, chunk, monkeypatch):
     """host entry point: the reference arrives in chunks and the segment matcher is launched once per chunk"""
@@ -373,6 +418,32 @@ def test_compress_device_abort_probe(ctx, shape):
     got, gmode = _compress_device_emu(ctx, ref, tgt, b">probe")
     assert (gmode, got) == (mode, exp)
     assert mode == (1 if shape in ("shifted_tail", "reference_insertion") else 0)
+
+
+@pytest.mark.parametrize("two_phase", [1, 0])
+@pytest.mark.parametrize("seed", range(6))
+def test_compress_device_two_phase_matcher(ctx, seed, two_phase, monkeypatch):
+    """device-resident pairs: the bulk launch of the matcher queues the segments that need the generic path, a second launch
+    works the queue off (pairs of 64 K segments and more; forced here for small ones, and off) -- same file either way, the oracle's"""
+    monkeypatch.setenv("SCCG_LM_TWO_PHASE_MIN", "0" if two_phase else "2000000000")
+    r = random.Random(repr(("2ph", seed)))
+    if seed % 3 == 0:
+        ref, tgt = _mutated_pair(("2ph", seed), 40_000, b"ACGT", snp=0.004, indel=0.0)          # equal lengths: identical / diagonal / generic mix
+        t = bytearray(tgt)
+        for _ in range(12):                                                                       # compensated indels: generic segments
+            x = r.randrange(1000, len(t) - 1000); d = r.randint(1, 8)
+            t[x:x] = bytes(r.choice(b"ACGT") for _ in range(d)); del t[x + 150:x + 150 + d]
+        tgt = bytes(t)
+    elif seed % 3 == 1:
+        pairs = [crowded_bucket_pair(r) for _ in range(30)]
+        pairs = [(a, b) for a, b in pairs if len(a) == 1000 and len(b) == 1000]
+        ref = b"".join(a for a, _ in pairs) + rnd(700, ("2ph-tail", seed)); tgt = b"".join(b for _, b in pairs) + rnd(350, ("2ph-tail2", seed))
+    else:
+        ref, tgt = _mutated_pair(("2ph", seed), 25_000, b"ACGTacgtN", snp=0.01, indel=0.0005)    # drifting diagonals, some failing segments
+    rc, exp, mode = ol.orc_compress(ref, tgt, b">two phase")
+    assert rc == 0
+    got, gmode = _compress_device_emu(ctx, ref, tgt, b">two phase")
+    assert (gmode, got) == (mode, exp)
 
 
 @pytest.mark.parametrize("bits", [4, 16, 24])

@@ -10,7 +10,7 @@ import pytest
 
 import oracle_lib as ol
 from cases import cases
-from test_emu_compress import _mutated_pair, check_compress_like_oracle, diag_fuzz_pair, grammar_pair
+from test_emu_compress import _mutated_pair, check_compress_like_oracle, crowded_bucket_pair, diag_fuzz_pair, grammar_pair
 
 pytestmark = pytest.mark.gpu
 CASES = cases()
@@ -244,3 +244,43 @@ def test_output_buffer_guess_too_small(monkeypatch):
 def test_lowercase_line_shapes(ctx):
     import robustness_cases
     robustness_cases.check_lowercase_line_shapes(ctx)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_crowded_buckets_vs_oracle(ctx, seed):
+    """low-complexity segments (runs of one symbol, short-period repeats, many copies of a stretch): crowded index buckets, ties
+    between candidates, the length pruning of lm_parse; function level and as whole files of many such segments"""
+    r = random.Random(repr(("crowd-gpu", seed)))
+    refs, tgts = [], []
+    for it in range(60):
+        ref, tgt = crowded_bucket_pair(r)
+        if it < 25:
+            for k in (14, 10):
+                exp = [(x.p, x.l, x.lit) for x in ol.orc_match_sequences(ref, tgt, k, 0, False, 0)]
+                got = [(x.p, x.l, x.lit) for x in ctx.match_sequences(ref, tgt, k, 0, False, 0)]
+                assert got == exp, (seed, it, k, ref, tgt)
+        if len(ref) == 1000 and len(tgt) == 1000:
+            refs.append(ref); tgts.append(tgt)
+    ref, tgt = b"".join(refs), b"".join(tgts)
+    rc, exp, mode = ol.orc_compress(ref, tgt, b">crowded")
+    assert rc == 0
+    got, gmode = ctx.compress(ref, tgt, b">crowded")
+    assert (gmode, got) == (mode, exp)
+
+
+@pytest.mark.parametrize("two_phase", [1, 0])
+def test_compress_device_two_phase_matcher(ctx, two_phase, monkeypatch):
+    """device-resident pair: bulk matcher launch + queue launch for the segments that need the generic path (forced on for this
+    small pair / forced off) -- the oracle's file either way"""
+    import torch
+    from sccg_genome_compression_b200 import synth
+    monkeypatch.setenv("SCCG_LM_TWO_PHASE_MIN", "0" if two_phase else "2000000000")
+    ref, tgt = synth.local_pair(6_000_000, synth.seed_for(2, 21))
+    rb, tb = ref.tobytes(), tgt.tobytes()
+    rc, exp, mode = ol.orc_compress(rb, tb, b">two phase")
+    assert rc == 0 and mode == 0
+    pad = torch.zeros(64, dtype=torch.uint8)
+    d_ref = torch.cat([torch.from_numpy(ref), pad]).cuda(); d_tgt = torch.cat([torch.from_numpy(tgt), pad]).cuda()
+    for rep in range(2):
+        ptr, n, gmode = ctx.compress_device(d_ref.data_ptr(), ref.size, d_tgt.data_ptr(), tgt.size, b">two phase")
+        assert (gmode, ctx.download(ptr, n)) == (mode, exp)

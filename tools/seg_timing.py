@@ -9,7 +9,10 @@ import numpy as np, torch
 import sccg_b200
 from sccg_genome_compression_b200 import synth
 so = "/tmp/libsccg_timing.so"
-subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "--cudart", "static",
+prebuilt = [a for a in sys.argv[1:] if a.endswith(".so")]
+sys.argv = [a for a in sys.argv if not a.endswith(".so")]
+if prebuilt: so = prebuilt[0]
+else: subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "--cudart", "static",
                        "-ccbin", "/usr/bin/g++", "-DSCCG_SEG_TIMING", "-o", so, str(ROOT / "sccg-genome-compression_b200/csrc/sccg_b200.cu")])
 chrom = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 ref, tgt = synth.local_pair(synth.CHR1_LEN, synth.seed_for(2, chrom))
@@ -32,5 +35,9 @@ for i in top:
     r = ref[i * 1000:(i + 1) * 1000]; t = tu[i * 1000:(i + 1) * 1000]
     m = min(r.size, t.size)
     print(f"seg {i}: cycles {c[i]}  mismatches {(r[:m] != t[:m]).sum()}  rN {(r == 78).sum()} tN {(t == 78).sum()}  r[:40]={r[:40].tobytes()}")
+reg = 10_000                                     # segments per region (10 Mbp)
+for a in range(0, nseg, reg):
+    x = c[a:a + reg]
+    print(f"segments {a:>7d}..: mean cycles {x.mean():9.0f}  max {x.max():9d}  > 100k cycles: {(x > 100000).sum()}")
 hist = np.bincount(np.minimum(c // 20000, 50).astype(np.int64))
 print("histogram (20k-cycle bins):", hist.tolist())
