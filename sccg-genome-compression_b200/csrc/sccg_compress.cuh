@@ -146,6 +146,9 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
     // (Measured and dropped: preparing the inputs of global mode -- N-strip of both sequences -- on the side lane underneath the
     // probe for pairs of different length: the local attempt gets as much slower as the preparation takes, 1.19 ms either way.)
     const bool probe = !arr && n_iter > 4 * LM_PROBE_SEGS && (nr > nt ? nr - nt : nt - nr) >= SEG;
+    // (measured and dropped: starting the run-list lane behind the bulk launch of a two-phase matcher -- the bulk launch got no
+    // faster alone, the step went from 0.339 to 0.414 ms)
+    const bool two_phase = !arr && c->use_diag && n_iter > 0 && n_iter >= lm_two_phase_min();
     {
         SideLane side(c);
         SCCG_TRY(rle_count<0>(c, d_tgt, nt, B_RUN_CNT, B_RUN_MASK, &cnt_s, &cnt_e, &low_mask, sc + S_LOW_K, sc + S_LOW_KE, sc + S_PAREN));
@@ -187,7 +190,7 @@ static int compress_device(sccg_ctx* c, const u8* d_ref, i64 nr, const u8* d_tgt
             if (arr) SCCG_CK(cudaStreamWaitEvent(c->stream, arr->ev_ref[i + 1 < n_launch ? i : arr->n - 1], 0));
             if (seg_hi <= seg_lo) continue;
             const unsigned w = div_up(seg_hi - seg_lo, LM_WARPS);
-            if (!arr && c->use_diag && n_iter >= lm_two_phase_min()) {
+            if (two_phase) {
                 // device-resident pair: the bulk launch queues the segments that need the generic path (the queue lives in
                 // seg_bytes until seg_bytes_k overwrites it), a second launch with fewer warps per SM works them off
                 SCCG_SET_MAX_SMEM(seg_match_defer_k, smem);

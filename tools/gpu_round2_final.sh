@@ -11,7 +11,7 @@ done
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_chr1.csv python tools/one_chr1.py 2 > $O/ncu_launch.log 2>&1; echo "launch list rc=$?"
 python - <<PY
 import json
-d=json.load(open("$O/bench.json"))
+d=json.loads([l for l in open("$O/bench.json") if l.startswith("{")][-1])      # (NCCL may print its version banner first)
 print("compress", d["ms_per_step"], d["value"], "frac", d["roofline"]["frac"], "decompress", d["decompress"]["ms_per_step"], "e2e", d["e2e"]["ms_per_step"], d["decompress"]["e2e"]["ms_per_step"])
 for k in ("global_gap_chr19", "global_divergent_chr21"):
     g=d[k]; print(k, g["ms_per_step"], g["index_ms"], g["parse_ms"], g["e2e"]["ms_per_step"], g.get("verified_against_oracle"), g.get("parity_vs_reference"), g.get("index_stride"))
