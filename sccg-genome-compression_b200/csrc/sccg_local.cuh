@@ -102,23 +102,86 @@ __device__ __forceinline__ int diag_lcp(const LmWarpSmem& S, const u32 (&wm)[4],
     return lim;
 }
 
-// k-mer index of r[0..Lr) (compression.cpp:41-47) as a chained hash table
-__device__ __forceinline__ void lm_build_index(LmWarpSmem& S, int Lr, int k) {
+// Runs of one symbol (the border of an N block, poly-A): every position of such a run of r holds the same k-mer, a bucket with
+// hundreds of entries -- a chain the parse would walk entry by entry, with one extension each.  Those k-mers are kept OUT of
+// the chains: lm_runs lists the maximal runs of length >= k of r (S.mis = first symbol, S.qv = one past the last; the
+// diagonal-hypothesis path is done with both arrays when the generic path starts), and a looked-up k-mer that is itself a run
+// of one symbol gets its candidates from that list in closed form (lm_fold_runs).  Returns the number of runs, or -1 if there
+// are more than LM_MAX_RUNS (then every k-mer goes into the chains and nothing changes).
+// A run of >= 7 equal symbols contains a 4-byte aligned word of 4 equal symbols: the lanes look at their 8 words of r, the
+// lane that owns the FIRST such word of a run measures the run.
+static const int LM_MAX_RUNS = 32;
+__device__ __forceinline__ int lm_runs(LmWarpSmem& S, int Lr, int k) {
+    const int lane = lane_of();
+    const u32* r32 = reinterpret_cast<const u32*>(S.r);
+    // quick look first (nine segments in ten have no such run): a run of >= 10 symbols around a word of 4 equal symbols also
+    // fills the 3 symbols before or the 3 symbols after that word
+    {
+        bool cand = false;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int q = 32 * it + lane;
+            const u32 x = r32[q];                                                // (words past Lr are zero padding inside the buffer: harmless here, checked below)
+            if (x == __funnelshift_r(x, x, 8) && 4 * q + 4 <= Lr)
+                cand = cand || (q > 0 && (r32[q - 1] >> 8) == (x >> 8)) || (r32[q + 1] & 0xffffffu) == (x & 0xffffffu);
+        }
+        if (!__any_sync(SCCG_FULL_MASK, cand)) return 0;
+    }
+    int n_runs = 0;
+    for (int it = 0; it < 8; ++it) {                                             // word q = 32 * it + lane: uniform trip count
+        const int q = 32 * it + lane;
+        int a = 0, b = 0;
+        bool first = false;
+        if (4 * q + 4 <= Lr) {
+            const u32 x = r32[q];
+            if (x == __funnelshift_r(x, x, 8)) {                                 // 4 equal symbols
+                const u8 sym = (u8)x;
+                first = q == 0 || r32[q - 1] != x;                               // the word before belongs to the same run: not mine
+                if (first) {
+                    a = 4 * q; while (a > 0 && S.r[a - 1] == sym) --a;           // <= 3 steps (the word before is not all sym)
+                    int qq = q + 1;
+                    while (4 * qq + 4 <= Lr && r32[qq] == x) ++qq;               // whole words of the run, then <= 3 symbols
+                    b = 4 * qq; while (b < Lr && S.r[b] == sym) ++b;
+                    first = b - a >= k;
+                }
+            }
+        }
+        const u32 bal = __ballot_sync(SCCG_FULL_MASK, first);
+        if (bal) {
+            const int slot = n_runs + __popc(bal & ((1u << lane) - 1u));
+            if (first && slot < LM_MAX_RUNS) { S.mis[slot] = (u16)a; S.qv[slot] = (u16)b; }
+            n_runs += __popc(bal);
+        }
+    }
+    __syncwarp();
+    return n_runs <= LM_MAX_RUNS ? n_runs : -1;
+}
+
+// k-mer index of r[0..Lr) (compression.cpp:41-47) as a chained hash table; k-mers inside the n_runs listed runs of one
+// symbol are left out (see lm_runs)
+__device__ __forceinline__ void lm_build_index(LmWarpSmem& S, int Lr, int k, int n_runs) {
     const int lane = lane_of();
     for (int x = lane; x < LM_HT; x += 32) S.head[x] = 0u;
     __syncwarp();
     int nk = Lr - k + 1;
     if (nk > 0) {
         const u32 mul = 1u << lm_hash_shift(k);
-        int chunk = (nk + 31) >> 5;
+        int chunk = (nk + 31) >> 5;                                              // <= 31 positions per lane
         int p = lane * chunk;
         int p1 = p + chunk < nk ? p + chunk : nk;
         if (p < p1) {
+            u32 skip = 0u;                                                       // bit i: the k-mer at p + i lies inside a listed run
+            for (int i = 0; i < n_runs; ++i) {
+                const int lo = (int)S.mis[i] - p, hi = (int)S.qv[i] - k - p;     // positions lo .. hi of this lane's chunk
+                if (hi >= 0 && lo < 32) skip |= (hi >= 31 ? 0xffffffffu : (2u << hi) - 1u) & (lo <= 0 ? 0xffffffffu : ~((1u << lo) - 1u));
+            }
+            const int p0 = p;
             u32 h = 0u;
             for (int i = 0; i < k - 1; ++i) h = h * mul + S.r[p + i];
             const u8* in = S.r + (k - 1);
             for (; p < p1; ++p) {
                 h = h * mul + in[p];                                             // slide: symbol p + k - 1 enters
+                if ((skip >> (p - p0)) & 1u) continue;
                 u32 hm = lm_mix(h);
                 u32 old = atomicExch(&S.head[lm_bucket(hm)], (u32)(p + 1) | lm_tag(hm));
                 S.next[p] = (u16)old;
@@ -176,8 +239,59 @@ __device__ __forceinline__ void lm_fold_one(LmFold& f, int p, int l, int e) {
     }
 }
 
+// Candidates of a looked-up k-mer t[j..j+k) that is a run of one symbol sym (see lm_runs), folded in closed form.  tr = length
+// of the run of sym in t from j on (>= k).  In a run [a, b) of sym in r the candidates are p = a .. b - k, with rr = b - p
+// symbols of the run ahead of them:
+//   rr < tr: the reference leaves the run first, l = rr          rr > tr: the target leaves it first, l = tr
+//   rr == tr (p* = b - tr): both leave it together, l = tr + lcp(r[b..], t[j+tr..])
+// so if tr > b - a the longest is p = a alone (l = b - a); else p* is the longest if it gets past the run, and if it does not
+// every p in [a, p*] ties at l = tr (the tie-break of :124-126 picks the one nearest to e: a clamp).  All lanes, uniform.
+__device__ __forceinline__ void lm_fold_runs(LmWarpSmem& S, LmFold& f, int n_runs, u8 sym, int j, int tr, int e, int Lr, int Lt) {
+    for (int i = 0; i < n_runs; ++i) {
+        const int a = (int)S.mis[i], b = (int)S.qv[i];
+        if (S.r[a] != sym) continue;
+        if (tr > b - a) { lm_fold_one(f, a, b - a, e); continue; }
+        const int ps = b - tr;
+        int ext = 0;
+        if (b < Lr && j + tr < Lt) ext = warp_lcp(S.r, b, S.t, j + tr, (Lr - b) < (Lt - j - tr) ? (Lr - b) : (Lt - j - tr));
+        if (ext > 0) { lm_fold_one(f, ps, tr + ext, e); continue; }
+        // a .. ps all reach exactly tr
+        if (tr > f.best_l) { f.best_l = tr; f.cnt = 0; f.zero_in = false; f.best_key = 0xffffffffu; }
+        if (tr == f.best_l) {
+            f.cnt += ps - a + 1;
+            if (a == 0) f.zero_in = true;
+            const int lo = a > 1 ? a : 1;
+            if (lo <= ps) {
+                const int pn = e < lo ? lo : (e > ps ? ps : e);
+                int d = pn - e; if (d < 0) d = -d;
+                const u32 key = ((u32)d << 16) | (u32)pn;
+                if (key < f.best_key) f.best_key = key;
+            }
+        }
+    }
+}
+// length of the run of sym in t from j on (t[j] == sym), capped at Lt - j; all lanes, uniform
+__device__ __forceinline__ int lm_run_len_t(const LmWarpSmem& S, u8 sym, int j, int Lt) {
+    const int lane = lane_of();
+    const u32 pat = (u32)sym * 0x01010101u;
+    const int maxl = Lt - j;
+    for (int base = 0; base < maxl; base += 128) {
+        const int o = base + 4 * lane;
+        u32 diff = 0xffffffffu;
+        if (o < maxl) diff = ld_unaligned32(S.t, j + o) ^ pat;
+        const u32 bal = __ballot_sync(SCCG_FULL_MASK, diff != 0u);
+        if (bal) {
+            const int src = __ffs((int)bal) - 1;
+            const u32 d = __shfl_sync(SCCG_FULL_MASK, diff, src);
+            const int l = base + 4 * src + ((__ffs((int)d) - 1) >> 3);
+            return l < maxl ? l : maxl;
+        }
+    }
+    return maxl;
+}
+
 // the greedy parse of one segment (compression.cpp:64-167); returns the number of matches, stored in S.mlist
-__device__ __forceinline__ int lm_parse(LmWarpSmem& S, const u32 (&wm)[4], int Lr, int Lt, int k, u32 powk) {
+__device__ __forceinline__ int lm_parse(LmWarpSmem& S, const u32 (&wm)[4], int Lr, int Lt, int k, u32 powk, int n_runs) {
     const int Lmin = Lr < Lt ? Lr : Lt;
     const int lane = lane_of();
     int j = 0, e = -1, nmatch = 0, misses = 0;
@@ -193,10 +307,14 @@ __device__ __forceinline__ int lm_parse(LmWarpSmem& S, const u32 (&wm)[4], int L
             bool hit = false;
             if (jj < Lt - k + 1) {
                 u32 h = 0u;
-                for (int x = 0; x < k; ++x) h = mad_u32(h, mul, S.t[jj + x]);
+                bool one_sym = n_runs > 0;                                       // (only worth knowing when r has runs at all)
+                for (int x = 0; x < k; ++x) { const u8 cx = S.t[jj + x]; h = mad_u32(h, mul, cx); one_sym = one_sym && cx == S.t[jj]; }
+                if (one_sym) {                                                   // a run of one symbol: its occurrences are the listed runs of that symbol
+                    for (int i = 0; i < n_runs; ++i) hit = hit || S.r[S.mis[i]] == S.t[jj];
+                }
                 const u32 hm = lm_mix(h);
                 const u32 qt = lm_tag(hm), t4 = ld_unaligned32(S.t, jj);
-                for (u32 c = S.head[lm_bucket(hm)]; c && !hit;) {
+                for (u32 c = one_sym ? 0u : S.head[lm_bucket(hm)]; c && !hit;) {
                     const int p = (int)(c & 0x3ffu) - 1;
                     if ((c & 0xfc00u) == qt && ld_unaligned32(S.r, p) == t4 && kmer_equal_smem(S.r, p, S.t, jj, k)) hit = true;
                     c = S.next[p];
@@ -213,6 +331,12 @@ __device__ __forceinline__ int lm_parse(LmWarpSmem& S, const u32 (&wm)[4], int L
         const u32 qtag = lm_tag(hm);                                             // already positioned at bit 10
         const u32 tag = ld_unaligned32(S.t, j);
         LmFold f; f.best_l = 0; f.cnt = 0; f.zero_in = false; f.best_key = 0xffffffffu;
+        if (n_runs > 0 && __all_sync(SCCG_FULL_MASK, lane >= k || S.t[j + lane] == S.t[j])) {
+            // the looked-up k-mer is a run of one symbol: candidates from the run list, nothing of the kind is in the chains
+            const u8 sym = S.t[j];
+            lm_fold_runs(S, f, n_runs, sym, j, lm_run_len_t(S, sym, j, Lt), e, Lr, Lt);
+            c = 0u;
+        }
         bool diag_folded = false;                                                // the diagonal candidate (p == j) has been folded: crowded buckets take it ahead of its turn
         while (c) {                                                              // :114 every candidate of the bucket
             // gather up to 32 chain entries whose first 4 symbols match (hash-chain false positives die here)
@@ -444,26 +568,31 @@ __device__ __forceinline__ int lm_diag_parse(LmWarpSmem& S, const u64 (&rw)[4], 
             hit |= (xo - 1u) < 1023u;
         }
         if (__any_sync(SCCG_FULL_MASK, hit)) {
-            // rare: some chunk of r has the content of a looked-up chunk at another position -- is it a whole k-mer?
-            if (hit) {
+            // rare: some chunk of r has the content of a looked-up chunk at another position -- is it a whole k-mer?  One real
+            // occurrence rejects the hypothesis, so the warp leaves at the first one any lane finds (a segment with a shifted
+            // stretch -- an insertion and a deletion a few dozen symbols apart -- has dozens of them: checking them all cost
+            // such a segment 50 k cycles, half of its total).
 #pragma unroll 1
-                for (int x = 0; x < 8; ++x) {
+            for (int x = 0; x < 8; ++x) {
+                if (hit) {
                     const int ra = (x < 4 ? 0 : 512) + 16 * lane + 4 * (x & 3);
                     const u32* r32 = reinterpret_cast<const u32*>(S.r) + (ra >> 2);   // (re-read: indexing the register copy would put it on the stack)
                     const u32 h = dv_hash(r32[0], r32[1]);
                     const u32 ent = tab[(h >> alt) & (u32)(DV_TAB - 1)];
                     const u32 xo = ((h & ~1023u) | 1024u | (u32)ra) ^ ent;
-                    if ((xo - 1u) >= 1023u) continue;
-                    const int u = (int)(ent & 1023u);
+                    if ((xo - 1u) < 1023u) {
+                        const int u = (int)(ent & 1023u);
 #pragma unroll 1
-                    for (int v = 0; v < nq; ++v) {
-                        const int j = (int)(S.qv[v] & 0x3ffu);
-                        const int d = u - j;
-                        if (d < 0 || d > 3) continue;
-                        const int pp = ra - d;
-                        if (pp >= 0 && pp <= L - k && kmer_equal_smem(S.r, pp, S.t, j, k)) bad = true;
+                        for (int v = 0; v < nq && !bad; ++v) {
+                            const int j = (int)(S.qv[v] & 0x3ffu);
+                            const int d = u - j;
+                            if (d < 0 || d > 3) continue;
+                            const int pp = ra - d;
+                            if (pp >= 0 && pp <= L - k && kmer_equal_smem(S.r, pp, S.t, j, k)) bad = true;
+                        }
                     }
                 }
+                if (__any_sync(SCCG_FULL_MASK, bad)) break;
             }
         }
     }
@@ -576,6 +705,10 @@ __device__ __forceinline__ void seg_match_body(const u8* __restrict__ ref, i64 n
         __syncwarp();                                        // previous segment fully consumed
 #ifdef SCCG_SEG_TIMING
         const long long t_begin = clock64();
+        long long t_ph[6] = {0, 0, 0, 0, 0, 0};
+#define SEG_PHASE(i) t_ph[i] = clock64()
+#else
+#define SEG_PHASE(i)
 #endif
         u32 wm[4];                                           // diagonal-0 mismatch flags per 8-byte word (uniform)
         // upper-case in place (:369-370) and compare on the diagonal, all in registers: an identical pair never touches shared memory
@@ -638,6 +771,7 @@ __device__ __forceinline__ void seg_match_body(const u8* __restrict__ ref, i64 n
             }
             if (lane < 2) reinterpret_cast<u64*>(S.r)[128 + lane] = 0ull, reinterpret_cast<u64*>(S.t)[128 + lane] = 0ull;
             __syncwarp();
+            SEG_PHASE(0);
             if (use_diag && Lr == Lt && Lt >= k1 && k1 >= 11 &&
                 (nmatch = lm_diag_parse(S, nrw, ntw, wm, Lt, k1, tab_clean, matches + (i64)seg * LM_SLOT, covered)) > 0) {
                 // near-identical segment: parse determined by the mismatch positions, hypothesis proven against all of r
@@ -663,8 +797,14 @@ __device__ __forceinline__ void seg_match_body(const u8* __restrict__ ref, i64 n
                     }
 #endif
                     if (pass) SEG_STAT(3);
-                    lm_build_index(S, Lr, k);
-                    nmatch = lm_parse(S, wm, Lr, Lt, k, pass ? pow2 : pow1);
+                    if (!pass) SEG_PHASE(1);
+                    int n_runs = lm_runs(S, Lr, k);
+                    if (n_runs < 0) n_runs = 0;                                   // too many runs to list: every k-mer goes into the chains
+                    if (!pass) SEG_PHASE(2);
+                    lm_build_index(S, Lr, k, n_runs);
+                    if (!pass) SEG_PHASE(3);
+                    nmatch = lm_parse(S, wm, Lr, Lt, k, pass ? pow2 : pow1, n_runs);
+                    if (!pass) SEG_PHASE(4);
                     if (nmatch) break;
                 }
             }
@@ -719,7 +859,19 @@ __device__ __forceinline__ void seg_match_body(const u8* __restrict__ ref, i64 n
             }
         }
 #ifdef SCCG_SEG_TIMING
-        if (lane == 0 && g_seg_cycles) g_seg_cycles[seg] = (unsigned long long)(clock64() - t_begin);
+        if (lane == 0 && g_seg_cycles) {
+            const long long t_end = clock64();
+            g_seg_cycles[seg] = (unsigned long long)(t_end - t_begin);
+            // phases (generic segments): the tool allocates 6 arrays of n_total entries behind the totals
+            if (t_ph[1]) {
+                g_seg_cycles[(size_t)n_total * 1 + seg] = (unsigned long long)(t_ph[0] - t_begin);
+                g_seg_cycles[(size_t)n_total * 2 + seg] = (unsigned long long)(t_ph[1] - t_ph[0]);
+                g_seg_cycles[(size_t)n_total * 3 + seg] = (unsigned long long)(t_ph[2] - t_ph[1]);
+                g_seg_cycles[(size_t)n_total * 4 + seg] = (unsigned long long)(t_ph[3] - t_ph[2]);
+                g_seg_cycles[(size_t)n_total * 5 + seg] = (unsigned long long)(t_ph[4] - t_ph[3]);
+                g_seg_cycles[(size_t)n_total * 6 + seg] = (unsigned long long)(t_end - t_ph[4]);
+            }
+        }
 #endif
         seg = next_seg;
     }

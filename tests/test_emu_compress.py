@@ -221,6 +221,14 @@ def crowded_bucket_pair(r: random.Random) -> tuple[bytes, bytes]:
     tgt = bytearray(ref)
     for _ in range(r.randint(0, 6)):
         x = r.randrange(len(tgt)); tgt[x] = r.choice(b"ACGTN")
+    for _ in range(r.randint(0, 2)):                # runs of one symbol grow / shrink in the target (closed-form candidate fold of lm_fold_runs)
+        x = r.randrange(len(tgt)); d = r.randint(1, 30)
+        if r.random() < 0.5:
+            tgt[x:x] = bytes([tgt[x]]) * d
+        else:
+            del tgt[x:x + d]
+    if r.random() < 0.15:
+        tgt = bytearray(b"N" * r.randint(10, 60)) + tgt
     if r.random() < 0.3:
         x = r.randrange(len(tgt)); d = r.randint(1, 6)
         tgt[x:x] = bytes(r.choice(b"ACGTN") for _ in range(d)); del tgt[-d:]
