@@ -103,30 +103,31 @@ __device__ __forceinline__ int diag_lcp(const LmWarpSmem& S, const u32 (&wm)[4],
 }
 
 // Runs of one symbol (the border of an N block, poly-A): every position of such a run of r holds the same k-mer, a bucket with
-// hundreds of entries -- a chain the parse would walk entry by entry, with one extension each.  Those k-mers are kept OUT of
-// the chains: lm_runs lists the maximal runs of length >= k of r (S.mis = first symbol, S.qv = one past the last; the
-// diagonal-hypothesis path is done with both arrays when the generic path starts), and a looked-up k-mer that is itself a run
-// of one symbol gets its candidates from that list in closed form (lm_fold_runs).  Returns the number of runs, or -1 if there
-// are more than LM_MAX_RUNS (then every k-mer goes into the chains and nothing changes).
-// A run of >= 7 equal symbols contains a 4-byte aligned word of 4 equal symbols: the lanes look at their 8 words of r, the
-// lane that owns the FIRST such word of a run measures the run.
+// hundreds of entries -- a chain the parse would walk entry by entry, with one extension each.  The k-mers of LONG runs are
+// kept out of the chains: lm_runs lists the maximal runs of r of at least max(k, 15) symbols (S.mis = first symbol, S.qv = one
+// past the last; the diagonal-hypothesis path is done with both arrays when the generic path starts), and a looked-up k-mer
+// that is itself a run of one symbol gets those candidates from the list in closed form (lm_fold_runs) and the rest -- runs
+// shorter than 15 -- from its chain as usual.  Returns the number of runs, or -1 if there are more than LM_MAX_RUNS (then
+// every k-mer goes into the chains and nothing changes).
+// 15 symbols because such a run contains an 8-byte aligned word of 8 equal symbols: the test "does this segment have a long
+// run at all" is four 8-byte loads and compares per lane, and almost always says no.
+// In the listing pass the lanes look at their eight 4-byte words of r; the lane that owns the FIRST word of 4 equal symbols of
+// a run measures the run.
 static const int LM_MAX_RUNS = 32;
+static const int LM_RUN_MIN = 15;
 __device__ __forceinline__ int lm_runs(LmWarpSmem& S, int Lr, int k) {
     const int lane = lane_of();
     const u32* r32 = reinterpret_cast<const u32*>(S.r);
-    // quick look first (nine segments in ten have no such run): a run of >= 10 symbols around a word of 4 equal symbols also
-    // fills the 3 symbols before or the 3 symbols after that word
     {
         bool cand = false;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int q = 32 * it + lane;
-            const u32 x = r32[q];                                                // (words past Lr are zero padding inside the buffer: harmless here, checked below)
-            if (x == __funnelshift_r(x, x, 8) && 4 * q + 4 <= Lr)
-                cand = cand || (q > 0 && (r32[q - 1] >> 8) == (x >> 8)) || (r32[q + 1] & 0xffffffu) == (x & 0xffffffu);
+        for (int it = 0; it < 4; ++it) {
+            const u64 x = reinterpret_cast<const u64*>(S.r)[lane + 32 * it];
+            cand = cand || (x == ((x << 8) | (x >> 56)) && 8 * (lane + 32 * it) + 8 <= Lr);
         }
         if (!__any_sync(SCCG_FULL_MASK, cand)) return 0;
     }
+    const int min_len = k > LM_RUN_MIN ? k : LM_RUN_MIN;
     int n_runs = 0;
     for (int it = 0; it < 8; ++it) {                                             // word q = 32 * it + lane: uniform trip count
         const int q = 32 * it + lane;
@@ -142,7 +143,7 @@ __device__ __forceinline__ int lm_runs(LmWarpSmem& S, int Lr, int k) {
                     int qq = q + 1;
                     while (4 * qq + 4 <= Lr && r32[qq] == x) ++qq;               // whole words of the run, then <= 3 symbols
                     b = 4 * qq; while (b < Lr && S.r[b] == sym) ++b;
-                    first = b - a >= k;
+                    first = b - a >= min_len;
                 }
             }
         }
@@ -309,12 +310,12 @@ __device__ __forceinline__ int lm_parse(LmWarpSmem& S, const u32 (&wm)[4], int L
                 u32 h = 0u;
                 bool one_sym = n_runs > 0;                                       // (only worth knowing when r has runs at all)
                 for (int x = 0; x < k; ++x) { const u8 cx = S.t[jj + x]; h = mad_u32(h, mul, cx); one_sym = one_sym && cx == S.t[jj]; }
-                if (one_sym) {                                                   // a run of one symbol: its occurrences are the listed runs of that symbol
+                if (one_sym) {                                                   // a run of one symbol occurs in every listed run of that symbol (and maybe in shorter ones: chain)
                     for (int i = 0; i < n_runs; ++i) hit = hit || S.r[S.mis[i]] == S.t[jj];
                 }
                 const u32 hm = lm_mix(h);
                 const u32 qt = lm_tag(hm), t4 = ld_unaligned32(S.t, jj);
-                for (u32 c = one_sym ? 0u : S.head[lm_bucket(hm)]; c && !hit;) {
+                for (u32 c = S.head[lm_bucket(hm)]; c && !hit;) {
                     const int p = (int)(c & 0x3ffu) - 1;
                     if ((c & 0xfc00u) == qt && ld_unaligned32(S.r, p) == t4 && kmer_equal_smem(S.r, p, S.t, jj, k)) hit = true;
                     c = S.next[p];
@@ -331,13 +332,14 @@ __device__ __forceinline__ int lm_parse(LmWarpSmem& S, const u32 (&wm)[4], int L
         const u32 qtag = lm_tag(hm);                                             // already positioned at bit 10
         const u32 tag = ld_unaligned32(S.t, j);
         LmFold f; f.best_l = 0; f.cnt = 0; f.zero_in = false; f.best_key = 0xffffffffu;
+        bool diag_folded = false;                                                // the diagonal candidate (p == j) has been folded: crowded buckets take it ahead of its turn
         if (n_runs > 0 && __all_sync(SCCG_FULL_MASK, lane >= k || S.t[j + lane] == S.t[j])) {
-            // the looked-up k-mer is a run of one symbol: candidates from the run list, nothing of the kind is in the chains
+            // the looked-up k-mer is a run of one symbol: its candidates inside the listed (long) runs of r come from the list, the
+            // chain below only holds those of shorter runs
             const u8 sym = S.t[j];
             lm_fold_runs(S, f, n_runs, sym, j, lm_run_len_t(S, sym, j, Lt), e, Lr, Lt);
-            c = 0u;
+            for (int i = 0; i < n_runs; ++i) diag_folded = diag_folded || (j >= (int)S.mis[i] && j + k <= (int)S.qv[i]);   // p == j is one of the listed candidates
         }
-        bool diag_folded = false;                                                // the diagonal candidate (p == j) has been folded: crowded buckets take it ahead of its turn
         while (c) {                                                              // :114 every candidate of the bucket
             // gather up to 32 chain entries whose first 4 symbols match (hash-chain false positives die here)
             int myp = -1, nb = 0;

@@ -237,6 +237,43 @@ def crowded_bucket_pair(r: random.Random) -> tuple[bytes, bytes]:
     return bytes(ref), bytes(tgt[:1000])
 
 
+def runs_of_one_symbol_pair(r: random.Random) -> tuple[bytes, bytes]:
+    """segment pairs around long runs of one symbol (N blocks, poly-A): runs at the start / end / inside of the reference, runs
+    that grow or shrink in the target, targets that begin inside a run, several runs of the same symbol -- the closed-form
+    candidate fold of lm_fold_runs next to the chains (runs shorter than 15 symbols stay there)"""
+    n = r.choice([1000, 1000, r.randint(30, 999)])
+    alpha = r.choice([b"ACGT", b"ACGT", b"AN", b"ACGTN"])
+    ref = bytearray(r.choice(alpha) for _ in range(n))
+    for _ in range(r.randint(1, 4)):
+        ln = r.randint(8, min(400, n)); at = r.choice([0, n - ln, r.randint(0, n - ln)])
+        ref[at:at + ln] = bytes([r.choice(b"NNA")]) * ln
+    tgt = bytearray(ref)
+    for _ in range(r.randint(0, 5)):
+        x = r.randrange(len(tgt)); tgt[x] = r.choice(b"ACGTN")
+    for _ in range(r.randint(0, 3)):
+        x = r.randrange(len(tgt)); d = r.randint(1, 30)
+        if r.random() < 0.5:
+            tgt[x:x] = bytes([tgt[x]]) * d
+        else:
+            del tgt[x:x + d]
+    if r.random() < 0.3:
+        tgt = tgt[r.randint(0, 50):]
+    if r.random() < 0.2:
+        tgt = bytearray(b"N" * r.randint(10, 60)) + tgt
+    return bytes(ref), bytes(tgt[:1000])
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_runs_of_one_symbol_vs_oracle(ctx, seed):
+    r = random.Random(repr(("runs", seed)))
+    for it in range(150):
+        ref, tgt = runs_of_one_symbol_pair(r)
+        for k in (14, 10):
+            exp = [(x.p, x.l, x.lit) for x in ol.orc_match_sequences(ref, tgt, k, 0, False, 0)]
+            got = [(x.p, x.l, x.lit) for x in ctx.match_sequences(ref, tgt, k, 0, False, 0)]
+            assert got == exp, (seed, it, k, ref, tgt)
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_crowded_buckets_vs_oracle(ctx, seed):
     """low-complexity segments: dozens to hundreds of candidates per looked-up k-mer, ties between them (the tie-break of

@@ -10,7 +10,7 @@ import pytest
 
 import oracle_lib as ol
 from cases import cases
-from test_emu_compress import _mutated_pair, check_compress_like_oracle, crowded_bucket_pair, diag_fuzz_pair, grammar_pair
+from test_emu_compress import _mutated_pair, check_compress_like_oracle, crowded_bucket_pair, diag_fuzz_pair, grammar_pair, runs_of_one_symbol_pair
 
 pytestmark = pytest.mark.gpu
 CASES = cases()
@@ -284,3 +284,26 @@ def test_compress_device_two_phase_matcher(ctx, two_phase, monkeypatch):
     for rep in range(2):
         ptr, n, gmode = ctx.compress_device(d_ref.data_ptr(), ref.size, d_tgt.data_ptr(), tgt.size, b">two phase")
         assert (gmode, ctx.download(ptr, n)) == (mode, exp)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_runs_of_one_symbol_vs_oracle(ctx, seed):
+    """long runs of one symbol in the reference (tests/test_emu_compress.runs_of_one_symbol_pair): function level, and whole files
+    of such segments through the device-resident entry point (two matcher launches forced)"""
+    import torch
+    r = random.Random(repr(("runs-gpu", seed)))
+    refs, tgts = [], []
+    for it in range(120):
+        ref, tgt = runs_of_one_symbol_pair(r)
+        if it < 40:
+            for k in (14, 10):
+                exp = [(x.p, x.l, x.lit) for x in ol.orc_match_sequences(ref, tgt, k, 0, False, 0)]
+                got = [(x.p, x.l, x.lit) for x in ctx.match_sequences(ref, tgt, k, 0, False, 0)]
+                assert got == exp, (seed, it, k, ref, tgt)
+        if len(ref) == 1000 and len(tgt) == 1000:
+            refs.append(ref); tgts.append(tgt)
+    ref, tgt = b"".join(refs), b"".join(tgts)
+    rc, exp, mode = ol.orc_compress(ref, tgt, b">runs")
+    assert rc == 0
+    got, gmode = ctx.compress(ref, tgt, b">runs")
+    assert (gmode, got) == (mode, exp)
