@@ -9,6 +9,9 @@ for shape in gap divergent; do
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_global_$shape.csv python tools/one_global.py $shape > $O/ncu_global_$shape.log 2>&1; echo "global $shape rc=$?"
 done
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_chr1.csv python tools/one_chr1.py 2 > $O/ncu_launch.log 2>&1; echo "launch list rc=$?"
+for k in seg_match_defer_k seg_match_queue_k; do
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:"$k" --launch-skip 1 -c 1 -o $O/full_$k python tools/one_chr1.py 2 > $O/ncu_full_$k.log 2>&1; echo "ncu $k rc=$?"
+done
 python - <<PY
 import json
 d=json.loads([l for l in open("$O/bench.json") if l.startswith("{")][-1])      # (NCCL may print its version banner first)
