@@ -72,21 +72,9 @@ sccg_ctx* sccg_create(int device) {
     if (c->sm_count <= 0) c->sm_count = 148;
     c->h_pinned_cap = 1 << 20;
     { const char* e = getenv("SCCG_NO_DIAG"); c->use_diag = (e && atoi(e) != 0) ? 0 : 1; }    // tests: force the generic segment parse
-    int prio_main = 0, prio_side = 0;
-#ifndef SCCG_EMU
-    {   // SCCG_STREAM_PRIO=main|side: that lane's CTAs are dispatched first when both lanes have kernels pending (experiment)
-        int lo = 0, hi = 0;
-        const char* e = getenv("SCCG_STREAM_PRIO");
-        if (e && cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess) { prio_main = prio_side = lo; if (!strcmp(e, "main")) prio_main = hi; else if (!strcmp(e, "side")) prio_side = hi; }
-    }
-    bool ok = cudaStreamCreateWithPriority(&c->main_stream, cudaStreamDefault, prio_main) == cudaSuccess &&
-              cudaStreamCreateWithPriority(&c->side_stream, cudaStreamDefault, prio_side) == cudaSuccess &&
-              cudaMallocHost(&c->h_pinned, c->h_pinned_cap) == cudaSuccess;
-#else
-    (void)prio_main; (void)prio_side;
+    // (stream priorities for either lane were measured: main first 0.343 -> 0.389 ms per chr1-sized pair, side first no change)
     bool ok = cudaStreamCreate(&c->main_stream) == cudaSuccess && cudaStreamCreate(&c->side_stream) == cudaSuccess &&
               cudaMallocHost(&c->h_pinned, c->h_pinned_cap) == cudaSuccess;
-#endif
     c->stream = c->main_stream;
     for (int i = 0; ok && i < 6; ++i) ok = cudaEventCreate(&c->ev_side[i]) == cudaSuccess;
     for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
