@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Development aid: device-resident compress / decompress times of local-mode pairs of several sizes (chr1-, chr8-, chr21-sized) with the
-library as built; environment overrides (SCCG_STREAM_PRIO, ...) apply.  usage: time_local.py [lib.so]"""
+library as built; environment overrides (SCCG_LM_TWO_PHASE_MIN, SCCG_LM_QUEUE_CTAS, ...) apply.  usage: time_local.py [lib.so]"""
 import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
